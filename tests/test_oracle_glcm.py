@@ -1,0 +1,55 @@
+"""GLCM oracle: scikit-image docstring known-answer example + self-consistency.
+(Parity for this stage is unpinned by the reference: see oracle/glcm.py.)"""
+import numpy as np
+
+from oracle import glcm as og
+
+DOC_IMAGE = np.array([[0, 0, 1, 1], [0, 0, 1, 1], [0, 2, 2, 2], [2, 2, 3, 3]], dtype=np.uint8)
+DOC_COUNTS = [
+    [[2, 2, 1, 0], [0, 2, 0, 0], [0, 0, 3, 1], [0, 0, 0, 1]],
+    [[1, 1, 3, 0], [0, 1, 1, 0], [0, 0, 0, 2], [0, 0, 0, 0]],
+    [[3, 0, 2, 0], [0, 2, 2, 0], [0, 0, 1, 2], [0, 0, 0, 0]],
+    [[2, 0, 0, 0], [1, 1, 2, 0], [0, 0, 2, 1], [0, 0, 0, 0]],
+]
+
+
+def test_docstring_example_numpy():
+    P = og.graycomatrix(DOC_IMAGE, (1,), og.DEFAULT_ANGLES, levels=4)
+    for a in range(4):
+        assert P[:, :, 0, a].tolist() == DOC_COUNTS[a]
+
+
+def test_docstring_example_c():
+    cnt = og.counts_map_c(DOC_IMAGE, 4, 4, 4)
+    assert cnt.shape == (1, 1, 4, 4, 4)
+    for a in range(4):
+        assert cnt[0, 0, a].tolist() == DOC_COUNTS[a]
+
+
+def test_offsets():
+    assert [(dr, dc) for _, _, dr, dc in og.offsets_for()] == [(0, 1), (1, 1), (1, 0), (1, -1)]
+
+
+def test_c_matches_numpy_props():
+    rng = np.random.default_rng(0)
+    base = rng.integers(0, 32, size=(8, 10)).repeat(5, 0).repeat(5, 1)
+    q = np.clip(base + rng.integers(-2, 3, size=base.shape), 0, 31).astype(np.uint8)
+    for win, step, L in ((7, 1, 32), (21, 21, 32), (5, 3, 16), (11, 4, 64)):
+        qq = (q.astype(np.int32) * L // 32).astype(np.uint8)
+        a = og.props_map_numpy(qq[:30, :34], L, win, step)
+        b = og.props_map_c(qq[:30, :34], L, win, step)
+        assert a.shape == b.shape
+        assert np.allclose(a, b, rtol=2e-6, atol=1e-7)
+
+
+def test_constant_window_correlation_is_one():
+    q = np.full((9, 9), 3, np.uint8)
+    m = og.props_map_numpy(q, 8, 7, 1)
+    assert np.all(m[4] == 1.0) and np.all(m[0] == 0.0) and np.all(m[3] == 1.0)
+    assert np.array_equal(m, og.props_map_c(q, 8, 7, 1))
+
+
+def test_pair_counts_per_angle():
+    q = np.zeros((7, 7), np.uint8)
+    cnt = og.counts_map_c(q, 4, 7, 1)[0, 0]
+    assert [int(cnt[a].sum()) for a in range(4)] == [42, 36, 42, 36]
