@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: feature stack (indices + PCA + dense GLCM) + KMeans, Mpixel/s.
+
+  python bench.py --gpus N --steps K --warmup W            rsx (this repo), one process per GPU under torchrun
+  python bench.py --impl reference ...                     the reference CPU path (oracle port) on the host cores
+
+Workload (BASELINE.json configs[1]): synthetic Landsat TM scene 7000x7000x7 uint8 per GPU (row strips of a
+7000*N x 7000 mosaic: weak scaling), GLCM 7x7 dense at 32 grey levels, stack-13, KMeans k=8, 20 Lloyd iterations
++ sklearn's final assignment pass.  One step = the whole path over the whole raster.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# algorithmic bytes per pixel
+def algorithmic_bytes(B, e, D, T, n_comp, glcm=True):
+    hist = B * e
+    indices = B * e + 7 * 4
+    pca = 2 * B * e + 4 * n_comp
+    g = 21 if glcm else 0
+    km = T * 4 * D + 4
+    return dict(hist=hist, indices=indices, pca=pca, glcm=g, kmeans=km, total=hist + indices + pca + g + km)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx),
+                 "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
+                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+                for n, v in zip(names, f[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------- reference (CPU) arm
+def cpu_reference_sample(raster_crop: np.ndarray, glcm_crop: np.ndarray, cfg, K, T, seed):
+    """The reference path (oracle port: numpy / sklearn as the reference calls them + the plain-C GLCM restatement)
+    on a bounded sample.  Returns per-pixel seconds per stage and the threads used."""
+    from oracle import features as of
+    from oracle import glcm as og
+    from oracle import kmeans as ok
+    h, w, B = raster_crop.shape
+    n = h * w
+    t = {}
+    t0 = time.perf_counter()
+    bands = [raster_crop[:, :, b].astype(np.float32) for b in range(B)]
+    nb = [of.robust_normalize(b) for b in bands]
+    ix = of.all_indices(nb)
+    t["normalize+indices"] = (time.perf_counter() - t0) / n
+    t0 = time.perf_counter()
+    pcs, _, _ = of.perform_pca(nb)
+    t["pca"] = (time.perf_counter() - t0) / n
+    # dense GLCM on a smaller crop (the reference's Python window loop would take ~0.85 ms per window)
+    gh, gw = glcm_crop.shape
+    t0 = time.perf_counter()
+    gmaps = og.glcm_features(glcm_crop, cfg.glcm_levels, cfg.glcm_window, cfg.glcm_step)
+    t["glcm"] = (time.perf_counter() - t0) / (gh * gw)
+    # KMeans on a 13-plane stack of the crop (GLCM planes replaced by resized copies so the stack has full depth)
+    import cv2
+    stack = [ix[k] for k in of.INDEX_ORDER] + [cv2.resize(gmaps[k], (w, h)) for k in og.PROPS] + [pcs[0]]
+    X = np.stack([s.ravel() for s in stack], axis=1).astype(np.float64)
+    t0 = time.perf_counter()
+    Xs = ok.minmax_scale(X)
+    rng = np.random.default_rng(seed)
+    c0 = Xs[rng.choice(n, K, replace=False)]
+    ok.lloyd_fixed(Xs, c0, T)
+    t["kmeans"] = (time.perf_counter() - t0) / n
+    return t
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path on the host cores, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from rs_image_segmentation_b200.pipeline import FeatureConfig
+    from rs_image_segmentation_b200.synth import synth_raster_numpy
+    cfg = FeatureConfig(glcm_window=7, glcm_step=1, glcm_levels=32)
+    S, G = args.cpu_sample, args.cpu_glcm_sample
+    raster = synth_raster_numpy(S, S, 7, np.uint8, seed=7000)
+    from oracle import features as of
+    nir = of.robust_normalize(raster[:G, :G, 3].astype(np.float32))
+    cores = os.cpu_count()
+    times = []
+    for i in range(args.warmup + args.steps):
+        t = cpu_reference_sample(raster, nir, cfg, args.k, args.iters, 7000)
+        if i >= args.warmup:
+            times.append(sum(t.values()))
+    per_px = float(np.mean(times))
+    value = 1e-6 / per_px
+    H = W = args.size
+    sample = (f"indices+PCA+KMeans(k={args.k},{args.iters} it) on a {S}x{S}x7 crop, dense 7x7/32-level GLCM on a {G}x{G} crop; "
+              f"per-pixel stage times summed; numpy/sklearn default threading + OpenMP C GLCM")
+    line = {
+        "impl": "reference", "metric": "feature-stack+KMeans throughput", "value": value, "unit": "Mpixel/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_px * H * W * args.gpus * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, H, W),
+        "cpu_baseline": {"value": value, "unit": "Mpixel/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args, H, W):
+    return {"workload": f"synthetic Landsat TM scene {H}x{W}x7 uint8 per GPU (row strips of a {H * args.gpus}x{W} mosaic), "
+                        f"indices + PCA(7) + dense GLCM 7x7 @32 levels + KMeans k={args.k}, {args.iters} iterations + final assignment, stack-13",
+            "l2": "inputs larger than L2 (raster 343 MB, stack 2.5 GB per GPU)", "per_gpu_pixels": H * W}
+
+
+# ------------------------------------------------------------------------------------------- rsx arm
+def run_rsx(args):
+    import torch
+    import torch.distributed as dist
+
+    from rs_image_segmentation_b200 import _lib
+    from rs_image_segmentation_b200 import pipeline as P
+    from rs_image_segmentation_b200.device import StageTimer
+    from rs_image_segmentation_b200.dist import Comm, strip_bounds
+    from rs_image_segmentation_b200.synth import synth_strip_torch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    comm = Comm()
+    H = W = args.size
+    H_total = H * world
+    bounds = strip_bounds(H_total, world)
+    own = bounds[rank]
+    cfg = P.FeatureConfig(glcm_window=7, glcm_step=1, glcm_levels=32)
+    D, K, T = 13, args.k, args.iters
+
+    raster = synth_strip_torch(H_total, W, 7, own[0], own[1] - own[0], "uint8", seed=7000, device="cuda")
+    torch.cuda.synchronize()
+    timer = StageTimer(enabled=True)
+
+    def step(t):
+        fr = P.extract_features(raster, cfg, comm, H_total, bounds, t)
+        res, km, c0 = P.kmeans_on_features(fr, D, K, T, 7000, comm, H_total, own[0], True, t)
+        return fr, res
+
+    def timed(fn, steps):
+        comm.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = None
+        for _ in range(steps):
+            out = fn()
+        b.record()
+        torch.cuda.synchronize()
+        comm.barrier()
+        ms = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device="cuda")
+        comm.all_reduce(ms, "max")
+        return float(ms.item()), out
+
+    for _ in range(args.warmup):
+        step(StageTimer(enabled=False))
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    timer.reset()
+    ms_total, (fr, res) = timed(lambda: step(timer), args.steps)
+    launches = _lib.launch_count() - launches0
+    stage = timer.totals_ms()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = ms_total / args.steps
+    n_global = H_total * W
+    value = n_global / (ms_per_step * 1e-3) / 1e6
+
+    # ---- end to end through the host-buffer API: H2D of the strip + D2H of the labels inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        del fr, res
+        pinned = raster.cpu().pin_memory()
+        torch.cuda.synchronize()
+
+        def e2e_step():
+            return P.segment_raster(None, cfg, K, T, 7000, D, comm, H_total, bounds, pinned=pinned)
+
+        for _ in range(min(args.warmup, 2)):
+            e2e_step()
+        e2e_steps = max(1, min(args.steps, 3))
+        ms_e2e, _ = timed(e2e_step, e2e_steps)
+        ms_e2e /= e2e_steps
+        e2e = {"value": n_global / (ms_e2e * 1e-3) / 1e6, "unit": "Mpixel/s", "h2d_bytes_per_step": int(pinned.numel()) * world,
+               "d2h_bytes_per_step": int(H * W * 4) * world, "ms_per_step": ms_e2e}
+
+    if rank != 0:
+        return 0
+    peak, peak_src = peaks()
+    ab = algorithmic_bytes(7, 1, D, T, 7)
+    n_local = H * W
+    km_ms, km_n = stage.get("kmeans_assign", (0.0, 0))
+    km_avg_ms = km_ms / max(km_n, 1)
+    km_bytes = n_local * 4 * D
+    achieved = km_bytes / (km_avg_ms * 1e-3) / 1e9 if km_avg_ms > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "kmeans_assign_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    whole = ab["total"] * n_local / (ms_per_step * 1e-3) / 1e9
+    line = {
+        "metric": "feature-stack+KMeans throughput", "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(args, H, W),
+        "roofline": {"bound": "hbm", "kernel": "km_assign_kernel<13,update> (20 of the 21 KMeans passes)", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": km_bytes, "avg_launch_ms": km_avg_ms, "launches_timed": km_n,
+                     "share_of_step": km_ms / args.steps / ms_per_step if ms_per_step else None},
+        "whole_path": {"algorithmic_bytes_per_pixel": ab["total"], "achieved_gbs_per_gpu": whole, "frac_of_peak": whole / peak,
+                       "stage_ms_per_step": {k: v[0] / args.steps for k, v in stage.items()},
+                       "stage_launches_per_step": {k: v[1] / args.steps for k, v in stage.items()}},
+        "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e,
+    }
+    if world == 1 and not args.no_cpu:
+        from oracle import features as of
+        S, G = args.cpu_sample, args.cpu_glcm_sample
+        crop = raster[:S, :S].cpu().numpy()
+        nir = of.robust_normalize(crop[:G, :G, 3].astype(np.float32))
+        t = cpu_reference_sample(crop, nir, cfg, K, T, 7000)
+        per_px = sum(t.values())
+        line["cpu_baseline"] = {
+            "value": 1e-6 / per_px, "unit": "Mpixel/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"indices+PCA+KMeans on a {S}x{S} crop, dense GLCM (C/OpenMP restatement) on a {G}x{G} crop, per-pixel times summed",
+            "stage_us_per_pixel": {k: v * 1e6 for k, v in t.items()}}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="rsx", choices=["rsx", "reference"])
+    ap.add_argument("--size", type=int, default=7000, help="rows = cols of the per-GPU scene")
+    ap.add_argument("--k", type=int, default=8)
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--cpu-sample", type=int, default=1024)
+    ap.add_argument("--cpu-glcm-sample", type=int, default=768)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_rsx(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,181 @@
+/* rsx - C ABI of the B200-native feature-stack + KMeans hot path.
+ *
+ * The reference (beilsme/rs-image-segmentation) is pure Python and has no FFI; the
+ * boundary it offers is the set of module-level functions of
+ * modules/features/indices.py and modules/features/extract.py.  This header is what a
+ * ctypes binding for those functions links against; each entry
+ * point names the reference lines whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - every pointer named d_* is DEVICE memory owned by the caller (the Python shim passes
+ *     torch tensor data pointers); h_* is host memory; nothing is allocated behind the
+ *     caller's back except where stated.
+ *   - `stream` is a cudaStream_t passed as void*; all work is asynchronous on it and no call
+ *     synchronises the device.
+ *   - return value 0 = ok; otherwise an RSX_ERR_* code and rsx_last_error() describes it
+ *     (thread-local string).
+ *   - rasters are PIXEL-INTERLEAVED ("BIP"): sample (pixel p, band b) at d_raster[p*B + b].
+ *   - feature maps are PLANAR float32: plane k starts at d_out + k*plane_stride (elements).
+ *   - min/max trackers are uint32 pairs holding order-preserving encodings of float32
+ *     (rsx_minmax_init / rsx_minmax_decode); they are updated with atomics so that several
+ *     producers and several GPUs' strips can share one tracker.
+ */
+#ifndef RSX_H
+#define RSX_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RSX_OK 0
+#define RSX_ERR_ARG 1      /* bad argument / unsupported configuration */
+#define RSX_ERR_CUDA 2     /* a CUDA runtime call or kernel launch failed */
+#define RSX_ERR_UNSUPPORTED 3
+
+#define RSX_MAX_BANDS 16
+#define RSX_MAX_FEATURES 32
+#define RSX_MAX_CLUSTERS 64
+#define RSX_NUM_INDICES 7  /* ndvi, evi, msavi, ndwi, mndwi, ndbi, bsi (scripts/2_feature_extraction.py:63-73) */
+#define RSX_NUM_GLCM_PROPS 5 /* contrast, dissimilarity, homogeneity, energy, correlation (indices.py:292-296) */
+
+typedef void* rsx_stream_t;
+
+const char* rsx_last_error(void);
+int rsx_abi_version(void);
+/* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
+int64_t rsx_launch_count(void);
+
+/* ---- K1: per-band histograms -------------------------------------------------------------
+ * Replaces the sorts inside np.percentile (indices.py:38-39) and RobustScaler's
+ * nanmedian/nanpercentile (sklearn/preprocessing/_data.py:1722,1738-1743): for integer-valued
+ * rasters every order statistic is derivable exactly from the histogram.
+ * d_hist: uint32 [B][256] (u8) or [B][65536] (u16); ACCUMULATED into (caller zeroes). */
+int rsx_hist_u8(const uint8_t* d_raster, int64_t n_px, int n_bands, uint32_t* d_hist, rsx_stream_t stream);
+int rsx_hist_u16(const uint16_t* d_raster, int64_t n_px, int n_bands, uint32_t* d_hist, rsx_stream_t stream);
+
+/* ---- K2: fused normalise + spectral indices (+ GLCM quantisation) ---------------------------
+ * Replaces robust_normalize x B (indices.py:25-48 via scripts/2...:43-47) and the seven index
+ * functions (indices.py:50-203) in one pass over the raster.
+ * h_norm:      float [B][3] = lo, hi, fl32(fl32(hi-lo)+1e-10f) per band
+ * band_map:    raster band numbers of blue, green, red, nir, swir1
+ * d_indices:   7 planes in RSX index order; plane_stride >= n_px
+ * d_minmax:    uint32 [7][2] tracker or NULL
+ * d_quant:     uint8 [n_px] or NULL: (robust_normalize(nir_norm) * (levels-1)).astype(uint8)
+ *              (indices.py:265-268); h_qnorm = lo, hi, den of that second normalisation.
+ * evi:         L, C1, C2, G of calculate_evi (indices.py:73) */
+int rsx_indices_fused_u8(const uint8_t* d_raster, int64_t n_px, int n_bands, const int* band_map, const float* h_norm,
+                         const float* evi, float* d_indices, int64_t plane_stride, uint32_t* d_minmax, uint8_t* d_quant,
+                         const float* h_qnorm, int levels, rsx_stream_t stream);
+int rsx_indices_fused_u16(const uint16_t* d_raster, int64_t n_px, int n_bands, const int* band_map, const float* h_norm,
+                          const float* evi, float* d_indices, int64_t plane_stride, uint32_t* d_minmax, uint8_t* d_quant,
+                          const float* h_qnorm, int levels, rsx_stream_t stream);
+
+/* ---- planar float32 element-wise entry points (the per-function drop-ins) ------------------ */
+/* robust_normalize given lo/hi (indices.py:42-46) */
+int rsx_normalize_f32(const float* d_in, int64_t n, float lo, float hi, float den, float* d_out, rsx_stream_t stream);
+/* (a-b)/(a+b) masked at a+b>0.001, clipped: ndvi/ndwi/mndwi/ndbi (indices.py:50-71,116-179) */
+int rsx_index_ratio_f32(const float* d_a, const float* d_b, int64_t n, float* d_out, rsx_stream_t stream);
+int rsx_index_evi_f32(const float* d_nir, const float* d_red, const float* d_blue, int64_t n, float L, float C1, float C2,
+                      float G, float* d_out, rsx_stream_t stream); /* indices.py:73-95 */
+int rsx_index_msavi_f32(const float* d_nir, const float* d_red, int64_t n, float* d_out, rsx_stream_t stream); /* :97-114 */
+int rsx_index_bsi_f32(const float* d_blue, const float* d_red, const float* d_nir, const float* d_swir, int64_t n,
+                      float* d_out, rsx_stream_t stream); /* :181-203 */
+/* quantise a float32 band: (norm(x) * (levels-1)).astype(uint8) (indices.py:265-268) */
+int rsx_quantize_f32(const float* d_in, int64_t n, float lo, float hi, float den, int levels, uint8_t* d_q, rsx_stream_t stream);
+
+/* ---- K3: PCA -----------------------------------------------------------------------------------
+ * Replaces perform_pca (indices.py:205-246): X = RobustScaler(normalised bands) in float32, with the
+ * division by the float64 scale_ evaluated in double and rounded (sklearn/preprocessing/_data.py:
+ * 1738-1743,1782-1784); Gram matrix X^T X and column sums (sklearn/decomposition/_pca.py:587-613)
+ * accumulated in float64 with warp-shuffle tree reductions and a fixed-order final sum; then the
+ * projection X @ components^T - mean @ components^T (sklearn/decomposition/_base.py:151-159).
+ * uint8:  d_lut float [B][256] (DEVICE) tabulates X for every grey level of every band.
+ * uint16: h_norm float [B][3] as in K2; h_center float [B] (median), h_scale double [B] (IQR, 0 -> 1).
+ * d_moments: double [B + B*(B+1)/2]: sums then upper-triangular cross sums, row-major (a<=b);
+ *            ACCUMULATED into (caller zeroes); a multi-GPU caller all-reduces it.
+ * d_scratch: double [rsx_pca_scratch_elems(B)] */
+int64_t rsx_pca_scratch_elems(int n_bands);
+int rsx_pca_moments_u8(const uint8_t* d_raster, int64_t n_px, int n_bands, const float* d_lut, double* d_moments,
+                       double* d_scratch, rsx_stream_t stream);
+int rsx_pca_moments_u16(const uint16_t* d_raster, int64_t n_px, int n_bands, const float* h_norm, const float* h_center,
+                        const double* h_scale, double* d_moments, double* d_scratch, rsx_stream_t stream);
+/* h_components: float [n_comp][B]; h_mean_proj: float [n_comp] = mean_ @ components^T */
+int rsx_pca_project_u8(const uint8_t* d_raster, int64_t n_px, int n_bands, const float* d_lut, const float* h_components,
+                       const float* h_mean_proj, int n_comp, float* d_out, int64_t plane_stride, uint32_t* d_minmax,
+                       rsx_stream_t stream);
+int rsx_pca_project_u16(const uint16_t* d_raster, int64_t n_px, int n_bands, const float* h_norm, const float* h_center,
+                        const double* h_scale, const float* h_components, const float* h_mean_proj, int n_comp, float* d_out,
+                        int64_t plane_stride, uint32_t* d_minmax, rsx_stream_t stream);
+
+/* ---- K4: GLCM texture --------------------------------------------------------------------------
+ * Replaces the window double loop of calculate_glcm_features (indices.py:283-305): for every
+ * window anchored at (i*step, j*step), distance 1, angles 0/45/90/135 deg, symmetric, normed;
+ * the five graycoprops averaged over the four angles, stored float32.
+ * d_q:      uint8 [rows_avail][W] quantised band; rows_avail >= (out_rows-1)*step + window
+ *           (a strip plus its halo rows; the windows of output row r start at row r*step).
+ * d_props:  5 planes [out_rows][out_cols], plane stride in elements. */
+int rsx_glcm_props(const uint8_t* d_q, int rows_avail, int W, int levels, int window, int step, int out_rows, int out_cols,
+                   float* d_props, int64_t plane_stride, rsx_stream_t stream);
+/* Directed (un-symmetrised) uint32 co-occurrence counts, [n_win][4][levels][levels], for the
+ * windows whose top-left corners are listed in d_anchors (int32 [n_win][2] = row, col):
+ * skimage graycomatrix(symmetric=False, normed=False) of each window.  Validation entry point. */
+int rsx_glcm_counts(const uint8_t* d_q, int H, int W, int levels, int window, const int32_t* d_anchors, int n_win,
+                    uint32_t* d_counts, rsx_stream_t stream);
+/* cv2.resize(src, (dst_w, dst_h), INTER_LINEAR) on n_planes float32 planes (indices.py:308).
+ * For row-strip sharding: src rows [src_row0, src_row0+src_rows_avail) of a src_h_total-row
+ * image are present; dst rows [dst_row0, dst_row0+dst_rows) of a dst_h_total-row image are made. */
+int rsx_resize_bilinear_f32(const float* d_src, int src_h_total, int src_w, int src_row0, int src_rows_avail,
+                            int64_t src_plane_stride, float* d_dst, int dst_h_total, int dst_w, int dst_row0, int dst_rows,
+                            int64_t dst_plane_stride, int n_planes, uint32_t* d_minmax, rsx_stream_t stream);
+
+/* ---- min/max trackers (MinMaxScaler.fit, sklearn/preprocessing/_data.py:527-541) --------------- */
+int rsx_minmax_init(uint32_t* d_minmax, int n, rsx_stream_t stream);
+int rsx_minmax_planes_f32(const float* d_planes, int64_t n_px, int64_t plane_stride, int n_planes, uint32_t* d_minmax,
+                          rsx_stream_t stream);
+void rsx_minmax_decode(const uint32_t* h_minmax, int n, float* h_min, float* h_max);
+void rsx_minmax_encode(const float* h_min, const float* h_max, int n, uint32_t* h_minmax);
+/* NaN -> 0 in place (extract.py:548-556) */
+int rsx_nan_to_zero_f32(float* d_planes, int64_t n, rsx_stream_t stream);
+
+/* ---- K5: KMeans -------------------------------------------------------------------------------
+ * Replaces MinMaxScaler.transform + the Lloyd iteration of sklearn KMeans as driven by
+ * unsupervised_kmeans_classification (extract.py:568-577; sklearn/cluster/_k_means_lloyd.pyx:
+ * 168-218, _k_means_common.pyx:274-311, _kmeans.py:1488-1493 for the centring).
+ *
+ * rsx_kmeans_state is a small DEVICE block owned by the caller, rsx_kmeans_state_bytes() long.
+ *   rsx_kmeans_setup     fills it: per-feature MinMax scale/min, data mean (centring), the
+ *                        fixed-point shifts for the exact int64 partial sums, the initial
+ *                        centroids (scaled, un-centred coordinates, double [K][D]).
+ *   rsx_kmeans_assign    ONE pass over the stack: argmin over centroids (fp32 fast path with a
+ *                        float64 re-evaluation of near ties, first minimum wins), and, fused,
+ *                        per-cluster int64 fixed-point sums + counts (update!=0), labels
+ *                        (d_labels_u8 / d_labels_i32, each may be NULL), inertia (d_inertia!=NULL).
+ *   rsx_kmeans_update    centroids <- sums/counts (multiply by 1/count), centre shift, empty-
+ *                        cluster flag; zeroes the accumulators for the next pass.
+ * d_acc: int64 [K*(D+1)] = sums [K][D] then counts [K]; a multi-GPU caller all-reduces it
+ * between assign and update (integer adds: bit-identical for any partition of the pixels). */
+int64_t rsx_kmeans_state_bytes(void);
+/* h_feat_min/max: per-feature min/max of the raw stack (MinMaxScaler.fit); h_mean_scaled: per-feature
+ * mean of the scaled stack (the centring of _kmeans.py:1488-1490 - any value gives the same labels in
+ * exact arithmetic, it only sets the origin the fp32 fast path works around);
+ * h_init_centroids: double [K][D], MinMax-scaled, un-centred coordinates.
+ * Not re-entrant: the state is mirrored in one __constant__ block per process. */
+int rsx_kmeans_setup(void* d_state, int D, int K, const double* h_feat_min, const double* h_feat_max,
+                     const double* h_mean_scaled, const double* h_init_centroids, int64_t n_px_global, rsx_stream_t stream);
+/* d_acc: int64 [K*D + K + 1] = sums [K][D], counts [K], near-tie counter [1]; caller zeroes it once.
+ * row_len: length (pixels) of an image row; only steers the traversal order (threads walk down columns
+ * so that runs of equal labels stay in registers); any value gives the same result. */
+int rsx_kmeans_assign(const float* d_stack, int64_t plane_stride, int64_t n_px, int row_len, const void* d_state,
+                      int64_t* d_acc, uint8_t* d_labels_u8, int32_t* d_labels_i32, double* d_inertia, int update, int D,
+                      int K, rsx_stream_t stream);
+int rsx_kmeans_update(void* d_state, int64_t* d_acc, rsx_stream_t stream);
+/* SYNCHRONISES the stream; centroids come back in scaled, un-centred coordinates, double [K][D];
+ * h_shift_sq = squared centre shift of the last update; h_empty = empty clusters met so far. */
+int rsx_kmeans_read(const void* d_state, double* h_centroids, double* h_shift_sq, int32_t* h_empty, rsx_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSX_H */

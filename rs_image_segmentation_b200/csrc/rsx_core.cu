@@ -1,0 +1,227 @@
+// Error handling, launch accounting, min/max trackers and the planar float32 element-wise
+// entry points (per-function drop-ins for modules/features/indices.py).
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "rsx_common.cuh"
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+void rsx_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int rsx_check_launch(const char* what) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        rsx_set_error("%s: %s", what, cudaGetErrorString(e));
+        return RSX_ERR_CUDA;
+    }
+    return RSX_OK;
+}
+
+int rsx_num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = RSX_SM_COUNT_FALLBACK;
+    }
+    return n;
+}
+
+extern "C" const char* rsx_last_error(void) { return g_err; }
+extern "C" int rsx_abi_version(void) { return 1; }
+extern "C" int64_t rsx_launch_count(void) { return g_launches.load(); }
+
+// ----------------------------------------------------------------------------- min/max trackers
+__global__ void minmax_init_kernel(uint32_t* mm, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        mm[2 * i] = 0xffffffffu;  // ordered +inf side
+        mm[2 * i + 1] = 0u;
+    }
+}
+
+extern "C" int rsx_minmax_init(uint32_t* d_minmax, int n, rsx_stream_t stream) {
+    RSX_REQUIRE(d_minmax && n > 0, "rsx_minmax_init: bad arguments");
+    minmax_init_kernel<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(d_minmax, n);
+    return rsx_check_launch("minmax_init");
+}
+
+static inline unsigned h_f2ord(float f) {
+    unsigned u;
+    memcpy(&u, &f, 4);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+static inline float h_ord2f(unsigned u) {
+    unsigned v = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+    float f;
+    memcpy(&f, &v, 4);
+    return f;
+}
+extern "C" void rsx_minmax_decode(const uint32_t* h, int n, float* h_min, float* h_max) {
+    for (int i = 0; i < n; ++i) {
+        h_min[i] = h_ord2f(h[2 * i]);
+        h_max[i] = h_ord2f(h[2 * i + 1]);
+    }
+}
+extern "C" void rsx_minmax_encode(const float* h_min, const float* h_max, int n, uint32_t* h) {
+    for (int i = 0; i < n; ++i) {
+        h[2 * i] = h_f2ord(h_min[i]);
+        h[2 * i + 1] = h_f2ord(h_max[i]);
+    }
+}
+
+// grid.y = plane; NaNs are ignored by fminf/fmaxf, matching the NaN->0 replacement being done first
+__global__ void __launch_bounds__(256) minmax_planes_kernel(const float* __restrict__ p, int64_t n, int64_t stride, uint32_t* mm) {
+    const float* base = p + (int64_t)blockIdx.y * stride;
+    float mn = INFINITY, mx = -INFINITY;
+    int64_t n4 = n >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 v = ldg_stream4(base + 4 * i);
+        mn = fminf(fminf(mn, fminf(v.x, v.y)), fminf(v.z, v.w));
+        mx = fmaxf(fmaxf(mx, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        float v = base[(n4 << 2) + threadIdx.x];
+        mn = fminf(mn, v);
+        mx = fmaxf(mx, v);
+    }
+    warp_minmax_commit(mn, mx, mm + 2 * blockIdx.y);
+}
+
+extern "C" int rsx_minmax_planes_f32(const float* d_planes, int64_t n_px, int64_t plane_stride, int n_planes, uint32_t* d_minmax,
+                                     rsx_stream_t stream) {
+    RSX_REQUIRE(d_planes && d_minmax && n_px > 0 && n_planes > 0, "rsx_minmax_planes_f32: bad arguments");
+    RSX_REQUIRE(((uintptr_t)d_planes & 15) == 0 && (plane_stride & 3) == 0, "rsx_minmax_planes_f32: planes must be 16-byte aligned");
+    int gx = (int)min((int64_t)rsx_num_sms() * 4 / n_planes + 1, ceil_div(n_px, (int64_t)1024));
+    minmax_planes_kernel<<<dim3(gx, n_planes), 256, 0, (cudaStream_t)stream>>>(d_planes, n_px, plane_stride, d_minmax);
+    return rsx_check_launch("minmax_planes");
+}
+
+__global__ void __launch_bounds__(256) nan_to_zero_kernel(float* p, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float v = p[i];
+        if (v != v) p[i] = 0.f;
+    }
+}
+extern "C" int rsx_nan_to_zero_f32(float* d, int64_t n, rsx_stream_t stream) {
+    RSX_REQUIRE(d && n > 0, "rsx_nan_to_zero_f32: bad arguments");
+    nan_to_zero_kernel<<<(int)min((int64_t)rsx_num_sms() * 8, ceil_div(n, (int64_t)256)), 256, 0, (cudaStream_t)stream>>>(d, n);
+    return rsx_check_launch("nan_to_zero");
+}
+
+// ----------------------------------------------------------------------------- planar element-wise ops
+// One functor per reference function; the driver handles vectorised body + scalar tail.
+struct OpNormalize {
+    NormParam p;
+    __device__ float operator()(float x, float, float, float) const { return norm_apply(x, p); }
+};
+// indices.py:62-69 and its three siblings: num = a-b, den = a+b
+struct OpRatio {
+    __device__ float operator()(float a, float b, float, float) const {
+        float den = f_add(a, b);
+        float r = den > 0.001f ? f_div(f_sub(a, b), den) : 0.f;
+        return f_clip(r, -1.f, 1.f);
+    }
+};
+// indices.py:86-93: den = nir + C1*red - C2*blue + L ; G*(nir-red)/den
+struct OpEvi {
+    float L, C1, C2, G;
+    __device__ float operator()(float nir, float red, float blue, float) const {
+        float den = f_add(f_sub(f_add(nir, f_mul(C1, red)), f_mul(C2, blue)), L);
+        float r = den > 0.001f ? f_div(f_mul(G, f_sub(nir, red)), den) : 0.f;
+        return f_clip(r, -1.f, 1.f);
+    }
+};
+// indices.py:109: (2n+1 - sqrt((2n+1)^2 - 8(n-r)))/2 ; NaN propagates through the clip like np.clip
+struct OpMsavi {
+    __device__ float operator()(float nir, float red, float, float) const {
+        float t = f_add(f_mul(2.f, nir), 1.f);
+        float rad = f_sub(f_mul(t, t), f_mul(8.f, f_sub(nir, red)));
+        float v = f_div(f_sub(t, f_sqrt(rad)), 2.f);
+        return v != v ? v : f_clip(v, -1.f, 1.f);
+    }
+};
+// indices.py:194-201
+struct OpBsi {
+    __device__ float operator()(float blue, float red, float nir, float swir) const {
+        float a = f_add(swir, red), b = f_add(nir, blue);
+        float den = f_add(a, b);
+        float r = den > 0.001f ? f_div(f_sub(a, b), den) : 0.f;
+        return f_clip(r, -1.f, 1.f);
+    }
+};
+
+template <int NIN, typename Op>
+__global__ void __launch_bounds__(256) planar_op_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
+                                                        const float* __restrict__ d, float* __restrict__ out, int64_t n, Op op) {
+    int64_t n4 = n >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 va = ldg_stream4(a + 4 * i), vb = va, vc = va, vd = va;
+        if (NIN > 1) vb = ldg_stream4(b + 4 * i);
+        if (NIN > 2) vc = ldg_stream4(c + 4 * i);
+        if (NIN > 3) vd = ldg_stream4(d + 4 * i);
+        float4 r;
+        r.x = op(va.x, vb.x, vc.x, vd.x);
+        r.y = op(va.y, vb.y, vc.y, vd.y);
+        r.z = op(va.z, vb.z, vc.z, vd.z);
+        r.w = op(va.w, vb.w, vc.w, vd.w);
+        stg_stream4(out + 4 * i, r);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        int64_t i = (n4 << 2) + threadIdx.x;
+        out[i] = op(a[i], NIN > 1 ? b[i] : 0.f, NIN > 2 ? c[i] : 0.f, NIN > 3 ? d[i] : 0.f);
+    }
+}
+
+template <int NIN, typename Op>
+static int launch_planar(const char* name, const float* a, const float* b, const float* c, const float* d, float* out, int64_t n, Op op,
+                         rsx_stream_t stream) {
+    RSX_REQUIRE(a && out && n > 0, "%s: bad arguments", name);
+    RSX_REQUIRE((((uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)d | (uintptr_t)out) & 15) == 0, "%s: buffers must be 16-byte aligned", name);
+    int grid = (int)min((int64_t)rsx_num_sms() * 8, ceil_div(n, (int64_t)1024));
+    planar_op_kernel<NIN, Op><<<grid, 256, 0, (cudaStream_t)stream>>>(a, b, c, d, out, n, op);
+    return rsx_check_launch(name);
+}
+
+extern "C" int rsx_normalize_f32(const float* d_in, int64_t n, float lo, float hi, float den, float* d_out, rsx_stream_t stream) {
+    OpNormalize op{{lo, hi, den}};
+    return launch_planar<1>("rsx_normalize_f32", d_in, nullptr, nullptr, nullptr, d_out, n, op, stream);
+}
+extern "C" int rsx_index_ratio_f32(const float* d_a, const float* d_b, int64_t n, float* d_out, rsx_stream_t stream) {
+    RSX_REQUIRE(d_b, "rsx_index_ratio_f32: bad arguments");
+    return launch_planar<2>("rsx_index_ratio_f32", d_a, d_b, nullptr, nullptr, d_out, n, OpRatio{}, stream);
+}
+extern "C" int rsx_index_evi_f32(const float* d_nir, const float* d_red, const float* d_blue, int64_t n, float L, float C1, float C2, float G,
+                                 float* d_out, rsx_stream_t stream) {
+    RSX_REQUIRE(d_red && d_blue, "rsx_index_evi_f32: bad arguments");
+    return launch_planar<3>("rsx_index_evi_f32", d_nir, d_red, d_blue, nullptr, d_out, n, OpEvi{L, C1, C2, G}, stream);
+}
+extern "C" int rsx_index_msavi_f32(const float* d_nir, const float* d_red, int64_t n, float* d_out, rsx_stream_t stream) {
+    RSX_REQUIRE(d_red, "rsx_index_msavi_f32: bad arguments");
+    return launch_planar<2>("rsx_index_msavi_f32", d_nir, d_red, nullptr, nullptr, d_out, n, OpMsavi{}, stream);
+}
+extern "C" int rsx_index_bsi_f32(const float* d_blue, const float* d_red, const float* d_nir, const float* d_swir, int64_t n, float* d_out,
+                                 rsx_stream_t stream) {
+    RSX_REQUIRE(d_red && d_nir && d_swir, "rsx_index_bsi_f32: bad arguments");
+    return launch_planar<4>("rsx_index_bsi_f32", d_blue, d_red, d_nir, d_swir, d_out, n, OpBsi{}, stream);
+}
+
+__global__ void __launch_bounds__(256) quantize_f32_kernel(const float* __restrict__ in, int64_t n, NormParam p, float lm1, uint8_t* __restrict__ q) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        q[i] = (uint8_t)(int)f_mul(norm_apply(in[i], p), lm1);
+}
+extern "C" int rsx_quantize_f32(const float* d_in, int64_t n, float lo, float hi, float den, int levels, uint8_t* d_q, rsx_stream_t stream) {
+    RSX_REQUIRE(d_in && d_q && n > 0 && levels >= 2 && levels <= 256, "rsx_quantize_f32: bad arguments");
+    quantize_f32_kernel<<<(int)min((int64_t)rsx_num_sms() * 8, ceil_div(n, (int64_t)256)), 256, 0, (cudaStream_t)stream>>>(
+        d_in, n, NormParam{lo, hi, den}, (float)(levels - 1), d_q);
+    return rsx_check_launch("rsx_quantize_f32");
+}

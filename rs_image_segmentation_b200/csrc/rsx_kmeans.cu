@@ -1,0 +1,455 @@
+// K5: KMeans (Lloyd) assign + partial-sum pass, centroid update.
+//
+// Replaces sklearn's lloyd_iter_chunked_dense as driven by extract.py:571-577:
+//   MinMaxScaler.transform  X*scale + min_            (sklearn/preprocessing/_data.py:574-575)
+//   centring                X -= X.mean(axis=0)       (sklearn/cluster/_kmeans.py:1488-1490)
+//   E step                  argmin_j |c_j|^2 - 2 x.c_j, first minimum wins (_k_means_lloyd.pyx:198-212)
+//   M step                  per-cluster sums / counts  (_k_means_lloyd.pyx:214-218, _k_means_common.pyx:274-296)
+//
+// HBM layout: the feature stack is planar float32, D planes of n_px; one pass reads 4*D bytes/pixel and
+// nothing else (centroids live in constant memory and reach FFMA2 as uniform-register operands).
+//
+// Exactness: the parity target is sklearn run on the float64 promotion of the same stack.  The fast
+// path evaluates the K distances in fp32 and keeps the best and second best; when their gap is below
+// a rigorous rounding bound tau (computed per update from the centroid magnitudes) the pixel is
+// re-evaluated in float64 with sklearn's operation order.  Partial sums are accumulated as int64
+// fixed point (x * 2^shift_d, rounded once per sample), so they are associative: any tiling, any
+// number of GPUs and any atomic ordering give bit-identical sums, hence bit-identical centroids.
+#include "rsx_common.cuh"
+
+#define KM_MAXD RSX_MAX_FEATURES
+#define KM_MAXK RSX_MAX_CLUSTERS
+
+struct KmState {
+    int D, K;
+    long long n_global;
+    double scale64[KM_MAXD], min64[KM_MAXD], mean64[KM_MAXD];  // MinMax scale_, min_; centring mean (scaled coords)
+    double absmax[KM_MAXD];                                     // max |raw x_d|
+    float scale32[KM_MAXD], off32[KM_MAXD];                     // x' ~= fma(x, scale32, off32), off = min_ - mean
+    float pow2[KM_MAXD];                                        // 2^shift_d (fixed-point scale of the raw feature)
+    double inv_pow2[KM_MAXD];
+    double cent64[KM_MAXK * KM_MAXD];                           // centred, scaled coordinates [K][D]
+    double cnorm64[KM_MAXK];
+    // fp32 fast path works on RAW features: dist_j = bias32[j] + sum_d x_d * w32[j][d] with
+    // w = -2 c_jd scale_d and bias = |c_j|^2 - 2 sum_d c_jd (min_d - mean_d): scaling and centring are folded in
+    float w32[KM_MAXK * KM_MAXD];
+    float bias32[KM_MAXK];
+    float tau;
+    float pad0;
+    double shift_sq;
+    int n_empty;
+    int n_updates;
+};
+
+__constant__ KmState g_km;  // refreshed (device-to-device) after every setup/update
+
+extern "C" int64_t rsx_kmeans_state_bytes(void) { return (int64_t)sizeof(KmState); }
+
+// ----------------------------------------------------------------------------- derived tables (device, 1 CTA)
+__device__ void km_derive(KmState* st) {
+    // called by one CTA; thread j < K handles centroid j
+    const int D = st->D, K = st->K;
+    __shared__ double e_arr[KM_MAXK];
+    for (int j = threadIdx.x; j < K; j += blockDim.x) {
+        double cn = 0.0, bias = 0.0, mag = 0.0;
+        for (int d = 0; d < D; ++d) {
+            double c = st->cent64[j * KM_MAXD + d];
+            double w = -2.0 * c * st->scale64[d];
+            cn += c * c;
+            bias += -2.0 * c * (st->min64[d] - st->mean64[d]);
+            st->w32[j * KM_MAXD + d] = (float)w;
+            mag += st->absmax[d] * fabs(w) + fabs(2.0 * c * (st->min64[d] - st->mean64[d]));
+        }
+        st->cnorm64[j] = cn;
+        st->bias32[j] = (float)(cn + bias);
+        // rounding bound of the fp32 path (DESIGN.md "KMeans near-tie bound"): every term of the D+1 term sum and
+        // every partial sum is below mag + cn in magnitude; w32, bias32 and each FMA round once (u = 2^-24)
+        e_arr[j] = (D + 3) * (mag + cn);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double e_max = 0.0;
+        for (int j = 0; j < K; ++j) e_max = fmax(e_max, e_arr[j]);
+        st->tau = (float)(2.0 * 1.5 * e_max * 5.9604644775390625e-08);  // two distances, 1.5x safety
+    }
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        st->scale32[d] = (float)st->scale64[d];
+        st->off32[d] = (float)(st->min64[d] - st->mean64[d]);
+    }
+}
+
+__global__ void km_setup_kernel(KmState* st) {
+    km_derive(st);
+    if (threadIdx.x == 0) {
+        st->shift_sq = 0.0;
+        st->n_empty = 0;
+        st->n_updates = 0;
+    }
+}
+
+static int km_publish(void* d_state, cudaStream_t s) {
+    cudaError_t e = cudaMemcpyToSymbolAsync(g_km, d_state, sizeof(KmState), 0, cudaMemcpyDeviceToDevice, s);
+    if (e != cudaSuccess) {
+        rsx_set_error("kmeans: publishing state to constant memory failed: %s", cudaGetErrorString(e));
+        return RSX_ERR_CUDA;
+    }
+    return RSX_OK;
+}
+
+extern "C" int rsx_kmeans_setup(void* d_state, int D, int K, const double* h_feat_min, const double* h_feat_max, const double* h_mean_scaled,
+                                const double* h_init_centroids, int64_t n_px_global, rsx_stream_t stream) {
+    RSX_REQUIRE(d_state && h_feat_min && h_feat_max && h_mean_scaled && h_init_centroids, "rsx_kmeans_setup: null argument");
+    RSX_REQUIRE(D >= 1 && D <= KM_MAXD && K >= 1 && K <= KM_MAXK && n_px_global > 0, "rsx_kmeans_setup: need 1<=D<=%d, 1<=K<=%d", KM_MAXD, KM_MAXK);
+    static thread_local KmState h;  // staging copy; cudaMemcpyAsync from pageable memory returns after staging
+    memset(&h, 0, sizeof(h));
+    h.D = D, h.K = K, h.n_global = n_px_global;
+    // bits available per sample so that n_global samples cannot overflow int64
+    int nbits = 0;
+    while (((int64_t)1 << nbits) < n_px_global) ++nbits;
+    int budget = 62 - nbits;
+    for (int d = 0; d < D; ++d) {
+        // MinMaxScaler.fit (sklearn/preprocessing/_data.py:527-541): scale_ = 1/range (range 0 -> 1), min_ = -data_min*scale_
+        double range = h_feat_max[d] - h_feat_min[d];
+        if (range < 10.0 * 2.220446049250313e-16) range = 1.0;
+        h.scale64[d] = 1.0 / range;
+        h.min64[d] = 0.0 - h_feat_min[d] * h.scale64[d];
+        h.mean64[d] = h_mean_scaled[d];
+        double am = fmax(fabs(h_feat_min[d]), fabs(h_feat_max[d]));
+        h.absmax[d] = am;
+        int e = 0;
+        if (am > 0) frexp(am, &e);  // am < 2^e
+        int shift = budget - e;
+        if (shift > 100) shift = 100;
+        if (shift < -100) shift = -100;
+        h.pow2[d] = (float)ldexp(1.0, shift);
+        h.inv_pow2[d] = ldexp(1.0, -shift);
+    }
+    for (int j = 0; j < K; ++j)
+        for (int d = 0; d < D; ++d) h.cent64[j * KM_MAXD + d] = h_init_centroids[j * D + d] - h.mean64[d];
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e = cudaMemcpyAsync(d_state, &h, sizeof(h), cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) {
+        rsx_set_error("rsx_kmeans_setup: %s", cudaGetErrorString(e));
+        return RSX_ERR_CUDA;
+    }
+    km_setup_kernel<<<1, 64, 0, s>>>((KmState*)d_state);
+    if (int rc = rsx_check_launch("km_setup")) return rc;
+    return km_publish(d_state, s);
+}
+
+// ----------------------------------------------------------------------------- exact (float64) re-evaluation
+template <int D>
+__device__ __noinline__ int km_exact_argmin(const float* x, double* dist_out) {
+    double X[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) X[d] = __dsub_rn(__dadd_rn(__dmul_rn((double)x[d], g_km.scale64[d]), g_km.min64[d]), g_km.mean64[d]);
+    double best = 0.0, xx = 0.0;
+    int bi = 0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) xx = fma(X[d], X[d], xx);
+    for (int j = 0; j < g_km.K; ++j) {
+        double dot = 0.0;
+#pragma unroll
+        for (int d = 0; d < D; ++d) dot = fma(X[d], g_km.cent64[j * KM_MAXD + d], dot);
+        double v = fma(-2.0, dot, g_km.cnorm64[j]);
+        if (j == 0 || v < best) best = v, bi = j;
+    }
+    *dist_out = fmax(xx + best, 0.0);
+    return bi;
+}
+
+// ----------------------------------------------------------------------------- assign + partial sums
+constexpr int KM_THREADS = 128;
+constexpr int KM_TILE_W = KM_THREADS * 4;  // pixels per tile row
+constexpr int KM_TILE_R = 32;              // rows per tile
+
+template <int D>
+struct KmRun {  // per-thread run-length accumulator: sums of consecutive same-label pixels stay in registers
+    long long s[D];
+    unsigned cnt;
+    int label;
+};
+
+template <int D>
+__device__ __forceinline__ void km_flush(KmRun<D>& run, unsigned* s_lo, int* s_hi) {
+    if (run.label >= 0) {
+        const int base = run.label * (D + 1);
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            unsigned lo = (unsigned)run.s[d];
+            int hi = (int)(run.s[d] >> 32);
+            unsigned old = atomicAdd(&s_lo[base + d], lo);
+            hi += (old + lo < old) ? 1 : 0;  // carry out of the low limb
+            if (hi) atomicAdd(&s_hi[base + d], hi);
+            run.s[d] = 0;
+        }
+        unsigned old = atomicAdd(&s_lo[base + D], run.cnt);
+        if (old + run.cnt < old) atomicAdd(&s_hi[base + D], 1);
+        run.cnt = 0;
+    }
+}
+
+template <int D, bool UPDATE, bool INERTIA>
+__device__ __forceinline__ void km_pixel(const float (&x)[D], float best, float second, int bi, KmRun<D>& run, unsigned* s_lo, int* s_hi,
+                                         int& label_out, double& inertia, unsigned& ties) {
+    double dist_exact = -1.0;
+    if (!(second - best > g_km.tau)) {  // near tie (or NaN): decide in float64
+        bi = km_exact_argmin<D>(x, &dist_exact);
+        ++ties;
+    }
+    label_out = bi;
+    if (INERTIA) {
+        if (dist_exact < 0.0) {
+            float xx = 0.f;
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                float xs = fmaf(x[d], g_km.scale32[d], g_km.off32[d]);
+                xx = fmaf(xs, xs, xx);
+            }
+            dist_exact = (double)fmaxf(xx + best, 0.f);
+        }
+        inertia += dist_exact;
+    }
+    if (UPDATE) {
+        if (bi != run.label) {
+            km_flush<D>(run, s_lo, s_hi);
+            run.label = bi;
+        }
+#pragma unroll
+        for (int d = 0; d < D; ++d) run.s[d] += __float2ll_rn(x[d] * g_km.pow2[d]);
+        run.cnt += 1;
+    }
+}
+
+template <int D, bool UPDATE, bool INERTIA>
+__global__ void __launch_bounds__(KM_THREADS) km_assign_kernel(const float* __restrict__ stack, int64_t plane_stride, int64_t n_px, int row_len,
+                                                               long long* __restrict__ acc, uint8_t* __restrict__ lab8, int32_t* __restrict__ lab32,
+                                                               double* __restrict__ inertia_out) {
+    extern __shared__ unsigned km_smem[];
+    const int K = g_km.K;
+    const int ncell = K * (D + 1);
+    unsigned* s_lo = km_smem;
+    int* s_hi = reinterpret_cast<int*>(km_smem + ncell);
+    if (UPDATE) {
+        for (int i = threadIdx.x; i < 2 * ncell; i += KM_THREADS) km_smem[i] = 0;
+        __syncthreads();
+    }
+    KmRun<D> run;
+#pragma unroll
+    for (int d = 0; d < D; ++d) run.s[d] = 0;
+    run.cnt = 0;
+    run.label = -1;
+    double inertia = 0.0;
+    unsigned ties = 0;
+
+    const int64_t n4 = n_px & ~(int64_t)3;                  // pixels covered by aligned quads
+    const int64_t v_rows = (n4 + row_len - 1) / row_len;    // virtual rows of row_len pixels over the flat array
+    const int tiles_x = (row_len + KM_TILE_W - 1) / KM_TILE_W;
+    const int64_t tiles_y = (v_rows + KM_TILE_R - 1) / KM_TILE_R;
+    const int64_t n_tiles = tiles_y * tiles_x;
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int tx = (int)(tile % tiles_x);
+        const int64_t ty = tile / tiles_x;
+        const int col = tx * KM_TILE_W + threadIdx.x * 4;
+        if (col >= row_len) continue;
+        const int64_t r_end = min(v_rows, (ty + 1) * KM_TILE_R);
+        for (int64_t r = ty * KM_TILE_R; r < r_end; ++r) {
+            const int64_t p = r * row_len + col;
+            if (p >= n4) break;
+            float4 v[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) v[d] = ldg_stream4(stack + d * plane_stride + p);
+            // fp32 distances for the four pixels, two packed pairs
+            float b0 = INFINITY, b1 = INFINITY, b2 = INFINITY, b3 = INFINITY;
+            float s0 = INFINITY, s1 = INFINITY, s2 = INFINITY, s3 = INFINITY;
+            int i0 = 0, i1 = 0, i2 = 0, i3 = 0;
+            for (int j = 0; j < K; ++j) {
+                const float cn = g_km.bias32[j];
+                float2 a01 = make_float2(cn, cn), a23 = a01;
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    const float c = g_km.w32[j * KM_MAXD + d];
+                    a01 = __ffma2_rn(make_float2(v[d].x, v[d].y), make_float2(c, c), a01);
+                    a23 = __ffma2_rn(make_float2(v[d].z, v[d].w), make_float2(c, c), a23);
+                }
+                // first minimum wins; keep the runner-up for the tie test
+                s0 = fminf(s0, fmaxf(a01.x, b0)); if (a01.x < b0) b0 = a01.x, i0 = j;
+                s1 = fminf(s1, fmaxf(a01.y, b1)); if (a01.y < b1) b1 = a01.y, i1 = j;
+                s2 = fminf(s2, fmaxf(a23.x, b2)); if (a23.x < b2) b2 = a23.x, i2 = j;
+                s3 = fminf(s3, fmaxf(a23.y, b3)); if (a23.y < b3) b3 = a23.y, i3 = j;
+            }
+            int l0, l1, l2, l3;
+            {
+                float x[D];
+#pragma unroll
+                for (int d = 0; d < D; ++d) x[d] = v[d].x;
+                km_pixel<D, UPDATE, INERTIA>(x, b0, s0, i0, run, s_lo, s_hi, l0, inertia, ties);
+#pragma unroll
+                for (int d = 0; d < D; ++d) x[d] = v[d].y;
+                km_pixel<D, UPDATE, INERTIA>(x, b1, s1, i1, run, s_lo, s_hi, l1, inertia, ties);
+#pragma unroll
+                for (int d = 0; d < D; ++d) x[d] = v[d].z;
+                km_pixel<D, UPDATE, INERTIA>(x, b2, s2, i2, run, s_lo, s_hi, l2, inertia, ties);
+#pragma unroll
+                for (int d = 0; d < D; ++d) x[d] = v[d].w;
+                km_pixel<D, UPDATE, INERTIA>(x, b3, s3, i3, run, s_lo, s_hi, l3, inertia, ties);
+            }
+            if (lab8) *reinterpret_cast<uint32_t*>(lab8 + p) = (uint32_t)l0 | ((uint32_t)l1 << 8) | ((uint32_t)l2 << 16) | ((uint32_t)l3 << 24);
+            if (lab32) *reinterpret_cast<int4*>(lab32 + p) = make_int4(l0, l1, l2, l3);
+        }
+    }
+    // ragged tail (n_px % 4 pixels): one thread, scalar
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (int64_t p = n4; p < n_px; ++p) {
+            float x[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) x[d] = stack[d * plane_stride + p];
+            float b = INFINITY, s = INFINITY;
+            int bi = 0;
+            for (int j = 0; j < K; ++j) {
+                float a = g_km.bias32[j];
+#pragma unroll
+                for (int d = 0; d < D; ++d) a = fmaf(x[d], g_km.w32[j * KM_MAXD + d], a);
+                s = fminf(s, fmaxf(a, b));
+                if (a < b) b = a, bi = j;
+            }
+            int l;
+            km_pixel<D, UPDATE, INERTIA>(x, b, s, bi, run, s_lo, s_hi, l, inertia, ties);
+            if (lab8) lab8[p] = (uint8_t)l;
+            if (lab32) lab32[p] = l;
+        }
+    }
+    if (UPDATE) {
+        km_flush<D>(run, s_lo, s_hi);
+        __syncthreads();
+        for (int i = threadIdx.x; i < ncell; i += KM_THREADS) {
+            long long v = ((long long)s_hi[i] << 32) + (long long)s_lo[i];
+            if (v) {
+                // acc layout: sums [K][D] then counts [K]
+                int j = i / (D + 1), d = i % (D + 1);
+                long long* dst = d < D ? &acc[j * D + d] : &acc[K * D + j];
+                atomicAdd(reinterpret_cast<unsigned long long*>(dst), (unsigned long long)v);
+            }
+        }
+    }
+    // ties + inertia
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ties += __shfl_xor_sync(0xffffffffu, ties, o);
+        if (INERTIA) inertia += __shfl_xor_sync(0xffffffffu, inertia, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (ties && acc) atomicAdd(reinterpret_cast<unsigned long long*>(&acc[K * D + K]), (unsigned long long)ties);
+        if (INERTIA && inertia_out) atomicAdd(inertia_out, inertia);
+    }
+}
+
+template <int D>
+static int km_launch(const float* d_stack, int64_t plane_stride, int64_t n_px, int row_len, long long* acc, uint8_t* l8, int32_t* l32,
+                     double* inertia, int update, int K, cudaStream_t s) {
+    const int64_t n4 = n_px & ~(int64_t)3;
+    const int64_t v_rows = (n4 + row_len - 1) / row_len;
+    const int64_t n_tiles = ceil_div(v_rows, (int64_t)KM_TILE_R) * ceil_div(row_len, KM_TILE_W);
+    const int grid = (int)max((int64_t)1, min(n_tiles, (int64_t)rsx_num_sms() * 4));
+    const int smem = 2 * K * (D + 1) * 4;
+    if (update && inertia)
+        km_assign_kernel<D, true, true><<<grid, KM_THREADS, smem, s>>>(d_stack, plane_stride, n_px, row_len, acc, l8, l32, inertia);
+    else if (update)
+        km_assign_kernel<D, true, false><<<grid, KM_THREADS, smem, s>>>(d_stack, plane_stride, n_px, row_len, acc, l8, l32, inertia);
+    else if (inertia)
+        km_assign_kernel<D, false, true><<<grid, KM_THREADS, smem, s>>>(d_stack, plane_stride, n_px, row_len, acc, l8, l32, inertia);
+    else
+        km_assign_kernel<D, false, false><<<grid, KM_THREADS, smem, s>>>(d_stack, plane_stride, n_px, row_len, acc, l8, l32, inertia);
+    return rsx_check_launch("km_assign");
+}
+
+extern "C" int rsx_kmeans_assign(const float* d_stack, int64_t plane_stride, int64_t n_px, int row_len, const void* d_state, int64_t* d_acc,
+                                 uint8_t* d_labels_u8, int32_t* d_labels_i32, double* d_inertia, int update, int D, int K,
+                                 rsx_stream_t stream) {
+    RSX_REQUIRE(d_stack && d_state && n_px > 0, "rsx_kmeans_assign: bad arguments");
+    RSX_REQUIRE(D >= 1 && D <= KM_MAXD && K >= 1 && K <= KM_MAXK, "rsx_kmeans_assign: D/K out of range");
+    RSX_REQUIRE(!update || d_acc, "rsx_kmeans_assign: update pass needs d_acc");
+    RSX_REQUIRE(((uintptr_t)d_stack & 15) == 0 && (plane_stride & 3) == 0, "rsx_kmeans_assign: stack planes must be 16-byte aligned");
+    RSX_REQUIRE((((uintptr_t)d_labels_u8) & 3) == 0 && (((uintptr_t)d_labels_i32) & 15) == 0, "rsx_kmeans_assign: label buffers must be aligned");
+    if (row_len <= 0) row_len = 4096;
+    row_len = (row_len + 3) & ~3;
+    cudaStream_t s = (cudaStream_t)stream;
+    long long* acc = reinterpret_cast<long long*>(d_acc);
+#define CASE(DD) \
+    case DD: return km_launch<DD>(d_stack, plane_stride, n_px, row_len, acc, d_labels_u8, d_labels_i32, d_inertia, update, K, s);
+    switch (D) {
+        CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14) CASE(15) CASE(16)
+        CASE(17) CASE(18) CASE(19) CASE(20)
+        default:
+            rsx_set_error("rsx_kmeans_assign: D=%d not compiled (1..20)", D);
+            return RSX_ERR_UNSUPPORTED;
+    }
+#undef CASE
+}
+
+// ----------------------------------------------------------------------------- centroid update (1 CTA)
+__global__ void km_update_kernel(KmState* st, long long* acc) {
+    const int D = st->D, K = st->K;
+    __shared__ double shift_part[KM_MAXK];
+    __shared__ int empty_part[KM_MAXK];
+    for (int j = threadIdx.x; j < K; j += blockDim.x) {
+        long long cnt = acc[K * D + j];
+        double sh = 0.0;
+        int empty = 0;
+        if (cnt > 0) {
+            // _average_centers: centers *= 1/weight  (_k_means_common.pyx:274-296)
+            double alpha = 1.0 / (double)cnt;
+            for (int d = 0; d < D; ++d) {
+                double mean_raw = ((double)acc[j * D + d] * st->inv_pow2[d]) * alpha;
+                double c = (mean_raw * st->scale64[d] + st->min64[d]) - st->mean64[d];
+                double old = st->cent64[j * KM_MAXD + d];
+                sh += (c - old) * (c - old);
+                st->cent64[j * KM_MAXD + d] = c;
+            }
+        } else {
+            empty = 1;  // relocation (_k_means_common.pyx:167-211) is not done on the device: reported to the host
+        }
+        shift_part[j] = sh;
+        empty_part[j] = empty;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        int e = 0;
+        for (int j = 0; j < K; ++j) s += shift_part[j], e += empty_part[j];
+        st->shift_sq = s;
+        st->n_empty += e;
+        st->n_updates += 1;
+    }
+    __syncthreads();
+    km_derive(st);
+    __syncthreads();
+    for (int i = threadIdx.x; i < K * (D + 1); i += blockDim.x) acc[i] = 0;  // ties counter (last slot) keeps accumulating
+}
+
+extern "C" int rsx_kmeans_update(void* d_state, int64_t* d_acc, rsx_stream_t stream) {
+    RSX_REQUIRE(d_state && d_acc, "rsx_kmeans_update: bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    km_update_kernel<<<1, 64, 0, s>>>((KmState*)d_state, reinterpret_cast<long long*>(d_acc));
+    if (int rc = rsx_check_launch("km_update")) return rc;
+    return km_publish(d_state, s);
+}
+
+extern "C" int rsx_kmeans_read(const void* d_state, double* h_centroids, double* h_shift_sq, int32_t* h_empty, rsx_stream_t stream) {
+    RSX_REQUIRE(d_state, "rsx_kmeans_read: bad arguments");
+    static thread_local KmState h;
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e = cudaMemcpyAsync(&h, d_state, sizeof(h), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) {
+        rsx_set_error("rsx_kmeans_read: %s", cudaGetErrorString(e));
+        return RSX_ERR_CUDA;
+    }
+    if (h_centroids)
+        for (int j = 0; j < h.K; ++j)
+            for (int d = 0; d < h.D; ++d) h_centroids[j * h.D + d] = h.cent64[j * KM_MAXD + d] + h.mean64[d];
+    if (h_shift_sq) *h_shift_sq = h.shift_sq;
+    if (h_empty) *h_empty = h.n_empty;
+    return RSX_OK;
+}

@@ -1,0 +1,564 @@
+// Kernels that stream the pixel-interleaved raster: K1 histograms, K2 fused normalise + spectral
+// indices (+ GLCM quantisation), K3 PCA moments (warp-shuffle tree reductions) and projection.
+#include "rsx_raster.cuh"
+
+// ============================================================================ K1: histograms
+// The raster is treated as a sample stream: sample s belongs to band s % B (tiles start on pixel
+// boundaries).  A lane reads one 32-bit word = 4 consecutive samples, so lanes that can collide on
+// one (band, value) bin are B apart - at most ceil(32/B) lanes, not 32 as with a pixel-per-lane map.
+template <int B, int NCOPY>
+__global__ void __launch_bounds__(256) hist_u8_kernel(const uint8_t* __restrict__ raster, int64_t n_px, uint32_t* __restrict__ hist) {
+    using RT = RasterTiles<uint8_t, B, 2>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint32_t* sh = reinterpret_cast<uint32_t*>(smem + RT::SMEM_BYTES);  // [NCOPY][B][256]
+    for (int i = threadIdx.x; i < NCOPY * B * 256; i += 256) sh[i] = 0;
+    __syncthreads();
+    uint32_t* mine = sh + ((threadIdx.x >> 5) % NCOPY) * (B * 256);
+    for_each_tile<uint8_t, B, 2>(raster, n_px, smem, [&](const uint32_t* words, int64_t, int npx) {
+        const int nwords = (npx * B + 3) >> 2;
+        const int nbytes = npx * B;
+        for (int wi = threadIdx.x; wi < nwords; wi += 256) {
+            uint32_t w = words[wi];
+            int band = (wi * 4) % B;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (wi * 4 + k < nbytes) atomicAdd(&mine[band * 256 + ((w >> (8 * k)) & 0xffu)], 1u);
+                band = band + 1 == B ? 0 : band + 1;
+            }
+        }
+    });
+    __syncthreads();
+    for (int i = threadIdx.x; i < B * 256; i += 256) {
+        uint32_t s = 0;
+#pragma unroll
+        for (int c = 0; c < NCOPY; ++c) s += sh[c * B * 256 + i];
+        if (s) atomicAdd(&hist[i], s);
+    }
+}
+
+template <int B>
+__global__ void __launch_bounds__(256) hist_u16_kernel(const uint16_t* __restrict__ raster, int64_t n_px, uint32_t* __restrict__ hist) {
+    using RT = RasterTiles<uint16_t, B, 2>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    (void)sizeof(RT);
+    for_each_tile<uint16_t, B, 2>(raster, n_px, smem, [&](const uint32_t* words, int64_t, int npx) {
+        const int nhalf = npx * B;
+        const int nwords = (nhalf + 1) >> 1;
+        for (int wi = threadIdx.x; wi < nwords; wi += 256) {
+            uint32_t w = words[wi];
+            int band = (wi * 2) % B;
+            atomicAdd(&hist[(size_t)band * 65536 + (w & 0xffffu)], 1u);
+            band = band + 1 == B ? 0 : band + 1;
+            if (wi * 2 + 1 < nhalf) atomicAdd(&hist[(size_t)band * 65536 + (w >> 16)], 1u);
+        }
+    });
+}
+
+template <typename K>
+static int set_smem(K kernel, int bytes) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) {
+        rsx_set_error("cudaFuncSetAttribute(%d bytes): %s", bytes, cudaGetErrorString(e));
+        return RSX_ERR_CUDA;
+    }
+    return RSX_OK;
+}
+
+static int persistent_grid(int64_t n_tiles, int ctas_per_sm) { return (int)min(n_tiles, (int64_t)rsx_num_sms() * ctas_per_sm); }
+
+extern "C" int rsx_hist_u8(const uint8_t* d_raster, int64_t n_px, int n_bands, uint32_t* d_hist, rsx_stream_t stream) {
+    RSX_REQUIRE(d_raster && d_hist && n_px > 0, "rsx_hist_u8: bad arguments");
+    RSX_REQUIRE(((uintptr_t)d_raster & 15) == 0, "rsx_hist_u8: raster must be 16-byte aligned");
+#define LAUNCH(BB)                                                                                         \
+    {                                                                                                      \
+        using RT = RasterTiles<uint8_t, BB, 2>;                                                            \
+        constexpr int NCOPY = 4;                                                                           \
+        int smem = RT::SMEM_BYTES + NCOPY * BB * 256 * 4;                                                  \
+        if (int rc = set_smem(hist_u8_kernel<BB, NCOPY>, smem)) return rc;                                 \
+        int grid = persistent_grid(ceil_div(n_px, (int64_t)RT::TILE_PX), 2);                               \
+        hist_u8_kernel<BB, NCOPY><<<grid, 256, smem, (cudaStream_t)stream>>>(d_raster, n_px, d_hist);      \
+    }
+    RSX_DISPATCH_BANDS(n_bands, LAUNCH)
+#undef LAUNCH
+    return rsx_check_launch("rsx_hist_u8");
+}
+
+extern "C" int rsx_hist_u16(const uint16_t* d_raster, int64_t n_px, int n_bands, uint32_t* d_hist, rsx_stream_t stream) {
+    RSX_REQUIRE(d_raster && d_hist && n_px > 0, "rsx_hist_u16: bad arguments");
+    RSX_REQUIRE(((uintptr_t)d_raster & 15) == 0, "rsx_hist_u16: raster must be 16-byte aligned");
+#define LAUNCH(BB)                                                                                    \
+    {                                                                                                 \
+        using RT = RasterTiles<uint16_t, BB, 2>;                                                      \
+        if (int rc = set_smem(hist_u16_kernel<BB>, RT::SMEM_BYTES)) return rc;                        \
+        int grid = persistent_grid(ceil_div(n_px, (int64_t)RT::TILE_PX), 2);                          \
+        hist_u16_kernel<BB><<<grid, 256, RT::SMEM_BYTES, (cudaStream_t)stream>>>(d_raster, n_px, d_hist); \
+    }
+    RSX_DISPATCH_BANDS(n_bands, LAUNCH)
+#undef LAUNCH
+    return rsx_check_launch("rsx_hist_u16");
+}
+
+// ============================================================================ K2: fused normalise + indices
+struct IndexParams {
+    NormParam norm[5];  // blue, green, red, nir, swir1 (already gathered through band_map)
+    int band[5];
+    float evi_L, evi_C1, evi_C2, evi_G;
+    NormParam qnorm;
+    float q_scale;  // levels - 1
+};
+
+// the seven maps of scripts/2_feature_extraction.py:63-73, in RSX index order
+__device__ __forceinline__ void seven_indices(float blue, float green, float red, float nir, float swir, const IndexParams& P, float (&o)[7]) {
+    // ndvi (indices.py:62-69)
+    {
+        float den = f_add(nir, red);
+        o[0] = f_clip(den > 0.001f ? f_div(f_sub(nir, red), den) : 0.f, -1.f, 1.f);
+    }
+    // evi (indices.py:86-93)
+    {
+        float den = f_add(f_sub(f_add(nir, f_mul(P.evi_C1, red)), f_mul(P.evi_C2, blue)), P.evi_L);
+        o[1] = f_clip(den > 0.001f ? f_div(f_mul(P.evi_G, f_sub(nir, red)), den) : 0.f, -1.f, 1.f);
+    }
+    // msavi (indices.py:109-112)
+    {
+        float t = f_add(f_mul(2.f, nir), 1.f);
+        float v = f_div(f_sub(t, f_sqrt(f_sub(f_mul(t, t), f_mul(8.f, f_sub(nir, red))))), 2.f);
+        o[2] = v != v ? v : f_clip(v, -1.f, 1.f);
+    }
+    // ndwi (indices.py:128-135)
+    {
+        float den = f_add(green, nir);
+        o[3] = f_clip(den > 0.001f ? f_div(f_sub(green, nir), den) : 0.f, -1.f, 1.f);
+    }
+    // mndwi (indices.py:150-156)
+    {
+        float den = f_add(green, swir);
+        o[4] = f_clip(den > 0.001f ? f_div(f_sub(green, swir), den) : 0.f, -1.f, 1.f);
+    }
+    // ndbi (indices.py:171-177)
+    {
+        float den = f_add(swir, nir);
+        o[5] = f_clip(den > 0.001f ? f_div(f_sub(swir, nir), den) : 0.f, -1.f, 1.f);
+    }
+    // bsi (indices.py:194-201)
+    {
+        float a = f_add(swir, red), b = f_add(nir, blue);
+        float den = f_add(a, b);
+        o[6] = f_clip(den > 0.001f ? f_div(f_sub(a, b), den) : 0.f, -1.f, 1.f);
+    }
+}
+
+template <typename T, int B>
+__global__ void __launch_bounds__(256) indices_fused_kernel(const T* __restrict__ raster, int64_t n_px, IndexParams P, float* __restrict__ out,
+                                                            int64_t plane_stride, uint32_t* __restrict__ minmax, uint8_t* __restrict__ quant) {
+    using RT = RasterTiles<T, B, 3>;
+    constexpr int PXT = RT::PXT;
+    extern __shared__ __align__(128) unsigned char smem[];
+    float mn[7], mx[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) mn[k] = INFINITY, mx[k] = -INFINITY;
+
+    for_each_tile<T, B, 3>(raster, n_px, smem, [&](const uint32_t* words, int64_t px0, int npx) {
+        const T* samples = reinterpret_cast<const T*>(words);
+#pragma unroll
+        for (int sub = 0; sub < RT::SUB; ++sub) {
+            const int g = sub * 256 + threadIdx.x;
+            const int lp = g * PXT;  // first pixel of this group inside the tile
+            if (lp >= npx) continue;
+            float o[PXT][7];
+            uint8_t q[PXT];
+#pragma unroll
+            for (int p = 0; p < PXT; ++p) {
+                const T* px = samples + (lp + p) * B;
+                float nb[5];
+#pragma unroll
+                for (int k = 0; k < 5; ++k) nb[k] = norm_apply((float)px[P.band[k]], P.norm[k]);
+                seven_indices(nb[0], nb[1], nb[2], nb[3], nb[4], P, o[p]);
+                q[p] = (uint8_t)(int)f_mul(norm_apply(nb[3], P.qnorm), P.q_scale);
+            }
+            const int64_t gp = px0 + lp;
+            if (lp + PXT <= npx) {
+#pragma unroll
+                for (int k = 0; k < 7; ++k) {
+                    float* dst = out + k * plane_stride + gp;
+                    if constexpr (PXT == 4)
+                        stg_stream4(dst, make_float4(o[0][k], o[1][k], o[2][k], o[3][k]));
+                    else
+                        *reinterpret_cast<float2*>(dst) = make_float2(o[0][k], o[1][k]);
+#pragma unroll
+                    for (int p = 0; p < PXT; ++p) mn[k] = fminf(mn[k], o[p][k]), mx[k] = fmaxf(mx[k], o[p][k]);
+                }
+                if (quant) {
+                    if constexpr (PXT == 4)
+                        *reinterpret_cast<uint32_t*>(quant + gp) = q[0] | (q[1] << 8) | (q[2] << 16) | ((uint32_t)q[3] << 24);
+                    else
+                        *reinterpret_cast<uint16_t*>(quant + gp) = (uint16_t)(q[0] | (q[1] << 8));
+                }
+            } else {
+#pragma unroll
+                for (int p = 0; p < PXT; ++p)
+                    if (lp + p < npx) {
+#pragma unroll
+                        for (int k = 0; k < 7; ++k) {
+                            out[k * plane_stride + gp + p] = o[p][k];
+                            mn[k] = fminf(mn[k], o[p][k]), mx[k] = fmaxf(mx[k], o[p][k]);
+                        }
+                        if (quant) quant[gp + p] = q[p];
+                    }
+            }
+        }
+    });
+    if (minmax) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) warp_minmax_commit(mn[k], mx[k], minmax + 2 * k);
+    }
+}
+
+template <typename T>
+static int indices_fused_impl(const T* d_raster, int64_t n_px, int n_bands, const int* band_map, const float* h_norm, const float* evi,
+                              float* d_indices, int64_t plane_stride, uint32_t* d_minmax, uint8_t* d_quant, const float* h_qnorm, int levels,
+                              rsx_stream_t stream) {
+    RSX_REQUIRE(d_raster && band_map && h_norm && evi && d_indices && n_px > 0, "rsx_indices_fused: bad arguments");
+    RSX_REQUIRE(((uintptr_t)d_raster & 15) == 0 && ((uintptr_t)d_indices & 15) == 0 && (plane_stride & 3) == 0 && plane_stride >= n_px,
+                "rsx_indices_fused: raster/planes must be 16-byte aligned, plane_stride a multiple of 4 and >= n_px");
+    RSX_REQUIRE(!d_quant || (h_qnorm && levels >= 2 && levels <= 256 && ((uintptr_t)d_quant & 3) == 0), "rsx_indices_fused: bad quantisation arguments");
+    IndexParams P;
+    for (int k = 0; k < 5; ++k) {
+        int b = band_map[k];
+        RSX_REQUIRE(b >= 0 && b < n_bands, "rsx_indices_fused: band_map[%d]=%d out of range", k, b);
+        P.band[k] = b;
+        P.norm[k] = NormParam{h_norm[3 * b], h_norm[3 * b + 1], h_norm[3 * b + 2]};
+    }
+    P.evi_L = evi[0], P.evi_C1 = evi[1], P.evi_C2 = evi[2], P.evi_G = evi[3];
+    P.qnorm = d_quant ? NormParam{h_qnorm[0], h_qnorm[1], h_qnorm[2]} : NormParam{0.f, 1.f, 1.f};
+    P.q_scale = (float)(levels - 1);
+#define LAUNCH(BB)                                                                                                                  \
+    {                                                                                                                               \
+        using RT = RasterTiles<T, BB, 3>;                                                                                           \
+        if (int rc = set_smem(indices_fused_kernel<T, BB>, RT::SMEM_BYTES)) return rc;                                              \
+        int grid = persistent_grid(ceil_div(n_px, (int64_t)RT::TILE_PX), RT::SMEM_BYTES > 110000 ? 1 : 2);                          \
+        indices_fused_kernel<T, BB><<<grid, 256, RT::SMEM_BYTES, (cudaStream_t)stream>>>(d_raster, n_px, P, d_indices, plane_stride, d_minmax, d_quant); \
+    }
+    RSX_DISPATCH_BANDS(n_bands, LAUNCH)
+#undef LAUNCH
+    return rsx_check_launch("rsx_indices_fused");
+}
+
+extern "C" int rsx_indices_fused_u8(const uint8_t* d_raster, int64_t n_px, int n_bands, const int* band_map, const float* h_norm, const float* evi,
+                                    float* d_indices, int64_t plane_stride, uint32_t* d_minmax, uint8_t* d_quant, const float* h_qnorm, int levels,
+                                    rsx_stream_t stream) {
+    return indices_fused_impl<uint8_t>(d_raster, n_px, n_bands, band_map, h_norm, evi, d_indices, plane_stride, d_minmax, d_quant, h_qnorm, levels, stream);
+}
+extern "C" int rsx_indices_fused_u16(const uint16_t* d_raster, int64_t n_px, int n_bands, const int* band_map, const float* h_norm, const float* evi,
+                                     float* d_indices, int64_t plane_stride, uint32_t* d_minmax, uint8_t* d_quant, const float* h_qnorm, int levels,
+                                     rsx_stream_t stream) {
+    return indices_fused_impl<uint16_t>(d_raster, n_px, n_bands, band_map, h_norm, evi, d_indices, plane_stride, d_minmax, d_quant, h_qnorm, levels, stream);
+}
+
+// ============================================================================ K3: PCA
+// X = RobustScaler().fit_transform(normalised bands) as sklearn computes it for float32 input:
+//   X -= center_ (float32);  X /= scale_ where scale_ is FLOAT64 (np.nanpercentile of a (25.0, 75.0) tuple), so the
+//   division is evaluated in float64 and rounded to float32 (sklearn/preprocessing/_data.py:1738-1743,1782-1784).
+// uint8 rasters: X is a function of the 256 grey levels of each band, so the host tabulates it once (same numpy
+// expressions as the reference) and the kernels look it up in shared memory: bit-exact by construction, no divisions.
+// uint16 rasters: evaluated arithmetically with the same operation order.
+template <int B>
+struct PcaParams {
+    NormParam norm[B];
+    float center[B];
+    double scale[B];
+    const float* lut;  // device [B][256] (uint8 rasters) or nullptr
+};
+
+template <typename T, int B>
+__device__ __forceinline__ void scaled_pixel(const int (&raw)[B], const PcaParams<B>& P, const float* lut_s, float (&x)[B]) {
+#pragma unroll
+    for (int b = 0; b < B; ++b) {
+        if constexpr (sizeof(T) == 1)
+            x[b] = lut_s[b * 256 + raw[b]];
+        else
+            x[b] = __double2float_rn(__ddiv_rn((double)f_sub(norm_apply((float)raw[b], P.norm[b]), P.center[b]), P.scale[b]));
+    }
+}
+
+template <typename T, int B>
+__device__ __forceinline__ const float* stage_lut(const PcaParams<B>& P, float* lut_s) {
+    if constexpr (sizeof(T) == 1) {
+        for (int i = threadIdx.x; i < B * 256; i += blockDim.x) lut_s[i] = P.lut[i];
+        __syncthreads();
+    }
+    return lut_s;
+}
+
+template <int B>
+struct Moments {
+    static constexpr int NPAIR = B * (B + 1) / 2;
+    static constexpr int M = B + NPAIR;
+    static constexpr int NSPLIT = B <= 8 ? 1 : 4;  // thread groups sharing the pair set (register budget)
+    static constexpr int NACC = (NPAIR + NSPLIT - 1) / NSPLIT;
+};
+
+template <int B, int PART>
+__device__ __forceinline__ void moments_accumulate(const float (&x)[B], double (&sum)[B], double (&acc)[Moments<B>::NACC]) {
+    constexpr int NS = Moments<B>::NSPLIT;
+    if (PART == 0) {
+#pragma unroll
+        for (int b = 0; b < B; ++b) sum[b] += (double)x[b];
+    }
+    int idx = 0;
+#pragma unroll
+    for (int a = 0; a < B; ++a)
+#pragma unroll
+        for (int b = a; b < B; ++b) {
+            if (idx % NS == PART) acc[idx / NS] = fma((double)x[a], (double)x[b], acc[idx / NS]);
+            ++idx;
+        }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <typename T>
+constexpr int lut_bytes(int B) { return sizeof(T) == 1 ? B * 256 * 4 : 0; }
+
+template <typename T, int B>
+__global__ void __launch_bounds__(256) pca_moments_kernel(const T* __restrict__ raster, int64_t n_px, const __grid_constant__ PcaParams<B> P,
+                                                          double* __restrict__ scratch) {
+    using RT = RasterTiles<T, B, 3>;
+    using MM = Moments<B>;
+    constexpr int PXT = RT::PXT;
+    constexpr int NS = MM::NSPLIT;
+    constexpr int TPP = 256 / NS;  // threads per part
+    extern __shared__ __align__(128) unsigned char smem[];
+    double* red = reinterpret_cast<double*>(smem + RT::SMEM_BYTES);                      // [8 warps][M]
+    float* lut_s = reinterpret_cast<float*>(smem + RT::SMEM_BYTES + 8 * MM::M * 8);      // [B][256]
+    stage_lut<T, B>(P, lut_s);
+    const int part = threadIdx.x / TPP, lt = threadIdx.x % TPP;
+
+    double sum[B], acc[MM::NACC];
+#pragma unroll
+    for (int b = 0; b < B; ++b) sum[b] = 0.0;
+#pragma unroll
+    for (int i = 0; i < MM::NACC; ++i) acc[i] = 0.0;
+
+    for_each_tile<T, B, 3>(raster, n_px, smem, [&](const uint32_t* words, int64_t, int npx) {
+        for (int g = lt; g * PXT < npx; g += TPP) {
+            uint32_t w[B];
+#pragma unroll
+            for (int i = 0; i < B; ++i) w[i] = words[g * B + i];
+            int raw[PXT][B];
+            unpack_pixels<T, B>(w, raw);
+#pragma unroll
+            for (int p = 0; p < PXT; ++p) {
+                if (g * PXT + p < npx) {
+                    float x[B];
+                    scaled_pixel<T, B>(raw[p], P, lut_s, x);
+                    if (NS == 1) {
+                        moments_accumulate<B, 0>(x, sum, acc);
+                    } else {
+                        switch (part) {
+                            case 0: moments_accumulate<B, 0>(x, sum, acc); break;
+                            case 1: moments_accumulate<B, 1 % NS>(x, sum, acc); break;
+                            case 2: moments_accumulate<B, 2 % NS>(x, sum, acc); break;
+                            default: moments_accumulate<B, 3 % NS>(x, sum, acc); break;
+                        }
+                    }
+                }
+            }
+        }
+    });
+
+    // warp-shuffle tree per accumulator, then a fixed-order sum over the CTA's warps
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 8 * MM::M; i += 256) red[i] = 0.0;
+    __syncthreads();
+#pragma unroll
+    for (int b = 0; b < B; ++b) {
+        double v = warp_sum(sum[b]);
+        if (lane == 0 && part == 0) red[warp * MM::M + b] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < MM::NACC; ++i) {
+        double v = warp_sum(acc[i]);
+        int idx = i * NS + part;
+        if (lane == 0 && idx < MM::NPAIR) red[warp * MM::M + B + idx] = v;
+    }
+    __syncthreads();
+    for (int m = threadIdx.x; m < MM::M; m += 256) {
+        double s = 0.0;
+#pragma unroll
+        for (int wv = 0; wv < 8; ++wv) s += red[wv * MM::M + m];
+        scratch[(size_t)blockIdx.x * MM::M + m] = s;
+    }
+}
+
+__global__ void pca_moments_finish_kernel(const double* __restrict__ scratch, int n_blocks, int M, double* __restrict__ moments) {
+    int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    double s = 0.0;
+    for (int i = 0; i < n_blocks; ++i) s += scratch[(size_t)i * M + m];
+    moments[m] += s;
+}
+
+static int pca_grid() { return rsx_num_sms(); }
+extern "C" int64_t rsx_pca_scratch_elems(int n_bands) { return (int64_t)pca_grid() * (n_bands + n_bands * (n_bands + 1) / 2); }
+
+template <int B>
+static void fill_pca_params(PcaParams<B>& P, const float* h_norm, const float* h_center, const double* h_scale, const float* d_lut) {
+    for (int b = 0; b < B; ++b) {
+        P.norm[b] = h_norm ? NormParam{h_norm[3 * b], h_norm[3 * b + 1], h_norm[3 * b + 2]} : NormParam{0.f, 1.f, 1.f};
+        P.center[b] = h_center ? h_center[b] : 0.f;
+        P.scale[b] = h_scale ? h_scale[b] : 1.0;
+    }
+    P.lut = d_lut;
+}
+
+template <typename T>
+static int pca_moments_impl(const T* d_raster, int64_t n_px, int n_bands, const float* h_norm, const float* h_center, const double* h_scale,
+                            const float* d_lut, double* d_moments, double* d_scratch, rsx_stream_t stream) {
+    RSX_REQUIRE(d_raster && d_moments && d_scratch && n_px > 0, "rsx_pca_moments: bad arguments");
+    RSX_REQUIRE(sizeof(T) == 1 ? d_lut != nullptr : (h_norm && h_center && h_scale), "rsx_pca_moments: missing scaling parameters");
+    RSX_REQUIRE(((uintptr_t)d_raster & 15) == 0, "rsx_pca_moments: raster must be 16-byte aligned");
+#define LAUNCH(BB)                                                                                                     \
+    {                                                                                                                  \
+        using RT = RasterTiles<T, BB, 3>;                                                                              \
+        using MM = Moments<BB>;                                                                                        \
+        PcaParams<BB> P;                                                                                               \
+        fill_pca_params<BB>(P, h_norm, h_center, h_scale, d_lut);                                                      \
+        int smem = RT::SMEM_BYTES + 8 * MM::M * 8 + lut_bytes<T>(BB);                                                  \
+        if (int rc = set_smem(pca_moments_kernel<T, BB>, smem)) return rc;                                             \
+        int grid = (int)min((int64_t)pca_grid(), ceil_div(n_px, (int64_t)RT::TILE_PX));                                \
+        pca_moments_kernel<T, BB><<<grid, 256, smem, (cudaStream_t)stream>>>(d_raster, n_px, P, d_scratch);            \
+        if (int rc = rsx_check_launch("pca_moments")) return rc;                                                       \
+        pca_moments_finish_kernel<<<ceil_div(MM::M, 128), 128, 0, (cudaStream_t)stream>>>(d_scratch, grid, MM::M, d_moments); \
+    }
+    RSX_DISPATCH_BANDS(n_bands, LAUNCH)
+#undef LAUNCH
+    return rsx_check_launch("pca_moments_finish");
+}
+extern "C" int rsx_pca_moments_u8(const uint8_t* d_raster, int64_t n_px, int n_bands, const float* d_lut, double* d_moments, double* d_scratch,
+                                  rsx_stream_t stream) {
+    return pca_moments_impl<uint8_t>(d_raster, n_px, n_bands, nullptr, nullptr, nullptr, d_lut, d_moments, d_scratch, stream);
+}
+extern "C" int rsx_pca_moments_u16(const uint16_t* d_raster, int64_t n_px, int n_bands, const float* h_norm, const float* h_center,
+                                   const double* h_scale, double* d_moments, double* d_scratch, rsx_stream_t stream) {
+    return pca_moments_impl<uint16_t>(d_raster, n_px, n_bands, h_norm, h_center, h_scale, nullptr, d_moments, d_scratch, stream);
+}
+
+// ---- projection: Y = X @ components^T - mean @ components^T  (sklearn/decomposition/_base.py:151-159)
+template <int B>
+struct ProjParams {
+    PcaParams<B> pca;
+    float comp[B][B];  // [component][band]
+    float mean_proj[B];
+    int n_comp;
+};
+
+template <typename T, int B>
+__global__ void __launch_bounds__(256) pca_project_kernel(const T* __restrict__ raster, int64_t n_px, const __grid_constant__ ProjParams<B> P,
+                                                          float* __restrict__ out, int64_t plane_stride, uint32_t* __restrict__ minmax) {
+    using RT = RasterTiles<T, B, 3>;
+    constexpr int PXT = RT::PXT;
+    extern __shared__ __align__(128) unsigned char smem[];
+    float* lut_s = reinterpret_cast<float*>(smem + RT::SMEM_BYTES);
+    stage_lut<T, B>(P.pca, lut_s);
+    float mn[B], mx[B];
+#pragma unroll
+    for (int c = 0; c < B; ++c) mn[c] = INFINITY, mx[c] = -INFINITY;
+
+    for_each_tile<T, B, 3>(raster, n_px, smem, [&](const uint32_t* words, int64_t px0, int npx) {
+#pragma unroll
+        for (int sub = 0; sub < RT::SUB; ++sub) {
+            const int g = sub * 256 + threadIdx.x;
+            const int lp = g * PXT;
+            if (lp >= npx) continue;
+            uint32_t w[B];
+#pragma unroll
+            for (int i = 0; i < B; ++i) w[i] = words[g * B + i];
+            int raw[PXT][B];
+            unpack_pixels<T, B>(w, raw);
+            float x[PXT][B];
+#pragma unroll
+            for (int p = 0; p < PXT; ++p) scaled_pixel<T, B>(raw[p], P.pca, lut_s, x[p]);
+            const int64_t gp = px0 + lp;
+            const bool full = lp + PXT <= npx;
+#pragma unroll
+            for (int c = 0; c < B; ++c) {
+                if (c < P.n_comp) {
+                    float y[PXT];
+#pragma unroll
+                    for (int p = 0; p < PXT; ++p) {
+                        float a = 0.f;
+#pragma unroll
+                        for (int b = 0; b < B; ++b) a = fmaf(x[p][b], P.comp[c][b], a);
+                        y[p] = f_sub(a, P.mean_proj[c]);
+                    }
+                    float* dst = out + c * plane_stride + gp;
+                    if (full) {
+                        if constexpr (PXT == 4)
+                            stg_stream4(dst, make_float4(y[0], y[1], y[2], y[3]));
+                        else
+                            *reinterpret_cast<float2*>(dst) = make_float2(y[0], y[1]);
+#pragma unroll
+                        for (int p = 0; p < PXT; ++p) mn[c] = fminf(mn[c], y[p]), mx[c] = fmaxf(mx[c], y[p]);
+                    } else {
+#pragma unroll
+                        for (int p = 0; p < PXT; ++p)
+                            if (lp + p < npx) {
+                                dst[p] = y[p];
+                                mn[c] = fminf(mn[c], y[p]), mx[c] = fmaxf(mx[c], y[p]);
+                            }
+                    }
+                }
+            }
+        }
+    });
+    if (minmax) {
+#pragma unroll
+        for (int c = 0; c < B; ++c)
+            if (c < P.n_comp) warp_minmax_commit(mn[c], mx[c], minmax + 2 * c);
+    }
+}
+
+template <typename T>
+static int pca_project_impl(const T* d_raster, int64_t n_px, int n_bands, const float* h_norm, const float* h_center, const double* h_scale,
+                            const float* d_lut, const float* h_components, const float* h_mean_proj, int n_comp, float* d_out, int64_t plane_stride,
+                            uint32_t* d_minmax, rsx_stream_t stream) {
+    RSX_REQUIRE(d_raster && h_components && h_mean_proj && d_out && n_px > 0, "rsx_pca_project: bad arguments");
+    RSX_REQUIRE(sizeof(T) == 1 ? d_lut != nullptr : (h_norm && h_center && h_scale), "rsx_pca_project: missing scaling parameters");
+    RSX_REQUIRE(n_comp >= 1 && n_comp <= n_bands, "rsx_pca_project: n_comp must be in [1, n_bands]");
+    RSX_REQUIRE(((uintptr_t)d_raster & 15) == 0 && ((uintptr_t)d_out & 15) == 0 && (plane_stride & 3) == 0 && plane_stride >= n_px,
+                "rsx_pca_project: raster/planes must be 16-byte aligned, plane_stride a multiple of 4 and >= n_px");
+#define LAUNCH(BB)                                                                                                           \
+    {                                                                                                                        \
+        using RT = RasterTiles<T, BB, 3>;                                                                                    \
+        ProjParams<BB> P;                                                                                                    \
+        fill_pca_params<BB>(P.pca, h_norm, h_center, h_scale, d_lut);                                                        \
+        for (int c = 0; c < BB; ++c) {                                                                                       \
+            for (int b = 0; b < BB; ++b) P.comp[c][b] = c < n_comp ? h_components[c * BB + b] : 0.f;                         \
+            P.mean_proj[c] = c < n_comp ? h_mean_proj[c] : 0.f;                                                              \
+        }                                                                                                                    \
+        P.n_comp = n_comp;                                                                                                   \
+        int smem = RT::SMEM_BYTES + lut_bytes<T>(BB);                                                                        \
+        if (int rc = set_smem(pca_project_kernel<T, BB>, smem)) return rc;                                                   \
+        int grid = persistent_grid(ceil_div(n_px, (int64_t)RT::TILE_PX), smem > 110000 ? 1 : 2);                             \
+        pca_project_kernel<T, BB><<<grid, 256, smem, (cudaStream_t)stream>>>(d_raster, n_px, P, d_out, plane_stride, d_minmax); \
+    }
+    RSX_DISPATCH_BANDS(n_bands, LAUNCH)
+#undef LAUNCH
+    return rsx_check_launch("rsx_pca_project");
+}
+extern "C" int rsx_pca_project_u8(const uint8_t* d_raster, int64_t n_px, int n_bands, const float* d_lut, const float* h_components,
+                                  const float* h_mean_proj, int n_comp, float* d_out, int64_t plane_stride, uint32_t* d_minmax, rsx_stream_t stream) {
+    return pca_project_impl<uint8_t>(d_raster, n_px, n_bands, nullptr, nullptr, nullptr, d_lut, h_components, h_mean_proj, n_comp, d_out, plane_stride,
+                                     d_minmax, stream);
+}
+extern "C" int rsx_pca_project_u16(const uint16_t* d_raster, int64_t n_px, int n_bands, const float* h_norm, const float* h_center,
+                                   const double* h_scale, const float* h_components, const float* h_mean_proj, int n_comp, float* d_out,
+                                   int64_t plane_stride, uint32_t* d_minmax, rsx_stream_t stream) {
+    return pca_project_impl<uint16_t>(d_raster, n_px, n_bands, h_norm, h_center, h_scale, nullptr, h_components, h_mean_proj, n_comp, d_out, plane_stride,
+                                      d_minmax, stream);
+}

@@ -1,0 +1,100 @@
+"""Thin helpers between torch (device memory, streams, torch.distributed) and the C ABI."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise _lib.RsxError("rsx needs a CUDA device: there is no CPU implementation of the hot path")
+    _lib.load()
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or NULL for None)."""
+    if t is None:
+        return C.c_void_p(0)
+    assert t.is_cuda and t.is_contiguous(), "rsx kernels need contiguous CUDA tensors"
+    return C.c_void_p(t.data_ptr())
+
+
+def hptr(a):
+    """Host pointer of a C-contiguous numpy array (or NULL for None); keep `a` alive during the call."""
+    if a is None:
+        return C.c_void_p(0)
+    assert isinstance(a, np.ndarray) and a.flags["C_CONTIGUOUS"]
+    return C.c_void_p(a.ctypes.data)
+
+
+def to_device(a: np.ndarray, pinned: bool = True):
+    """H2D copy of a numpy array through pinned memory on the current stream."""
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if pinned:
+        t = t.pin_memory()
+    return t.cuda(non_blocking=True)
+
+
+class MinMaxTracker:
+    """uint32 [n][2] device tracker (include/rsx.h 'min/max trackers')."""
+
+    def __init__(self, n: int, device=None):
+        self.n = n
+        self.buf = torch.empty((n, 2), dtype=torch.int32, device=device or "cuda")
+        _lib.call("rsx_minmax_init", ptr(self.buf), n, stream_ptr())
+
+    def slot(self, i: int):
+        return C.c_void_p(self.buf.data_ptr() + 8 * i)
+
+    def read(self):
+        """(min float32[n], max float32[n]); synchronises."""
+        h = self.buf.cpu().numpy().view(np.uint32)
+        mn, mx = np.zeros(self.n, np.float32), np.zeros(self.n, np.float32)
+        _lib.load().rsx_minmax_decode(hptr(np.ascontiguousarray(h)), self.n, hptr(mn), hptr(mx))
+        return mn, mx
+
+
+class StageTimer:
+    """CUDA-event sections on the current stream: `with timer("name"):`; totals after a synchronise."""
+
+    def __init__(self, enabled: bool = True):
+        self.enabled = enabled
+        self.events = {}
+
+    class _Section:
+        def __init__(self, timer, name):
+            self.t, self.name = timer, name
+
+        def __enter__(self):
+            if self.t.enabled:
+                self.a = torch.cuda.Event(enable_timing=True)
+                self.b = torch.cuda.Event(enable_timing=True)
+                self.a.record()
+            return self
+
+        def __exit__(self, *exc):
+            if self.t.enabled:
+                self.b.record()
+                self.t.events.setdefault(self.name, []).append((self.a, self.b))
+            return False
+
+    def __call__(self, name: str):
+        return StageTimer._Section(self, name)
+
+    def reset(self):
+        self.events = {}
+
+    def totals_ms(self):
+        """name -> (total ms, launches); call after torch.cuda.synchronize()."""
+        return {k: (sum(a.elapsed_time(b) for a, b in v), len(v)) for k, v in self.events.items()}
+
+
+NO_TIMER = StageTimer(enabled=False)

@@ -1,0 +1,181 @@
+"""Host-side order statistics from per-band histograms.
+
+For an integer-valued raster every statistic the reference obtains by sorting
+(np.percentile in robust_normalize, modules/features/indices.py:38-39; np.nanmedian /
+np.nanpercentile inside RobustScaler, sklearn/preprocessing/_data.py:1722,1738-1743) is a
+function of the 256- or 65536-bin histogram.  The GPU builds the histograms (K1); this module
+turns them into the handful of scalars the next kernels need.  It is O(levels) work on a few
+kilobytes, not a fallback for the pixel path.
+
+The interpolation arithmetic follows numpy's `_quantile` for method="linear" with the dtypes numpy
+ends up using for a float32 array: np.percentile(a, 2) divides q by float32(100), so the virtual
+index (n-1)*q, gamma and the lerp are all float32; np.nanpercentile(a, (25.0, 75.0)) keeps q in
+float64, so gamma is float64 and the result is float64 (which is why RobustScaler.scale_ is
+float64 for float32 data).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+F32 = np.float32
+
+
+def _lerp(a, b, t):
+    """numpy/lib/_function_base_impl.py `_lerp`, same expressions so the rounding is the same."""
+    a, b, t = np.asanyarray(a), np.asanyarray(b), np.asanyarray(t)
+    diff = np.subtract(b, a)
+    out = np.asanyarray(np.add(a, diff * t))
+    np.subtract(b, diff * (1 - t), out=out, where=t >= 0.5, casting="unsafe", dtype=type(out.dtype))
+    return out[()]
+
+
+class LevelOrder:
+    """Sorted view of one band: cumulative counts over grey levels + the value each level maps to."""
+
+    def __init__(self, hist, values):
+        hist = np.asarray(hist, dtype=np.int64)
+        self.cum = np.cumsum(hist)
+        self.n = int(self.cum[-1]) if hist.size else 0
+        self.values = np.asarray(values)
+        if self.n <= 0:
+            raise ValueError("empty histogram")
+        if self.values.shape != hist.shape:
+            raise ValueError("values/hist shape mismatch")
+
+    def at(self, k: int):
+        """k-th smallest sample (0-based) of the band."""
+        k = min(max(int(k), 0), self.n - 1)
+        return self.values[int(np.searchsorted(self.cum, k, side="right"))]
+
+    def _quantile(self, q):
+        # q is a numpy scalar / 0-d array whose dtype decides the arithmetic, as in numpy
+        vi = np.asanyarray((self.n - 1) * q)
+        prev = np.floor(vi)
+        nxt = prev + 1
+        if vi >= self.n - 1:
+            prev = nxt = np.asanyarray(-1.0)
+        if vi < 0:
+            prev = nxt = np.asanyarray(0.0)
+        pi, ni = int(prev), int(nxt)
+        gamma = np.asanyarray(vi - np.intp(pi), dtype=vi.dtype)
+        a = self.at(pi if pi >= 0 else self.n - 1)
+        b = self.at(ni if ni >= 0 else self.n - 1)
+        return _lerp(a, b, gamma)
+
+    def percentile_scalar(self, q):
+        """np.percentile(band_float32, q) for a Python-number q: float32 arithmetic, float32 result."""
+        q32 = np.true_divide(q, self.values.dtype.type(100) if self.values.dtype.kind == "f" else 100)
+        return self._quantile(q32)
+
+    def nanpercentile_pair(self, qs=(25.0, 75.0)):
+        """np.nanpercentile(column_float32, (25.0, 75.0)): float64 quantiles, float64 result."""
+        q = np.true_divide(np.asanyarray(qs), self.values.dtype.type(100) if self.values.dtype.kind == "f" else 100)
+        return np.array([self._quantile(qi) for qi in q])
+
+    def median(self):
+        """np.nanmedian of a float32 column without NaNs: middle element, or the float32 mean of the two."""
+        n = self.n
+        if n % 2 == 1:
+            return self.values[0:1].dtype.type(self.at(n // 2))
+        pair = np.array([self.at(n // 2 - 1), self.at(n // 2)], dtype=self.values.dtype)
+        return np.mean(pair)
+
+
+def norm_params(lo, hi):
+    """(lo, hi, den) of robust_normalize, indices.py:42-46: den = hi - lo + 1e-10 in the band dtype."""
+    lo, hi = F32(lo), F32(hi)
+    den = hi - lo + 1e-10
+    return lo, hi, F32(den)
+
+
+def normalize_levels(values, lo, hi, den):
+    """robust_normalize applied to the value of every level: (clip(x, lo, hi) - lo) / den, float32."""
+    values = np.asarray(values, dtype=F32)
+    return (np.clip(values, lo, hi) - lo) / den
+
+
+class RasterStats:
+    """Everything the kernels need that comes from the histograms of a (.., B) integer raster.
+
+    norm      float32 [B][3]   lo, hi, den of robust_normalize per band
+    norm_lut  float32 [B][L]   normalised value of every grey level
+    qnorm     float32 [3]      second robust_normalize inside calculate_glcm_features (indices.py:265) on `glcm_band`
+    center    float32 [B]      RobustScaler.center_ of the normalised bands
+    scale     float64 [B]      RobustScaler.scale_
+    x_lut     float32 [B][L]   RobustScaler().fit_transform value of every grey level (uint8 rasters)
+    """
+
+    def __init__(self, hist, glcm_band=3, lower=2, upper=98):
+        hist = np.asarray(hist, dtype=np.int64)
+        B, L = hist.shape
+        self.B, self.L = B, L
+        self.n = int(hist[0].sum())
+        levels = np.arange(L, dtype=F32)
+        self.norm = np.zeros((B, 3), F32)
+        self.norm_lut = np.zeros((B, L), F32)
+        self.center = np.zeros(B, F32)
+        self.scale = np.ones(B, np.float64)
+        self.x_lut = np.zeros((B, L), F32)
+        for b in range(B):
+            raw = LevelOrder(hist[b], levels)
+            lo, hi, den = norm_params(raw.percentile_scalar(lower), raw.percentile_scalar(upper))
+            self.norm[b] = (lo, hi, den)
+            f = normalize_levels(levels, lo, hi, den)
+            self.norm_lut[b] = f
+            nb = LevelOrder(hist[b], f)
+            self.center[b] = nb.median()
+            q = nb.nanpercentile_pair((25.0, 75.0))
+            s = np.float64(q[1] - q[0])
+            if s < 10 * np.finfo(np.float64).eps:  # sklearn _handle_zeros_in_scale
+                s = 1.0
+            self.scale[b] = s
+            # X -= center_ (float32); X /= scale_ (float64 divisor -> evaluated in float64, stored float32)
+            self.x_lut[b] = ((f - self.center[b]).astype(np.float64) / s).astype(F32)
+            if b == glcm_band:
+                lo2, hi2, den2 = norm_params(nb.percentile_scalar(lower), nb.percentile_scalar(upper))
+                self.qnorm = np.array([lo2, hi2, den2], F32)
+        if not hasattr(self, "qnorm"):
+            self.qnorm = np.array([0, 1, 1], F32)
+
+    def quant_lut(self, band, levels):
+        """(robust_normalize(norm) * (levels-1)).astype(uint8) per grey level (indices.py:265-268)."""
+        g = normalize_levels(self.norm_lut[band], *self.qnorm)
+        return (g * (levels - 1)).astype(np.uint8)
+
+
+def float_band_order(band):
+    """LevelOrder for an arbitrary float32 band (host np.unique; used only by the per-function drop-ins
+    when they are handed small float arrays that are not integer valued)."""
+    vals, counts = np.unique(np.asarray(band, dtype=F32).ravel(), return_counts=True)
+    return LevelOrder(counts, vals)
+
+
+def pca_from_moments(moments, n, n_components=None):
+    """sklearn PCA(svd_solver='covariance_eigh') from the Gram matrix and column sums
+    (sklearn/decomposition/_pca.py:587-640), evaluated in float64.
+
+    moments: float64 [B + B(B+1)/2] (column sums, then upper-triangular X^T X row-major).
+    Returns dict(mean, components, explained_variance, explained_variance_ratio, singular_values).
+    """
+    moments = np.asarray(moments, dtype=np.float64)
+    B = int((np.sqrt(9 + 8 * moments.size) - 3) / 2 + 0.5)
+    assert B + B * (B + 1) // 2 == moments.size
+    mean = moments[:B] / n
+    G = np.zeros((B, B))
+    G[np.triu_indices(B)] = moments[B:]
+    G = G + np.triu(G, 1).T
+    Cov = (G - n * np.outer(mean, mean)) / (n - 1)
+    w, v = np.linalg.eigh(Cov)
+    w, v = w[::-1].copy(), v[:, ::-1]
+    w[w < 0.0] = 0.0
+    Vt = v.T.copy()
+    # svd_flip(u_based_decision=False): largest-|.| entry of every component row is positive
+    idx = np.argmax(np.abs(Vt), axis=1)
+    signs = np.sign(Vt[np.arange(B), idx])
+    signs[signs == 0] = 1.0
+    Vt *= signs[:, None]
+    k = B if n_components is None else int(n_components)
+    total = w.sum()
+    return dict(mean=mean, components=Vt[:k], explained_variance=w[:k],
+                explained_variance_ratio=(w / total)[:k], singular_values=np.sqrt(w * (n - 1))[:k],
+                noise_variance=float(w[k:].mean()) if k < B else 0.0)

@@ -1,0 +1,330 @@
+"""Device-resident hot path: raster strip -> feature stack -> KMeans labels.
+
+Mirrors the data flow of scripts/2_feature_extraction.py:27-127 (robust_normalize x B, the seven indices,
+perform_pca, calculate_glcm_features on the NIR band, stack assembly) and of
+modules/features/extract.py:568-577 (MinMaxScaler + KMeans), but keeps everything in HBM:
+
+    raster (h, W, B) uint8/uint16, pixel interleaved            B*e bytes / pixel
+      K1 histograms  -> host order statistics (hoststats.RasterStats)
+      K2 fused normalise + 7 indices (+ quantised NIR)           planes 0..6 of the stack, q plane (1 B/px)
+      K3 PCA moments -> host eigh -> projection                  planes after the GLCM planes
+      K4 GLCM props (dense or tiled) -> bilinear upsample        planes 7..11
+      K5 KMeans assign/update passes over the first D planes
+
+The stack is planar float32: plane k at planes[k] (stride = padded pixel count).  Every producer also
+folds its output's min/max into a tracker so MinMaxScaler.fit costs no extra pass.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib, hoststats
+from .device import NO_TIMER, MinMaxTracker, StageTimer, hptr, ptr, require_cuda, stream_ptr
+from .dist import Comm, glcm_rows_needed, strip_bounds
+
+INDEX_NAMES = ("ndvi", "evi", "msavi", "ndwi", "mndwi", "ndbi", "bsi")       # RSX plane order (rsx.h)
+GLCM_NAMES = ("contrast", "dissimilarity", "homogeneity", "energy", "correlation")
+
+
+@dataclass
+class FeatureConfig:
+    band_map: Tuple[int, int, int, int, int] = (0, 1, 2, 3, 4)   # blue, green, red, nir, swir1 (scripts/2...:50-54)
+    evi: Tuple[float, float, float, float] = (1.0, 6.0, 7.5, 2.5)  # L, C1, C2, G (indices.py:73)
+    n_components: Optional[int] = None                           # perform_pca(n_components=None) -> all bands
+    glcm: bool = True
+    glcm_levels: int = 32                                        # indices.py:248-249 defaults
+    glcm_window: int = 21
+    glcm_step: int = 21
+    percentiles: Tuple[float, float] = (2, 98)
+
+
+@dataclass
+class FeatureResult:
+    planes: torch.Tensor                 # (P, stride) float32
+    names: List[str]
+    n_px: int
+    H: int                               # rows of this strip
+    W: int
+    stats: hoststats.RasterStats
+    pca: dict
+    minmax: MinMaxTracker
+    quant: Optional[torch.Tensor] = None
+    timings: dict = field(default_factory=dict)
+
+    def plane(self, name: str) -> torch.Tensor:
+        return self.planes[self.names.index(name), :self.n_px].view(self.H, self.W)
+
+
+def _pad4(n: int) -> int:
+    return (n + 31) // 32 * 32
+
+
+def extract_features(raster: torch.Tensor, cfg: FeatureConfig = FeatureConfig(), comm: Optional[Comm] = None,
+                     H_total: Optional[int] = None, bounds: Optional[Sequence[Tuple[int, int]]] = None,
+                     timer: StageTimer = NO_TIMER) -> FeatureResult:
+    """raster: (h, W, B) uint8 or uint16 CUDA tensor = this rank's row strip of an (H_total, W, B) image."""
+    require_cuda()
+    comm = comm or Comm()
+    assert raster.is_cuda and raster.is_contiguous() and raster.dim() == 3
+    h, W, B = raster.shape
+    H_total = H_total if H_total is not None else h
+    bounds = list(bounds) if bounds is not None else [(0, h)]
+    own = bounds[comm.rank]
+    assert own[1] - own[0] == h
+    n_px = h * W
+    n_global = H_total * W
+    is16 = raster.dtype in (getattr(torch, 'uint16', torch.int16), torch.int16)
+    assert is16 or raster.dtype == torch.uint8
+    sfx = "u16" if is16 else "u8"
+    L = 65536 if is16 else 256
+    dev = raster.device
+    st = stream_ptr()
+
+    # ---- K1 histograms (+ all-reduce), host order statistics
+    hist = torch.zeros((B, L), dtype=torch.int32, device=dev)
+    if n_px:
+        with timer("hist"):
+            _lib.call(f"rsx_hist_{sfx}", ptr(raster), n_px, B, ptr(hist), st)
+    hist64 = hist.to(torch.int64) & 0xFFFFFFFF      # the kernel's counters are uint32
+    comm.all_reduce(hist64)
+    stats = hoststats.RasterStats(hist64.cpu().numpy(), glcm_band=cfg.band_map[3],
+                                  lower=cfg.percentiles[0], upper=cfg.percentiles[1])
+
+    n_comp = B if cfg.n_components is None else int(cfg.n_components)
+    names = list(INDEX_NAMES) + (["glcm_" + g for g in GLCM_NAMES] if cfg.glcm else []) + [f"pc{i}" for i in range(n_comp)]
+    stride = _pad4(max(n_px, 1))
+    planes = torch.empty((len(names), stride), dtype=torch.float32, device=dev)
+    mm = MinMaxTracker(len(names), device=dev)
+    quant = torch.empty(_pad4(max(n_px, 1)), dtype=torch.uint8, device=dev) if cfg.glcm else None
+
+    # ---- K2 fused normalise + indices (+ quantised NIR)
+    band_map = np.asarray(cfg.band_map, dtype=np.int32)
+    norm = np.ascontiguousarray(stats.norm, dtype=np.float32)
+    evi = np.asarray(cfg.evi, dtype=np.float32)
+    qnorm = np.ascontiguousarray(stats.qnorm, dtype=np.float32)
+    if n_px:
+        with timer("indices"):
+            _lib.call(f"rsx_indices_fused_{sfx}", ptr(raster), n_px, B, hptr(band_map), hptr(norm), hptr(evi), ptr(planes), stride,
+                      mm.slot(0), ptr(quant), hptr(qnorm), cfg.glcm_levels, st)
+
+    # ---- K3 PCA: moments (+ all-reduce) -> eigh on the host -> projection
+    M = B + B * (B + 1) // 2
+    moments = torch.zeros(M, dtype=torch.float64, device=dev)
+    scratch = torch.empty(int(_lib.load().rsx_pca_scratch_elems(B)), dtype=torch.float64, device=dev)
+    center = np.ascontiguousarray(stats.center, dtype=np.float32)
+    scale = np.ascontiguousarray(stats.scale, dtype=np.float64)
+    lut = None
+    if not is16:
+        lut = torch.from_numpy(np.ascontiguousarray(stats.x_lut, dtype=np.float32)).to(dev)
+    if n_px:
+        with timer("pca_moments"):
+            if is16:
+                _lib.call("rsx_pca_moments_u16", ptr(raster), n_px, B, hptr(norm), hptr(center), hptr(scale), ptr(moments), ptr(scratch), st)
+            else:
+                _lib.call("rsx_pca_moments_u8", ptr(raster), n_px, B, ptr(lut), ptr(moments), ptr(scratch), st)
+    comm.all_reduce(moments)
+    pca = hoststats.pca_from_moments(moments.cpu().numpy(), n_global, n_comp)
+    comps = np.ascontiguousarray(pca["components"], dtype=np.float32)
+    mean32 = pca["mean"].astype(np.float32)
+    # sklearn: X_transformed -= mean_ @ components_.T, both float32 for float32 data
+    mean_proj = np.ascontiguousarray((mean32.reshape(1, -1) @ comps.T).ravel(), dtype=np.float32)
+    pc0 = len(names) - n_comp
+    if n_px:
+        with timer("pca_project"):
+            if is16:
+                _lib.call("rsx_pca_project_u16", ptr(raster), n_px, B, hptr(norm), hptr(center), hptr(scale), hptr(comps), hptr(mean_proj),
+                          n_comp, C.c_void_p(planes[pc0].data_ptr()), stride, mm.slot(pc0), st)
+            else:
+                _lib.call("rsx_pca_project_u8", ptr(raster), n_px, B, ptr(lut), hptr(comps), hptr(mean_proj), n_comp,
+                          C.c_void_p(planes[pc0].data_ptr()), stride, mm.slot(pc0), st)
+
+    # ---- K4 GLCM texture on the quantised NIR band (+ halo rows from the strips below/above), upsample
+    if cfg.glcm:
+        w, s = cfg.glcm_window, cfg.glcm_step
+        if H_total < w or W < w:
+            raise ValueError(f"GLCM window {w} larger than the {H_total}x{W} image")
+        out_rows_total = (H_total - w) // s + 1
+        out_cols = (W - w) // s + 1
+        needs = [glcm_rows_needed(b, H_total, w, s) for b in bounds]
+        (p0, p1), _ = needs[comm.rank]
+        q_local = quant[:n_px].view(h, W)
+        q_ext = comm.fetch_rows(q_local, bounds, [qr for _, qr in needs])
+        if p1 > p0:
+            props = torch.empty((5, _pad4((p1 - p0) * out_cols)), dtype=torch.float32, device=dev)
+            with timer("glcm_props"):
+                _lib.call("rsx_glcm_props", ptr(q_ext), q_ext.shape[0], W, cfg.glcm_levels, w, s, p1 - p0, out_cols, ptr(props),
+                          props.shape[1], st)
+            with timer("glcm_resize"):
+                _lib.call("rsx_resize_bilinear_f32", ptr(props), out_rows_total, out_cols, p0, p1 - p0, props.shape[1],
+                          C.c_void_p(planes[7].data_ptr()), H_total, W, own[0], h, stride, 5, mm.slot(7), st)
+    return FeatureResult(planes=planes, names=names, n_px=n_px, H=h, W=W, stats=stats, pca=pca, minmax=mm, quant=quant)
+
+
+# ============================================================================================ KMeans
+def draw_init_indices(n: int, k: int, seed: int) -> np.ndarray:
+    """k distinct pixel indices in [0, n), reproducible, without materialising a permutation of n."""
+    rng = np.random.default_rng(seed)
+    seen, out = set(), []
+    while len(out) < k:
+        v = int(rng.integers(0, n))
+        if v not in seen:
+            seen.add(v)
+            out.append(v)
+    return np.asarray(out, dtype=np.int64)
+
+
+def minmax_scale_params(fmin: np.ndarray, fmax: np.ndarray):
+    """MinMaxScaler.fit in float64 (sklearn/preprocessing/_data.py:527-541)."""
+    fmin, fmax = np.asarray(fmin, np.float64), np.asarray(fmax, np.float64)
+    rng = fmax - fmin
+    rng[rng < 10 * np.finfo(np.float64).eps] = 1.0
+    scale = 1.0 / rng
+    return scale, 0.0 - fmin * scale
+
+
+@dataclass
+class KMeansResult:
+    labels: torch.Tensor          # (n_px,) int32 on the device (this strip)
+    centroids: np.ndarray         # (K, D) float64, MinMax-scaled coordinates
+    inertia: float
+    n_iter: int
+    near_ties: int
+    shift_sq: float
+
+
+class DeviceKMeans:
+    """Lloyd iterations on a planar float32 stack that stays in HBM."""
+
+    def __init__(self, planes: torch.Tensor, n_px: int, D: int, K: int, feat_min, feat_max, n_global: int, row_len: int,
+                 comm: Optional[Comm] = None, timer: StageTimer = NO_TIMER):
+        require_cuda()
+        self.comm = comm or Comm()
+        self.timer = timer
+        self.planes, self.n_px, self.D, self.K = planes, int(n_px), int(D), int(K)
+        self.stride = planes.stride(0)
+        self.row_len = int(row_len)
+        self.n_global = int(n_global)
+        self.fmin = np.ascontiguousarray(feat_min, dtype=np.float64)
+        self.fmax = np.ascontiguousarray(feat_max, dtype=np.float64)
+        self.scale, self.min_ = minmax_scale_params(self.fmin, self.fmax)
+        dev = planes.device
+        self.state = torch.zeros(int(_lib.load().rsx_kmeans_state_bytes()), dtype=torch.uint8, device=dev)
+        self.acc = torch.zeros(K * D + K + 1, dtype=torch.int64, device=dev)
+        self.inertia = torch.zeros(1, dtype=torch.float64, device=dev)
+
+    def scale_rows(self, raw_rows: np.ndarray) -> np.ndarray:
+        """MinMaxScaler.transform of raw feature rows in float64: X*scale + min_."""
+        return np.asarray(raw_rows, np.float64) * self.scale + self.min_
+
+    def gather_rows(self, global_idx: np.ndarray, first_px: int) -> np.ndarray:
+        """Raw float32 feature rows of the given GLOBAL pixel indices (all-reduced so every rank has all of them)."""
+        rows = torch.zeros((len(global_idx), self.D), dtype=torch.float64, device=self.planes.device)
+        loc = torch.as_tensor(global_idx - first_px, device=self.planes.device)
+        mine = (loc >= 0) & (loc < self.n_px)
+        if bool(mine.any()):
+            sel = loc[mine]
+            rows[mine] = self.planes[:self.D, :][:, sel].t().to(torch.float64)
+        self.comm.all_reduce(rows)
+        return rows.cpu().numpy()
+
+    def setup(self, init_centroids_scaled: np.ndarray, mean_scaled: Optional[np.ndarray] = None):
+        c0 = np.ascontiguousarray(init_centroids_scaled, dtype=np.float64)
+        assert c0.shape == (self.K, self.D)
+        # any centring origin gives the same labels in exact arithmetic; 0.5 minimises the fp32 rounding bound
+        mu = np.full(self.D, 0.5) if mean_scaled is None else np.ascontiguousarray(mean_scaled, dtype=np.float64)
+        self.acc.zero_()
+        _lib.call("rsx_kmeans_setup", ptr(self.state), self.D, self.K, hptr(self.fmin), hptr(self.fmax), hptr(mu), hptr(c0),
+                  self.n_global, stream_ptr())
+
+    def step(self):
+        """One fused assign + partial-sum pass, the all-reduce of K*(D+1) integers, one centroid update."""
+        if self.n_px:
+            with self.timer("kmeans_assign"):
+                _lib.call("rsx_kmeans_assign", ptr(self.planes), self.stride, self.n_px, self.row_len, ptr(self.state), ptr(self.acc),
+                          None, None, None, 1, self.D, self.K, stream_ptr())
+        self.comm.all_reduce(self.acc)
+        with self.timer("kmeans_update"):
+            _lib.call("rsx_kmeans_update", ptr(self.state), ptr(self.acc), stream_ptr())
+
+    def finish(self, labels_i32: bool = True):
+        """The extra assignment pass of sklearn (_kmeans.py:742-754) + inertia."""
+        dev = self.planes.device
+        lab = torch.empty((self.n_px + 3) // 4 * 4, dtype=torch.int32 if labels_i32 else torch.uint8, device=dev)
+        self.inertia.zero_()
+        if self.n_px:
+            with self.timer("kmeans_final"):
+                _lib.call("rsx_kmeans_assign", ptr(self.planes), self.stride, self.n_px, self.row_len, ptr(self.state), ptr(self.acc),
+                          None if labels_i32 else ptr(lab), ptr(lab) if labels_i32 else None, ptr(self.inertia), 0, self.D, self.K,
+                          stream_ptr())
+        self.comm.all_reduce(self.inertia)
+        return lab[:self.n_px]
+
+    def read(self):
+        cent = np.zeros((self.K, self.D), np.float64)
+        shift = np.zeros(1, np.float64)
+        empty = np.zeros(1, np.int32)
+        _lib.call("rsx_kmeans_read", ptr(self.state), hptr(cent), hptr(shift), hptr(empty), stream_ptr())
+        return cent, float(shift[0]), int(empty[0])
+
+    def fit(self, init_centroids_scaled: np.ndarray, n_iter: int, labels_i32: bool = True) -> KMeansResult:
+        self.setup(init_centroids_scaled)
+        for _ in range(n_iter):
+            self.step()
+        labels = self.finish(labels_i32)
+        cent, shift, empty = self.read()
+        ties = self.acc[-1:].clone()
+        self.comm.all_reduce(ties)
+        if empty:
+            raise _lib.RsxError(f"KMeans: {empty} empty cluster(s) met; empty-cluster relocation "
+                                "(sklearn _k_means_common.pyx:167-211) is not implemented on the device")
+        return KMeansResult(labels=labels, centroids=cent, inertia=float(self.inertia.item()), n_iter=n_iter,
+                            near_ties=int(ties.item()), shift_sq=shift)
+
+
+def kmeans_on_features(fr: FeatureResult, D: int, K: int, n_iter: int, seed: int, comm: Optional[Comm] = None,
+                       H_total: Optional[int] = None, first_row: int = 0, labels_i32: bool = True, timer: StageTimer = NO_TIMER):
+    """Benchmark protocol: MinMax from the fused trackers, K initial centroids = seeded pixel
+    rows of the scaled stack, exactly n_iter update passes, then the final assignment + inertia."""
+    comm = comm or Comm()
+    H_total = H_total if H_total is not None else fr.H
+    n_global = H_total * fr.W
+    mn, mx = fr.minmax.read()
+    tmn = torch.from_numpy(mn[:D].copy()).to(fr.planes.device)
+    tmx = torch.from_numpy(mx[:D].copy()).to(fr.planes.device)
+    comm.all_reduce(tmn, "min")
+    comm.all_reduce(tmx, "max")
+    km = DeviceKMeans(fr.planes, fr.n_px, D, K, tmn.cpu().numpy(), tmx.cpu().numpy(), n_global, fr.W, comm, timer)
+    idx = draw_init_indices(n_global, K, seed)
+    raw = km.gather_rows(idx, first_row * fr.W)
+    c0 = km.scale_rows(raw)
+    res = km.fit(c0, n_iter, labels_i32)
+    return res, km, c0
+
+
+# ============================================================================================ public entry: host raster -> labels
+def segment_raster(raster_host: np.ndarray, cfg: FeatureConfig = FeatureConfig(), n_clusters: int = 8, n_iter: int = 20, seed: int = 42,
+                   stack_depth: Optional[int] = None, comm: Optional[Comm] = None, H_total: Optional[int] = None,
+                   bounds: Optional[Sequence[Tuple[int, int]]] = None, timer: StageTimer = NO_TIMER, pinned: Optional[torch.Tensor] = None):
+    """End-to-end call with HOST buffers: (h, W, B) uint8/uint16 numpy strip in, (h, W) int32 numpy labels out.
+
+    Copies the strip to the device (pinned staging), runs extract_features + the fixed-iteration KMeans protocol,
+    copies the labels back.  Returns (labels, KMeansResult, FeatureResult)."""
+    require_cuda()
+    comm = comm or Comm()
+    if pinned is None:
+        a = np.ascontiguousarray(raster_host)
+        if a.dtype == np.uint16:
+            a = a.view(np.int16)
+        pinned = torch.from_numpy(a).pin_memory()
+    dev_raster = pinned.cuda(non_blocking=True)
+    fr = extract_features(dev_raster, cfg, comm, H_total, bounds, timer)
+    D = stack_depth if stack_depth is not None else (13 if cfg.glcm else 7 + min(6, len(fr.names) - 7))
+    first_row = bounds[comm.rank][0] if bounds is not None else 0
+    res, km, c0 = kmeans_on_features(fr, D, n_clusters, n_iter, seed, comm, H_total, first_row, True, timer)
+    labels = res.labels.view(fr.H, fr.W).cpu().numpy()
+    return labels, res, fr

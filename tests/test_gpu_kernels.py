@@ -1,0 +1,189 @@
+"""GPU parity tests, kernel by kernel, through the C ABI (librsx.so) against the CPU oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def rsx():
+    import torch
+    from rs_image_segmentation_b200 import _lib, device
+    device.require_cuda()
+    return _lib
+
+
+def _dev(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _hist_np(r, L):
+    B = r.shape[-1]
+    flat = r.reshape(-1, B)
+    return np.stack([np.bincount(flat[:, b], minlength=L) for b in range(B)])
+
+
+# ------------------------------------------------------------------------------------------ K1
+@pytest.mark.parametrize("n_px", [1, 5, 517, 4096, 4096 * 3 + 517, 300 * 211])
+@pytest.mark.parametrize("B", [7, 5, 8])
+def test_hist_u8(rsx, n_px, B):
+    import torch
+    from rs_image_segmentation_b200.device import ptr, stream_ptr
+    rng = np.random.default_rng(n_px + B)
+    r = rng.integers(0, 256, size=(n_px, B), dtype=np.uint8)
+    r[: n_px // 2, 0] = 7                     # heavy same-bin contention
+    d = _dev(r)
+    h = torch.zeros((B, 256), dtype=torch.int32, device="cuda")
+    rsx.call("rsx_hist_u8", ptr(d), n_px, B, ptr(h), stream_ptr())
+    assert np.array_equal(h.cpu().numpy(), _hist_np(r, 256))
+
+
+@pytest.mark.parametrize("n_px", [3, 2048, 2048 * 5 + 77])
+def test_hist_u16(rsx, n_px):
+    import torch
+    from rs_image_segmentation_b200.device import ptr, stream_ptr
+    rng = np.random.default_rng(n_px)
+    r = rng.integers(0, 10001, size=(n_px, 13)).astype(np.uint16)
+    d = _dev(r.view(np.int16))
+    h = torch.zeros((13, 65536), dtype=torch.int32, device="cuda")
+    rsx.call("rsx_hist_u16", ptr(d), n_px, 13, ptr(h), stream_ptr())
+    assert np.array_equal(h.cpu().numpy(), _hist_np(r, 65536))
+
+
+# ------------------------------------------------------------------------------------------ planar element-wise drop-ins
+def test_planar_ops_bit_exact(rsx):
+    import torch
+    from oracle import features as of
+    from rs_image_segmentation_b200.device import ptr, stream_ptr
+    rng = np.random.default_rng(0)
+    n = 4096 * 2 + 3
+    a, b, c, d = (rng.random(n).astype(np.float32) for _ in range(4))
+    a[:10] = 0
+    b[:10] = 0
+    A, Bt, Ct, Dt = map(_dev, (a, b, c, d))
+    out = torch.empty(n + 1, dtype=torch.float32, device="cuda")[:n]
+    out = torch.empty(n, dtype=torch.float32, device="cuda")
+    st = stream_ptr()
+    rsx.call("rsx_index_ratio_f32", ptr(A), ptr(Bt), n, ptr(out), st)
+    assert np.array_equal(out.cpu().numpy(), of.ndvi(a, b))
+    rsx.call("rsx_index_evi_f32", ptr(A), ptr(Bt), ptr(Ct), n, 1.0, 6.0, 7.5, 2.5, ptr(out), st)
+    assert np.array_equal(out.cpu().numpy(), of.evi(a, b, c))
+    rsx.call("rsx_index_msavi_f32", ptr(A), ptr(Bt), n, ptr(out), st)
+    assert np.array_equal(out.cpu().numpy(), of.msavi(a, b), equal_nan=True)
+    rsx.call("rsx_index_bsi_f32", ptr(A), ptr(Bt), ptr(Ct), ptr(Dt), n, ptr(out), st)
+    assert np.array_equal(out.cpu().numpy(), of.bsi(a, b, c, d))
+    x = (rng.random(n) * 255).astype(np.float32)
+    lo, hi = np.percentile(x, 2), np.percentile(x, 98)
+    den = np.float32(hi - lo + 1e-10)
+    rsx.call("rsx_normalize_f32", ptr(_dev(x)), n, float(lo), float(hi), float(den), ptr(out), st)
+    assert np.array_equal(out.cpu().numpy(), of.robust_normalize(x))
+
+
+# ------------------------------------------------------------------------------------------ GLCM
+DOC_IMAGE = np.array([[0, 0, 1, 1], [0, 0, 1, 1], [0, 2, 2, 2], [2, 2, 3, 3]], dtype=np.uint8)
+DOC_COUNTS = [
+    [[2, 2, 1, 0], [0, 2, 0, 0], [0, 0, 3, 1], [0, 0, 0, 1]],
+    [[1, 1, 3, 0], [0, 1, 1, 0], [0, 0, 0, 2], [0, 0, 0, 0]],
+    [[3, 0, 2, 0], [0, 2, 2, 0], [0, 0, 1, 2], [0, 0, 0, 0]],
+    [[2, 0, 0, 0], [1, 1, 2, 0], [0, 0, 2, 1], [0, 0, 0, 0]],
+]
+
+
+def _counts(rsx, q, L, win, anchors):
+    import torch
+    from rs_image_segmentation_b200.device import ptr, stream_ptr
+    H, W = q.shape
+    an = _dev(np.asarray(anchors, dtype=np.int32))
+    out = torch.empty((len(anchors), 4, L, L), dtype=torch.int32, device="cuda")
+    rsx.call("rsx_glcm_counts", ptr(_dev(q)), H, W, L, win, ptr(an), len(anchors), ptr(out), stream_ptr())
+    return out.cpu().numpy().astype(np.uint32)
+
+
+def test_glcm_counts_docstring_example(rsx):
+    c = _counts(rsx, DOC_IMAGE, 4, 4, [(0, 0)])
+    for a in range(4):
+        assert c[0, a].tolist() == DOC_COUNTS[a]
+
+
+def _texture_image(H, W, L, seed):
+    rng = np.random.default_rng(seed)
+    base = rng.integers(0, L, size=(H // 6 + 2, W // 6 + 2)).repeat(6, 0).repeat(6, 1)[:H, :W]
+    return np.clip(base + rng.integers(-2, 3, size=(H, W)), 0, L - 1).astype(np.uint8)
+
+
+@pytest.mark.parametrize("L,win", [(32, 7), (32, 21), (16, 5), (64, 11)])
+def test_glcm_counts_bit_exact(rsx, L, win):
+    from oracle import glcm as og
+    q = _texture_image(60, 70, L, L + win)
+    ref = og.counts_map_c(q, L, win, 1)
+    rng = np.random.default_rng(1)
+    anchors = [(int(rng.integers(0, 60 - win + 1)), int(rng.integers(0, 70 - win + 1))) for _ in range(25)] + [(0, 0), (60 - win, 70 - win)]
+    got = _counts(rsx, q, L, win, anchors)
+    for k, (i, j) in enumerate(anchors):
+        assert np.array_equal(got[k], ref[i, j]), (i, j)
+
+
+def _props(rsx, q, L, win, step):
+    import torch
+    from rs_image_segmentation_b200.device import ptr, stream_ptr
+    H, W = q.shape
+    oh, ow = (H - win) // step + 1, (W - win) // step + 1
+    stride = (oh * ow + 31) // 32 * 32
+    out = torch.zeros((5, stride), dtype=torch.float32, device="cuda")
+    rsx.call("rsx_glcm_props", ptr(_dev(q)), H, W, L, win, step, oh, ow, ptr(out), stride, stream_ptr())
+    return out[:, : oh * ow].reshape(5, oh, ow).cpu().numpy()
+
+
+@pytest.mark.parametrize("L,win,step", [(32, 7, 1), (32, 21, 21), (16, 5, 1), (64, 11, 1), (32, 11, 1), (64, 5, 1),
+                                        (16, 11, 1), (32, 5, 3), (32, 7, 7), (128, 9, 4)])
+def test_glcm_props_match_oracle(rsx, L, win, step):
+    from oracle import glcm as og
+    q = _texture_image(97, 141, L, L * win + step)
+    q[:30, :40] = 5                                 # constant area: correlation == 1 branch
+    ref = og.props_map_c(q, L, win, step)
+    got = _props(rsx, q, L, win, step)
+    assert got.shape == ref.shape
+    np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-6)
+
+
+def test_glcm_props_uniform_noise_worst_case(rsx):
+    from oracle import glcm as og
+    q = np.random.default_rng(5).integers(0, 32, size=(64, 200)).astype(np.uint8)
+    np.testing.assert_allclose(_props(rsx, q, 32, 7, 1), og.props_map_c(q, 32, 7, 1), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("sh,dh", [((28, 28), (600, 600)), ((91, 135), (97, 141)), ((5, 7), (64, 96)), ((33, 17), (33, 17))])
+def test_resize_matches_cv2(rsx, sh, dh):
+    import cv2
+    import torch
+    from rs_image_segmentation_b200.device import ptr, stream_ptr
+    rng = np.random.default_rng(sh[0])
+    src = rng.random((3,) + sh).astype(np.float32) * 10
+    d = torch.empty((3, dh[0] * dh[1]), dtype=torch.float32, device="cuda")
+    rsx.call("rsx_resize_bilinear_f32", ptr(_dev(src)), sh[0], sh[1], 0, sh[0], sh[0] * sh[1], ptr(d), dh[0], dh[1], 0, dh[0],
+             dh[0] * dh[1], 3, None, stream_ptr())
+    got = d.reshape(3, *dh).cpu().numpy()
+    for k in range(3):
+        ref = cv2.resize(src[k], (dh[1], dh[0]), interpolation=cv2.INTER_LINEAR)
+        np.testing.assert_allclose(got[k], ref, rtol=1e-5, atol=1e-5)
+
+
+def test_resize_strip_equals_whole(rsx):
+    import torch
+    from rs_image_segmentation_b200.device import ptr, stream_ptr
+    from rs_image_segmentation_b200.dist import resize_src_rows
+    rng = np.random.default_rng(2)
+    src = rng.random((1, 40, 30)).astype(np.float32)
+    H, W = 173, 61
+    whole = torch.empty((1, H * W), dtype=torch.float32, device="cuda")
+    rsx.call("rsx_resize_bilinear_f32", ptr(_dev(src)), 40, 30, 0, 40, 1200, ptr(whole), H, W, 0, H, H * W, 1, None, stream_ptr())
+    whole = whole.reshape(H, W).cpu().numpy()
+    for r0, r1 in ((0, 60), (60, 120), (120, 173)):
+        a, b = resize_src_rows(r0, r1, H, 40)
+        part = torch.empty((1, (r1 - r0) * W), dtype=torch.float32, device="cuda")
+        rsx.call("rsx_resize_bilinear_f32", ptr(_dev(src[:, a:b])), 40, 30, a, b - a, (b - a) * 30, ptr(part), H, W, r0, r1 - r0,
+                 (r1 - r0) * W, 1, None, stream_ptr())
+        assert np.array_equal(part.reshape(r1 - r0, W).cpu().numpy(), whole[r0:r1])

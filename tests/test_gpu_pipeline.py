@@ -1,0 +1,158 @@
+"""GPU parity tests for the fused path: raster -> feature stack -> KMeans labels, against the oracle
+(and against the reference outputs recorded in tests/golden/aa_crop.npz)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def P():
+    from rs_image_segmentation_b200 import device, pipeline
+    device.require_cuda()
+    return pipeline
+
+
+def _to_bip(planar_u8):
+    return np.ascontiguousarray(np.moveaxis(planar_u8, 0, -1))
+
+
+def _oracle_features(bip, cfg):
+    """Oracle feature maps of a (H, W, B) integer raster, in pipeline plane order."""
+    from oracle import features as of
+    from oracle import glcm as og
+    bands = [bip[:, :, b].astype(np.float32) for b in range(bip.shape[2])]
+    nb = [of.robust_normalize(b) for b in bands]
+    bm = cfg.band_map
+    ix = of.all_indices([nb[bm[0]], nb[bm[1]], nb[bm[2]], nb[bm[3]], nb[bm[4]]])
+    out = {k: ix[k] for k in of.INDEX_ORDER}
+    if cfg.glcm:
+        g = og.glcm_features(nb[bm[3]], cfg.glcm_levels, cfg.glcm_window, cfg.glcm_step)
+        out.update({"glcm_" + k: v for k, v in g.items()})
+        out["_q"] = og.quantize(nb[bm[3]], cfg.glcm_levels)
+    pcs, evr, model = of.perform_pca(nb, n_components=cfg.n_components)
+    for i, p in enumerate(pcs):
+        out[f"pc{i}"] = p
+    out["_evr"], out["_components"] = evr, model.components_
+    return out
+
+
+def _check_features(fr, ref, cfg, pc_tol=2e-4):
+    from oracle import features as of
+    for k in of.INDEX_ORDER:
+        assert np.array_equal(fr.plane(k).cpu().numpy(), ref[k], equal_nan=True), k       # bit exact
+    if cfg.glcm:
+        assert np.array_equal(fr.quant[:fr.n_px].view(fr.H, fr.W).cpu().numpy(), ref["_q"])  # bit exact
+        for k in ("contrast", "dissimilarity", "homogeneity", "energy", "correlation"):
+            np.testing.assert_allclose(fr.plane("glcm_" + k).cpu().numpy(), ref["glcm_" + k], rtol=1e-5, atol=1e-6, err_msg=k)
+    comps = fr.pca["components"]
+    for i in range(comps.shape[0]):
+        r = ref["_components"][i]
+        cos = abs(float(np.dot(comps[i], r) / np.linalg.norm(comps[i]) / np.linalg.norm(r)))
+        assert cos > 1 - 1e-6, (i, cos)
+        sgn = np.sign(np.dot(comps[i], r))
+        got = fr.plane(f"pc{i}").cpu().numpy() * sgn
+        scale = max(1.0, float(np.abs(ref[f"pc{i}"]).max()))
+        assert np.abs(got - ref[f"pc{i}"]).max() <= pc_tol * scale, i
+    np.testing.assert_allclose(fr.pca["explained_variance_ratio"], ref["_evr"], rtol=2e-4)
+
+
+def _mm_check(fr):
+    mn, mx = fr.minmax.read()
+    for i, name in enumerate(fr.names):
+        p = fr.plane(name).cpu().numpy()
+        assert mn[i] == np.nanmin(p) and mx[i] == np.nanmax(p), name
+
+
+def test_golden_crop_features(P, aa_crop):
+    import torch
+    bip = _to_bip(aa_crop["stage1_u8"])
+    cfg = P.FeatureConfig(glcm_window=21, glcm_step=21)
+    fr = P.extract_features(torch.from_numpy(bip).cuda(), cfg)
+    # reference outputs (golden): indices, quantised NIR and PCA maps produced by the reference's own functions
+    for k in P.INDEX_NAMES:
+        assert np.array_equal(fr.plane(k).cpu().numpy(), aa_crop["ix_" + k]), k
+    assert np.array_equal(fr.quant[:fr.n_px].view(fr.H, fr.W).cpu().numpy(), aa_crop["q32"])
+    for i in range(7):
+        r = aa_crop["pca_components"][i]
+        c = fr.pca["components"][i]
+        sgn = np.sign(np.dot(c, r))
+        assert abs(np.dot(c, r)) > 1 - 1e-6
+        assert np.abs(fr.plane(f"pc{i}").cpu().numpy() * sgn - aa_crop["pca_maps"][i]).max() < 2e-4
+    _check_features(fr, _oracle_features(bip, cfg), cfg)
+    _mm_check(fr)
+
+
+@pytest.mark.parametrize("H,W,win,step,seed", [(97, 141, 7, 1, 1), (233, 310, 21, 21, 2), (64, 4096 // 64 + 3, 5, 1, 3), (130, 257, 11, 1, 4)])
+def test_synthetic_u8_features(P, H, W, win, step, seed):
+    import torch
+    from rs_image_segmentation_b200.synth import synth_raster_numpy
+    bip = synth_raster_numpy(H, W, 7, np.uint8, seed, cell=16)
+    cfg = P.FeatureConfig(glcm_window=win, glcm_step=step)
+    fr = P.extract_features(torch.from_numpy(bip).cuda(), cfg)
+    _check_features(fr, _oracle_features(bip, cfg), cfg)
+    _mm_check(fr)
+
+
+def test_synthetic_u16_13band_features(P):
+    import torch
+    from rs_image_segmentation_b200.synth import synth_raster_numpy
+    bip = synth_raster_numpy(150, 203, 13, np.uint16, 7, cell=16)
+    cfg = P.FeatureConfig(band_map=(1, 2, 3, 7, 11), n_components=6, glcm=False)
+    fr = P.extract_features(torch.from_numpy(bip.view(np.int16)).cuda(), cfg)
+    _check_features(fr, _oracle_features(bip, cfg), cfg)
+    _mm_check(fr)
+
+
+def _kmeans_oracle(stack_nd, c0_scaled, n_iter, fmin, fmax):
+    from oracle import kmeans as ok
+    X = stack_nd.astype(np.float64)
+    rng_ = fmax.astype(np.float64) - fmin.astype(np.float64)
+    rng_[rng_ < 10 * np.finfo(np.float64).eps] = 1.0
+    Xs = ok.minmax_scale(X)
+    return ok.lloyd_fixed(Xs, c0_scaled, n_iter), Xs
+
+
+@pytest.mark.parametrize("K,n_iter,H,W", [(8, 5, 120, 160), (5, 20, 97, 141), (32, 6, 150, 200), (3, 1, 33, 35)])
+def test_kmeans_labels_bit_exact(P, K, n_iter, H, W):
+    import torch
+    from rs_image_segmentation_b200.synth import synth_raster_numpy
+    bip = synth_raster_numpy(H, W, 7, np.uint8, K + n_iter, cell=16)
+    cfg = P.FeatureConfig(glcm_window=7, glcm_step=1)
+    fr = P.extract_features(torch.from_numpy(bip).cuda(), cfg)
+    D = 13
+    res, km, c0 = P.kmeans_on_features(fr, D, K, n_iter, seed=11)
+    stack = fr.planes[:D, :fr.n_px].t().contiguous().cpu().numpy()           # (N, D) float32, the GPU's own stack
+    (lab, cent, inertia, n_run), Xs = _kmeans_oracle(stack, c0, n_iter, km.fmin, km.fmax)
+    assert n_run == n_iter
+    assert np.allclose(Xs[P.draw_init_indices(H * W, K, 11)], c0, rtol=0, atol=1e-15)
+    got = res.labels.cpu().numpy()
+    assert got.dtype == np.int32
+    assert np.array_equal(got, lab), f"{(got != lab).sum()} labels differ"
+    np.testing.assert_allclose(res.centroids, cent, rtol=0, atol=1e-9)
+    assert abs(res.inertia - inertia) <= 1e-5 * inertia
+
+
+def test_kmeans_partition_invariance(P):
+    """Integer partial sums: assigning two halves separately and adding the accumulators equals one pass."""
+    import torch
+    from rs_image_segmentation_b200 import _lib
+    from rs_image_segmentation_b200.device import ptr, stream_ptr
+    from rs_image_segmentation_b200.synth import synth_raster_numpy
+    bip = synth_raster_numpy(200, 300, 7, np.uint8, 3, cell=16)
+    fr = P.extract_features(torch.from_numpy(bip).cuda(), P.FeatureConfig(glcm=False))
+    D, K = 8, 6
+    mn, mx = fr.minmax.read()
+    km = P.DeviceKMeans(fr.planes, fr.n_px, D, K, mn[:D], mx[:D], fr.n_px, fr.W)
+    c0 = km.scale_rows(km.gather_rows(P.draw_init_indices(fr.n_px, K, 1), 0))
+    km.setup(c0)
+    _lib.call("rsx_kmeans_assign", ptr(fr.planes), km.stride, fr.n_px, fr.W, ptr(km.state), ptr(km.acc), None, None, None, 1, D, K, stream_ptr())
+    whole = km.acc.clone()
+    km.acc.zero_()
+    half = (fr.n_px // 2) // 4 * 4 + 4
+    import ctypes as C
+    _lib.call("rsx_kmeans_assign", ptr(fr.planes), km.stride, half, 64, ptr(km.state), ptr(km.acc), None, None, None, 1, D, K, stream_ptr())
+    _lib.call("rsx_kmeans_assign", C.c_void_p(fr.planes.data_ptr() + 4 * half), km.stride, fr.n_px - half, 1000, ptr(km.state), ptr(km.acc),
+              None, None, None, 1, D, K, stream_ptr())
+    assert torch.equal(whole[:K * D + K], km.acc[:K * D + K])
+    assert int(whole[K * D:K * D + K].sum()) == fr.n_px
