@@ -89,8 +89,12 @@ def all_indices(nb):
 
 
 # --------------------------------------------------------------------------- a6
-def perform_pca(bands, n_components=None, use_robust_scaling=True):
-    """indices.py:205-246 - (N,B) float32 matrix -> RobustScaler -> sklearn PCA."""
+def perform_pca(bands, n_components=None, use_robust_scaling=True, promote=False):
+    """indices.py:205-246 - (N,B) float32 matrix -> RobustScaler -> sklearn PCA.
+
+    promote=True runs the PCA itself on the float64 promotion of the (float32) scaled matrix: the same
+    mathematical object without the float32 Gram-matrix noise of sklearn's covariance_eigh solver, which
+    for the minor components (tiny eigenvalue gaps) exceeds the 1e-5 parity bar on its own."""
     from sklearn.decomposition import PCA
     from sklearn.preprocessing import RobustScaler
 
@@ -100,6 +104,8 @@ def perform_pca(bands, n_components=None, use_robust_scaling=True):
         X = RobustScaler().fit_transform(X)
     else:
         X = (X - X.min(axis=0)) / (X.max(axis=0) - X.min(axis=0) + 1e-10)
+    if promote:
+        X = X.astype(np.float64)
     model = PCA(n_components=n_components)
     Y = model.fit_transform(X)
     return [Y[:, i].reshape(h, w) for i in range(Y.shape[1])], model.explained_variance_ratio_, model

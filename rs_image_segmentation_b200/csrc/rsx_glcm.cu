@@ -325,9 +325,11 @@ extern "C" int rsx_glcm_counts(const uint8_t* d_q, int H, int W, int levels, int
 }
 
 // ----------------------------------------------------------------------------- cv2.resize(INTER_LINEAR) for float32 planes
-// OpenCV semantics (modules/imgproc/src/resize.cpp): scale = 1/(dst/src) in double; fx = (float)((dx+0.5)*scale-0.5);
-// sx = floor(fx); fx -= sx; horizontally sx<0 -> (0, fx=0), sx>=src_w-1 -> (src_w-1, fx=0); vertically the two rows
-// are clamped to [0, src_h-1] and the weights (1-fy, fy) are kept; horizontal pass first, then vertical.
+// The oracle is cv2.resize as shipped in opencv-python (built with Intel IPP, which handles float32 linear resize).
+// Its arithmetic, established by probing it (DESIGN.md "cv2.resize parity"): source coordinate c = (d+0.5)*scale-0.5
+// in DOUBLE with scale = 1/(dst/src); s = floor(c); weight f = (float)(c - s); the two taps are clamped to the image
+// (replicated border); horizontal pass first, then vertical, each as fma(q - p, f, p).
+// (OpenCV's own non-IPP path rounds c to float before taking the fraction and differs from this by ~6e-5 relative.)
 __global__ void __launch_bounds__(256) resize_bilinear_kernel(const float* __restrict__ src, int src_h, int src_w, int src_row0, int src_rows_avail,
                                                               int64_t src_stride, float* __restrict__ dst, int dst_w, int dst_row0, int dst_rows,
                                                               int64_t dst_stride, double scale_x, double scale_y, uint32_t* __restrict__ minmax) {
@@ -337,24 +339,28 @@ __global__ void __launch_bounds__(256) resize_bilinear_kernel(const float* __res
     float mn = INFINITY, mx = -INFINITY;
     const int dx = blockIdx.x * blockDim.x + threadIdx.x;
     if (dx < dst_w) {
-        float fx = (float)((dx + 0.5) * scale_x - 0.5);
-        int sx = (int)floorf(fx);
-        fx -= (float)sx;
-        if (sx < 0) sx = 0, fx = 0.f;
-        if (sx >= src_w - 1) sx = src_w - 1, fx = 0.f;
-        const int sx1 = min(sx + 1, src_w - 1);
-        const float a0 = 1.f - fx, a1 = fx;
+        const double cx = (dx + 0.5) * scale_x - 0.5;
+        const double fxd = floor(cx);
+        const float fx = (float)(cx - fxd);
+        const int sx = (int)fxd;
+        const int x0 = min(max(sx, 0), src_w - 1), x1 = min(max(sx + 1, 0), src_w - 1);
         for (int ly = blockIdx.y; ly < dst_rows; ly += gridDim.y) {
             const int dy = dst_row0 + ly;
-            float fy = (float)((dy + 0.5) * scale_y - 0.5);
-            int sy = (int)floorf(fy);
-            fy -= (float)sy;
+            const double cy = (dy + 0.5) * scale_y - 0.5;
+            const double fyd = floor(cy);
+            const float fy = (float)(cy - fyd);
+            const int sy = (int)fyd;
             const int y0 = min(max(sy, 0), src_h - 1) - src_row0, y1 = min(max(sy + 1, 0), src_h - 1) - src_row0;
-            const float b0 = 1.f - fy, b1 = fy;
             float r0 = 0.f, r1 = 0.f;
-            if (y0 >= 0 && y0 < src_rows_avail) r0 = f_add(f_mul(sp[(int64_t)y0 * src_w + sx], a0), f_mul(sp[(int64_t)y0 * src_w + sx1], a1));
-            if (y1 >= 0 && y1 < src_rows_avail) r1 = f_add(f_mul(sp[(int64_t)y1 * src_w + sx], a0), f_mul(sp[(int64_t)y1 * src_w + sx1], a1));
-            const float v = f_add(f_mul(r0, b0), f_mul(r1, b1));
+            if (y0 >= 0 && y0 < src_rows_avail) {
+                const float p = sp[(int64_t)y0 * src_w + x0], q = sp[(int64_t)y0 * src_w + x1];
+                r0 = fmaf(f_sub(q, p), fx, p);
+            }
+            if (y1 >= 0 && y1 < src_rows_avail) {
+                const float p = sp[(int64_t)y1 * src_w + x0], q = sp[(int64_t)y1 * src_w + x1];
+                r1 = fmaf(f_sub(q, p), fx, p);
+            }
+            const float v = fmaf(f_sub(r1, r0), fy, r0);
             dp[(int64_t)ly * dst_w + dx] = v;
             mn = fminf(mn, v), mx = fmaxf(mx, v);
         }

@@ -37,8 +37,7 @@ def resize_src_rows(dst_r0: int, dst_r1: int, dst_h: int, src_h: int) -> Range:
     scale = 1.0 / (dst_h / src_h)
 
     def sy(dy):
-        import numpy as np
-        return int(math.floor(float(np.float32((dy + 0.5) * scale - 0.5))))
+        return int(math.floor((dy + 0.5) * scale - 0.5))
 
     a = min(max(sy(dst_r0), 0), src_h - 1)
     b = min(max(sy(dst_r1 - 1) + 1, 0), src_h - 1) + 1
