@@ -34,6 +34,7 @@ struct KmState {
     // w = -2 c_jd scale_d and bias = |c_j|^2 - 2 sum_d c_jd (min_d - mean_d): scaling and centring are folded in
     float w32[KM_MAXK * KM_MAXD];
     float bias32[KM_MAXK];
+    float cent32[KM_MAXK * KM_MAXD];                            // centred, scaled coordinates in fp32 (inertia only)
     float tau;
     float pad0;
     double shift_sq;
@@ -58,6 +59,7 @@ __device__ void km_derive(KmState* st) {
             cn += c * c;
             bias += -2.0 * c * (st->min64[d] - st->mean64[d]);
             st->w32[j * KM_MAXD + d] = (float)w;
+            st->cent32[j * KM_MAXD + d] = (float)c;
             mag += st->absmax[d] * fabs(w) + fabs(2.0 * c * (st->min64[d] - st->mean64[d]));
         }
         st->cnorm64[j] = cn;
@@ -70,7 +72,14 @@ __device__ void km_derive(KmState* st) {
     if (threadIdx.x == 0) {
         double e_max = 0.0;
         for (int j = 0; j < K; ++j) e_max = fmax(e_max, e_arr[j]);
-        st->tau = (float)(2.0 * 1.5 * e_max * 5.9604644775390625e-08);  // two distances, 1.5x safety
+        const double e_max_mag = e_max / (D + 3);  // largest |distance| the fp32 path can produce
+        // two distances, 1.5x safety; plus the index tag written over the low mantissa bits of each distance
+        st->tau = (float)(2.0 * 1.5 * e_max * 5.9604644775390625e-08 + 2.0 * e_max_mag * 64.0 * 1.1920928955078125e-07);
+        // never-chosen padding centroids: the kernel evaluates KM_SLOTS (K <= 8) or an even number of centroids
+        for (int j = K; j < KM_MAXK && j < ((K <= 8) ? 8 : ((K + 1) & ~1)); ++j) {
+            st->bias32[j] = 1e30f;  // finite: the index tag must not turn it into a NaN
+            for (int d = 0; d < D; ++d) st->w32[j * KM_MAXD + d] = 0.f;
+        }
     }
     for (int d = threadIdx.x; d < D; d += blockDim.x) {
         st->scale32[d] = (float)st->scale64[d];
@@ -138,11 +147,13 @@ extern "C" int rsx_kmeans_setup(void* d_state, int D, int K, const double* h_fea
 }
 
 // ----------------------------------------------------------------------------- exact (float64) re-evaluation
+// Cold path: re-loads the pixel's features (L1/L2 hits) so the hot loop keeps nothing in local memory.
 template <int D>
-__device__ __noinline__ int km_exact_argmin(const float* x, double* dist_out) {
+__device__ __noinline__ int km_exact_argmin(const float* __restrict__ stack, int64_t plane_stride, int64_t p, double* dist_out) {
     double X[D];
 #pragma unroll
-    for (int d = 0; d < D; ++d) X[d] = __dsub_rn(__dadd_rn(__dmul_rn((double)x[d], g_km.scale64[d]), g_km.min64[d]), g_km.mean64[d]);
+    for (int d = 0; d < D; ++d)
+        X[d] = __dsub_rn(__dadd_rn(__dmul_rn((double)stack[d * plane_stride + p], g_km.scale64[d]), g_km.min64[d]), g_km.mean64[d]);
     double best = 0.0, xx = 0.0;
     int bi = 0;
 #pragma unroll
@@ -159,190 +170,321 @@ __device__ __noinline__ int km_exact_argmin(const float* x, double* dist_out) {
 }
 
 // ----------------------------------------------------------------------------- assign + partial sums
+// Work decomposition: the flat pixel array is viewed as rows of row_len pixels; a tile is KM_TILE_W columns x
+// KM_TILE_R rows; a thread owns 4 adjacent columns (one float4 per plane) and walks down the tile rows, with the
+// next row's 4*D floats already in flight in a second register set (software prefetch).
+//
+// Partial sums: every thread owns KM_SLOTS accumulator slots in shared memory, laid out [slot][feature][thread]
+// as int64 so that a warp's accesses are 256 contiguous bytes (2 wavefronts, no bank conflicts, no atomics).
+// With K <= KM_SLOTS the slot is the label itself; for larger K the slots form a direct-mapped cache keyed by
+// label % KM_SLOTS whose evictions go to a CTA-wide [K][D+1] accumulator with 32-bit shared atomics (carry
+// propagated by hand).  At the end of the CTA the slots are summed over the threads and added to the global
+// int64 accumulators with one 64-bit reduction per cell.
 constexpr int KM_THREADS = 128;
 constexpr int KM_TILE_W = KM_THREADS * 4;  // pixels per tile row
 constexpr int KM_TILE_R = 32;              // rows per tile
+constexpr int KM_SLOTS = 8;
 
 template <int D>
-struct KmRun {  // per-thread run-length accumulator: sums of consecutive same-label pixels stay in registers
-    long long s[D];
-    unsigned cnt;
-    int label;
+struct KmSmem {
+    static constexpr int CELLS = KM_SLOTS * (D + 1);
+    static constexpr int CACHE_BYTES = CELLS * KM_THREADS * 8;
 };
 
-template <int D>
-__device__ __forceinline__ void km_flush(KmRun<D>& run, unsigned* s_lo, int* s_hi) {
-    if (run.label >= 0) {
-        const int base = run.label * (D + 1);
-#pragma unroll
-        for (int d = 0; d < D; ++d) {
-            unsigned lo = (unsigned)run.s[d];
-            int hi = (int)(run.s[d] >> 32);
-            unsigned old = atomicAdd(&s_lo[base + d], lo);
-            hi += (old + lo < old) ? 1 : 0;  // carry out of the low limb
-            if (hi) atomicAdd(&s_hi[base + d], hi);
-            run.s[d] = 0;
+struct KmWalk {  // (tile, row) iteration over the tiles a CTA owns
+    int64_t v_rows, tiles_total, tile;
+    int64_t r, r_end, n4;
+    int tiles_x, row_len, col;
+    __device__ __forceinline__ bool open_tile() {
+        while (tile < tiles_total) {
+            const int tx = (int)(tile % tiles_x);
+            const int64_t ty = tile / tiles_x;
+            col = tx * KM_TILE_W + threadIdx.x * 4;
+            r = ty * KM_TILE_R;
+            r_end = min(v_rows, r + KM_TILE_R);
+            if (col < row_len && r * row_len + col < n4) return true;
+            tile += gridDim.x;
         }
-        unsigned old = atomicAdd(&s_lo[base + D], run.cnt);
-        if (old + run.cnt < old) atomicAdd(&s_hi[base + D], 1);
-        run.cnt = 0;
+        return false;
     }
-}
+    __device__ __forceinline__ int64_t start(int64_t n4_, int row_len_) {
+        n4 = n4_, row_len = row_len_;
+        v_rows = (n4 + row_len - 1) / row_len;
+        tiles_x = (row_len + KM_TILE_W - 1) / KM_TILE_W;
+        tiles_total = ((v_rows + KM_TILE_R - 1) / KM_TILE_R) * tiles_x;
+        tile = blockIdx.x;
+        return open_tile() ? r * row_len + col : -1;
+    }
+    __device__ __forceinline__ int64_t next() {
+        ++r;
+        if (r < r_end) {
+            const int64_t p = r * row_len + col;
+            if (p < n4) return p;
+        }
+        tile += gridDim.x;
+        return open_tile() ? r * row_len + col : -1;
+    }
+};
 
-template <int D, bool UPDATE, bool INERTIA>
-__device__ __forceinline__ void km_pixel(const float (&x)[D], float best, float second, int bi, KmRun<D>& run, unsigned* s_lo, int* s_hi,
-                                         int& label_out, double& inertia, unsigned& ties) {
+template <int D, bool DIRECT>
+struct KmAcc {
+    long long* cache;      // [KM_SLOTS][D+1][KM_THREADS], this thread's column pre-applied
+    unsigned* s_lo;        // CTA-wide [K][D+1] limbs (only when !DIRECT)
+    int* s_hi;
+    unsigned long long tags;  // 8 x (label+1) bytes, 0 = empty (only when !DIRECT)
+
+    __device__ __forceinline__ long long* cell(int slot, int d) const { return cache + (slot * (D + 1) + d) * KM_THREADS; }
+
+    __device__ __noinline__ void evict(int slot) {
+        const int lab = (int)((tags >> (8 * slot)) & 0xff) - 1;
+        if (lab < 0) return;
+        const int base = lab * (D + 1);
+#pragma unroll 1
+        for (int d = 0; d <= D; ++d) {
+            long long v = *cell(slot, d);
+            *cell(slot, d) = 0;
+            unsigned lo = (unsigned)v;
+            int hi = (int)(v >> 32);
+            unsigned old = atomicAdd(&s_lo[base + d], lo);
+            hi += (old + lo < old) ? 1 : 0;
+            if (hi) atomicAdd(&s_hi[base + d], hi);
+        }
+    }
+
+    __device__ __forceinline__ void add(int label, const float (&x)[D]) {
+        int slot = label;
+        if (!DIRECT) {
+            slot = label & (KM_SLOTS - 1);
+            const int tag = (int)((tags >> (8 * slot)) & 0xff);
+            if (tag != label + 1) {
+                evict(slot);
+                tags = (tags & ~(0xffull << (8 * slot))) | ((unsigned long long)(label + 1) << (8 * slot));
+            }
+        }
+#pragma unroll
+        for (int d = 0; d < D; ++d) *cell(slot, d) += __float2ll_rn(x[d] * g_km.pow2[d]);
+        *cell(slot, D) += 1;
+    }
+};
+
+template <int D, bool UPDATE, bool INERTIA, bool DIRECT>
+__device__ __forceinline__ int km_finish_pixel(const float* __restrict__ stack, int64_t plane_stride, int64_t p, const float (&x)[D], float best,
+                                               float second, int bi, KmAcc<D, DIRECT>& acc, double& inertia, unsigned& ties) {
     double dist_exact = -1.0;
     if (!(second - best > g_km.tau)) {  // near tie (or NaN): decide in float64
-        bi = km_exact_argmin<D>(x, &dist_exact);
+        bi = km_exact_argmin<D>(stack, plane_stride, p, &dist_exact);
         ++ties;
     }
-    label_out = bi;
     if (INERTIA) {
         if (dist_exact < 0.0) {
-            float xx = 0.f;
+            // sum of squares of (x' - c): all terms positive, relative error ~D * 2^-24
+            float dd = 0.f;
 #pragma unroll
             for (int d = 0; d < D; ++d) {
-                float xs = fmaf(x[d], g_km.scale32[d], g_km.off32[d]);
-                xx = fmaf(xs, xs, xx);
+                float df = fmaf(x[d], g_km.scale32[d], g_km.off32[d]) - g_km.cent32[bi * KM_MAXD + d];
+                dd = fmaf(df, df, dd);
             }
-            dist_exact = (double)fmaxf(xx + best, 0.f);
+            dist_exact = (double)dd;
         }
         inertia += dist_exact;
     }
-    if (UPDATE) {
-        if (bi != run.label) {
-            km_flush<D>(run, s_lo, s_hi);
-            run.label = bi;
-        }
-#pragma unroll
-        for (int d = 0; d < D; ++d) run.s[d] += __float2ll_rn(x[d] * g_km.pow2[d]);
-        run.cnt += 1;
-    }
+    if (UPDATE) acc.add(bi, x);
+    return bi;
 }
 
-template <int D, bool UPDATE, bool INERTIA>
-__global__ void __launch_bounds__(KM_THREADS) km_assign_kernel(const float* __restrict__ stack, int64_t plane_stride, int64_t n_px, int row_len,
-                                                               long long* __restrict__ acc, uint8_t* __restrict__ lab8, int32_t* __restrict__ lab32,
-                                                               double* __restrict__ inertia_out) {
-    extern __shared__ unsigned km_smem[];
+#define KM_ARGMIN_STEP(A, B_, S_, I_, J)          \
+    S_ = fminf(S_, fmaxf(A, B_));                 \
+    if (A < B_) B_ = A, I_ = J;
+
+// Index-in-mantissa variant: the low KM_IDX_BITS bits of the fp32 distance are replaced by the centroid index, so
+// best/runner-up tracking is three FMNMX and no index bookkeeping.  The perturbation (< 2^KM_IDX_BITS ulp) is part
+// of the near-tie bound tau; anything closer than tau is decided in float64 anyway, so fp32 ties never pick a label.
+constexpr int KM_IDX_BITS = 6;
+__device__ __forceinline__ float km_tag(float a, int j) { return __uint_as_float((__float_as_uint(a) & ~((1u << KM_IDX_BITS) - 1u)) | (unsigned)j); }
+#define KM_ARGMIN_TAGGED(A, B_, S_, J)                \
+    {                                                 \
+        const float t_ = km_tag(A, J);                \
+        S_ = fminf(S_, fmaxf(t_, B_));                \
+        B_ = fminf(B_, t_);                           \
+    }
+
+template <int D, bool UPDATE, bool INERTIA, int KU>
+__global__ void __launch_bounds__(KM_THREADS, 2) km_assign_kernel(const float* __restrict__ stack, int64_t plane_stride, int64_t n_px, int row_len,
+                                                                  long long* __restrict__ gacc, uint8_t* __restrict__ lab8,
+                                                                  int32_t* __restrict__ lab32, double* __restrict__ inertia_out) {
+    constexpr bool DIRECT = KU > 0;  // K <= KM_SLOTS: an accumulator slot per label, no evictions
+    extern __shared__ __align__(16) unsigned char km_smem[];
     const int K = g_km.K;
-    const int ncell = K * (D + 1);
-    unsigned* s_lo = km_smem;
-    int* s_hi = reinterpret_cast<int*>(km_smem + ncell);
+    KmAcc<D, DIRECT> acc;
+    acc.cache = reinterpret_cast<long long*>(km_smem) + threadIdx.x;
+    acc.s_lo = reinterpret_cast<unsigned*>(km_smem + KmSmem<D>::CACHE_BYTES);
+    acc.s_hi = reinterpret_cast<int*>(acc.s_lo + K * (D + 1));
+    acc.tags = 0;
     if (UPDATE) {
-        for (int i = threadIdx.x; i < 2 * ncell; i += KM_THREADS) km_smem[i] = 0;
+        for (int i = threadIdx.x; i < KmSmem<D>::CELLS * KM_THREADS; i += KM_THREADS) reinterpret_cast<long long*>(km_smem)[i] = 0;
+        if (!DIRECT)
+            for (int i = threadIdx.x; i < 2 * K * (D + 1); i += KM_THREADS) acc.s_lo[i] = 0;
         __syncthreads();
     }
-    KmRun<D> run;
-#pragma unroll
-    for (int d = 0; d < D; ++d) run.s[d] = 0;
-    run.cnt = 0;
-    run.label = -1;
     double inertia = 0.0;
     unsigned ties = 0;
+    const int64_t n4 = n_px & ~(int64_t)3;
+    const int Kp = (K + 1) & ~1;  // centroids are processed in pairs; slot K (if K is odd) holds bias=+inf
 
-    const int64_t n4 = n_px & ~(int64_t)3;                  // pixels covered by aligned quads
-    const int64_t v_rows = (n4 + row_len - 1) / row_len;    // virtual rows of row_len pixels over the flat array
-    const int tiles_x = (row_len + KM_TILE_W - 1) / KM_TILE_W;
-    const int64_t tiles_y = (v_rows + KM_TILE_R - 1) / KM_TILE_R;
-    const int64_t n_tiles = tiles_y * tiles_x;
-
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int tx = (int)(tile % tiles_x);
-        const int64_t ty = tile / tiles_x;
-        const int col = tx * KM_TILE_W + threadIdx.x * 4;
-        if (col >= row_len) continue;
-        const int64_t r_end = min(v_rows, (ty + 1) * KM_TILE_R);
-        for (int64_t r = ty * KM_TILE_R; r < r_end; ++r) {
-            const int64_t p = r * row_len + col;
-            if (p >= n4) break;
-            float4 v[D];
+    KmWalk walk;
+    int64_t p = walk.start(n4, row_len);
+    float4 va[D], vb[D];  // ping-pong register sets: one is consumed while the other is being loaded
+    auto load_row = [&](float4 (&dst)[D], int64_t at) {
 #pragma unroll
-            for (int d = 0; d < D; ++d) v[d] = ldg_stream4(stack + d * plane_stride + p);
-            // fp32 distances for the four pixels, two packed pairs
-            float b0 = INFINITY, b1 = INFINITY, b2 = INFINITY, b3 = INFINITY;
-            float s0 = INFINITY, s1 = INFINITY, s2 = INFINITY, s3 = INFINITY;
-            int i0 = 0, i1 = 0, i2 = 0, i3 = 0;
-            for (int j = 0; j < K; ++j) {
-                const float cn = g_km.bias32[j];
-                float2 a01 = make_float2(cn, cn), a23 = a01;
+        for (int d = 0; d < D; ++d) dst[d] = ldg_stream4(stack + d * plane_stride + at);
+    };
+    auto process_row = [&](const float4 (&v)[D], int64_t p) {
+        float b0 = INFINITY, b1 = INFINITY, b2 = INFINITY, b3 = INFINITY;
+        float s0 = INFINITY, s1 = INFINITY, s2 = INFINITY, s3 = INFINITY;
+        if (KU > 0) {
+            // K <= KU: fully unrolled, the weights are immediate constant-bank operands of FFMA2 (no loads at all)
+#pragma unroll
+            for (int j = 0; j < KU; ++j) {
+                const float cA = g_km.bias32[j];
+                float2 a01 = make_float2(cA, cA), a23 = a01;
 #pragma unroll
                 for (int d = 0; d < D; ++d) {
-                    const float c = g_km.w32[j * KM_MAXD + d];
-                    a01 = __ffma2_rn(make_float2(v[d].x, v[d].y), make_float2(c, c), a01);
-                    a23 = __ffma2_rn(make_float2(v[d].z, v[d].w), make_float2(c, c), a23);
+                    const float wa = g_km.w32[j * KM_MAXD + d];
+                    a01 = __ffma2_rn(make_float2(v[d].x, v[d].y), make_float2(wa, wa), a01);
+                    a23 = __ffma2_rn(make_float2(v[d].z, v[d].w), make_float2(wa, wa), a23);
                 }
-                // first minimum wins; keep the runner-up for the tie test
-                s0 = fminf(s0, fmaxf(a01.x, b0)); if (a01.x < b0) b0 = a01.x, i0 = j;
-                s1 = fminf(s1, fmaxf(a01.y, b1)); if (a01.y < b1) b1 = a01.y, i1 = j;
-                s2 = fminf(s2, fmaxf(a23.x, b2)); if (a23.x < b2) b2 = a23.x, i2 = j;
-                s3 = fminf(s3, fmaxf(a23.y, b3)); if (a23.y < b3) b3 = a23.y, i3 = j;
+                KM_ARGMIN_TAGGED(a01.x, b0, s0, j) KM_ARGMIN_TAGGED(a01.y, b1, s1, j)
+                KM_ARGMIN_TAGGED(a23.x, b2, s2, j) KM_ARGMIN_TAGGED(a23.y, b3, s3, j)
             }
-            int l0, l1, l2, l3;
-            {
-                float x[D];
+        } else {
+#pragma unroll 1
+            for (int j = 0; j < Kp; j += 2) {
+                const float cA = g_km.bias32[j], cB = g_km.bias32[j + 1];
+                float2 a01 = make_float2(cA, cA), a23 = a01, e01 = make_float2(cB, cB), e23 = e01;
 #pragma unroll
-                for (int d = 0; d < D; ++d) x[d] = v[d].x;
-                km_pixel<D, UPDATE, INERTIA>(x, b0, s0, i0, run, s_lo, s_hi, l0, inertia, ties);
-#pragma unroll
-                for (int d = 0; d < D; ++d) x[d] = v[d].y;
-                km_pixel<D, UPDATE, INERTIA>(x, b1, s1, i1, run, s_lo, s_hi, l1, inertia, ties);
-#pragma unroll
-                for (int d = 0; d < D; ++d) x[d] = v[d].z;
-                km_pixel<D, UPDATE, INERTIA>(x, b2, s2, i2, run, s_lo, s_hi, l2, inertia, ties);
-#pragma unroll
-                for (int d = 0; d < D; ++d) x[d] = v[d].w;
-                km_pixel<D, UPDATE, INERTIA>(x, b3, s3, i3, run, s_lo, s_hi, l3, inertia, ties);
+                for (int d = 0; d < D; ++d) {
+                    const float wa = g_km.w32[j * KM_MAXD + d], wb = g_km.w32[(j + 1) * KM_MAXD + d];
+                    const float2 x01 = make_float2(v[d].x, v[d].y), x23 = make_float2(v[d].z, v[d].w);
+                    a01 = __ffma2_rn(x01, make_float2(wa, wa), a01);
+                    a23 = __ffma2_rn(x23, make_float2(wa, wa), a23);
+                    e01 = __ffma2_rn(x01, make_float2(wb, wb), e01);
+                    e23 = __ffma2_rn(x23, make_float2(wb, wb), e23);
+                }
+                KM_ARGMIN_TAGGED(a01.x, b0, s0, j) KM_ARGMIN_TAGGED(a01.y, b1, s1, j)
+                KM_ARGMIN_TAGGED(a23.x, b2, s2, j) KM_ARGMIN_TAGGED(a23.y, b3, s3, j)
+                KM_ARGMIN_TAGGED(e01.x, b0, s0, j + 1) KM_ARGMIN_TAGGED(e01.y, b1, s1, j + 1)
+                KM_ARGMIN_TAGGED(e23.x, b2, s2, j + 1) KM_ARGMIN_TAGGED(e23.y, b3, s3, j + 1)
             }
-            if (lab8) *reinterpret_cast<uint32_t*>(lab8 + p) = (uint32_t)l0 | ((uint32_t)l1 << 8) | ((uint32_t)l2 << 16) | ((uint32_t)l3 << 24);
-            if (lab32) *reinterpret_cast<int4*>(lab32 + p) = make_int4(l0, l1, l2, l3);
         }
+        const int i0 = (int)(__float_as_uint(b0) & ((1u << KM_IDX_BITS) - 1u)), i1 = (int)(__float_as_uint(b1) & ((1u << KM_IDX_BITS) - 1u));
+        const int i2 = (int)(__float_as_uint(b2) & ((1u << KM_IDX_BITS) - 1u)), i3 = (int)(__float_as_uint(b3) & ((1u << KM_IDX_BITS) - 1u));
+        int l0, l1, l2, l3;
+        {
+            float x[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) x[d] = v[d].x;
+            l0 = km_finish_pixel<D, UPDATE, INERTIA, DIRECT>(stack, plane_stride, p, x, b0, s0, i0, acc, inertia, ties);
+#pragma unroll
+            for (int d = 0; d < D; ++d) x[d] = v[d].y;
+            l1 = km_finish_pixel<D, UPDATE, INERTIA, DIRECT>(stack, plane_stride, p + 1, x, b1, s1, i1, acc, inertia, ties);
+#pragma unroll
+            for (int d = 0; d < D; ++d) x[d] = v[d].z;
+            l2 = km_finish_pixel<D, UPDATE, INERTIA, DIRECT>(stack, plane_stride, p + 2, x, b2, s2, i2, acc, inertia, ties);
+#pragma unroll
+            for (int d = 0; d < D; ++d) x[d] = v[d].w;
+            l3 = km_finish_pixel<D, UPDATE, INERTIA, DIRECT>(stack, plane_stride, p + 3, x, b3, s3, i3, acc, inertia, ties);
+        }
+        if (lab8) *reinterpret_cast<uint32_t*>(lab8 + p) = (uint32_t)l0 | ((uint32_t)l1 << 8) | ((uint32_t)l2 << 16) | ((uint32_t)l3 << 24);
+        if (lab32) *reinterpret_cast<int4*>(lab32 + p) = make_int4(l0, l1, l2, l3);
+    };
+    if (p >= 0) load_row(va, p);
+    while (p >= 0) {
+        const int64_t pn = walk.next();
+        if (pn >= 0) load_row(vb, pn);
+        process_row(va, p);
+        if (pn < 0) break;
+        p = walk.next();
+        if (p >= 0) load_row(va, p);
+        process_row(vb, pn);
     }
     // ragged tail (n_px % 4 pixels): one thread, scalar
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        for (int64_t p = n4; p < n_px; ++p) {
+        for (int64_t q = n4; q < n_px; ++q) {
             float x[D];
 #pragma unroll
-            for (int d = 0; d < D; ++d) x[d] = stack[d * plane_stride + p];
+            for (int d = 0; d < D; ++d) x[d] = stack[d * plane_stride + q];
             float b = INFINITY, s = INFINITY;
             int bi = 0;
             for (int j = 0; j < K; ++j) {
                 float a = g_km.bias32[j];
 #pragma unroll
                 for (int d = 0; d < D; ++d) a = fmaf(x[d], g_km.w32[j * KM_MAXD + d], a);
-                s = fminf(s, fmaxf(a, b));
-                if (a < b) b = a, bi = j;
+                KM_ARGMIN_STEP(a, b, s, bi, j)
             }
-            int l;
-            km_pixel<D, UPDATE, INERTIA>(x, b, s, bi, run, s_lo, s_hi, l, inertia, ties);
-            if (lab8) lab8[p] = (uint8_t)l;
-            if (lab32) lab32[p] = l;
+            int l = km_finish_pixel<D, UPDATE, INERTIA, DIRECT>(stack, plane_stride, q, x, b, s, bi, acc, inertia, ties);
+            if (lab8) lab8[q] = (uint8_t)l;
+            if (lab32) lab32[q] = l;
         }
     }
     if (UPDATE) {
-        km_flush<D>(run, s_lo, s_hi);
-        __syncthreads();
-        for (int i = threadIdx.x; i < ncell; i += KM_THREADS) {
-            long long v = ((long long)s_hi[i] << 32) + (long long)s_lo[i];
-            if (v) {
-                // acc layout: sums [K][D] then counts [K]
-                int j = i / (D + 1), d = i % (D + 1);
-                long long* dst = d < D ? &acc[j * D + d] : &acc[K * D + j];
-                atomicAdd(reinterpret_cast<unsigned long long*>(dst), (unsigned long long)v);
+        if (DIRECT) {
+            __syncthreads();
+            // column sums over the CTA's threads: warp w takes cells w, w+4, ...
+            const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+            const long long* base = reinterpret_cast<const long long*>(km_smem);
+            for (int c = warp; c < K * (D + 1); c += KM_THREADS / 32) {
+                long long t = 0;
+#pragma unroll
+                for (int i = 0; i < KM_THREADS / 32; ++i) t += base[c * KM_THREADS + lane + 32 * i];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+                if (lane == 0 && t) {
+                    const int j = c / (D + 1), d = c % (D + 1);
+                    long long* dst = d < D ? &gacc[j * D + d] : &gacc[K * D + j];
+                    atomicAdd(reinterpret_cast<unsigned long long*>(dst), (unsigned long long)t);
+                }
+            }
+        } else {
+#pragma unroll 1
+            for (int slot = 0; slot < KM_SLOTS; ++slot) acc.evict(slot);
+            __syncthreads();
+            for (int i = threadIdx.x; i < K * (D + 1); i += KM_THREADS) {
+                long long t = ((long long)acc.s_hi[i] << 32) + (long long)acc.s_lo[i];
+                if (t) {
+                    const int j = i / (D + 1), d = i % (D + 1);
+                    long long* dst = d < D ? &gacc[j * D + d] : &gacc[K * D + j];
+                    atomicAdd(reinterpret_cast<unsigned long long*>(dst), (unsigned long long)t);
+                }
             }
         }
     }
-    // ties + inertia
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         ties += __shfl_xor_sync(0xffffffffu, ties, o);
         if (INERTIA) inertia += __shfl_xor_sync(0xffffffffu, inertia, o);
     }
     if ((threadIdx.x & 31) == 0) {
-        if (ties && acc) atomicAdd(reinterpret_cast<unsigned long long*>(&acc[K * D + K]), (unsigned long long)ties);
+        if (ties && gacc) atomicAdd(reinterpret_cast<unsigned long long*>(&gacc[K * D + K]), (unsigned long long)ties);
         if (INERTIA && inertia_out) atomicAdd(inertia_out, inertia);
     }
+}
+
+template <int D, bool UPDATE, bool INERTIA, int KU>
+static int km_launch2(const float* d_stack, int64_t plane_stride, int64_t n_px, int row_len, long long* acc, uint8_t* l8, int32_t* l32,
+                      double* inertia, int K, int grid, cudaStream_t s) {
+    int smem = UPDATE ? KmSmem<D>::CACHE_BYTES + (KU > 0 ? 0 : 2 * K * (D + 1) * 4) : 0;
+    auto kern = km_assign_kernel<D, UPDATE, INERTIA, KU>;
+    static int configured = -1;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max(smem, 48 * 1024));
+        if (e != cudaSuccess) {
+            rsx_set_error("km_assign: cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e));
+            return RSX_ERR_CUDA;
+        }
+        configured = max(smem, 48 * 1024);
+    }
+    kern<<<grid, KM_THREADS, smem, s>>>(d_stack, plane_stride, n_px, row_len, acc, l8, l32, inertia);
+    return rsx_check_launch("km_assign");
 }
 
 template <int D>
@@ -351,17 +493,17 @@ static int km_launch(const float* d_stack, int64_t plane_stride, int64_t n_px, i
     const int64_t n4 = n_px & ~(int64_t)3;
     const int64_t v_rows = (n4 + row_len - 1) / row_len;
     const int64_t n_tiles = ceil_div(v_rows, (int64_t)KM_TILE_R) * ceil_div(row_len, KM_TILE_W);
-    const int grid = (int)max((int64_t)1, min(n_tiles, (int64_t)rsx_num_sms() * 4));
-    const int smem = 2 * K * (D + 1) * 4;
-    if (update && inertia)
-        km_assign_kernel<D, true, true><<<grid, KM_THREADS, smem, s>>>(d_stack, plane_stride, n_px, row_len, acc, l8, l32, inertia);
-    else if (update)
-        km_assign_kernel<D, true, false><<<grid, KM_THREADS, smem, s>>>(d_stack, plane_stride, n_px, row_len, acc, l8, l32, inertia);
-    else if (inertia)
-        km_assign_kernel<D, false, true><<<grid, KM_THREADS, smem, s>>>(d_stack, plane_stride, n_px, row_len, acc, l8, l32, inertia);
-    else
-        km_assign_kernel<D, false, false><<<grid, KM_THREADS, smem, s>>>(d_stack, plane_stride, n_px, row_len, acc, l8, l32, inertia);
-    return rsx_check_launch("km_assign");
+    const int per_sm = (update && KmSmem<D>::CACHE_BYTES > 113 * 1024) ? 1 : 2;
+    const int grid = (int)max((int64_t)1, min(n_tiles, (int64_t)rsx_num_sms() * per_sm));
+    const bool direct = K <= KM_SLOTS;
+    if (update)  // inertia is only produced by the final (assign-only) pass
+        return direct ? km_launch2<D, true, false, KM_SLOTS>(d_stack, plane_stride, n_px, row_len, acc, l8, l32, nullptr, K, grid, s)
+                      : km_launch2<D, true, false, 0>(d_stack, plane_stride, n_px, row_len, acc, l8, l32, nullptr, K, grid, s);
+    if (inertia)
+        return direct ? km_launch2<D, false, true, KM_SLOTS>(d_stack, plane_stride, n_px, row_len, acc, l8, l32, inertia, K, grid, s)
+                      : km_launch2<D, false, true, 0>(d_stack, plane_stride, n_px, row_len, acc, l8, l32, inertia, K, grid, s);
+    return direct ? km_launch2<D, false, false, KM_SLOTS>(d_stack, plane_stride, n_px, row_len, acc, l8, l32, inertia, K, grid, s)
+                  : km_launch2<D, false, false, 0>(d_stack, plane_stride, n_px, row_len, acc, l8, l32, inertia, K, grid, s);
 }
 
 extern "C" int rsx_kmeans_assign(const float* d_stack, int64_t plane_stride, int64_t n_px, int row_len, const void* d_state, int64_t* d_acc,
@@ -370,6 +512,7 @@ extern "C" int rsx_kmeans_assign(const float* d_stack, int64_t plane_stride, int
     RSX_REQUIRE(d_stack && d_state && n_px > 0, "rsx_kmeans_assign: bad arguments");
     RSX_REQUIRE(D >= 1 && D <= KM_MAXD && K >= 1 && K <= KM_MAXK, "rsx_kmeans_assign: D/K out of range");
     RSX_REQUIRE(!update || d_acc, "rsx_kmeans_assign: update pass needs d_acc");
+    RSX_REQUIRE(!(update && d_inertia), "rsx_kmeans_assign: inertia is produced by the assign-only pass (update == 0)");
     RSX_REQUIRE(((uintptr_t)d_stack & 15) == 0 && (plane_stride & 3) == 0, "rsx_kmeans_assign: stack planes must be 16-byte aligned");
     RSX_REQUIRE((((uintptr_t)d_labels_u8) & 3) == 0 && (((uintptr_t)d_labels_i32) & 15) == 0, "rsx_kmeans_assign: label buffers must be aligned");
     if (row_len <= 0) row_len = 4096;
