@@ -74,7 +74,7 @@ __device__ void km_derive(KmState* st) {
         for (int j = 0; j < K; ++j) e_max = fmax(e_max, e_arr[j]);
         const double e_max_mag = e_max / (D + 3);  // largest |distance| the fp32 path can produce
         // two distances, 1.5x safety; plus the index tag written over the low mantissa bits of each distance
-        st->tau = (float)(2.0 * 1.5 * e_max * 5.9604644775390625e-08 + 2.0 * e_max_mag * 64.0 * 1.1920928955078125e-07);
+        st->tau = (float)(2.0 * 1.5 * e_max * 5.9604644775390625e-08 + 2.0 * e_max_mag * (K <= 8 ? 8.0 : 64.0) * 1.1920928955078125e-07);
         // never-chosen padding centroids: the kernel evaluates KM_SLOTS (K <= 8) or an even number of centroids
         for (int j = K; j < KM_MAXK && j < ((K <= 8) ? 8 : ((K + 1) & ~1)); ++j) {
             st->bias32[j] = 1e30f;  // finite: the index tag must not turn it into a NaN
@@ -299,11 +299,13 @@ __device__ __forceinline__ int km_finish_pixel(const float* __restrict__ stack, 
 // Index-in-mantissa variant: the low KM_IDX_BITS bits of the fp32 distance are replaced by the centroid index, so
 // best/runner-up tracking is three FMNMX and no index bookkeeping.  The perturbation (< 2^KM_IDX_BITS ulp) is part
 // of the near-tie bound tau; anything closer than tau is decided in float64 anyway, so fp32 ties never pick a label.
-constexpr int KM_IDX_BITS = 6;
-__device__ __forceinline__ float km_tag(float a, int j) { return __uint_as_float((__float_as_uint(a) & ~((1u << KM_IDX_BITS) - 1u)) | (unsigned)j); }
+constexpr int KM_IDX_BITS_SMALL = 3;  // K <= 8 (unrolled path)
+constexpr int KM_IDX_BITS_LARGE = 6;  // K <= 64
+template <int BITS>
+__device__ __forceinline__ float km_tag(float a, int j) { return __uint_as_float((__float_as_uint(a) & ~((1u << BITS) - 1u)) | (unsigned)j); }
 #define KM_ARGMIN_TAGGED(A, B_, S_, J)                \
     {                                                 \
-        const float t_ = km_tag(A, J);                \
+        const float t_ = km_tag<KM_IDX_BITS>(A, J);   \
         S_ = fminf(S_, fmaxf(t_, B_));                \
         B_ = fminf(B_, t_);                           \
     }
@@ -338,7 +340,19 @@ __global__ void __launch_bounds__(KM_THREADS, 2) km_assign_kernel(const float* _
 #pragma unroll
         for (int d = 0; d < D; ++d) dst[d] = ldg_stream4(stack + d * plane_stride + at);
     };
+    // L2 prefetch of the row two steps ahead (no registers, no scoreboard): HBM latency is paid there, the
+    // register loads of the next row then hit L2
+    const int lane_pf = threadIdx.x & 31;
+    const bool do_pf = (lane_pf & 7) == 0 || lane_pf == 31;
+    auto prefetch_l2 = [&](int64_t at) {
+        if (do_pf && at + 4 <= n4) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) asm volatile("prefetch.global.L2 [%0];" ::"l"(stack + d * plane_stride + at));
+        }
+    };
     auto process_row = [&](const float4 (&v)[D], int64_t p) {
+        prefetch_l2(p + 2 * (int64_t)row_len);
+        constexpr int KM_IDX_BITS = KU > 0 ? KM_IDX_BITS_SMALL : KM_IDX_BITS_LARGE;
         float b0 = INFINITY, b1 = INFINITY, b2 = INFINITY, b3 = INFINITY;
         float s0 = INFINITY, s1 = INFINITY, s2 = INFINITY, s3 = INFINITY;
         if (KU > 0) {
