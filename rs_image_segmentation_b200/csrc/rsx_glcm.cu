@@ -125,126 +125,258 @@ __global__ void __launch_bounds__(128) glcm_props_warp_kernel(const uint8_t* __r
     }
 }
 
-// ----------------------------------------------------------------------------- dense kernel (step == 1): one thread per window column
-// Lane = window column j, the thread slides its window DOWN the rows.  Moving down by one row removes
-// the pairs anchored in the row that leaves and adds those of the row that enters (2*(4w-2) pair updates
-// instead of 4w(w-1)+... recounts).  Integer moments are maintained incrementally and exactly; the
-// energy term needs per-window cell multiplicities, kept as uint8 counters (<= w(w-1) <= 255 for w <= 16)
-// in a thread-private slice of shared memory laid out [cell][lane] so that the 32 lanes of a warp
-// hit 32 consecutive bytes (8 banks) per cell index.
-template <int NTHREADS>
-struct DenseCfg {
-    static constexpr int TILE_COLS = NTHREADS;  // windows per CTA row
+// ----------------------------------------------------------------------------- dense kernel (step == 1)
+// One thread per window column; the CTA slides a band of NTW = NT-(WIN-1) windows DOWN the rows.
+//
+// Per image row that enters (and per row that leaves) every thread handles ONE image column x = t:
+//   * the four pair codes anchored there (unordered cell index | "a==b" flag) go to a shared ring, so that the
+//     WIN windows containing a pair never recompute its cell;
+//   * the packed integer moments of those pairs update the thread's COLUMN sums (registers):
+//        W1 = |a-b| + (a*b << 13)       W2 = (a+b) + ((a^2+b^2) << 14)       SH = round(2^40/(1+(a-b)^2)) (u64)
+//     fields never overflow for levels <= 32, WIN <= 12, so one integer add updates two sums.
+// Column sums are exchanged through shared memory and each window thread adds the WIN (or WIN-1) columns it
+// spans.  Only the energy term needs co-occurrence multiplicities: per window, uint8 counters indexed by
+// (angle, unordered cell), thread-private in shared memory laid out [cell][thread]; a row slide does WIN-ish
+// decrements and increments per angle and maintains E = sum_cells weight*count^2 incrementally.
+// column range [c0, c1) of the anchors of each angle inside a window
+__host__ __device__ constexpr int dense_c0(int ang) { return ang == 3 ? 1 : 0; }
+__host__ __device__ constexpr int dense_c1(int ang, int win) { return ang <= 1 ? win - 1 : win; }
+
+__device__ __forceinline__ unsigned pair_code(int a, int b) { return (unsigned)tri_cell(a, b) | (a == b ? 0x8000u : 0u); }
+
+struct ColSums {
+    unsigned w1[4], w2[4];
+    unsigned long long sh[4];
 };
 
-template <int NTHREADS>
-__global__ void __launch_bounds__(NTHREADS) glcm_props_dense_kernel(const uint8_t* __restrict__ q, int W, int L, int win, int out_rows, int out_cols,
-                                                                    int rows_per_cta, float* __restrict__ props, int64_t plane_stride) {
-    extern __shared__ unsigned char dsm[];
-    // layout: counters [4 angles][ncell][NTHREADS] u8, then the q tile rows ring [(win+1)][tile_w]
-    const int ncell = L * (L + 1) / 2;
-    unsigned char* cnt = dsm;
-    const int tile_w = NTHREADS + win - 1;
-    unsigned char* qt = dsm + (size_t)4 * ncell * NTHREADS;  // ring of win+1 rows
-    const int ring = win + 1;
+__device__ __forceinline__ void pair_terms(int a, int b, unsigned& w1, unsigned& w2, unsigned long long& sh, const unsigned long long* __restrict__ homog_fx) {
+    const int d = abs(a - b);
+    w1 = (unsigned)d + ((unsigned)(a * b) << 13);
+    w2 = (unsigned)(a + b) + ((unsigned)(a * a + b * b) << 14);
+    sh = homog_fx[d];
+}
 
-    const int j0 = blockIdx.x * NTHREADS;           // first window column of this CTA
-    const int i_begin = blockIdx.y * rows_per_cta;  // first window row
+template <int WIN, int NT>
+__global__ void __launch_bounds__(NT) glcm_dense_kernel(const uint8_t* __restrict__ q, int W, int L, int out_rows, int out_cols, int rows_per_cta,
+                                                        float* __restrict__ props, int64_t plane_stride) {
+    constexpr int NTW = NT - (WIN - 1);  // windows per CTA
+    constexpr int RING = WIN + 1;
+    extern __shared__ __align__(16) unsigned char dsm[];
+    const int ncell = L * (L + 1) / 2;
+    unsigned char* cnt = dsm;                                                            // [4][ncell][NTW] u8
+    unsigned short* codes = reinterpret_cast<unsigned short*>(dsm + (size_t)4 * ncell * NTW);  // [4][RING][NT] u16
+    unsigned* xch = reinterpret_cast<unsigned*>(codes + 4 * RING * NT);                        // [16][NT] u32 column sums
+    unsigned char* qring = reinterpret_cast<unsigned char*>(xch + 16 * NT);               // [RING][NT] u8
+    __shared__ unsigned long long homog_fx[64];
+
+    const int t = threadIdx.x;
+    const int j0 = blockIdx.x * NTW;  // first window column == first image column of this CTA
+    const int i_begin = blockIdx.y * rows_per_cta;
     const int i_end = min(out_rows, i_begin + rows_per_cta);
     if (i_begin >= i_end) return;
-    const int t = threadIdx.x;
-    const int j = j0 + t;
-    const bool active = j < out_cols;
+    const bool has_win = t < NTW && j0 + t < out_cols;
 
-    for (int i = t; i < 4 * ncell * NTHREADS / 4; i += NTHREADS) reinterpret_cast<unsigned*>(cnt)[i] = 0;
+    for (int i = t; i < 4 * ncell * NTW / 4; i += NT) reinterpret_cast<unsigned*>(cnt)[i] = 0;
+    if (t < 64) homog_fx[t] = (unsigned long long)(1099511627776.0 / (1.0 + (double)t * (double)t) + 0.5);  // 2^40/(1+k^2)
 
-    auto load_row = [&](int img_row) {
-        unsigned char* dst = qt + (img_row % ring) * tile_w;
-        const uint8_t* src = q + (int64_t)img_row * W + j0;
-        const int valid = min(tile_w, W - j0);
-        for (int c = t; c < tile_w; c += NTHREADS) dst[c] = c < valid ? (unsigned char)min((int)src[c], L - 1) : 0;
-    };
-    auto Q = [&](int img_row, int c) -> int { return qt[(img_row % ring) * tile_w + c]; };
+    ColSums cs;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) cs.w1[a] = 0, cs.w2[a] = 0, cs.sh[a] = 0;
+    int e[4] = {0, 0, 0, 0};
+    const bool col_ok = j0 + t < W;
 
-    // per-angle running sums for this thread's window
-    int s1[4] = {0, 0, 0, 0}, sa[4] = {0, 0, 0, 0}, sq[4] = {0, 0, 0, 0}, sab[4] = {0, 0, 0, 0}, e[4] = {0, 0, 0, 0};
-    double sh[4] = {0, 0, 0, 0};
+    auto Q = [&](int row, int c) -> int { return qring[(row % RING) * NT + c]; };
+    auto CODE = [&](int ang, int row, int c) -> unsigned { return codes[(ang * RING + (row % RING)) * NT + c]; };
 
-    // add (sign=+1) or remove (sign=-1) the pairs of all four angles anchored in image row r (window columns t..t+win-1).
-    // angle 0: (r,c)-(r,c+1), c in [0,win-1)        needs row r
-    // angle 1: (r,c)-(r+1,c+1), c in [0,win-1)      needs rows r, r+1
-    // angle 2: (r,c)-(r+1,c), c in [0,win)          needs rows r, r+1
-    // angle 3: (r,c)-(r+1,c-1), c in [1,win)        needs rows r, r+1
-    auto pair_update = [&](int ang, int a, int b, int sign) {
-        const int d = abs(a - b);
-        s1[ang] += sign * d;
-        sa[ang] += sign * (a + b);
-        sq[ang] += sign * (a * a + b * b);
-        sab[ang] += sign * (a * b);
-        sh[ang] += sign > 0 ? g_homog[d] : -g_homog[d];
-        unsigned char* cell = cnt + ((size_t)ang * ncell + tri_cell(a, b)) * NTHREADS + t;
-        const int wgt = a != b ? 2 : 4;
-        int u = *cell;
-        if (sign > 0) {
-            e[ang] += wgt * (2 * u + 1);  // (u+1)^2 - u^2
-            *cell = (unsigned char)(u + 1);
-        } else {
-            e[ang] -= wgt * (2 * u - 1);  // u^2 - (u-1)^2
-            *cell = (unsigned char)(u - 1);
+    // Bring image row r in: q ring, then the pairs that become complete (angle 0 inside row r; angles 1-3 between
+    // rows r-1 and r, anchored in row r-1).  `first` = r is the first row of the band (no row above).
+    auto enter_row = [&](int r, bool first) {
+        qring[(r % RING) * NT + t] = col_ok ? (unsigned char)min((int)q[(int64_t)r * W + j0 + t], L - 1) : 0;
+        __syncthreads();
+        const int a = Q(r, t);
+        unsigned w1, w2;
+        unsigned long long sh;
+        if (t + 1 < NT) {  // angle 0: (r,t)-(r,t+1)
+            const int b = Q(r, t + 1);
+            codes[(0 * RING + (r % RING)) * NT + t] = (unsigned short)pair_code(a, b);
+            pair_terms(a, b, w1, w2, sh, homog_fx);
+            cs.w1[0] += w1, cs.w2[0] += w2, cs.sh[0] += sh;
         }
-    };
-    auto row_update = [&](int r, bool with_next, int sign) {
-        for (int c = 0; c < win; ++c) {
-            const int a = Q(r, t + c);
-            if (c + 1 < win) pair_update(0, a, Q(r, t + c + 1), sign);
-            if (with_next) {
-                if (c + 1 < win) pair_update(1, a, Q(r + 1, t + c + 1), sign);
-                pair_update(2, a, Q(r + 1, t + c), sign);
-                if (c >= 1) pair_update(3, a, Q(r + 1, t + c - 1), sign);
+        if (!first) {
+            const int up = Q(r - 1, t);
+            if (t + 1 < NT) {  // angle 1: (r-1,t)-(r,t+1)
+                const int b = Q(r, t + 1);
+                codes[(1 * RING + ((r - 1) % RING)) * NT + t] = (unsigned short)pair_code(up, b);
+                pair_terms(up, b, w1, w2, sh, homog_fx);
+                cs.w1[1] += w1, cs.w2[1] += w2, cs.sh[1] += sh;
+            }
+            {  // angle 2: (r-1,t)-(r,t)
+                codes[(2 * RING + ((r - 1) % RING)) * NT + t] = (unsigned short)pair_code(up, a);
+                pair_terms(up, a, w1, w2, sh, homog_fx);
+                cs.w1[2] += w1, cs.w2[2] += w2, cs.sh[2] += sh;
+            }
+            if (t >= 1) {  // angle 3: (r-1,t)-(r,t-1)
+                const int b = Q(r, t - 1);
+                codes[(3 * RING + ((r - 1) % RING)) * NT + t] = (unsigned short)pair_code(up, b);
+                pair_terms(up, b, w1, w2, sh, homog_fx);
+                cs.w1[3] += w1, cs.w2[3] += w2, cs.sh[3] += sh;
             }
         }
     };
-
-    // prologue: rows of the first window
-    for (int r = 0; r < win; ++r) load_row(i_begin + r);
-    __syncthreads();
-    if (active)
-        for (int r = 0; r < win; ++r) row_update(i_begin + r, r + 1 < win, +1);
-
-    for (int i = i_begin; i < i_end; ++i) {
-        if (active) {
-            double acc[5] = {0, 0, 0, 0, 0};
+    // Take the pairs anchored in image row r out of the column sums (rows r and r+1 are still in the ring).
+    auto leave_row = [&](int r) {
+        const int a = Q(r, t);
+        unsigned w1, w2;
+        unsigned long long sh;
+        if (t + 1 < NT) {
+            pair_terms(a, Q(r, t + 1), w1, w2, sh, homog_fx);
+            cs.w1[0] -= w1, cs.w2[0] -= w2, cs.sh[0] -= sh;
+            pair_terms(a, Q(r + 1, t + 1), w1, w2, sh, homog_fx);
+            cs.w1[1] -= w1, cs.w2[1] -= w2, cs.sh[1] -= sh;
+        }
+        pair_terms(a, Q(r + 1, t), w1, w2, sh, homog_fx);
+        cs.w1[2] -= w1, cs.w2[2] -= w2, cs.sh[2] -= sh;
+        if (t >= 1) {
+            pair_terms(a, Q(r + 1, t - 1), w1, w2, sh, homog_fx);
+            cs.w1[3] -= w1, cs.w2[3] -= w2, cs.sh[3] -= sh;
+        }
+    };
+    // energy counters of this thread's window: add (SIGN=+1) / remove (SIGN=-1) the pairs anchored in image row r
+    auto energy_row = [&](int r, bool with_ang0, bool with_ang123, int sign) {
+#pragma unroll
+        for (int c = 0; c < WIN; ++c) {
 #pragma unroll
             for (int ang = 0; ang < 4; ++ang) {
-                const int n = (ang == 0 || ang == 2) ? win * (win - 1) : (win - 1) * (win - 1);
-                AngleSums ts = {s1[ang], sa[ang], sq[ang], sab[ang], e[ang], sh[ang]};
-                angle_props(ts, n, acc);
+                if (ang == 0 ? !with_ang0 : !with_ang123) continue;
+                if (c < dense_c0(ang) || c >= dense_c1(ang, WIN)) continue;
+                const unsigned code = CODE(ang, r, t + c);
+                unsigned char* cell = cnt + ((size_t)ang * ncell + (code & 0x3ffu)) * NTW + t;
+                const int wgt = (code & 0x8000u) ? 4 : 2;
+                const int u = *cell;
+                if (sign > 0) {
+                    e[ang] += wgt * (2 * u + 1);
+                    *cell = (unsigned char)(u + 1);
+                } else {
+                    e[ang] -= wgt * (2 * u - 1);
+                    *cell = (unsigned char)(u - 1);
+                }
             }
-            const int64_t o = (int64_t)i * out_cols + j;
-#pragma unroll
-            for (int k = 0; k < 5; ++k) props[k * plane_stride + o] = (float)(acc[k] * 0.25);
         }
-        if (i + 1 >= i_end) break;
-        // slide down: image row i leaves, image row i+win enters
-        __syncthreads();  // everyone finished reading the ring slot that row i+win overwrites (slot of row i-1... see ring = win+1)
-        load_row(i + win);
-        __syncthreads();
-        if (active) {
-            // leaving: pairs anchored in row i (angle 0 within row i; angles 1-3 between rows i and i+1)
-            row_update(i, true, -1);
-            // entering: angle 0 within row i+win; angles 1-3 between rows i+win-1 and i+win
-            for (int c = 0; c < win; ++c) {
-                const int a = Q(i + win, t + c);
-                if (c + 1 < win) pair_update(0, a, Q(i + win, t + c + 1), +1);
-            }
-            for (int c = 0; c < win; ++c) {
-                const int a = Q(i + win - 1, t + c);
-                if (c + 1 < win) pair_update(1, a, Q(i + win, t + c + 1), +1);
-                pair_update(2, a, Q(i + win, t + c), +1);
-                if (c >= 1) pair_update(3, a, Q(i + win, t + c - 1), +1);
-            }
+    };
+
+    __syncthreads();
+    // prologue: the WIN rows of the first window
+    for (int r = 0; r < WIN; ++r) {
+        enter_row(i_begin + r, r == 0);
+        __syncthreads();  // codes of this row (and of row-1 for angles 1-3) are visible
+        if (has_win) {
+            energy_row(i_begin + r, true, false, +1);
+            if (r > 0) energy_row(i_begin + r - 1, false, true, +1);
         }
     }
+
+    const float inv_n[4] = {1.f / (WIN * (WIN - 1)), 1.f / ((WIN - 1) * (WIN - 1)), 1.f / (WIN * (WIN - 1)), 1.f / ((WIN - 1) * (WIN - 1))};
+    const int n_pairs[4] = {WIN * (WIN - 1), (WIN - 1) * (WIN - 1), WIN * (WIN - 1), (WIN - 1) * (WIN - 1)};
+
+    for (int i = i_begin; i < i_end; ++i) {
+        // publish column sums, then every window adds the columns it spans
+        __syncthreads();  // previous iteration's readers of xch are done
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            xch[(a * 4 + 0) * NT + t] = cs.w1[a];
+            xch[(a * 4 + 1) * NT + t] = cs.w2[a];
+            xch[(a * 4 + 2) * NT + t] = (unsigned)cs.sh[a];
+            xch[(a * 4 + 3) * NT + t] = (unsigned)(cs.sh[a] >> 32);
+        }
+        __syncthreads();
+        if (has_win) {
+            float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                unsigned w1 = 0, w2 = 0;
+                unsigned long long sh = 0;
+#pragma unroll
+                for (int c = dense_c0(a); c < dense_c1(a, WIN); ++c) {
+                    w1 += xch[(a * 4 + 0) * NT + t + c];
+                    w2 += xch[(a * 4 + 1) * NT + t + c];
+                    sh += (unsigned long long)xch[(a * 4 + 2) * NT + t + c] | ((unsigned long long)xch[(a * 4 + 3) * NT + t + c] << 32);
+                }
+                const int s1 = (int)(w1 & 0x1fffu), sab = (int)(w1 >> 13);
+                const int sa = (int)(w2 & 0x3fffu), sq = (int)(w2 >> 14);
+                const int n = n_pairs[a];
+                acc[0] += (float)(sq - 2 * sab) * inv_n[a];
+                acc[1] += (float)s1 * inv_n[a];
+                acc[2] += (float)((double)sh * 9.094947017729282e-13) * inv_n[a];  // 2^-40
+                acc[3] += sqrtf((float)e[a]) * (0.5f * inv_n[a]);
+                const int var_num = 2 * n * sq - sa * sa, cov_num = 4 * n * sab - sa * sa;
+                acc[4] += var_num <= 0 ? 1.f : (float)cov_num / (float)var_num;
+            }
+            const int64_t o = (int64_t)i * out_cols + j0 + t;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) props[k * plane_stride + o] = acc[k] * 0.25f;
+        }
+        if (i + 1 >= i_end) break;
+        // slide: image row i leaves, image row i+WIN enters
+        leave_row(i);
+        __syncthreads();  // every thread has read rows i, i+1 of the q ring before row i+WIN overwrites slot (i-1... RING = WIN+1)
+        if (has_win) {
+            energy_row(i, true, true, -1);
+        }
+        __syncthreads();  // codes of row i consumed before its ring slot is reused
+        enter_row(i + WIN, false);
+        __syncthreads();
+        if (has_win) {
+            energy_row(i + WIN, true, false, +1);
+            energy_row(i + WIN - 1, false, true, +1);
+        }
+    }
+}
+
+template <int WIN, int NT>
+static int launch_dense(const uint8_t* d_q, int W, int levels, int out_rows, int out_cols, float* d_props, int64_t plane_stride, cudaStream_t s) {
+    constexpr int NTW = NT - (WIN - 1);
+    const int ncell = levels * (levels + 1) / 2;
+    const size_t smem = (size_t)4 * ncell * NTW + (size_t)4 * (WIN + 1) * NT * 2 + (size_t)16 * NT * 4 + (size_t)(WIN + 1) * NT + 64;
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(glcm_dense_kernel<WIN, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max(smem, (size_t)49152));
+        if (e != cudaSuccess) {
+            rsx_set_error("rsx_glcm_props: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
+            return RSX_ERR_CUDA;
+        }
+        configured = smem;
+    }
+    const int gx = ceil_div(out_cols, NTW);
+    // rows per CTA: balance whole waves over the SMs against the (WIN-1)-row prologue every CTA pays
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, glcm_dense_kernel<WIN, NT>, NT, smem);
+    occ = max(occ, 1);
+    const int slots = rsx_num_sms() * occ;
+    int best_gy = 1;
+    double best_eff = 0.0;
+    for (int gy = 1; gy <= max(1, out_rows / (4 * WIN)); ++gy) {
+        const int rows = ceil_div(out_rows, gy);
+        const int64_t ctas = (int64_t)gx * ceil_div(out_rows, rows);
+        const double waves = (double)ctas / slots;
+        const double eff = waves / ceil(waves) * rows / (rows + WIN - 1.0);
+        if (eff > best_eff + 1e-9) best_eff = eff, best_gy = gy;
+    }
+    const int rows_per_cta = ceil_div(out_rows, best_gy);
+    const int gy = ceil_div(out_rows, rows_per_cta);
+    glcm_dense_kernel<WIN, NT><<<dim3(gx, gy), NT, smem, s>>>(d_q, W, levels, out_rows, out_cols, rows_per_cta, d_props, plane_stride);
+    return rsx_check_launch("glcm_dense");
+}
+
+// pick the widest CTA whose private counters fit in shared memory
+template <int WIN>
+static int dispatch_dense(const uint8_t* d_q, int W, int levels, int out_rows, int out_cols, float* d_props, int64_t plane_stride, cudaStream_t s) {
+    const int ncell = levels * (levels + 1) / 2;
+    auto fits = [&](int nt) { return (size_t)4 * ncell * (nt - (WIN - 1)) + (size_t)nt * (8 * (WIN + 1) + 64 + (WIN + 1)) + 64 <= (size_t)220 * 1024; };
+    if (fits(256)) return launch_dense<WIN, 256>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, s);
+    if (fits(128)) return launch_dense<WIN, 128>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, s);
+    if (fits(96)) return launch_dense<WIN, 96>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, s);
+    if (fits(64)) return launch_dense<WIN, 64>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, s);
+    return -1;
 }
 
 extern "C" int rsx_glcm_props(const uint8_t* d_q, int rows_avail, int W, int levels, int window, int step, int out_rows, int out_cols,
@@ -258,27 +390,18 @@ extern "C" int rsx_glcm_props(const uint8_t* d_q, int rows_avail, int W, int lev
     if (int rc = ensure_homog()) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     const int ncell = levels * (levels + 1) / 2;
-    // dense path: thread-private uint8 counters must hold w(w-1) and fit in shared memory
-    constexpr int NT = 64;
-    const size_t dense_smem = (size_t)4 * ncell * NT + (size_t)(window + 1) * (NT + window - 1);
-    if (step == 1 && window * (window - 1) <= 255 && dense_smem <= 200 * 1024) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaError_t e = cudaFuncSetAttribute(glcm_props_dense_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            if (e != cudaSuccess) {
-                rsx_set_error("rsx_glcm_props: %s", cudaGetErrorString(e));
-                return RSX_ERR_CUDA;
-            }
-            attr_set = true;
+    // dense fast path: packed moments need levels <= 32 and window <= 12; uint8 counters hold w(w-1) <= 132
+    if (step == 1 && levels <= 32) {
+        int rc = -1;
+        switch (window) {
+            case 3: rc = dispatch_dense<3>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, s); break;
+            case 5: rc = dispatch_dense<5>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, s); break;
+            case 7: rc = dispatch_dense<7>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, s); break;
+            case 9: rc = dispatch_dense<9>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, s); break;
+            case 11: rc = dispatch_dense<11>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, s); break;
+            default: break;
         }
-        const int gx = ceil_div(out_cols, NT);
-        // enough row strips to fill the machine ~4x, but long enough to amortise the (window-1)-row prologue
-        int strips = max(1, (rsx_num_sms() * 4) / gx);
-        int rows_per_cta = max(8 * window, ceil_div(out_rows, strips));
-        rows_per_cta = min(rows_per_cta, out_rows);
-        const int gy = ceil_div(out_rows, rows_per_cta);
-        glcm_props_dense_kernel<NT><<<dim3(gx, gy), NT, dense_smem, s>>>(d_q, W, levels, window, out_rows, out_cols, rows_per_cta, d_props, plane_stride);
-        return rsx_check_launch("glcm_props_dense");
+        if (rc >= 0) return rc;
     }
     const size_t smem = (size_t)4 * ncell * 4;
     static bool attr_set2 = false;
