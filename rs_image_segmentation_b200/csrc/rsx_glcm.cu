@@ -156,179 +156,163 @@ __device__ __forceinline__ void pair_terms(int a, int b, unsigned& w1, unsigned&
     sh = homog_fx[d];
 }
 
+// Thread (t, ang): t = image column inside the CTA's band (threadIdx.x, NT of them, NT % 32 == 0 so a warp has one
+// angle), ang = threadIdx.y.  Each thread owns the column sums of ITS angle at ITS column and - if t < NTW - the
+// angle's energy counters and window sums of window t; the four angle threads of a window meet in shared memory.
 template <int WIN, int NT>
-__global__ void __launch_bounds__(NT) glcm_dense_kernel(const uint8_t* __restrict__ q, int W, int L, int out_rows, int out_cols, int rows_per_cta,
-                                                        float* __restrict__ props, int64_t plane_stride) {
+__global__ void __launch_bounds__(NT * 4) glcm_dense_kernel(const uint8_t* __restrict__ q, int W, int L, int out_rows, int out_cols, int rows_per_cta,
+                                                            float* __restrict__ props, int64_t plane_stride) {
     constexpr int NTW = NT - (WIN - 1);  // windows per CTA
     constexpr int RING = WIN + 1;
     extern __shared__ __align__(16) unsigned char dsm[];
     const int ncell = L * (L + 1) / 2;
-    unsigned char* cnt = dsm;                                                            // [4][ncell][NTW] u8
+    unsigned char* cnt = dsm;                                                                  // [4][ncell][NTW] u8
     unsigned short* codes = reinterpret_cast<unsigned short*>(dsm + (size_t)4 * ncell * NTW);  // [4][RING][NT] u16
-    unsigned* xch = reinterpret_cast<unsigned*>(codes + 4 * RING * NT);                        // [16][NT] u32 column sums
-    unsigned char* qring = reinterpret_cast<unsigned char*>(xch + 16 * NT);               // [RING][NT] u8
+    unsigned* xch = reinterpret_cast<unsigned*>(codes + 4 * RING * NT);                        // [4 ang][4 words][NT] u32 column sums
+    float* outx = reinterpret_cast<float*>(xch + 16 * NT);                                     // [4 ang][5][NT] partial properties
+    unsigned char* qring = reinterpret_cast<unsigned char*>(outx + 20 * NT);                   // [RING][NT] u8
     __shared__ unsigned long long homog_fx[64];
 
-    const int t = threadIdx.x;
+    const int t = threadIdx.x, ang = threadIdx.y;
+    const int tid = ang * NT + t;
     const int j0 = blockIdx.x * NTW;  // first window column == first image column of this CTA
     const int i_begin = blockIdx.y * rows_per_cta;
     const int i_end = min(out_rows, i_begin + rows_per_cta);
     if (i_begin >= i_end) return;
     const bool has_win = t < NTW && j0 + t < out_cols;
-
-    for (int i = t; i < 4 * ncell * NTW / 4; i += NT) reinterpret_cast<unsigned*>(cnt)[i] = 0;
-    if (t < 64) homog_fx[t] = (unsigned long long)(1099511627776.0 / (1.0 + (double)t * (double)t) + 0.5);  // 2^40/(1+k^2)
-
-    ColSums cs;
-#pragma unroll
-    for (int a = 0; a < 4; ++a) cs.w1[a] = 0, cs.w2[a] = 0, cs.sh[a] = 0;
-    int e[4] = {0, 0, 0, 0};
     const bool col_ok = j0 + t < W;
 
-    auto Q = [&](int row, int c) -> int { return qring[(row % RING) * NT + c]; };
-    auto CODE = [&](int ang, int row, int c) -> unsigned { return codes[(ang * RING + (row % RING)) * NT + c]; };
+    for (int i = tid; i < 4 * ncell * NTW / 4; i += 4 * NT) reinterpret_cast<unsigned*>(cnt)[i] = 0;
+    if (tid < 64) homog_fx[tid] = (unsigned long long)(1099511627776.0 / (1.0 + (double)tid * (double)tid) + 0.5);  // 2^40/(1+k^2)
 
-    // Bring image row r in: q ring, then the pairs that become complete (angle 0 inside row r; angles 1-3 between
-    // rows r-1 and r, anchored in row r-1).  `first` = r is the first row of the band (no row above).
-    auto enter_row = [&](int r, bool first) {
-        qring[(r % RING) * NT + t] = col_ok ? (unsigned char)min((int)q[(int64_t)r * W + j0 + t], L - 1) : 0;
-        __syncthreads();
-        const int a = Q(r, t);
-        unsigned w1, w2;
-        unsigned long long sh;
-        if (t + 1 < NT) {  // angle 0: (r,t)-(r,t+1)
-            const int b = Q(r, t + 1);
-            codes[(0 * RING + (r % RING)) * NT + t] = (unsigned short)pair_code(a, b);
+    // geometry of this thread's angle: the partner of anchor (r, c) is (r + dr, c + dc)
+    const int dr = ang == 0 ? 0 : 1;
+    const int dc = ang == 0 ? 1 : (ang == 1 ? 1 : (ang == 2 ? 0 : -1));
+    const int c0 = ang == 3 ? 1 : 0, c1 = ang <= 1 ? WIN - 1 : WIN;  // anchor columns of the angle inside a window
+    const bool pair_ok = t + dc >= 0 && t + dc < NT;                  // partner column inside the band
+    const int n = (ang == 0 || ang == 2) ? WIN * (WIN - 1) : (WIN - 1) * (WIN - 1);
+    const float inv_n = 1.f / (float)n;
+
+    unsigned cw1 = 0, cw2 = 0;  // column sums of this (column, angle): packed moments
+    unsigned long long csh = 0;
+    int e = 0;
+    unsigned short* my_codes = codes + ang * RING * NT;
+    unsigned char* my_cnt = cnt + (size_t)ang * ncell * NTW + t;
+
+    auto Q = [&](int row, int c) -> int { return qring[(row % RING) * NT + c]; };
+    auto load_q = [&](int r) -> unsigned char { return col_ok ? (unsigned char)min((int)q[(int64_t)r * W + j0 + t], L - 1) : (unsigned char)0; };
+
+    // pairs of this angle anchored in row ra become complete when row ra + dr is in the ring
+    auto enter_pairs = [&](int ra) {
+        if (pair_ok) {
+            const int a = Q(ra, t), b = Q(ra + dr, t + dc);
+            my_codes[(ra % RING) * NT + t] = (unsigned short)pair_code(a, b);
+            unsigned w1, w2;
+            unsigned long long sh;
             pair_terms(a, b, w1, w2, sh, homog_fx);
-            cs.w1[0] += w1, cs.w2[0] += w2, cs.sh[0] += sh;
-        }
-        if (!first) {
-            const int up = Q(r - 1, t);
-            if (t + 1 < NT) {  // angle 1: (r-1,t)-(r,t+1)
-                const int b = Q(r, t + 1);
-                codes[(1 * RING + ((r - 1) % RING)) * NT + t] = (unsigned short)pair_code(up, b);
-                pair_terms(up, b, w1, w2, sh, homog_fx);
-                cs.w1[1] += w1, cs.w2[1] += w2, cs.sh[1] += sh;
-            }
-            {  // angle 2: (r-1,t)-(r,t)
-                codes[(2 * RING + ((r - 1) % RING)) * NT + t] = (unsigned short)pair_code(up, a);
-                pair_terms(up, a, w1, w2, sh, homog_fx);
-                cs.w1[2] += w1, cs.w2[2] += w2, cs.sh[2] += sh;
-            }
-            if (t >= 1) {  // angle 3: (r-1,t)-(r,t-1)
-                const int b = Q(r, t - 1);
-                codes[(3 * RING + ((r - 1) % RING)) * NT + t] = (unsigned short)pair_code(up, b);
-                pair_terms(up, b, w1, w2, sh, homog_fx);
-                cs.w1[3] += w1, cs.w2[3] += w2, cs.sh[3] += sh;
-            }
+            cw1 += w1, cw2 += w2, csh += sh;
         }
     };
-    // Take the pairs anchored in image row r out of the column sums (rows r and r+1 are still in the ring).
-    auto leave_row = [&](int r) {
-        const int a = Q(r, t);
-        unsigned w1, w2;
-        unsigned long long sh;
-        if (t + 1 < NT) {
-            pair_terms(a, Q(r, t + 1), w1, w2, sh, homog_fx);
-            cs.w1[0] -= w1, cs.w2[0] -= w2, cs.sh[0] -= sh;
-            pair_terms(a, Q(r + 1, t + 1), w1, w2, sh, homog_fx);
-            cs.w1[1] -= w1, cs.w2[1] -= w2, cs.sh[1] -= sh;
-        }
-        pair_terms(a, Q(r + 1, t), w1, w2, sh, homog_fx);
-        cs.w1[2] -= w1, cs.w2[2] -= w2, cs.sh[2] -= sh;
-        if (t >= 1) {
-            pair_terms(a, Q(r + 1, t - 1), w1, w2, sh, homog_fx);
-            cs.w1[3] -= w1, cs.w2[3] -= w2, cs.sh[3] -= sh;
+    auto leave_pairs = [&](int ra) {
+        if (pair_ok) {
+            unsigned w1, w2;
+            unsigned long long sh;
+            pair_terms(Q(ra, t), Q(ra + dr, t + dc), w1, w2, sh, homog_fx);
+            cw1 -= w1, cw2 -= w2, csh -= sh;
         }
     };
-    // energy counters of this thread's window: add (SIGN=+1) / remove (SIGN=-1) the pairs anchored in image row r
-    auto energy_row = [&](int r, bool with_ang0, bool with_ang123, int sign) {
+    auto energy_add = [&](int ra) {
+        const unsigned short* row = my_codes + (ra % RING) * NT + t;
 #pragma unroll
         for (int c = 0; c < WIN; ++c) {
+            if (c < c0 || c >= c1) continue;
+            const unsigned code = row[c];
+            unsigned char* cell = my_cnt + (code & 0x3ffu) * NTW;
+            const int u = *cell;
+            e += ((code & 0x8000u) ? 4 : 2) * (2 * u + 1);
+            *cell = (unsigned char)(u + 1);
+        }
+    };
+    auto energy_sub = [&](int ra) {
+        const unsigned short* row = my_codes + (ra % RING) * NT + t;
 #pragma unroll
-            for (int ang = 0; ang < 4; ++ang) {
-                if (ang == 0 ? !with_ang0 : !with_ang123) continue;
-                if (c < dense_c0(ang) || c >= dense_c1(ang, WIN)) continue;
-                const unsigned code = CODE(ang, r, t + c);
-                unsigned char* cell = cnt + ((size_t)ang * ncell + (code & 0x3ffu)) * NTW + t;
-                const int wgt = (code & 0x8000u) ? 4 : 2;
-                const int u = *cell;
-                if (sign > 0) {
-                    e[ang] += wgt * (2 * u + 1);
-                    *cell = (unsigned char)(u + 1);
-                } else {
-                    e[ang] -= wgt * (2 * u - 1);
-                    *cell = (unsigned char)(u - 1);
-                }
-            }
+        for (int c = 0; c < WIN; ++c) {
+            if (c < c0 || c >= c1) continue;
+            const unsigned code = row[c];
+            unsigned char* cell = my_cnt + (code & 0x3ffu) * NTW;
+            const int u = *cell;
+            e -= ((code & 0x8000u) ? 4 : 2) * (2 * u - 1);
+            *cell = (unsigned char)(u - 1);
         }
     };
 
+    // prologue: bring in the WIN rows of the first window
     __syncthreads();
-    // prologue: the WIN rows of the first window
     for (int r = 0; r < WIN; ++r) {
-        enter_row(i_begin + r, r == 0);
-        __syncthreads();  // codes of this row (and of row-1 for angles 1-3) are visible
-        if (has_win) {
-            energy_row(i_begin + r, true, false, +1);
-            if (r > 0) energy_row(i_begin + r - 1, false, true, +1);
-        }
+        if (ang == 0) qring[((i_begin + r) % RING) * NT + t] = load_q(i_begin + r);
+        __syncthreads();
+        const int ra = i_begin + r - dr;  // anchor row completed by this row
+        if (ra >= i_begin) enter_pairs(ra);
+        __syncthreads();
+        if (has_win && ra >= i_begin) energy_add(ra);
     }
-
-    const float inv_n[4] = {1.f / (WIN * (WIN - 1)), 1.f / ((WIN - 1) * (WIN - 1)), 1.f / (WIN * (WIN - 1)), 1.f / ((WIN - 1) * (WIN - 1))};
-    const int n_pairs[4] = {WIN * (WIN - 1), (WIN - 1) * (WIN - 1), WIN * (WIN - 1), (WIN - 1) * (WIN - 1)};
+    unsigned char q_next = 0;  // register prefetch of the next row's sample
+    if (ang == 0 && i_begin + WIN < i_end + WIN - 1) q_next = load_q(i_begin + WIN);
 
     for (int i = i_begin; i < i_end; ++i) {
-        // publish column sums, then every window adds the columns it spans
-        __syncthreads();  // previous iteration's readers of xch are done
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            xch[(a * 4 + 0) * NT + t] = cs.w1[a];
-            xch[(a * 4 + 1) * NT + t] = cs.w2[a];
-            xch[(a * 4 + 2) * NT + t] = (unsigned)cs.sh[a];
-            xch[(a * 4 + 3) * NT + t] = (unsigned)(cs.sh[a] >> 32);
-        }
-        __syncthreads();
+        // (a) publish column sums
+        unsigned* xa = xch + ang * 4 * NT;
+        xa[0 * NT + t] = cw1;
+        xa[1 * NT + t] = cw2;
+        xa[2 * NT + t] = (unsigned)csh;
+        xa[3 * NT + t] = (unsigned)(csh >> 32);
+        __syncthreads();  // #1
+        // (b) window sums of this angle -> its share of the five properties
         if (has_win) {
-            float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+            unsigned w1 = 0, w2 = 0;
+            unsigned long long sh = 0;
 #pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                unsigned w1 = 0, w2 = 0;
-                unsigned long long sh = 0;
-#pragma unroll
-                for (int c = dense_c0(a); c < dense_c1(a, WIN); ++c) {
-                    w1 += xch[(a * 4 + 0) * NT + t + c];
-                    w2 += xch[(a * 4 + 1) * NT + t + c];
-                    sh += (unsigned long long)xch[(a * 4 + 2) * NT + t + c] | ((unsigned long long)xch[(a * 4 + 3) * NT + t + c] << 32);
-                }
-                const int s1 = (int)(w1 & 0x1fffu), sab = (int)(w1 >> 13);
-                const int sa = (int)(w2 & 0x3fffu), sq = (int)(w2 >> 14);
-                const int n = n_pairs[a];
-                acc[0] += (float)(sq - 2 * sab) * inv_n[a];
-                acc[1] += (float)s1 * inv_n[a];
-                acc[2] += (float)((double)sh * 9.094947017729282e-13) * inv_n[a];  // 2^-40
-                acc[3] += sqrtf((float)e[a]) * (0.5f * inv_n[a]);
-                const int var_num = 2 * n * sq - sa * sa, cov_num = 4 * n * sab - sa * sa;
-                acc[4] += var_num <= 0 ? 1.f : (float)cov_num / (float)var_num;
+            for (int c = 0; c < WIN; ++c) {
+                if (c < c0 || c >= c1) continue;
+                w1 += xa[0 * NT + t + c];
+                w2 += xa[1 * NT + t + c];
+                sh += (unsigned long long)xa[2 * NT + t + c] | ((unsigned long long)xa[3 * NT + t + c] << 32);
             }
-            const int64_t o = (int64_t)i * out_cols + j0 + t;
+            const int s1 = (int)(w1 & 0x1fffu), sab = (int)(w1 >> 13);
+            const int sa = (int)(w2 & 0x3fffu), sq = (int)(w2 >> 14);
+            float* o = outx + ang * 5 * NT + t;
+            o[0 * NT] = (float)(sq - 2 * sab) * inv_n;
+            o[1 * NT] = (float)s1 * inv_n;
+            o[2 * NT] = (float)((double)sh * 9.094947017729282e-13) * inv_n;  // 2^-40
+            o[3 * NT] = sqrtf((float)e) * (0.5f * inv_n);
+            const int var_num = 2 * n * sq - sa * sa, cov_num = 4 * n * sab - sa * sa;
+            o[4 * NT] = var_num <= 0 ? 1.f : (float)cov_num / (float)var_num;
+        }
+        const bool more = i + 1 < i_end;
+        if (more) {
+            // (c) the window moves down: pairs anchored in image row i leave
+            leave_pairs(i);
+            if (has_win) energy_sub(i);
+            // (d) image row i + WIN enters the ring
+            if (ang == 0) qring[((i + WIN) % RING) * NT + t] = q_next;
+        }
+        __syncthreads();  // #2: outx complete, new q row visible
+        if (ang == 0) {
+            if (more && i + 2 < i_end) q_next = load_q(i + WIN + 1);
+            if (has_win) {
+                const int64_t o = (int64_t)i * out_cols + j0 + t;
 #pragma unroll
-            for (int k = 0; k < 5; ++k) props[k * plane_stride + o] = acc[k] * 0.25f;
+                for (int k = 0; k < 5; ++k) {
+                    const float v = (outx[(0 * 5 + k) * NT + t] + outx[(1 * 5 + k) * NT + t]) + (outx[(2 * 5 + k) * NT + t] + outx[(3 * 5 + k) * NT + t]);
+                    props[k * plane_stride + o] = v * 0.25f;
+                }
+            }
         }
-        if (i + 1 >= i_end) break;
-        // slide: image row i leaves, image row i+WIN enters
-        leave_row(i);
-        __syncthreads();  // every thread has read rows i, i+1 of the q ring before row i+WIN overwrites slot (i-1... RING = WIN+1)
-        if (has_win) {
-            energy_row(i, true, true, -1);
-        }
-        __syncthreads();  // codes of row i consumed before its ring slot is reused
-        enter_row(i + WIN, false);
-        __syncthreads();
-        if (has_win) {
-            energy_row(i + WIN, true, false, +1);
-            energy_row(i + WIN - 1, false, true, +1);
-        }
+        if (!more) break;
+        // (e) pairs completed by the new row: anchored in row i + WIN - dr
+        enter_pairs(i + WIN - dr);
+        __syncthreads();  // #3: their codes are visible
+        if (has_win) energy_add(i + WIN - dr);
     }
 }
 
@@ -336,7 +320,7 @@ template <int WIN, int NT>
 static int launch_dense(const uint8_t* d_q, int W, int levels, int out_rows, int out_cols, float* d_props, int64_t plane_stride, cudaStream_t s) {
     constexpr int NTW = NT - (WIN - 1);
     const int ncell = levels * (levels + 1) / 2;
-    const size_t smem = (size_t)4 * ncell * NTW + (size_t)4 * (WIN + 1) * NT * 2 + (size_t)16 * NT * 4 + (size_t)(WIN + 1) * NT + 64;
+    const size_t smem = (size_t)4 * ncell * NTW + (size_t)4 * (WIN + 1) * NT * 2 + (size_t)16 * NT * 4 + (size_t)20 * NT * 4 + (size_t)(WIN + 1) * NT + 64;
     static size_t configured = 0;
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(glcm_dense_kernel<WIN, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max(smem, (size_t)49152));
@@ -349,7 +333,7 @@ static int launch_dense(const uint8_t* d_q, int W, int levels, int out_rows, int
     const int gx = ceil_div(out_cols, NTW);
     // rows per CTA: balance whole waves over the SMs against the (WIN-1)-row prologue every CTA pays
     int occ = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, glcm_dense_kernel<WIN, NT>, NT, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, glcm_dense_kernel<WIN, NT>, NT * 4, smem);
     occ = max(occ, 1);
     const int slots = rsx_num_sms() * occ;
     int best_gy = 1;
@@ -363,7 +347,7 @@ static int launch_dense(const uint8_t* d_q, int W, int levels, int out_rows, int
     }
     const int rows_per_cta = ceil_div(out_rows, best_gy);
     const int gy = ceil_div(out_rows, rows_per_cta);
-    glcm_dense_kernel<WIN, NT><<<dim3(gx, gy), NT, smem, s>>>(d_q, W, levels, out_rows, out_cols, rows_per_cta, d_props, plane_stride);
+    glcm_dense_kernel<WIN, NT><<<dim3(gx, gy), dim3(NT, 4), smem, s>>>(d_q, W, levels, out_rows, out_cols, rows_per_cta, d_props, plane_stride);
     return rsx_check_launch("glcm_dense");
 }
 
@@ -371,7 +355,7 @@ static int launch_dense(const uint8_t* d_q, int W, int levels, int out_rows, int
 template <int WIN>
 static int dispatch_dense(const uint8_t* d_q, int W, int levels, int out_rows, int out_cols, float* d_props, int64_t plane_stride, cudaStream_t s) {
     const int ncell = levels * (levels + 1) / 2;
-    auto fits = [&](int nt) { return (size_t)4 * ncell * (nt - (WIN - 1)) + (size_t)nt * (8 * (WIN + 1) + 64 + (WIN + 1)) + 64 <= (size_t)220 * 1024; };
+    auto fits = [&](int nt) { return (size_t)4 * ncell * (nt - (WIN - 1)) + (size_t)nt * (8 * (WIN + 1) + 64 + 80 + (WIN + 1)) + 64 <= (size_t)224 * 1024; };
     if (fits(256)) return launch_dense<WIN, 256>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, s);
     if (fits(128)) return launch_dense<WIN, 128>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, s);
     if (fits(96)) return launch_dense<WIN, 96>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, s);
