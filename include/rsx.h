@@ -164,12 +164,15 @@ int64_t rsx_kmeans_state_bytes(void);
  * Not re-entrant: the state is mirrored in one __constant__ block per process. */
 int rsx_kmeans_setup(void* d_state, int D, int K, const double* h_feat_min, const double* h_feat_max,
                      const double* h_mean_scaled, const double* h_init_centroids, int64_t n_px_global, rsx_stream_t stream);
-/* d_acc: int64 [K*D + K + 1] = sums [K][D], counts [K], near-tie counter [1]; caller zeroes it once.
+/* d_acc: int64 [K*D + K + 2] = sums [K][D], counts [K], near-tie counter, changed-label counter; the caller
+ * zeroes it once (rsx_kmeans_update re-zeroes sums and counts, the two counters keep accumulating).
+ * d_labels_prev_u8 (may be NULL): labels of the previous pass; the number of pixels whose label differs is
+ * added to the changed-label counter (sklearn's strict-convergence test, _kmeans.py:723).
  * row_len: length (pixels) of an image row; only steers the traversal order (threads walk down columns
  * so that runs of equal labels stay in registers); any value gives the same result. */
 int rsx_kmeans_assign(const float* d_stack, int64_t plane_stride, int64_t n_px, int row_len, const void* d_state,
-                      int64_t* d_acc, uint8_t* d_labels_u8, int32_t* d_labels_i32, double* d_inertia, int update, int D,
-                      int K, rsx_stream_t stream);
+                      int64_t* d_acc, uint8_t* d_labels_u8, const uint8_t* d_labels_prev_u8, int32_t* d_labels_i32,
+                      double* d_inertia, int update, int D, int K, rsx_stream_t stream);
 int rsx_kmeans_update(void* d_state, int64_t* d_acc, rsx_stream_t stream);
 /* SYNCHRONISES the stream; centroids come back in scaled, un-centred coordinates, double [K][D];
  * h_shift_sq = squared centre shift of the last update; h_empty = empty clusters met so far. */

@@ -166,11 +166,12 @@ __global__ void __launch_bounds__(NT * 4) glcm_dense_kernel(const uint8_t* __res
     constexpr int RING = WIN + 1;
     extern __shared__ __align__(16) unsigned char dsm[];
     const int ncell = L * (L + 1) / 2;
-    unsigned char* cnt = dsm;                                                                  // [4][ncell][NTW] u8
-    unsigned short* codes = reinterpret_cast<unsigned short*>(dsm + (size_t)4 * ncell * NTW);  // [4][RING][NT] u16
-    unsigned* xch = reinterpret_cast<unsigned*>(codes + 4 * RING * NT);                        // [4 ang][4 words][NT] u32 column sums
-    float* outx = reinterpret_cast<float*>(xch + 16 * NT);                                     // [4 ang][5][NT] partial properties
-    unsigned char* qring = reinterpret_cast<unsigned char*>(outx + 20 * NT);                   // [RING][NT] u8
+    // shared layout (16-byte aligned pieces first)
+    uint4* xch = reinterpret_cast<uint4*>(dsm);                             // [4 ang][NT]: w1, w2, sh.lo, sh.hi column sums
+    float* outx = reinterpret_cast<float*>(xch + 4 * NT);                   // [4 ang][5][NT] partial properties
+    unsigned* codes = reinterpret_cast<unsigned*>(outx + 20 * NT);          // [4][RING][NT]: (cell*NTW) << 1 | (a == b)
+    unsigned char* qring = reinterpret_cast<unsigned char*>(codes + 4 * RING * NT);  // [RING][NT] u8
+    unsigned char* cnt = qring + RING * NT;                                 // [4][ncell][NTW] u8
     __shared__ unsigned long long homog_fx[64];
 
     const int t = threadIdx.x, ang = threadIdx.y;
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(NT * 4) glcm_dense_kernel(const uint8_t* __res
     const bool has_win = t < NTW && j0 + t < out_cols;
     const bool col_ok = j0 + t < W;
 
-    for (int i = tid; i < 4 * ncell * NTW / 4; i += 4 * NT) reinterpret_cast<unsigned*>(cnt)[i] = 0;
+    for (int i = tid; i < 4 * ncell * NTW; i += 4 * NT) cnt[i] = 0;
     if (tid < 64) homog_fx[tid] = (unsigned long long)(1099511627776.0 / (1.0 + (double)tid * (double)tid) + 0.5);  // 2^40/(1+k^2)
 
     // geometry of this thread's angle: the partner of anchor (r, c) is (r + dr, c + dc)
@@ -196,87 +197,89 @@ __global__ void __launch_bounds__(NT * 4) glcm_dense_kernel(const uint8_t* __res
     unsigned cw1 = 0, cw2 = 0;  // column sums of this (column, angle): packed moments
     unsigned long long csh = 0;
     int e = 0;
-    unsigned short* my_codes = codes + ang * RING * NT;
+    unsigned* my_codes = codes + ang * RING * NT + t;
     unsigned char* my_cnt = cnt + (size_t)ang * ncell * NTW + t;
+    const unsigned char* qt = qring + t;
 
-    auto Q = [&](int row, int c) -> int { return qring[(row % RING) * NT + c]; };
+    // ring slot of an image row, kept incrementally: slot(i_begin + k) = k % RING
+    auto slot_add = [](int s, int k) { s += k; return s >= RING ? s - RING : s; };
+
     auto load_q = [&](int r) -> unsigned char { return col_ok ? (unsigned char)min((int)q[(int64_t)r * W + j0 + t], L - 1) : (unsigned char)0; };
-
-    // pairs of this angle anchored in row ra become complete when row ra + dr is in the ring
-    auto enter_pairs = [&](int ra) {
+    // pairs of this angle anchored in ring slot sa (partner row in slot sb) become complete
+    auto enter_pairs = [&](int sa, int sb) {
         if (pair_ok) {
-            const int a = Q(ra, t), b = Q(ra + dr, t + dc);
-            my_codes[(ra % RING) * NT + t] = (unsigned short)pair_code(a, b);
+            const int a = qt[sa * NT], b = qt[sb * NT + dc];
+            my_codes[sa * NT] = ((unsigned)(tri_cell(a, b) * NTW) << 1) | (a == b ? 1u : 0u);
             unsigned w1, w2;
             unsigned long long sh;
             pair_terms(a, b, w1, w2, sh, homog_fx);
             cw1 += w1, cw2 += w2, csh += sh;
         }
     };
-    auto leave_pairs = [&](int ra) {
+    auto leave_pairs = [&](int sa, int sb) {
         if (pair_ok) {
             unsigned w1, w2;
             unsigned long long sh;
-            pair_terms(Q(ra, t), Q(ra + dr, t + dc), w1, w2, sh, homog_fx);
+            pair_terms(qt[sa * NT], qt[sb * NT + dc], w1, w2, sh, homog_fx);
             cw1 -= w1, cw2 -= w2, csh -= sh;
         }
     };
-    auto energy_add = [&](int ra) {
-        const unsigned short* row = my_codes + (ra % RING) * NT + t;
+    // E = sum_cells weight * count^2, weight 2 (a != b) or 4 (a == b): (u+1)^2 - u^2 = 2u+1
+    auto energy_add = [&](int sa) {
+        const unsigned* row = my_codes + sa * NT;
 #pragma unroll
         for (int c = 0; c < WIN; ++c) {
             if (c < c0 || c >= c1) continue;
             const unsigned code = row[c];
-            unsigned char* cell = my_cnt + (code & 0x3ffu) * NTW;
+            unsigned char* cell = my_cnt + (code >> 1);
             const int u = *cell;
-            e += ((code & 0x8000u) ? 4 : 2) * (2 * u + 1);
+            e += (2 * u + 1) << (1 + (code & 1u));
             *cell = (unsigned char)(u + 1);
         }
     };
-    auto energy_sub = [&](int ra) {
-        const unsigned short* row = my_codes + (ra % RING) * NT + t;
+    auto energy_sub = [&](int sa) {
+        const unsigned* row = my_codes + sa * NT;
 #pragma unroll
         for (int c = 0; c < WIN; ++c) {
             if (c < c0 || c >= c1) continue;
             const unsigned code = row[c];
-            unsigned char* cell = my_cnt + (code & 0x3ffu) * NTW;
+            unsigned char* cell = my_cnt + (code >> 1);
             const int u = *cell;
-            e -= ((code & 0x8000u) ? 4 : 2) * (2 * u - 1);
+            e -= (2 * u - 1) << (1 + (code & 1u));
             *cell = (unsigned char)(u - 1);
         }
     };
 
-    // prologue: bring in the WIN rows of the first window
+    // prologue: bring in the WIN rows of the first window (row i_begin + r lives in slot r)
     __syncthreads();
     for (int r = 0; r < WIN; ++r) {
-        if (ang == 0) qring[((i_begin + r) % RING) * NT + t] = load_q(i_begin + r);
+        if (ang == 0) qring[r * NT + t] = load_q(i_begin + r);
         __syncthreads();
-        const int ra = i_begin + r - dr;  // anchor row completed by this row
-        if (ra >= i_begin) enter_pairs(ra);
+        if (r - dr >= 0) enter_pairs(r - dr, r);
         __syncthreads();
-        if (has_win && ra >= i_begin) energy_add(ra);
+        if (has_win && r - dr >= 0) energy_add(r - dr);
     }
     unsigned char q_next = 0;  // register prefetch of the next row's sample
-    if (ang == 0 && i_begin + WIN < i_end + WIN - 1) q_next = load_q(i_begin + WIN);
+    if (ang == 0 && i_begin + 1 < i_end) q_next = load_q(i_begin + WIN);
 
+    int s_top = 0;  // ring slot of image row i (the top row of the current window)
+    // the property this thread finalises for the whole window (the four angle threads share the five properties)
     for (int i = i_begin; i < i_end; ++i) {
         // (a) publish column sums
-        unsigned* xa = xch + ang * 4 * NT;
-        xa[0 * NT + t] = cw1;
-        xa[1 * NT + t] = cw2;
-        xa[2 * NT + t] = (unsigned)csh;
-        xa[3 * NT + t] = (unsigned)(csh >> 32);
+        xch[ang * NT + t] = make_uint4(cw1, cw2, (unsigned)csh, (unsigned)(csh >> 32));
         __syncthreads();  // #1
         // (b) window sums of this angle -> its share of the five properties
         if (has_win) {
             unsigned w1 = 0, w2 = 0;
             unsigned long long sh = 0;
+            const uint4* xa = xch + ang * NT + t;
 #pragma unroll
             for (int c = 0; c < WIN; ++c) {
                 if (c < c0 || c >= c1) continue;
-                w1 += xa[0 * NT + t + c];
-                w2 += xa[1 * NT + t + c];
-                sh += (unsigned long long)xa[2 * NT + t + c] | ((unsigned long long)xa[3 * NT + t + c] << 32);
+                const uint4 v = xa[c];
+                w1 += v.x;
+                w2 += v.y;
+                sh += (unsigned long long)v.z | ((unsigned long long)v.w << 32);
             }
             const int s1 = (int)(w1 & 0x1fffu), sab = (int)(w1 >> 13);
             const int sa = (int)(w2 & 0x3fffu), sq = (int)(w2 >> 14);
@@ -289,30 +292,37 @@ __global__ void __launch_bounds__(NT * 4) glcm_dense_kernel(const uint8_t* __res
             o[4 * NT] = var_num <= 0 ? 1.f : (float)cov_num / (float)var_num;
         }
         const bool more = i + 1 < i_end;
+        const int s_new = slot_add(s_top, WIN);  // slot that receives image row i + WIN (== slot of row i - 1)
         if (more) {
             // (c) the window moves down: pairs anchored in image row i leave
-            leave_pairs(i);
-            if (has_win) energy_sub(i);
+            leave_pairs(s_top, slot_add(s_top, dr));
+            if (has_win) energy_sub(s_top);
             // (d) image row i + WIN enters the ring
-            if (ang == 0) qring[((i + WIN) % RING) * NT + t] = q_next;
+            if (ang == 0) qring[s_new * NT + t] = q_next;
         }
         __syncthreads();  // #2: outx complete, new q row visible
-        if (ang == 0) {
-            if (more && i + 2 < i_end) q_next = load_q(i + WIN + 1);
-            if (has_win) {
-                const int64_t o = (int64_t)i * out_cols + j0 + t;
-#pragma unroll
-                for (int k = 0; k < 5; ++k) {
-                    const float v = (outx[(0 * 5 + k) * NT + t] + outx[(1 * 5 + k) * NT + t]) + (outx[(2 * 5 + k) * NT + t] + outx[(3 * 5 + k) * NT + t]);
-                    props[k * plane_stride + o] = v * 0.25f;
-                }
+        if (ang == 0 && more && i + 2 < i_end) q_next = load_q(i + WIN + 1);
+        if (has_win) {
+            // combine the four angles: thread `ang` writes property `ang` (angle-0 threads also property 4)
+            const int64_t o = (int64_t)i * out_cols + j0 + t;
+            {
+                const int k = ang;
+                const float v = (outx[(0 * 5 + k) * NT + t] + outx[(1 * 5 + k) * NT + t]) + (outx[(2 * 5 + k) * NT + t] + outx[(3 * 5 + k) * NT + t]);
+                props[k * plane_stride + o] = v * 0.25f;
+            }
+            if (ang == 0) {
+                const int k = 4;
+                const float v = (outx[(0 * 5 + k) * NT + t] + outx[(1 * 5 + k) * NT + t]) + (outx[(2 * 5 + k) * NT + t] + outx[(3 * 5 + k) * NT + t]);
+                props[k * plane_stride + o] = v * 0.25f;
             }
         }
         if (!more) break;
         // (e) pairs completed by the new row: anchored in row i + WIN - dr
-        enter_pairs(i + WIN - dr);
+        const int s_anchor = dr ? slot_add(s_top, WIN - 1) : s_new;
+        enter_pairs(s_anchor, s_new);
         __syncthreads();  // #3: their codes are visible
-        if (has_win) energy_add(i + WIN - dr);
+        if (has_win) energy_add(s_anchor);
+        s_top = slot_add(s_top, 1);
     }
 }
 
@@ -320,7 +330,7 @@ template <int WIN, int NT>
 static int launch_dense(const uint8_t* d_q, int W, int levels, int out_rows, int out_cols, float* d_props, int64_t plane_stride, cudaStream_t s) {
     constexpr int NTW = NT - (WIN - 1);
     const int ncell = levels * (levels + 1) / 2;
-    const size_t smem = (size_t)4 * ncell * NTW + (size_t)4 * (WIN + 1) * NT * 2 + (size_t)16 * NT * 4 + (size_t)20 * NT * 4 + (size_t)(WIN + 1) * NT + 64;
+    const size_t smem = (size_t)4 * ncell * NTW + (size_t)4 * (WIN + 1) * NT * 4 + (size_t)16 * NT * 4 + (size_t)20 * NT * 4 + (size_t)(WIN + 1) * NT + 64;
     static size_t configured = 0;
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(glcm_dense_kernel<WIN, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max(smem, (size_t)49152));
@@ -355,7 +365,7 @@ static int launch_dense(const uint8_t* d_q, int W, int levels, int out_rows, int
 template <int WIN>
 static int dispatch_dense(const uint8_t* d_q, int W, int levels, int out_rows, int out_cols, float* d_props, int64_t plane_stride, cudaStream_t s) {
     const int ncell = levels * (levels + 1) / 2;
-    auto fits = [&](int nt) { return (size_t)4 * ncell * (nt - (WIN - 1)) + (size_t)nt * (8 * (WIN + 1) + 64 + 80 + (WIN + 1)) + 64 <= (size_t)224 * 1024; };
+    auto fits = [&](int nt) { return (size_t)4 * ncell * (nt - (WIN - 1)) + (size_t)nt * (16 * (WIN + 1) + 64 + 80 + (WIN + 1)) + 64 <= (size_t)224 * 1024; };
     if (fits(256)) return launch_dense<WIN, 256>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, s);
     if (fits(128)) return launch_dense<WIN, 128>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, s);
     if (fits(96)) return launch_dense<WIN, 96>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, s);

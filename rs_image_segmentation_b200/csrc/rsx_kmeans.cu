@@ -313,7 +313,8 @@ __device__ __forceinline__ float km_tag(float a, int j) { return __uint_as_float
 template <int D, bool UPDATE, bool INERTIA, int KU>
 __global__ void __launch_bounds__(KM_THREADS, 2) km_assign_kernel(const float* __restrict__ stack, int64_t plane_stride, int64_t n_px, int row_len,
                                                                   long long* __restrict__ gacc, uint8_t* __restrict__ lab8,
-                                                                  int32_t* __restrict__ lab32, double* __restrict__ inertia_out) {
+                                                                  const uint8_t* __restrict__ prev8, int32_t* __restrict__ lab32,
+                                                                  double* __restrict__ inertia_out) {
     constexpr bool DIRECT = KU > 0;  // K <= KM_SLOTS: an accumulator slot per label, no evictions
     extern __shared__ __align__(16) unsigned char km_smem[];
     const int K = g_km.K;
@@ -329,7 +330,7 @@ __global__ void __launch_bounds__(KM_THREADS, 2) km_assign_kernel(const float* _
         __syncthreads();
     }
     double inertia = 0.0;
-    unsigned ties = 0;
+    unsigned ties = 0, changed = 0;
     const int64_t n4 = n_px & ~(int64_t)3;
     const int Kp = (K + 1) & ~1;  // centroids are processed in pairs; slot K (if K is odd) holds bias=+inf
 
@@ -408,7 +409,12 @@ __global__ void __launch_bounds__(KM_THREADS, 2) km_assign_kernel(const float* _
             for (int d = 0; d < D; ++d) x[d] = v[d].w;
             l3 = km_finish_pixel<D, UPDATE, INERTIA, DIRECT>(stack, plane_stride, p + 3, x, b3, s3, i3, acc, inertia, ties);
         }
-        if (lab8) *reinterpret_cast<uint32_t*>(lab8 + p) = (uint32_t)l0 | ((uint32_t)l1 << 8) | ((uint32_t)l2 << 16) | ((uint32_t)l3 << 24);
+        const uint32_t packed = (uint32_t)l0 | ((uint32_t)l1 << 8) | ((uint32_t)l2 << 16) | ((uint32_t)l3 << 24);
+        if (prev8) {  // strict-convergence test of sklearn (_kmeans.py:723): count labels that differ from the previous pass
+            const uint32_t x = packed ^ *reinterpret_cast<const uint32_t*>(prev8 + p);
+            changed += ((x & 0xffu) != 0) + ((x & 0xff00u) != 0) + ((x & 0xff0000u) != 0) + ((x & 0xff000000u) != 0);
+        }
+        if (lab8) *reinterpret_cast<uint32_t*>(lab8 + p) = packed;
         if (lab32) *reinterpret_cast<int4*>(lab32 + p) = make_int4(l0, l1, l2, l3);
     };
     if (p >= 0) load_row(va, p);
@@ -436,6 +442,7 @@ __global__ void __launch_bounds__(KM_THREADS, 2) km_assign_kernel(const float* _
                 KM_ARGMIN_STEP(a, b, s, bi, j)
             }
             int l = km_finish_pixel<D, UPDATE, INERTIA, DIRECT>(stack, plane_stride, q, x, b, s, bi, acc, inertia, ties);
+            if (prev8) changed += prev8[q] != (uint8_t)l;
             if (lab8) lab8[q] = (uint8_t)l;
             if (lab32) lab32[q] = l;
         }
@@ -475,17 +482,19 @@ __global__ void __launch_bounds__(KM_THREADS, 2) km_assign_kernel(const float* _
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         ties += __shfl_xor_sync(0xffffffffu, ties, o);
+        changed += __shfl_xor_sync(0xffffffffu, changed, o);
         if (INERTIA) inertia += __shfl_xor_sync(0xffffffffu, inertia, o);
     }
     if ((threadIdx.x & 31) == 0) {
         if (ties && gacc) atomicAdd(reinterpret_cast<unsigned long long*>(&gacc[K * D + K]), (unsigned long long)ties);
+        if (changed && gacc) atomicAdd(reinterpret_cast<unsigned long long*>(&gacc[K * D + K + 1]), (unsigned long long)changed);
         if (INERTIA && inertia_out) atomicAdd(inertia_out, inertia);
     }
 }
 
 template <int D, bool UPDATE, bool INERTIA, int KU>
-static int km_launch2(const float* d_stack, int64_t plane_stride, int64_t n_px, int row_len, long long* acc, uint8_t* l8, int32_t* l32,
-                      double* inertia, int K, int grid, cudaStream_t s) {
+static int km_launch2(const float* d_stack, int64_t plane_stride, int64_t n_px, int row_len, long long* acc, uint8_t* l8, const uint8_t* p8,
+                      int32_t* l32, double* inertia, int K, int grid, cudaStream_t s) {
     int smem = UPDATE ? KmSmem<D>::CACHE_BYTES + (KU > 0 ? 0 : 2 * K * (D + 1) * 4) : 0;
     auto kern = km_assign_kernel<D, UPDATE, INERTIA, KU>;
     static int configured = -1;
@@ -497,13 +506,13 @@ static int km_launch2(const float* d_stack, int64_t plane_stride, int64_t n_px, 
         }
         configured = max(smem, 48 * 1024);
     }
-    kern<<<grid, KM_THREADS, smem, s>>>(d_stack, plane_stride, n_px, row_len, acc, l8, l32, inertia);
+    kern<<<grid, KM_THREADS, smem, s>>>(d_stack, plane_stride, n_px, row_len, acc, l8, p8, l32, inertia);
     return rsx_check_launch("km_assign");
 }
 
 template <int D>
-static int km_launch(const float* d_stack, int64_t plane_stride, int64_t n_px, int row_len, long long* acc, uint8_t* l8, int32_t* l32,
-                     double* inertia, int update, int K, cudaStream_t s) {
+static int km_launch(const float* d_stack, int64_t plane_stride, int64_t n_px, int row_len, long long* acc, uint8_t* l8, const uint8_t* p8,
+                     int32_t* l32, double* inertia, int update, int K, cudaStream_t s) {
     const int64_t n4 = n_px & ~(int64_t)3;
     const int64_t v_rows = (n4 + row_len - 1) / row_len;
     const int64_t n_tiles = ceil_div(v_rows, (int64_t)KM_TILE_R) * ceil_div(row_len, KM_TILE_W);
@@ -511,30 +520,32 @@ static int km_launch(const float* d_stack, int64_t plane_stride, int64_t n_px, i
     const int grid = (int)max((int64_t)1, min(n_tiles, (int64_t)rsx_num_sms() * per_sm));
     const bool direct = K <= KM_SLOTS;
     if (update)  // inertia is only produced by the final (assign-only) pass
-        return direct ? km_launch2<D, true, false, KM_SLOTS>(d_stack, plane_stride, n_px, row_len, acc, l8, l32, nullptr, K, grid, s)
-                      : km_launch2<D, true, false, 0>(d_stack, plane_stride, n_px, row_len, acc, l8, l32, nullptr, K, grid, s);
+        return direct ? km_launch2<D, true, false, KM_SLOTS>(d_stack, plane_stride, n_px, row_len, acc, l8, p8, l32, nullptr, K, grid, s)
+                      : km_launch2<D, true, false, 0>(d_stack, plane_stride, n_px, row_len, acc, l8, p8, l32, nullptr, K, grid, s);
     if (inertia)
-        return direct ? km_launch2<D, false, true, KM_SLOTS>(d_stack, plane_stride, n_px, row_len, acc, l8, l32, inertia, K, grid, s)
-                      : km_launch2<D, false, true, 0>(d_stack, plane_stride, n_px, row_len, acc, l8, l32, inertia, K, grid, s);
-    return direct ? km_launch2<D, false, false, KM_SLOTS>(d_stack, plane_stride, n_px, row_len, acc, l8, l32, inertia, K, grid, s)
-                  : km_launch2<D, false, false, 0>(d_stack, plane_stride, n_px, row_len, acc, l8, l32, inertia, K, grid, s);
+        return direct ? km_launch2<D, false, true, KM_SLOTS>(d_stack, plane_stride, n_px, row_len, acc, l8, p8, l32, inertia, K, grid, s)
+                      : km_launch2<D, false, true, 0>(d_stack, plane_stride, n_px, row_len, acc, l8, p8, l32, inertia, K, grid, s);
+    return direct ? km_launch2<D, false, false, KM_SLOTS>(d_stack, plane_stride, n_px, row_len, acc, l8, p8, l32, inertia, K, grid, s)
+                  : km_launch2<D, false, false, 0>(d_stack, plane_stride, n_px, row_len, acc, l8, p8, l32, inertia, K, grid, s);
 }
 
 extern "C" int rsx_kmeans_assign(const float* d_stack, int64_t plane_stride, int64_t n_px, int row_len, const void* d_state, int64_t* d_acc,
-                                 uint8_t* d_labels_u8, int32_t* d_labels_i32, double* d_inertia, int update, int D, int K,
-                                 rsx_stream_t stream) {
+                                 uint8_t* d_labels_u8, const uint8_t* d_labels_prev_u8, int32_t* d_labels_i32, double* d_inertia, int update,
+                                 int D, int K, rsx_stream_t stream) {
     RSX_REQUIRE(d_stack && d_state && n_px > 0, "rsx_kmeans_assign: bad arguments");
     RSX_REQUIRE(D >= 1 && D <= KM_MAXD && K >= 1 && K <= KM_MAXK, "rsx_kmeans_assign: D/K out of range");
     RSX_REQUIRE(!update || d_acc, "rsx_kmeans_assign: update pass needs d_acc");
     RSX_REQUIRE(!(update && d_inertia), "rsx_kmeans_assign: inertia is produced by the assign-only pass (update == 0)");
     RSX_REQUIRE(((uintptr_t)d_stack & 15) == 0 && (plane_stride & 3) == 0, "rsx_kmeans_assign: stack planes must be 16-byte aligned");
-    RSX_REQUIRE((((uintptr_t)d_labels_u8) & 3) == 0 && (((uintptr_t)d_labels_i32) & 15) == 0, "rsx_kmeans_assign: label buffers must be aligned");
+    RSX_REQUIRE((((uintptr_t)d_labels_u8 | (uintptr_t)d_labels_prev_u8) & 3) == 0 && (((uintptr_t)d_labels_i32) & 15) == 0,
+                "rsx_kmeans_assign: label buffers must be aligned");
+    RSX_REQUIRE(!d_labels_prev_u8 || d_acc, "rsx_kmeans_assign: the changed-label counter lives in d_acc");
     if (row_len <= 0) row_len = 4096;
     row_len = (row_len + 3) & ~3;
     cudaStream_t s = (cudaStream_t)stream;
     long long* acc = reinterpret_cast<long long*>(d_acc);
 #define CASE(DD) \
-    case DD: return km_launch<DD>(d_stack, plane_stride, n_px, row_len, acc, d_labels_u8, d_labels_i32, d_inertia, update, K, s);
+    case DD: return km_launch<DD>(d_stack, plane_stride, n_px, row_len, acc, d_labels_u8, d_labels_prev_u8, d_labels_i32, d_inertia, update, K, s);
     switch (D) {
         CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14) CASE(15) CASE(16)
         CASE(17) CASE(18) CASE(19) CASE(20)

@@ -29,23 +29,14 @@ def _lerp(a, b, t):
     return out[()]
 
 
-class LevelOrder:
-    """Sorted view of one band: cumulative counts over grey levels + the value each level maps to."""
+class OrderBase:
+    """numpy's quantile arithmetic on top of `at(k)` = k-th smallest sample; subclasses provide n, dtype, at."""
 
-    def __init__(self, hist, values):
-        hist = np.asarray(hist, dtype=np.int64)
-        self.cum = np.cumsum(hist)
-        self.n = int(self.cum[-1]) if hist.size else 0
-        self.values = np.asarray(values)
-        if self.n <= 0:
-            raise ValueError("empty histogram")
-        if self.values.shape != hist.shape:
-            raise ValueError("values/hist shape mismatch")
+    n: int
+    dtype: np.dtype
 
     def at(self, k: int):
-        """k-th smallest sample (0-based) of the band."""
-        k = min(max(int(k), 0), self.n - 1)
-        return self.values[int(np.searchsorted(self.cum, k, side="right"))]
+        raise NotImplementedError
 
     def _quantile(self, q):
         # q is a numpy scalar / 0-d array whose dtype decides the arithmetic, as in numpy
@@ -64,21 +55,41 @@ class LevelOrder:
 
     def percentile_scalar(self, q):
         """np.percentile(band_float32, q) for a Python-number q: float32 arithmetic, float32 result."""
-        q32 = np.true_divide(q, self.values.dtype.type(100) if self.values.dtype.kind == "f" else 100)
+        q32 = np.true_divide(q, self.dtype.type(100) if self.dtype.kind == "f" else 100)
         return self._quantile(q32)
 
     def nanpercentile_pair(self, qs=(25.0, 75.0)):
         """np.nanpercentile(column_float32, (25.0, 75.0)): float64 quantiles, float64 result."""
-        q = np.true_divide(np.asanyarray(qs), self.values.dtype.type(100) if self.values.dtype.kind == "f" else 100)
+        q = np.true_divide(np.asanyarray(qs), self.dtype.type(100) if self.dtype.kind == "f" else 100)
         return np.array([self._quantile(qi) for qi in q])
 
     def median(self):
         """np.nanmedian of a float32 column without NaNs: middle element, or the float32 mean of the two."""
         n = self.n
         if n % 2 == 1:
-            return self.values[0:1].dtype.type(self.at(n // 2))
-        pair = np.array([self.at(n // 2 - 1), self.at(n // 2)], dtype=self.values.dtype)
+            return self.dtype.type(self.at(n // 2))
+        pair = np.array([self.at(n // 2 - 1), self.at(n // 2)], dtype=self.dtype)
         return np.mean(pair)
+
+
+class LevelOrder(OrderBase):
+    """Sorted view of one band: cumulative counts over grey levels + the value each level maps to."""
+
+    def __init__(self, hist, values):
+        hist = np.asarray(hist, dtype=np.int64)
+        self.cum = np.cumsum(hist)
+        self.n = int(self.cum[-1]) if hist.size else 0
+        self.values = np.asarray(values)
+        self.dtype = self.values.dtype
+        if self.n <= 0:
+            raise ValueError("empty histogram")
+        if self.values.shape != hist.shape:
+            raise ValueError("values/hist shape mismatch")
+
+    def at(self, k: int):
+        """k-th smallest sample (0-based) of the band."""
+        k = min(max(int(k), 0), self.n - 1)
+        return self.values[int(np.searchsorted(self.cum, k, side="right"))]
 
 
 def norm_params(lo, hi):

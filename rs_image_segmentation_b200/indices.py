@@ -1,0 +1,282 @@
+"""Drop-in for the hot-path functions of the reference's modules/features/indices.py.
+
+Same names, positional order, keyword names, defaults and return types as the reference, so that
+`from rs_image_segmentation_b200.indices import *` can replace `from modules.features.indices import *`
+(scripts/2_feature_extraction.py:20) for the functions on the hot path.  Inputs and outputs are host numpy
+arrays; the arithmetic runs in the CUDA kernels of librsx.so (no CPU fallback: without a GPU every function
+raises).  The fused, device-resident route for whole scenes is `run_feature_extraction_stage` /
+`pipeline.extract_features`; the per-function entry points below pay one host<->device round trip each.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, hoststats
+from .device import hptr, ptr, require_cuda, stream_ptr
+
+__all__ = ["robust_normalize", "calculate_ndvi", "calculate_evi", "calculate_msavi", "calculate_ndwi", "calculate_mndwi",
+           "calculate_ndbi", "calculate_bsi", "perform_pca", "calculate_glcm_features", "prepare_level_1_features",
+           "run_feature_extraction_stage", "RsxPCA"]
+
+_DEFAULT_ANGLES = [0, np.pi / 4, np.pi / 2, 3 * np.pi / 4]
+
+
+# ------------------------------------------------------------------------------------------- helpers
+def _dev32(a) -> torch.Tensor:
+    """float32 device copy of a 2-D array (the reference feeds float32 maps: scripts/2_feature_extraction.py:158)."""
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+    return torch.from_numpy(a).cuda(non_blocking=False)
+
+
+def _out_like(t: torch.Tensor) -> torch.Tensor:
+    return torch.empty(t.numel(), dtype=torch.float32, device=t.device)
+
+
+class _DeviceOrder(hoststats.OrderBase):
+    """Order statistics of an arbitrary float32 band: one device sort, numpy's interpolation on the host."""
+
+    def __init__(self, flat: torch.Tensor):
+        self.sorted = torch.sort(flat).values
+        self.n = int(flat.numel())
+        self.dtype = np.dtype(np.float32)
+
+    def at(self, k: int):
+        k = min(max(int(k), 0), self.n - 1)
+        return np.float32(self.sorted[k].item())
+
+
+def _norm_params_device(flat: torch.Tensor, lower, upper):
+    order = _DeviceOrder(flat)
+    return hoststats.norm_params(order.percentile_scalar(lower), order.percentile_scalar(upper))
+
+
+# ------------------------------------------------------------------------------------------- a1
+def robust_normalize(band, lower_percentile=2, upper_percentile=98):
+    """modules/features/indices.py:25-48."""
+    require_cuda()
+    band = np.asarray(band)
+    x = _dev32(band)
+    flat = x.reshape(-1)
+    if bool(torch.isnan(flat).any()):
+        return np.full(band.shape, np.nan, dtype=np.float32)      # np.percentile of a NaN band is NaN
+    lo, hi, den = _norm_params_device(flat, lower_percentile, upper_percentile)
+    out = _out_like(flat)
+    _lib.call("rsx_normalize_f32", ptr(flat), flat.numel(), float(lo), float(hi), float(den), ptr(out), stream_ptr())
+    return out.cpu().numpy().reshape(band.shape)
+
+
+# ------------------------------------------------------------------------------------------- a2..a5
+def _ratio(a, b):
+    require_cuda()
+    shape = np.asarray(a).shape
+    A, B = _dev32(a).reshape(-1), _dev32(b).reshape(-1)
+    out = _out_like(A)
+    _lib.call("rsx_index_ratio_f32", ptr(A), ptr(B), A.numel(), ptr(out), stream_ptr())
+    return out.cpu().numpy().reshape(shape)
+
+
+def calculate_ndvi(nir_band, red_band):
+    """indices.py:50-71."""
+    return _ratio(nir_band, red_band)
+
+
+def calculate_ndwi(green_band, nir_band):
+    """indices.py:116-137."""
+    return _ratio(green_band, nir_band)
+
+
+def calculate_mndwi(green_band, swir_band):
+    """indices.py:139-158."""
+    return _ratio(green_band, swir_band)
+
+
+def calculate_ndbi(swir_band, nir_band):
+    """indices.py:160-179."""
+    return _ratio(swir_band, nir_band)
+
+
+def calculate_evi(nir_band, red_band, blue_band, L=1, C1=6, C2=7.5, G=2.5):
+    """indices.py:73-95."""
+    require_cuda()
+    shape = np.asarray(nir_band).shape
+    N, R, Bl = _dev32(nir_band).reshape(-1), _dev32(red_band).reshape(-1), _dev32(blue_band).reshape(-1)
+    out = _out_like(N)
+    _lib.call("rsx_index_evi_f32", ptr(N), ptr(R), ptr(Bl), N.numel(), float(L), float(C1), float(C2), float(G), ptr(out), stream_ptr())
+    return out.cpu().numpy().reshape(shape)
+
+
+def calculate_msavi(nir_band, red_band):
+    """indices.py:97-114."""
+    require_cuda()
+    shape = np.asarray(nir_band).shape
+    N, R = _dev32(nir_band).reshape(-1), _dev32(red_band).reshape(-1)
+    out = _out_like(N)
+    _lib.call("rsx_index_msavi_f32", ptr(N), ptr(R), N.numel(), ptr(out), stream_ptr())
+    return out.cpu().numpy().reshape(shape)
+
+
+def calculate_bsi(blue_band, red_band, nir_band, swir_band):
+    """indices.py:181-203."""
+    require_cuda()
+    shape = np.asarray(blue_band).shape
+    Bl, R, N, S = (_dev32(x).reshape(-1) for x in (blue_band, red_band, nir_band, swir_band))
+    out = _out_like(Bl)
+    _lib.call("rsx_index_bsi_f32", ptr(Bl), ptr(R), ptr(N), ptr(S), Bl.numel(), ptr(out), stream_ptr())
+    return out.cpu().numpy().reshape(shape)
+
+
+# ------------------------------------------------------------------------------------------- a6
+class RsxPCA:
+    """What perform_pca returns in place of the fitted sklearn PCA (indices.py:246): same attribute names."""
+
+    def __init__(self, pca: dict, n_samples: int, n_features: int):
+        self.components_ = pca["components"].astype(np.float32)
+        self.mean_ = pca["mean"].astype(np.float32)
+        self.explained_variance_ = pca["explained_variance"].astype(np.float32)
+        self.explained_variance_ratio_ = pca["explained_variance_ratio"].astype(np.float32)
+        self.singular_values_ = pca["singular_values"].astype(np.float32)
+        self.noise_variance_ = pca["noise_variance"]
+        self.n_components_ = self.components_.shape[0]
+        self.n_samples_, self.n_features_in_ = n_samples, n_features
+
+    def transform(self, X):
+        """sklearn/decomposition/_base.py:151-159 on the device (cuBLAS through torch; not on the reference's path)."""
+        require_cuda()
+        Xd = torch.from_numpy(np.ascontiguousarray(X, dtype=np.float32)).cuda()
+        V = torch.from_numpy(self.components_).cuda()
+        mu = torch.from_numpy(self.mean_).cuda()
+        return (Xd @ V.t() - (mu.reshape(1, -1) @ V.t())).cpu().numpy()
+
+
+_COMPILED_BANDS = (5, 6, 7, 8, 10, 12, 13)
+
+
+def perform_pca(bands_data, n_components=None, use_robust_scaling=True):
+    """indices.py:205-246.
+
+    The bands the reference passes here are robust-normalised uint8 bands, i.e. float maps with at most 256
+    distinct values each.  Each band is rank-coded on the device (torch.unique), which turns the call into the
+    uint8 raster path: histogram -> RobustScaler statistics -> per-level table of X -> Gram/moments kernel ->
+    eigh (host, BxB) -> projection kernel.  Bands with more than 256 distinct values are not supported yet.
+    """
+    require_cuda()
+    H, W = np.asarray(bands_data[0]).shape
+    B = len(bands_data)
+    if B not in _COMPILED_BANDS:
+        raise _lib.RsxError(f"perform_pca: {B} bands; kernels are compiled for {_COMPILED_BANDS}")
+    n = H * W
+    st = stream_ptr()
+    levels, value_tables = [], []
+    for b in bands_data:
+        x = _dev32(b).reshape(-1)
+        if bool(torch.isnan(x).any()):
+            raise ValueError("Input X contains NaN.")                      # what sklearn raises
+        vals, inv = torch.unique(x, return_inverse=True)
+        if vals.numel() > 256:
+            raise _lib.RsxError("perform_pca: a band has more than 256 distinct values; the float-band path is not implemented")
+        levels.append(inv.to(torch.uint8))
+        value_tables.append(vals.cpu().numpy().astype(np.float32))
+    raster = torch.stack(levels, dim=1).contiguous()                       # (N, B) uint8, pixel interleaved
+    hist = torch.zeros((B, 256), dtype=torch.int32, device="cuda")
+    _lib.call("rsx_hist_u8", ptr(raster), n, B, ptr(hist), st)
+    hist = hist.cpu().numpy().astype(np.int64)
+    lut = np.zeros((B, 256), np.float32)
+    for b in range(B):
+        v = value_tables[b]
+        k = len(v)
+        if use_robust_scaling:                                             # RobustScaler().fit_transform
+            order = hoststats.LevelOrder(hist[b, :k], v)
+            center = order.median()
+            q = order.nanpercentile_pair((25.0, 75.0))
+            s = np.float64(q[1] - q[0])
+            if s < 10 * np.finfo(np.float64).eps:
+                s = 1.0
+            lut[b, :k] = ((v - center).astype(np.float64) / s).astype(np.float32)
+        else:                                                              # indices.py:234
+            lut[b, :k] = (v - v.min()) / (v.max() - v.min() + 1e-10)
+    n_comp = B if n_components is None else int(n_components)
+    dlut = torch.from_numpy(lut).cuda()
+    M = B + B * (B + 1) // 2
+    moments = torch.zeros(M, dtype=torch.float64, device="cuda")
+    scratch = torch.empty(int(_lib.load().rsx_pca_scratch_elems(B)), dtype=torch.float64, device="cuda")
+    _lib.call("rsx_pca_moments_u8", ptr(raster), n, B, ptr(dlut), ptr(moments), ptr(scratch), st)
+    pca = hoststats.pca_from_moments(moments.cpu().numpy(), n, n_comp)
+    comps = np.ascontiguousarray(pca["components"], dtype=np.float32)
+    mean_proj = np.ascontiguousarray((pca["mean"].astype(np.float32).reshape(1, -1) @ comps.T).ravel(), dtype=np.float32)
+    stride = (n + 31) // 32 * 32
+    out = torch.empty((n_comp, stride), dtype=torch.float32, device="cuda")
+    _lib.call("rsx_pca_project_u8", ptr(raster), n, B, ptr(dlut), hptr(comps), hptr(mean_proj), n_comp, ptr(out), stride, None, st)
+    maps = out[:, :n].cpu().numpy()
+    model = RsxPCA(pca, n, B)
+    return [maps[i].reshape(H, W) for i in range(n_comp)], model.explained_variance_ratio_, model
+
+
+# ------------------------------------------------------------------------------------------- a7
+def calculate_glcm_features(band, distances=[1], angles=[0, np.pi / 4, np.pi / 2, 3 * np.pi / 4], levels=32, window_size=21, step_size=21):
+    """indices.py:248-318 (distance 1 and the four default angles, which is all the reference ever asks for)."""
+    require_cuda()
+    if list(distances) != [1] or not np.allclose(list(angles), _DEFAULT_ANGLES):
+        raise _lib.RsxError("calculate_glcm_features: only distances=[1] with angles 0, pi/4, pi/2, 3pi/4 are implemented")
+    band = np.asarray(band)
+    H, W = band.shape
+    if window_size > H or window_size > W:
+        raise ValueError("window larger than the band")
+    st = stream_ptr()
+    x = _dev32(band).reshape(-1)
+    lo, hi, den = _norm_params_device(x, 2, 98)                             # indices.py:265
+    q = torch.empty((H * W + 3) // 4 * 4, dtype=torch.uint8, device="cuda")
+    _lib.call("rsx_quantize_f32", ptr(x), H * W, float(lo), float(hi), float(den), int(levels), ptr(q), st)   # :268
+    oh, ow = (H - window_size) // step_size + 1, (W - window_size) // step_size + 1
+    pstride = (oh * ow + 31) // 32 * 32
+    props = torch.empty((5, pstride), dtype=torch.float32, device="cuda")
+    _lib.call("rsx_glcm_props", ptr(q), H, W, int(levels), int(window_size), int(step_size), oh, ow, ptr(props), pstride, st)
+    full = torch.empty((5, H * W), dtype=torch.float32, device="cuda")
+    _lib.call("rsx_resize_bilinear_f32", ptr(props), oh, ow, 0, oh, pstride, ptr(full), H, W, 0, H, H * W, 5, None, st)   # :308
+    maps = full.cpu().numpy().reshape(5, H, W)
+    names = ("contrast", "dissimilarity", "homogeneity", "energy", "correlation")
+    return {k: maps[i] for i, k in enumerate(names)}
+
+
+# ------------------------------------------------------------------------------------------- a8 (glue)
+def prepare_level_1_features(features_dict):
+    """indices.py:808-835: [ndwi, mndwi, ndvi, evi, ndbi, bsi, pc0] stacked on the last axis (host glue)."""
+    maps = [features_dict[k] for k in ("ndwi", "mndwi", "ndvi", "evi", "ndbi", "bsi")]
+    if "pca_result" in features_dict and len(features_dict["pca_result"]) > 0:
+        maps.append(features_dict["pca_result"][0])
+    return np.stack(maps, axis=-1)
+
+
+def run_feature_extraction_stage(bands_data, preprocessing=True, texture_band_index=3):
+    """scripts/2_feature_extraction.py:27-133, hot-path part, fused on the device.
+
+    bands_data: list of 2-D integer-valued arrays in TM order (what stage 1 writes: uint8 levels stored as
+    float32).  One H2D copy of the packed raster, K1-K4 on the device, one D2H copy of the maps.  Returns
+    (features_dict, hierarchical_features) with the reference's keys for the stages on the hot path: the seven
+    indices, 'pca_result', 'variance_ratio', 'glcm_features'; hierarchical_features['level_1'] is the 7-channel
+    stack of prepare_level_1_features.  The LBP / multi-scale / morphology / filter features and the spatial
+    context channels (scripts/2...:93-119) are outside the hot path and are not produced.
+    `texture_band_index` is accepted and ignored, like in the reference (the texture band is always NIR).
+    """
+    from . import pipeline as P
+    require_cuda()
+    if not preprocessing:
+        raise _lib.RsxError("run_feature_extraction_stage: the fused path includes robust_normalize (preprocessing=True)")
+    arrs = [np.asarray(b) for b in bands_data]
+    H, W = arrs[0].shape
+    stack = np.stack(arrs, axis=-1)
+    if np.isnan(stack).any() or (stack != np.rint(stack)).any() or stack.min() < 0 or stack.max() > 65535:
+        raise _lib.RsxError("run_feature_extraction_stage: bands must hold integer levels in [0, 65535] (stage-1 output)")
+    packed = stack.astype(np.uint8) if stack.max() <= 255 else stack.astype(np.uint16).view(np.int16)
+    fr = P.extract_features(torch.from_numpy(np.ascontiguousarray(packed)).cuda(), P.FeatureConfig())
+    host = fr.planes[:, :fr.n_px].cpu().numpy().reshape(len(fr.names), H, W)
+    get = lambda name: host[fr.names.index(name)]
+    features = {k: get(k) for k in P.INDEX_NAMES}
+    n_comp = fr.pca["components"].shape[0]
+    features["pca_result"] = [get(f"pc{i}") for i in range(n_comp)]
+    features["variance_ratio"] = fr.pca["explained_variance_ratio"].astype(np.float32)
+    features["glcm_features"] = {k: get("glcm_" + k) for k in P.GLCM_NAMES}
+    level1 = prepare_level_1_features(features)
+    return features, {"level_1": level1}

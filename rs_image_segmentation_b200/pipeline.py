@@ -214,7 +214,7 @@ class DeviceKMeans:
         self.scale, self.min_ = minmax_scale_params(self.fmin, self.fmax)
         dev = planes.device
         self.state = torch.zeros(int(_lib.load().rsx_kmeans_state_bytes()), dtype=torch.uint8, device=dev)
-        self.acc = torch.zeros(K * D + K + 1, dtype=torch.int64, device=dev)
+        self.acc = torch.zeros(K * D + K + 2, dtype=torch.int64, device=dev)
         self.inertia = torch.zeros(1, dtype=torch.float64, device=dev)
 
     def scale_rows(self, raw_rows: np.ndarray) -> np.ndarray:
@@ -241,12 +241,13 @@ class DeviceKMeans:
         _lib.call("rsx_kmeans_setup", ptr(self.state), self.D, self.K, hptr(self.fmin), hptr(self.fmax), hptr(mu), hptr(c0),
                   self.n_global, stream_ptr())
 
-    def step(self):
-        """One fused assign + partial-sum pass, the all-reduce of K*(D+1) integers, one centroid update."""
+    def step(self, labels_out: Optional[torch.Tensor] = None, labels_prev: Optional[torch.Tensor] = None):
+        """One fused assign + partial-sum pass, the all-reduce of K*(D+1) integers, one centroid update.
+        labels_out / labels_prev: optional uint8 label planes (this pass / the previous one) for the convergence test."""
         if self.n_px:
             with self.timer("kmeans_assign"):
                 _lib.call("rsx_kmeans_assign", ptr(self.planes), self.stride, self.n_px, self.row_len, ptr(self.state), ptr(self.acc),
-                          None, None, None, 1, self.D, self.K, stream_ptr())
+                          ptr(labels_out), ptr(labels_prev), None, None, 1, self.D, self.K, stream_ptr())
         self.comm.all_reduce(self.acc)
         with self.timer("kmeans_update"):
             _lib.call("rsx_kmeans_update", ptr(self.state), ptr(self.acc), stream_ptr())
@@ -259,8 +260,8 @@ class DeviceKMeans:
         if self.n_px:
             with self.timer("kmeans_final"):
                 _lib.call("rsx_kmeans_assign", ptr(self.planes), self.stride, self.n_px, self.row_len, ptr(self.state), ptr(self.acc),
-                          None if labels_i32 else ptr(lab), ptr(lab) if labels_i32 else None, ptr(self.inertia), 0, self.D, self.K,
-                          stream_ptr())
+                          None if labels_i32 else ptr(lab), None, ptr(lab) if labels_i32 else None, ptr(self.inertia), 0, self.D,
+                          self.K, stream_ptr())
         self.comm.all_reduce(self.inertia)
         return lab[:self.n_px]
 
@@ -271,13 +272,46 @@ class DeviceKMeans:
         _lib.call("rsx_kmeans_read", ptr(self.state), hptr(cent), hptr(shift), hptr(empty), stream_ptr())
         return cent, float(shift[0]), int(empty[0])
 
+    def fit_converge(self, init_centroids_scaled: np.ndarray, max_iter: int = 300, tol: float = 0.0,
+                     mean_scaled: Optional[np.ndarray] = None) -> KMeansResult:
+        """sklearn's _kmeans_single_lloyd stopping rules (_kmeans.py:703-754): stop when no label changed between two
+        passes (strict convergence) or when the squared centre shift is <= tol; then the final assignment + inertia."""
+        self.setup(init_centroids_scaled, mean_scaled)
+        dev = self.planes.device
+        npad = (self.n_px + 3) // 4 * 4
+        cur = torch.full((npad,), 255, dtype=torch.uint8, device=dev)
+        prev = torch.full((npad,), 255, dtype=torch.uint8, device=dev)
+        chg = self.K * self.D + self.K + 1
+        n_iter = 0
+        for it in range(max_iter):
+            self.acc[chg] = 0
+            self.step(cur, prev)
+            n_iter = it + 1
+            changed = self.acc[chg:chg + 1].clone()
+            self.comm.all_reduce(changed)
+            if int(changed.item()) == 0:
+                break
+            _, shift, _ = self.read()
+            if shift <= tol:
+                break
+            cur, prev = prev, cur
+        labels = self.finish(True)
+        cent, shift, empty = self.read()
+        if empty:
+            raise _lib.RsxError(f"KMeans: {empty} empty cluster(s) met; empty-cluster relocation "
+                                "(sklearn _k_means_common.pyx:167-211) is not implemented on the device")
+        ties = self.acc[self.K * self.D + self.K:self.K * self.D + self.K + 1].clone()
+        self.comm.all_reduce(ties)
+        return KMeansResult(labels=labels, centroids=cent, inertia=float(self.inertia.item()), n_iter=n_iter,
+                            near_ties=int(ties.item()), shift_sq=shift)
+
     def fit(self, init_centroids_scaled: np.ndarray, n_iter: int, labels_i32: bool = True) -> KMeansResult:
         self.setup(init_centroids_scaled)
         for _ in range(n_iter):
             self.step()
         labels = self.finish(labels_i32)
         cent, shift, empty = self.read()
-        ties = self.acc[-1:].clone()
+        ties = self.acc[self.K * self.D + self.K:self.K * self.D + self.K + 1].clone()
         self.comm.all_reduce(ties)
         if empty:
             raise _lib.RsxError(f"KMeans: {empty} empty cluster(s) met; empty-cluster relocation "

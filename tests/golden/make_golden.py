@@ -10,7 +10,7 @@ registered first.  What is recorded:
   aa_crop.npz      a 64x96 crop of the stage-1 output of data/raw/AA.tif (uint8, 7 bands)
                    and the reference's outputs on it: robust_normalize, the seven indices,
                    perform_pca, prepare_level_1_features, add_spatial_context,
-                   unsupervised_kmeans_classification (indices as features, k=5)
+                   unsupervised_kmeans_classification (indices as features, k=5; float32 and float64 inputs; k=7 on a 3-D stack)
   aa_full_stats.npz  P2/P98, index means, PCA evr/components of the full 600x600 scene
                    (SURVEY.md 8(c) table), for the oracle only
 
@@ -138,12 +138,21 @@ def main():
     kdict = {k: v for k, v in ix.items()}
     kdict.update(height=h, width=w)
     labels = ext.unsupervised_kmeans_classification(kdict, n_clusters=5, feature_keys_to_use=list(ix.keys()))
+    # the same call on the float64 promotion of the same maps (the reference's real stack is float64):
+    # this is the variant whose result does not depend on float32 BLAS summation order
+    kdict64 = {k: v.astype(np.float64) for k, v in ix.items()}
+    kdict64.update(height=h, width=w)
+    labels64 = ext.unsupervised_kmeans_classification(kdict64, n_clusters=5, feature_keys_to_use=list(ix.keys()))
+    stack3d = np.stack([ix[k] for k in ix], axis=-1).astype(np.float64)
+    labels64_k7 = ext.unsupervised_kmeans_classification({"hierarchical_all": stack3d, "height": h, "width": w}, n_clusters=7,
+                                                         feature_keys_to_use=["hierarchical_all"])
     np.savez_compressed(
         os.path.join(HERE, "aa_crop.npz"),
         stage1_u8=crop, pct=pct, norm=np.stack(nb),
         **{"ix_" + k: v for k, v in ix.items()},
         pca_maps=np.stack(pcs), pca_evr=evr, pca_components=model.components_, pca_mean=model.mean_,
         level1=l1, level1_ctx=l1c, q32=q32, kmeans_labels_k5=labels.astype(np.int32),
+        kmeans_labels_k5_f64=labels64.astype(np.int32), kmeans_labels_k7_f64_3d=labels64_k7.astype(np.int32),
     )
     # ---- full-scene statistics
     nb, pct, ix, pcs, evr, model, l1, l1c, q32 = run(stage1)

@@ -1,0 +1,203 @@
+"""GPU parity tests for the drop-in modules (rs_image_segmentation_b200.indices / .extract): the reference's own
+function signatures with host numpy arrays in and out, checked against the outputs the UNMODIFIED reference produced
+on the same inputs (tests/golden/aa_crop.npz, made by tests/golden/make_golden.py) and against the oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def I():
+    from rs_image_segmentation_b200 import device, indices
+    device.require_cuda()
+    return indices
+
+
+@pytest.fixture(scope="module")
+def E():
+    from rs_image_segmentation_b200 import device, extract
+    device.require_cuda()
+    return extract
+
+
+def _bands(aa_crop):
+    return [b.astype(np.float32) for b in aa_crop["stage1_u8"]]          # scripts/2_feature_extraction.py:158
+
+
+def test_robust_normalize_matches_reference(I, aa_crop):
+    for b, ref in zip(_bands(aa_crop), aa_crop["norm"]):
+        got = I.robust_normalize(b)
+        assert got.dtype == np.float32 and got.shape == b.shape
+        assert np.array_equal(got, ref)
+
+
+def test_robust_normalize_float_band_and_percentiles(I):
+    """A band with ~N distinct float values (the device-sort route) and non-default percentiles."""
+    from oracle import features as of
+    rng = np.random.default_rng(5)
+    b = (rng.standard_normal((77, 131)) * 10 + 3).astype(np.float32)
+    for lo, hi in ((2, 98), (0, 100), (10.5, 63)):
+        assert np.array_equal(I.robust_normalize(b, lo, hi), of.robust_normalize(b, lo, hi))
+    nanband = b.copy()
+    nanband[3, 4] = np.nan
+    assert np.isnan(I.robust_normalize(nanband)).all()                   # np.percentile of a NaN band is NaN
+
+
+def test_index_functions_match_reference(I, aa_crop):
+    nb = [aa_crop["norm"][i] for i in range(7)]
+    blue, green, red, nir, swir1 = nb[0], nb[1], nb[2], nb[3], nb[4]
+    got = {
+        "ndvi": I.calculate_ndvi(nir, red),
+        "evi": I.calculate_evi(nir, red, blue),
+        "msavi": I.calculate_msavi(nir, red),
+        "ndwi": I.calculate_ndwi(green, nir),
+        "mndwi": I.calculate_mndwi(green, swir1),
+        "ndbi": I.calculate_ndbi(swir1, nir),
+        "bsi": I.calculate_bsi(blue, red, nir, swir1),
+    }
+    for k, v in got.items():
+        assert v.dtype == np.float32
+        assert np.array_equal(v, aa_crop["ix_" + k]), k
+
+
+def test_index_functions_edge_values(I):
+    """Masked denominators (d <= 0.001 -> 0), clipping to [-1, 1], non-default EVI constants."""
+    from oracle import features as of
+    rng = np.random.default_rng(9)
+    a = rng.random((40, 50), dtype=np.float32)
+    b = rng.random((40, 50), dtype=np.float32)
+    c = rng.random((40, 50), dtype=np.float32)
+    d = rng.random((40, 50), dtype=np.float32)
+    a[:5] = 0
+    b[:5] = 0                                                             # zero denominators
+    a[5:8] = 0.0004
+    b[5:8] = 0.0005                                                       # just under the 0.001 mask
+    assert np.array_equal(I.calculate_ndvi(a, b), of.ndvi(a, b))
+    assert np.array_equal(I.calculate_evi(a, b, c, L=0.5, C1=5, C2=7, G=2), of.evi(a, b, c, L=0.5, C1=5, C2=7, G=2))
+    assert np.array_equal(I.calculate_msavi(a, b), of.msavi(a, b))
+    assert np.array_equal(I.calculate_bsi(a, b, c, d), of.bsi(a, b, c, d))
+
+
+def test_perform_pca_matches_reference(I, aa_crop):
+    nb = [aa_crop["norm"][i] for i in range(7)]
+    maps, evr, model = I.perform_pca(nb, use_robust_scaling=True)
+    assert len(maps) == 7 and maps[0].shape == nb[0].shape and maps[0].dtype == np.float32
+    np.testing.assert_allclose(evr, aa_crop["pca_evr"], rtol=5e-4)
+    for i in range(7):
+        r = aa_crop["pca_components"][i]
+        c = model.components_[i]
+        assert abs(float(np.dot(c, r))) > 1 - 1e-6
+        sgn = np.sign(np.dot(c, r))
+        assert np.abs(maps[i] * sgn - aa_crop["pca_maps"][i]).max() < 2e-4
+    np.testing.assert_allclose(model.mean_, aa_crop["pca_mean"], atol=1e-6)
+    # the model object quacks like sklearn's: transform() of the scaled data reproduces the maps
+    from sklearn.preprocessing import RobustScaler
+    Xs = RobustScaler().fit_transform(np.stack([b.ravel() for b in nb], axis=1))
+    t = model.transform(Xs)
+    assert np.abs(t[:, 0].reshape(nb[0].shape) - maps[0]).max() < 1e-4
+    # n_components < B
+    maps3, evr3, _ = I.perform_pca(nb, n_components=3)
+    assert len(maps3) == 3 and np.allclose(evr3, evr[:3])
+    assert np.array_equal(maps3[0], maps[0])
+
+
+def test_glcm_features_defaults_and_dense(I, aa_crop):
+    from oracle import glcm as og
+    nir = aa_crop["norm"][3]
+    for kw in (dict(), dict(levels=16, window_size=7, step_size=1), dict(levels=64, window_size=5, step_size=2)):
+        got = I.calculate_glcm_features(nir, **kw)
+        ref = og.glcm_features(nir, kw.get("levels", 32), kw.get("window_size", 21), kw.get("step_size", 21))
+        assert set(got) == {"contrast", "dissimilarity", "homogeneity", "energy", "correlation"}
+        for k in got:
+            assert got[k].shape == nir.shape and got[k].dtype == np.float32
+            np.testing.assert_allclose(got[k], ref[k], rtol=1e-5, atol=1e-6, err_msg=f"{k} {kw}")
+    with pytest.raises(Exception):
+        I.calculate_glcm_features(nir, distances=[2])
+
+
+def test_run_feature_extraction_stage(I, aa_crop):
+    bands = _bands(aa_crop)
+    feats, hier = I.run_feature_extraction_stage(bands)
+    for k in ("ndvi", "evi", "msavi", "ndwi", "mndwi", "ndbi", "bsi"):
+        assert np.array_equal(feats[k], aa_crop["ix_" + k]), k
+    assert len(feats["pca_result"]) == 7
+    np.testing.assert_allclose(feats["variance_ratio"], aa_crop["pca_evr"], rtol=5e-4)
+    l1 = hier["level_1"]
+    assert l1.shape == aa_crop["level1"].shape and l1.dtype == np.float32
+    assert np.array_equal(l1[..., :6], aa_crop["level1"][..., :6])        # ndwi, mndwi, ndvi, evi, ndbi, bsi
+    sgn = np.sign(np.dot(l1[..., 6].ravel(), aa_crop["level1"][..., 6].ravel()))
+    assert np.abs(l1[..., 6] * sgn - aa_crop["level1"][..., 6]).max() < 2e-4
+    assert set(feats["glcm_features"]) == {"contrast", "dissimilarity", "homogeneity", "energy", "correlation"}
+
+
+# ------------------------------------------------------------------------------------------- KMeans drop-in
+def _ix_dict(aa_crop, dtype):
+    names = ("ndvi", "evi", "msavi", "ndwi", "mndwi", "ndbi", "bsi")
+    d = {k: aa_crop["ix_" + k].astype(dtype) for k in names}
+    h, w = aa_crop["ix_ndvi"].shape
+    d.update(height=h, width=w)
+    return d, list(names)
+
+
+def test_kmeans_dropin_bit_exact_vs_reference_f64(E, aa_crop):
+    """Labels of the reference's own unsupervised_kmeans_classification (sklearn KMeans, k-means++ with seed 42,
+    convergence-driven stopping) on the float64 promotion of the features: bit exact."""
+    d, keys = _ix_dict(aa_crop, np.float64)
+    lab = E.unsupervised_kmeans_classification(d, n_clusters=5, feature_keys_to_use=keys)
+    assert lab.dtype == np.int32 and lab.shape == aa_crop["kmeans_labels_k5_f64"].shape
+    assert np.array_equal(lab, aa_crop["kmeans_labels_k5_f64"]), f"{(lab != aa_crop['kmeans_labels_k5_f64']).sum()} differ"
+
+
+def test_kmeans_dropin_3d_stack_key(E, aa_crop):
+    d, keys = _ix_dict(aa_crop, np.float64)
+    stack = np.stack([d[k] for k in keys], axis=-1)
+    lab = E.unsupervised_kmeans_classification({"hierarchical_all": stack, "height": d["height"], "width": d["width"]},
+                                               n_clusters=7, feature_keys_to_use=["hierarchical_all"])
+    assert np.array_equal(lab, aa_crop["kmeans_labels_k7_f64_3d"])
+
+
+def test_kmeans_dropin_auto_keys_and_nan(E, aa_crop):
+    """feature_keys_to_use=None selects every (H, W) array; NaNs are replaced by 0 (extract.py:548-556)."""
+    d, keys = _ix_dict(aa_crop, np.float64)
+    ref = E.unsupervised_kmeans_classification(dict(d), n_clusters=5, feature_keys_to_use=keys)
+    auto = E.unsupervised_kmeans_classification(dict(d), n_clusters=5)
+    assert np.array_equal(ref, auto)
+    d2 = dict(d)
+    z = d["ndvi"].copy()
+    z[4:9, 10:20] = 0.0
+    n = d["ndvi"].copy()
+    n[4:9, 10:20] = np.nan
+    d2["ndvi"] = z
+    a = E.unsupervised_kmeans_classification(d2, n_clusters=4, feature_keys_to_use=keys)
+    d2["ndvi"] = n
+    b = E.unsupervised_kmeans_classification(d2, n_clusters=4, feature_keys_to_use=keys)
+    assert np.array_equal(a, b)
+
+
+def test_kmeans_dropin_errors(E, aa_crop):
+    d, keys = _ix_dict(aa_crop, np.float32)
+    with pytest.raises(ValueError):
+        E.unsupervised_kmeans_classification({"ndvi": d["ndvi"]}, 5)                       # no height/width
+    with pytest.raises(ValueError):
+        E.unsupervised_kmeans_classification({}, 5)
+    with pytest.raises(ValueError):
+        E.unsupervised_kmeans_classification(dict(d), 5, feature_keys_to_use=[])           # no usable keys
+    with pytest.raises(ValueError):                                                        # all keys mis-shaped -> nothing stacked
+        E.unsupervised_kmeans_classification({"x": np.zeros((3, 3)), "height": d["height"], "width": d["width"]}, 5,
+                                             feature_keys_to_use=["x"])
+
+
+def test_kmeans_dropin_f32_agreement(E, aa_crop):
+    """float32 features: sklearn's own float32 result depends on BLAS summation order, so this is an agreement
+    check (cluster partition identical for >= 99 % of the pixels), not a bit-exact one."""
+    d, keys = _ix_dict(aa_crop, np.float32)
+    lab = E.unsupervised_kmeans_classification(d, n_clusters=5, feature_keys_to_use=keys)
+    ref = aa_crop["kmeans_labels_k5"]
+    # labels may be permuted if the seeding differed; map by majority
+    agree = 0
+    for k in range(5):
+        m = lab == k
+        if m.any():
+            agree += np.bincount(ref[m], minlength=5).max()
+    assert agree >= 0.99 * lab.size, agree / lab.size

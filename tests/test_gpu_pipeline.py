@@ -162,13 +162,13 @@ def test_kmeans_partition_invariance(P):
     km = P.DeviceKMeans(fr.planes, fr.n_px, D, K, mn[:D], mx[:D], fr.n_px, fr.W)
     c0 = km.scale_rows(km.gather_rows(P.draw_init_indices(fr.n_px, K, 1), 0))
     km.setup(c0)
-    _lib.call("rsx_kmeans_assign", ptr(fr.planes), km.stride, fr.n_px, fr.W, ptr(km.state), ptr(km.acc), None, None, None, 1, D, K, stream_ptr())
+    _lib.call("rsx_kmeans_assign", ptr(fr.planes), km.stride, fr.n_px, fr.W, ptr(km.state), ptr(km.acc), None, None, None, None, 1, D, K, stream_ptr())
     whole = km.acc.clone()
     km.acc.zero_()
     half = (fr.n_px // 2) // 4 * 4 + 4
     import ctypes as C
-    _lib.call("rsx_kmeans_assign", ptr(fr.planes), km.stride, half, 64, ptr(km.state), ptr(km.acc), None, None, None, 1, D, K, stream_ptr())
+    _lib.call("rsx_kmeans_assign", ptr(fr.planes), km.stride, half, 64, ptr(km.state), ptr(km.acc), None, None, None, None, 1, D, K, stream_ptr())
     _lib.call("rsx_kmeans_assign", C.c_void_p(fr.planes.data_ptr() + 4 * half), km.stride, fr.n_px - half, 1000, ptr(km.state), ptr(km.acc),
-              None, None, None, 1, D, K, stream_ptr())
+              None, None, None, None, 1, D, K, stream_ptr())
     assert torch.equal(whole[:K * D + K], km.acc[:K * D + K])
     assert int(whole[K * D:K * D + K].sum()) == fr.n_px
