@@ -150,12 +150,17 @@ int rsx_nan_to_zero_f32(float* d_planes, int64_t n, rsx_stream_t stream);
  *                        centroids (scaled, un-centred coordinates, double [K][D]).
  *   rsx_kmeans_assign    ONE pass over the stack: argmin over centroids (fp32 fast path with a
  *                        float64 re-evaluation of near ties, first minimum wins), and, fused,
- *                        per-cluster int64 fixed-point sums + counts (update!=0), labels
- *                        (d_labels_u8 / d_labels_i32, each may be NULL), inertia (d_inertia!=NULL).
- *   rsx_kmeans_update    centroids <- sums/counts (multiply by 1/count), centre shift, empty-
- *                        cluster flag; zeroes the accumulators for the next pass.
- * d_acc: int64 [K*(D+1)] = sums [K][D] then counts [K]; a multi-GPU caller all-reduces it
- * between assign and update (integer adds: bit-identical for any partition of the pixels). */
+ *                        per-cluster int64 fixed-point sums + counts (update = 1: from scratch;
+ *                        update = 2: only the pixels whose label differs from the previous pass
+ *                        move their sample between clusters), labels (d_labels_u8 /
+ *                        d_labels_i32, each may be NULL), inertia (d_inertia != NULL).
+ *   rsx_kmeans_update    totals <- acc (delta = 0) or totals += acc (delta = 1); centroids <-
+ *                        totals/counts (multiply by 1/count), centre shift, empty-cluster flag;
+ *                        zeroes the pass accumulators.
+ * d_acc: int64 [2*(K*D + K + 2)] = the PASS block: sums [K][D], counts [K], near-tie counter, changed-label
+ * counter; then the TOTALS block of the same shape: running sums and counts, near ties so far, labels
+ * changed in the last pass.  A multi-GPU caller all-reduces the pass block between assign and update
+ * (integer adds: bit-identical for any partition); rsx_kmeans_update folds it into the totals and zeroes it. */
 int64_t rsx_kmeans_state_bytes(void);
 /* h_feat_min/max: per-feature min/max of the raw stack (MinMaxScaler.fit); h_mean_scaled: per-feature
  * mean of the scaled stack (the centring of _kmeans.py:1488-1490 - any value gives the same labels in
@@ -164,8 +169,8 @@ int64_t rsx_kmeans_state_bytes(void);
  * Not re-entrant: the state is mirrored in one __constant__ block per process. */
 int rsx_kmeans_setup(void* d_state, int D, int K, const double* h_feat_min, const double* h_feat_max,
                      const double* h_mean_scaled, const double* h_init_centroids, int64_t n_px_global, rsx_stream_t stream);
-/* d_acc: int64 [K*D + K + 2] = sums [K][D], counts [K], near-tie counter, changed-label counter; the caller
- * zeroes it once (rsx_kmeans_update re-zeroes sums and counts, the two counters keep accumulating).
+/* The caller zeroes d_acc once.  update: 0 = assign only, 1 = full update pass, 2 = delta update pass (needs d_labels_u8 and
+ * d_labels_prev_u8, distinct buffers; entries >= RSX_MAX_CLUSTERS in the previous labels mean "no previous label").
  * d_labels_prev_u8 (may be NULL): labels of the previous pass; the number of pixels whose label differs is
  * added to the changed-label counter (sklearn's strict-convergence test, _kmeans.py:723).
  * row_len: length (pixels) of an image row; only steers the traversal order (threads walk down columns
@@ -173,7 +178,7 @@ int rsx_kmeans_setup(void* d_state, int D, int K, const double* h_feat_min, cons
 int rsx_kmeans_assign(const float* d_stack, int64_t plane_stride, int64_t n_px, int row_len, const void* d_state,
                       int64_t* d_acc, uint8_t* d_labels_u8, const uint8_t* d_labels_prev_u8, int32_t* d_labels_i32,
                       double* d_inertia, int update, int D, int K, rsx_stream_t stream);
-int rsx_kmeans_update(void* d_state, int64_t* d_acc, rsx_stream_t stream);
+int rsx_kmeans_update(void* d_state, int64_t* d_acc, int delta, int D, rsx_stream_t stream);
 /* SYNCHRONISES the stream; centroids come back in scaled, un-centred coordinates, double [K][D];
  * h_shift_sq = squared centre shift of the last update; h_empty = empty clusters met so far. */
 int rsx_kmeans_read(const void* d_state, double* h_centroids, double* h_shift_sq, int32_t* h_empty, rsx_stream_t stream);

@@ -16,7 +16,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "librsx.so")
-SOURCES = ["rsx_core.cu", "rsx_raster_kernels.cu", "rsx_glcm.cu", "rsx_kmeans.cu"]
+# (source, object name, extra flags): the KMeans assign kernels are one source compiled once per range of D
+SOURCES = [("rsx_core.cu", "rsx_core", []), ("rsx_raster_kernels.cu", "rsx_raster_kernels", []), ("rsx_glcm.cu", "rsx_glcm", []),
+           ("rsx_kmeans.cu", "rsx_kmeans", [])] + [("rsx_kmeans_part.cu", f"rsx_kmeans_part{i}", [f"-DRSX_KM_PART={i}"]) for i in range(5)]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
@@ -28,8 +30,9 @@ def _nvcc():
     return exe
 
 
-def _digest(paths):
+def _digest(paths, extra=()):
     h = hashlib.sha256()
+    h.update(" ".join(extra).encode())
     for p in sorted(paths):
         h.update(p.encode())
         with open(p, "rb") as f:
@@ -49,19 +52,19 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
     deps = _deps()
     objs, jobs = [], []
-    for src in SOURCES:
+    for src, name, extra in SOURCES:
         sp = os.path.join(CSRC, src)
-        op = os.path.join(OBJ, src[:-3] + ".o")
+        op = os.path.join(OBJ, name + ".o")
         stamp = op + ".sha"
-        dig = _digest([sp] + deps)
+        dig = _digest([sp] + deps, extra)
         objs.append(op)
         if not force and os.path.exists(op) and os.path.exists(stamp) and open(stamp).read() == dig:
             continue
-        jobs.append((sp, op, stamp, dig))
+        jobs.append((sp, op, stamp, dig, extra))
 
     def compile_one(job):
-        sp, op, stamp, dig = job
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", sp, "-o", op]
+        sp, op, stamp, dig, extra = job
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", sp, "-o", op]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {sp}:\n{r.stdout}\n{r.stderr}")
@@ -70,7 +73,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return r.stderr
 
     if jobs:
-        with cf.ThreadPoolExecutor(max_workers=min(4, len(jobs))) as ex:
+        with cf.ThreadPoolExecutor(max_workers=min(os.cpu_count() or 4, 8, len(jobs))) as ex:
             for log in ex.map(compile_one, jobs):
                 if verbose and log:
                     print(log, file=sys.stderr)

@@ -1,0 +1,611 @@
+// K5 assign kernels: one pass over the feature stack = distances, argmin, partial sums, labels, inertia.
+// Compiled once per range of D (-DRSX_KM_PART=n, see rsx_kmeans_state.cuh); the host API lives in rsx_kmeans.cu.
+//
+// HBM layout: the feature stack is planar float32, D planes of n_px; one pass reads 4*D bytes/pixel (+1 B/px of previous
+// labels and 1 B/px of new labels when labels are tracked); centroids live in constant memory and reach FFMA2 as
+// uniform-register operands.
+//
+// Exactness: the parity target is sklearn run on the float64 promotion of the same stack.  The fast path evaluates the K
+// distances in fp32 and keeps the best and second best; when their gap is below a rigorous rounding bound tau (computed
+// per update from the centroid magnitudes) the pixel is re-evaluated in float64 with sklearn's operation order.  Partial
+// sums are int64 fixed point (x * 2^shift_d, rounded once per sample), so they are associative: any tiling, any number of
+// GPUs and any atomic ordering give bit-identical sums, hence bit-identical centroids.  For the same reason a DELTA pass
+// (only the pixels whose label changed move their sample from one cluster's sum to another's) reproduces exactly the
+// sums of a full pass.
+#include "rsx_kmeans_state.cuh"
+
+#ifndef RSX_KM_PART
+#error "compile with -DRSX_KM_PART=<0..4>"
+#endif
+
+__constant__ KmState g_km;  // refreshed (device-to-device) after every setup/update, per translation unit
+
+// ----------------------------------------------------------------------------- exact (float64) re-evaluation
+// Cold path: re-loads the pixel's features (L2 hits) so the hot loop keeps nothing in local memory.
+template <int D>
+__device__ __noinline__ int km_exact_argmin(const float* __restrict__ stack, int64_t plane_stride, int64_t p, double* dist_out) {
+    double X[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d)
+        X[d] = __dsub_rn(__dadd_rn(__dmul_rn((double)stack[d * plane_stride + p], g_km.scale64[d]), g_km.min64[d]), g_km.mean64[d]);
+    double best = 0.0, xx = 0.0;
+    int bi = 0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) xx = fma(X[d], X[d], xx);
+    for (int j = 0; j < g_km.K; ++j) {
+        double dot = 0.0;
+#pragma unroll
+        for (int d = 0; d < D; ++d) dot = fma(X[d], g_km.cent64[j * KM_MAXD + d], dot);
+        double v = fma(-2.0, dot, g_km.cnorm64[j]);
+        if (j == 0 || v < best) best = v, bi = j;
+    }
+    *dist_out = fmax(xx + best, 0.0);
+    return bi;
+}
+
+// ----------------------------------------------------------------------------- fp32 distances + tagged argmin
+#define KM_ARGMIN_STEP(A, B_, S_, I_, J)          \
+    S_ = fminf(S_, fmaxf(A, B_));                 \
+    if (A < B_) B_ = A, I_ = J;
+
+// Index-in-mantissa argmin: the low BITS bits of the fp32 distance are replaced by the centroid index, so best/runner-up
+// tracking is three FMNMX and no index bookkeeping.  The perturbation (< 2^BITS ulp) is part of the near-tie bound tau;
+// anything closer than tau is decided in float64 anyway, so fp32 ties never pick a label.
+template <int BITS>
+__device__ __forceinline__ float km_tag(float a, int j) { return __uint_as_float((__float_as_uint(a) & ~((1u << BITS) - 1u)) | (unsigned)j); }
+#define KM_ARGMIN_TAGGED(A, B_, S_, J)            \
+    {                                             \
+        const float t_ = km_tag<BITS>(A, J);      \
+        S_ = fminf(S_, fmaxf(t_, B_));            \
+        B_ = fminf(B_, t_);                       \
+    }
+
+__host__ __device__ constexpr int km_idx_bits(int KU) { return KU == 8 ? 3 : KU == 16 ? 4 : KU == 32 ? 5 : 6; }
+
+constexpr int KM_THREADS = 128;
+constexpr int KM_SLOTS = 8;
+
+// best / second-best tagged distances of the thread's 4 pixels (v[d] = feature d of pixels p..p+3).
+// KU = 8, 16, 32: that many centroid slots, fully unrolled, weights as constant-bank (uniform register) operands of FFMA2
+// (K <= KU; padding slots carry bias 1e30).  KU = 0: rolled loop over K (K > 32).
+template <int D, int KU>
+__device__ __forceinline__ void km_distances(const float4* v, int K, float (&b)[4], float (&s)[4]) {
+    constexpr int BITS = km_idx_bits(KU);
+    b[0] = b[1] = b[2] = b[3] = INFINITY;
+    s[0] = s[1] = s[2] = s[3] = INFINITY;
+    if (KU > 0) {
+#pragma unroll
+        for (int j = 0; j < KU; ++j) {
+            const float cA = g_km.bias32[j];
+            float2 a01 = make_float2(cA, cA), a23 = a01;
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                const float wa = g_km.w32[j * KM_MAXD + d];
+                a01 = __ffma2_rn(make_float2(v[d].x, v[d].y), make_float2(wa, wa), a01);
+                a23 = __ffma2_rn(make_float2(v[d].z, v[d].w), make_float2(wa, wa), a23);
+            }
+            KM_ARGMIN_TAGGED(a01.x, b[0], s[0], j) KM_ARGMIN_TAGGED(a01.y, b[1], s[1], j)
+            KM_ARGMIN_TAGGED(a23.x, b[2], s[2], j) KM_ARGMIN_TAGGED(a23.y, b[3], s[3], j)
+        }
+    } else {
+        const int Kp = (K + 1) & ~1;  // centroids in pairs; slot K (if K is odd) holds bias 1e30
+#pragma unroll 1
+        for (int j = 0; j < Kp; j += 2) {
+            const float cA = g_km.bias32[j], cB = g_km.bias32[j + 1];
+            float2 a01 = make_float2(cA, cA), a23 = a01, e01 = make_float2(cB, cB), e23 = e01;
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                const float wa = g_km.w32[j * KM_MAXD + d], wb = g_km.w32[(j + 1) * KM_MAXD + d];
+                const float2 x01 = make_float2(v[d].x, v[d].y), x23 = make_float2(v[d].z, v[d].w);
+                a01 = __ffma2_rn(x01, make_float2(wa, wa), a01);
+                a23 = __ffma2_rn(x23, make_float2(wa, wa), a23);
+                e01 = __ffma2_rn(x01, make_float2(wb, wb), e01);
+                e23 = __ffma2_rn(x23, make_float2(wb, wb), e23);
+            }
+            KM_ARGMIN_TAGGED(a01.x, b[0], s[0], j) KM_ARGMIN_TAGGED(a01.y, b[1], s[1], j)
+            KM_ARGMIN_TAGGED(a23.x, b[2], s[2], j) KM_ARGMIN_TAGGED(a23.y, b[3], s[3], j)
+            KM_ARGMIN_TAGGED(e01.x, b[0], s[0], j + 1) KM_ARGMIN_TAGGED(e01.y, b[1], s[1], j + 1)
+            KM_ARGMIN_TAGGED(e23.x, b[2], s[2], j + 1) KM_ARGMIN_TAGGED(e23.y, b[3], s[3], j + 1)
+        }
+    }
+}
+
+// label of one pixel from its tagged best/second distances (+ float64 decision of near ties, + inertia)
+template <int D, int KU, bool INERTIA>
+__device__ __forceinline__ int km_decide(const float* __restrict__ stack, int64_t plane_stride, int64_t p, const float (&x)[D], float best, float second,
+                                         double& inertia, unsigned& ties) {
+    int bi = (int)(__float_as_uint(best) & ((1u << km_idx_bits(KU)) - 1u));
+    double dist_exact = -1.0;
+    if (!(second - best > g_km.tau)) {  // near tie (or NaN): decide in float64
+        bi = km_exact_argmin<D>(stack, plane_stride, p, &dist_exact);
+        ++ties;
+    }
+    if (INERTIA) {
+        if (dist_exact < 0.0) {
+            // sum of squares of (x' - c): all terms positive, relative error ~D * 2^-24
+            float dd = 0.f;
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                float df = fmaf(x[d], g_km.scale32[d], g_km.off32[d]) - g_km.cent32[bi * KM_MAXD + d];
+                dd = fmaf(df, df, dd);
+            }
+            dist_exact = (double)dd;
+        }
+        inertia += dist_exact;
+    }
+    return bi;
+}
+
+// scalar path for the ragged tail (n_px % 4 pixels)
+template <int D>
+__device__ __forceinline__ int km_scalar_pixel(const float* __restrict__ stack, int64_t plane_stride, int64_t q, int K, float (&x)[D], bool want_inertia,
+                                               double& inertia, unsigned& ties) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) x[d] = stack[d * plane_stride + q];
+    float b = INFINITY, s = INFINITY;
+    int bi = 0;
+    for (int j = 0; j < K; ++j) {
+        float a = g_km.bias32[j];
+#pragma unroll
+        for (int d = 0; d < D; ++d) a = fmaf(x[d], g_km.w32[j * KM_MAXD + d], a);
+        KM_ARGMIN_STEP(a, b, s, bi, j)
+    }
+    double dist_exact = -1.0;
+    if (!(s - b > g_km.tau)) {
+        bi = km_exact_argmin<D>(stack, plane_stride, q, &dist_exact);
+        ++ties;
+    }
+    if (want_inertia) {
+        if (dist_exact < 0.0) {
+            float dd = 0.f;
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                float df = fmaf(x[d], g_km.scale32[d], g_km.off32[d]) - g_km.cent32[bi * KM_MAXD + d];
+                dd = fmaf(df, df, dd);
+            }
+            dist_exact = (double)dd;
+        }
+        inertia += dist_exact;
+    }
+    return bi;
+}
+
+__device__ __forceinline__ unsigned km_changed_mask(uint32_t diff) {
+    return ((diff & 0xffu) != 0) | (((diff & 0xff00u) != 0) << 1) | (((diff & 0xff0000u) != 0) << 2) | (((diff & 0xff000000u) != 0) << 3);
+}
+
+__device__ __forceinline__ void km_commit_counters(long long* __restrict__ gacc, int K, int D, unsigned ties, unsigned changed, double inertia,
+                                                   double* __restrict__ inertia_out, bool want_inertia) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ties += __shfl_xor_sync(0xffffffffu, ties, o);
+        changed += __shfl_xor_sync(0xffffffffu, changed, o);
+        if (want_inertia) inertia += __shfl_xor_sync(0xffffffffu, inertia, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (ties && gacc) atomicAdd(reinterpret_cast<unsigned long long*>(&gacc[K * D + K]), (unsigned long long)ties);
+        if (changed && gacc) atomicAdd(reinterpret_cast<unsigned long long*>(&gacc[K * D + K + 1]), (unsigned long long)changed);
+        if (want_inertia && inertia_out) atomicAdd(inertia_out, inertia);
+    }
+}
+
+// ============================================================================= kernel A: full pass, K <= 8
+// Sums from scratch with per-thread accumulators: every thread owns 8 slots (= labels) in shared memory, laid out
+// [slot][feature][thread] as int64 so that a warp's accesses are 256 contiguous bytes (2 wavefronts, no bank conflicts, no
+// atomics).  112 KB per CTA at D = 13, hence two CTAs per SM, a ping-pong register prefetch of the next row and an L2
+// prefetch further ahead.  The flat pixel array is viewed as rows of row_len pixels; a tile is 512 columns x 32 rows; a
+// thread owns 4 adjacent columns (one float4 per plane) and walks down the tile rows (CTA-uniform walk).
+constexpr int KM_TILE_W = KM_THREADS * 4;
+constexpr int KM_TILE_R = 32;
+
+struct KmWalk {
+    int64_t v_rows, tiles_total, tile, r, r_end, n4;
+    int tiles_x, row_len, col;
+    __device__ __forceinline__ bool open_tile() {
+        if (tile >= tiles_total) return false;
+        const int tx = (int)(tile % tiles_x);
+        const int64_t ty = tile / tiles_x;
+        col = tx * KM_TILE_W + threadIdx.x * 4;
+        r = ty * KM_TILE_R;
+        r_end = min(v_rows, r + KM_TILE_R);
+        return true;
+    }
+    __device__ __forceinline__ bool start(int64_t n4_, int row_len_) {
+        n4 = n4_, row_len = row_len_;
+        v_rows = (n4 + row_len - 1) / row_len;
+        tiles_x = (row_len + KM_TILE_W - 1) / KM_TILE_W;
+        tiles_total = ((v_rows + KM_TILE_R - 1) / KM_TILE_R) * tiles_x;
+        tile = blockIdx.x;
+        return open_tile();
+    }
+    __device__ __forceinline__ bool advance() {
+        if (++r < r_end) return true;
+        tile += gridDim.x;
+        return open_tile();
+    }
+    __device__ __forceinline__ int64_t pos() const { return r * row_len + col; }
+    __device__ __forceinline__ bool valid() const { return col < row_len && r * row_len + col < n4; }
+};
+
+template <int D>
+struct KmSmem {
+    static constexpr int CELLS = KM_SLOTS * (D + 1);
+    static constexpr int CACHE_BYTES = CELLS * KM_THREADS * 8;
+};
+
+template <int D>
+__global__ void __launch_bounds__(KM_THREADS, 2) km_full_kernel(const float* __restrict__ stack, int64_t plane_stride, int64_t n_px, int row_len,
+                                                                long long* __restrict__ gacc, uint8_t* __restrict__ lab8, const uint8_t* __restrict__ prev8,
+                                                                int32_t* __restrict__ lab32, int pf_rows) {
+    extern __shared__ __align__(16) unsigned char km_smem[];
+    const int K = g_km.K;
+    long long* cache = reinterpret_cast<long long*>(km_smem) + threadIdx.x;  // [slot][d][thread], this thread's column pre-applied
+    for (int i = threadIdx.x; i < KmSmem<D>::CELLS * KM_THREADS; i += KM_THREADS) reinterpret_cast<long long*>(km_smem)[i] = 0;
+    __syncthreads();
+    double inertia = 0.0;
+    unsigned ties = 0, changed = 0;
+    const int64_t n4 = n_px & ~(int64_t)3;
+    auto accumulate = [&](int label, const float (&x)[D]) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) cache[(label * (D + 1) + d) * KM_THREADS] += __float2ll_rn(x[d] * g_km.pow2[d]);
+        cache[(label * (D + 1) + D) * KM_THREADS] += 1;
+    };
+    float4 va[D], vb[D];  // ping-pong register sets, one is consumed while the other is being loaded
+    uint32_t pva = 0xffffffffu, pvb = 0xffffffffu;
+    auto load_row = [&](float4* dst, uint32_t& pv, int64_t at) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) dst[d] = ldg_stream4(stack + d * plane_stride + at);
+        if (prev8) pv = __ldg(reinterpret_cast<const uint32_t*>(prev8 + at));
+    };
+    const int lane_pf = threadIdx.x & 31;
+    const bool do_pf = pf_rows > 0 && ((lane_pf & 7) == 0 || lane_pf == 31);
+    auto process_row = [&](const float4* v, uint32_t pv, int64_t p) {
+        if (do_pf && p + pf_rows * (int64_t)row_len + 4 <= n4) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) asm volatile("prefetch.global.L2 [%0];" ::"l"(stack + d * plane_stride + p + pf_rows * (int64_t)row_len));
+        }
+        float b[4], s[4];
+        km_distances<D, 8>(v, K, b, s);
+        int l[4];
+        float x[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) x[d] = v[d].x;
+        l[0] = km_decide<D, 8, false>(stack, plane_stride, p, x, b[0], s[0], inertia, ties);
+        accumulate(l[0], x);
+#pragma unroll
+        for (int d = 0; d < D; ++d) x[d] = v[d].y;
+        l[1] = km_decide<D, 8, false>(stack, plane_stride, p + 1, x, b[1], s[1], inertia, ties);
+        accumulate(l[1], x);
+#pragma unroll
+        for (int d = 0; d < D; ++d) x[d] = v[d].z;
+        l[2] = km_decide<D, 8, false>(stack, plane_stride, p + 2, x, b[2], s[2], inertia, ties);
+        accumulate(l[2], x);
+#pragma unroll
+        for (int d = 0; d < D; ++d) x[d] = v[d].w;
+        l[3] = km_decide<D, 8, false>(stack, plane_stride, p + 3, x, b[3], s[3], inertia, ties);
+        accumulate(l[3], x);
+        const uint32_t packed = (uint32_t)l[0] | ((uint32_t)l[1] << 8) | ((uint32_t)l[2] << 16) | ((uint32_t)l[3] << 24);
+        if (prev8) changed += __popc(km_changed_mask(packed ^ pv));  // sklearn's strict-convergence test (_kmeans.py:723)
+        if (lab8) *reinterpret_cast<uint32_t*>(lab8 + p) = packed;
+        if (lab32) *reinterpret_cast<int4*>(lab32 + p) = make_int4(l[0], l[1], l[2], l[3]);
+    };
+    KmWalk walk;
+    bool more = walk.start(n4, row_len);
+    int64_t pa = 0, pb = 0;
+    bool oka = false, okb = false;
+    if (more) {
+        pa = walk.pos(), oka = walk.valid();
+        if (oka) load_row(va, pva, pa);
+    }
+    while (more) {
+        more = walk.advance();
+        if (more) {
+            pb = walk.pos(), okb = walk.valid();
+            if (okb) load_row(vb, pvb, pb);
+        }
+        if (oka) process_row(va, pva, pa);
+        if (!more) break;
+        more = walk.advance();
+        if (more) {
+            pa = walk.pos(), oka = walk.valid();
+            if (oka) load_row(va, pva, pa);
+        }
+        if (okb) process_row(vb, pvb, pb);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (int64_t q = n4; q < n_px; ++q) {
+            float x[D];
+            const int l = km_scalar_pixel<D>(stack, plane_stride, q, K, x, false, inertia, ties);
+            accumulate(l, x);
+            if (prev8) changed += prev8[q] != l;
+            if (lab8) lab8[q] = (uint8_t)l;
+            if (lab32) lab32[q] = l;
+        }
+    }
+    __syncthreads();
+    // column sums over the CTA's threads: warp w takes cells w, w+4, ...
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long* base = reinterpret_cast<const long long*>(km_smem);
+    for (int c = warp; c < K * (D + 1); c += KM_THREADS / 32) {
+        long long t = 0;
+#pragma unroll
+        for (int i = 0; i < KM_THREADS / 32; ++i) t += base[c * KM_THREADS + lane + 32 * i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0 && t) {
+            const int j = c / (D + 1), d = c % (D + 1);
+            long long* dst = d < D ? &gacc[j * D + d] : &gacc[K * D + j];
+            atomicAdd(reinterpret_cast<unsigned long long*>(dst), (unsigned long long)t);
+        }
+    }
+    km_commit_counters(gacc, K, D, ties, changed, 0.0, nullptr, false);
+}
+
+// ============================================================================= kernel B: TMA-staged streaming pass
+// The flat pixel array is cut into blocks of 512 pixels; CTA b handles blocks b, b + grid, ...  One elected thread stages
+// each block's D plane segments (2 KB each) into shared memory with bulk asynchronous copies (TMA engine, no tensor map)
+// that complete on an mbarrier; n_stages blocks are in flight per CTA, so HBM latency is decoupled from registers and the
+// kernel runs at up to four CTAs per SM.  Every thread then takes its 4 pixels (one LDS.128 per plane).
+//   KM_ASSIGN  labels (+ inertia)
+//   KM_DELTA   labels + the pixels whose label differs from the previous pass move their fixed-point sample between the
+//              clusters' sums: the warp handles its changed pixels together - lane d reads feature d of the pixel from the
+//              staged block, converts it and updates the WARP's private [K][D+1] int64 accumulator in shared memory (plain
+//              read-modify-write: lanes own distinct cells, control flow is CTA-uniform); lane D moves the count.
+//   KM_FULL    as KM_DELTA with every pixel "moving in" from nowhere (used for K > 8, where per-thread accumulators do
+//              not fit in shared memory)
+constexpr int KM_BLOCK_PX = KM_THREADS * 4;
+
+template <int D>
+__device__ __forceinline__ void km_move_samples(const float* __restrict__ st, unsigned cm, int local_px, uint32_t old_packed, uint32_t new_packed,
+                                                long long* __restrict__ wacc, float my_pow2) {
+    unsigned b = __ballot_sync(0xffffffffu, cm != 0);
+    const int lane = threadIdx.x & 31;
+    while (b) {
+        const int src = __ffs(b) - 1;
+        b &= b - 1;
+        const unsigned m = __shfl_sync(0xffffffffu, cm, src);
+        const int px = __shfl_sync(0xffffffffu, local_px, src);
+        const uint32_t ov = __shfl_sync(0xffffffffu, old_packed, src), nv = __shfl_sync(0xffffffffu, new_packed, src);
+        if (lane <= D) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (m & (1u << i)) {
+                    const int from = (int)((ov >> (8 * i)) & 0xffu), to = (int)((nv >> (8 * i)) & 0xffu);
+                    long long q = 1;
+                    if (lane < D) q = __float2ll_rn(st[lane * KM_BLOCK_PX + px + i] * my_pow2);
+                    wacc[to * (D + 1) + lane] += q;
+                    if (from < KM_MAXK) wacc[from * (D + 1) + lane] -= q;
+                }
+            }
+        }
+    }
+}
+
+template <int D, int MODE, bool INERTIA, int KU>
+__global__ void __launch_bounds__(KM_THREADS, 4) km_stream_kernel(const float* __restrict__ stack, int64_t plane_stride, int64_t n_px,
+                                                                  long long* __restrict__ gacc, uint8_t* __restrict__ lab8,
+                                                                  const uint8_t* __restrict__ prev8, int32_t* __restrict__ lab32,
+                                                                  double* __restrict__ inertia_out, int n_stages) {
+    constexpr bool SUMS = MODE != KM_ASSIGN;
+    extern __shared__ __align__(128) unsigned char km_smem[];
+    const int K = g_km.K;
+    float* stages = reinterpret_cast<float*>(km_smem);                                                     // [n_stages][D][512]
+    long long* wacc_all = reinterpret_cast<long long*>(km_smem + (size_t)n_stages * D * KM_BLOCK_PX * 4);  // [4 warps][K][D+1]
+    uint64_t* full = reinterpret_cast<uint64_t*>(wacc_all + (SUMS ? (KM_THREADS / 32) * K * (D + 1) : 0)); // [n_stages]
+    long long* wacc = wacc_all + (threadIdx.x >> 5) * K * (D + 1);
+    const int64_t n4 = n_px & ~(int64_t)3;
+    const int64_t n_blocks = (n4 + KM_BLOCK_PX - 1) / KM_BLOCK_PX;
+    const int tid = threadIdx.x;
+
+    if (SUMS)
+        for (int i = tid; i < (KM_THREADS / 32) * K * (D + 1); i += KM_THREADS) wacc_all[i] = 0;
+    if (tid == 0) {
+        for (int s = 0; s < n_stages; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    auto issue = [&](int64_t blk, int s) {  // one thread: stage block blk
+        const int64_t p0 = blk * KM_BLOCK_PX;
+        const unsigned bytes = (unsigned)min((int64_t)KM_BLOCK_PX, n4 - p0) * 4u;
+        mbar_expect_tx(&full[s], bytes * D);
+        float* dst = stages + (size_t)s * D * KM_BLOCK_PX;
+#pragma unroll 1
+        for (int d = 0; d < D; ++d) bulk_g2s(dst + d * KM_BLOCK_PX, stack + d * plane_stride + p0, bytes, &full[s]);
+    };
+    if (tid == 0)
+        for (int s = 0; s < n_stages; ++s) {
+            const int64_t blk = blockIdx.x + (int64_t)s * gridDim.x;
+            if (blk < n_blocks) issue(blk, s);
+        }
+    const float my_pow2 = SUMS ? g_km.pow2[min((int)(tid & 31), D - 1)] : 0.f;
+    double inertia = 0.0;
+    unsigned ties = 0, changed = 0;
+    uint32_t pv_next = 0xffffffffu;
+    if (prev8 && (int64_t)blockIdx.x * KM_BLOCK_PX + 4 * tid < n4) pv_next = __ldg(reinterpret_cast<const uint32_t*>(prev8 + (int64_t)blockIdx.x * KM_BLOCK_PX + 4 * tid));
+
+    int s = 0;
+    unsigned parity = 0;
+    for (int64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+        const int64_t p = blk * KM_BLOCK_PX + 4 * tid;
+        const bool valid = p < n4;
+        const uint32_t pv = pv_next;
+        {
+            const int64_t pn = p + (int64_t)gridDim.x * KM_BLOCK_PX;  // previous labels of the next block: in flight during this one
+            pv_next = 0xffffffffu;
+            if (prev8 && pn < n4) pv_next = __ldg(reinterpret_cast<const uint32_t*>(prev8 + pn));
+        }
+        mbar_wait(&full[s], parity);
+        const float* st = stages + (size_t)s * D * KM_BLOCK_PX;
+        uint32_t packed = 0, diff = 0;
+        if (valid) {
+            float4 v[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) v[d] = *reinterpret_cast<const float4*>(st + d * KM_BLOCK_PX + 4 * tid);
+            float b[4], sc[4];
+            km_distances<D, KU>(v, K, b, sc);
+            int l[4];
+            float x[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) x[d] = v[d].x;
+            l[0] = km_decide<D, KU, INERTIA>(stack, plane_stride, p, x, b[0], sc[0], inertia, ties);
+#pragma unroll
+            for (int d = 0; d < D; ++d) x[d] = v[d].y;
+            l[1] = km_decide<D, KU, INERTIA>(stack, plane_stride, p + 1, x, b[1], sc[1], inertia, ties);
+#pragma unroll
+            for (int d = 0; d < D; ++d) x[d] = v[d].z;
+            l[2] = km_decide<D, KU, INERTIA>(stack, plane_stride, p + 2, x, b[2], sc[2], inertia, ties);
+#pragma unroll
+            for (int d = 0; d < D; ++d) x[d] = v[d].w;
+            l[3] = km_decide<D, KU, INERTIA>(stack, plane_stride, p + 3, x, b[3], sc[3], inertia, ties);
+            packed = (uint32_t)l[0] | ((uint32_t)l[1] << 8) | ((uint32_t)l[2] << 16) | ((uint32_t)l[3] << 24);
+            if (prev8) diff = packed ^ pv;
+            if (lab8) *reinterpret_cast<uint32_t*>(lab8 + p) = packed;
+            if (lab32) *reinterpret_cast<int4*>(lab32 + p) = make_int4(l[0], l[1], l[2], l[3]);
+        }
+        unsigned cm = km_changed_mask(diff);
+        changed += __popc(cm);  // sklearn's strict-convergence test (_kmeans.py:723)
+        if (MODE == KM_FULL) cm = valid ? 0xfu : 0u;
+        if (SUMS) km_move_samples<D>(st, cm, 4 * tid, MODE == KM_FULL ? 0xffffffffu : pv, packed, wacc, my_pow2);
+        __syncthreads();  // everyone is done with stage s: refill it
+        if (tid == 0) {
+            const int64_t nb = blk + (int64_t)n_stages * gridDim.x;
+            if (nb < n_blocks) issue(nb, s);
+        }
+        if (++s == n_stages) s = 0, parity ^= 1u;
+    }
+    // ragged tail (n_px % 4 pixels): one thread, scalar
+    if (blockIdx.x == 0 && tid == 0) {
+        for (int64_t q = n4; q < n_px; ++q) {
+            float x[D];
+            const int l = km_scalar_pixel<D>(stack, plane_stride, q, K, x, INERTIA, inertia, ties);
+            const int old = (MODE == KM_FULL || !prev8) ? 255 : (int)prev8[q];
+            if (prev8 && prev8[q] != l) ++changed;
+            if (SUMS && (MODE == KM_FULL || old != l)) {  // warp 0's accumulator; its other lanes are past their loops
+                for (int d = 0; d < D; ++d) {
+                    const long long qv = __float2ll_rn(x[d] * g_km.pow2[d]);
+                    wacc[l * (D + 1) + d] += qv;
+                    if (old < KM_MAXK) wacc[old * (D + 1) + d] -= qv;
+                }
+                wacc[l * (D + 1) + D] += 1;
+                if (old < KM_MAXK) wacc[old * (D + 1) + D] -= 1;
+            }
+            if (lab8) lab8[q] = (uint8_t)l;
+            if (lab32) lab32[q] = l;
+        }
+    }
+    if (SUMS) {
+        __syncthreads();
+        for (int i = tid; i < K * (D + 1); i += KM_THREADS) {
+            long long t = 0;
+#pragma unroll
+            for (int w = 0; w < KM_THREADS / 32; ++w) t += wacc_all[w * K * (D + 1) + i];
+            if (t) {
+                const int j = i / (D + 1), d = i % (D + 1);
+                long long* dst = d < D ? &gacc[j * D + d] : &gacc[K * D + j];
+                atomicAdd(reinterpret_cast<unsigned long long*>(dst), (unsigned long long)t);
+            }
+        }
+    }
+    km_commit_counters(gacc, K, D, ties, changed, inertia, inertia_out, INERTIA);
+}
+
+// ----------------------------------------------------------------------------- launchers
+template <int D>
+static int km_launch_full(const KmLaunch& a, cudaStream_t s) {
+    const int smem = KmSmem<D>::CACHE_BYTES;
+    auto kern = km_full_kernel<D>;
+    static int per_sm = 0;
+    if (per_sm <= 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max(smem, 48 * 1024));
+        if (e != cudaSuccess) {
+            rsx_set_error("km_full: cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e));
+            return RSX_ERR_CUDA;
+        }
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, KM_THREADS, smem);
+        per_sm = max(per_sm, 1);
+    }
+    const int64_t n4 = a.n_px & ~(int64_t)3;
+    const int64_t v_rows = (n4 + a.row_len - 1) / a.row_len;
+    const int64_t n_tiles = ceil_div(v_rows, (int64_t)KM_TILE_R) * ceil_div(a.row_len, KM_TILE_W);
+    const int grid = (int)max((int64_t)1, min(n_tiles, (int64_t)rsx_num_sms() * per_sm));
+    kern<<<grid, KM_THREADS, smem, s>>>(a.stack, a.plane_stride, a.n_px, a.row_len, a.acc, a.lab8, a.prev8, a.lab32, a.pf_rows);
+    return rsx_check_launch("km_full");
+}
+
+template <int D, int MODE, bool INERTIA, int KU>
+static int km_launch_stream(const KmLaunch& a, cudaStream_t s) {
+    auto kern = km_stream_kernel<D, MODE, INERTIA, KU>;
+    const int acc_bytes = MODE == KM_ASSIGN ? 0 : (KM_THREADS / 32) * a.K * (D + 1) * 8;
+    auto smem_for = [&](int stages) { return stages * D * KM_BLOCK_PX * 4 + acc_bytes + stages * 8; };
+    // stages: enough blocks in flight per SM to cover HBM latency at full bandwidth (~64 KB/SM), within shared memory
+    static int cfg_K = -1, cfg_stages = 0, cfg_per_sm = 0;
+    if (cfg_K != a.K) {
+        int best_stages = 2, best_per_sm = 0;
+        for (int stages = a.n_stages > 0 ? a.n_stages : 2; stages <= (a.n_stages > 0 ? a.n_stages : 3); ++stages) {
+            const int smem = smem_for(stages);
+            if (smem > 227 * 1024) break;
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max(smem, 48 * 1024)) != cudaSuccess) break;
+            int per_sm = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, KM_THREADS, smem);
+            // prefer more resident CTAs (warps hide the compute latency), then more stages
+            if (per_sm > best_per_sm || (per_sm == best_per_sm && per_sm > 0)) best_per_sm = per_sm, best_stages = stages;
+        }
+        if (best_per_sm <= 0) {
+            cudaGetLastError();
+            rsx_set_error("km_stream: no launch configuration fits (D=%d, K=%d)", D, a.K);
+            return RSX_ERR_CUDA;
+        }
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max(smem_for(best_stages), 48 * 1024));
+        cfg_K = a.K, cfg_stages = best_stages, cfg_per_sm = best_per_sm;
+    }
+    const int64_t n4 = a.n_px & ~(int64_t)3;
+    const int64_t n_blocks = ceil_div(n4, (int64_t)KM_BLOCK_PX);
+    const int grid = (int)max((int64_t)1, min(n_blocks, (int64_t)rsx_num_sms() * cfg_per_sm));
+    kern<<<grid, KM_THREADS, smem_for(cfg_stages), s>>>(a.stack, a.plane_stride, a.n_px, a.acc, a.lab8, a.prev8, a.lab32, a.inertia, cfg_stages);
+    return rsx_check_launch("km_stream");
+}
+
+template <int D, int KU>
+static int km_launch2(const KmLaunch& a, cudaStream_t s) {
+    if (a.mode == KM_FULL) {
+        if (KU == 8) return km_launch_full<D>(a, s);
+        return km_launch_stream<D, KM_FULL, false, KU>(a, s);
+    }
+    if (a.mode == KM_DELTA) return km_launch_stream<D, KM_DELTA, false, KU>(a, s);
+    if (a.inertia) return km_launch_stream<D, KM_ASSIGN, true, KU>(a, s);
+    return km_launch_stream<D, KM_ASSIGN, false, KU>(a, s);
+}
+
+template <int D>
+static int km_launch(const KmLaunch& a, cudaStream_t s) {
+    if (a.K <= 8) return km_launch2<D, 8>(a, s);
+    if (a.K <= 16) return km_launch2<D, 16>(a, s);
+    if (a.K <= 32) return km_launch2<D, 32>(a, s);
+    return km_launch2<D, 0>(a, s);
+}
+
+#define KM_CAT2(a, b) a##b
+#define KM_CAT(a, b) KM_CAT2(a, b)
+#define KM_PART_FN(name) KM_CAT(KM_CAT(rsx_km_part, RSX_KM_PART), name)
+
+template <int D>
+static int km_dispatch(const KmLaunch& a, cudaStream_t s) {
+    if constexpr (D > km_part_hi(RSX_KM_PART)) {
+        rsx_set_error("rsx_kmeans_assign: D=%d is not in this translation unit", a.D);
+        return RSX_ERR_UNSUPPORTED;
+    } else {
+        if (a.D == D) return km_launch<D>(a, s);
+        return km_dispatch<D + 1>(a, s);
+    }
+}
+
+int KM_PART_FN(_assign)(const KmLaunch& a, cudaStream_t s) { return km_dispatch<km_part_lo(RSX_KM_PART)>(a, s); }
+
+int KM_PART_FN(_publish)(const void* d_state, cudaStream_t s) {
+    cudaError_t e = cudaMemcpyToSymbolAsync(g_km, d_state, sizeof(KmState), 0, cudaMemcpyDeviceToDevice, s);
+    if (e != cudaSuccess) {
+        rsx_set_error("kmeans: publishing state to constant memory failed: %s", cudaGetErrorString(e));
+        return RSX_ERR_CUDA;
+    }
+    return RSX_OK;
+}

@@ -1,0 +1,58 @@
+// KMeans device state + constants shared by the host-side API (rsx_kmeans.cu) and the assign-kernel translation units
+// (rsx_kmeans_part.cu, compiled once per range of D).
+#pragma once
+#include "rsx_common.cuh"
+
+#define KM_MAXD RSX_MAX_FEATURES
+#define KM_MAXK RSX_MAX_CLUSTERS
+
+struct KmState {
+    int D, K;
+    long long n_global;
+    double scale64[KM_MAXD], min64[KM_MAXD], mean64[KM_MAXD];  // MinMax scale_, min_; centring mean (scaled coords)
+    double absmax[KM_MAXD];                                     // max |raw x_d|
+    float scale32[KM_MAXD], off32[KM_MAXD];                     // x' ~= fma(x, scale32, off32), off = min_ - mean
+    float pow2[KM_MAXD];                                        // 2^shift_d (fixed-point scale of the raw feature)
+    double inv_pow2[KM_MAXD];
+    double cent64[KM_MAXK * KM_MAXD];                           // centred, scaled coordinates [K][D]
+    double cnorm64[KM_MAXK];
+    // fp32 fast path works on RAW features: dist_j = bias32[j] + sum_d x_d * w32[j][d] with
+    // w = -2 c_jd scale_d and bias = |c_j|^2 - 2 sum_d c_jd (min_d - mean_d): scaling and centring are folded in
+    float w32[KM_MAXK * KM_MAXD];
+    float bias32[KM_MAXK];
+    float cent32[KM_MAXK * KM_MAXD];                            // centred, scaled coordinates in fp32 (inertia only)
+    float tau;
+    float pad0;
+    double shift_sq;
+    int n_empty;
+    int n_updates;
+};
+
+
+constexpr int KM_ASSIGN = 0, KM_FULL = 1, KM_DELTA = 2;  // the `update` argument of rsx_kmeans_assign
+
+// one translation unit per range of D (compile time); each owns a __constant__ mirror of the state
+#define KM_NUM_PARTS 5
+__host__ __device__ constexpr int km_part_of(int D) { return D <= 8 ? 0 : D <= 12 ? 1 : D <= 15 ? 2 : D <= 18 ? 3 : 4; }
+__host__ __device__ constexpr int km_part_lo(int part) { return part == 0 ? 1 : part == 1 ? 9 : part == 2 ? 13 : part == 3 ? 16 : 19; }
+__host__ __device__ constexpr int km_part_hi(int part) { return part == 0 ? 8 : part == 1 ? 12 : part == 2 ? 15 : part == 3 ? 18 : 20; }
+
+struct KmLaunch {
+    const float* stack;
+    int64_t plane_stride, n_px;
+    int row_len;
+    long long* acc;
+    uint8_t* lab8;
+    const uint8_t* prev8;
+    int32_t* lab32;
+    double* inertia;
+    int mode, D, K;
+    int pf_rows;   // full-pass kernel: L2 prefetch distance in rows (0 = off)
+    int n_stages;  // streaming kernel: blocks in flight per CTA (0 = choose)
+};
+typedef int (*km_assign_fn)(const KmLaunch&, cudaStream_t);
+typedef int (*km_publish_fn)(const void* d_state, cudaStream_t);
+#define KM_DECLARE_PART(N)                                      \
+    int rsx_km_part##N##_assign(const KmLaunch&, cudaStream_t); \
+    int rsx_km_part##N##_publish(const void* d_state, cudaStream_t);
+KM_DECLARE_PART(0) KM_DECLARE_PART(1) KM_DECLARE_PART(2) KM_DECLARE_PART(3) KM_DECLARE_PART(4)

@@ -201,7 +201,7 @@ class DeviceKMeans:
     """Lloyd iterations on a planar float32 stack that stays in HBM."""
 
     def __init__(self, planes: torch.Tensor, n_px: int, D: int, K: int, feat_min, feat_max, n_global: int, row_len: int,
-                 comm: Optional[Comm] = None, timer: StageTimer = NO_TIMER):
+                 comm: Optional[Comm] = None, timer: StageTimer = NO_TIMER, delta: bool = True):
         require_cuda()
         self.comm = comm or Comm()
         self.timer = timer
@@ -214,8 +214,15 @@ class DeviceKMeans:
         self.scale, self.min_ = minmax_scale_params(self.fmin, self.fmax)
         dev = planes.device
         self.state = torch.zeros(int(_lib.load().rsx_kmeans_state_bytes()), dtype=torch.uint8, device=dev)
-        self.acc = torch.zeros(K * D + K + 2, dtype=torch.int64, device=dev)
+        # pass sums/counts + near-tie and changed-label counters (all-reduced), then the running totals (rsx.h)
+        self.n_acc = K * D + K + 2
+        self.acc = torch.zeros(2 * (K * D + K + 2), dtype=torch.int64, device=dev)
         self.inertia = torch.zeros(1, dtype=torch.float64, device=dev)
+        # delta passes: after the first (full) pass only the pixels whose label changed move their sample between the
+        # clusters' integer sums - the same totals as a full pass, without touching the accumulators for the rest
+        self.delta = bool(delta)
+        self._labels = None
+        self._passes = 0
 
     def scale_rows(self, raw_rows: np.ndarray) -> np.ndarray:
         """MinMaxScaler.transform of raw feature rows in float64: X*scale + min_."""
@@ -238,19 +245,47 @@ class DeviceKMeans:
         # any centring origin gives the same labels in exact arithmetic; 0.5 minimises the fp32 rounding bound
         mu = np.full(self.D, 0.5) if mean_scaled is None else np.ascontiguousarray(mean_scaled, dtype=np.float64)
         self.acc.zero_()
+        self._passes = 0
         _lib.call("rsx_kmeans_setup", ptr(self.state), self.D, self.K, hptr(self.fmin), hptr(self.fmax), hptr(mu), hptr(c0),
                   self.n_global, stream_ptr())
 
-    def step(self, labels_out: Optional[torch.Tensor] = None, labels_prev: Optional[torch.Tensor] = None):
-        """One fused assign + partial-sum pass, the all-reduce of K*(D+1) integers, one centroid update.
-        labels_out / labels_prev: optional uint8 label planes (this pass / the previous one) for the convergence test."""
+    def _label_planes(self):
+        if self._labels is None:
+            npad = (self.n_px + 3) // 4 * 4
+            self._labels = [torch.full((max(npad, 4),), 255, dtype=torch.uint8, device=self.planes.device) for _ in range(2)]
+        return self._labels
+
+    def step(self, track_labels: bool = False):
+        """One fused assign + partial-sum pass, the all-reduce of K*(D+1)+2 integers, one centroid update.
+        The first pass accumulates from scratch; later passes are delta passes (if enabled).  With track_labels (or delta)
+        every pass writes uint8 labels and counts the pixels whose label changed (acc[K*D+K+1])."""
+        use_labels = track_labels or self.delta
+        # K > 8: the delta kernel is also the full pass (previous labels = 255: every pixel "moves in" from nowhere)
+        mode = 2 if (self.delta and (self._passes > 0 or self.K > 8)) else 1
+        cur = prev = None
+        if use_labels:
+            planes = self._label_planes()
+            if self._passes == 0:
+                planes[1].fill_(255)
+            cur, prev = planes[self._passes % 2], planes[(self._passes + 1) % 2]
         if self.n_px:
             with self.timer("kmeans_assign"):
                 _lib.call("rsx_kmeans_assign", ptr(self.planes), self.stride, self.n_px, self.row_len, ptr(self.state), ptr(self.acc),
-                          ptr(labels_out), ptr(labels_prev), None, None, 1, self.D, self.K, stream_ptr())
-        self.comm.all_reduce(self.acc)
+                          ptr(cur), ptr(prev), None, None, mode, self.D, self.K, stream_ptr())
+        self.comm.all_reduce(self.acc[:self.n_acc])
         with self.timer("kmeans_update"):
-            _lib.call("rsx_kmeans_update", ptr(self.state), ptr(self.acc), stream_ptr())
+            _lib.call("rsx_kmeans_update", ptr(self.state), ptr(self.acc), 1 if mode == 2 else 0, self.D, stream_ptr())
+        self._passes += 1
+
+    def changed_count(self) -> int:
+        """Pixels (all ranks) whose label changed in the last update pass; synchronises."""
+        return int(self.acc[2 * self.n_acc - 1].item())
+
+    def near_ties(self) -> int:
+        """Pixels (all ranks, all passes) decided by the float64 re-evaluation; collective, synchronises."""
+        t = self.acc[self.n_acc - 2:self.n_acc - 1].clone()          # the final assign-only pass is not folded by an update
+        self.comm.all_reduce(t)
+        return int(t.item()) + int(self.acc[2 * self.n_acc - 2].item())
 
     def finish(self, labels_i32: bool = True):
         """The extra assignment pass of sklearn (_kmeans.py:742-754) + inertia."""
@@ -277,33 +312,22 @@ class DeviceKMeans:
         """sklearn's _kmeans_single_lloyd stopping rules (_kmeans.py:703-754): stop when no label changed between two
         passes (strict convergence) or when the squared centre shift is <= tol; then the final assignment + inertia."""
         self.setup(init_centroids_scaled, mean_scaled)
-        dev = self.planes.device
-        npad = (self.n_px + 3) // 4 * 4
-        cur = torch.full((npad,), 255, dtype=torch.uint8, device=dev)
-        prev = torch.full((npad,), 255, dtype=torch.uint8, device=dev)
-        chg = self.K * self.D + self.K + 1
         n_iter = 0
         for it in range(max_iter):
-            self.acc[chg] = 0
-            self.step(cur, prev)
+            self.step(track_labels=True)       # the changed-label counter is part of the all-reduced block
             n_iter = it + 1
-            changed = self.acc[chg:chg + 1].clone()
-            self.comm.all_reduce(changed)
-            if int(changed.item()) == 0:
+            if self.changed_count() == 0:
                 break
             _, shift, _ = self.read()
             if shift <= tol:
                 break
-            cur, prev = prev, cur
         labels = self.finish(True)
         cent, shift, empty = self.read()
         if empty:
             raise _lib.RsxError(f"KMeans: {empty} empty cluster(s) met; empty-cluster relocation "
                                 "(sklearn _k_means_common.pyx:167-211) is not implemented on the device")
-        ties = self.acc[self.K * self.D + self.K:self.K * self.D + self.K + 1].clone()
-        self.comm.all_reduce(ties)
         return KMeansResult(labels=labels, centroids=cent, inertia=float(self.inertia.item()), n_iter=n_iter,
-                            near_ties=int(ties.item()), shift_sq=shift)
+                            near_ties=self.near_ties(), shift_sq=shift)
 
     def fit(self, init_centroids_scaled: np.ndarray, n_iter: int, labels_i32: bool = True) -> KMeansResult:
         self.setup(init_centroids_scaled)
@@ -311,17 +335,16 @@ class DeviceKMeans:
             self.step()
         labels = self.finish(labels_i32)
         cent, shift, empty = self.read()
-        ties = self.acc[self.K * self.D + self.K:self.K * self.D + self.K + 1].clone()
-        self.comm.all_reduce(ties)
         if empty:
             raise _lib.RsxError(f"KMeans: {empty} empty cluster(s) met; empty-cluster relocation "
                                 "(sklearn _k_means_common.pyx:167-211) is not implemented on the device")
         return KMeansResult(labels=labels, centroids=cent, inertia=float(self.inertia.item()), n_iter=n_iter,
-                            near_ties=int(ties.item()), shift_sq=shift)
+                            near_ties=self.near_ties(), shift_sq=shift)
 
 
 def kmeans_on_features(fr: FeatureResult, D: int, K: int, n_iter: int, seed: int, comm: Optional[Comm] = None,
-                       H_total: Optional[int] = None, first_row: int = 0, labels_i32: bool = True, timer: StageTimer = NO_TIMER):
+                       H_total: Optional[int] = None, first_row: int = 0, labels_i32: bool = True, timer: StageTimer = NO_TIMER,
+                       delta: bool = True):
     """Benchmark protocol: MinMax from the fused trackers, K initial centroids = seeded pixel
     rows of the scaled stack, exactly n_iter update passes, then the final assignment + inertia."""
     comm = comm or Comm()
@@ -332,7 +355,7 @@ def kmeans_on_features(fr: FeatureResult, D: int, K: int, n_iter: int, seed: int
     tmx = torch.from_numpy(mx[:D].copy()).to(fr.planes.device)
     comm.all_reduce(tmn, "min")
     comm.all_reduce(tmx, "max")
-    km = DeviceKMeans(fr.planes, fr.n_px, D, K, tmn.cpu().numpy(), tmx.cpu().numpy(), n_global, fr.W, comm, timer)
+    km = DeviceKMeans(fr.planes, fr.n_px, D, K, tmn.cpu().numpy(), tmx.cpu().numpy(), n_global, fr.W, comm, timer, delta)
     idx = draw_init_indices(n_global, K, seed)
     raw = km.gather_rows(idx, first_row * fr.W)
     c0 = km.scale_rows(raw)

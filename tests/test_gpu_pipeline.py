@@ -172,3 +172,43 @@ def test_kmeans_partition_invariance(P):
               None, None, None, None, 1, D, K, stream_ptr())
     assert torch.equal(whole[:K * D + K], km.acc[:K * D + K])
     assert int(whole[K * D:K * D + K].sum()) == fr.n_px
+
+
+@pytest.mark.parametrize("K,D,n_iter", [(8, 13, 7), (20, 9, 5)])
+def test_kmeans_delta_passes_equal_full_passes(P, K, D, n_iter):
+    """Delta passes (only pixels whose label changed touch the integer sums) give bit-identical totals, centroids,
+    labels and counters' meaning as recomputing the sums from scratch in every pass."""
+    import torch
+    from rs_image_segmentation_b200.synth import synth_raster_numpy
+    bip = synth_raster_numpy(143, 211, 7, np.uint8, 21, cell=16)
+    fr = P.extract_features(torch.from_numpy(bip).cuda(), P.FeatureConfig(glcm_window=5, glcm_step=1))
+    out = {}
+    for delta in (False, True):
+        res, km, c0 = P.kmeans_on_features(fr, D, K, n_iter, seed=5, delta=delta)
+        n = km.n_acc
+        out[delta] = (res.labels.cpu().numpy(), res.centroids, res.inertia, km.acc[n:n + K * D + K].cpu().numpy(), res.near_ties)
+    assert np.array_equal(out[False][3], out[True][3])                  # integer totals: sums and counts
+    assert int(out[True][3][K * D:].sum()) == fr.n_px
+    assert np.array_equal(out[False][1], out[True][1])                  # centroids bit for bit
+    assert np.array_equal(out[False][0], out[True][0])
+    assert out[False][2] == out[True][2]
+    assert out[False][4] == out[True][4]
+
+
+def test_kmeans_changed_counter(P):
+    """The changed-label counter of an update pass equals the number of labels that differ from the previous pass."""
+    import torch
+    from rs_image_segmentation_b200.synth import synth_raster_numpy
+    bip = synth_raster_numpy(90, 131, 7, np.uint8, 8, cell=16)
+    fr = P.extract_features(torch.from_numpy(bip).cuda(), P.FeatureConfig(glcm=False))
+    D, K = 7, 6
+    mn, mx = fr.minmax.read()
+    km = P.DeviceKMeans(fr.planes, fr.n_px, D, K, mn[:D], mx[:D], fr.n_px, fr.W)
+    km.setup(km.scale_rows(km.gather_rows(P.draw_init_indices(fr.n_px, K, 2), 0)))
+    prev = None
+    for it in range(4):
+        km.step(track_labels=True)
+        cur = km._labels[it % 2][:fr.n_px].cpu().numpy().copy()
+        expect = fr.n_px if prev is None else int((cur != prev).sum())
+        assert km.changed_count() == expect
+        prev = cur
