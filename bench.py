@@ -244,7 +244,7 @@ def run_rsx(args):
     peak, peak_src = peaks()
     ab = algorithmic_bytes(7, 1, D, T, 7)
     n_local = H * W
-    km_ms, km_n = stage.get("kmeans_assign", (0.0, 0))
+    km_ms, km_n = stage.get("kmeans_assign_delta", (0.0, 0))
     km_avg_ms = km_ms / max(km_n, 1)
     km_bytes = n_local * 4 * D
     achieved = km_bytes / (km_avg_ms * 1e-3) / 1e9 if km_avg_ms > 0 else 0.0
@@ -260,9 +260,11 @@ def run_rsx(args):
         "metric": "feature-stack+KMeans throughput", "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(args, H, W),
-        "roofline": {"bound": "hbm", "kernel": "km_assign_kernel<13,update> (20 of the 21 KMeans passes)", "achieved": achieved, "peak": peak,
+        "roofline": {"bound": "hbm", "kernel": "km_stream_kernel<13,DELTA,K<=8> (19 of the 21 KMeans passes: TMA-staged assign + exact delta update)",
+                     "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": km_bytes, "avg_launch_ms": km_avg_ms, "launches_timed": km_n,
+                     "algorithmic_bytes_per_launch": km_bytes, "algorithmic_bytes_per_pixel": 4 * D,
+                     "actual_bytes_per_pixel": 4 * D + 2, "avg_launch_ms": km_avg_ms, "launches_timed": km_n,
                      "share_of_step": km_ms / args.steps / ms_per_step if ms_per_step else None},
         "whole_path": {"algorithmic_bytes_per_pixel": ab["total"], "achieved_gbs_per_gpu": whole, "frac_of_peak": whole / peak,
                        "stage_ms_per_step": {k: v[0] / args.steps for k, v in stage.items()},

@@ -142,140 +142,158 @@ __global__ void __launch_bounds__(128) glcm_props_warp_kernel(const uint8_t* __r
 __host__ __device__ constexpr int dense_c0(int ang) { return ang == 3 ? 1 : 0; }
 __host__ __device__ constexpr int dense_c1(int ang, int win) { return ang <= 1 ? win - 1 : win; }
 
-__device__ __forceinline__ unsigned pair_code(int a, int b) { return (unsigned)tri_cell(a, b) | (a == b ? 0x8000u : 0u); }
-
-struct ColSums {
-    unsigned w1[4], w2[4];
-    unsigned long long sh[4];
+// Thread (t, ang): warp w serves angle w & 3 (so each SM sub-partition runs one angle's specialised code) and image
+// columns (w >> 2) * 32 + lane of the CTA's band.  Each thread owns the column sums of ITS angle at ITS column and - if
+// t < NTW - the angle's energy counters and window sums of window t; the four angle threads of a window meet in shared
+// memory.
+//
+// Energy without dependent read-modify-write chains: the WIN-ish pairs of one image row that enter (leave) a window may
+// hit the same cell, so a naive loop is a chain of LDS -> add -> STS.  Instead every pair code carries an "equal to the
+// pair d columns to the left" mask (computed once by the thread that produces the code, shared by all the windows that
+// contain it); a window then loads all its counters at once and corrects each by the number of equal pairs that precede
+// it inside the window (popc of the masked bits) - independent loads, ordered stores.
+// With weight w = 2 (a != b) or 4 (a == b):  E = sum_cells w U^2 = e + SW,  where e accumulates 2w*U_before on every
+// increment (and -2w*U_after on every decrement) and SW = sum over the window's pairs of w = 2n + 2*Neq (Neq = pairs with
+// a == b, one more packed column sum).
+// Pair code word: bits 0..3 = 2w, bits 4..13 = equality mask (bit 3+d: equal to the pair d columns left), bits 16..31 =
+// byte offset of the counter (cell * NTW).
+struct DenseShared {
+    uint4* xch;            // [4 ang][NT]: w1, w2, sh.lo, sh.hi column sums
+    float* outx;           // [4 ang][5][NT] partial properties
+    unsigned* codes;       // [4][RING][NT] pair code words
+    unsigned* base;        // [4][WIN + NT] cell ids of the row being entered (WIN sentinels on the left)
+    unsigned char* qring;  // [RING][NT] u8
+    unsigned char* cnt;    // [4][ncell][NTW] u8
+    const unsigned long long* homog_fx;
 };
 
-__device__ __forceinline__ void pair_terms(int a, int b, unsigned& w1, unsigned& w2, unsigned long long& sh, const unsigned long long* __restrict__ homog_fx) {
-    const int d = abs(a - b);
-    w1 = (unsigned)d + ((unsigned)(a * b) << 13);
-    w2 = (unsigned)(a + b) + ((unsigned)(a * a + b * b) << 14);
-    sh = homog_fx[d];
-}
-
-// Thread (t, ang): t = image column inside the CTA's band (threadIdx.x, NT of them, NT % 32 == 0 so a warp has one
-// angle), ang = threadIdx.y.  Each thread owns the column sums of ITS angle at ITS column and - if t < NTW - the
-// angle's energy counters and window sums of window t; the four angle threads of a window meet in shared memory.
-template <int WIN, int NT>
-__global__ void __launch_bounds__(NT * 4) glcm_dense_kernel(const uint8_t* __restrict__ q, int W, int L, int out_rows, int out_cols, int rows_per_cta,
-                                                            float* __restrict__ props, int64_t plane_stride) {
-    constexpr int NTW = NT - (WIN - 1);  // windows per CTA
+template <int WIN, int NT, int ANG>
+__device__ __forceinline__ void glcm_dense_body(const DenseShared sm, const uint8_t* __restrict__ q, int W, int L, int out_cols, int i_begin, int i_end,
+                                                int j0, int t, float* __restrict__ props, int64_t plane_stride) {
+    constexpr int NTW = NT - (WIN - 1);
     constexpr int RING = WIN + 1;
-    extern __shared__ __align__(16) unsigned char dsm[];
+    constexpr int DR = ANG == 0 ? 0 : 1;
+    constexpr int DC = ANG == 0 ? 1 : (ANG == 1 ? 1 : (ANG == 2 ? 0 : -1));
+    constexpr int C0 = ANG == 3 ? 1 : 0, C1 = ANG <= 1 ? WIN - 1 : WIN;  // anchor columns of the angle inside a window
+    constexpr int NPAIR = (ANG == 0 || ANG == 2) ? WIN * (WIN - 1) : (WIN - 1) * (WIN - 1);
     const int ncell = L * (L + 1) / 2;
-    // shared layout (16-byte aligned pieces first)
-    uint4* xch = reinterpret_cast<uint4*>(dsm);                             // [4 ang][NT]: w1, w2, sh.lo, sh.hi column sums
-    float* outx = reinterpret_cast<float*>(xch + 4 * NT);                   // [4 ang][5][NT] partial properties
-    unsigned* codes = reinterpret_cast<unsigned*>(outx + 20 * NT);          // [4][RING][NT]: (cell*NTW) << 1 | (a == b)
-    unsigned char* qring = reinterpret_cast<unsigned char*>(codes + 4 * RING * NT);  // [RING][NT] u8
-    unsigned char* cnt = qring + RING * NT;                                 // [4][ncell][NTW] u8
-    __shared__ unsigned long long homog_fx[64];
-
-    const int t = threadIdx.x, ang = threadIdx.y;
-    const int tid = ang * NT + t;
-    const int j0 = blockIdx.x * NTW;  // first window column == first image column of this CTA
-    const int i_begin = blockIdx.y * rows_per_cta;
-    const int i_end = min(out_rows, i_begin + rows_per_cta);
-    if (i_begin >= i_end) return;
     const bool has_win = t < NTW && j0 + t < out_cols;
     const bool col_ok = j0 + t < W;
-
-    for (int i = tid; i < 4 * ncell * NTW; i += 4 * NT) cnt[i] = 0;
-    if (tid < 64) homog_fx[tid] = (unsigned long long)(1099511627776.0 / (1.0 + (double)tid * (double)tid) + 0.5);  // 2^40/(1+k^2)
-
-    // geometry of this thread's angle: the partner of anchor (r, c) is (r + dr, c + dc)
-    const int dr = ang == 0 ? 0 : 1;
-    const int dc = ang == 0 ? 1 : (ang == 1 ? 1 : (ang == 2 ? 0 : -1));
-    const int c0 = ang == 3 ? 1 : 0, c1 = ang <= 1 ? WIN - 1 : WIN;  // anchor columns of the angle inside a window
-    const bool pair_ok = t + dc >= 0 && t + dc < NT;                  // partner column inside the band
-    const int n = (ang == 0 || ang == 2) ? WIN * (WIN - 1) : (WIN - 1) * (WIN - 1);
-    const float inv_n = 1.f / (float)n;
+    const bool pair_ok = t + DC >= 0 && t + DC < NT;  // partner column inside the band
+    const float inv_n = 1.f / (float)NPAIR;
 
     unsigned cw1 = 0, cw2 = 0;  // column sums of this (column, angle): packed moments
     unsigned long long csh = 0;
     int e = 0;
-    unsigned* my_codes = codes + ang * RING * NT + t;
-    unsigned char* my_cnt = cnt + (size_t)ang * ncell * NTW + t;
-    const unsigned char* qt = qring + t;
+    unsigned* my_codes = sm.codes + ANG * RING * NT + t;
+    unsigned* my_base = sm.base + ANG * (WIN + NT) + WIN + t;
+    unsigned char* my_cnt = sm.cnt + (size_t)ANG * ncell * NTW + t;
+    const unsigned char* qt = sm.qring + t;
 
-    // ring slot of an image row, kept incrementally: slot(i_begin + k) = k % RING
     auto slot_add = [](int s, int k) { s += k; return s >= RING ? s - RING : s; };
-
     auto load_q = [&](int r) -> unsigned char { return col_ok ? (unsigned char)min((int)q[(int64_t)r * W + j0 + t], L - 1) : (unsigned char)0; };
-    // pairs of this angle anchored in ring slot sa (partner row in slot sb) become complete
+    auto pair_terms = [&](int a, int b, unsigned& w1, unsigned& w2, unsigned long long& sh) {
+        const int d = abs(a - b);
+        w1 = (unsigned)d + ((unsigned)(a * b) << 13);
+        w2 = (unsigned)(a + b) + ((unsigned)(a * a + b * b) << 14);
+        sh = sm.homog_fx[d];  // 2^40/(1+d^2), plus 2^52 when d == 0 (the Neq field)
+    };
+    // pairs of this angle anchored in ring slot sa (partner row in slot sb) become complete: column sums + cell id
     auto enter_pairs = [&](int sa, int sb) {
+        unsigned cell = 0xfffffff0u;  // never equal to a real cell
         if (pair_ok) {
-            const int a = qt[sa * NT], b = qt[sb * NT + dc];
-            my_codes[sa * NT] = ((unsigned)(tri_cell(a, b) * NTW) << 1) | (a == b ? 1u : 0u);
+            const int a = qt[sa * NT], b = qt[sb * NT + DC];
+            cell = ((unsigned)(tri_cell(a, b) * NTW) << 16) | (a == b ? 8u : 4u);
             unsigned w1, w2;
             unsigned long long sh;
-            pair_terms(a, b, w1, w2, sh, homog_fx);
+            pair_terms(a, b, w1, w2, sh);
             cw1 += w1, cw2 += w2, csh += sh;
         }
+        *my_base = cell;
+    };
+    // after a barrier: attach the equality mask and publish the code word in ring slot sa
+    auto publish_code = [&](int sa) {
+        const unsigned cell = *my_base;
+        unsigned mask = 0;
+#pragma unroll
+        for (int d = 1; d < WIN; ++d)
+            if (my_base[-d] == cell) mask |= 1u << (3 + d);
+        my_codes[sa * NT] = cell | mask;
     };
     auto leave_pairs = [&](int sa, int sb) {
         if (pair_ok) {
             unsigned w1, w2;
             unsigned long long sh;
-            pair_terms(qt[sa * NT], qt[sb * NT + dc], w1, w2, sh, homog_fx);
+            pair_terms(qt[sa * NT], qt[sb * NT + DC], w1, w2, sh);
             cw1 -= w1, cw2 -= w2, csh -= sh;
         }
     };
-    // E = sum_cells weight * count^2, weight 2 (a != b) or 4 (a == b): (u+1)^2 - u^2 = 2u+1
     auto energy_add = [&](int sa) {
         const unsigned* row = my_codes + sa * NT;
+        unsigned code[WIN];
+        int u[WIN];
 #pragma unroll
-        for (int c = 0; c < WIN; ++c) {
-            if (c < c0 || c >= c1) continue;
-            const unsigned code = row[c];
-            unsigned char* cell = my_cnt + (code >> 1);
-            const int u = *cell;
-            e += (2 * u + 1) << (1 + (code & 1u));
-            *cell = (unsigned char)(u + 1);
+        for (int c = C0; c < C1; ++c) code[c] = row[c];
+#pragma unroll
+        for (int c = C0; c < C1; ++c) u[c] = my_cnt[code[c] >> 16];
+#pragma unroll
+        for (int c = C0; c < C1; ++c) {
+            constexpr unsigned all = 0x3ff0u;
+            const unsigned kmask = (((1u << (c - C0)) - 1u) << 4) & all;  // pairs of this window to the left of c
+            const int uu = u[c] + __popc(code[c] & kmask);
+            e += uu * (int)(code[c] & 0xfu);
+            my_cnt[code[c] >> 16] = (unsigned char)(uu + 1);
         }
     };
     auto energy_sub = [&](int sa) {
         const unsigned* row = my_codes + sa * NT;
+        unsigned code[WIN];
+        int u[WIN];
 #pragma unroll
-        for (int c = 0; c < WIN; ++c) {
-            if (c < c0 || c >= c1) continue;
-            const unsigned code = row[c];
-            unsigned char* cell = my_cnt + (code >> 1);
-            const int u = *cell;
-            e -= (2 * u - 1) << (1 + (code & 1u));
-            *cell = (unsigned char)(u - 1);
+        for (int c = C0; c < C1; ++c) code[c] = row[c];
+#pragma unroll
+        for (int c = C0; c < C1; ++c) u[c] = my_cnt[code[c] >> 16];
+#pragma unroll
+        for (int c = C0; c < C1; ++c) {
+            constexpr unsigned all = 0x3ff0u;
+            const unsigned kmask = (((1u << (c - C0)) - 1u) << 4) & all;
+            const int uu = u[c] - __popc(code[c] & kmask) - 1;
+            e -= uu * (int)(code[c] & 0xfu);
+            my_cnt[code[c] >> 16] = (unsigned char)uu;
         }
     };
 
     // prologue: bring in the WIN rows of the first window (row i_begin + r lives in slot r)
-    __syncthreads();
     for (int r = 0; r < WIN; ++r) {
-        if (ang == 0) qring[r * NT + t] = load_q(i_begin + r);
+        if (ANG == 0) sm.qring[r * NT + t] = load_q(i_begin + r);
         __syncthreads();
-        if (r - dr >= 0) enter_pairs(r - dr, r);
+        if (r - DR >= 0) enter_pairs(r - DR, r);
         __syncthreads();
-        if (has_win && r - dr >= 0) energy_add(r - dr);
+        if (r - DR >= 0) publish_code(r - DR);
+        __syncthreads();
+        if (has_win && r - DR >= 0) energy_add(r - DR);
     }
     unsigned char q_next = 0;  // register prefetch of the next row's sample
-    if (ang == 0 && i_begin + 1 < i_end) q_next = load_q(i_begin + WIN);
+    if (ANG == 0 && i_begin + 1 < i_end) q_next = load_q(i_begin + WIN);
 
-    int s_top = 0;  // ring slot of image row i (the top row of the current window)
-    // the property this thread finalises for the whole window (the four angle threads share the five properties)
+    int s_top = 0;       // ring slot of image row i (the top row of the current window)
+    int s_pending = -1;  // ring slot whose pairs were published in the previous iteration and still have to enter E
     for (int i = i_begin; i < i_end; ++i) {
-        // (a) publish column sums
-        xch[ang * NT + t] = make_uint4(cw1, cw2, (unsigned)csh, (unsigned)(csh >> 32));
+        const bool more = i + 1 < i_end;
+        const int s_new = slot_add(s_top, WIN);  // slot that receives image row i + WIN (== slot of row i - 1)
+        // publish column sums; image row i + WIN enters the ring
+        sm.xch[ANG * NT + t] = make_uint4(cw1, cw2, (unsigned)csh, (unsigned)(csh >> 32));
+        if (ANG == 0 && more) sm.qring[s_new * NT + t] = q_next;
         __syncthreads();  // #1
-        // (b) window sums of this angle -> its share of the five properties
+        if (ANG == 0 && more && i + 2 < i_end) q_next = load_q(i + WIN + 1);
         if (has_win) {
+            if (s_pending >= 0) energy_add(s_pending);
+            // window sums of this angle -> its share of the five properties
             unsigned w1 = 0, w2 = 0;
             unsigned long long sh = 0;
-            const uint4* xa = xch + ang * NT + t;
+            const uint4* xa = sm.xch + ANG * NT + t;
 #pragma unroll
-            for (int c = 0; c < WIN; ++c) {
-                if (c < c0 || c >= c1) continue;
+            for (int c = C0; c < C1; ++c) {
                 const uint4 v = xa[c];
                 w1 += v.x;
                 w2 += v.y;
@@ -283,46 +301,81 @@ __global__ void __launch_bounds__(NT * 4) glcm_dense_kernel(const uint8_t* __res
             }
             const int s1 = (int)(w1 & 0x1fffu), sab = (int)(w1 >> 13);
             const int sa = (int)(w2 & 0x3fffu), sq = (int)(w2 >> 14);
-            float* o = outx + ang * 5 * NT + t;
+            const int neq = (int)(sh >> 52);
+            const unsigned long long shom = sh & ((1ull << 52) - 1ull);
+            float* o = sm.outx + ANG * 5 * NT + t;
             o[0 * NT] = (float)(sq - 2 * sab) * inv_n;
             o[1 * NT] = (float)s1 * inv_n;
-            o[2 * NT] = (float)((double)sh * 9.094947017729282e-13) * inv_n;  // 2^-40
-            o[3 * NT] = sqrtf((float)e) * (0.5f * inv_n);
-            const int var_num = 2 * n * sq - sa * sa, cov_num = 4 * n * sab - sa * sa;
+            o[2 * NT] = (float)((double)shom * 9.094947017729282e-13) * inv_n;  // 2^-40
+            o[3 * NT] = sqrtf((float)(e + 2 * NPAIR + 2 * neq)) * (0.5f * inv_n);
+            const int var_num = 2 * NPAIR * sq - sa * sa, cov_num = 4 * NPAIR * sab - sa * sa;
             o[4 * NT] = var_num <= 0 ? 1.f : (float)cov_num / (float)var_num;
         }
-        const bool more = i + 1 < i_end;
-        const int s_new = slot_add(s_top, WIN);  // slot that receives image row i + WIN (== slot of row i - 1)
+        int s_anchor = -1;
         if (more) {
-            // (c) the window moves down: pairs anchored in image row i leave
-            leave_pairs(s_top, slot_add(s_top, dr));
+            // the window moves down: pairs anchored in image row i leave, pairs completed by row i + WIN enter
+            leave_pairs(s_top, slot_add(s_top, DR));
             if (has_win) energy_sub(s_top);
-            // (d) image row i + WIN enters the ring
-            if (ang == 0) qring[s_new * NT + t] = q_next;
+            s_anchor = DR ? slot_add(s_top, WIN - 1) : s_new;
+            enter_pairs(s_anchor, s_new);
         }
-        __syncthreads();  // #2: outx complete, new q row visible
-        if (ang == 0 && more && i + 2 < i_end) q_next = load_q(i + WIN + 1);
+        __syncthreads();  // #2: outx complete, cell ids of the entering pairs visible
         if (has_win) {
             // combine the four angles: thread `ang` writes property `ang` (angle-0 threads also property 4)
             const int64_t o = (int64_t)i * out_cols + j0 + t;
             {
-                const int k = ang;
-                const float v = (outx[(0 * 5 + k) * NT + t] + outx[(1 * 5 + k) * NT + t]) + (outx[(2 * 5 + k) * NT + t] + outx[(3 * 5 + k) * NT + t]);
+                constexpr int k = ANG;
+                const float v = (sm.outx[(0 * 5 + k) * NT + t] + sm.outx[(1 * 5 + k) * NT + t]) + (sm.outx[(2 * 5 + k) * NT + t] + sm.outx[(3 * 5 + k) * NT + t]);
                 props[k * plane_stride + o] = v * 0.25f;
             }
-            if (ang == 0) {
-                const int k = 4;
-                const float v = (outx[(0 * 5 + k) * NT + t] + outx[(1 * 5 + k) * NT + t]) + (outx[(2 * 5 + k) * NT + t] + outx[(3 * 5 + k) * NT + t]);
+            if (ANG == 0) {
+                constexpr int k = 4;
+                const float v = (sm.outx[(0 * 5 + k) * NT + t] + sm.outx[(1 * 5 + k) * NT + t]) + (sm.outx[(2 * 5 + k) * NT + t] + sm.outx[(3 * 5 + k) * NT + t]);
                 props[k * plane_stride + o] = v * 0.25f;
             }
         }
         if (!more) break;
-        // (e) pairs completed by the new row: anchored in row i + WIN - dr
-        const int s_anchor = dr ? slot_add(s_top, WIN - 1) : s_new;
-        enter_pairs(s_anchor, s_new);
-        __syncthreads();  // #3: their codes are visible
-        if (has_win) energy_add(s_anchor);
+        publish_code(s_anchor);  // consumed after the next barrier #1
+        s_pending = s_anchor;
         s_top = slot_add(s_top, 1);
+    }
+}
+
+template <int WIN, int NT>
+__global__ void __launch_bounds__(NT * 4) glcm_dense_kernel(const uint8_t* __restrict__ q, int W, int L, int out_rows, int out_cols, int rows_per_cta,
+                                                            float* __restrict__ props, int64_t plane_stride) {
+    constexpr int NTW = NT - (WIN - 1);  // windows per CTA
+    constexpr int RING = WIN + 1;
+    extern __shared__ __align__(16) unsigned char dsm[];
+    __shared__ unsigned long long homog_fx[64];
+    const int ncell = L * (L + 1) / 2;
+    DenseShared sm;
+    sm.xch = reinterpret_cast<uint4*>(dsm);
+    sm.outx = reinterpret_cast<float*>(sm.xch + 4 * NT);
+    sm.codes = reinterpret_cast<unsigned*>(sm.outx + 20 * NT);
+    sm.base = sm.codes + 4 * RING * NT;
+    sm.qring = reinterpret_cast<unsigned char*>(sm.base + 4 * (WIN + NT));
+    sm.cnt = sm.qring + RING * NT;
+    sm.homog_fx = homog_fx;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int ang = warp & 3, t = (warp >> 2) * 32 + (tid & 31);
+    const int j0 = blockIdx.x * NTW;  // first window column == first image column of this CTA
+    const int i_begin = blockIdx.y * rows_per_cta;
+    const int i_end = min(out_rows, i_begin + rows_per_cta);
+    if (i_begin >= i_end) return;
+
+    for (int i = tid; i < 4 * ncell * NTW; i += 4 * NT) sm.cnt[i] = 0;
+    for (int i = tid; i < 4 * (WIN + NT); i += 4 * NT) sm.base[i] = 0xfffffff0u;
+    if (tid < 64)  // 2^40/(1+k^2); the k == 0 entry also counts the pair in the Neq field (bit 52)
+        homog_fx[tid] = (unsigned long long)(1099511627776.0 / (1.0 + (double)tid * (double)tid) + 0.5) + (tid == 0 ? (1ull << 52) : 0ull);
+    __syncthreads();
+    switch (ang) {  // warp-uniform
+        case 0: glcm_dense_body<WIN, NT, 0>(sm, q, W, L, out_cols, i_begin, i_end, j0, t, props, plane_stride); break;
+        case 1: glcm_dense_body<WIN, NT, 1>(sm, q, W, L, out_cols, i_begin, i_end, j0, t, props, plane_stride); break;
+        case 2: glcm_dense_body<WIN, NT, 2>(sm, q, W, L, out_cols, i_begin, i_end, j0, t, props, plane_stride); break;
+        default: glcm_dense_body<WIN, NT, 3>(sm, q, W, L, out_cols, i_begin, i_end, j0, t, props, plane_stride); break;
     }
 }
 
@@ -330,7 +383,7 @@ template <int WIN, int NT>
 static int launch_dense(const uint8_t* d_q, int W, int levels, int out_rows, int out_cols, float* d_props, int64_t plane_stride, cudaStream_t s) {
     constexpr int NTW = NT - (WIN - 1);
     const int ncell = levels * (levels + 1) / 2;
-    const size_t smem = (size_t)4 * ncell * NTW + (size_t)4 * (WIN + 1) * NT * 4 + (size_t)16 * NT * 4 + (size_t)20 * NT * 4 + (size_t)(WIN + 1) * NT + 64;
+    const size_t smem = (size_t)4 * ncell * NTW + (size_t)4 * (WIN + 1) * NT * 4 + (size_t)16 * (NT + WIN) + (size_t)16 * NT * 4 + (size_t)20 * NT * 4 + (size_t)(WIN + 1) * NT + 64;
     static size_t configured = 0;
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(glcm_dense_kernel<WIN, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max(smem, (size_t)49152));
@@ -357,7 +410,7 @@ static int launch_dense(const uint8_t* d_q, int W, int levels, int out_rows, int
     }
     const int rows_per_cta = ceil_div(out_rows, best_gy);
     const int gy = ceil_div(out_rows, rows_per_cta);
-    glcm_dense_kernel<WIN, NT><<<dim3(gx, gy), dim3(NT, 4), smem, s>>>(d_q, W, levels, out_rows, out_cols, rows_per_cta, d_props, plane_stride);
+    glcm_dense_kernel<WIN, NT><<<dim3(gx, gy), NT * 4, smem, s>>>(d_q, W, levels, out_rows, out_cols, rows_per_cta, d_props, plane_stride);
     return rsx_check_launch("glcm_dense");
 }
 
@@ -365,7 +418,7 @@ static int launch_dense(const uint8_t* d_q, int W, int levels, int out_rows, int
 template <int WIN>
 static int dispatch_dense(const uint8_t* d_q, int W, int levels, int out_rows, int out_cols, float* d_props, int64_t plane_stride, cudaStream_t s) {
     const int ncell = levels * (levels + 1) / 2;
-    auto fits = [&](int nt) { return (size_t)4 * ncell * (nt - (WIN - 1)) + (size_t)nt * (16 * (WIN + 1) + 64 + 80 + (WIN + 1)) + 64 <= (size_t)224 * 1024; };
+    auto fits = [&](int nt) { return (size_t)4 * ncell * (nt - (WIN - 1)) + (size_t)nt * (16 * (WIN + 1) + 16 + 64 + 80 + (WIN + 1)) + 16 * WIN + 64 <= (size_t)224 * 1024; };
     if (fits(256)) return launch_dense<WIN, 256>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, s);
     if (fits(128)) return launch_dense<WIN, 128>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, s);
     if (fits(96)) return launch_dense<WIN, 96>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, s);

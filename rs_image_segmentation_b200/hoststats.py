@@ -48,9 +48,11 @@ class OrderBase:
         if vi < 0:
             prev = nxt = np.asanyarray(0.0)
         pi, ni = int(prev), int(nxt)
-        gamma = np.asanyarray(vi - np.intp(pi), dtype=vi.dtype)
         a = self.at(pi if pi >= 0 else self.n - 1)
         b = self.at(ni if ni >= 0 else self.n - 1)
+        if a == b:  # both order statistics on one level (the usual case for a histogram): lerp(a, a, t) == a exactly
+            return np.result_type(a, vi).type(a)
+        gamma = np.asanyarray(vi - np.intp(pi), dtype=vi.dtype)
         return _lerp(a, b, gamma)
 
     def percentile_scalar(self, q):
@@ -75,9 +77,9 @@ class OrderBase:
 class LevelOrder(OrderBase):
     """Sorted view of one band: cumulative counts over grey levels + the value each level maps to."""
 
-    def __init__(self, hist, values):
+    def __init__(self, hist, values, cum=None):
         hist = np.asarray(hist, dtype=np.int64)
-        self.cum = np.cumsum(hist)
+        self.cum = np.cumsum(hist) if cum is None else cum
         self.n = int(self.cum[-1]) if hist.size else 0
         self.values = np.asarray(values)
         self.dtype = self.values.dtype
@@ -88,8 +90,9 @@ class LevelOrder(OrderBase):
 
     def at(self, k: int):
         """k-th smallest sample (0-based) of the band."""
-        k = min(max(int(k), 0), self.n - 1)
-        return self.values[int(np.searchsorted(self.cum, k, side="right"))]
+        k = int(k)
+        k = 0 if k < 0 else (self.n - 1 if k >= self.n else k)
+        return self.values[self.cum.searchsorted(k, "right")]
 
 
 def norm_params(lo, hi):
@@ -120,33 +123,57 @@ class RasterStats:
         hist = np.asarray(hist, dtype=np.int64)
         B, L = hist.shape
         self.B, self.L = B, L
+        self.hist = hist
         self.n = int(hist[0].sum())
         levels = np.arange(L, dtype=F32)
         self.norm = np.zeros((B, 3), F32)
         self.norm_lut = np.zeros((B, L), F32)
-        self.center = np.zeros(B, F32)
-        self.scale = np.ones(B, np.float64)
-        self.x_lut = np.zeros((B, L), F32)
+        self.qnorm = np.array([0, 1, 1], F32)
+        self._scaler = None
+        # phase 1 (what K2 needs): robust_normalize parameters of every band, and of the normalised texture band
         for b in range(B):
             raw = LevelOrder(hist[b], levels)
             lo, hi, den = norm_params(raw.percentile_scalar(lower), raw.percentile_scalar(upper))
             self.norm[b] = (lo, hi, den)
-            f = normalize_levels(levels, lo, hi, den)
-            self.norm_lut[b] = f
-            nb = LevelOrder(hist[b], f)
-            self.center[b] = nb.median()
-            q = nb.nanpercentile_pair((25.0, 75.0))
-            s = np.float64(q[1] - q[0])
-            if s < 10 * np.finfo(np.float64).eps:  # sklearn _handle_zeros_in_scale
-                s = 1.0
-            self.scale[b] = s
-            # X -= center_ (float32); X /= scale_ (float64 divisor -> evaluated in float64, stored float32)
-            self.x_lut[b] = ((f - self.center[b]).astype(np.float64) / s).astype(F32)
+            self.norm_lut[b] = normalize_levels(levels, lo, hi, den)
             if b == glcm_band:
+                nb = LevelOrder(hist[b], self.norm_lut[b], cum=raw.cum)
                 lo2, hi2, den2 = norm_params(nb.percentile_scalar(lower), nb.percentile_scalar(upper))
                 self.qnorm = np.array([lo2, hi2, den2], F32)
-        if not hasattr(self, "qnorm"):
-            self.qnorm = np.array([0, 1, 1], F32)
+
+    def _ensure_scaler(self):
+        """phase 2 (what K3 needs): RobustScaler statistics of the normalised bands; computed on first use so that the
+        caller can launch K2 first and do this while the device is busy."""
+        if self._scaler is None:
+            B, L = self.B, self.L
+            center = np.zeros(B, F32)
+            scale = np.ones(B, np.float64)
+            x_lut = np.zeros((B, L), F32)
+            for b in range(B):
+                f = self.norm_lut[b]
+                nb = LevelOrder(self.hist[b], f)
+                center[b] = nb.median()
+                q = nb.nanpercentile_pair((25.0, 75.0))
+                s = np.float64(q[1] - q[0])
+                if s < 10 * np.finfo(np.float64).eps:  # sklearn _handle_zeros_in_scale
+                    s = 1.0
+                scale[b] = s
+                # X -= center_ (float32); X /= scale_ (float64 divisor -> evaluated in float64, stored float32)
+                x_lut[b] = ((f - center[b]).astype(np.float64) / s).astype(F32)
+            self._scaler = (center, scale, x_lut)
+        return self._scaler
+
+    @property
+    def center(self):
+        return self._ensure_scaler()[0]
+
+    @property
+    def scale(self):
+        return self._ensure_scaler()[1]
+
+    @property
+    def x_lut(self):
+        return self._ensure_scaler()[2]
 
     def quant_lut(self, band, levels):
         """(robust_normalize(norm) * (levels-1)).astype(uint8) per grey level (indices.py:265-268)."""

@@ -85,15 +85,18 @@ def extract_features(raster: torch.Tensor, cfg: FeatureConfig = FeatureConfig(),
     dev = raster.device
     st = stream_ptr()
 
-    # ---- K1 histograms (+ all-reduce), host order statistics
+    # ---- K1 histograms (+ all-reduce), host order statistics (phase 1: robust_normalize parameters)
     hist = torch.zeros((B, L), dtype=torch.int32, device=dev)
     if n_px:
         with timer("hist"):
             _lib.call(f"rsx_hist_{sfx}", ptr(raster), n_px, B, ptr(hist), st)
-    hist64 = hist.to(torch.int64) & 0xFFFFFFFF      # the kernel's counters are uint32
-    comm.all_reduce(hist64)
-    stats = hoststats.RasterStats(hist64.cpu().numpy(), glcm_band=cfg.band_map[3],
-                                  lower=cfg.percentiles[0], upper=cfg.percentiles[1])
+    if comm.world > 1:
+        hist64 = hist.to(torch.int64) & 0xFFFFFFFF      # the kernel's counters are uint32
+        comm.all_reduce(hist64)
+        hist_host = hist64.cpu().numpy()
+    else:
+        hist_host = hist.cpu().numpy().view(np.uint32).astype(np.int64)
+    stats = hoststats.RasterStats(hist_host, glcm_band=cfg.band_map[3], lower=cfg.percentiles[0], upper=cfg.percentiles[1])
 
     n_comp = B if cfg.n_components is None else int(cfg.n_components)
     names = list(INDEX_NAMES) + (["glcm_" + g for g in GLCM_NAMES] if cfg.glcm else []) + [f"pc{i}" for i in range(n_comp)]
@@ -112,7 +115,8 @@ def extract_features(raster: torch.Tensor, cfg: FeatureConfig = FeatureConfig(),
             _lib.call(f"rsx_indices_fused_{sfx}", ptr(raster), n_px, B, hptr(band_map), hptr(norm), hptr(evi), ptr(planes), stride,
                       mm.slot(0), ptr(quant), hptr(qnorm), cfg.glcm_levels, st)
 
-    # ---- K3 PCA: moments (+ all-reduce) -> eigh on the host -> projection
+    # ---- K3a PCA moments (+ all-reduce).  The RobustScaler statistics (host, phase 2) are computed while K2 runs; the
+    #      moments come back through pinned memory so that the host can do the eigen-decomposition under the GLCM kernel.
     M = B + B * (B + 1) // 2
     moments = torch.zeros(M, dtype=torch.float64, device=dev)
     scratch = torch.empty(int(_lib.load().rsx_pca_scratch_elems(B)), dtype=torch.float64, device=dev)
@@ -128,20 +132,10 @@ def extract_features(raster: torch.Tensor, cfg: FeatureConfig = FeatureConfig(),
             else:
                 _lib.call("rsx_pca_moments_u8", ptr(raster), n_px, B, ptr(lut), ptr(moments), ptr(scratch), st)
     comm.all_reduce(moments)
-    pca = hoststats.pca_from_moments(moments.cpu().numpy(), n_global, n_comp)
-    comps = np.ascontiguousarray(pca["components"], dtype=np.float32)
-    mean32 = pca["mean"].astype(np.float32)
-    # sklearn: X_transformed -= mean_ @ components_.T, both float32 for float32 data
-    mean_proj = np.ascontiguousarray((mean32.reshape(1, -1) @ comps.T).ravel(), dtype=np.float32)
-    pc0 = len(names) - n_comp
-    if n_px:
-        with timer("pca_project"):
-            if is16:
-                _lib.call("rsx_pca_project_u16", ptr(raster), n_px, B, hptr(norm), hptr(center), hptr(scale), hptr(comps), hptr(mean_proj),
-                          n_comp, C.c_void_p(planes[pc0].data_ptr()), stride, mm.slot(pc0), st)
-            else:
-                _lib.call("rsx_pca_project_u8", ptr(raster), n_px, B, ptr(lut), hptr(comps), hptr(mean_proj), n_comp,
-                          C.c_void_p(planes[pc0].data_ptr()), stride, mm.slot(pc0), st)
+    moments_host = torch.empty(M, dtype=torch.float64, pin_memory=True)
+    moments_host.copy_(moments, non_blocking=True)
+    moments_ready = torch.cuda.Event()
+    moments_ready.record()
 
     # ---- K4 GLCM texture on the quantised NIR band (+ halo rows from the strips below/above), upsample
     if cfg.glcm:
@@ -162,6 +156,23 @@ def extract_features(raster: torch.Tensor, cfg: FeatureConfig = FeatureConfig(),
             with timer("glcm_resize"):
                 _lib.call("rsx_resize_bilinear_f32", ptr(props), out_rows_total, out_cols, p0, p1 - p0, props.shape[1],
                           C.c_void_p(planes[7].data_ptr()), H_total, W, own[0], h, stride, 5, mm.slot(7), st)
+
+    # ---- K3b eigh on the host (the device is busy with K4), projection
+    moments_ready.synchronize()
+    pca = hoststats.pca_from_moments(moments_host.numpy(), n_global, n_comp)
+    comps = np.ascontiguousarray(pca["components"], dtype=np.float32)
+    mean32 = pca["mean"].astype(np.float32)
+    # sklearn: X_transformed -= mean_ @ components_.T, both float32 for float32 data
+    mean_proj = np.ascontiguousarray((mean32.reshape(1, -1) @ comps.T).ravel(), dtype=np.float32)
+    pc0 = len(names) - n_comp
+    if n_px:
+        with timer("pca_project"):
+            if is16:
+                _lib.call("rsx_pca_project_u16", ptr(raster), n_px, B, hptr(norm), hptr(center), hptr(scale), hptr(comps), hptr(mean_proj),
+                          n_comp, C.c_void_p(planes[pc0].data_ptr()), stride, mm.slot(pc0), st)
+            else:
+                _lib.call("rsx_pca_project_u8", ptr(raster), n_px, B, ptr(lut), hptr(comps), hptr(mean_proj), n_comp,
+                          C.c_void_p(planes[pc0].data_ptr()), stride, mm.slot(pc0), st)
     return FeatureResult(planes=planes, names=names, n_px=n_px, H=h, W=W, stats=stats, pca=pca, minmax=mm, quant=quant)
 
 
@@ -197,6 +208,17 @@ class KMeansResult:
     shift_sq: float
 
 
+def gather_rows_device(planes: torch.Tensor, D: int, n_px: int, global_idx: np.ndarray, first_px: int, comm: Comm) -> torch.Tensor:
+    """Raw float32 feature rows of the given GLOBAL pixel indices as a (len, D) float64 device tensor (all-reduced so
+    every rank has all of them); asynchronous."""
+    loc = torch.as_tensor(global_idx - first_px, device=planes.device)
+    mine = (loc >= 0) & (loc < n_px)
+    sel = torch.where(mine, loc, torch.zeros_like(loc))
+    rows = planes[:D].index_select(1, sel).t().to(torch.float64) * mine.to(torch.float64).unsqueeze(1)
+    comm.all_reduce(rows)
+    return rows
+
+
 class DeviceKMeans:
     """Lloyd iterations on a planar float32 stack that stays in HBM."""
 
@@ -230,14 +252,7 @@ class DeviceKMeans:
 
     def gather_rows(self, global_idx: np.ndarray, first_px: int) -> np.ndarray:
         """Raw float32 feature rows of the given GLOBAL pixel indices (all-reduced so every rank has all of them)."""
-        rows = torch.zeros((len(global_idx), self.D), dtype=torch.float64, device=self.planes.device)
-        loc = torch.as_tensor(global_idx - first_px, device=self.planes.device)
-        mine = (loc >= 0) & (loc < self.n_px)
-        if bool(mine.any()):
-            sel = loc[mine]
-            rows[mine] = self.planes[:self.D, :][:, sel].t().to(torch.float64)
-        self.comm.all_reduce(rows)
-        return rows.cpu().numpy()
+        return gather_rows_device(self.planes, self.D, self.n_px, global_idx, first_px, self.comm).cpu().numpy()
 
     def setup(self, init_centroids_scaled: np.ndarray, mean_scaled: Optional[np.ndarray] = None):
         c0 = np.ascontiguousarray(init_centroids_scaled, dtype=np.float64)
@@ -269,7 +284,7 @@ class DeviceKMeans:
                 planes[1].fill_(255)
             cur, prev = planes[self._passes % 2], planes[(self._passes + 1) % 2]
         if self.n_px:
-            with self.timer("kmeans_assign"):
+            with self.timer("kmeans_assign_delta" if mode == 2 else "kmeans_assign_full"):
                 _lib.call("rsx_kmeans_assign", ptr(self.planes), self.stride, self.n_px, self.row_len, ptr(self.state), ptr(self.acc),
                           ptr(cur), ptr(prev), None, None, mode, self.D, self.K, stream_ptr())
         self.comm.all_reduce(self.acc[:self.n_acc])
@@ -350,15 +365,17 @@ def kmeans_on_features(fr: FeatureResult, D: int, K: int, n_iter: int, seed: int
     comm = comm or Comm()
     H_total = H_total if H_total is not None else fr.H
     n_global = H_total * fr.W
-    mn, mx = fr.minmax.read()
-    tmn = torch.from_numpy(mn[:D].copy()).to(fr.planes.device)
-    tmx = torch.from_numpy(mx[:D].copy()).to(fr.planes.device)
-    comm.all_reduce(tmn, "min")
-    comm.all_reduce(tmx, "max")
-    km = DeviceKMeans(fr.planes, fr.n_px, D, K, tmn.cpu().numpy(), tmx.cpu().numpy(), n_global, fr.W, comm, timer, delta)
     idx = draw_init_indices(n_global, K, seed)
-    raw = km.gather_rows(idx, first_row * fr.W)
-    c0 = km.scale_rows(raw)
+    rows_dev = gather_rows_device(fr.planes, D, fr.n_px, idx, first_row * fr.W, comm)   # asynchronous
+    mn, mx = fr.minmax.read()                       # the one synchronisation between the feature kernels and KMeans
+    if comm.world > 1:
+        tmn = torch.from_numpy(mn[:D].copy()).to(fr.planes.device)
+        tmx = torch.from_numpy(mx[:D].copy()).to(fr.planes.device)
+        comm.all_reduce(tmn, "min")
+        comm.all_reduce(tmx, "max")
+        mn, mx = tmn.cpu().numpy(), tmx.cpu().numpy()
+    km = DeviceKMeans(fr.planes, fr.n_px, D, K, mn[:D], mx[:D], n_global, fr.W, comm, timer, delta)
+    c0 = km.scale_rows(rows_dev.cpu().numpy())
     res = km.fit(c0, n_iter, labels_i32)
     return res, km, c0
 
@@ -366,7 +383,8 @@ def kmeans_on_features(fr: FeatureResult, D: int, K: int, n_iter: int, seed: int
 # ============================================================================================ public entry: host raster -> labels
 def segment_raster(raster_host: np.ndarray, cfg: FeatureConfig = FeatureConfig(), n_clusters: int = 8, n_iter: int = 20, seed: int = 42,
                    stack_depth: Optional[int] = None, comm: Optional[Comm] = None, H_total: Optional[int] = None,
-                   bounds: Optional[Sequence[Tuple[int, int]]] = None, timer: StageTimer = NO_TIMER, pinned: Optional[torch.Tensor] = None):
+                   bounds: Optional[Sequence[Tuple[int, int]]] = None, timer: StageTimer = NO_TIMER, pinned: Optional[torch.Tensor] = None,
+                   out_pinned: Optional[torch.Tensor] = None):
     """End-to-end call with HOST buffers: (h, W, B) uint8/uint16 numpy strip in, (h, W) int32 numpy labels out.
 
     Copies the strip to the device (pinned staging), runs extract_features + the fixed-iteration KMeans protocol,
@@ -383,5 +401,22 @@ def segment_raster(raster_host: np.ndarray, cfg: FeatureConfig = FeatureConfig()
     D = stack_depth if stack_depth is not None else (13 if cfg.glcm else 7 + min(6, len(fr.names) - 7))
     first_row = bounds[comm.rank][0] if bounds is not None else 0
     res, km, c0 = kmeans_on_features(fr, D, n_clusters, n_iter, seed, comm, H_total, first_row, True, timer)
-    labels = res.labels.view(fr.H, fr.W).cpu().numpy()
+    # labels come back through page-locked memory (a pageable destination costs several times the copy itself)
+    if out_pinned is None or out_pinned.numel() != fr.n_px:
+        out_pinned = _pinned_labels(fr.n_px)
+    out_pinned.copy_(res.labels, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    labels = out_pinned.numpy().reshape(fr.H, fr.W)
     return labels, res, fr
+
+
+_PINNED_LABELS = {}
+
+
+def _pinned_labels(n: int) -> torch.Tensor:
+    """Reusable page-locked int32 staging buffer for the label image (valid until the next call of the same size)."""
+    buf = _PINNED_LABELS.get(n)
+    if buf is None:
+        _PINNED_LABELS.clear()
+        buf = _PINNED_LABELS[n] = torch.empty(n, dtype=torch.int32, pin_memory=True)
+    return buf

@@ -22,7 +22,7 @@ for delta in (False, True):
             ch.append(km.changed_count() / fr.n_px)
         lab = km.finish(True)
         torch.cuda.synchronize()
-    ev = timer.events["kmeans_assign"]
+    ev = timer.events.get("kmeans_assign_full", []) + timer.events.get("kmeans_assign_delta", [])
     ms = [a.elapsed_time(b) for a, b in ev]
     print(f"delta={delta} total assign {sum(ms):.2f} ms; final {timer.totals_ms()['kmeans_final'][0]:.3f} ms")
     print("  ms/pass:", " ".join(f"{m:.3f}" for m in ms))
