@@ -41,43 +41,71 @@ def peaks():
 
 
 class ClockSampler:
-    def __init__(self, gpu_index: int):
-        self.rows, self.proc, self.idx = [], None, gpu_index
+    """SM clock + throttle reasons sampled DURING the timed region.  NVML in a thread (a polling `nvidia-smi -lms` child
+    takes driver locks and was measured to stretch the timed region by milliseconds); nvidia-smi once as a fallback."""
+
+    def __init__(self, gpu_index: int, period_s: float = 0.02):
+        self.idx, self.period = gpu_index, period_s
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.thread, self.stop_flag, self.nvml = None, threading.Event(), None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.idx),
-                 "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
-                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may remap indices: resolve through the PCI bus id of the torch device
+            import torch
+            bus = torch.cuda.get_device_properties(self.idx).pci_bus_id if hasattr(torch.cuda.get_device_properties(self.idx), "pci_bus_id") else None
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+            if bus is not None:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    h = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if pynvml.nvmlDeviceGetPciInfo(h).bus == bus:
+                        self.handle = h
+                        break
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
         except Exception:
-            self.proc = None
+            self.nvml = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+    def _sample(self):
+        n = self.nvml
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        self.mx.append(float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        for name, bit in (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40),
+                          ("hw_power_brake_slowdown", 0x80)):
+            if r & bit:
+                self.reasons.add(name)
 
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
+    def _loop(self):
+        while not self.stop_flag.is_set():
             try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
-                for n, v in zip(names, f[2:6]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
+                self._sample()
             except Exception:
                 pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+            self.stop_flag.wait(self.period)
+
+    def stop(self):
+        if self.nvml is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=1.0)
+            if not self.sm:
+                try:
+                    self._sample()
+                except Exception:
+                    pass
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "how": "NVML, sampled during the timed region"}
+        try:
+            out = subprocess.run(["nvidia-smi", "-i", str(self.idx), "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits"],
+                                 capture_output=True, text=True, timeout=10).stdout.strip().split(",")
+            return {"sm_mhz": float(out[0]), "sm_max_mhz": float(out[1]), "reasons": ["unknown (NVML unavailable)"], "samples": 1,
+                    "how": "nvidia-smi once after the timed region"}
+        except Exception:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
 
 
 # ------------------------------------------------------------------------------------------- reference (CPU) arm
@@ -147,7 +175,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": "Mpixel/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    _emit(line)
     return 0
 
 
@@ -184,7 +212,7 @@ def run_rsx(args):
 
     raster = synth_strip_torch(H_total, W, 7, own[0], own[1] - own[0], "uint8", seed=7000, device="cuda")
     torch.cuda.synchronize()
-    timer = StageTimer(enabled=True)
+    timer = StageTimer(enabled=os.environ.get("RSX_BENCH_NOTIMER", "0") != "1")
 
     def step(t):
         fr = P.extract_features(raster, cfg, comm, H_total, bounds, t)
@@ -209,7 +237,7 @@ def run_rsx(args):
     for _ in range(args.warmup):
         step(StageTimer(enabled=False))
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and os.environ.get("RSX_BENCH_NOCLOCKS", "0") != "1":
         sampler.start()
     launches0 = _lib.launch_count()
     timer.reset()
@@ -282,10 +310,19 @@ def run_rsx(args):
             "value": 1e-6 / per_px, "unit": "Mpixel/s", "cores": os.cpu_count(), "kind": "port",
             "sample": f"indices+PCA+KMeans on a {S}x{S} crop, dense GLCM (C/OpenMP restatement) on a {G}x{G} crop, per-pixel times summed",
             "stage_us_per_pixel": {k: v * 1e6 for k, v in t.items()}}
-    print(json.dumps(line))
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def _emit(line: dict):
+    """The one JSON line on the real stdout (everything else - NCCL banners, warnings - was redirected to stderr)."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
 
 
 def main():

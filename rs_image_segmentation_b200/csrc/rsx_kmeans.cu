@@ -50,9 +50,9 @@ __device__ void km_derive(KmState* st) {
         for (int j = 0; j < K; ++j) e_max = fmax(e_max, e_arr[j]);
         const double e_max_mag = e_max / (D + 3);  // largest |distance| the fp32 path can produce
         // two distances, 1.5x safety; plus the index tag written over the low mantissa bits of each distance
-        st->tau = (float)(2.0 * 1.5 * e_max * 5.9604644775390625e-08 + 2.0 * e_max_mag * (K <= 8 ? 8.0 : K <= 16 ? 16.0 : K <= 32 ? 32.0 : 64.0) * 1.1920928955078125e-07);
-        // never-chosen padding centroids: the kernel evaluates 8, 16 or 32 centroid slots (K <= 32) or an even number of them
-        for (int j = K; j < KM_MAXK && j < (K <= 8 ? 8 : K <= 16 ? 16 : K <= 32 ? 32 : ((K + 1) & ~1)); ++j) {
+        st->tau = (float)(2.0 * 1.5 * e_max * 5.9604644775390625e-08 + 2.0 * e_max_mag * (K <= 8 ? 8.0 : 64.0) * 1.1920928955078125e-07);
+        // never-chosen padding centroids: the kernels evaluate centroids in groups of 8
+        for (int j = K; j < KM_MAXK && j < ((K + 7) & ~7); ++j) {
             st->bias32[j] = 1e30f;  // finite: the index tag must not turn it into a NaN
             for (int d = 0; d < D; ++d) st->w32[j * KM_MAXD + d] = 0.f;
         }

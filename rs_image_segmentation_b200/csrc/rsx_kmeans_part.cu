@@ -60,16 +60,16 @@ __device__ __forceinline__ float km_tag(float a, int j) { return __uint_as_float
         B_ = fminf(B_, t_);                       \
     }
 
-__host__ __device__ constexpr int km_idx_bits(int KU) { return KU == 8 ? 3 : KU == 16 ? 4 : KU == 32 ? 5 : 6; }
+__host__ __device__ constexpr int km_idx_bits(int KU) { return KU == 8 ? 3 : 6; }
 
 constexpr int KM_THREADS = 128;
 constexpr int KM_SLOTS = 8;
 
 // best / second-best tagged distances of the thread's 4 pixels (v[d] = feature d of pixels p..p+3).
-// KU = 8, 16, 32: that many centroid slots, fully unrolled, weights as constant-bank (uniform register) operands of FFMA2
-// (K <= KU; padding slots carry bias 1e30).  KU = 0: rolled loop over K (K > 32).
+// KU = 8: eight centroid slots, fully unrolled, weights as constant-bank (uniform register) operands of FFMA2 (K <= 8;
+// padding slots carry bias 1e30).  KU = 0: any K, chunks of 8 centroids with the weights in shared memory.
 template <int D, int KU>
-__device__ __forceinline__ void km_distances(const float4* v, int K, float (&b)[4], float (&s)[4]) {
+__device__ __forceinline__ void km_distances(const float4* v, int K, const float* __restrict__ wsm, float (&b)[4], float (&s)[4]) {
     constexpr int BITS = km_idx_bits(KU);
     b[0] = b[1] = b[2] = b[3] = INFINITY;
     s[0] = s[1] = s[2] = s[3] = INFINITY;
@@ -88,24 +88,35 @@ __device__ __forceinline__ void km_distances(const float4* v, int K, float (&b)[
             KM_ARGMIN_TAGGED(a23.x, b[2], s[2], j) KM_ARGMIN_TAGGED(a23.y, b[3], s[3], j)
         }
     } else {
-        const int Kp = (K + 1) & ~1;  // centroids in pairs; slot K (if K is odd) holds bias 1e30
+        // K > 8: chunks of 8 centroids, weights from shared memory (wsm = [D][KP] then bias [KP], KP = K rounded up to 8;
+        // padding slots carry bias 1e30); broadcast LDS.128, small code whatever K is
+        const int KP = (K + 7) & ~7;
+        const float* bias = wsm + D * KP;
 #pragma unroll 1
-        for (int j = 0; j < Kp; j += 2) {
-            const float cA = g_km.bias32[j], cB = g_km.bias32[j + 1];
-            float2 a01 = make_float2(cA, cA), a23 = a01, e01 = make_float2(cB, cB), e23 = e01;
+        for (int jc = 0; jc < KP; jc += 8) {
+            float2 a[8][2];
+            {
+                const float4 bA = *reinterpret_cast<const float4*>(bias + jc), bB = *reinterpret_cast<const float4*>(bias + jc + 4);
+                const float bb[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) a[jj][0] = a[jj][1] = make_float2(bb[jj], bb[jj]);
+            }
 #pragma unroll
             for (int d = 0; d < D; ++d) {
-                const float wa = g_km.w32[j * KM_MAXD + d], wb = g_km.w32[(j + 1) * KM_MAXD + d];
+                const float4 wA = *reinterpret_cast<const float4*>(wsm + d * KP + jc), wB = *reinterpret_cast<const float4*>(wsm + d * KP + jc + 4);
+                const float ww[8] = {wA.x, wA.y, wA.z, wA.w, wB.x, wB.y, wB.z, wB.w};
                 const float2 x01 = make_float2(v[d].x, v[d].y), x23 = make_float2(v[d].z, v[d].w);
-                a01 = __ffma2_rn(x01, make_float2(wa, wa), a01);
-                a23 = __ffma2_rn(x23, make_float2(wa, wa), a23);
-                e01 = __ffma2_rn(x01, make_float2(wb, wb), e01);
-                e23 = __ffma2_rn(x23, make_float2(wb, wb), e23);
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                    a[jj][0] = __ffma2_rn(x01, make_float2(ww[jj], ww[jj]), a[jj][0]);
+                    a[jj][1] = __ffma2_rn(x23, make_float2(ww[jj], ww[jj]), a[jj][1]);
+                }
             }
-            KM_ARGMIN_TAGGED(a01.x, b[0], s[0], j) KM_ARGMIN_TAGGED(a01.y, b[1], s[1], j)
-            KM_ARGMIN_TAGGED(a23.x, b[2], s[2], j) KM_ARGMIN_TAGGED(a23.y, b[3], s[3], j)
-            KM_ARGMIN_TAGGED(e01.x, b[0], s[0], j + 1) KM_ARGMIN_TAGGED(e01.y, b[1], s[1], j + 1)
-            KM_ARGMIN_TAGGED(e23.x, b[2], s[2], j + 1) KM_ARGMIN_TAGGED(e23.y, b[3], s[3], j + 1)
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+                KM_ARGMIN_TAGGED(a[jj][0].x, b[0], s[0], jc + jj) KM_ARGMIN_TAGGED(a[jj][0].y, b[1], s[1], jc + jj)
+                KM_ARGMIN_TAGGED(a[jj][1].x, b[2], s[2], jc + jj) KM_ARGMIN_TAGGED(a[jj][1].y, b[3], s[3], jc + jj)
+            }
         }
     }
 }
@@ -265,7 +276,7 @@ __global__ void __launch_bounds__(KM_THREADS, 2) km_full_kernel(const float* __r
             for (int d = 0; d < D; ++d) asm volatile("prefetch.global.L2 [%0];" ::"l"(stack + d * plane_stride + p + pf_rows * (int64_t)row_len));
         }
         float b[4], s[4];
-        km_distances<D, 8>(v, K, b, s);
+        km_distances<D, 8>(v, K, nullptr, b, s);
         int l[4];
         float x[D];
 #pragma unroll
@@ -343,20 +354,23 @@ __global__ void __launch_bounds__(KM_THREADS, 2) km_full_kernel(const float* __r
 
 // ============================================================================= kernel B: TMA-staged streaming pass
 // The flat pixel array is cut into blocks of 512 pixels; CTA b handles blocks b, b + grid, ...  One elected thread stages
-// each block's D plane segments (2 KB each) into shared memory with bulk asynchronous copies (TMA engine, no tensor map)
-// that complete on an mbarrier; n_stages blocks are in flight per CTA, so HBM latency is decoupled from registers and the
-// kernel runs at up to four CTAs per SM.  Every thread then takes its 4 pixels (one LDS.128 per plane).
+// each block's D plane segments (2 KB each) into a ring in shared memory with bulk asynchronous copies (TMA engine, no
+// tensor map) that complete on the stage's "full" mbarrier; n_stages blocks are in flight per CTA, so HBM latency is
+// decoupled from registers and the kernel runs at up to four CTAs per SM.  Every thread takes its 4 pixels of a block
+// (one LDS.128 per plane).  The warps of a CTA are NOT kept in lockstep: a warp that is done with a stage arrives on the
+// stage's "empty" mbarrier, and the producer refills a stage one block late, when all four warps have left it.
 //   KM_ASSIGN  labels (+ inertia)
 //   KM_DELTA   labels + the pixels whose label differs from the previous pass move their fixed-point sample between the
 //              clusters' sums: the warp handles its changed pixels together - lane d reads feature d of the pixel from the
 //              staged block, converts it and updates the WARP's private [K][D+1] int64 accumulator in shared memory (plain
-//              read-modify-write: lanes own distinct cells, control flow is CTA-uniform); lane D moves the count.
+//              read-modify-write: lanes own distinct cells, control flow is warp-uniform); lane D moves the count.
 //   KM_FULL    as KM_DELTA with every pixel "moving in" from nowhere (used for K > 8, where per-thread accumulators do
 //              not fit in shared memory)
+constexpr int KM_WARPS = KM_THREADS / 32;
 constexpr int KM_BLOCK_PX = KM_THREADS * 4;
 
 template <int D>
-__device__ __forceinline__ void km_move_samples(const float* __restrict__ st, unsigned cm, int local_px, uint32_t old_packed, uint32_t new_packed,
+__device__ __forceinline__ void km_move_samples(const float* __restrict__ st, int warp_px, unsigned cm, uint32_t old_packed, uint32_t new_packed,
                                                 long long* __restrict__ wacc, float my_pow2) {
     unsigned b = __ballot_sync(0xffffffffu, cm != 0);
     const int lane = threadIdx.x & 31;
@@ -364,7 +378,6 @@ __device__ __forceinline__ void km_move_samples(const float* __restrict__ st, un
         const int src = __ffs(b) - 1;
         b &= b - 1;
         const unsigned m = __shfl_sync(0xffffffffu, cm, src);
-        const int px = __shfl_sync(0xffffffffu, local_px, src);
         const uint32_t ov = __shfl_sync(0xffffffffu, old_packed, src), nv = __shfl_sync(0xffffffffu, new_packed, src);
         if (lane <= D) {
 #pragma unroll
@@ -372,7 +385,7 @@ __device__ __forceinline__ void km_move_samples(const float* __restrict__ st, un
                 if (m & (1u << i)) {
                     const int from = (int)((ov >> (8 * i)) & 0xffu), to = (int)((nv >> (8 * i)) & 0xffu);
                     long long q = 1;
-                    if (lane < D) q = __float2ll_rn(st[lane * KM_BLOCK_PX + px + i] * my_pow2);
+                    if (lane < D) q = __float2ll_rn(st[lane * KM_BLOCK_PX + warp_px + 4 * src + i] * my_pow2);
                     wacc[to * (D + 1) + lane] += q;
                     if (from < KM_MAXK) wacc[from * (D + 1) + lane] -= q;
                 }
@@ -387,20 +400,33 @@ __global__ void __launch_bounds__(KM_THREADS, 4) km_stream_kernel(const float* _
                                                                   const uint8_t* __restrict__ prev8, int32_t* __restrict__ lab32,
                                                                   double* __restrict__ inertia_out, int n_stages) {
     constexpr bool SUMS = MODE != KM_ASSIGN;
+    // large unrolled bodies (K > 8) run faster with the CTA's warps in lockstep (they share the instruction stream); the
+    // small ones with decoupled warps
+    constexpr bool LOCKSTEP = KU != 8;
     extern __shared__ __align__(128) unsigned char km_smem[];
     const int K = g_km.K;
-    float* stages = reinterpret_cast<float*>(km_smem);                                                     // [n_stages][D][512]
-    long long* wacc_all = reinterpret_cast<long long*>(km_smem + (size_t)n_stages * D * KM_BLOCK_PX * 4);  // [4 warps][K][D+1]
-    uint64_t* full = reinterpret_cast<uint64_t*>(wacc_all + (SUMS ? (KM_THREADS / 32) * K * (D + 1) : 0)); // [n_stages]
-    long long* wacc = wacc_all + (threadIdx.x >> 5) * K * (D + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float* stages = reinterpret_cast<float*>(km_smem);                                                          // [n_stages][D][512]
+    long long* wacc_all = reinterpret_cast<long long*>(km_smem + (size_t)n_stages * D * KM_BLOCK_PX * 4);       // [4 warps][K][D+1]
+    uint64_t* full = reinterpret_cast<uint64_t*>(wacc_all + (SUMS ? KM_WARPS * K * (D + 1) : 0));               // [n_stages]
+    uint64_t* empty = full + n_stages;                                                                          // [n_stages]
+    float* wsm = reinterpret_cast<float*>(empty + n_stages);                                                    // KU == 0: [D][KP] weights, [KP] biases
+    long long* wacc = wacc_all + warp * K * (D + 1);
+    if (KU == 0) {
+        const int KP = (K + 7) & ~7;
+        for (int i = tid; i < D * KP; i += KM_THREADS) {
+            const int d = i / KP, j = i - d * KP;
+            wsm[i] = g_km.w32[j * KM_MAXD + d];
+        }
+        for (int j = tid; j < KP; j += KM_THREADS) wsm[D * KP + j] = g_km.bias32[j];
+    }
     const int64_t n4 = n_px & ~(int64_t)3;
     const int64_t n_blocks = (n4 + KM_BLOCK_PX - 1) / KM_BLOCK_PX;
-    const int tid = threadIdx.x;
 
     if (SUMS)
-        for (int i = tid; i < (KM_THREADS / 32) * K * (D + 1); i += KM_THREADS) wacc_all[i] = 0;
+        for (int i = tid; i < KM_WARPS * K * (D + 1); i += KM_THREADS) wacc_all[i] = 0;
     if (tid == 0) {
-        for (int s = 0; s < n_stages; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < n_stages; ++s) mbar_init(&full[s], 1), mbar_init(&empty[s], KM_WARPS);
         mbar_fence_init();
     }
     __syncthreads();
@@ -417,14 +443,14 @@ __global__ void __launch_bounds__(KM_THREADS, 4) km_stream_kernel(const float* _
             const int64_t blk = blockIdx.x + (int64_t)s * gridDim.x;
             if (blk < n_blocks) issue(blk, s);
         }
-    const float my_pow2 = SUMS ? g_km.pow2[min((int)(tid & 31), D - 1)] : 0.f;
+    const float my_pow2 = SUMS ? g_km.pow2[min(lane, D - 1)] : 0.f;
     double inertia = 0.0;
     unsigned ties = 0, changed = 0;
     uint32_t pv_next = 0xffffffffu;
     if (prev8 && (int64_t)blockIdx.x * KM_BLOCK_PX + 4 * tid < n4) pv_next = __ldg(reinterpret_cast<const uint32_t*>(prev8 + (int64_t)blockIdx.x * KM_BLOCK_PX + 4 * tid));
 
-    int s = 0;
-    unsigned parity = 0;
+    int s = 0, s_prev = -1;
+    unsigned parity = 0, parity_prev = 0;
     for (int64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
         const int64_t p = blk * KM_BLOCK_PX + 4 * tid;
         const bool valid = p < n4;
@@ -434,6 +460,13 @@ __global__ void __launch_bounds__(KM_THREADS, 4) km_stream_kernel(const float* _
             pv_next = 0xffffffffu;
             if (prev8 && pn < n4) pv_next = __ldg(reinterpret_cast<const uint32_t*>(prev8 + pn));
         }
+        if (!LOCKSTEP && tid == 0 && s_prev >= 0) {  // refill the stage of the previous block once all four warps have left it
+            const int64_t nb = blk + (int64_t)(n_stages - 1) * gridDim.x;
+            if (nb < n_blocks) {
+                mbar_wait(&empty[s_prev], parity_prev);
+                issue(nb, s_prev);
+            }
+        }
         mbar_wait(&full[s], parity);
         const float* st = stages + (size_t)s * D * KM_BLOCK_PX;
         uint32_t packed = 0, diff = 0;
@@ -442,7 +475,7 @@ __global__ void __launch_bounds__(KM_THREADS, 4) km_stream_kernel(const float* _
 #pragma unroll
             for (int d = 0; d < D; ++d) v[d] = *reinterpret_cast<const float4*>(st + d * KM_BLOCK_PX + 4 * tid);
             float b[4], sc[4];
-            km_distances<D, KU>(v, K, b, sc);
+            km_distances<D, KU>(v, K, wsm, b, sc);
             int l[4];
             float x[D];
 #pragma unroll
@@ -465,12 +498,18 @@ __global__ void __launch_bounds__(KM_THREADS, 4) km_stream_kernel(const float* _
         unsigned cm = km_changed_mask(diff);
         changed += __popc(cm);  // sklearn's strict-convergence test (_kmeans.py:723)
         if (MODE == KM_FULL) cm = valid ? 0xfu : 0u;
-        if (SUMS) km_move_samples<D>(st, cm, 4 * tid, MODE == KM_FULL ? 0xffffffffu : pv, packed, wacc, my_pow2);
-        __syncthreads();  // everyone is done with stage s: refill it
-        if (tid == 0) {
-            const int64_t nb = blk + (int64_t)n_stages * gridDim.x;
-            if (nb < n_blocks) issue(nb, s);
+        if (SUMS) km_move_samples<D>(st, warp * 128, cm, MODE == KM_FULL ? 0xffffffffu : pv, packed, wacc, my_pow2);
+        if (LOCKSTEP) {
+            __syncthreads();  // everyone is done with stage s: refill it
+            if (tid == 0) {
+                const int64_t nb = blk + (int64_t)n_stages * gridDim.x;
+                if (nb < n_blocks) issue(nb, s);
+            }
+        } else {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);  // this warp has left stage s
         }
+        s_prev = s, parity_prev = parity;
         if (++s == n_stages) s = 0, parity ^= 1u;
     }
     // ragged tail (n_px % 4 pixels): one thread, scalar
@@ -498,7 +537,7 @@ __global__ void __launch_bounds__(KM_THREADS, 4) km_stream_kernel(const float* _
         for (int i = tid; i < K * (D + 1); i += KM_THREADS) {
             long long t = 0;
 #pragma unroll
-            for (int w = 0; w < KM_THREADS / 32; ++w) t += wacc_all[w * K * (D + 1) + i];
+            for (int w = 0; w < KM_WARPS; ++w) t += wacc_all[w * K * (D + 1) + i];
             if (t) {
                 const int j = i / (D + 1), d = i % (D + 1);
                 long long* dst = d < D ? &gacc[j * D + d] : &gacc[K * D + j];
@@ -535,8 +574,9 @@ static int km_launch_full(const KmLaunch& a, cudaStream_t s) {
 template <int D, int MODE, bool INERTIA, int KU>
 static int km_launch_stream(const KmLaunch& a, cudaStream_t s) {
     auto kern = km_stream_kernel<D, MODE, INERTIA, KU>;
-    const int acc_bytes = MODE == KM_ASSIGN ? 0 : (KM_THREADS / 32) * a.K * (D + 1) * 8;
-    auto smem_for = [&](int stages) { return stages * D * KM_BLOCK_PX * 4 + acc_bytes + stages * 8; };
+    const int acc_bytes = MODE == KM_ASSIGN ? 0 : KM_WARPS * a.K * (D + 1) * 8;
+    const int w_bytes = KU == 0 ? (D + 1) * ((a.K + 7) & ~7) * 4 : 0;
+    auto smem_for = [&](int stages) { return stages * D * KM_BLOCK_PX * 4 + acc_bytes + 2 * stages * 8 + w_bytes; };
     // stages: enough blocks in flight per SM to cover HBM latency at full bandwidth (~64 KB/SM), within shared memory
     static int cfg_K = -1, cfg_stages = 0, cfg_per_sm = 0;
     if (cfg_K != a.K) {
@@ -579,8 +619,6 @@ static int km_launch2(const KmLaunch& a, cudaStream_t s) {
 template <int D>
 static int km_launch(const KmLaunch& a, cudaStream_t s) {
     if (a.K <= 8) return km_launch2<D, 8>(a, s);
-    if (a.K <= 16) return km_launch2<D, 16>(a, s);
-    if (a.K <= 32) return km_launch2<D, 32>(a, s);
     return km_launch2<D, 0>(a, s);
 }
 

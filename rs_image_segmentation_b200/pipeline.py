@@ -214,7 +214,7 @@ def gather_rows_device(planes: torch.Tensor, D: int, n_px: int, global_idx: np.n
     loc = torch.as_tensor(global_idx - first_px, device=planes.device)
     mine = (loc >= 0) & (loc < n_px)
     sel = torch.where(mine, loc, torch.zeros_like(loc))
-    rows = planes[:D].index_select(1, sel).t().to(torch.float64) * mine.to(torch.float64).unsqueeze(1)
+    rows = (planes[:D].index_select(1, sel).t().to(torch.float64) * mine.to(torch.float64).unsqueeze(1)).contiguous()
     comm.all_reduce(rows)
     return rows
 

@@ -91,8 +91,14 @@ def _worker(rank, world, port, H, W, w, s, ret):
         comm.all_reduce(mn, "min")
         comm.all_reduce(mx, "max")
         ok_mm = mn.item() == 0.0 and mx.item() == float(H)
+        # initial-centroid rows: every rank ends up with the rows of all requested global pixels
+        from rs_image_segmentation_b200.pipeline import gather_rows_device
+        planes_full = torch.arange(3 * H * W, dtype=torch.float32).reshape(3, H * W)
+        idx = np.array([0, W * bounds[0][1] - 1, H * W - 1, (H // 2) * W + 3], dtype=np.int64)   # the same on every rank
+        rows = gather_rows_device(planes_full[:, r0 * W:r1 * W].contiguous(), 3, (r1 - r0) * W, idx, r0 * W, comm)
+        ok_gather = bool(torch.equal(rows, planes_full[:, torch.from_numpy(idx)].t().to(torch.float64)))
         comm.barrier()
-        ret[rank] = (ok_rows, ok_sum, ok_mm)
+        ret[rank] = (ok_rows, ok_sum, ok_mm, ok_gather)
     finally:
         dist.destroy_process_group()
 
