@@ -50,6 +50,7 @@ __device__ void km_derive(KmState* st) {
         for (int j = 0; j < K; ++j) e_max = fmax(e_max, e_arr[j]);
         const double e_max_mag = e_max / (D + 3);  // largest |distance| the fp32 path can produce
         // two distances, 1.5x safety; plus the index tag written over the low mantissa bits of each distance
+        st->tau_tight = (float)(2.0 * 1.5 * e_max * 5.9604644775390625e-08);
         st->tau = (float)(2.0 * 1.5 * e_max * 5.9604644775390625e-08 + 2.0 * e_max_mag * (K <= 8 ? 8.0 : 64.0) * 1.1920928955078125e-07);
         // never-chosen padding centroids: the kernels evaluate centroids in groups of 8
         for (int j = K; j < KM_MAXK && j < ((K + 7) & ~7); ++j) {
@@ -63,13 +64,29 @@ __device__ void km_derive(KmState* st) {
     }
 }
 
-__global__ void km_setup_kernel(KmState* st) {
+// The set-up / update kernels are one CTA of dependent scalar work; run against a shared-memory mirror of the state their
+// per-centroid loops cost shared-memory latency instead of a chain of global-memory round trips.
+constexpr int KM_CTRL_THREADS = 256;
+__device__ __forceinline__ void km_state_copy(void* dst, const void* src) {
+    static_assert(sizeof(KmState) % 16 == 0, "KmState is copied in 16-byte pieces");
+    const int4* s4 = reinterpret_cast<const int4*>(src);
+    int4* d4 = reinterpret_cast<int4*>(dst);
+    for (int i = threadIdx.x; i < (int)(sizeof(KmState) / 16); i += blockDim.x) d4[i] = s4[i];
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(KM_CTRL_THREADS) km_setup_kernel(KmState* gst) {
+    __shared__ __align__(16) KmState sst;
+    KmState* st = &sst;
+    km_state_copy(st, gst);
     km_derive(st);
     if (threadIdx.x == 0) {
         st->shift_sq = 0.0;
         st->n_empty = 0;
         st->n_updates = 0;
     }
+    __syncthreads();
+    km_state_copy(gst, st);
 }
 
 static const km_assign_fn g_part_assign[KM_NUM_PARTS] = {rsx_km_part0_assign, rsx_km_part1_assign, rsx_km_part2_assign, rsx_km_part3_assign,
@@ -119,7 +136,7 @@ extern "C" int rsx_kmeans_setup(void* d_state, int D, int K, const double* h_fea
         rsx_set_error("rsx_kmeans_setup: %s", cudaGetErrorString(e));
         return RSX_ERR_CUDA;
     }
-    km_setup_kernel<<<1, 64, 0, s>>>((KmState*)d_state);
+    km_setup_kernel<<<1, KM_CTRL_THREADS, 0, s>>>((KmState*)d_state);
     if (int rc = rsx_check_launch("km_setup")) return rc;
     return km_publish(d_state, D, s);
 }
@@ -167,7 +184,10 @@ extern "C" int rsx_kmeans_assign(const float* d_stack, int64_t plane_stride, int
 // acc = pass block [sums K*D][counts K][near ties][changed] ++ totals block [sums K*D][counts K][near ties so far][changed in
 // the last pass].  A full pass produced the sums themselves (delta == 0: totals <- pass), a delta pass their change (totals +=
 // pass); the centroids come from the totals; the pass block is zeroed for the next pass.
-__global__ void km_update_kernel(KmState* st, long long* acc, int delta) {
+__global__ void __launch_bounds__(KM_CTRL_THREADS) km_update_kernel(KmState* gst, long long* acc, int delta) {
+    __shared__ __align__(16) KmState sst;
+    KmState* st = &sst;
+    km_state_copy(st, gst);
     const int D = st->D, K = st->K;
     long long* tot = acc + K * D + K + 2;
     for (int i = threadIdx.x; i < K * D + K; i += blockDim.x) {
@@ -215,12 +235,13 @@ __global__ void km_update_kernel(KmState* st, long long* acc, int delta) {
     km_derive(st);
     __syncthreads();
     for (int i = threadIdx.x; i < K * D + K + 2; i += blockDim.x) (tot - (K * D + K + 2))[i] = 0;
+    km_state_copy(gst, st);
 }
 
 extern "C" int rsx_kmeans_update(void* d_state, int64_t* d_acc, int delta, int D, rsx_stream_t stream) {
     RSX_REQUIRE(d_state && d_acc && D >= 1 && D <= KM_MAXD, "rsx_kmeans_update: bad arguments");
     cudaStream_t s = (cudaStream_t)stream;
-    km_update_kernel<<<1, 64, 0, s>>>((KmState*)d_state, reinterpret_cast<long long*>(d_acc), delta);
+    km_update_kernel<<<1, KM_CTRL_THREADS, 0, s>>>((KmState*)d_state, reinterpret_cast<long long*>(d_acc), delta);
     if (int rc = rsx_check_launch("km_update")) return rc;
     return km_publish(d_state, D, s);
 }

@@ -122,14 +122,35 @@ __device__ __forceinline__ void km_distances(const float4* v, int K, const float
 }
 
 // label of one pixel from its tagged best/second distances (+ float64 decision of near ties, + inertia)
+// K > 8: the 6-bit index tags widen the near-tie band five-fold.  Before paying for float64, redo the K distances of this one
+// pixel in fp32 WITHOUT tags (same FMA order, weights from shared memory) and apply the rounding-only bound tau_tight.
+template <int D>
+__device__ __noinline__ bool km_recheck_fp32(const float (&x)[D], int K, const float* __restrict__ wsm, int* bi_out) {
+    const int KP = (K + 7) & ~7;
+    float b = INFINITY, s = INFINITY;
+    int bi = 0;
+    for (int j = 0; j < K; ++j) {
+        float a = wsm[D * KP + j];
+#pragma unroll
+        for (int d = 0; d < D; ++d) a = fmaf(x[d], wsm[d * KP + j], a);
+        KM_ARGMIN_STEP(a, b, s, bi, j)
+    }
+    *bi_out = bi;
+    return s - b > g_km.tau_tight;  // false also for NaN
+}
+
 template <int D, int KU, bool INERTIA>
 __device__ __forceinline__ int km_decide(const float* __restrict__ stack, int64_t plane_stride, int64_t p, const float (&x)[D], float best, float second,
-                                         double& inertia, unsigned& ties) {
+                                         const float* __restrict__ wsm, double& inertia, unsigned& ties) {
     int bi = (int)(__float_as_uint(best) & ((1u << km_idx_bits(KU)) - 1u));
     double dist_exact = -1.0;
     if (!(second - best > g_km.tau)) {  // near tie (or NaN): decide in float64
-        bi = km_exact_argmin<D>(stack, plane_stride, p, &dist_exact);
-        ++ties;
+        bool decided = false;
+        if (KU == 0) decided = km_recheck_fp32<D>(x, g_km.K, wsm, &bi);
+        if (!decided) {
+            bi = km_exact_argmin<D>(stack, plane_stride, p, &dist_exact);
+            ++ties;
+        }
     }
     if (INERTIA) {
         if (dist_exact < 0.0) {
@@ -281,19 +302,19 @@ __global__ void __launch_bounds__(KM_THREADS, 2) km_full_kernel(const float* __r
         float x[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) x[d] = v[d].x;
-        l[0] = km_decide<D, 8, false>(stack, plane_stride, p, x, b[0], s[0], inertia, ties);
+        l[0] = km_decide<D, 8, false>(stack, plane_stride, p, x, b[0], s[0], nullptr, inertia, ties);
         accumulate(l[0], x);
 #pragma unroll
         for (int d = 0; d < D; ++d) x[d] = v[d].y;
-        l[1] = km_decide<D, 8, false>(stack, plane_stride, p + 1, x, b[1], s[1], inertia, ties);
+        l[1] = km_decide<D, 8, false>(stack, plane_stride, p + 1, x, b[1], s[1], nullptr, inertia, ties);
         accumulate(l[1], x);
 #pragma unroll
         for (int d = 0; d < D; ++d) x[d] = v[d].z;
-        l[2] = km_decide<D, 8, false>(stack, plane_stride, p + 2, x, b[2], s[2], inertia, ties);
+        l[2] = km_decide<D, 8, false>(stack, plane_stride, p + 2, x, b[2], s[2], nullptr, inertia, ties);
         accumulate(l[2], x);
 #pragma unroll
         for (int d = 0; d < D; ++d) x[d] = v[d].w;
-        l[3] = km_decide<D, 8, false>(stack, plane_stride, p + 3, x, b[3], s[3], inertia, ties);
+        l[3] = km_decide<D, 8, false>(stack, plane_stride, p + 3, x, b[3], s[3], nullptr, inertia, ties);
         accumulate(l[3], x);
         const uint32_t packed = (uint32_t)l[0] | ((uint32_t)l[1] << 8) | ((uint32_t)l[2] << 16) | ((uint32_t)l[3] << 24);
         if (prev8) changed += __popc(km_changed_mask(packed ^ pv));  // sklearn's strict-convergence test (_kmeans.py:723)
@@ -400,9 +421,7 @@ __global__ void __launch_bounds__(KM_THREADS, 4) km_stream_kernel(const float* _
                                                                   const uint8_t* __restrict__ prev8, int32_t* __restrict__ lab32,
                                                                   double* __restrict__ inertia_out, int n_stages) {
     constexpr bool SUMS = MODE != KM_ASSIGN;
-    // large unrolled bodies (K > 8) run faster with the CTA's warps in lockstep (they share the instruction stream); the
-    // small ones with decoupled warps
-    constexpr bool LOCKSTEP = KU != 8;
+    constexpr bool LOCKSTEP = false;  // true: one CTA barrier per block instead of the empty mbarriers (kept for experiments)
     extern __shared__ __align__(128) unsigned char km_smem[];
     const int K = g_km.K;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -480,16 +499,16 @@ __global__ void __launch_bounds__(KM_THREADS, 4) km_stream_kernel(const float* _
             float x[D];
 #pragma unroll
             for (int d = 0; d < D; ++d) x[d] = v[d].x;
-            l[0] = km_decide<D, KU, INERTIA>(stack, plane_stride, p, x, b[0], sc[0], inertia, ties);
+            l[0] = km_decide<D, KU, INERTIA>(stack, plane_stride, p, x, b[0], sc[0], wsm, inertia, ties);
 #pragma unroll
             for (int d = 0; d < D; ++d) x[d] = v[d].y;
-            l[1] = km_decide<D, KU, INERTIA>(stack, plane_stride, p + 1, x, b[1], sc[1], inertia, ties);
+            l[1] = km_decide<D, KU, INERTIA>(stack, plane_stride, p + 1, x, b[1], sc[1], wsm, inertia, ties);
 #pragma unroll
             for (int d = 0; d < D; ++d) x[d] = v[d].z;
-            l[2] = km_decide<D, KU, INERTIA>(stack, plane_stride, p + 2, x, b[2], sc[2], inertia, ties);
+            l[2] = km_decide<D, KU, INERTIA>(stack, plane_stride, p + 2, x, b[2], sc[2], wsm, inertia, ties);
 #pragma unroll
             for (int d = 0; d < D; ++d) x[d] = v[d].w;
-            l[3] = km_decide<D, KU, INERTIA>(stack, plane_stride, p + 3, x, b[3], sc[3], inertia, ties);
+            l[3] = km_decide<D, KU, INERTIA>(stack, plane_stride, p + 3, x, b[3], sc[3], wsm, inertia, ties);
             packed = (uint32_t)l[0] | ((uint32_t)l[1] << 8) | ((uint32_t)l[2] << 16) | ((uint32_t)l[3] << 24);
             if (prev8) diff = packed ^ pv;
             if (lab8) *reinterpret_cast<uint32_t*>(lab8 + p) = packed;

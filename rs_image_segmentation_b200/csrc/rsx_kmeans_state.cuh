@@ -6,7 +6,7 @@
 #define KM_MAXD RSX_MAX_FEATURES
 #define KM_MAXK RSX_MAX_CLUSTERS
 
-struct KmState {
+struct __align__(16) KmState {
     int D, K;
     long long n_global;
     double scale64[KM_MAXD], min64[KM_MAXD], mean64[KM_MAXD];  // MinMax scale_, min_; centring mean (scaled coords)
@@ -21,8 +21,8 @@ struct KmState {
     float w32[KM_MAXK * KM_MAXD];
     float bias32[KM_MAXK];
     float cent32[KM_MAXK * KM_MAXD];                            // centred, scaled coordinates in fp32 (inertia only)
-    float tau;
-    float pad0;
+    float tau;        // near-tie band of the tagged fp32 distances
+    float tau_tight;  // rounding-only bound (untagged fp32 distances)
     double shift_sq;
     int n_empty;
     int n_updates;

@@ -122,7 +122,7 @@ __device__ __forceinline__ void seven_indices(float blue, float green, float red
     // msavi (indices.py:109-112)
     {
         float t = f_add(f_mul(2.f, nir), 1.f);
-        float v = f_div(f_sub(t, f_sqrt(f_sub(f_mul(t, t), f_mul(8.f, f_sub(nir, red))))), 2.f);
+        float v = f_mul(f_sub(t, f_sqrt(f_sub(f_mul(t, t), f_mul(8.f, f_sub(nir, red))))), 0.5f);  // x / 2 == x * 0.5 exactly
         o[2] = v != v ? v : f_clip(v, -1.f, 1.f);
     }
     // ndwi (indices.py:128-135)
@@ -157,6 +157,16 @@ __global__ void __launch_bounds__(256) indices_fused_kernel(const T* __restrict_
     float mn[7], mx[7];
 #pragma unroll
     for (int k = 0; k < 7; ++k) mn[k] = INFINITY, mx[k] = -INFINITY;
+    // uint8 rasters: the normalised value of every grey level of the five bands (and the quantised NIR level) is tabulated
+    // once per CTA with the same float32 expressions, so the per-pixel work has 6 IEEE divisions instead of 12
+    __shared__ float nlut[sizeof(T) == 1 ? 5 * 256 : 1];
+    __shared__ uint8_t qlut[sizeof(T) == 1 ? 256 : 1];
+    if constexpr (sizeof(T) == 1) {
+        for (int i = threadIdx.x; i < 5 * 256; i += 256) nlut[i] = norm_apply((float)(i & 255), P.norm[i >> 8]);
+        __syncthreads();
+        for (int i = threadIdx.x; i < 256; i += 256) qlut[i] = (uint8_t)(int)f_mul(norm_apply(nlut[3 * 256 + i], P.qnorm), P.q_scale);
+        __syncthreads();
+    }
 
     for_each_tile<T, B, 3>(raster, n_px, smem, [&](const uint32_t* words, int64_t px0, int npx) {
         const T* samples = reinterpret_cast<const T*>(words);
@@ -171,10 +181,16 @@ __global__ void __launch_bounds__(256) indices_fused_kernel(const T* __restrict_
             for (int p = 0; p < PXT; ++p) {
                 const T* px = samples + (lp + p) * B;
                 float nb[5];
+                if constexpr (sizeof(T) == 1) {
 #pragma unroll
-                for (int k = 0; k < 5; ++k) nb[k] = norm_apply((float)px[P.band[k]], P.norm[k]);
+                    for (int k = 0; k < 5; ++k) nb[k] = nlut[k * 256 + px[P.band[k]]];
+                    q[p] = qlut[px[P.band[3]]];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) nb[k] = norm_apply((float)px[P.band[k]], P.norm[k]);
+                    q[p] = (uint8_t)(int)f_mul(norm_apply(nb[3], P.qnorm), P.q_scale);
+                }
                 seven_indices(nb[0], nb[1], nb[2], nb[3], nb[4], P, o[p]);
-                q[p] = (uint8_t)(int)f_mul(norm_apply(nb[3], P.qnorm), P.q_scale);
             }
             const int64_t gp = px0 + lp;
             if (lp + PXT <= npx) {
