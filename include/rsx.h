@@ -130,6 +130,14 @@ int rsx_resize_bilinear_f32(const float* d_src, int src_h_total, int src_w, int 
                             int64_t src_plane_stride, float* d_dst, int dst_h_total, int dst_w, int dst_row0, int dst_rows,
                             int64_t dst_plane_stride, int n_planes, uint32_t* d_minmax, rsx_stream_t stream);
 
+/* N1: add_spatial_context (indices.py:760-776): cv2.boxFilter(plane, -1, (ksize, ksize), normalize=True,
+ * borderType=BORDER_REFLECT) on n_planes float32 planes (double sums, (float)(sum * 1/k^2) like OpenCV).
+ * Row-strip sharding as for the resize: source rows [src_row0, src_row0+rows_avail) are present (the strip plus
+ * ksize/2 halo rows where the image continues), destination rows [dst_row0, dst_row0+dst_rows) are made. */
+int rsx_box_mean_f32(const float* d_src, int H_total, int W, int src_row0, int rows_avail, int64_t src_plane_stride,
+                     float* d_dst, int dst_row0, int dst_rows, int64_t dst_plane_stride, int n_planes, int ksize,
+                     uint32_t* d_minmax, rsx_stream_t stream);
+
 /* ---- min/max trackers (MinMaxScaler.fit, sklearn/preprocessing/_data.py:527-541) --------------- */
 int rsx_minmax_init(uint32_t* d_minmax, int n, rsx_stream_t stream);
 int rsx_minmax_planes_f32(const float* d_planes, int64_t n_px, int64_t plane_stride, int n_planes, uint32_t* d_minmax,

@@ -40,6 +40,7 @@ SIGNATURES = {
     "rsx_minmax_decode": (None, [vp, i32, vp, vp]),
     "rsx_minmax_encode": (None, [vp, vp, i32, vp]),
     "rsx_nan_to_zero_f32": (i32, [vp, i64, vp]),
+    "rsx_box_mean_f32": (i32, [vp, i32, i32, i32, i32, i64, vp, i32, i32, i64, i32, i32, vp, vp]),
     "rsx_kmeans_state_bytes": (i64, []),
     "rsx_kmeans_setup": (i32, [vp, i32, i32, vp, vp, vp, vp, i64, vp]),
     "rsx_kmeans_assign": (i32, [vp, i64, i64, i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),

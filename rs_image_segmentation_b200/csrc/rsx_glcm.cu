@@ -549,3 +549,88 @@ extern "C" int rsx_resize_bilinear_f32(const float* d_src, int src_h_total, int 
                                                                    dst_row0, dst_rows, dst_plane_stride, scale_x, scale_y, d_minmax);
     return rsx_check_launch("resize_bilinear");
 }
+
+// ----------------------------------------------------------------------------- N1: add_spatial_context (indices.py:760-776)
+// cv2.boxFilter(feature, -1, (k, k), normalize=True, borderType=BORDER_REFLECT) on float32 planes.  OpenCV sums float32
+// sources in double (row sums, then column sums) and stores (float)(sum * (1.0 / (k*k))); the same arithmetic here with
+// direct k-term sums (OpenCV's running sums differ from them by ~1e-16 relative, below float32 resolution).
+// Row-strip sharding: source rows [src_row0, src_row0 + rows_avail) of an H_total-row image are present; destination rows
+// [dst_row0, dst_row0 + dst_rows) are produced.
+__device__ __forceinline__ int reflect_index(int i, int n) {  // BORDER_REFLECT: fedcba|abcdefgh|hgfedcb
+    if (i < 0) i = -i - 1;
+    if (i >= n) i = 2 * n - i - 1;
+    return min(max(i, 0), n - 1);
+}
+
+template <int KS>
+__global__ void __launch_bounds__(128) box_mean_kernel(const float* __restrict__ src, int H_total, int W, int src_row0, int rows_avail, int64_t src_stride,
+                                                       float* __restrict__ dst, int dst_row0, int dst_rows, int64_t dst_stride, int rows_per_cta,
+                                                       uint32_t* __restrict__ minmax) {
+    constexpr int R = KS / 2;
+    __shared__ float row[128 + 2 * R];
+    const int plane = blockIdx.z;
+    const float* sp = src + plane * src_stride;
+    float* dp = dst + plane * dst_stride;
+    const int x0 = blockIdx.x * 128, x = x0 + threadIdx.x;
+    const int ly0 = blockIdx.y * rows_per_cta, ly1 = min(dst_rows, ly0 + rows_per_cta);
+    double ring[KS];
+#pragma unroll
+    for (int k = 0; k < KS; ++k) ring[k] = 0.0;
+    float mn = INFINITY, mx = -INFINITY;
+    const double scale = 1.0 / (double)(KS * KS);
+    // image rows gy0 - R .. gy1 - 1 + R stream through; an output row is complete when KS rows are in the ring
+    for (int gy = dst_row0 + ly0 - R; gy < dst_row0 + ly1 + R; ++gy) {
+        const int sy = reflect_index(gy, H_total) - src_row0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < 128 + 2 * R; i += 128) {
+            const int sx = reflect_index(x0 - R + i, W);
+            row[i] = (sy >= 0 && sy < rows_avail) ? sp[(int64_t)sy * W + sx] : 0.f;
+        }
+        __syncthreads();
+        double hs = 0.0;
+#pragma unroll
+        for (int k = 0; k < KS; ++k) hs += (double)row[threadIdx.x + k];
+#pragma unroll
+        for (int k = 0; k < KS - 1; ++k) ring[k] = ring[k + 1];
+        ring[KS - 1] = hs;
+        const int oy = gy - R;  // output row completed by this input row
+        if (oy >= dst_row0 + ly0 && x < W) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < KS; ++k) s += ring[k];
+            const float v = (float)(s * scale);
+            dp[(int64_t)(oy - dst_row0) * W + x] = v;
+            mn = fminf(mn, v), mx = fmaxf(mx, v);
+        }
+    }
+    if (minmax) warp_minmax_commit(mn, mx, minmax + 2 * plane);
+}
+
+extern "C" int rsx_box_mean_f32(const float* d_src, int H_total, int W, int src_row0, int rows_avail, int64_t src_plane_stride, float* d_dst,
+                                int dst_row0, int dst_rows, int64_t dst_plane_stride, int n_planes, int ksize, uint32_t* d_minmax,
+                                rsx_stream_t stream) {
+    RSX_REQUIRE(d_src && d_dst && H_total >= 1 && W >= 1 && dst_rows >= 1 && n_planes >= 1, "rsx_box_mean_f32: bad arguments");
+    RSX_REQUIRE(ksize >= 3 && ksize <= 11 && (ksize & 1), "rsx_box_mean_f32: window size must be odd, 3..11");
+    RSX_REQUIRE(ksize / 2 <= H_total && ksize / 2 <= W, "rsx_box_mean_f32: window larger than the image");
+    {
+        const int r = ksize / 2;
+        const int lo = max(dst_row0 - r, -(r)), hi = dst_row0 + dst_rows - 1 + r;
+        // reflected rows stay inside [0, H_total); the non-reflected range must be available
+        RSX_REQUIRE(max(dst_row0 - r, 0) >= src_row0 && min(hi, H_total - 1) < src_row0 + rows_avail, "rsx_box_mean_f32: halo rows missing");
+        (void)lo;
+    }
+    const int gx = ceil_div(W, 128);
+    const int rows_per_cta = max(32, ceil_div(dst_rows, max(1, rsx_num_sms() * 8 / max(1, gx * n_planes))));
+    dim3 grid(gx, ceil_div(dst_rows, rows_per_cta), n_planes);
+    cudaStream_t s = (cudaStream_t)stream;
+#define BOX(K)                                                                                                                                   \
+    case K:                                                                                                                                      \
+        box_mean_kernel<K><<<grid, 128, 0, s>>>(d_src, H_total, W, src_row0, rows_avail, src_plane_stride, d_dst, dst_row0, dst_rows, dst_plane_stride, \
+                                                 rows_per_cta, d_minmax);                                                                       \
+        break;
+    switch (ksize) {
+        BOX(3) BOX(5) BOX(7) BOX(9) BOX(11)
+    }
+#undef BOX
+    return rsx_check_launch("box_mean");
+}

@@ -19,7 +19,7 @@ from .device import hptr, ptr, require_cuda, stream_ptr
 
 __all__ = ["robust_normalize", "calculate_ndvi", "calculate_evi", "calculate_msavi", "calculate_ndwi", "calculate_mndwi",
            "calculate_ndbi", "calculate_bsi", "perform_pca", "calculate_glcm_features", "prepare_level_1_features",
-           "run_feature_extraction_stage", "RsxPCA"]
+           "add_spatial_context", "run_feature_extraction_stage", "RsxPCA"]
 
 _DEFAULT_ANGLES = [0, np.pi / 4, np.pi / 2, 3 * np.pi / 4]
 
@@ -249,15 +249,29 @@ def prepare_level_1_features(features_dict):
     return np.stack(maps, axis=-1)
 
 
+def add_spatial_context(features_array, window_size=7):
+    """indices.py:760-776: the (H, W, n) stack followed by the window_size x window_size box mean (cv2.boxFilter,
+    normalize=True, BORDER_REFLECT) of every channel; float64 (H, W, 2n) like the reference (np.zeros default dtype)."""
+    require_cuda()
+    features_array = np.asarray(features_array)
+    H, W, n = features_array.shape
+    planar = np.ascontiguousarray(np.moveaxis(features_array, -1, 0), dtype=np.float32)
+    src = torch.from_numpy(planar).cuda().reshape(n, H * W)
+    dst = torch.empty_like(src)
+    _lib.call("rsx_box_mean_f32", ptr(src), H, W, 0, H, H * W, ptr(dst), 0, H, H * W, n, int(window_size), None, stream_ptr())
+    ctx = np.moveaxis(dst.cpu().numpy().reshape(n, H, W), 0, -1)
+    return np.concatenate([features_array, ctx.astype(np.float64)], axis=-1)
+
+
 def run_feature_extraction_stage(bands_data, preprocessing=True, texture_band_index=3):
     """scripts/2_feature_extraction.py:27-133, hot-path part, fused on the device.
 
     bands_data: list of 2-D integer-valued arrays in TM order (what stage 1 writes: uint8 levels stored as
     float32).  One H2D copy of the packed raster, K1-K4 on the device, one D2H copy of the maps.  Returns
     (features_dict, hierarchical_features) with the reference's keys for the stages on the hot path: the seven
-    indices, 'pca_result', 'variance_ratio', 'glcm_features'; hierarchical_features['level_1'] is the 7-channel
-    stack of prepare_level_1_features.  The LBP / multi-scale / morphology / filter features and the spatial
-    context channels (scripts/2...:93-119) are outside the hot path and are not produced.
+    indices, 'pca_result', 'variance_ratio', 'glcm_features'; hierarchical_features['level_1'] is the 14-channel
+    float64 stack add_spatial_context(prepare_level_1_features(...)).  The LBP / multi-scale / morphology / filter
+    features (scripts/2...:93-107, level 2) are outside the hot path and are not produced.
     `texture_band_index` is accepted and ignored, like in the reference (the texture band is always NIR).
     """
     from . import pipeline as P
@@ -278,5 +292,7 @@ def run_feature_extraction_stage(bands_data, preprocessing=True, texture_band_in
     features["pca_result"] = [get(f"pc{i}") for i in range(n_comp)]
     features["variance_ratio"] = fr.pca["explained_variance_ratio"].astype(np.float32)
     features["glcm_features"] = {k: get("glcm_" + k) for k in P.GLCM_NAMES}
-    level1 = prepare_level_1_features(features)
+    # hierarchical['level_1'] = add_spatial_context(prepare_level_1_features(...)) (scripts/2...:112-119), on the device
+    l1, l1_names, _ = P.level1_with_context(fr)
+    level1 = np.moveaxis(l1[:, :fr.n_px].cpu().numpy().reshape(len(l1_names), H, W), 0, -1).astype(np.float64)
     return features, {"level_1": level1}

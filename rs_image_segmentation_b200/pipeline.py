@@ -176,6 +176,44 @@ def extract_features(raster: torch.Tensor, cfg: FeatureConfig = FeatureConfig(),
     return FeatureResult(planes=planes, names=names, n_px=n_px, H=h, W=W, stats=stats, pca=pca, minmax=mm, quant=quant)
 
 
+# ============================================================================================ level-1 stack with spatial context
+LEVEL1_NAMES = ("ndwi", "mndwi", "ndvi", "evi", "ndbi", "bsi", "pc0")     # prepare_level_1_features (indices.py:808-835)
+
+
+def level1_with_context(fr: FeatureResult, window_size: int = 7, comm: Optional[Comm] = None, H_total: Optional[int] = None,
+                        bounds: Optional[Sequence[Tuple[int, int]]] = None, timer: StageTimer = NO_TIMER):
+    """The reference's real level-1 stack (scripts/2_feature_extraction.py:112-119): the seven maps of
+    prepare_level_1_features followed by their window_size x window_size box means (add_spatial_context, indices.py:760-776;
+    BORDER_REFLECT), as a planar float32 device stack.  Returns (planes (14, stride), names, MinMaxTracker).
+    Row strips: the box filter needs window_size // 2 halo rows from the neighbouring strips."""
+    comm = comm or Comm()
+    H_total = H_total if H_total is not None else fr.H
+    bounds = list(bounds) if bounds is not None else [(0, fr.H)]
+    r0, r1 = bounds[comm.rank]
+    names = list(LEVEL1_NAMES) + ["ctx_" + n for n in LEVEL1_NAMES]
+    n = len(LEVEL1_NAMES)
+    dev = fr.planes.device
+    out = torch.empty((2 * n, fr.planes.shape[1]), dtype=torch.float32, device=dev)
+    mm = MinMaxTracker(2 * n, device=dev)
+    src_mn, src_mx = fr.minmax.buf, None
+    half = window_size // 2
+    needs = [(max(a - half, 0), min(b + half, H_total)) if b > a else (0, 0) for a, b in bounds]
+    for k, name in enumerate(LEVEL1_NAMES):
+        i = fr.names.index(name)
+        out[k].copy_(fr.planes[i])
+        mm.buf[k].copy_(fr.minmax.buf[i])
+        if fr.n_px == 0:
+            continue
+        local = fr.planes[i, :fr.n_px].view(fr.H, fr.W)
+        ext = comm.fetch_rows(local, bounds, needs)
+        if not ext.is_contiguous():
+            ext = ext.contiguous()
+        with timer("spatial_context"):
+            _lib.call("rsx_box_mean_f32", ptr(ext), H_total, fr.W, needs[comm.rank][0], ext.shape[0], ext.numel(),
+                      C.c_void_p(out[n + k].data_ptr()), r0, fr.H, out.shape[1], 1, int(window_size), mm.slot(n + k), stream_ptr())
+    return out, names, mm
+
+
 # ============================================================================================ KMeans
 def draw_init_indices(n: int, k: int, seed: int) -> np.ndarray:
     """k distinct pixel indices in [0, n), reproducible, without materialising a permutation of n."""

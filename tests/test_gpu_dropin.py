@@ -123,12 +123,32 @@ def test_run_feature_extraction_stage(I, aa_crop):
         assert np.array_equal(feats[k], aa_crop["ix_" + k]), k
     assert len(feats["pca_result"]) == 7
     np.testing.assert_allclose(feats["variance_ratio"], aa_crop["pca_evr"], rtol=5e-4)
-    l1 = hier["level_1"]
-    assert l1.shape == aa_crop["level1"].shape and l1.dtype == np.float32
-    assert np.array_equal(l1[..., :6], aa_crop["level1"][..., :6])        # ndwi, mndwi, ndvi, evi, ndbi, bsi
-    sgn = np.sign(np.dot(l1[..., 6].ravel(), aa_crop["level1"][..., 6].ravel()))
-    assert np.abs(l1[..., 6] * sgn - aa_crop["level1"][..., 6]).max() < 2e-4
+    l1 = hier["level_1"]                                                  # 7 maps + their 7x7 context means, float64
+    ref = aa_crop["level1_ctx"]
+    assert l1.shape == ref.shape and l1.dtype == np.float64
+    assert np.array_equal(l1[..., :6], ref[..., :6])                      # ndwi, mndwi, ndvi, evi, ndbi, bsi
+    sgn = np.sign(np.dot(l1[..., 6].ravel(), ref[..., 6].ravel()))
+    assert np.abs(l1[..., 6] * sgn - ref[..., 6]).max() < 2e-4
+    np.testing.assert_allclose(l1[..., 7:13], ref[..., 7:13], rtol=1e-6, atol=1e-7)   # context of the six indices
+    assert np.abs(l1[..., 13] * sgn - ref[..., 13]).max() < 2e-4
     assert set(feats["glcm_features"]) == {"contrast", "dissimilarity", "homogeneity", "energy", "correlation"}
+
+
+def test_add_spatial_context_matches_reference(I, aa_crop):
+    """add_spatial_context against the reference's own output (cv2.boxFilter, BORDER_REFLECT) and cv2 on odd shapes."""
+    got = I.add_spatial_context(aa_crop["level1"])
+    ref = aa_crop["level1_ctx"]
+    assert got.shape == ref.shape and got.dtype == np.float64
+    assert np.array_equal(got[..., :7], ref[..., :7])
+    assert np.abs(got[..., 7:] - ref[..., 7:]).max() <= 1.2e-7 * max(1.0, np.abs(ref).max())
+    assert (got[..., 7:] == ref[..., 7:]).mean() > 0.999                  # bit exact except for rare 1-ulp cases
+    from oracle import features as of
+    rng = np.random.default_rng(3)
+    for shape, k in (((37, 141, 2), 7), ((9, 300, 1), 5), ((130, 129, 3), 3), ((40, 33, 1), 11)):
+        x = rng.standard_normal(shape).astype(np.float32)
+        g = I.add_spatial_context(x, window_size=k)
+        r = of.spatial_context(x, window_size=k)
+        np.testing.assert_allclose(g, r, rtol=0, atol=2.4e-7 * np.abs(x).max())
 
 
 # ------------------------------------------------------------------------------------------- KMeans drop-in

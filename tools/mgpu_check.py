@@ -48,6 +48,10 @@ def main():
         planes = torch.zeros((len(fr.names), H * W), dtype=torch.float32, device="cuda")
         planes[:, r0 * W:r1 * W] = fr.planes[:, :fr.n_px]
         dist.all_reduce(planes)
+        l1, l1_names, _ = P.level1_with_context(fr, 7, comm, H, bounds)     # 3 halo rows from the neighbouring strips
+        ctx = torch.zeros((len(l1_names), H * W), dtype=torch.float32, device="cuda")
+        ctx[:, r0 * W:r1 * W] = l1[:, :fr.n_px]
+        dist.all_reduce(ctx)
         if rank == 0:
             one = Comm.__new__(Comm)                        # a 1-rank communicator although a process group exists
             one.dist, one.active, one.group, one.rank, one.world = dist, False, None, 0, 1
@@ -57,6 +61,9 @@ def main():
             if not torch.equal(planes, fr1.planes[:, :fr1.n_px]):
                 bad = [n for i, n in enumerate(fr1.names) if not torch.equal(planes[i], fr1.planes[i, :fr1.n_px])]
                 failures.append(f"{name}: feature planes differ: {bad}")
+            l11, _, _ = P.level1_with_context(fr1, 7, one)
+            if not torch.equal(ctx, l11[:, :fr1.n_px]):
+                failures.append(f"{name}: level-1 context planes differ")
             if not np.array_equal(c0, c01):
                 failures.append(f"{name}: initial centroids differ")
             if not np.array_equal(res.centroids, res1.centroids):
