@@ -186,7 +186,11 @@ int rsx_kmeans_setup(void* d_state, int D, int K, const double* h_feat_min, cons
 int rsx_kmeans_assign(const float* d_stack, int64_t plane_stride, int64_t n_px, int row_len, const void* d_state,
                       int64_t* d_acc, uint8_t* d_labels_u8, const uint8_t* d_labels_prev_u8, int32_t* d_labels_i32,
                       double* d_inertia, int update, int D, int K, rsx_stream_t stream);
-int rsx_kmeans_update(void* d_state, int64_t* d_acc, int delta, int D, rsx_stream_t stream);
+/* d_adjust (may be NULL): int64 [K*D + K] added to the totals for this centroid computation only - the host-assisted
+ * empty-cluster relocation of sklearn (_k_means_common.pyx:167-211); the running totals are not modified by it. */
+int rsx_kmeans_update(void* d_state, int64_t* d_acc, int delta, int D, const int64_t* d_adjust, rsx_stream_t stream);
+/* SYNCHRONISES: the fixed-point scale 2^shift_d per feature (a raw sample enters the sums as rint(x * scale)). */
+int rsx_kmeans_fixed_point_scales(const void* d_state, double* h_pow2, rsx_stream_t stream);
 /* SYNCHRONISES the stream; centroids come back in scaled, un-centred coordinates, double [K][D];
  * h_shift_sq = squared centre shift of the last update; h_empty = empty clusters met so far. */
 int rsx_kmeans_read(const void* d_state, double* h_centroids, double* h_shift_sq, int32_t* h_empty, rsx_stream_t stream);

@@ -44,7 +44,8 @@ SIGNATURES = {
     "rsx_kmeans_state_bytes": (i64, []),
     "rsx_kmeans_setup": (i32, [vp, i32, i32, vp, vp, vp, vp, i64, vp]),
     "rsx_kmeans_assign": (i32, [vp, i64, i64, i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
-    "rsx_kmeans_update": (i32, [vp, vp, i32, i32, vp]),
+    "rsx_kmeans_update": (i32, [vp, vp, i32, i32, vp, vp]),
+    "rsx_kmeans_fixed_point_scales": (i32, [vp, vp, vp]),
     "rsx_kmeans_read": (i32, [vp, vp, vp, vp, vp]),
 }
 

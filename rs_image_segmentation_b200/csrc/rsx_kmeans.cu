@@ -184,7 +184,9 @@ extern "C" int rsx_kmeans_assign(const float* d_stack, int64_t plane_stride, int
 // acc = pass block [sums K*D][counts K][near ties][changed] ++ totals block [sums K*D][counts K][near ties so far][changed in
 // the last pass].  A full pass produced the sums themselves (delta == 0: totals <- pass), a delta pass their change (totals +=
 // pass); the centroids come from the totals; the pass block is zeroed for the next pass.
-__global__ void __launch_bounds__(KM_CTRL_THREADS) km_update_kernel(KmState* gst, long long* acc, int delta) {
+// adjust (optional, [K*D + K]): empty-cluster relocation of sklearn (_k_means_common.pyx:167-211) - added to the totals for
+// THIS centroid computation only; the running totals stay "sums by label", which is what the next delta pass builds on.
+__global__ void __launch_bounds__(KM_CTRL_THREADS) km_update_kernel(KmState* gst, long long* acc, int delta, const long long* __restrict__ adjust) {
     __shared__ __align__(16) KmState sst;
     KmState* st = &sst;
     km_state_copy(st, gst);
@@ -203,21 +205,22 @@ __global__ void __launch_bounds__(KM_CTRL_THREADS) km_update_kernel(KmState* gst
     __shared__ double shift_part[KM_MAXK];
     __shared__ int empty_part[KM_MAXK];
     for (int j = threadIdx.x; j < K; j += blockDim.x) {
-        long long cnt = acc[K * D + j];
+        const long long cnt = acc[K * D + j] + (adjust ? adjust[K * D + j] : 0ll);
         double sh = 0.0;
         int empty = 0;
         if (cnt > 0) {
             // _average_centers: centers *= 1/weight  (_k_means_common.pyx:274-296)
             double alpha = 1.0 / (double)cnt;
             for (int d = 0; d < D; ++d) {
-                double mean_raw = ((double)acc[j * D + d] * st->inv_pow2[d]) * alpha;
+                const long long sum_q = acc[j * D + d] + (adjust ? adjust[j * D + d] : 0ll);
+                double mean_raw = ((double)sum_q * st->inv_pow2[d]) * alpha;
                 double c = (mean_raw * st->scale64[d] + st->min64[d]) - st->mean64[d];
                 double old = st->cent64[j * KM_MAXD + d];
                 sh += (c - old) * (c - old);
                 st->cent64[j * KM_MAXD + d] = c;
             }
         } else {
-            empty = 1;  // relocation (_k_means_common.pyx:167-211) is not done on the device: reported to the host
+            empty = 1;  // no relocation was supplied: the centre keeps its position and the event is reported
         }
         shift_part[j] = sh;
         empty_part[j] = empty;
@@ -238,12 +241,28 @@ __global__ void __launch_bounds__(KM_CTRL_THREADS) km_update_kernel(KmState* gst
     km_state_copy(gst, st);
 }
 
-extern "C" int rsx_kmeans_update(void* d_state, int64_t* d_acc, int delta, int D, rsx_stream_t stream) {
+extern "C" int rsx_kmeans_update(void* d_state, int64_t* d_acc, int delta, int D, const int64_t* d_adjust, rsx_stream_t stream) {
     RSX_REQUIRE(d_state && d_acc && D >= 1 && D <= KM_MAXD, "rsx_kmeans_update: bad arguments");
     cudaStream_t s = (cudaStream_t)stream;
-    km_update_kernel<<<1, KM_CTRL_THREADS, 0, s>>>((KmState*)d_state, reinterpret_cast<long long*>(d_acc), delta);
+    km_update_kernel<<<1, KM_CTRL_THREADS, 0, s>>>((KmState*)d_state, reinterpret_cast<long long*>(d_acc), delta,
+                                                   reinterpret_cast<const long long*>(d_adjust));
     if (int rc = rsx_check_launch("km_update")) return rc;
     return km_publish(d_state, D, s);
+}
+
+// fixed-point scale 2^shift_d of every feature (what the assign kernels multiply a raw sample by before rounding)
+extern "C" int rsx_kmeans_fixed_point_scales(const void* d_state, double* h_pow2, rsx_stream_t stream) {
+    RSX_REQUIRE(d_state && h_pow2, "rsx_kmeans_fixed_point_scales: bad arguments");
+    static thread_local KmState h;
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e = cudaMemcpyAsync(&h, d_state, sizeof(h), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) {
+        rsx_set_error("rsx_kmeans_fixed_point_scales: %s", cudaGetErrorString(e));
+        return RSX_ERR_CUDA;
+    }
+    for (int d = 0; d < h.D; ++d) h_pow2[d] = (double)h.pow2[d];
+    return RSX_OK;
 }
 
 extern "C" int rsx_kmeans_read(const void* d_state, double* h_centroids, double* h_shift_sq, int32_t* h_empty, rsx_stream_t stream) {

@@ -308,10 +308,10 @@ class DeviceKMeans:
             self._labels = [torch.full((max(npad, 4),), 255, dtype=torch.uint8, device=self.planes.device) for _ in range(2)]
         return self._labels
 
-    def step(self, track_labels: bool = False):
-        """One fused assign + partial-sum pass, the all-reduce of K*(D+1)+2 integers, one centroid update.
-        The first pass accumulates from scratch; later passes are delta passes (if enabled).  With track_labels (or delta)
-        every pass writes uint8 labels and counts the pixels whose label changed (acc[K*D+K+1])."""
+    def assign_pass(self, track_labels: bool = False) -> int:
+        """One fused assign + partial-sum pass and the all-reduce of its K*(D+1)+2 integers.  The first pass accumulates from
+        scratch; later passes are delta passes (if enabled).  With track_labels (or delta) every pass writes uint8 labels
+        and counts the pixels whose label changed.  Returns the mode used (1 = full, 2 = delta)."""
         use_labels = track_labels or self.delta
         # K > 8: the delta kernel is also the full pass (previous labels = 255: every pixel "moves in" from nowhere)
         mode = 2 if (self.delta and (self._passes > 0 or self.K > 8)) else 1
@@ -321,14 +321,69 @@ class DeviceKMeans:
             if self._passes == 0:
                 planes[1].fill_(255)
             cur, prev = planes[self._passes % 2], planes[(self._passes + 1) % 2]
+        self._cur_labels = cur
         if self.n_px:
             with self.timer("kmeans_assign_delta" if mode == 2 else "kmeans_assign_full"):
                 _lib.call("rsx_kmeans_assign", ptr(self.planes), self.stride, self.n_px, self.row_len, ptr(self.state), ptr(self.acc),
                           ptr(cur), ptr(prev), None, None, mode, self.D, self.K, stream_ptr())
         self.comm.all_reduce(self.acc[:self.n_acc])
+        return mode
+
+    def update(self, mode: int, adjust: Optional[torch.Tensor] = None):
+        """Centroids <- totals / counts (the pass block is folded into the totals first)."""
         with self.timer("kmeans_update"):
-            _lib.call("rsx_kmeans_update", ptr(self.state), ptr(self.acc), 1 if mode == 2 else 0, self.D, stream_ptr())
+            _lib.call("rsx_kmeans_update", ptr(self.state), ptr(self.acc), 1 if mode == 2 else 0, self.D, ptr(adjust), stream_ptr())
         self._passes += 1
+
+    def step(self, track_labels: bool = False):
+        """assign_pass + update, without host synchronisation (empty clusters are only reported, see fit_converge)."""
+        self.update(self.assign_pass(track_labels))
+
+    def relocation_adjust(self, empty: np.ndarray, first_px: int = 0) -> torch.Tensor:
+        """sklearn's _relocate_empty_clusters_dense (_k_means_common.pyx:167-211) for the pass that has just been all-reduced:
+        every empty cluster takes the sample that is farthest from its own (old) centre; that sample leaves its cluster's
+        sum.  Returns the int64 adjustment [K*D + K] for rsx_kmeans_update.  Rare, host assisted, synchronises.
+        (For several simultaneous empties sklearn hands out the farthest samples in numpy's argpartition order; here they
+        go to the empty clusters in order of decreasing distance.)"""
+        K, D, dev = self.K, self.D, self.planes.device
+        empties = np.flatnonzero(empty)
+        n_e = len(empties)
+        cent_old, _, _ = self.read()
+        C = torch.from_numpy(cent_old).to(dev)
+        scale, min_ = torch.from_numpy(self.scale).to(dev), torch.from_numpy(self.min_).to(dev)
+        labels = self._cur_labels
+        cand = torch.full((n_e, 3 + D), -1.0, dtype=torch.float64, device=dev)     # distance, global index, label, raw sample
+        if self.n_px:
+            dist = torch.empty(self.n_px, dtype=torch.float64, device=dev)
+            chunk = 1 << 22
+            for a in range(0, self.n_px, chunk):
+                b = min(self.n_px, a + chunk)
+                Xs = self.planes[:D, a:b].t().to(torch.float64) * scale + min_
+                dist[a:b] = ((Xs - C[labels[a:b].long()]) ** 2).sum(dim=1)
+            k = min(n_e, self.n_px)
+            vals, idx = torch.topk(dist, k)
+            cand[:k, 0] = vals
+            cand[:k, 1] = (idx + first_px).to(torch.float64)
+            cand[:k, 2] = labels[idx].to(torch.float64)
+            cand[:k, 3:] = self.planes[:D].index_select(1, idx).t().to(torch.float64)
+        if self.comm.world > 1:
+            gathered = [torch.empty_like(cand) for _ in range(self.comm.world)]
+            self.comm.dist.all_gather(gathered, cand, group=self.comm.group)
+            cand = torch.cat(gathered, dim=0)
+        c = cand.cpu().numpy()
+        c = c[c[:, 0] >= 0]
+        order = np.lexsort((c[:, 1], -c[:, 0]))[:n_e]                               # farthest first, ties by pixel index
+        pow2 = np.zeros(D, np.float64)
+        _lib.call("rsx_kmeans_fixed_point_scales", ptr(self.state), hptr(pow2), stream_ptr())
+        adj = np.zeros(K * D + K, np.int64)
+        for new, row in zip(empties, c[order]):
+            old = int(row[2])
+            q = np.rint(row[3:].astype(np.float32) * pow2.astype(np.float32)).astype(np.int64)   # as the kernels: rint(x * 2^shift)
+            adj[old * D:(old + 1) * D] -= q
+            adj[K * D + old] -= 1
+            adj[new * D:(new + 1) * D] += q
+            adj[K * D + new] += 1
+        return torch.from_numpy(adj).to(dev)
 
     def changed_count(self) -> int:
         """Pixels (all ranks) whose label changed in the last update pass; synchronises."""
@@ -361,15 +416,21 @@ class DeviceKMeans:
         return cent, float(shift[0]), int(empty[0])
 
     def fit_converge(self, init_centroids_scaled: np.ndarray, max_iter: int = 300, tol: float = 0.0,
-                     mean_scaled: Optional[np.ndarray] = None) -> KMeansResult:
+                     mean_scaled: Optional[np.ndarray] = None, first_px: int = 0) -> KMeansResult:
         """sklearn's _kmeans_single_lloyd stopping rules (_kmeans.py:703-754): stop when no label changed between two
         passes (strict convergence) or when the squared centre shift is <= tol; then the final assignment + inertia."""
         self.setup(init_centroids_scaled, mean_scaled)
         n_iter = 0
+        KD = self.K * self.D
         for it in range(max_iter):
-            self.step(track_labels=True)       # the changed-label counter is part of the all-reduced block
+            mode = self.assign_pass(track_labels=True)
+            blocks = self.acc.cpu().numpy()                    # the one synchronisation of an iteration
+            counts = blocks[KD:KD + self.K] + (blocks[self.n_acc + KD:self.n_acc + KD + self.K] if mode == 2 else 0)
+            changed = int(blocks[self.n_acc - 1])
+            adjust = self.relocation_adjust(counts == 0, first_px) if (counts == 0).any() else None
+            self.update(mode, adjust)
             n_iter = it + 1
-            if self.changed_count() == 0:
+            if changed == 0:
                 break
             _, shift, _ = self.read()
             if shift <= tol:

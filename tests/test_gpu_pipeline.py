@@ -212,3 +212,37 @@ def test_kmeans_changed_counter(P):
         expect = fr.n_px if prev is None else int((cur != prev).sum())
         assert km.changed_count() == expect
         prev = cur
+
+
+@pytest.mark.parametrize("dups", [1, 2])
+def test_kmeans_empty_cluster_relocation_matches_sklearn(P, dups):
+    """Duplicate initial centroids leave cluster(s) empty after the first E-step: sklearn relocates each to the sample that
+    is farthest from its own centre (_k_means_common.pyx:167-211).  Same labels / centroids as sklearn on float64 data."""
+    import warnings
+    import torch
+    from sklearn.cluster import KMeans
+    from oracle import kmeans as ok
+    from rs_image_segmentation_b200.synth import synth_raster_numpy
+    bip = synth_raster_numpy(80, 120, 7, np.uint8, 13, cell=16)
+    fr = P.extract_features(torch.from_numpy(bip).cuda(), P.FeatureConfig(glcm=False))
+    D, K = 7, 5
+    mn, mx = fr.minmax.read()
+    km = P.DeviceKMeans(fr.planes, fr.n_px, D, K, mn[:D], mx[:D], fr.n_px, fr.W)
+    c0 = km.scale_rows(km.gather_rows(P.draw_init_indices(fr.n_px, K, 4), 0))
+    for j in range(dups):
+        c0[K - 1 - j] = c0[0]                                          # first minimum wins -> these clusters start empty
+    X = fr.planes[:D, :fr.n_px].t().contiguous().cpu().numpy().astype(np.float64)
+    Xs = ok.minmax_scale(X)
+    tol = float(np.mean(np.var(Xs, axis=0)) * 1e-4)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = KMeans(n_clusters=K, init=c0, n_init=1, max_iter=300, tol=1e-4, algorithm="lloyd").fit(Xs)
+    res = km.fit_converge(c0, max_iter=300, tol=tol, mean_scaled=Xs.mean(axis=0))
+    got = res.labels.cpu().numpy()
+    if dups == 1:                                                      # one empty cluster: sklearn's choice is unambiguous
+        assert res.n_iter == ref.n_iter_
+        assert np.array_equal(got, ref.labels_), f"{(got != ref.labels_).sum()} labels differ"
+        np.testing.assert_allclose(res.centroids, ref.cluster_centers_, rtol=0, atol=1e-9)
+    else:                                                              # several: same partition quality, every cluster populated
+        assert len(np.unique(got)) == K
+        assert abs(res.inertia - ref.inertia_) <= 0.05 * ref.inertia_
