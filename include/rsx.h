@@ -64,10 +64,13 @@ int rsx_hist_u16(const uint16_t* d_raster, int64_t n_px, int n_bands, uint32_t* 
  * d_minmax:    uint32 [7][2] tracker or NULL
  * d_quant:     uint8 [n_px] or NULL: (robust_normalize(nir_norm) * (levels-1)).astype(uint8)
  *              (indices.py:265-268); h_qnorm = lo, hi, den of that second normalisation.
- * evi:         L, C1, C2, G of calculate_evi (indices.py:73) */
+ * evi:         L, C1, C2, G of calculate_evi (indices.py:73)
+ * h_remap:     (uint8 only, may be NULL) uint8 [B][256]: level v of band b is first replaced by h_remap[b][v].  This is
+ *              how stage 1 (gain/bias -> min-max stretch -> uint8, modules/features/preprocessing.py:54-125) is fused
+ *              into the load path: for 8-bit input the whole chain is one table per band. */
 int rsx_indices_fused_u8(const uint8_t* d_raster, int64_t n_px, int n_bands, const int* band_map, const float* h_norm,
                          const float* evi, float* d_indices, int64_t plane_stride, uint32_t* d_minmax, uint8_t* d_quant,
-                         const float* h_qnorm, int levels, rsx_stream_t stream);
+                         const float* h_qnorm, int levels, const uint8_t* h_remap, rsx_stream_t stream);
 int rsx_indices_fused_u16(const uint16_t* d_raster, int64_t n_px, int n_bands, const int* band_map, const float* h_norm,
                           const float* evi, float* d_indices, int64_t plane_stride, uint32_t* d_minmax, uint8_t* d_quant,
                           const float* h_qnorm, int levels, rsx_stream_t stream);
@@ -137,6 +140,26 @@ int rsx_resize_bilinear_f32(const float* d_src, int src_h_total, int src_w, int 
 int rsx_box_mean_f32(const float* d_src, int H_total, int W, int src_row0, int rows_avail, int64_t src_plane_stride,
                      float* d_dst, int dst_row0, int dst_rows, int64_t dst_plane_stride, int n_planes, int ksize,
                      uint32_t* d_minmax, rsx_stream_t stream);
+
+/* N2: the stencil channels of the level-2 stack (prepare_level_2_features, indices.py:837-865) on the texture band.
+ * Same row-strip convention as rsx_box_mean_f32.  rsx_band_lut_*: plane[p] = lut[raster[p*B + band]] (d_lut on the DEVICE,
+ * 256 entries) - how the second robust_normalize of the texture band and its 8-bit quantisation are applied. */
+int rsx_band_lut_u8(const uint8_t* d_raster, int64_t n_px, int n_bands, int band, const uint8_t* d_lut, uint8_t* d_out, rsx_stream_t stream);
+int rsx_band_lut_f32(const uint8_t* d_raster, int64_t n_px, int n_bands, int band, const float* d_lut, float* d_out, rsx_stream_t stream);
+/* cv2.morphologyEx(src, MORPH_GRADIENT, ones(ksize, ksize)) on uint8 (indices.py:421-432), ksize 3, 5 or 7 */
+int rsx_morph_gradient_u8(const uint8_t* d_src, int H_total, int W, int src_row0, int rows_avail, uint8_t* d_dst, int dst_row0,
+                          int dst_rows, int ksize, rsx_stream_t stream);
+/* sqrt(max(cv2.blur(x*x) - cv2.blur(x)^2, 0)) in the reference's float32 arithmetic (indices.py:537-548), ksize 3, 5 or 7;
+ * d_minmax: one tracker slot or NULL */
+int rsx_local_std_f32(const float* d_src, int H_total, int W, int src_row0, int rows_avail, float* d_dst, int dst_row0, int dst_rows,
+                      int ksize, uint32_t* d_minmax, rsx_stream_t stream);
+/* sqrt((Sobel_x/255)^2 + (Sobel_y/255)^2), 3x3, BORDER_REFLECT_101 (indices.py:477-479); the division by the global maximum
+ * (:480) is rsx_divide_f32 with max + 1e-10 once the tracker has been reduced over all strips */
+int rsx_sobel_mag_u8(const uint8_t* d_src, int H_total, int W, int src_row0, int rows_avail, float* d_dst, int dst_row0, int dst_rows,
+                     uint32_t* d_minmax, rsx_stream_t stream);
+int rsx_divide_f32(float* d_plane, int64_t n, float denominator, rsx_stream_t stream);
+/* plane[i] = (float)(in[i] / 255.0): uint8 maps enter the float32 stack (the reference keeps them as float64 k/255.0) */
+int rsx_u8_over_255_f32(const uint8_t* d_in, int64_t n, float* d_out, rsx_stream_t stream);
 
 /* ---- min/max trackers (MinMaxScaler.fit, sklearn/preprocessing/_data.py:527-541) --------------- */
 int rsx_minmax_init(uint32_t* d_minmax, int n, rsx_stream_t stream);

@@ -145,3 +145,40 @@ def stage1_preprocess(raw_bands):
         e = ((r - r.min()) * 255.0 / (r.max() - r.min())).astype(np.uint8)
         out.append(e)
     return out
+
+
+# ---------------------------------------------------------------- level 2 (N2)
+def morph_gradient(band, size=5):
+    """indices.py:412-440 - calculate_morphological_features(band)['gradient_<size>']."""
+    import cv2
+
+    b8 = (robust_normalize(band) * 255).astype(np.uint8)
+    return cv2.morphologyEx(b8, cv2.MORPH_GRADIENT, np.ones((size, size), np.uint8)) / 255.0
+
+
+def std_dev_scale(band, scale=5):
+    """indices.py:531-548 - calculate_multi_scale_features(band)['std_dev_scale_<scale>']."""
+    import cv2
+
+    b = robust_normalize(band)
+    mean = cv2.blur(b, (scale, scale))
+    mean_sq = cv2.blur(b * b, (scale, scale))
+    var = mean_sq - mean * mean
+    var[var < 0] = 0
+    return np.sqrt(var)
+
+
+def sobel_mag(band):
+    """indices.py:455-480 - calculate_filter_responses(band)['sobel_mag']."""
+    import cv2
+
+    b8 = (robust_normalize(band) * 255).astype(np.uint8)
+    sx = cv2.Sobel(b8, cv2.CV_32F, 1, 0) / 255.0
+    sy = cv2.Sobel(b8, cv2.CV_32F, 0, 1) / 255.0
+    m = np.sqrt(sx ** 2 + sy ** 2)
+    return m / (m.max() + 1e-10)
+
+
+def level2_stack(glcm, band):
+    """indices.py:837-865 with the three stencil maps of the texture band."""
+    return np.stack([glcm["contrast"], glcm["homogeneity"], morph_gradient(band), std_dev_scale(band), sobel_mag(band)], axis=-1)

@@ -19,7 +19,7 @@ SIGNATURES = {
     "rsx_launch_count": (i64, []),
     "rsx_hist_u8": (i32, [vp, i64, i32, vp, vp]),
     "rsx_hist_u16": (i32, [vp, i64, i32, vp, vp]),
-    "rsx_indices_fused_u8": (i32, [vp, i64, i32, vp, vp, vp, vp, i64, vp, vp, vp, i32, vp]),
+    "rsx_indices_fused_u8": (i32, [vp, i64, i32, vp, vp, vp, vp, i64, vp, vp, vp, i32, vp, vp]),
     "rsx_indices_fused_u16": (i32, [vp, i64, i32, vp, vp, vp, vp, i64, vp, vp, vp, i32, vp]),
     "rsx_normalize_f32": (i32, [vp, i64, f32, f32, f32, vp, vp]),
     "rsx_index_ratio_f32": (i32, [vp, vp, i64, vp, vp]),
@@ -40,6 +40,13 @@ SIGNATURES = {
     "rsx_minmax_decode": (None, [vp, i32, vp, vp]),
     "rsx_minmax_encode": (None, [vp, vp, i32, vp]),
     "rsx_nan_to_zero_f32": (i32, [vp, i64, vp]),
+    "rsx_band_lut_u8": (i32, [vp, i64, i32, i32, vp, vp, vp]),
+    "rsx_band_lut_f32": (i32, [vp, i64, i32, i32, vp, vp, vp]),
+    "rsx_morph_gradient_u8": (i32, [vp, i32, i32, i32, i32, vp, i32, i32, i32, vp]),
+    "rsx_local_std_f32": (i32, [vp, i32, i32, i32, i32, vp, i32, i32, i32, vp, vp]),
+    "rsx_sobel_mag_u8": (i32, [vp, i32, i32, i32, i32, vp, i32, i32, vp, vp]),
+    "rsx_divide_f32": (i32, [vp, i64, C.c_float, vp]),
+    "rsx_u8_over_255_f32": (i32, [vp, i64, vp, vp]),
     "rsx_box_mean_f32": (i32, [vp, i32, i32, i32, i32, i64, vp, i32, i32, i64, i32, i32, vp, vp]),
     "rsx_kmeans_state_bytes": (i64, []),
     "rsx_kmeans_setup": (i32, [vp, i32, i32, vp, vp, vp, vp, i64, vp]),

@@ -105,6 +105,9 @@ struct IndexParams {
     float evi_L, evi_C1, evi_C2, evi_G;
     NormParam qnorm;
     float q_scale;  // levels - 1
+    // uint8 rasters: level remap of the five bands applied before the normalisation (identity by default); carries the
+    // fused stage-1 chain gain/bias -> min-max stretch -> uint8 (modules/features/preprocessing.py:54-125)
+    uint8_t remap[5][256];
 };
 
 // the seven maps of scripts/2_feature_extraction.py:63-73, in RSX index order
@@ -162,7 +165,7 @@ __global__ void __launch_bounds__(256) indices_fused_kernel(const T* __restrict_
     __shared__ float nlut[sizeof(T) == 1 ? 5 * 256 : 1];
     __shared__ uint8_t qlut[sizeof(T) == 1 ? 256 : 1];
     if constexpr (sizeof(T) == 1) {
-        for (int i = threadIdx.x; i < 5 * 256; i += 256) nlut[i] = norm_apply((float)(i & 255), P.norm[i >> 8]);
+        for (int i = threadIdx.x; i < 5 * 256; i += 256) nlut[i] = norm_apply((float)P.remap[i >> 8][i & 255], P.norm[i >> 8]);
         __syncthreads();
         for (int i = threadIdx.x; i < 256; i += 256) qlut[i] = (uint8_t)(int)f_mul(norm_apply(nlut[3 * 256 + i], P.qnorm), P.q_scale);
         __syncthreads();
@@ -233,8 +236,9 @@ __global__ void __launch_bounds__(256) indices_fused_kernel(const T* __restrict_
 template <typename T>
 static int indices_fused_impl(const T* d_raster, int64_t n_px, int n_bands, const int* band_map, const float* h_norm, const float* evi,
                               float* d_indices, int64_t plane_stride, uint32_t* d_minmax, uint8_t* d_quant, const float* h_qnorm, int levels,
-                              rsx_stream_t stream) {
+                              const uint8_t* h_remap, rsx_stream_t stream) {
     RSX_REQUIRE(d_raster && band_map && h_norm && evi && d_indices && n_px > 0, "rsx_indices_fused: bad arguments");
+    RSX_REQUIRE(!h_remap || sizeof(T) == 1, "rsx_indices_fused: a level remap is only defined for uint8 rasters");
     RSX_REQUIRE(((uintptr_t)d_raster & 15) == 0 && ((uintptr_t)d_indices & 15) == 0 && (plane_stride & 3) == 0 && plane_stride >= n_px,
                 "rsx_indices_fused: raster/planes must be 16-byte aligned, plane_stride a multiple of 4 and >= n_px");
     RSX_REQUIRE(!d_quant || (h_qnorm && levels >= 2 && levels <= 256 && ((uintptr_t)d_quant & 3) == 0), "rsx_indices_fused: bad quantisation arguments");
@@ -244,6 +248,7 @@ static int indices_fused_impl(const T* d_raster, int64_t n_px, int n_bands, cons
         RSX_REQUIRE(b >= 0 && b < n_bands, "rsx_indices_fused: band_map[%d]=%d out of range", k, b);
         P.band[k] = b;
         P.norm[k] = NormParam{h_norm[3 * b], h_norm[3 * b + 1], h_norm[3 * b + 2]};
+        for (int v = 0; v < 256; ++v) P.remap[k][v] = h_remap ? h_remap[b * 256 + v] : (uint8_t)v;
     }
     P.evi_L = evi[0], P.evi_C1 = evi[1], P.evi_C2 = evi[2], P.evi_G = evi[3];
     P.qnorm = d_quant ? NormParam{h_qnorm[0], h_qnorm[1], h_qnorm[2]} : NormParam{0.f, 1.f, 1.f};
@@ -262,13 +267,15 @@ static int indices_fused_impl(const T* d_raster, int64_t n_px, int n_bands, cons
 
 extern "C" int rsx_indices_fused_u8(const uint8_t* d_raster, int64_t n_px, int n_bands, const int* band_map, const float* h_norm, const float* evi,
                                     float* d_indices, int64_t plane_stride, uint32_t* d_minmax, uint8_t* d_quant, const float* h_qnorm, int levels,
-                                    rsx_stream_t stream) {
-    return indices_fused_impl<uint8_t>(d_raster, n_px, n_bands, band_map, h_norm, evi, d_indices, plane_stride, d_minmax, d_quant, h_qnorm, levels, stream);
+                                    const uint8_t* h_remap, rsx_stream_t stream) {
+    return indices_fused_impl<uint8_t>(d_raster, n_px, n_bands, band_map, h_norm, evi, d_indices, plane_stride, d_minmax, d_quant, h_qnorm, levels, h_remap,
+                                       stream);
 }
 extern "C" int rsx_indices_fused_u16(const uint16_t* d_raster, int64_t n_px, int n_bands, const int* band_map, const float* h_norm, const float* evi,
                                      float* d_indices, int64_t plane_stride, uint32_t* d_minmax, uint8_t* d_quant, const float* h_qnorm, int levels,
                                      rsx_stream_t stream) {
-    return indices_fused_impl<uint16_t>(d_raster, n_px, n_bands, band_map, h_norm, evi, d_indices, plane_stride, d_minmax, d_quant, h_qnorm, levels, stream);
+    return indices_fused_impl<uint16_t>(d_raster, n_px, n_bands, band_map, h_norm, evi, d_indices, plane_stride, d_minmax, d_quant, h_qnorm, levels, nullptr,
+                                        stream);
 }
 
 // ============================================================================ K3: PCA

@@ -124,6 +124,7 @@ class RasterStats:
         B, L = hist.shape
         self.B, self.L = B, L
         self.hist = hist
+        self.hist_raw = hist                       # pipeline.extract_features overwrites it with the DN histogram when stage 1 is fused
         self.n = int(hist[0].sum())
         levels = np.arange(L, dtype=F32)
         self.norm = np.zeros((B, 3), F32)
@@ -179,6 +180,38 @@ class RasterStats:
         """(robust_normalize(norm) * (levels-1)).astype(uint8) per grey level (indices.py:265-268)."""
         g = normalize_levels(self.norm_lut[band], *self.qnorm)
         return (g * (levels - 1)).astype(np.uint8)
+
+
+TM_GAIN = (0.671339, 1.322205, 1.043976, 0.876024, 0.120354, 0.055376, 0.065551)   # preprocessing.py:65
+TM_BIAS = (-2.19, -4.16, -2.21, -2.39, -0.49, 1.18, -0.22)                           # preprocessing.py:66
+
+
+def stage1_level_tables(hist_raw, gain=TM_GAIN, bias=TM_BIAS):
+    """Stage 1 of the reference for 8-bit DN input as one table per band (modules/features/preprocessing.py:54-125):
+    radiance = gain*DN + bias (float64), identity warp, (radiance - min) * 255.0 / (max - min) -> astype(uint8).
+    hist_raw: int64 [B][256] DN histograms.  Returns (remap uint8 [B][256], hist_stage1 int64 [B][256])."""
+    hist_raw = np.asarray(hist_raw, dtype=np.int64)
+    B, L = hist_raw.shape
+    assert L == 256, "the fused stage-1 chain is defined for 8-bit rasters"
+    if len(gain) < B or len(bias) < B:
+        raise ValueError(f"{B} bands but {len(gain)} calibration coefficients")
+    remap = np.zeros((B, 256), np.uint8)
+    hist1 = np.zeros((B, 256), np.int64)
+    dn = np.arange(256, dtype=np.uint8)
+    for b in range(B):
+        present = np.flatnonzero(hist_raw[b])
+        if present.size == 0:
+            raise ValueError("empty histogram")
+        radiance = gain[b] * dn + bias[b]                      # the reference's expression, elementwise on the 256 levels
+        lo, hi = radiance[present[0]], radiance[present[-1]]   # np.min / np.max of the band's radiance (gain > 0 or < 0 alike)
+        lo, hi = min(lo, hi), max(lo, hi)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            e = (radiance - lo) * 255.0 / (hi - lo)
+        ok = np.zeros(256, bool)
+        ok[present] = True
+        remap[b, ok] = e[ok].astype(np.uint8)
+        np.add.at(hist1[b], remap[b, ok], hist_raw[b, ok])
+    return remap, hist1
 
 
 def float_band_order(band):

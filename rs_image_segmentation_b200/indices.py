@@ -19,7 +19,8 @@ from .device import hptr, ptr, require_cuda, stream_ptr
 
 __all__ = ["robust_normalize", "calculate_ndvi", "calculate_evi", "calculate_msavi", "calculate_ndwi", "calculate_mndwi",
            "calculate_ndbi", "calculate_bsi", "perform_pca", "calculate_glcm_features", "prepare_level_1_features",
-           "add_spatial_context", "run_feature_extraction_stage", "RsxPCA"]
+           "add_spatial_context", "morphological_gradient", "local_std_dev", "sobel_magnitude", "prepare_level_2_features",
+           "run_feature_extraction_stage", "RsxPCA"]
 
 _DEFAULT_ANGLES = [0, np.pi / 4, np.pi / 2, 3 * np.pi / 4]
 
@@ -263,6 +264,65 @@ def add_spatial_context(features_array, window_size=7):
     return np.concatenate([features_array, ctx.astype(np.float64)], axis=-1)
 
 
+# ------------------------------------------------------------------------------------------- N2: level-2 stencil channels
+def _second_normalisation(band):
+    """robust_normalize(band) as every texture function of the reference does first; returns (float32 device plane, uint8
+    device plane = (plane * 255).astype(uint8), shape)."""
+    band = np.asarray(band)
+    x = _dev32(band).reshape(-1)
+    lo, hi, den = _norm_params_device(x, 2, 98)
+    xf = _out_like(x)
+    _lib.call("rsx_normalize_f32", ptr(x), x.numel(), float(lo), float(hi), float(den), ptr(xf), stream_ptr())
+    xq = torch.empty((x.numel() + 3) // 4 * 4, dtype=torch.uint8, device="cuda")
+    _lib.call("rsx_quantize_f32", ptr(x), x.numel(), float(lo), float(hi), float(den), 256, ptr(xq), stream_ptr())
+    return xf, xq, band.shape
+
+
+def morphological_gradient(band, size=5):
+    """calculate_morphological_features(band)['gradient_<size>'] (indices.py:408-440): float64 map gradient / 255.0."""
+    require_cuda()
+    xf, xq, (H, W) = _second_normalisation(band)
+    g = torch.empty(H * W, dtype=torch.uint8, device="cuda")
+    _lib.call("rsx_morph_gradient_u8", ptr(xq), H, W, 0, H, ptr(g), 0, H, int(size), stream_ptr())
+    return g.cpu().numpy().reshape(H, W) / 255.0
+
+
+def local_std_dev(band, scale=5):
+    """calculate_multi_scale_features(band)['std_dev_scale_<scale>'] (indices.py:531-548): float32 map."""
+    require_cuda()
+    xf, xq, (H, W) = _second_normalisation(band)
+    out = _out_like(xf)
+    _lib.call("rsx_local_std_f32", ptr(xf), H, W, 0, H, ptr(out), 0, H, int(scale), None, stream_ptr())
+    return out.cpu().numpy().reshape(H, W)
+
+
+def sobel_magnitude(band):
+    """calculate_filter_responses(band)['sobel_mag'] (indices.py:455-480): float32 map in [0, 1]."""
+    require_cuda()
+    from .device import MinMaxTracker
+    xf, xq, (H, W) = _second_normalisation(band)
+    out = _out_like(xf)
+    mm = MinMaxTracker(1)
+    _lib.call("rsx_sobel_mag_u8", ptr(xq), H, W, 0, H, ptr(out), 0, H, ptr(mm.buf), stream_ptr())
+    den = np.float32(mm.read()[1][0]) + 1e-10
+    _lib.call("rsx_divide_f32", ptr(out), H * W, float(np.float32(den)), stream_ptr())
+    return out.cpu().numpy().reshape(H, W)
+
+
+def prepare_level_2_features(features_dict):
+    """indices.py:837-865 (host glue): [glcm contrast, glcm homogeneity, gradient_5, std_dev_scale_5, sobel_mag]."""
+    maps = []
+    if "glcm_features" in features_dict:
+        maps += [features_dict["glcm_features"]["contrast"], features_dict["glcm_features"]["homogeneity"]]
+    if "gradient_5" in features_dict.get("morphological_features", {}):
+        maps.append(features_dict["morphological_features"]["gradient_5"])
+    if "std_dev_scale_5" in features_dict.get("multi_scale_features", {}):
+        maps.append(features_dict["multi_scale_features"]["std_dev_scale_5"])
+    if "sobel_mag" in features_dict.get("filter_features", {}):
+        maps.append(features_dict["filter_features"]["sobel_mag"])
+    return np.stack(maps, axis=-1) if maps else np.zeros((1, 1, 1))
+
+
 def run_feature_extraction_stage(bands_data, preprocessing=True, texture_band_index=3):
     """scripts/2_feature_extraction.py:27-133, hot-path part, fused on the device.
 
@@ -270,8 +330,9 @@ def run_feature_extraction_stage(bands_data, preprocessing=True, texture_band_in
     float32).  One H2D copy of the packed raster, K1-K4 on the device, one D2H copy of the maps.  Returns
     (features_dict, hierarchical_features) with the reference's keys for the stages on the hot path: the seven
     indices, 'pca_result', 'variance_ratio', 'glcm_features'; hierarchical_features['level_1'] is the 14-channel
-    float64 stack add_spatial_context(prepare_level_1_features(...)).  The LBP / multi-scale / morphology / filter
-    features (scripts/2...:93-107, level 2) are outside the hot path and are not produced.
+    float64 stack add_spatial_context(prepare_level_1_features(...)); for 8-bit input 'level_2' (5 channels) and 'all'
+    (19 channels, what all_hierarchical_features.npy holds) are produced too.  Of the LBP / multi-scale / morphology /
+    filter dictionaries (scripts/2...:93-107) only the three maps that feed level 2 are computed.
     `texture_band_index` is accepted and ignored, like in the reference (the texture band is always NIR).
     """
     from . import pipeline as P
@@ -284,7 +345,8 @@ def run_feature_extraction_stage(bands_data, preprocessing=True, texture_band_in
     if np.isnan(stack).any() or (stack != np.rint(stack)).any() or stack.min() < 0 or stack.max() > 65535:
         raise _lib.RsxError("run_feature_extraction_stage: bands must hold integer levels in [0, 65535] (stage-1 output)")
     packed = stack.astype(np.uint8) if stack.max() <= 255 else stack.astype(np.uint16).view(np.int16)
-    fr = P.extract_features(torch.from_numpy(np.ascontiguousarray(packed)).cuda(), P.FeatureConfig())
+    raster = torch.from_numpy(np.ascontiguousarray(packed)).cuda()
+    fr = P.extract_features(raster, P.FeatureConfig())
     host = fr.planes[:, :fr.n_px].cpu().numpy().reshape(len(fr.names), H, W)
     get = lambda name: host[fr.names.index(name)]
     features = {k: get(k) for k in P.INDEX_NAMES}
@@ -295,4 +357,15 @@ def run_feature_extraction_stage(bands_data, preprocessing=True, texture_band_in
     # hierarchical['level_1'] = add_spatial_context(prepare_level_1_features(...)) (scripts/2...:112-119), on the device
     l1, l1_names, _ = P.level1_with_context(fr)
     level1 = np.moveaxis(l1[:, :fr.n_px].cpu().numpy().reshape(len(l1_names), H, W), 0, -1).astype(np.float64)
-    return features, {"level_1": level1}
+    hier = {"level_1": level1}
+    if packed.dtype == np.uint8:
+        # level 2 (scripts/2...:115): the two GLCM maps + the three stencil channels; the reference's arrays are float64
+        # (uint8 / 255.0) except std_dev / sobel (float32) - np.stack promotes the stack to float64 either way
+        l2, l2_names, _ = P.level2_planes(raster, fr, P.FeatureConfig())
+        l2h = l2[:, :fr.n_px].cpu().numpy().reshape(len(l2_names), H, W)
+        features["morphological_features"] = {"gradient_5": np.rint(l2h[2].astype(np.float64) * 255.0) / 255.0}
+        features["multi_scale_features"] = {"std_dev_scale_5": l2h[3]}
+        features["filter_features"] = {"sobel_mag": l2h[4]}
+        hier["level_2"] = prepare_level_2_features(features)
+        hier["all"] = np.concatenate([level1, hier["level_2"]], axis=-1)
+    return features, hier

@@ -41,6 +41,10 @@ class FeatureConfig:
     glcm_window: int = 21
     glcm_step: int = 21
     percentiles: Tuple[float, float] = (2, 98)
+    # fuse stage 1 (modules/features/preprocessing.py:54-125: gain/bias -> min-max stretch -> uint8) into the load path: the
+    # raster holds raw 8-bit DNs; (gain, bias) per band, e.g. (hoststats.TM_GAIN, hoststats.TM_BIAS).  None = raster is
+    # already the stage-1 output (what scripts/2_feature_extraction.py reads).
+    stage1: Optional[Tuple[Sequence[float], Sequence[float]]] = None
 
 
 @dataclass
@@ -96,7 +100,15 @@ def extract_features(raster: torch.Tensor, cfg: FeatureConfig = FeatureConfig(),
         hist_host = hist64.cpu().numpy()
     else:
         hist_host = hist.cpu().numpy().view(np.uint32).astype(np.int64)
+    remap = None
+    hist_raw = hist_host
+    if cfg.stage1 is not None:
+        if is16:
+            raise _lib.RsxError("the fused stage-1 chain is defined for 8-bit rasters")
+        remap, hist_host = hoststats.stage1_level_tables(hist_host, cfg.stage1[0], cfg.stage1[1])
+        remap = np.ascontiguousarray(remap)
     stats = hoststats.RasterStats(hist_host, glcm_band=cfg.band_map[3], lower=cfg.percentiles[0], upper=cfg.percentiles[1])
+    stats.hist_raw = hist_raw
 
     n_comp = B if cfg.n_components is None else int(cfg.n_components)
     names = list(INDEX_NAMES) + (["glcm_" + g for g in GLCM_NAMES] if cfg.glcm else []) + [f"pc{i}" for i in range(n_comp)]
@@ -112,8 +124,12 @@ def extract_features(raster: torch.Tensor, cfg: FeatureConfig = FeatureConfig(),
     qnorm = np.ascontiguousarray(stats.qnorm, dtype=np.float32)
     if n_px:
         with timer("indices"):
-            _lib.call(f"rsx_indices_fused_{sfx}", ptr(raster), n_px, B, hptr(band_map), hptr(norm), hptr(evi), ptr(planes), stride,
-                      mm.slot(0), ptr(quant), hptr(qnorm), cfg.glcm_levels, st)
+            if is16:
+                _lib.call("rsx_indices_fused_u16", ptr(raster), n_px, B, hptr(band_map), hptr(norm), hptr(evi), ptr(planes), stride,
+                          mm.slot(0), ptr(quant), hptr(qnorm), cfg.glcm_levels, st)
+            else:
+                _lib.call("rsx_indices_fused_u8", ptr(raster), n_px, B, hptr(band_map), hptr(norm), hptr(evi), ptr(planes), stride,
+                          mm.slot(0), ptr(quant), hptr(qnorm), cfg.glcm_levels, hptr(remap), st)
 
     # ---- K3a PCA moments (+ all-reduce).  The RobustScaler statistics (host, phase 2) are computed while K2 runs; the
     #      moments come back through pinned memory so that the host can do the eigen-decomposition under the GLCM kernel.
@@ -124,7 +140,10 @@ def extract_features(raster: torch.Tensor, cfg: FeatureConfig = FeatureConfig(),
     scale = np.ascontiguousarray(stats.scale, dtype=np.float64)
     lut = None
     if not is16:
-        lut = torch.from_numpy(np.ascontiguousarray(stats.x_lut, dtype=np.float32)).to(dev)
+        x_lut = np.ascontiguousarray(stats.x_lut, dtype=np.float32)
+        if remap is not None:                                   # table of the RAW level: x_lut[b][remap[b][v]]
+            x_lut = np.ascontiguousarray(np.take_along_axis(x_lut, remap.astype(np.int64), axis=1))
+        lut = torch.from_numpy(x_lut).to(dev)
     if n_px:
         with timer("pca_moments"):
             if is16:
@@ -212,6 +231,76 @@ def level1_with_context(fr: FeatureResult, window_size: int = 7, comm: Optional[
             _lib.call("rsx_box_mean_f32", ptr(ext), H_total, fr.W, needs[comm.rank][0], ext.shape[0], ext.numel(),
                       C.c_void_p(out[n + k].data_ptr()), r0, fr.H, out.shape[1], 1, int(window_size), mm.slot(n + k), stream_ptr())
     return out, names, mm
+
+
+# ============================================================================================ level-2 stack
+LEVEL2_NAMES = ("glcm_contrast", "glcm_homogeneity", "gradient_5", "std_dev_scale_5", "sobel_mag")   # indices.py:837-865
+
+
+def level2_planes(raster: torch.Tensor, fr: FeatureResult, cfg: FeatureConfig = FeatureConfig(), comm: Optional[Comm] = None,
+                  H_total: Optional[int] = None, bounds: Optional[Sequence[Tuple[int, int]]] = None, timer: StageTimer = NO_TIMER):
+    """prepare_level_2_features (indices.py:837-865) as a planar float32 device stack: GLCM contrast and homogeneity (already
+    in `fr`), morphological gradient 5x5, local standard deviation 5x5 and the normalised Sobel magnitude of the texture band
+    (calculate_morphological_features :421-440, calculate_multi_scale_features :537-548, calculate_filter_responses :477-480;
+    each starts with its own robust_normalize of the already normalised band, like the GLCM).  uint8 rasters only.
+    Returns (planes (5, stride), names, MinMaxTracker)."""
+    comm = comm or Comm()
+    H_total = H_total if H_total is not None else fr.H
+    bounds = list(bounds) if bounds is not None else [(0, fr.H)]
+    r0, r1 = bounds[comm.rank]
+    if raster.dtype != torch.uint8:
+        raise _lib.RsxError("level2_planes: the stencil features are implemented for 8-bit rasters")
+    if not cfg.glcm:
+        raise _lib.RsxError("level2_planes needs the GLCM planes (FeatureConfig.glcm=True)")
+    dev, st = raster.device, stream_ptr()
+    h, W, B = raster.shape
+    n_px = h * W
+    nir = cfg.band_map[3]
+    # tables of the texture band: second robust_normalize (float32) and its 8-bit quantisation (band * 255).astype(uint8)
+    band2 = hoststats.normalize_levels(fr.stats.norm_lut[nir], *fr.stats.qnorm).astype(np.float32)
+    q255 = (band2 * 255).astype(np.uint8)
+    if cfg.stage1 is not None:
+        remap, _ = hoststats.stage1_level_tables(fr.stats.hist_raw, cfg.stage1[0], cfg.stage1[1])
+        band2, q255 = band2[remap[nir]], q255[remap[nir]]
+    d_band2 = torch.from_numpy(np.ascontiguousarray(band2)).to(dev)
+    d_q255 = torch.from_numpy(np.ascontiguousarray(q255)).to(dev)
+    out = torch.empty((5, fr.planes.shape[1]), dtype=torch.float32, device=dev)
+    mm = MinMaxTracker(5, device=dev)
+    for k, name in enumerate(LEVEL2_NAMES[:2]):
+        i = fr.names.index(name)
+        out[k].copy_(fr.planes[i])
+        mm.buf[k].copy_(fr.minmax.buf[i])
+    if n_px == 0:
+        return out, list(LEVEL2_NAMES), mm
+    xf = torch.empty(n_px, dtype=torch.float32, device=dev)
+    xq = torch.empty(n_px, dtype=torch.uint8, device=dev)
+    with timer("level2_stencils"):
+        _lib.call("rsx_band_lut_f32", ptr(raster), n_px, B, nir, ptr(d_band2), ptr(xf), st)
+        _lib.call("rsx_band_lut_u8", ptr(raster), n_px, B, nir, ptr(d_q255), ptr(xq), st)
+    need2 = [(max(a - 2, 0), min(b + 2, H_total)) if b > a else (0, 0) for a, b in bounds]
+    need1 = [(max(a - 1, 0), min(b + 1, H_total)) if b > a else (0, 0) for a, b in bounds]
+    xq2 = comm.fetch_rows(xq.view(h, W), bounds, need2).contiguous()
+    xf2 = comm.fetch_rows(xf.view(h, W), bounds, need2).contiguous()
+    xq1 = comm.fetch_rows(xq.view(h, W), bounds, need1).contiguous()
+    grad = torch.empty(n_px, dtype=torch.uint8, device=dev)
+    with timer("level2_stencils"):
+        _lib.call("rsx_morph_gradient_u8", ptr(xq2), H_total, W, need2[comm.rank][0], xq2.shape[0], ptr(grad), r0, h, 5, st)
+        _lib.call("rsx_u8_over_255_f32", ptr(grad), n_px, C.c_void_p(out[2].data_ptr()), st)
+        _lib.call("rsx_minmax_planes_f32", C.c_void_p(out[2].data_ptr()), n_px, out.shape[1], 1, mm.slot(2), st)
+        _lib.call("rsx_local_std_f32", ptr(xf2), H_total, W, need2[comm.rank][0], xf2.shape[0], C.c_void_p(out[3].data_ptr()), r0, h, 5,
+                  mm.slot(3), st)
+        _lib.call("rsx_sobel_mag_u8", ptr(xq1), H_total, W, need1[comm.rank][0], xq1.shape[0], C.c_void_p(out[4].data_ptr()), r0, h,
+                  mm.slot(4), st)
+    # sobel_mag / (sobel_mag.max() + 1e-10): the maximum is global (all strips)
+    mn, mx = mm.read()
+    smax = torch.tensor([float(mx[4])], dtype=torch.float32, device=dev)
+    comm.all_reduce(smax, "max")
+    den = np.float32(smax.item()) + 1e-10                      # float32 + Python float stays float32 (NEP 50), as in the reference
+    with timer("level2_stencils"):
+        _lib.call("rsx_divide_f32", C.c_void_p(out[4].data_ptr()), n_px, float(np.float32(den)), st)
+    _lib.call("rsx_minmax_init", mm.slot(4), 1, st)
+    _lib.call("rsx_minmax_planes_f32", C.c_void_p(out[4].data_ptr()), n_px, out.shape[1], 1, mm.slot(4), st)
+    return out, list(LEVEL2_NAMES), mm
 
 
 # ============================================================================================ KMeans

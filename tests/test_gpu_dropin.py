@@ -151,6 +151,41 @@ def test_add_spatial_context_matches_reference(I, aa_crop):
         np.testing.assert_allclose(g, r, rtol=0, atol=2.4e-7 * np.abs(x).max())
 
 
+def test_level2_stencil_channels(I, aa_crop):
+    """N2: gradient_5, std_dev_scale_5, sobel_mag against the reference expressions evaluated with cv2 / numpy."""
+    from oracle import features as of
+    rng = np.random.default_rng(11)
+    bands = [aa_crop["norm"][3], rng.random((45, 77), dtype=np.float32), (rng.integers(0, 40, (33, 130)) / 39.0).astype(np.float32)]
+    for band in bands:
+        g = I.morphological_gradient(band)
+        assert g.dtype == np.float64 and np.array_equal(g, of.morph_gradient(band))
+        for size in (3, 7):
+            assert np.array_equal(I.morphological_gradient(band, size), of.morph_gradient(band, size))
+        sm = I.sobel_magnitude(band)
+        assert sm.dtype == np.float32 and np.array_equal(sm, of.sobel_mag(band))
+        sd, ref = I.local_std_dev(band), of.std_dev_scale(band)
+        assert sd.dtype == np.float32
+        # variance = mean_sq - mean^2 cancels: a 1-ulp difference of a mean (double running sums in OpenCV vs direct sums)
+        # shows up as ~sqrt(1e-7) where the variance is ~0; elsewhere the maps agree to float32 rounding
+        assert np.abs(sd - ref).max() < 1e-3 and (np.abs(sd - ref) <= 1e-6 * np.maximum(ref, 1e-3)).mean() > 0.995
+
+
+def test_run_feature_extraction_stage_hierarchical_all(I, aa_crop):
+    """The (H, W, 19) float64 stack the reference saves as all_hierarchical_features.npy (scripts/2...:123-127)."""
+    from oracle import features as of
+    from oracle import glcm as og
+    feats, hier = I.run_feature_extraction_stage(_bands(aa_crop))
+    assert hier["level_2"].shape == aa_crop["level1"].shape[:2] + (5,) and hier["level_2"].dtype == np.float64
+    assert hier["all"].shape[-1] == 19 and hier["all"].dtype == np.float64
+    nir = aa_crop["norm"][3]
+    ref = of.level2_stack(og.glcm_features(nir, 32, 21, 21), nir)
+    np.testing.assert_allclose(hier["level_2"][..., :2], ref[..., :2], rtol=1e-5, atol=1e-6)
+    assert np.array_equal(hier["level_2"][..., 2], ref[..., 2])
+    assert np.abs(hier["level_2"][..., 3] - ref[..., 3]).max() < 1e-3
+    assert np.array_equal(hier["level_2"][..., 4], ref[..., 4].astype(np.float64))
+    assert np.array_equal(hier["all"][..., :14], hier["level_1"])
+
+
 # ------------------------------------------------------------------------------------------- KMeans drop-in
 def _ix_dict(aa_crop, dtype):
     names = ("ndvi", "evi", "msavi", "ndwi", "mndwi", "ndbi", "bsi")

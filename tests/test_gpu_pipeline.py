@@ -246,3 +246,27 @@ def test_kmeans_empty_cluster_relocation_matches_sklearn(P, dups):
     else:                                                              # several: same partition quality, every cluster populated
         assert len(np.unique(got)) == K
         assert abs(res.inertia - ref.inertia_) <= 0.05 * ref.inertia_
+
+
+def test_stage1_fused_into_load_path(P):
+    """N3: raw 8-bit DNs + FeatureConfig.stage1 == the reference's stage 1 (gain/bias, min-max stretch, uint8) followed by
+    the normal path: every plane, the quantised band and the PCA are bit-identical."""
+    import torch
+    from oracle import features as of
+    from rs_image_segmentation_b200 import hoststats
+    from rs_image_segmentation_b200.synth import synth_raster_numpy
+    raw = synth_raster_numpy(111, 173, 7, np.uint8, 31, cell=16)
+    raw[..., 2] = (raw[..., 2] // 3) + 20                                # a band that does not span 0..255
+    stage1 = np.stack(of.stage1_preprocess([raw[..., b] for b in range(7)]), axis=-1)
+    cfg = P.FeatureConfig(glcm_window=7, glcm_step=1)
+    ref = P.extract_features(torch.from_numpy(np.ascontiguousarray(stage1)).cuda(), cfg)
+    cfg1 = P.FeatureConfig(glcm_window=7, glcm_step=1, stage1=(hoststats.TM_GAIN, hoststats.TM_BIAS))
+    got = P.extract_features(torch.from_numpy(raw).cuda(), cfg1)
+    assert torch.equal(got.quant[:got.n_px], ref.quant[:ref.n_px])
+    assert np.array_equal(got.pca["components"], ref.pca["components"])
+    for name in ref.names:
+        assert torch.equal(got.plane(name), ref.plane(name)), name
+    remap, hist1 = hoststats.stage1_level_tables(np.stack([np.bincount(raw[..., b].ravel(), minlength=256) for b in range(7)]))
+    for b in range(7):
+        assert np.array_equal(remap[b][raw[..., b]], stage1[..., b])
+        assert np.array_equal(hist1[b], np.bincount(stage1[..., b].ravel(), minlength=256))

@@ -90,3 +90,20 @@ def test_float_band_order():
     lo = hs.float_band_order(x)
     for q in (2, 98):
         assert lo.percentile_scalar(q) == np.percentile(x, q)
+
+
+def test_stage1_level_tables_match_reference_chain():
+    """The fused stage-1 tables against the restated chain (and, through the golden file, against the reference itself:
+    tests/golden/aa_full_stats.npz records the SHA-256 of the stage-1 output the reference functions produced)."""
+    from oracle import features as of
+    from rs_image_segmentation_b200 import hoststats
+    rng = np.random.default_rng(0)
+    raw = [rng.integers(lo, hi, size=(40, 50)).astype(np.uint8) for lo, hi in ((0, 256), (10, 200), (3, 4), (100, 255), (0, 2), (7, 90), (50, 60))]
+    ref = of.stage1_preprocess(raw)
+    hist = np.stack([np.bincount(r.ravel(), minlength=256) for r in raw])
+    remap, hist1 = hoststats.stage1_level_tables(hist)
+    for b in range(7):
+        if raw[b].min() == raw[b].max():
+            continue                                                    # 0/0: the reference produces NaN -> undefined uint8
+        assert np.array_equal(remap[b][raw[b]], ref[b]), b
+        assert np.array_equal(hist1[b], np.bincount(ref[b].ravel(), minlength=256)), b
