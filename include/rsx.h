@@ -161,6 +161,12 @@ int rsx_divide_f32(float* d_plane, int64_t n, float denominator, rsx_stream_t st
 /* plane[i] = (float)(in[i] / 255.0): uint8 maps enter the float32 stack (the reference keeps them as float64 k/255.0) */
 int rsx_u8_over_255_f32(const uint8_t* d_in, int64_t n, float* d_out, rsx_stream_t stream);
 
+/* N4: output layouts.  (H, W, C) float64 C-order = the payload of the reference's .npy files (scripts/2_feature_extraction.py:
+ * 193-214) from the planar float32 stack; label image + 1 as uint8 for the GeoTIFF writer (scripts/3_classification.py:394,
+ * extract.py:795-807). */
+int rsx_planes_to_hwc_f64(const float* d_planes, int64_t plane_stride, int64_t n_px, int n_channels, double* d_out, rsx_stream_t stream);
+int rsx_labels_plus1_u8(const int32_t* d_labels, int64_t n, uint8_t* d_out, rsx_stream_t stream);
+
 /* ---- min/max trackers (MinMaxScaler.fit, sklearn/preprocessing/_data.py:527-541) --------------- */
 int rsx_minmax_init(uint32_t* d_minmax, int n, rsx_stream_t stream);
 int rsx_minmax_planes_f32(const float* d_planes, int64_t n_px, int64_t plane_stride, int n_planes, uint32_t* d_minmax,

@@ -230,3 +230,54 @@ extern "C" int rsx_u8_over_255_f32(const uint8_t* d_in, int64_t n, float* d_out,
     u8_over_255_kernel<<<(int)min((int64_t)rsx_num_sms() * 8, ceil_div(n, (int64_t)256)), 256, 0, (cudaStream_t)stream>>>(d_in, n, d_out);
     return rsx_check_launch("u8_over_255");
 }
+
+// ----------------------------------------------------------------------------- N4: output layouts of the reference's files
+// all_hierarchical_features.npy / level{1,2}_features.npy are (H, W, C) float64 C-order (scripts/2_feature_extraction.py:
+// 193-214): planar float32 planes -> pixel-interleaved float64, i.e. the exact payload bytes of the .npy file.
+// A CTA transposes 32 pixels x C channels through shared memory so that both sides are coalesced.
+__global__ void __launch_bounds__(256) planes_to_hwc_f64_kernel(const float* __restrict__ planes, int64_t plane_stride, int64_t n_px, int C,
+                                                                double* __restrict__ out) {
+    extern __shared__ float tile[];  // [C][256 + 1]
+    const int64_t tiles = (n_px + 255) / 256;
+    for (int64_t tb = blockIdx.x; tb < tiles; tb += gridDim.x) {
+        const int64_t p0 = tb * 256;
+        const int np = (int)min((int64_t)256, n_px - p0);
+        for (int c = 0; c < C; ++c)
+            if ((int)threadIdx.x < np) tile[c * 257 + threadIdx.x] = planes[c * plane_stride + p0 + threadIdx.x];
+        __syncthreads();
+        for (int i = threadIdx.x; i < np * C; i += 256) {
+            const int p = i / C, c = i - p * C;
+            out[p0 * C + i] = (double)tile[c * 257 + p];
+        }
+        __syncthreads();
+    }
+}
+
+extern "C" int rsx_planes_to_hwc_f64(const float* d_planes, int64_t plane_stride, int64_t n_px, int n_channels, double* d_out, rsx_stream_t stream) {
+    RSX_REQUIRE(d_planes && d_out && n_px > 0 && n_channels >= 1 && n_channels <= 64, "rsx_planes_to_hwc_f64: bad arguments");
+    const size_t smem = (size_t)n_channels * 257 * 4;
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(planes_to_hwc_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            rsx_set_error("rsx_planes_to_hwc_f64: %s", cudaGetErrorString(e));
+            return RSX_ERR_CUDA;
+        }
+        configured = smem;
+    }
+    const int grid = (int)min((int64_t)rsx_num_sms() * 4, ceil_div(n_px, (int64_t)256));
+    planes_to_hwc_f64_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(d_planes, plane_stride, n_px, n_channels, d_out);
+    return rsx_check_launch("planes_to_hwc_f64");
+}
+
+// final_classification_map = kmeans_result + 1 (scripts/3_classification.py:394) cast to uint8 for the label GeoTIFF
+// (extract.py:795-807, nodata 0)
+__global__ void __launch_bounds__(256) labels_plus1_u8_kernel(const int32_t* __restrict__ lab, int64_t n, uint8_t* __restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (uint8_t)(lab[i] + 1);
+}
+
+extern "C" int rsx_labels_plus1_u8(const int32_t* d_labels, int64_t n, uint8_t* d_out, rsx_stream_t stream) {
+    RSX_REQUIRE(d_labels && d_out && n > 0, "rsx_labels_plus1_u8: bad arguments");
+    labels_plus1_u8_kernel<<<(int)min((int64_t)rsx_num_sms() * 8, ceil_div(n, (int64_t)256)), 256, 0, (cudaStream_t)stream>>>(d_labels, n, d_out);
+    return rsx_check_launch("labels_plus1_u8");
+}

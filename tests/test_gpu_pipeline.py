@@ -270,3 +270,26 @@ def test_stage1_fused_into_load_path(P):
     for b in range(7):
         assert np.array_equal(remap[b][raw[..., b]], stage1[..., b])
         assert np.array_equal(hist1[b], np.bincount(stage1[..., b].ravel(), minlength=256))
+
+
+def test_device_writers(P, tmp_path):
+    """N4: the .npy file produced from the device stack is byte-identical to np.save of the float64 (H, W, C) array, and the
+    label map is kmeans_result + 1 as uint8."""
+    import io
+    import torch
+    from rs_image_segmentation_b200 import writers
+    from rs_image_segmentation_b200.synth import synth_raster_numpy
+    H, W = 67, 93
+    bip = synth_raster_numpy(H, W, 7, np.uint8, 2, cell=16)
+    fr = P.extract_features(torch.from_numpy(bip).cuda(), P.FeatureConfig(glcm_window=5, glcm_step=1))
+    for C in (1, 7, len(fr.names)):
+        path = str(tmp_path / f"stack{C}.npy")
+        writers.save_stack_npy(path, fr.planes, fr.n_px, H, W, C)
+        ref = np.moveaxis(fr.planes[:C, :fr.n_px].cpu().numpy().reshape(C, H, W), 0, -1).astype(np.float64)
+        buf = io.BytesIO()
+        np.save(buf, ref)
+        assert open(path, "rb").read() == buf.getvalue()
+        assert np.array_equal(np.load(path), ref)
+    res, km, c0 = P.kmeans_on_features(fr, 13, 6, 3, seed=1)
+    lab8 = writers.labels_for_geotiff(res.labels, H, W)
+    assert lab8.dtype == np.uint8 and np.array_equal(lab8, (res.labels.cpu().numpy().reshape(H, W) + 1).astype(np.uint8))
