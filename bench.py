@@ -41,10 +41,12 @@ def peaks():
 
 
 class ClockSampler:
-    """SM clock + throttle reasons sampled DURING the timed region.  NVML in a thread (a polling `nvidia-smi -lms` child
-    takes driver locks and was measured to stretch the timed region by milliseconds); nvidia-smi once as a fallback."""
+    """SM clock + throttle reasons sampled DURING the timed region.  NVML in a thread, two cheap queries every 100 ms: every
+    NVML / nvidia-smi query takes driver locks that stall kernel launches (a polling `nvidia-smi -lms 100` child stretched
+    a 20 ms step to 37 ms, NVML every 20 ms a 2-GPU step to 40 ms), so the sampling is kept sparse; nvidia-smi once as a
+    fallback."""
 
-    def __init__(self, gpu_index: int, period_s: float = 0.02):
+    def __init__(self, gpu_index: int, period_s: float = 0.1):
         self.idx, self.period = gpu_index, period_s
         self.sm, self.mx, self.reasons = [], [], set()
         self.thread, self.stop_flag, self.nvml = None, threading.Event(), None
@@ -72,7 +74,8 @@ class ClockSampler:
     def _sample(self):
         n = self.nvml
         self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
-        self.mx.append(float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        if not self.mx:
+            self.mx.append(float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)))
         r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
             else n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
         for name, bit in (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40),
@@ -81,6 +84,7 @@ class ClockSampler:
                 self.reasons.add(name)
 
     def _loop(self):
+        self.stop_flag.wait(0.01)                               # first sample once the first timed step is in flight
         while not self.stop_flag.is_set():
             try:
                 self._sample()

@@ -95,8 +95,9 @@ def extract_features(raster: torch.Tensor, cfg: FeatureConfig = FeatureConfig(),
         with timer("hist"):
             _lib.call(f"rsx_hist_{sfx}", ptr(raster), n_px, B, ptr(hist), st)
     if comm.world > 1:
-        hist64 = hist.to(torch.int64) & 0xFFFFFFFF      # the kernel's counters are uint32
-        comm.all_reduce(hist64)
+        with timer("hist_allreduce"):
+            hist64 = hist.to(torch.int64) & 0xFFFFFFFF      # the kernel's counters are uint32
+            comm.all_reduce(hist64)
         hist_host = hist64.cpu().numpy()
     else:
         hist_host = hist.cpu().numpy().view(np.uint32).astype(np.int64)
@@ -150,7 +151,9 @@ def extract_features(raster: torch.Tensor, cfg: FeatureConfig = FeatureConfig(),
                 _lib.call("rsx_pca_moments_u16", ptr(raster), n_px, B, hptr(norm), hptr(center), hptr(scale), ptr(moments), ptr(scratch), st)
             else:
                 _lib.call("rsx_pca_moments_u8", ptr(raster), n_px, B, ptr(lut), ptr(moments), ptr(scratch), st)
-    comm.all_reduce(moments)
+    if comm.world > 1:
+        with timer("pca_allreduce"):
+            comm.all_reduce(moments)
     moments_host = torch.empty(M, dtype=torch.float64, pin_memory=True)
     moments_host.copy_(moments, non_blocking=True)
     moments_ready = torch.cuda.Event()
@@ -166,7 +169,8 @@ def extract_features(raster: torch.Tensor, cfg: FeatureConfig = FeatureConfig(),
         needs = [glcm_rows_needed(b, H_total, w, s) for b in bounds]
         (p0, p1), _ = needs[comm.rank]
         q_local = quant[:n_px].view(h, W)
-        q_ext = comm.fetch_rows(q_local, bounds, [qr for _, qr in needs])
+        with timer("glcm_halo"):
+            q_ext = comm.fetch_rows(q_local, bounds, [qr for _, qr in needs])
         if p1 > p0:
             props = torch.empty((5, _pad4((p1 - p0) * out_cols)), dtype=torch.float32, device=dev)
             with timer("glcm_props"):
@@ -415,7 +419,9 @@ class DeviceKMeans:
             with self.timer("kmeans_assign_delta" if mode == 2 else "kmeans_assign_full"):
                 _lib.call("rsx_kmeans_assign", ptr(self.planes), self.stride, self.n_px, self.row_len, ptr(self.state), ptr(self.acc),
                           ptr(cur), ptr(prev), None, None, mode, self.D, self.K, stream_ptr())
-        self.comm.all_reduce(self.acc[:self.n_acc])
+        if self.comm.world > 1:
+            with self.timer("kmeans_allreduce"):
+                self.comm.all_reduce(self.acc[:self.n_acc])
         return mode
 
     def update(self, mode: int, adjust: Optional[torch.Tensor] = None):
