@@ -11,6 +11,8 @@
 //     energy        = sqrt(sum_cells P^2) = sqrt(E)/2n, E = sum_s (a!=b ? 2 U[{a,b}] : 4 U[{a,a}])
 // where U[{a,b}] counts the pairs of the window whose UNORDERED levels are {a,b}.  All sums are exact
 // integers; only E needs the histogram, and it needs it only at the cells the window touches.
+#include <cstdlib>
+
 #include "rsx_common.cuh"
 
 __constant__ double g_homog[256];  // 1/(1+k^2)
@@ -167,10 +169,12 @@ struct DenseShared {
     const unsigned long long* homog_fx;
 };
 
-template <int WIN, int NT, int ANG>
+// WIDE (levels > 32): sum of a^2+b^2 needs its own 32-bit word, so the sum of a+b moves into the u64:
+//   narrow: W1 = s1 | sab << 13,  W2 = sa | sq << 14,  SH = homog * 2^40 | Neq << 52
+//   wide:   W1 = s1 | sab << 13,  W2 = sq,             SH = homog * 2^36 | Neq << 43 | sa << 50
+template <int WIN, int NT, int ANG, bool WIDE>
 __device__ __forceinline__ void glcm_dense_body(const DenseShared sm, const uint8_t* __restrict__ q, int W, int L, int out_cols, int i_begin, int i_end,
-                                                int j0, int t, float* __restrict__ props, int64_t plane_stride) {
-    constexpr int NTW = NT - (WIN - 1);
+                                                int j0, int t, int NTW, float* __restrict__ props, int64_t plane_stride) {
     constexpr int RING = WIN + 1;
     constexpr int DR = ANG == 0 ? 0 : 1;
     constexpr int DC = ANG == 0 ? 1 : (ANG == 1 ? 1 : (ANG == 2 ? 0 : -1));
@@ -195,8 +199,13 @@ __device__ __forceinline__ void glcm_dense_body(const DenseShared sm, const uint
     auto pair_terms = [&](int a, int b, unsigned& w1, unsigned& w2, unsigned long long& sh) {
         const int d = abs(a - b);
         w1 = (unsigned)d + ((unsigned)(a * b) << 13);
-        w2 = (unsigned)(a + b) + ((unsigned)(a * a + b * b) << 14);
-        sh = sm.homog_fx[d];  // 2^40/(1+d^2), plus 2^52 when d == 0 (the Neq field)
+        if (WIDE) {
+            w2 = (unsigned)(a * a + b * b);
+            sh = sm.homog_fx[d] + ((unsigned long long)(a + b) << 50);
+        } else {
+            w2 = (unsigned)(a + b) + ((unsigned)(a * a + b * b) << 14);
+            sh = sm.homog_fx[d];  // scaled 1/(1+d^2), plus the Neq unit when d == 0
+        }
     };
     // pairs of this angle anchored in ring slot sa (partner row in slot sb) become complete: column sums + cell id
     auto enter_pairs = [&](int sa, int sb) {
@@ -300,13 +309,13 @@ __device__ __forceinline__ void glcm_dense_body(const DenseShared sm, const uint
                 sh += (unsigned long long)v.z | ((unsigned long long)v.w << 32);
             }
             const int s1 = (int)(w1 & 0x1fffu), sab = (int)(w1 >> 13);
-            const int sa = (int)(w2 & 0x3fffu), sq = (int)(w2 >> 14);
-            const int neq = (int)(sh >> 52);
-            const unsigned long long shom = sh & ((1ull << 52) - 1ull);
+            const int sa = WIDE ? (int)(sh >> 50) : (int)(w2 & 0x3fffu), sq = WIDE ? (int)w2 : (int)(w2 >> 14);
+            const int neq = WIDE ? (int)((sh >> 43) & 0x7fu) : (int)(sh >> 52);
+            const unsigned long long shom = sh & ((1ull << (WIDE ? 43 : 52)) - 1ull);
             float* o = sm.outx + ANG * 5 * NT + t;
             o[0 * NT] = (float)(sq - 2 * sab) * inv_n;
             o[1 * NT] = (float)s1 * inv_n;
-            o[2 * NT] = (float)((double)shom * 9.094947017729282e-13) * inv_n;  // 2^-40
+            o[2 * NT] = (float)((double)shom * (WIDE ? 1.4551915228366852e-11 : 9.094947017729282e-13)) * inv_n;  // 2^-36 / 2^-40
             o[3 * NT] = sqrtf((float)(e + 2 * NPAIR + 2 * neq)) * (0.5f * inv_n);
             const int var_num = 2 * NPAIR * sq - sa * sa, cov_num = 4 * NPAIR * sab - sa * sa;
             o[4 * NT] = var_num <= 0 ? 1.f : (float)cov_num / (float)var_num;
@@ -341,10 +350,10 @@ __device__ __forceinline__ void glcm_dense_body(const DenseShared sm, const uint
     }
 }
 
-template <int WIN, int NT>
+template <int WIN, int NT, bool WIDE>
 __global__ void __launch_bounds__(NT * 4) glcm_dense_kernel(const uint8_t* __restrict__ q, int W, int L, int out_rows, int out_cols, int rows_per_cta,
-                                                            float* __restrict__ props, int64_t plane_stride) {
-    constexpr int NTW = NT - (WIN - 1);  // windows per CTA
+                                                            int NTW, float* __restrict__ props, int64_t plane_stride) {
+    // NTW = windows per CTA, <= NT - (WIN - 1), capped by what the private counters leave of shared memory
     constexpr int RING = WIN + 1;
     extern __shared__ __align__(16) unsigned char dsm[];
     __shared__ unsigned long long homog_fx[64];
@@ -368,35 +377,40 @@ __global__ void __launch_bounds__(NT * 4) glcm_dense_kernel(const uint8_t* __res
 
     for (int i = tid; i < 4 * ncell * NTW; i += 4 * NT) sm.cnt[i] = 0;
     for (int i = tid; i < 4 * (WIN + NT); i += 4 * NT) sm.base[i] = 0xfffffff0u;
-    if (tid < 64)  // 2^40/(1+k^2); the k == 0 entry also counts the pair in the Neq field (bit 52)
-        homog_fx[tid] = (unsigned long long)(1099511627776.0 / (1.0 + (double)tid * (double)tid) + 0.5) + (tid == 0 ? (1ull << 52) : 0ull);
+    if (tid < 64)  // 2^40 (wide: 2^36) / (1+k^2); the k == 0 entry also counts the pair in the Neq field
+        homog_fx[tid] = (unsigned long long)((WIDE ? 68719476736.0 : 1099511627776.0) / (1.0 + (double)tid * (double)tid) + 0.5) +
+                        (tid == 0 ? (1ull << (WIDE ? 43 : 52)) : 0ull);
     __syncthreads();
     switch (ang) {  // warp-uniform
-        case 0: glcm_dense_body<WIN, NT, 0>(sm, q, W, L, out_cols, i_begin, i_end, j0, t, props, plane_stride); break;
-        case 1: glcm_dense_body<WIN, NT, 1>(sm, q, W, L, out_cols, i_begin, i_end, j0, t, props, plane_stride); break;
-        case 2: glcm_dense_body<WIN, NT, 2>(sm, q, W, L, out_cols, i_begin, i_end, j0, t, props, plane_stride); break;
-        default: glcm_dense_body<WIN, NT, 3>(sm, q, W, L, out_cols, i_begin, i_end, j0, t, props, plane_stride); break;
+        case 0: glcm_dense_body<WIN, NT, 0, WIDE>(sm, q, W, L, out_cols, i_begin, i_end, j0, t, NTW, props, plane_stride); break;
+        case 1: glcm_dense_body<WIN, NT, 1, WIDE>(sm, q, W, L, out_cols, i_begin, i_end, j0, t, NTW, props, plane_stride); break;
+        case 2: glcm_dense_body<WIN, NT, 2, WIDE>(sm, q, W, L, out_cols, i_begin, i_end, j0, t, NTW, props, plane_stride); break;
+        default: glcm_dense_body<WIN, NT, 3, WIDE>(sm, q, W, L, out_cols, i_begin, i_end, j0, t, NTW, props, plane_stride); break;
     }
 }
 
-template <int WIN, int NT>
-static int launch_dense(const uint8_t* d_q, int W, int levels, int out_rows, int out_cols, float* d_props, int64_t plane_stride, cudaStream_t s) {
-    constexpr int NTW = NT - (WIN - 1);
+static size_t dense_smem_bytes(int win, int nt, int ntw, int ncell) {
+    return (size_t)4 * ncell * ntw + (size_t)nt * (16 * (win + 1) + 16 + 64 + 80 + (win + 1)) + 16 * win + 64;
+}
+
+template <int WIN, int NT, bool WIDE>
+static int launch_dense(const uint8_t* d_q, int W, int levels, int ntw, int out_rows, int out_cols, float* d_props, int64_t plane_stride, cudaStream_t s) {
     const int ncell = levels * (levels + 1) / 2;
-    const size_t smem = (size_t)4 * ncell * NTW + (size_t)4 * (WIN + 1) * NT * 4 + (size_t)16 * (NT + WIN) + (size_t)16 * NT * 4 + (size_t)20 * NT * 4 + (size_t)(WIN + 1) * NT + 64;
+    const size_t smem = dense_smem_bytes(WIN, NT, ntw, ncell);
+    auto kern = glcm_dense_kernel<WIN, NT, WIDE>;
     static size_t configured = 0;
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(glcm_dense_kernel<WIN, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max(smem, (size_t)49152));
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max(smem, (size_t)49152));
         if (e != cudaSuccess) {
             rsx_set_error("rsx_glcm_props: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
             return RSX_ERR_CUDA;
         }
         configured = smem;
     }
-    const int gx = ceil_div(out_cols, NTW);
+    const int gx = ceil_div(out_cols, ntw);
     // rows per CTA: balance whole waves over the SMs against the (WIN-1)-row prologue every CTA pays
     int occ = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, glcm_dense_kernel<WIN, NT>, NT * 4, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT * 4, smem);
     occ = max(occ, 1);
     const int slots = rsx_num_sms() * occ;
     int best_gy = 1;
@@ -410,19 +424,38 @@ static int launch_dense(const uint8_t* d_q, int W, int levels, int out_rows, int
     }
     const int rows_per_cta = ceil_div(out_rows, best_gy);
     const int gy = ceil_div(out_rows, rows_per_cta);
-    glcm_dense_kernel<WIN, NT><<<dim3(gx, gy), NT * 4, smem, s>>>(d_q, W, levels, out_rows, out_cols, rows_per_cta, d_props, plane_stride);
+    kern<<<dim3(gx, gy), NT * 4, smem, s>>>(d_q, W, levels, out_rows, out_cols, rows_per_cta, ntw, d_props, plane_stride);
     return rsx_check_launch("glcm_dense");
 }
 
-// pick the widest CTA whose private counters fit in shared memory
-template <int WIN>
+// pick the widest CTA whose private counters fit in shared memory (and whose counter offsets fit the 16-bit code field)
+template <int WIN, bool WIDE>
 static int dispatch_dense(const uint8_t* d_q, int W, int levels, int out_rows, int out_cols, float* d_props, int64_t plane_stride, cudaStream_t s) {
     const int ncell = levels * (levels + 1) / 2;
-    auto fits = [&](int nt) { return (size_t)4 * ncell * (nt - (WIN - 1)) + (size_t)nt * (16 * (WIN + 1) + 16 + 64 + 80 + (WIN + 1)) + 16 * WIN + 64 <= (size_t)224 * 1024; };
-    if (fits(256)) return launch_dense<WIN, 256>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, s);
-    if (fits(128)) return launch_dense<WIN, 128>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, s);
-    if (fits(96)) return launch_dense<WIN, 96>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, s);
-    if (fits(64)) return launch_dense<WIN, 64>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, s);
+    const size_t limit = (size_t)226 * 1024;
+    auto windows = [&](int nt) {  // windows per CTA for this width (0 = does not fit)
+        int ntw = nt - (WIN - 1);
+        while (ntw > 0 && (dense_smem_bytes(WIN, nt, ntw, ncell) > limit || (size_t)ncell * ntw > 65535)) --ntw;
+        return ntw;
+    };
+    // a narrower CTA wastes fewer columns per window but has fewer warps; prefer the widest that keeps >= 3/4 of its windows
+    static int forced = -1;
+    if (forced < 0) {
+        const char* e = getenv("RSX_GLCM_NT");
+        forced = e ? atoi(e) : 0;
+    }
+    const int nts[4] = {256, 128, 96, 64};
+    for (int k = 0; k < 4; ++k) {
+        const int nt = nts[k], ntw = windows(nt);
+        if (forced ? (nt == forced && ntw >= 8) : (ntw * 4 >= (nt - (WIN - 1)) * 3)) {
+            if (nt == 256) return launch_dense<WIN, 256, WIDE>(d_q, W, levels, ntw, out_rows, out_cols, d_props, plane_stride, s);
+            if (nt == 128) return launch_dense<WIN, 128, WIDE>(d_q, W, levels, ntw, out_rows, out_cols, d_props, plane_stride, s);
+            if (nt == 96) return launch_dense<WIN, 96, WIDE>(d_q, W, levels, ntw, out_rows, out_cols, d_props, plane_stride, s);
+            return launch_dense<WIN, 64, WIDE>(d_q, W, levels, ntw, out_rows, out_cols, d_props, plane_stride, s);
+        }
+    }
+    const int ntw = windows(32);
+    if (ntw >= 8) return launch_dense<WIN, 32, WIDE>(d_q, W, levels, ntw, out_rows, out_cols, d_props, plane_stride, s);
     return -1;
 }
 
@@ -437,17 +470,19 @@ extern "C" int rsx_glcm_props(const uint8_t* d_q, int rows_avail, int W, int lev
     if (int rc = ensure_homog()) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     const int ncell = levels * (levels + 1) / 2;
-    // dense fast path: packed moments need levels <= 32 and window <= 12; uint8 counters hold w(w-1) <= 132
-    if (step == 1 && levels <= 32) {
+    // dense fast path: packed integer moments hold for levels <= 64 and window <= 11; uint8 counters hold w(w-1) <= 110
+    if (step == 1 && levels <= 64) {
         int rc = -1;
+#define DENSE(WW)                                                                                                    \
+    case WW:                                                                                                         \
+        rc = levels <= 32 ? dispatch_dense<WW, false>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, s)  \
+                          : dispatch_dense<WW, true>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, s);  \
+        break;
         switch (window) {
-            case 3: rc = dispatch_dense<3>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, s); break;
-            case 5: rc = dispatch_dense<5>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, s); break;
-            case 7: rc = dispatch_dense<7>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, s); break;
-            case 9: rc = dispatch_dense<9>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, s); break;
-            case 11: rc = dispatch_dense<11>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, s); break;
+            DENSE(3) DENSE(5) DENSE(7) DENSE(9) DENSE(11)
             default: break;
         }
+#undef DENSE
         if (rc >= 0) return rc;
     }
     const size_t smem = (size_t)4 * ncell * 4;

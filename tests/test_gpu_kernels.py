@@ -187,3 +187,18 @@ def test_resize_strip_equals_whole(rsx):
         rsx.call("rsx_resize_bilinear_f32", ptr(_dev(src[:, a:b])), 40, 30, a, b - a, (b - a) * 30, ptr(part), H, W, r0, r1 - r0,
                  (r1 - r0) * W, 1, None, stream_ptr())
         assert np.array_equal(part.reshape(r1 - r0, W).cpu().numpy(), whole[r0:r1])
+
+
+@pytest.mark.parametrize("levels,win", [(64, 7), (64, 5), (64, 11), (48, 9), (33, 3)])
+def test_glcm_dense_wide_levels(levels, win):
+    """Dense GLCM with more than 32 grey levels (wide packed moments, capped windows per CTA) against the oracle."""
+    import torch
+    from oracle import glcm as og
+    from rs_image_segmentation_b200 import indices as I
+    rng = np.random.default_rng(levels + win)
+    yy, xx = np.mgrid[0:83, 0:147]
+    band = (0.5 + 0.35 * np.sin(yy / 9.0) * np.cos(xx / 13.0) + 0.15 * rng.random((83, 147))).astype(np.float32)
+    got = I.calculate_glcm_features(band, levels=levels, window_size=win, step_size=1)
+    ref = og.glcm_features(band, levels, win, 1)
+    for k in ref:
+        np.testing.assert_allclose(got[k], ref[k], rtol=1e-5, atol=1e-6, err_msg=f"{k} L={levels} w={win}")
