@@ -102,15 +102,19 @@ int rsx_quantize_f32(const float* d_in, int64_t n, float lo, float hi, float den
 int64_t rsx_pca_scratch_elems(int n_bands);
 int rsx_pca_moments_u8(const uint8_t* d_raster, int64_t n_px, int n_bands, const float* d_lut, double* d_moments,
                        double* d_scratch, rsx_stream_t stream);
+/* d_lut16 (may be NULL): float [B][65536] on the device made by rsx_pca_build_lut_u16 - X tabulated per 16-bit level with
+ * the per-sample arithmetic, so that a sample costs a look-up instead of a float32 and a float64 division */
+int rsx_pca_build_lut_u16(const float* d_norm, const float* d_center, const double* d_scale, int n_bands, float* d_lut,
+                          rsx_stream_t stream);   /* d_norm [B][3], d_center [B], d_scale [B]: DEVICE copies of h_norm/h_center/h_scale */
 int rsx_pca_moments_u16(const uint16_t* d_raster, int64_t n_px, int n_bands, const float* h_norm, const float* h_center,
-                        const double* h_scale, double* d_moments, double* d_scratch, rsx_stream_t stream);
+                        const double* h_scale, const float* d_lut16, double* d_moments, double* d_scratch, rsx_stream_t stream);
 /* h_components: float [n_comp][B]; h_mean_proj: float [n_comp] = mean_ @ components^T */
 int rsx_pca_project_u8(const uint8_t* d_raster, int64_t n_px, int n_bands, const float* d_lut, const float* h_components,
                        const float* h_mean_proj, int n_comp, float* d_out, int64_t plane_stride, uint32_t* d_minmax,
                        rsx_stream_t stream);
 int rsx_pca_project_u16(const uint16_t* d_raster, int64_t n_px, int n_bands, const float* h_norm, const float* h_center,
-                        const double* h_scale, const float* h_components, const float* h_mean_proj, int n_comp, float* d_out,
-                        int64_t plane_stride, uint32_t* d_minmax, rsx_stream_t stream);
+                        const double* h_scale, const float* d_lut16, const float* h_components, const float* h_mean_proj, int n_comp,
+                        float* d_out, int64_t plane_stride, uint32_t* d_minmax, rsx_stream_t stream);
 
 /* ---- K4: GLCM texture --------------------------------------------------------------------------
  * Replaces the window double loop of calculate_glcm_features (indices.py:283-305): for every

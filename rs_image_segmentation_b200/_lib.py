@@ -29,9 +29,10 @@ SIGNATURES = {
     "rsx_quantize_f32": (i32, [vp, i64, f32, f32, f32, i32, vp, vp]),
     "rsx_pca_scratch_elems": (i64, [i32]),
     "rsx_pca_moments_u8": (i32, [vp, i64, i32, vp, vp, vp, vp]),
-    "rsx_pca_moments_u16": (i32, [vp, i64, i32, vp, vp, vp, vp, vp, vp]),
+    "rsx_pca_build_lut_u16": (i32, [vp, vp, vp, i32, vp, vp]),
+    "rsx_pca_moments_u16": (i32, [vp, i64, i32, vp, vp, vp, vp, vp, vp, vp]),
     "rsx_pca_project_u8": (i32, [vp, i64, i32, vp, vp, vp, i32, vp, i64, vp, vp]),
-    "rsx_pca_project_u16": (i32, [vp, i64, i32, vp, vp, vp, vp, vp, i32, vp, i64, vp, vp]),
+    "rsx_pca_project_u16": (i32, [vp, i64, i32, vp, vp, vp, vp, vp, vp, i32, vp, i64, vp, vp]),
     "rsx_glcm_props": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, vp, i64, vp]),
     "rsx_glcm_counts": (i32, [vp, i32, i32, i32, i32, vp, i32, vp, vp]),
     "rsx_resize_bilinear_f32": (i32, [vp, i32, i32, i32, i32, i64, vp, i32, i32, i32, i32, i64, i32, vp, vp]),

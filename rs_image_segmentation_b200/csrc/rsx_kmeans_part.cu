@@ -156,9 +156,11 @@ __device__ __forceinline__ int km_decide(const float* __restrict__ stack, int64_
         if (dist_exact < 0.0) {
             // sum of squares of (x' - c): all terms positive, relative error ~D * 2^-24
             float dd = 0.f;
+            // K > 8: the centroid comes from shared memory (lanes hold different labels; a constant-bank read would replay)
+            const float* cent = KU == 0 ? wsm + (D + 1) * ((g_km.K + 7) & ~7) + bi * D : nullptr;
 #pragma unroll
             for (int d = 0; d < D; ++d) {
-                float df = fmaf(x[d], g_km.scale32[d], g_km.off32[d]) - g_km.cent32[bi * KM_MAXD + d];
+                float df = fmaf(x[d], g_km.scale32[d], g_km.off32[d]) - (KU == 0 ? cent[d] : g_km.cent32[bi * KM_MAXD + d]);
                 dd = fmaf(df, df, dd);
             }
             dist_exact = (double)dd;
@@ -438,6 +440,8 @@ __global__ void __launch_bounds__(KM_THREADS, 4) km_stream_kernel(const float* _
             wsm[i] = g_km.w32[j * KM_MAXD + d];
         }
         for (int j = tid; j < KP; j += KM_THREADS) wsm[D * KP + j] = g_km.bias32[j];
+        if (INERTIA)
+            for (int i = tid; i < K * D; i += KM_THREADS) wsm[(D + 1) * KP + i] = g_km.cent32[(i / D) * KM_MAXD + i % D];
     }
     const int64_t n4 = n_px & ~(int64_t)3;
     const int64_t n_blocks = (n4 + KM_BLOCK_PX - 1) / KM_BLOCK_PX;
@@ -594,7 +598,7 @@ template <int D, int MODE, bool INERTIA, int KU>
 static int km_launch_stream(const KmLaunch& a, cudaStream_t s) {
     auto kern = km_stream_kernel<D, MODE, INERTIA, KU>;
     const int acc_bytes = MODE == KM_ASSIGN ? 0 : KM_WARPS * a.K * (D + 1) * 8;
-    const int w_bytes = KU == 0 ? (D + 1) * ((a.K + 7) & ~7) * 4 : 0;
+    const int w_bytes = KU == 0 ? ((D + 1) * ((a.K + 7) & ~7) + (INERTIA ? a.K * D : 0)) * 4 : 0;
     auto smem_for = [&](int stages) { return stages * D * KM_BLOCK_PX * 4 + acc_bytes + 2 * stages * 8 + w_bytes; };
     // stages: enough blocks in flight per SM to cover HBM latency at full bandwidth (~64 KB/SM), within shared memory
     static int cfg_K = -1, cfg_stages = 0, cfg_per_sm = 0;

@@ -36,6 +36,8 @@ __global__ void __launch_bounds__(256) hist_u8_kernel(const uint8_t* __restrict_
     }
 }
 
+// uint16: 65536 bins per band live in global memory (L2 atomics).  (Merging equal values inside a warp with match_any was
+// measured and is no faster; an exact two-pass digit histogram restricted to the needed order statistics is the next step.)
 template <int B>
 __global__ void __launch_bounds__(256) hist_u16_kernel(const uint16_t* __restrict__ raster, int64_t n_px, uint32_t* __restrict__ hist) {
     using RT = RasterTiles<uint16_t, B, 2>;
@@ -290,7 +292,7 @@ struct PcaParams {
     NormParam norm[B];
     float center[B];
     double scale[B];
-    const float* lut;  // device [B][256] (uint8 rasters) or nullptr
+    const float* lut;  // device [B][256] (uint8 rasters), [B][65536] (uint16 rasters, optional) or nullptr
 };
 
 template <typename T, int B>
@@ -299,6 +301,8 @@ __device__ __forceinline__ void scaled_pixel(const int (&raw)[B], const PcaParam
     for (int b = 0; b < B; ++b) {
         if constexpr (sizeof(T) == 1)
             x[b] = lut_s[b * 256 + raw[b]];
+        else if (P.lut)
+            x[b] = __ldg(P.lut + b * 65536 + raw[b]);  // built by pca_lut_u16_kernel with the expression below
         else
             x[b] = __double2float_rn(__ddiv_rn((double)f_sub(norm_apply((float)raw[b], P.norm[b]), P.center[b]), P.scale[b]));
     }
@@ -346,6 +350,23 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 template <typename T>
 constexpr int lut_bytes(int B) { return sizeof(T) == 1 ? B * 256 * 4 : 0; }
+
+// X of every 16-bit level of every band, same arithmetic as the per-sample path (one IEEE float32 division, one float64
+// division per entry instead of per sample)
+__global__ void __launch_bounds__(256) pca_lut_u16_kernel(const float* __restrict__ norm, const float* __restrict__ center, const double* __restrict__ scale,
+                                                          int B, float* __restrict__ lut) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= B * 65536) return;
+    const int b = i >> 16, v = i & 0xffff;
+    const NormParam np_{norm[3 * b], norm[3 * b + 1], norm[3 * b + 2]};
+    lut[i] = __double2float_rn(__ddiv_rn((double)f_sub(norm_apply((float)v, np_), center[b]), scale[b]));
+}
+
+extern "C" int rsx_pca_build_lut_u16(const float* d_norm, const float* d_center, const double* d_scale, int n_bands, float* d_lut, rsx_stream_t stream) {
+    RSX_REQUIRE(d_norm && d_center && d_scale && d_lut && n_bands >= 1 && n_bands <= RSX_MAX_BANDS, "rsx_pca_build_lut_u16: bad arguments");
+    pca_lut_u16_kernel<<<n_bands * 256, 256, 0, (cudaStream_t)stream>>>(d_norm, d_center, d_scale, n_bands, d_lut);
+    return rsx_check_launch("pca_lut_u16");
+}
 
 template <typename T, int B>
 __global__ void __launch_bounds__(256) pca_moments_kernel(const T* __restrict__ raster, int64_t n_px, const __grid_constant__ PcaParams<B> P,
@@ -467,8 +488,8 @@ extern "C" int rsx_pca_moments_u8(const uint8_t* d_raster, int64_t n_px, int n_b
     return pca_moments_impl<uint8_t>(d_raster, n_px, n_bands, nullptr, nullptr, nullptr, d_lut, d_moments, d_scratch, stream);
 }
 extern "C" int rsx_pca_moments_u16(const uint16_t* d_raster, int64_t n_px, int n_bands, const float* h_norm, const float* h_center,
-                                   const double* h_scale, double* d_moments, double* d_scratch, rsx_stream_t stream) {
-    return pca_moments_impl<uint16_t>(d_raster, n_px, n_bands, h_norm, h_center, h_scale, nullptr, d_moments, d_scratch, stream);
+                                   const double* h_scale, const float* d_lut16, double* d_moments, double* d_scratch, rsx_stream_t stream) {
+    return pca_moments_impl<uint16_t>(d_raster, n_px, n_bands, h_norm, h_center, h_scale, d_lut16, d_moments, d_scratch, stream);
 }
 
 // ---- projection: Y = X @ components^T - mean @ components^T  (sklearn/decomposition/_base.py:151-159)
@@ -580,8 +601,8 @@ extern "C" int rsx_pca_project_u8(const uint8_t* d_raster, int64_t n_px, int n_b
                                      d_minmax, stream);
 }
 extern "C" int rsx_pca_project_u16(const uint16_t* d_raster, int64_t n_px, int n_bands, const float* h_norm, const float* h_center,
-                                   const double* h_scale, const float* h_components, const float* h_mean_proj, int n_comp, float* d_out,
-                                   int64_t plane_stride, uint32_t* d_minmax, rsx_stream_t stream) {
-    return pca_project_impl<uint16_t>(d_raster, n_px, n_bands, h_norm, h_center, h_scale, nullptr, h_components, h_mean_proj, n_comp, d_out, plane_stride,
+                                   const double* h_scale, const float* d_lut16, const float* h_components, const float* h_mean_proj, int n_comp,
+                                   float* d_out, int64_t plane_stride, uint32_t* d_minmax, rsx_stream_t stream) {
+    return pca_project_impl<uint16_t>(d_raster, n_px, n_bands, h_norm, h_center, h_scale, d_lut16, h_components, h_mean_proj, n_comp, d_out, plane_stride,
                                       d_minmax, stream);
 }

@@ -139,7 +139,13 @@ def extract_features(raster: torch.Tensor, cfg: FeatureConfig = FeatureConfig(),
     scratch = torch.empty(int(_lib.load().rsx_pca_scratch_elems(B)), dtype=torch.float64, device=dev)
     center = np.ascontiguousarray(stats.center, dtype=np.float32)
     scale = np.ascontiguousarray(stats.scale, dtype=np.float64)
-    lut = None
+    lut = lut_inputs = None
+    if is16:
+        # X per 16-bit level, tabulated on the device with the per-sample arithmetic (3.4 MB for 13 bands, L2 resident)
+        lut = torch.empty((B, 65536), dtype=torch.float32, device=dev)
+        d_norm, d_center, d_scale = torch.from_numpy(norm).to(dev), torch.from_numpy(center).to(dev), torch.from_numpy(scale).to(dev)
+        _lib.call("rsx_pca_build_lut_u16", ptr(d_norm), ptr(d_center), ptr(d_scale), B, ptr(lut), st)
+        lut_inputs = (d_norm, d_center, d_scale)            # stay referenced until the stream has consumed them
     if not is16:
         x_lut = np.ascontiguousarray(stats.x_lut, dtype=np.float32)
         if remap is not None:                                   # table of the RAW level: x_lut[b][remap[b][v]]
@@ -148,7 +154,8 @@ def extract_features(raster: torch.Tensor, cfg: FeatureConfig = FeatureConfig(),
     if n_px:
         with timer("pca_moments"):
             if is16:
-                _lib.call("rsx_pca_moments_u16", ptr(raster), n_px, B, hptr(norm), hptr(center), hptr(scale), ptr(moments), ptr(scratch), st)
+                _lib.call("rsx_pca_moments_u16", ptr(raster), n_px, B, hptr(norm), hptr(center), hptr(scale), ptr(lut), ptr(moments),
+                          ptr(scratch), st)
             else:
                 _lib.call("rsx_pca_moments_u8", ptr(raster), n_px, B, ptr(lut), ptr(moments), ptr(scratch), st)
     if comm.world > 1:
@@ -191,11 +198,12 @@ def extract_features(raster: torch.Tensor, cfg: FeatureConfig = FeatureConfig(),
     if n_px:
         with timer("pca_project"):
             if is16:
-                _lib.call("rsx_pca_project_u16", ptr(raster), n_px, B, hptr(norm), hptr(center), hptr(scale), hptr(comps), hptr(mean_proj),
-                          n_comp, C.c_void_p(planes[pc0].data_ptr()), stride, mm.slot(pc0), st)
+                _lib.call("rsx_pca_project_u16", ptr(raster), n_px, B, hptr(norm), hptr(center), hptr(scale), ptr(lut), hptr(comps),
+                          hptr(mean_proj), n_comp, C.c_void_p(planes[pc0].data_ptr()), stride, mm.slot(pc0), st)
             else:
                 _lib.call("rsx_pca_project_u8", ptr(raster), n_px, B, ptr(lut), hptr(comps), hptr(mean_proj), n_comp,
                           C.c_void_p(planes[pc0].data_ptr()), stride, mm.slot(pc0), st)
+    del lut_inputs
     return FeatureResult(planes=planes, names=names, n_px=n_px, H=h, W=W, stats=stats, pca=pca, minmax=mm, quant=quant)
 
 
