@@ -55,6 +55,15 @@ int64_t rsx_launch_count(void);
 int rsx_hist_u8(const uint8_t* d_raster, int64_t n_px, int n_bands, uint32_t* d_hist, rsx_stream_t stream);
 int rsx_hist_u16(const uint16_t* d_raster, int64_t n_px, int n_bands, uint32_t* d_hist, rsx_stream_t stream);
 
+/* Host-side order statistics from the K1 histograms (no device work): numpy's float32 percentile arithmetic for
+ * robust_normalize (indices.py:38-46; also the second normalisation of the texture band, :265) and RobustScaler's
+ * median / inter-quartile range (sklearn/preprocessing/_data.py:1722,1738-1743).
+ * h_hist int64 [B][L] (L = 256 or 65536); h_norm float [B][3] = lo, hi, den; h_qnorm float [3] for band texture_band
+ * (-1: none); h_center float [B], h_scale double [B] (both may be NULL); h_norm_lut / h_x_lut float [B][L] (may be NULL):
+ * the normalised value / the RobustScaler-transformed value of every level. */
+int rsx_raster_stats(const int64_t* h_hist, int n_bands, int n_levels, int texture_band, double lower, double upper,
+                     float* h_norm, float* h_qnorm, float* h_center, double* h_scale, float* h_norm_lut, float* h_x_lut);
+
 /* ---- K2: fused normalise + spectral indices (+ GLCM quantisation) ---------------------------
  * Replaces robust_normalize x B (indices.py:25-48 via scripts/2...:43-47) and the seven index
  * functions (indices.py:50-203) in one pass over the raster.

@@ -1,8 +1,10 @@
 // Error handling, launch accounting, min/max trackers and the planar float32 element-wise
 // entry points (per-function drop-ins for modules/features/indices.py).
 #include <atomic>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstring>
 
 #include "rsx_common.cuh"
 
@@ -224,4 +226,123 @@ extern "C" int rsx_quantize_f32(const float* d_in, int64_t n, float lo, float hi
     quantize_f32_kernel<<<(int)min((int64_t)rsx_num_sms() * 8, ceil_div(n, (int64_t)256)), 256, 0, (cudaStream_t)stream>>>(
         d_in, n, NormParam{lo, hi, den}, (float)(levels - 1), d_q);
     return rsx_check_launch("rsx_quantize_f32");
+}
+
+// ----------------------------------------------------------------------------- host: order statistics from band histograms
+// The few scalars (and per-level tables) the kernels need from the K1 histograms: robust_normalize's P2/P98
+// (modules/features/indices.py:38-46), the second robust_normalize of the texture band (:265), RobustScaler's median / IQR
+// (sklearn/preprocessing/_data.py:1722,1738-1743) and the per-level table of the scaled value.  This is numpy's `_quantile`
+// (method="linear") restated operation by operation in the dtypes numpy ends up using for float32 data - see
+// rs_image_segmentation_b200/hoststats.py, the Python statement of the same arithmetic that the tests hold it against.
+// Host code, O(levels) per band; it sits between two kernels, so it has to take microseconds, not a millisecond of Python.
+namespace {
+struct Order {
+    const int64_t* cum;   // inclusive cumulative counts over the levels
+    const float* values;  // value of every level (float32)
+    int L;
+    int64_t n;
+    float at(int64_t k) const {  // k-th smallest sample
+        k = k < 0 ? 0 : (k >= n ? n - 1 : k);
+        int lo = 0, hi = L;  // first level with cum > k  (np.searchsorted(cum, k, "right"))
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (cum[mid] > k) hi = mid; else lo = mid + 1;
+        }
+        return values[lo < L ? lo : L - 1];
+    }
+    // np.percentile(float32 band, q) with a Python-number q: everything in float32
+    float percentile32(double q) const {
+        const float q32 = (float)q / 100.0f;
+        const float nm1 = (float)(n - 1);
+        const volatile float vi = nm1 * q32;
+        float prev = floorf(vi), nxt = prev + 1.0f;
+        if (vi >= nm1) prev = nxt = -1.0f;
+        if (vi < 0.0f) prev = nxt = 0.0f;
+        const int64_t pi = (int64_t)prev, ni = (int64_t)nxt;
+        const float a = at(pi >= 0 ? pi : n - 1), b = at(ni >= 0 ? ni : n - 1);
+        if (a == b) return a;
+        const float t = (float)((double)vi - (double)pi);
+        const volatile float diff = b - a;
+        volatile float prod = diff * t;
+        volatile float out = a + prod;
+        if (t >= 0.5f) {
+            volatile float omt = 1.0f - t;
+            prod = diff * omt;
+            out = b - prod;
+        }
+        return out;
+    }
+    // np.nanpercentile(float32 column, (..., q, ...)) with float64 q: float64 virtual index, float64 result
+    double percentile64(double q) const {
+        const double qq = q / 100.0;
+        const volatile double vi = (double)(n - 1) * qq;
+        double prev = floor(vi), nxt = prev + 1.0;
+        if (vi >= (double)(n - 1)) prev = nxt = -1.0;
+        if (vi < 0.0) prev = nxt = 0.0;
+        const int64_t pi = (int64_t)prev, ni = (int64_t)nxt;
+        const float a = at(pi >= 0 ? pi : n - 1), b = at(ni >= 0 ? ni : n - 1);
+        if (a == b) return (double)a;
+        const double t = vi - (double)pi;
+        const volatile float diff = b - a;
+        volatile double out = (double)a + (double)diff * t;
+        if (t >= 0.5) out = (double)b - (double)diff * (1.0 - t);
+        return out;
+    }
+    float median32() const {
+        if (n & 1) return at(n / 2);
+        const volatile float s = at(n / 2 - 1) + at(n / 2);
+        return s / 2.0f;
+    }
+};
+}  // namespace
+
+extern "C" int rsx_raster_stats(const int64_t* h_hist, int n_bands, int n_levels, int texture_band, double lower, double upper, float* h_norm,
+                                float* h_qnorm, float* h_center, double* h_scale, float* h_norm_lut, float* h_x_lut) {
+    RSX_REQUIRE(h_hist && h_norm && h_qnorm && n_bands >= 1 && n_bands <= RSX_MAX_BANDS && (n_levels == 256 || n_levels == 65536),
+                "rsx_raster_stats: bad arguments");
+    static thread_local int64_t* cum = nullptr;
+    static thread_local float *levels = nullptr, *f = nullptr;
+    static thread_local int cap = 0;
+    if (cap < n_levels) {
+        delete[] cum, delete[] levels, delete[] f;
+        cum = new int64_t[n_levels], levels = new float[n_levels], f = new float[n_levels];
+        cap = n_levels;
+        for (int v = 0; v < n_levels; ++v) levels[v] = (float)v;
+    }
+    h_qnorm[0] = 0.f, h_qnorm[1] = 1.f, h_qnorm[2] = 1.f;
+    for (int b = 0; b < n_bands; ++b) {
+        const int64_t* h = h_hist + (size_t)b * n_levels;
+        int64_t run = 0;
+        for (int v = 0; v < n_levels; ++v) run += h[v], cum[v] = run;
+        RSX_REQUIRE(run > 0, "rsx_raster_stats: empty histogram (band %d)", b);
+        const Order raw{cum, levels, n_levels, run};
+        const float lo = raw.percentile32(lower), hi = raw.percentile32(upper);
+        const volatile float range = hi - lo;
+        const float den = range + 1e-10f;  // hi - lo + 1e-10 in float32 (indices.py:46)
+        h_norm[3 * b] = lo, h_norm[3 * b + 1] = hi, h_norm[3 * b + 2] = den;
+        for (int v = 0; v < n_levels; ++v) {  // robust_normalize of every level
+            const float c = fminf(fmaxf(levels[v], lo), hi);
+            const volatile float num = c - lo;
+            f[v] = num / den;
+        }
+        if (h_norm_lut) memcpy(h_norm_lut + (size_t)b * n_levels, f, sizeof(float) * n_levels);
+        const Order nb{cum, f, n_levels, run};
+        if (b == texture_band) {
+            const float lo2 = nb.percentile32(lower), hi2 = nb.percentile32(upper);
+            const volatile float r2 = hi2 - lo2;
+            h_qnorm[0] = lo2, h_qnorm[1] = hi2, h_qnorm[2] = r2 + 1e-10f;
+        }
+        if (h_center && h_scale) {
+            const float center = nb.median32();
+            double s = nb.percentile64(75.0) - nb.percentile64(25.0);
+            if (s < 10.0 * 2.220446049250313e-16) s = 1.0;  // sklearn _handle_zeros_in_scale
+            h_center[b] = center, h_scale[b] = s;
+            if (h_x_lut)
+                for (int v = 0; v < n_levels; ++v) {
+                    const volatile float d = f[v] - center;
+                    h_x_lut[(size_t)b * n_levels + v] = (float)((double)d / s);
+                }
+        }
+    }
+    return RSX_OK;
 }

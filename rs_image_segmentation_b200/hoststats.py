@@ -119,18 +119,29 @@ class RasterStats:
     x_lut     float32 [B][L]   RobustScaler().fit_transform value of every grey level (uint8 rasters)
     """
 
-    def __init__(self, hist, glcm_band=3, lower=2, upper=98):
-        hist = np.asarray(hist, dtype=np.int64)
+    def __init__(self, hist, glcm_band=3, lower=2, upper=98, native=True):
+        hist = np.ascontiguousarray(hist, dtype=np.int64)
         B, L = hist.shape
         self.B, self.L = B, L
         self.hist = hist
         self.hist_raw = hist                       # pipeline.extract_features overwrites it with the DN histogram when stage 1 is fused
         self.n = int(hist[0].sum())
-        levels = np.arange(L, dtype=F32)
         self.norm = np.zeros((B, 3), F32)
         self.norm_lut = np.zeros((B, L), F32)
         self.qnorm = np.array([0, 1, 1], F32)
         self._scaler = None
+        if native and L in (256, 65536):
+            # the same arithmetic in C (librsx.so, rsx_raster_stats): microseconds instead of a millisecond between two kernels
+            from . import _lib
+            center, scale, x_lut = np.zeros(B, F32), np.ones(B, np.float64), np.zeros((B, L), F32)
+            p = lambda a: a.ctypes.data_as(_lib.C.c_void_p)
+            rc = _lib.load().rsx_raster_stats(p(hist), B, L, int(glcm_band) if 0 <= glcm_band < B else -1, float(lower), float(upper),
+                                              p(self.norm), p(self.qnorm), p(center), p(scale), p(self.norm_lut), p(x_lut))
+            if rc != 0:
+                raise ValueError(_lib.load().rsx_last_error().decode())
+            self._scaler = (center, scale, x_lut)
+            return
+        levels = np.arange(L, dtype=F32)
         # phase 1 (what K2 needs): robust_normalize parameters of every band, and of the normalised texture band
         for b in range(B):
             raw = LevelOrder(hist[b], levels)

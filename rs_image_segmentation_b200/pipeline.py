@@ -94,6 +94,14 @@ def extract_features(raster: torch.Tensor, cfg: FeatureConfig = FeatureConfig(),
     if n_px:
         with timer("hist"):
             _lib.call(f"rsx_hist_{sfx}", ptr(raster), n_px, B, ptr(hist), st)
+    # allocations first: they overlap the histogram kernel, the host is needed again right after the read-back
+    n_comp = B if cfg.n_components is None else int(cfg.n_components)
+    names = list(INDEX_NAMES) + (["glcm_" + g for g in GLCM_NAMES] if cfg.glcm else []) + [f"pc{i}" for i in range(n_comp)]
+    stride = _pad4(max(n_px, 1))
+    planes = torch.empty((len(names), stride), dtype=torch.float32, device=dev)
+    mm = MinMaxTracker(len(names), device=dev)
+    quant = torch.empty(_pad4(max(n_px, 1)), dtype=torch.uint8, device=dev) if cfg.glcm else None
+
     if comm.world > 1:
         with timer("hist_allreduce"):
             hist64 = hist.to(torch.int64) & 0xFFFFFFFF      # the kernel's counters are uint32
@@ -110,13 +118,6 @@ def extract_features(raster: torch.Tensor, cfg: FeatureConfig = FeatureConfig(),
         remap = np.ascontiguousarray(remap)
     stats = hoststats.RasterStats(hist_host, glcm_band=cfg.band_map[3], lower=cfg.percentiles[0], upper=cfg.percentiles[1])
     stats.hist_raw = hist_raw
-
-    n_comp = B if cfg.n_components is None else int(cfg.n_components)
-    names = list(INDEX_NAMES) + (["glcm_" + g for g in GLCM_NAMES] if cfg.glcm else []) + [f"pc{i}" for i in range(n_comp)]
-    stride = _pad4(max(n_px, 1))
-    planes = torch.empty((len(names), stride), dtype=torch.float32, device=dev)
-    mm = MinMaxTracker(len(names), device=dev)
-    quant = torch.empty(_pad4(max(n_px, 1)), dtype=torch.uint8, device=dev) if cfg.glcm else None
 
     # ---- K2 fused normalise + indices (+ quantised NIR)
     band_map = np.asarray(cfg.band_map, dtype=np.int32)

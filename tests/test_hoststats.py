@@ -107,3 +107,47 @@ def test_stage1_level_tables_match_reference_chain():
             continue                                                    # 0/0: the reference produces NaN -> undefined uint8
         assert np.array_equal(remap[b][raw[b]], ref[b]), b
         assert np.array_equal(hist1[b], np.bincount(ref[b].ravel(), minlength=256)), b
+
+
+def _random_hists(rng, B, L, kind):
+    if kind == "dense":
+        return rng.integers(0, 5000, size=(B, L)).astype(np.int64)
+    if kind == "sparse":
+        h = np.zeros((B, L), np.int64)
+        for b in range(B):
+            idx = rng.choice(L, size=int(rng.integers(1, 12)), replace=False)
+            h[b, idx] = rng.integers(1, 40, size=idx.size)
+        return h
+    if kind == "huge":                                   # n > 2^24: the float32 virtual index is no longer exact
+        return rng.integers(0, 400000, size=(B, L)).astype(np.int64)
+    if kind == "single":
+        h = np.zeros((B, L), np.int64)
+        h[np.arange(B), rng.integers(0, L, size=B)] = rng.integers(1, 1000, size=B)
+        return h
+    h = rng.integers(0, 3, size=(B, L)).astype(np.int64)  # "tiny": few samples, many ties
+    h[:, 0] += 1
+    return h
+
+
+@pytest.mark.parametrize("L", [256, 65536])
+@pytest.mark.parametrize("kind", ["dense", "sparse", "huge", "single", "tiny"])
+def test_native_raster_stats_match_python_statement(L, kind):
+    """rsx_raster_stats (C, in librsx.so) against the numpy-faithful Python statement, bit for bit."""
+    from rs_image_segmentation_b200 import hoststats
+    rng = np.random.default_rng(L + len(kind))
+    for trial in range(3 if L == 256 else 1):
+        B = int(rng.integers(1, 14))
+        hist = _random_hists(rng, B, L, kind)
+        if L == 65536:
+            hist[:, 12000:] = 0                           # keep the Python statement quick
+            hist[:, 0] += 1
+        gb = int(rng.integers(0, B))
+        for lower, upper in ((2, 98), (0, 100), (10.5, 63.25)):
+            a = hoststats.RasterStats(hist, glcm_band=gb, lower=lower, upper=upper, native=True)
+            b = hoststats.RasterStats(hist, glcm_band=gb, lower=lower, upper=upper, native=False)
+            assert np.array_equal(a.norm.view(np.uint32), b.norm.view(np.uint32))
+            assert np.array_equal(a.qnorm.view(np.uint32), b.qnorm.view(np.uint32))
+            assert np.array_equal(a.norm_lut.view(np.uint32), b.norm_lut.view(np.uint32))
+            assert np.array_equal(a.center.view(np.uint32), b.center.view(np.uint32))
+            assert np.array_equal(a.scale.view(np.uint64), b.scale.view(np.uint64))
+            assert np.array_equal(a.x_lut.view(np.uint32), b.x_lut.view(np.uint32))
