@@ -230,7 +230,8 @@ def run_rsx(args):
         a.record()
         out = None
         for _ in range(steps):
-            out = fn()
+            out = None          # release the previous step's buffers first: the caching allocator then reuses the same blocks
+            out = fn()          # (a second live generation would cost a multi-GB cudaMalloc inside the timed region)
         b.record()
         torch.cuda.synchronize()
         comm.barrier()
@@ -238,8 +239,11 @@ def run_rsx(args):
         comm.all_reduce(ms, "max")
         return float(ms.item()), out
 
+    keep = None
     for _ in range(args.warmup):
-        step(StageTimer(enabled=False))
+        keep = None
+        keep = step(StageTimer(enabled=False))
+    keep = None
     sampler = ClockSampler(local)
     if rank == 0 and os.environ.get("RSX_BENCH_NOCLOCKS", "0") != "1":
         sampler.start()

@@ -11,6 +11,7 @@
 //     energy        = sqrt(sum_cells P^2) = sqrt(E)/2n, E = sum_s (a!=b ? 2 U[{a,b}] : 4 U[{a,a}])
 // where U[{a,b}] counts the pairs of the window whose UNORDERED levels are {a,b}.  All sums are exact
 // integers; only E needs the histogram, and it needs it only at the cells the window touches.
+#include <climits>
 #include <cstdlib>
 
 #include "rsx_common.cuh"
@@ -537,7 +538,8 @@ extern "C" int rsx_glcm_counts(const uint8_t* d_q, int H, int W, int levels, int
 // (OpenCV's own non-IPP path rounds c to float before taking the fraction and differs from this by ~6e-5 relative.)
 __global__ void __launch_bounds__(256) resize_bilinear_kernel(const float* __restrict__ src, int src_h, int src_w, int src_row0, int src_rows_avail,
                                                               int64_t src_stride, float* __restrict__ dst, int dst_w, int dst_row0, int dst_rows,
-                                                              int64_t dst_stride, double scale_x, double scale_y, uint32_t* __restrict__ minmax) {
+                                                              int64_t dst_stride, double scale_x, double scale_y, int rows_per_cta,
+                                                              uint32_t* __restrict__ minmax) {
     const int plane = blockIdx.z;
     const float* sp = src + plane * src_stride;
     float* dp = dst + plane * dst_stride;
@@ -549,22 +551,27 @@ __global__ void __launch_bounds__(256) resize_bilinear_kernel(const float* __res
         const float fx = (float)(cx - fxd);
         const int sx = (int)fxd;
         const int x0 = min(max(sx, 0), src_w - 1), x1 = min(max(sx + 1, 0), src_w - 1);
-        for (int ly = blockIdx.y; ly < dst_rows; ly += gridDim.y) {
+        // a thread walks down a run of destination rows; the horizontally interpolated source rows are kept from one
+        // destination row to the next (consecutive destination rows share at least one source row when upsampling)
+        auto hrow = [&](int y) -> float {  // y: source row relative to the rows present
+            if (y < 0 || y >= src_rows_avail) return 0.f;
+            const float p = sp[(int64_t)y * src_w + x0], q = sp[(int64_t)y * src_w + x1];
+            return fmaf(f_sub(q, p), fx, p);
+        };
+        const int ly0 = blockIdx.y * rows_per_cta, ly1 = min(dst_rows, ly0 + rows_per_cta);
+        int cy0 = INT_MIN, cy1 = INT_MIN;  // source rows held in r0, r1
+        float r0 = 0.f, r1 = 0.f;
+        for (int ly = ly0; ly < ly1; ++ly) {
             const int dy = dst_row0 + ly;
             const double cy = (dy + 0.5) * scale_y - 0.5;
             const double fyd = floor(cy);
             const float fy = (float)(cy - fyd);
             const int sy = (int)fyd;
             const int y0 = min(max(sy, 0), src_h - 1) - src_row0, y1 = min(max(sy + 1, 0), src_h - 1) - src_row0;
-            float r0 = 0.f, r1 = 0.f;
-            if (y0 >= 0 && y0 < src_rows_avail) {
-                const float p = sp[(int64_t)y0 * src_w + x0], q = sp[(int64_t)y0 * src_w + x1];
-                r0 = fmaf(f_sub(q, p), fx, p);
-            }
-            if (y1 >= 0 && y1 < src_rows_avail) {
-                const float p = sp[(int64_t)y1 * src_w + x0], q = sp[(int64_t)y1 * src_w + x1];
-                r1 = fmaf(f_sub(q, p), fx, p);
-            }
+            float n0, n1;
+            n0 = y0 == cy0 ? r0 : (y0 == cy1 ? r1 : hrow(y0));
+            n1 = y1 == cy1 ? r1 : (y1 == cy0 ? r0 : hrow(y1));
+            r0 = n0, r1 = n1, cy0 = y0, cy1 = y1;
             const float v = fmaf(f_sub(r1, r0), fy, r0);
             dp[(int64_t)ly * dst_w + dx] = v;
             mn = fminf(mn, v), mx = fmaxf(mx, v);
@@ -579,9 +586,11 @@ extern "C" int rsx_resize_bilinear_f32(const float* d_src, int src_h_total, int 
     RSX_REQUIRE(d_src && d_dst && src_h_total >= 1 && src_w >= 1 && dst_h_total >= 1 && dst_w >= 1 && dst_rows >= 1 && n_planes >= 1,
                 "rsx_resize_bilinear_f32: bad arguments");
     const double scale_x = 1.0 / ((double)dst_w / (double)src_w), scale_y = 1.0 / ((double)dst_h_total / (double)src_h_total);
-    dim3 grid(ceil_div(dst_w, 256), min(dst_rows, max(1, rsx_num_sms() * 8 / ceil_div(dst_w, 256))), n_planes);
+    const int gx = ceil_div(dst_w, 256);
+    const int rows_per_cta = max(8, ceil_div(dst_rows, max(1, rsx_num_sms() * 16 / max(1, gx * n_planes))));
+    dim3 grid(gx, ceil_div(dst_rows, rows_per_cta), n_planes);
     resize_bilinear_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_src, src_h_total, src_w, src_row0, src_rows_avail, src_plane_stride, d_dst, dst_w,
-                                                                   dst_row0, dst_rows, dst_plane_stride, scale_x, scale_y, d_minmax);
+                                                                   dst_row0, dst_rows, dst_plane_stride, scale_x, scale_y, rows_per_cta, d_minmax);
     return rsx_check_launch("resize_bilinear");
 }
 
