@@ -456,7 +456,7 @@ static int dispatch_dense(const uint8_t* d_q, int W, int levels, int out_rows, i
         }
     }
     const int ntw = windows(32);
-    if (ntw >= 8) return launch_dense<WIN, 32, WIDE>(d_q, W, levels, ntw, out_rows, out_cols, d_props, plane_stride, s);
+    if (ntw >= 8 && (!forced || forced == 32)) return launch_dense<WIN, 32, WIDE>(d_q, W, levels, ntw, out_rows, out_cols, d_props, plane_stride, s);
     return -1;
 }
 

@@ -293,3 +293,24 @@ def test_device_writers(P, tmp_path):
     res, km, c0 = P.kmeans_on_features(fr, 13, 6, 3, seed=1)
     lab8 = writers.labels_for_geotiff(res.labels, H, W)
     assert lab8.dtype == np.uint8 and np.array_equal(lab8, (res.labels.cpu().numpy().reshape(H, W) + 1).astype(np.uint8))
+
+
+@pytest.mark.parametrize("H,W,win,step,K", [(9, 9, 7, 1, 2), (13, 17, 5, 1, 3), (8, 31, 7, 7, 4), (21, 21, 21, 21, 2), (11, 514, 3, 1, 5), (7, 7, 7, 1, 1)])
+def test_ragged_and_tiny_rasters(P, H, W, win, step, K):
+    """Tiny / ragged shapes: n_px not a multiple of 4 or of the 512-pixel KMeans block, a single GLCM window, W below one tile."""
+    import torch
+    from rs_image_segmentation_b200.synth import synth_raster_numpy
+    bip = synth_raster_numpy(H, W, 7, np.uint8, H * W, cell=4)
+    cfg = P.FeatureConfig(glcm_window=win, glcm_step=step)
+    fr = P.extract_features(torch.from_numpy(bip).cuda(), cfg)
+    _check_features(fr, _oracle_features(bip, cfg), cfg)
+    _mm_check(fr)
+    D, n_iter = 13, 3
+    res, km, c0 = P.kmeans_on_features(fr, D, K, n_iter, seed=2)
+    stack = fr.planes[:D, :fr.n_px].t().contiguous().cpu().numpy()
+    (lab, cent, inertia, n_run), Xs = _kmeans_oracle(stack, c0, n_iter, km.fmin, km.fmax)
+    got = res.labels.cpu().numpy()
+    if n_run == n_iter:                                   # sklearn may stop early on tiny inputs (strict convergence)
+        assert np.array_equal(got, lab)
+        np.testing.assert_allclose(res.centroids, cent, rtol=0, atol=1e-9)
+    assert int(km.acc[km.n_acc + K * D:km.n_acc + K * D + K].sum()) == fr.n_px
