@@ -626,3 +626,76 @@ def _pinned_labels(n: int) -> torch.Tensor:
         _PINNED_LABELS.clear()
         buf = _PINNED_LABELS[n] = torch.empty(n, dtype=torch.int32, pin_memory=True)
     return buf
+
+
+def segment_stream(rasters, cfg: FeatureConfig = FeatureConfig(), n_clusters: int = 8, n_iter: int = 20, seed: int = 42,
+                   stack_depth: Optional[int] = None, comm: Optional[Comm] = None, H_total: Optional[int] = None,
+                   bounds: Optional[Sequence[Tuple[int, int]]] = None):
+    """Pipelined end-to-end path for a sequence of scenes (or of this rank's strips of them), all of one shape: an iterable of
+    page-locked host rasters in, a generator of (labels (h, W) int32 numpy, KMeansResult) out, in order.
+
+    The host-to-device copy of scene i+1 and the device-to-host copy of the labels of scene i-1 run on their own streams
+    (the two copy engines) under the kernels of scene i, so a step costs max(compute, copies) instead of their sum.
+    A yielded label array lives in one of two page-locked buffers: it is valid until two more scenes have been yielded."""
+    require_cuda()
+    comm = comm or Comm()
+    compute = torch.cuda.current_stream()
+    up, down = torch.cuda.Stream(), torch.cuda.Stream()
+    it = iter(rasters)
+
+    def as_pinned(r):
+        if isinstance(r, np.ndarray):
+            a = np.ascontiguousarray(r)
+            r = torch.from_numpy(a.view(np.int16) if a.dtype == np.uint16 else a)
+        return r if r.is_pinned() else r.pin_memory()
+
+    first = next(it, None)
+    if first is None:
+        return
+    first = as_pinned(first)
+    dev = [torch.empty(first.shape, dtype=first.dtype, device="cuda") for _ in range(2)]       # double-buffered device rasters
+    out = [torch.empty(first.shape[0] * first.shape[1], dtype=torch.int32, pin_memory=True) for _ in range(2)]
+    uploaded = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]       # compute no longer reads dev[k]
+    downloaded = [torch.cuda.Event() for _ in range(2)]
+
+    def upload(host, k, wait_consumed):
+        with torch.cuda.stream(up):
+            if wait_consumed:
+                up.wait_event(consumed[k])
+            dev[k].copy_(host, non_blocking=True)
+            uploaded[k].record(up)
+
+    upload(first, 0, False)
+    pending = None                                          # (slot, KMeansResult, H, W) whose labels are on their way to the host
+    i = 0
+    cur = first
+    while cur is not None:
+        k = i & 1
+        nxt = next(it, None)
+        if nxt is not None:
+            nxt = as_pinned(nxt)
+            upload(nxt, k ^ 1, i >= 1)                     # dev[k^1] was read by scene i-1
+        compute.wait_event(uploaded[k])
+        fr = extract_features(dev[k], cfg, comm, H_total, bounds)
+        D = stack_depth if stack_depth is not None else (13 if cfg.glcm else 7 + min(6, len(fr.names) - 7))
+        first_row = bounds[comm.rank][0] if bounds is not None else 0
+        res, km, c0 = kmeans_on_features(fr, D, n_clusters, n_iter, seed, comm, H_total, first_row, True)
+        consumed[k].record(compute)
+        done = torch.cuda.Event()
+        done.record(compute)
+        if pending is not None:                             # hand out scene i-1 (its download overlapped this scene's kernels)
+            pk, pres, ph, pw = pending
+            downloaded[pk].synchronize()
+            yield out[pk].numpy().reshape(ph, pw), pres
+        with torch.cuda.stream(down):
+            down.wait_event(done)
+            out[k].copy_(res.labels, non_blocking=True)
+            downloaded[k].record(down)
+        res.labels.record_stream(down)
+        pending = (k, res, fr.H, fr.W)
+        cur = nxt
+        i += 1
+    pk, pres, ph, pw = pending
+    downloaded[pk].synchronize()
+    yield out[pk].numpy().reshape(ph, pw), pres

@@ -314,3 +314,20 @@ def test_ragged_and_tiny_rasters(P, H, W, win, step, K):
         assert np.array_equal(got, lab)
         np.testing.assert_allclose(res.centroids, cent, rtol=0, atol=1e-9)
     assert int(km.acc[km.n_acc + K * D:km.n_acc + K * D + K].sum()) == fr.n_px
+
+
+def test_segment_stream_matches_single_scene_calls(P):
+    """The pipelined host-buffer API (uploads / downloads on the copy engines under the neighbouring scenes' kernels) returns,
+    scene by scene, exactly what the one-scene call returns."""
+    from rs_image_segmentation_b200.synth import synth_raster_numpy
+    cfg = P.FeatureConfig(glcm_window=7, glcm_step=1)
+    scenes = [synth_raster_numpy(90, 150, 7, np.uint8, 100 + i, cell=16) for i in range(5)]
+    ref = [P.segment_raster(s, cfg, 6, 5, 9)[0].copy() for s in scenes]
+    got = []
+    for labels, res in P.segment_stream(scenes, cfg, 6, 5, 9):
+        got.append(labels.copy())                          # a yielded buffer is reused two scenes later
+        assert res.n_iter == 5
+    assert len(got) == len(ref)
+    for a, b in zip(got, ref):
+        assert a.dtype == np.int32 and np.array_equal(a, b)
+    assert list(P.segment_stream([], cfg)) == []
