@@ -51,7 +51,9 @@ __device__ void km_derive(KmState* st) {
         const double e_max_mag = e_max / (D + 3);  // largest |distance| the fp32 path can produce
         // two distances, 1.5x safety; plus the index tag written over the low mantissa bits of each distance
         st->tau_tight = (float)(2.0 * 1.5 * e_max * 5.9604644775390625e-08);
-        st->tau = (float)(2.0 * 1.5 * e_max * 5.9604644775390625e-08 + 2.0 * e_max_mag * (K <= 8 ? 8.0 : 64.0) * 1.1920928955078125e-07);
+        const int tag_bits = K <= 8 ? 3 : K <= 16 ? 4 : K <= 32 ? 5 : 6;
+        st->tag_bits = tag_bits;
+        st->tau = (float)(2.0 * 1.5 * e_max * 5.9604644775390625e-08 + 2.0 * e_max_mag * (double)(1 << tag_bits) * 1.1920928955078125e-07);
         // never-chosen padding centroids: the kernels evaluate centroids in groups of 8
         for (int j = K; j < KM_MAXK && j < ((K + 7) & ~7); ++j) {
             st->bias32[j] = 1e30f;  // finite: the index tag must not turn it into a NaN

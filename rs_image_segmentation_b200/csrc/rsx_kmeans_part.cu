@@ -51,16 +51,15 @@ __device__ __noinline__ int km_exact_argmin(const float* __restrict__ stack, int
 // Index-in-mantissa argmin: the low BITS bits of the fp32 distance are replaced by the centroid index, so best/runner-up
 // tracking is three FMNMX and no index bookkeeping.  The perturbation (< 2^BITS ulp) is part of the near-tie bound tau;
 // anything closer than tau is decided in float64 anyway, so fp32 ties never pick a label.
-template <int BITS>
-__device__ __forceinline__ float km_tag(float a, int j) { return __uint_as_float((__float_as_uint(a) & ~((1u << BITS) - 1u)) | (unsigned)j); }
+__device__ __forceinline__ float km_tag(float a, unsigned keep_mask, int j) { return __uint_as_float((__float_as_uint(a) & keep_mask) | (unsigned)j); }
 #define KM_ARGMIN_TAGGED(A, B_, S_, J)            \
     {                                             \
-        const float t_ = km_tag<BITS>(A, J);      \
+        const float t_ = km_tag(A, KEEP, J);      \
         S_ = fminf(S_, fmaxf(t_, B_));            \
         B_ = fminf(B_, t_);                       \
     }
 
-__host__ __device__ constexpr int km_idx_bits(int KU) { return KU == 8 ? 3 : 6; }
+// tag width: 3 bits for the unrolled K <= 8 path; 4 / 5 / 6 bits for K <= 16 / 32 / 64 (g_km.tag_bits, set with tau)
 
 constexpr int KM_THREADS = 128;
 constexpr int KM_SLOTS = 8;
@@ -70,7 +69,7 @@ constexpr int KM_SLOTS = 8;
 // padding slots carry bias 1e30).  KU = 0: any K, chunks of 8 centroids with the weights in shared memory.
 template <int D, int KU>
 __device__ __forceinline__ void km_distances(const float4* v, int K, const float* __restrict__ wsm, float (&b)[4], float (&s)[4]) {
-    constexpr int BITS = km_idx_bits(KU);
+    const unsigned KEEP = KU == 8 ? ~7u : ~((1u << g_km.tag_bits) - 1u);
     b[0] = b[1] = b[2] = b[3] = INFINITY;
     s[0] = s[1] = s[2] = s[3] = INFINITY;
     if (KU > 0) {
@@ -88,13 +87,14 @@ __device__ __forceinline__ void km_distances(const float4* v, int K, const float
             KM_ARGMIN_TAGGED(a23.x, b[2], s[2], j) KM_ARGMIN_TAGGED(a23.y, b[3], s[3], j)
         }
     } else {
-        // K > 8: chunks of 8 centroids, weights from shared memory (wsm = [D][KP] then bias [KP], KP = K rounded up to 8;
-        // padding slots carry bias 1e30); broadcast LDS.128, small code whatever K is
+        // K > 8: chunks of 8 centroids, weights from shared memory (wsm = [chunk][D][8] then bias [KP], KP = K rounded up to
+        // 8; padding slots carry bias 1e30); broadcast LDS.128 at immediate offsets from one base, small code whatever K is
         const int KP = (K + 7) & ~7;
         const float* bias = wsm + D * KP;
 #pragma unroll 1
         for (int jc = 0; jc < KP; jc += 8) {
             float2 a[8][2];
+            const float* wc = wsm + jc * D;  // this chunk's [D][8] block
             {
                 const float4 bA = *reinterpret_cast<const float4*>(bias + jc), bB = *reinterpret_cast<const float4*>(bias + jc + 4);
                 const float bb[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
@@ -103,7 +103,7 @@ __device__ __forceinline__ void km_distances(const float4* v, int K, const float
             }
 #pragma unroll
             for (int d = 0; d < D; ++d) {
-                const float4 wA = *reinterpret_cast<const float4*>(wsm + d * KP + jc), wB = *reinterpret_cast<const float4*>(wsm + d * KP + jc + 4);
+                const float4 wA = *reinterpret_cast<const float4*>(wc + d * 8), wB = *reinterpret_cast<const float4*>(wc + d * 8 + 4);
                 const float ww[8] = {wA.x, wA.y, wA.z, wA.w, wB.x, wB.y, wB.z, wB.w};
                 const float2 x01 = make_float2(v[d].x, v[d].y), x23 = make_float2(v[d].z, v[d].w);
 #pragma unroll
@@ -124,15 +124,20 @@ __device__ __forceinline__ void km_distances(const float4* v, int K, const float
 // label of one pixel from its tagged best/second distances (+ float64 decision of near ties, + inertia)
 // K > 8: the 6-bit index tags widen the near-tie band five-fold.  Before paying for float64, redo the K distances of this one
 // pixel in fp32 WITHOUT tags (same FMA order, weights from shared memory) and apply the rounding-only bound tau_tight.
+// (cold path: re-loads the pixel's features, an L2 hit, so that the hot loop keeps nothing in local memory)
 template <int D>
-__device__ __noinline__ bool km_recheck_fp32(const float (&x)[D], int K, const float* __restrict__ wsm, int* bi_out) {
+__device__ __noinline__ bool km_recheck_fp32(const float* __restrict__ stack, int64_t plane_stride, int64_t p, int K, const float* __restrict__ wsm,
+                                             int* bi_out) {
     const int KP = (K + 7) & ~7;
+    float x[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) x[d] = stack[d * plane_stride + p];
     float b = INFINITY, s = INFINITY;
     int bi = 0;
     for (int j = 0; j < K; ++j) {
         float a = wsm[D * KP + j];
 #pragma unroll
-        for (int d = 0; d < D; ++d) a = fmaf(x[d], wsm[d * KP + j], a);
+        for (int d = 0; d < D; ++d) a = fmaf(x[d], wsm[(j >> 3) * (D * 8) + d * 8 + (j & 7)], a);
         KM_ARGMIN_STEP(a, b, s, bi, j)
     }
     *bi_out = bi;
@@ -142,11 +147,11 @@ __device__ __noinline__ bool km_recheck_fp32(const float (&x)[D], int K, const f
 template <int D, int KU, bool INERTIA>
 __device__ __forceinline__ int km_decide(const float* __restrict__ stack, int64_t plane_stride, int64_t p, const float (&x)[D], float best, float second,
                                          const float* __restrict__ wsm, double& inertia, unsigned& ties) {
-    int bi = (int)(__float_as_uint(best) & ((1u << km_idx_bits(KU)) - 1u));
+    int bi = (int)(__float_as_uint(best) & (KU == 8 ? 7u : ((1u << g_km.tag_bits) - 1u)));
     double dist_exact = -1.0;
     if (!(second - best > g_km.tau)) {  // near tie (or NaN): decide in float64
         bool decided = false;
-        if (KU == 0) decided = km_recheck_fp32<D>(x, g_km.K, wsm, &bi);
+        if (KU == 0) decided = km_recheck_fp32<D>(stack, plane_stride, p, g_km.K, wsm, &bi);
         if (!decided) {
             bi = km_exact_argmin<D>(stack, plane_stride, p, &dist_exact);
             ++ties;
@@ -435,8 +440,8 @@ __global__ void __launch_bounds__(KM_THREADS, 4) km_stream_kernel(const float* _
     long long* wacc = wacc_all + warp * K * (D + 1);
     if (KU == 0) {
         const int KP = (K + 7) & ~7;
-        for (int i = tid; i < D * KP; i += KM_THREADS) {
-            const int d = i / KP, j = i - d * KP;
+        for (int i = tid; i < D * KP; i += KM_THREADS) {  // [chunk][D][8]
+            const int c = i / (D * 8), r = i - c * (D * 8), d = r >> 3, j = c * 8 + (r & 7);
             wsm[i] = g_km.w32[j * KM_MAXD + d];
         }
         for (int j = tid; j < KP; j += KM_THREADS) wsm[D * KP + j] = g_km.bias32[j];

@@ -26,6 +26,8 @@ struct __align__(16) KmState {
     double shift_sq;
     int n_empty;
     int n_updates;
+    int tag_bits;  // width of the index tag in the fp32 distances: 3 (K <= 8), 4, 5, 6
+    int pad1;
 };
 
 
