@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(KM_THREADS, 2) km_full_kernel(const float* __r
 // tensor map) that complete on the stage's "full" mbarrier; n_stages blocks are in flight per CTA, so HBM latency is
 // decoupled from registers and the kernel runs at up to four CTAs per SM.  Every thread takes its 4 pixels of a block
 // (one LDS.128 per plane).  The warps of a CTA are NOT kept in lockstep: a warp that is done with a stage arrives on the
-// stage's "empty" mbarrier, and the producer refills a stage one block late, when all four warps have left it.
+// stage's "empty" mbarrier, and the last warp out (it sees the phase complete; a ticket makes it unique) refills the stage.
 //   KM_ASSIGN  labels (+ inertia)
 //   KM_DELTA   labels + the pixels whose label differs from the previous pass move their fixed-point sample between the
 //              clusters' sums: the warp handles its changed pixels together - lane d reads feature d of the pixel from the
@@ -436,7 +436,8 @@ __global__ void __launch_bounds__(KM_THREADS, 4) km_stream_kernel(const float* _
     long long* wacc_all = reinterpret_cast<long long*>(km_smem + (size_t)n_stages * D * KM_BLOCK_PX * 4);       // [4 warps][K][D+1]
     uint64_t* full = reinterpret_cast<uint64_t*>(wacc_all + (SUMS ? KM_WARPS * K * (D + 1) : 0));               // [n_stages]
     uint64_t* empty = full + n_stages;                                                                          // [n_stages]
-    float* wsm = reinterpret_cast<float*>(empty + n_stages);                                                    // KU == 0: [D][KP] weights, [KP] biases
+    int* ticket = reinterpret_cast<int*>(empty + n_stages);                                                     // [n_stages] (+ pad): refills issued per stage
+    float* wsm = reinterpret_cast<float*>(empty + n_stages) + 4;                                                    // KU == 0: [D][KP] weights, [KP] biases
     long long* wacc = wacc_all + warp * K * (D + 1);
     if (KU == 0) {
         const int KP = (K + 7) & ~7;
@@ -454,13 +455,14 @@ __global__ void __launch_bounds__(KM_THREADS, 4) km_stream_kernel(const float* _
     if (SUMS)
         for (int i = tid; i < KM_WARPS * K * (D + 1); i += KM_THREADS) wacc_all[i] = 0;
     if (tid == 0) {
-        for (int s = 0; s < n_stages; ++s) mbar_init(&full[s], 1), mbar_init(&empty[s], KM_WARPS);
+        for (int s = 0; s < n_stages; ++s) mbar_init(&full[s], 1), mbar_init(&empty[s], KM_WARPS), ticket[s] = 0;
         mbar_fence_init();
     }
     __syncthreads();
     auto issue = [&](int64_t blk, int s) {  // one thread: stage block blk
         const int64_t p0 = blk * KM_BLOCK_PX;
         const unsigned bytes = (unsigned)min((int64_t)KM_BLOCK_PX, n4 - p0) * 4u;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads of this stage precede the async refill
         mbar_expect_tx(&full[s], bytes * D);
         float* dst = stages + (size_t)s * D * KM_BLOCK_PX;
 #pragma unroll 1
@@ -477,8 +479,8 @@ __global__ void __launch_bounds__(KM_THREADS, 4) km_stream_kernel(const float* _
     uint32_t pv_next = 0xffffffffu;
     if (prev8 && (int64_t)blockIdx.x * KM_BLOCK_PX + 4 * tid < n4) pv_next = __ldg(reinterpret_cast<const uint32_t*>(prev8 + (int64_t)blockIdx.x * KM_BLOCK_PX + 4 * tid));
 
-    int s = 0, s_prev = -1;
-    unsigned parity = 0, parity_prev = 0;
+    int s = 0, use = 0;  // stage of the current block, how many times that stage has been used before
+    unsigned parity = 0;
     for (int64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
         const int64_t p = blk * KM_BLOCK_PX + 4 * tid;
         const bool valid = p < n4;
@@ -487,13 +489,6 @@ __global__ void __launch_bounds__(KM_THREADS, 4) km_stream_kernel(const float* _
             const int64_t pn = p + (int64_t)gridDim.x * KM_BLOCK_PX;  // previous labels of the next block: in flight during this one
             pv_next = 0xffffffffu;
             if (prev8 && pn < n4) pv_next = __ldg(reinterpret_cast<const uint32_t*>(prev8 + pn));
-        }
-        if (!LOCKSTEP && tid == 0 && s_prev >= 0) {  // refill the stage of the previous block once all four warps have left it
-            const int64_t nb = blk + (int64_t)(n_stages - 1) * gridDim.x;
-            if (nb < n_blocks) {
-                mbar_wait(&empty[s_prev], parity_prev);
-                issue(nb, s_prev);
-            }
         }
         mbar_wait(&full[s], parity);
         const float* st = stages + (size_t)s * D * KM_BLOCK_PX;
@@ -534,11 +529,17 @@ __global__ void __launch_bounds__(KM_THREADS, 4) km_stream_kernel(const float* _
                 if (nb < n_blocks) issue(nb, s);
             }
         } else {
+            // this warp has left stage s; the warp whose arrival completes the phase (the last one out) refills the stage
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);  // this warp has left stage s
+            if (lane == 0) {
+                mbar_arrive(&empty[s]);
+                if (mbar_test(&empty[s], parity) && atomicCAS(&ticket[s], use, use + 1) == use) {
+                    const int64_t nb = blk + (int64_t)n_stages * gridDim.x;
+                    if (nb < n_blocks) issue(nb, s);
+                }
+            }
         }
-        s_prev = s, parity_prev = parity;
-        if (++s == n_stages) s = 0, parity ^= 1u;
+        if (++s == n_stages) s = 0, parity ^= 1u, ++use;
     }
     // ragged tail (n_px % 4 pixels): one thread, scalar
     if (blockIdx.x == 0 && tid == 0) {
@@ -604,7 +605,7 @@ static int km_launch_stream(const KmLaunch& a, cudaStream_t s) {
     auto kern = km_stream_kernel<D, MODE, INERTIA, KU>;
     const int acc_bytes = MODE == KM_ASSIGN ? 0 : KM_WARPS * a.K * (D + 1) * 8;
     const int w_bytes = KU == 0 ? ((D + 1) * ((a.K + 7) & ~7) + (INERTIA ? a.K * D : 0)) * 4 : 0;
-    auto smem_for = [&](int stages) { return stages * D * KM_BLOCK_PX * 4 + acc_bytes + 2 * stages * 8 + w_bytes; };
+    auto smem_for = [&](int stages) { return stages * D * KM_BLOCK_PX * 4 + acc_bytes + 2 * stages * 8 + 16 + w_bytes; };
     // stages: enough blocks in flight per SM to cover HBM latency at full bandwidth (~64 KB/SM), within shared memory
     static int cfg_K = -1, cfg_stages = 0, cfg_per_sm = 0;
     if (cfg_K != a.K) {
