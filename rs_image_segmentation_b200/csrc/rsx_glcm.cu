@@ -551,30 +551,35 @@ __global__ void __launch_bounds__(256) resize_bilinear_kernel(const float* __res
         const float fx = (float)(cx - fxd);
         const int sx = (int)fxd;
         const int x0 = min(max(sx, 0), src_w - 1), x1 = min(max(sx + 1, 0), src_w - 1);
-        // a thread walks down a run of destination rows; the horizontally interpolated source rows are kept from one
-        // destination row to the next (consecutive destination rows share at least one source row when upsampling)
-        auto hrow = [&](int y) -> float {  // y: source row relative to the rows present
-            if (y < 0 || y >= src_rows_avail) return 0.f;
-            const float p = sp[(int64_t)y * src_w + x0], q = sp[(int64_t)y * src_w + x1];
-            return fmaf(f_sub(q, p), fx, p);
-        };
+        // a thread walks down a run of destination rows, four at a time: the 16 taps of four rows are requested before any
+        // of them is used (duplicates between neighbouring rows / threads are L1 hits), so that enough loads are in flight
         const int ly0 = blockIdx.y * rows_per_cta, ly1 = min(dst_rows, ly0 + rows_per_cta);
-        int cy0 = INT_MIN, cy1 = INT_MIN;  // source rows held in r0, r1
-        float r0 = 0.f, r1 = 0.f;
-        for (int ly = ly0; ly < ly1; ++ly) {
-            const int dy = dst_row0 + ly;
-            const double cy = (dy + 0.5) * scale_y - 0.5;
-            const double fyd = floor(cy);
-            const float fy = (float)(cy - fyd);
-            const int sy = (int)fyd;
-            const int y0 = min(max(sy, 0), src_h - 1) - src_row0, y1 = min(max(sy + 1, 0), src_h - 1) - src_row0;
-            float n0, n1;
-            n0 = y0 == cy0 ? r0 : (y0 == cy1 ? r1 : hrow(y0));
-            n1 = y1 == cy1 ? r1 : (y1 == cy0 ? r0 : hrow(y1));
-            r0 = n0, r1 = n1, cy0 = y0, cy1 = y1;
-            const float v = fmaf(f_sub(r1, r0), fy, r0);
-            dp[(int64_t)ly * dst_w + dx] = v;
-            mn = fminf(mn, v), mx = fmaxf(mx, v);
+        for (int lyb = ly0; lyb < ly1; lyb += 4) {
+            float p0[4], q0[4], p1[4], q1[4], fy[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int dy = dst_row0 + min(lyb + u, ly1 - 1);
+                const double cy = (dy + 0.5) * scale_y - 0.5;
+                const double fyd = floor(cy);
+                fy[u] = (float)(cy - fyd);
+                const int sy = (int)fyd;
+                const int y0 = min(max(sy, 0), src_h - 1) - src_row0, y1 = min(max(sy + 1, 0), src_h - 1) - src_row0;
+                const bool ok0 = y0 >= 0 && y0 < src_rows_avail, ok1 = y1 >= 0 && y1 < src_rows_avail;
+                p0[u] = ok0 ? sp[(int64_t)y0 * src_w + x0] : 0.f;
+                q0[u] = ok0 ? sp[(int64_t)y0 * src_w + x1] : 0.f;
+                p1[u] = ok1 ? sp[(int64_t)y1 * src_w + x0] : 0.f;
+                q1[u] = ok1 ? sp[(int64_t)y1 * src_w + x1] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (lyb + u < ly1) {
+                    const float r0 = fmaf(f_sub(q0[u], p0[u]), fx, p0[u]);
+                    const float r1 = fmaf(f_sub(q1[u], p1[u]), fx, p1[u]);
+                    const float v = fmaf(f_sub(r1, r0), fy[u], r0);
+                    dp[(int64_t)(lyb + u) * dst_w + dx] = v;
+                    mn = fminf(mn, v), mx = fmaxf(mx, v);
+                }
+            }
         }
     }
     if (minmax) warp_minmax_commit(mn, mx, minmax + 2 * plane);
@@ -587,7 +592,7 @@ extern "C" int rsx_resize_bilinear_f32(const float* d_src, int src_h_total, int 
                 "rsx_resize_bilinear_f32: bad arguments");
     const double scale_x = 1.0 / ((double)dst_w / (double)src_w), scale_y = 1.0 / ((double)dst_h_total / (double)src_h_total);
     const int gx = ceil_div(dst_w, 256);
-    const int rows_per_cta = max(8, ceil_div(dst_rows, max(1, rsx_num_sms() * 16 / max(1, gx * n_planes))));
+    const int rows_per_cta = 32;  // many small CTAs: tens of waves, so the last partial wave costs a few percent at most
     dim3 grid(gx, ceil_div(dst_rows, rows_per_cta), n_planes);
     resize_bilinear_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_src, src_h_total, src_w, src_row0, src_rows_avail, src_plane_stride, d_dst, dst_w,
                                                                    dst_row0, dst_rows, dst_plane_stride, scale_x, scale_y, rows_per_cta, d_minmax);
