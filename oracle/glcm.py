@@ -189,3 +189,23 @@ def counts_map_c(q, levels, window, step):
     if rc != 0:
         raise RuntimeError(f"oracle_glcm_counts failed: {rc}")
     return out
+
+
+# ------------------------------------------------------------------ closed-form known answers (implementation independent)
+def analytic_stripes(a, b, win):
+    """Closed-form graycoprops means for vertical stripes of levels a, b (columns alternate a, b, a, ...; window starts on an
+    `a` column): what the textbook definition gives, independent of any implementation.
+    0 deg / 45 deg / 135 deg: every pair joins an a and a b column -> symmetric P[a,b] = P[b,a] = 1/2.
+    90 deg: pairs stay inside a column -> P[a,a] = na/(na+nb), P[b,b] = nb/(na+nb) (na, nb = columns of each level)."""
+    d = abs(a - b)
+    cross = dict(contrast=d * d, dissimilarity=d, homogeneity=1.0 / (1.0 + d * d), energy=np.sqrt(0.5), correlation=-1.0)
+    na, nb = (win + 1) // 2, win // 2
+    pa, pb = na / (na + nb), nb / (na + nb)
+    vert = dict(contrast=0.0, dissimilarity=0.0, homogeneity=1.0, energy=np.sqrt(pa * pa + pb * pb), correlation=1.0)
+    return {k: (3 * cross[k] + vert[k]) / 4 for k in cross}
+
+
+def stripes_image(a, b, H, W):
+    q = np.empty((H, W), np.uint8)
+    q[:, 0::2], q[:, 1::2] = a, b
+    return q

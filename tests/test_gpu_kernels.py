@@ -202,3 +202,23 @@ def test_glcm_dense_wide_levels(levels, win):
     ref = og.glcm_features(band, levels, win, 1)
     for k in ref:
         np.testing.assert_allclose(got[k], ref[k], rtol=1e-5, atol=1e-6, err_msg=f"{k} L={levels} w={win}")
+
+
+@pytest.mark.parametrize("win,step", [(7, 1), (5, 1), (3, 1), (7, 7), (11, 1)])
+def test_glcm_props_analytic_known_answers(rsx, win, step):
+    """Vertical stripes / constant image: closed-form textbook values (tests/test_oracle_glcm.py), dense and tiled kernels."""
+    from oracle.glcm import analytic_stripes, stripes_image
+    names = ("contrast", "dissimilarity", "homogeneity", "energy", "correlation")
+    for a, b, L in ((0, 31, 32), (3, 9, 16), (10, 11, 64)):
+        q = stripes_image(a, b, 40, 66)
+        got = _props(rsx, q, L, win, step)
+        # windows starting on an `a` column (even) and on a `b` column (odd) swap na and nb
+        exp_even = analytic_stripes(a, b, win)
+        exp_odd = analytic_stripes(b, a, win)
+        for i, k in enumerate(names):
+            cols = np.arange(got.shape[2]) * step
+            exp = np.where(cols % 2 == 0, exp_even[k], exp_odd[k])
+            np.testing.assert_allclose(got[i], np.broadcast_to(exp, got[i].shape), rtol=1e-5, atol=1e-6, err_msg=f"{k} {a} {b} {L}")
+    got = _props(rsx, np.full((30, 45), 7, np.uint8), 32, win, step)
+    for i, v in enumerate((0, 0, 1, 1, 1)):
+        assert np.all(got[i] == v)

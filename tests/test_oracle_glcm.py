@@ -53,3 +53,21 @@ def test_pair_counts_per_angle():
     q = np.zeros((7, 7), np.uint8)
     cnt = og.counts_map_c(q, 4, 7, 1)[0, 0]
     assert [int(cnt[a].sum()) for a in range(4)] == [42, 36, 42, 36]
+
+
+from oracle.glcm import analytic_stripes, stripes_image  # noqa: E402
+
+
+def test_analytic_known_answers():
+    """Constant image, vertical stripes, horizontal stripes: properties from the definitions, not from an implementation."""
+    for win in (3, 5, 7):
+        for a, b, L in ((0, 31, 32), (3, 9, 16), (10, 11, 64)):
+            m = og.props_map_numpy(stripes_image(a, b, win, win), L, win, 1)[:, 0, 0]
+            exp = analytic_stripes(a, b, win)
+            for i, k in enumerate(og.PROPS):
+                assert abs(m[i] - exp[k]) < 1e-6, (win, a, b, k, m[i], exp[k])
+            # the transposed pattern swaps the roles of 0 deg and 90 deg; the mean over the four angles is unchanged
+            mt = og.props_map_numpy(stripes_image(a, b, win, win).T.copy(), L, win, 1)[:, 0, 0]
+            assert np.allclose(mt, m, atol=1e-6)
+    c = og.props_map_numpy(np.full((7, 7), 5, np.uint8), 32, 7, 1)[:, 0, 0]
+    assert np.allclose(c, [0, 0, 1, 1, 1])
