@@ -331,3 +331,44 @@ def test_segment_stream_matches_single_scene_calls(P):
     for a, b in zip(got, ref):
         assert a.dtype == np.int32 and np.array_equal(a, b)
     assert list(P.segment_stream([], cfg)) == []
+
+
+def test_full_size_scene_properties(P):
+    """BASELINE config B at full size (7000 x 7000 x 7, 49 Mpx): size-independent properties instead of an oracle run -
+    histogram totals, bit-exact index planes on a pixel sample, integer totals consistent with the labels, delta passes ==
+    full passes, and every sampled label is the float64 argmin for the final centroids."""
+    import torch
+    from oracle import features as of
+    from rs_image_segmentation_b200.synth import synth_strip_torch
+    H = W = 7000
+    n = H * W
+    raster = synth_strip_torch(H, W, 7, 0, H, "uint8", seed=7000, device="cuda")
+    fr = P.extract_features(raster, P.FeatureConfig(glcm_window=7, glcm_step=1, glcm_levels=32))
+    assert all(int(fr.stats.hist[b].sum()) == n for b in range(7))
+    rng = np.random.default_rng(0)
+    idx = np.unique(np.concatenate([rng.integers(0, n, 4000), [0, n - 1, W - 1, n - W]]))
+    tidx = torch.from_numpy(idx).cuda()
+    rows = raster.view(-1, 7)[tidx].cpu().numpy().astype(np.float32)
+    norm = fr.stats.norm
+    nb = [((np.clip(rows[:, b], norm[b, 0], norm[b, 1]) - norm[b, 0]) / norm[b, 2]).reshape(-1, 1) for b in range(7)]
+    ix = of.all_indices(nb)
+    for k in P.INDEX_NAMES:
+        assert np.array_equal(fr.planes[fr.names.index(k)][tidx].cpu().numpy(), ix[k].ravel()), k
+    D, K, T = 13, 8, 6
+    out = {}
+    for delta in (True, False):
+        res, km, c0 = P.kmeans_on_features(fr, D, K, T, seed=7000, delta=delta)
+        tot = km.acc[km.n_acc:km.n_acc + K * D + K].cpu().numpy()
+        assert int(tot[K * D:].sum()) == n
+        assert int(res.labels.min()) >= 0 and int(res.labels.max()) < K
+        out[delta] = (tot, res.centroids, res.inertia, res.labels[tidx].cpu().numpy(), km)
+    assert np.array_equal(out[True][0], out[False][0]) and np.array_equal(out[True][1], out[False][1])
+    assert np.array_equal(out[True][3], out[False][3])
+    # sampled labels against a float64 argmin with the final centroids (MinMax-scaled coordinates)
+    km = out[True][4]
+    X = fr.planes[:D][:, tidx].t().to(torch.float64).cpu().numpy() * km.scale + km.min_
+    d2 = ((X[:, None, :] - out[True][1][None, :, :]) ** 2).sum(-1)
+    best = d2.argmin(1)
+    gap = np.partition(d2, 1, axis=1)
+    clear = (gap[:, 1] - gap[:, 0]) > 1e-9                       # leave exact near-ties to the kernel's own float64 rule
+    assert np.array_equal(best[clear], out[True][3][clear])
