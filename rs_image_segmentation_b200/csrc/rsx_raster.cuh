@@ -14,11 +14,11 @@ struct PxPerThread {
     static constexpr int value = 4 / sizeof(T);  // 4 px (u8) or 2 px (u16): PXT*B*sizeof(T) = 4*B bytes = B words
 };
 
-template <typename T, int B, int NSTAGE_ = 3>
+template <typename T, int B, int NSTAGE_ = 3, int SUB_ = 4>
 struct RasterTiles {
     static constexpr int PXT = PxPerThread<T>::value;
     static constexpr int THREADS = 256;
-    static constexpr int SUB = 4;                            // pixel groups per thread per tile
+    static constexpr int SUB = SUB_;                         // pixel groups per thread per tile
     static constexpr int TILE_PX = THREADS * PXT * SUB;      // 4096 (u8) / 2048 (u16)
     static constexpr int TILE_BYTES = TILE_PX * B * (int)sizeof(T);
     static constexpr int NSTAGE = NSTAGE_;
@@ -46,9 +46,9 @@ __device__ __forceinline__ void unpack_pixels(const uint32_t (&w)[B], int (&v)[P
 
 // Persistent tile loop.  body(tile_smem_words, first_pixel_of_tile, pixels_in_tile) is called by all
 // threads of the CTA for every tile the CTA owns; a partial last tile is staged with plain loads.
-template <typename T, int B, int NSTAGE, typename Body>
+template <typename T, int B, int NSTAGE, int SUB = 4, typename Body>
 __device__ __forceinline__ void for_each_tile(const T* __restrict__ raster, int64_t n_px, unsigned char* smem_raw, Body body) {
-    using RT = RasterTiles<T, B, NSTAGE>;
+    using RT = RasterTiles<T, B, NSTAGE, SUB>;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + RT::NSTAGE * RT::TILE_BYTES);
     const int64_t n_tiles = (n_px + RT::TILE_PX - 1) / RT::TILE_PX;
     const int tid = threadIdx.x;

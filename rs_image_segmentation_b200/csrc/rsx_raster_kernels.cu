@@ -36,24 +36,58 @@ __global__ void __launch_bounds__(256) hist_u8_kernel(const uint8_t* __restrict_
     }
 }
 
-// uint16: 65536 bins per band live in global memory (L2 atomics).  (Merging equal values inside a warp with match_any was
-// measured and is no faster; an exact two-pass digit histogram restricted to the needed order statistics is the next step.)
+// uint16: the low `nb` values of every band are counted in shared memory - 16-bit counters, two per 32-bit word, bumped with
+// 32-bit shared atomics and flushed to the global [B][65536] histogram before any of them can wrap (every < 65536 pixels of
+// the CTA); values >= nb (rare for reflectance data) go to global atomics directly.  512-pixel tiles leave ~200 KB for the
+// counters (nb ~ 7.8 k for 13 bands).  A lane reads one 32-bit word = 2 samples of neighbouring bands, so lanes that can
+// collide on a bin are B/2 words apart.
 template <int B>
-__global__ void __launch_bounds__(256) hist_u16_kernel(const uint16_t* __restrict__ raster, int64_t n_px, uint32_t* __restrict__ hist) {
-    using RT = RasterTiles<uint16_t, B, 2>;
+__global__ void __launch_bounds__(256) hist_u16_kernel(const uint16_t* __restrict__ raster, int64_t n_px, uint32_t* __restrict__ hist, int nb) {
+    using RT = RasterTiles<uint16_t, B, 2, 1>;
     extern __shared__ __align__(128) unsigned char smem[];
-    (void)sizeof(RT);
-    for_each_tile<uint16_t, B, 2>(raster, n_px, smem, [&](const uint32_t* words, int64_t, int npx) {
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(smem + ((RT::SMEM_BYTES + 15) & ~15));
+    const int n_words = B * nb / 2;
+    for (int i = threadIdx.x; i < n_words; i += 256) cnt[i] = 0;
+    __syncthreads();
+    auto flush = [&]() {
+        __syncthreads();
+        for (int w = threadIdx.x; w < n_words; w += 256) {
+            const uint32_t x = cnt[w];
+            if (x) {
+                cnt[w] = 0;
+                const int i = 2 * w, band = i / nb, v = i - band * nb;  // nb is even: both halves belong to one band
+                if (x & 0xffffu) atomicAdd(&hist[(size_t)band * 65536 + v], x & 0xffffu);
+                if (x >> 16) atomicAdd(&hist[(size_t)band * 65536 + v + 1], x >> 16);
+            }
+        }
+        __syncthreads();
+    };
+    int since_flush = 0;  // pixels (= samples per band) counted since the last flush; CTA-uniform
+    for_each_tile<uint16_t, B, 2, 1>(raster, n_px, smem, [&](const uint32_t* words, int64_t, int npx) {
+        if (since_flush + npx > 65535) {
+            flush();
+            since_flush = 0;
+        }
+        since_flush += npx;
         const int nhalf = npx * B;
         const int nwords = (nhalf + 1) >> 1;
+        auto count = [&](int band, unsigned v) {
+            if ((int)v < nb) {
+                const int i = band * nb + (int)v;
+                atomicAdd(&cnt[i >> 1], (i & 1) ? 65536u : 1u);
+            } else {
+                atomicAdd(&hist[(size_t)band * 65536 + v], 1u);
+            }
+        };
         for (int wi = threadIdx.x; wi < nwords; wi += 256) {
-            uint32_t w = words[wi];
+            const uint32_t w = words[wi];
             int band = (wi * 2) % B;
-            atomicAdd(&hist[(size_t)band * 65536 + (w & 0xffffu)], 1u);
+            count(band, w & 0xffffu);
             band = band + 1 == B ? 0 : band + 1;
-            if (wi * 2 + 1 < nhalf) atomicAdd(&hist[(size_t)band * 65536 + (w >> 16)], 1u);
+            if (wi * 2 + 1 < nhalf) count(band, w >> 16);
         }
     });
+    flush();
 }
 
 template <typename K>
@@ -90,10 +124,14 @@ extern "C" int rsx_hist_u16(const uint16_t* d_raster, int64_t n_px, int n_bands,
     RSX_REQUIRE(((uintptr_t)d_raster & 15) == 0, "rsx_hist_u16: raster must be 16-byte aligned");
 #define LAUNCH(BB)                                                                                    \
     {                                                                                                 \
-        using RT = RasterTiles<uint16_t, BB, 2>;                                                      \
-        if (int rc = set_smem(hist_u16_kernel<BB>, RT::SMEM_BYTES)) return rc;                        \
-        int grid = persistent_grid(ceil_div(n_px, (int64_t)RT::TILE_PX), 2);                          \
-        hist_u16_kernel<BB><<<grid, 256, RT::SMEM_BYTES, (cudaStream_t)stream>>>(d_raster, n_px, d_hist); \
+        using RT = RasterTiles<uint16_t, BB, 2, 1>;                                                   \
+        const int tile_bytes = (RT::SMEM_BYTES + 15) & ~15;                                           \
+        int nb = ((226 * 1024 - tile_bytes) / (2 * BB)) & ~1;                                         \
+        nb = nb > 65536 ? 65536 : nb;                                                                 \
+        const int smem = tile_bytes + BB * nb * 2;                                                    \
+        if (int rc = set_smem(hist_u16_kernel<BB>, smem)) return rc;                                  \
+        int grid = persistent_grid(ceil_div(n_px, (int64_t)RT::TILE_PX), 1);                          \
+        hist_u16_kernel<BB><<<grid, 256, smem, (cudaStream_t)stream>>>(d_raster, n_px, d_hist, nb);   \
     }
     RSX_DISPATCH_BANDS(n_bands, LAUNCH)
 #undef LAUNCH

@@ -222,3 +222,22 @@ def test_glcm_props_analytic_known_answers(rsx, win, step):
     got = _props(rsx, np.full((30, 45), 7, np.uint8), 32, win, step)
     for i, v in enumerate((0, 0, 1, 1, 1)):
         assert np.all(got[i] == v)
+
+
+@pytest.mark.parametrize("B,n_px", [(13, 12_000_003), (5, 3_000_001), (13, 70_001)])
+def test_hist_u16_large_and_mixed_range(rsx, B, n_px):
+    """uint16 histogram: shared-memory 16-bit counters with periodic flushes (> 65535 pixels per CTA), values above the
+    shared window, a constant band (one bin takes every sample) - against torch.bincount."""
+    import torch
+    from rs_image_segmentation_b200.device import ptr, stream_ptr
+    g = torch.Generator(device="cuda").manual_seed(n_px)
+    r = torch.randint(0, 9000, (n_px, B), generator=g, device="cuda", dtype=torch.int32)
+    r[:, 1] = torch.randint(0, 65536, (n_px,), generator=g, device="cuda", dtype=torch.int32)      # full 16-bit range
+    r[:, 2] = 4321                                                                                 # one hot bin
+    r[:, 3] = torch.randint(7000, 9000, (n_px,), generator=g, device="cuda", dtype=torch.int32)   # straddles the window edge
+    d = r.to(torch.int16).contiguous()                       # uint16 bit patterns
+    h = torch.zeros((B, 65536), dtype=torch.int32, device="cuda")
+    rsx.call("rsx_hist_u16", ptr(d), n_px, B, ptr(h), stream_ptr())
+    for b in range(B):
+        ref = torch.bincount(r[:, b].to(torch.int64), minlength=65536)
+        assert torch.equal(h[b].to(torch.int64), ref), b
