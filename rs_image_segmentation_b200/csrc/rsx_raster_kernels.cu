@@ -330,6 +330,7 @@ struct PcaParams {
     NormParam norm[B];
     float center[B];
     double scale[B];
+    double inv_scale[B], inv_den[B];  // reciprocals for the uint16 arithmetic path
     const float* lut;  // device [B][256] (uint8 rasters), [B][65536] (uint16 rasters, optional) or nullptr
 };
 
@@ -341,8 +342,16 @@ __device__ __forceinline__ void scaled_pixel(const int (&raw)[B], const PcaParam
             x[b] = lut_s[b * 256 + raw[b]];
         else if (P.lut)
             x[b] = __ldg(P.lut + b * 65536 + raw[b]);  // built by pca_lut_u16_kernel with the expression below
-        else
-            x[b] = __double2float_rn(__ddiv_rn((double)f_sub(norm_apply((float)raw[b], P.norm[b]), P.center[b]), P.scale[b]));
+        else {
+            // uint16 without a table: the two divisions (float32 by den, float64 by scale_) become float64 multiplications
+            // by the reciprocals.  The product is within 1 ulp(double) of the quotient, so the float32 result differs from
+            // sklearn's only when the quotient sits within 2^-29 (relative) of a float32 rounding boundary - a 1-ulp
+            // difference in ~1 sample per 10^8, far below the 1e-5 bar of the PCA outputs (the index maps, which must be
+            // bit exact, never use this path).
+            const float num = f_sub(f_clip((float)raw[b], P.norm[b].lo, P.norm[b].hi), P.norm[b].lo);
+            const float n = __double2float_rn(__dmul_rn((double)num, P.inv_den[b]));
+            x[b] = __double2float_rn(__dmul_rn((double)f_sub(n, P.center[b]), P.inv_scale[b]));
+        }
     }
 }
 
@@ -494,6 +503,8 @@ static void fill_pca_params(PcaParams<B>& P, const float* h_norm, const float* h
         P.norm[b] = h_norm ? NormParam{h_norm[3 * b], h_norm[3 * b + 1], h_norm[3 * b + 2]} : NormParam{0.f, 1.f, 1.f};
         P.center[b] = h_center ? h_center[b] : 0.f;
         P.scale[b] = h_scale ? h_scale[b] : 1.0;
+        P.inv_scale[b] = 1.0 / P.scale[b];
+        P.inv_den[b] = h_norm ? 1.0 / (double)h_norm[3 * b + 2] : 1.0;
     }
     P.lut = d_lut;
 }

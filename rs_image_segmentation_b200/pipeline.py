@@ -45,6 +45,7 @@ class FeatureConfig:
     # raster holds raw 8-bit DNs; (gain, bias) per band, e.g. (hoststats.TM_GAIN, hoststats.TM_BIAS).  None = raster is
     # already the stage-1 output (what scripts/2_feature_extraction.py reads).
     stage1: Optional[Tuple[Sequence[float], Sequence[float]]] = None
+    u16_level_table: bool = False                                # uint16 PCA: exact per-level table instead of reciprocal arithmetic
 
 
 @dataclass
@@ -141,8 +142,9 @@ def extract_features(raster: torch.Tensor, cfg: FeatureConfig = FeatureConfig(),
     center = np.ascontiguousarray(stats.center, dtype=np.float32)
     scale = np.ascontiguousarray(stats.scale, dtype=np.float64)
     lut = lut_inputs = None
-    if is16:
-        # X per 16-bit level, tabulated on the device with the per-sample arithmetic (3.4 MB for 13 bands, L2 resident)
+    if is16 and cfg.u16_level_table:
+        # X per 16-bit level, tabulated on the device with the exact per-sample arithmetic (3.4 MB for 13 bands, L2
+        # resident).  Off by default: 13 scattered 4-byte gathers per pixel cost more than the reciprocal arithmetic.
         lut = torch.empty((B, 65536), dtype=torch.float32, device=dev)
         d_norm, d_center, d_scale = torch.from_numpy(norm).to(dev), torch.from_numpy(center).to(dev), torch.from_numpy(scale).to(dev)
         _lib.call("rsx_pca_build_lut_u16", ptr(d_norm), ptr(d_center), ptr(d_scale), B, ptr(lut), st)

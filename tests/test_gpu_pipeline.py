@@ -110,11 +110,13 @@ def test_synthetic_u8_features(P, H, W, win, step, seed):
     _mm_check(fr)
 
 
-def test_synthetic_u16_13band_features(P):
+@pytest.mark.parametrize("level_table", [False, True])
+def test_synthetic_u16_13band_features(P, level_table):
+    """uint16 x 13 bands; the PCA's scaled values either by reciprocal arithmetic (default) or from the exact per-level table."""
     import torch
     from rs_image_segmentation_b200.synth import synth_raster_numpy
     bip = synth_raster_numpy(150, 203, 13, np.uint16, 7, cell=16)
-    cfg = P.FeatureConfig(band_map=(1, 2, 3, 7, 11), n_components=6, glcm=False)
+    cfg = P.FeatureConfig(band_map=(1, 2, 3, 7, 11), n_components=6, glcm=False, u16_level_table=level_table)
     fr = P.extract_features(torch.from_numpy(bip.view(np.int16)).cuda(), cfg)
     _check_features(fr, _oracle_features(bip, cfg), cfg)
     _mm_check(fr)
