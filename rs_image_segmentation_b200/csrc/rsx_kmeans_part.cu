@@ -12,6 +12,9 @@
 // GPUs and any atomic ordering give bit-identical sums, hence bit-identical centroids.  For the same reason a DELTA pass
 // (only the pixels whose label changed move their sample from one cluster's sum to another's) reproduces exactly the
 // sums of a full pass.
+#include <cstdio>
+#include <cstdlib>
+
 #include "rsx_kmeans_state.cuh"
 
 #ifndef RSX_KM_PART
@@ -626,6 +629,7 @@ static int km_launch_stream(const KmLaunch& a, cudaStream_t s) {
         }
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max(smem_for(best_stages), 48 * 1024));
         cfg_K = a.K, cfg_stages = best_stages, cfg_per_sm = best_per_sm;
+        if (getenv("RSX_DEBUG")) fprintf(stderr, "[rsx] km_stream D=%d K=%d mode=%d: %d stages, %d CTAs/SM, %d B smem\n", D, a.K, MODE, best_stages, best_per_sm, smem_for(best_stages));
     }
     const int64_t n4 = a.n_px & ~(int64_t)3;
     const int64_t n_blocks = ceil_div(n4, (int64_t)KM_BLOCK_PX);
