@@ -373,9 +373,8 @@ class DeviceKMeans:
         self.stride = planes.stride(0)
         self.row_len = int(row_len)
         self.n_global = int(n_global)
-        self.fmin = np.ascontiguousarray(feat_min, dtype=np.float64)
-        self.fmax = np.ascontiguousarray(feat_max, dtype=np.float64)
-        self.scale, self.min_ = minmax_scale_params(self.fmin, self.fmax)
+        if feat_min is not None:
+            self.configure(feat_min, feat_max)
         dev = planes.device
         self.state = torch.zeros(int(_lib.load().rsx_kmeans_state_bytes()), dtype=torch.uint8, device=dev)
         # pass sums/counts + near-tie and changed-label counters (all-reduced), then the running totals (rsx.h)
@@ -390,6 +389,13 @@ class DeviceKMeans:
         self.full_passes = max(1, int(full_passes))
         self._labels = None
         self._passes = 0
+
+    def configure(self, feat_min, feat_max):
+        """MinMaxScaler.fit result (per-feature min / max of the raw stack).  May follow the constructor (feat_min=None) so
+        that the device buffers are allocated while the feature kernels are still running."""
+        self.fmin = np.ascontiguousarray(feat_min, dtype=np.float64)
+        self.fmax = np.ascontiguousarray(feat_max, dtype=np.float64)
+        self.scale, self.min_ = minmax_scale_params(self.fmin, self.fmax)
 
     def scale_rows(self, raw_rows: np.ndarray) -> np.ndarray:
         """MinMaxScaler.transform of raw feature rows in float64: X*scale + min_."""
@@ -574,7 +580,10 @@ def kmeans_on_features(fr: FeatureResult, D: int, K: int, n_iter: int, seed: int
     H_total = H_total if H_total is not None else fr.H
     n_global = H_total * fr.W
     idx = draw_init_indices(n_global, K, seed)
-    rows_dev = gather_rows_device(fr.planes, D, fr.n_px, idx, first_row * fr.W, comm)   # asynchronous
+    km = DeviceKMeans(fr.planes, fr.n_px, D, K, None, None, n_global, fr.W, comm, timer, delta)   # buffers first, ...
+    if km.delta:
+        km._label_planes()
+    rows_dev = gather_rows_device(fr.planes, D, fr.n_px, idx, first_row * fr.W, comm)   # ... all asynchronous
     mn, mx = fr.minmax.read()                       # the one synchronisation between the feature kernels and KMeans
     if comm.world > 1:
         tmn = torch.from_numpy(mn[:D].copy()).to(fr.planes.device)
@@ -582,7 +591,7 @@ def kmeans_on_features(fr: FeatureResult, D: int, K: int, n_iter: int, seed: int
         comm.all_reduce(tmn, "min")
         comm.all_reduce(tmx, "max")
         mn, mx = tmn.cpu().numpy(), tmx.cpu().numpy()
-    km = DeviceKMeans(fr.planes, fr.n_px, D, K, mn[:D], mx[:D], n_global, fr.W, comm, timer, delta)
+    km.configure(mn[:D], mx[:D])
     c0 = km.scale_rows(rows_dev.cpu().numpy())
     res = km.fit(c0, n_iter, labels_i32)
     return res, km, c0
