@@ -266,10 +266,14 @@ def run_rsx(args):
 
         # the public host-buffer API, pipelined over the steps: every step's H2D (pinned raster) and D2H (int32 labels) are
         # inside the timed region; the copy engines work under the kernels of the neighbouring steps
+        yields = []
+
         def e2e_run(steps):
             last = None
+            yields.clear()
             for labels, res in P.segment_stream((pinned for _ in range(steps)), cfg, K, T, 7000, D, comm, H_total, bounds):
                 last = int(labels[0, 0]) + res.n_iter          # touch the result on the host
+                yields.append(time.perf_counter())
             return last
 
         e2e_run(2)
@@ -280,6 +284,11 @@ def run_rsx(args):
                "d2h_bytes_per_step": int(H * W * 4) * world, "ms_per_step": ms_e2e, "steps": e2e_steps,
                "api": "pipeline.segment_stream (double-buffered H2D / D2H on the copy engines); one scene alone through "
                       "pipeline.segment_raster: see single_scene_ms"}
+        if len(yields) >= 4:
+            # host-clock interval between consecutive label arrays in the middle of the run: what a long stream of scenes
+            # costs per scene; ms_per_step above also carries the first upload and the last download of this short run
+            gaps = np.diff(np.array(yields[:-1])) * 1e3
+            e2e["steady_state_ms_per_step"] = float(np.median(gaps[1:])) if len(gaps) > 1 else float(gaps[0])
         for _ in range(2):
             t0 = time.perf_counter()
             P.segment_raster(None, cfg, K, T, 7000, D, comm, H_total, bounds, pinned=pinned)

@@ -46,6 +46,11 @@ const char* rsx_last_error(void);
 int rsx_abi_version(void);
 /* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
 int64_t rsx_launch_count(void);
+/* Copies `bytes` from device memory into PAGE-LOCKED host memory (cudaHostAlloc / torch pin_memory: under unified addressing
+ * the device writes through the same pointer) with a kernel, on `stream`; the caller synchronises.  For the small per-scene
+ * results (histograms, moments, min/max, KMeans state): unlike cudaMemcpyAsync it does not queue behind a large transfer on
+ * the device-to-host copy engine. */
+int rsx_store_to_host(const void* d_src, void* h_mapped_dst, int64_t bytes, rsx_stream_t stream);
 
 /* ---- K1: per-band histograms -------------------------------------------------------------
  * Replaces the sorts inside np.percentile (indices.py:38-39) and RobustScaler's

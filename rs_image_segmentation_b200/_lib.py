@@ -17,6 +17,7 @@ SIGNATURES = {
     "rsx_last_error": (C.c_char_p, []),
     "rsx_abi_version": (i32, []),
     "rsx_launch_count": (i64, []),
+    "rsx_store_to_host": (i32, [vp, vp, i64, vp]),
     "rsx_raster_stats": (i32, [vp, i32, i32, i32, f64, f64, vp, vp, vp, vp, vp, vp]),
     "rsx_hist_u8": (i32, [vp, i64, i32, vp, vp]),
     "rsx_hist_u16": (i32, [vp, i64, i32, vp, vp]),

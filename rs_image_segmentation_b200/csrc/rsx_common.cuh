@@ -11,6 +11,8 @@
 void rsx_set_error(const char* fmt, ...);
 int rsx_check_launch(const char* what);
 int rsx_num_sms();
+// device -> host of a small block through a kernel store into a page-locked staging buffer; synchronises the stream
+int rsx_fetch_small(void* h_dst, const void* d_src, size_t bytes, cudaStream_t s);
 
 #define RSX_REQUIRE(cond, ...)          \
     do {                                \

@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 
 #include "rsx_common.cuh"
 
@@ -41,6 +42,54 @@ int rsx_num_sms() {
 extern "C" const char* rsx_last_error(void) { return g_err; }
 extern "C" int rsx_abi_version(void) { return 1; }
 extern "C" int64_t rsx_launch_count(void) { return g_launches.load(); }
+
+// ----------------------------------------------------------------------------- small results to the host without a copy engine
+// The device-to-host copy engine serves one transfer at a time; a histogram or min/max read-back queued behind a scene-sized
+// label download waits for all of it (3.5 ms at 196 MB).  A kernel that stores straight into page-locked (mapped) host memory
+// does not queue there.
+__global__ void store_to_host_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int64_t n16, int64_t n) {
+    const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = i0; i < n16; i += stride) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
+    for (int64_t i = (n16 << 4) + i0; i < n; i += stride) dst[i] = src[i];
+}
+
+extern "C" int rsx_store_to_host(const void* d_src, void* h_mapped_dst, int64_t bytes, rsx_stream_t stream) {
+    RSX_REQUIRE(d_src && h_mapped_dst && bytes >= 0, "rsx_store_to_host: bad arguments");
+    if (bytes == 0) return RSX_OK;
+    const bool vec = (((uintptr_t)d_src | (uintptr_t)h_mapped_dst) & 15) == 0;
+    const int64_t n16 = vec ? bytes >> 4 : 0;
+    const int64_t work = vec ? n16 + 15 : bytes;
+    const int grid = (int)max((int64_t)1, min((work + 255) / 256, (int64_t)rsx_num_sms() * 4));
+    store_to_host_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint8_t*)d_src, (uint8_t*)h_mapped_dst, n16, bytes);
+    return rsx_check_launch("store_to_host");
+}
+
+int rsx_fetch_small(void* h_dst, const void* d_src, size_t bytes, cudaStream_t s) {
+    static std::mutex mu;
+    static void* stage = nullptr;
+    static size_t cap = 0;
+    std::lock_guard<std::mutex> lock(mu);
+    if (bytes > cap) {
+        if (stage) cudaFreeHost(stage);
+        stage = nullptr, cap = 0;
+        const size_t want = max(bytes, (size_t)1 << 16);
+        cudaError_t e = cudaHostAlloc(&stage, want, cudaHostAllocDefault);
+        if (e != cudaSuccess) {
+            stage = nullptr;
+            rsx_set_error("rsx_fetch_small: cudaHostAlloc(%zu): %s", want, cudaGetErrorString(e));
+            return RSX_ERR_CUDA;
+        }
+        cap = want;
+    }
+    if (int rc = rsx_store_to_host(d_src, stage, (int64_t)bytes, (rsx_stream_t)s)) return rc;
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) {
+        rsx_set_error("rsx_fetch_small: %s", cudaGetErrorString(e));
+        return RSX_ERR_CUDA;
+    }
+    memcpy(h_dst, stage, bytes);
+    return RSX_OK;
+}
 
 // ----------------------------------------------------------------------------- min/max trackers
 __global__ void minmax_init_kernel(uint32_t* mm, int n) {

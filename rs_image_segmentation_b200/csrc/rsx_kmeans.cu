@@ -256,13 +256,7 @@ extern "C" int rsx_kmeans_update(void* d_state, int64_t* d_acc, int delta, int D
 extern "C" int rsx_kmeans_fixed_point_scales(const void* d_state, double* h_pow2, rsx_stream_t stream) {
     RSX_REQUIRE(d_state && h_pow2, "rsx_kmeans_fixed_point_scales: bad arguments");
     static thread_local KmState h;
-    cudaStream_t s = (cudaStream_t)stream;
-    cudaError_t e = cudaMemcpyAsync(&h, d_state, sizeof(h), cudaMemcpyDeviceToHost, s);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-    if (e != cudaSuccess) {
-        rsx_set_error("rsx_kmeans_fixed_point_scales: %s", cudaGetErrorString(e));
-        return RSX_ERR_CUDA;
-    }
+    if (int rc = rsx_fetch_small(&h, d_state, sizeof(h), (cudaStream_t)stream)) return rc;
     for (int d = 0; d < h.D; ++d) h_pow2[d] = (double)h.pow2[d];
     return RSX_OK;
 }
@@ -270,13 +264,7 @@ extern "C" int rsx_kmeans_fixed_point_scales(const void* d_state, double* h_pow2
 extern "C" int rsx_kmeans_read(const void* d_state, double* h_centroids, double* h_shift_sq, int32_t* h_empty, rsx_stream_t stream) {
     RSX_REQUIRE(d_state, "rsx_kmeans_read: bad arguments");
     static thread_local KmState h;
-    cudaStream_t s = (cudaStream_t)stream;
-    cudaError_t e = cudaMemcpyAsync(&h, d_state, sizeof(h), cudaMemcpyDeviceToHost, s);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-    if (e != cudaSuccess) {
-        rsx_set_error("rsx_kmeans_read: %s", cudaGetErrorString(e));
-        return RSX_ERR_CUDA;
-    }
+    if (int rc = rsx_fetch_small(&h, d_state, sizeof(h), (cudaStream_t)stream)) return rc;
     if (h_centroids)
         for (int j = 0; j < h.K; ++j)
             for (int d = 0; d < h.D; ++d) h_centroids[j * h.D + d] = h.cent64[j * KM_MAXD + d] + h.mean64[d];

@@ -43,6 +43,25 @@ def to_device(a: np.ndarray, pinned: bool = True):
     return t.cuda(non_blocking=True)
 
 
+_FETCH_STAGE = {}
+
+
+def fetch(t: torch.Tensor) -> np.ndarray:
+    """Small device tensor -> new numpy array; synchronises the current stream.  A kernel stores the bytes straight into
+    page-locked host memory (rsx_store_to_host), so the read-back never waits behind a large transfer on the copy engine."""
+    t = t.contiguous()
+    nbytes = t.numel() * t.element_size()
+    if nbytes == 0:
+        return t.cpu().numpy()
+    cap = max(4096, 1 << (nbytes - 1).bit_length())
+    stage = _FETCH_STAGE.get(cap)
+    if stage is None:
+        stage = _FETCH_STAGE[cap] = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+    _lib.call("rsx_store_to_host", ptr(t), C.c_void_p(stage.data_ptr()), nbytes, stream_ptr())
+    torch.cuda.current_stream().synchronize()
+    return stage[:nbytes].view(t.dtype).reshape(t.shape).numpy().copy()
+
+
 class MinMaxTracker:
     """uint32 [n][2] device tracker (include/rsx.h 'min/max trackers')."""
 
@@ -56,7 +75,7 @@ class MinMaxTracker:
 
     def read(self):
         """(min float32[n], max float32[n]); synchronises."""
-        h = self.buf.cpu().numpy().view(np.uint32)
+        h = fetch(self.buf).view(np.uint32)
         mn, mx = np.zeros(self.n, np.float32), np.zeros(self.n, np.float32)
         _lib.load().rsx_minmax_decode(hptr(np.ascontiguousarray(h)), self.n, hptr(mn), hptr(mx))
         return mn, mx

@@ -17,6 +17,7 @@ folds its output's min/max into a tracker so MinMaxScaler.fit costs no extra pas
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence, Tuple
 
@@ -24,7 +25,7 @@ import numpy as np
 import torch
 
 from . import _lib, hoststats
-from .device import NO_TIMER, MinMaxTracker, StageTimer, hptr, ptr, require_cuda, stream_ptr
+from .device import NO_TIMER, MinMaxTracker, StageTimer, fetch, hptr, ptr, require_cuda, stream_ptr
 from .dist import Comm, glcm_rows_needed, strip_bounds
 
 INDEX_NAMES = ("ndvi", "evi", "msavi", "ndwi", "mndwi", "ndbi", "bsi")       # RSX plane order (rsx.h)
@@ -107,9 +108,9 @@ def extract_features(raster: torch.Tensor, cfg: FeatureConfig = FeatureConfig(),
         with timer("hist_allreduce"):
             hist64 = hist.to(torch.int64) & 0xFFFFFFFF      # the kernel's counters are uint32
             comm.all_reduce(hist64)
-        hist_host = hist64.cpu().numpy()
+        hist_host = fetch(hist64)
     else:
-        hist_host = hist.cpu().numpy().view(np.uint32).astype(np.int64)
+        hist_host = fetch(hist).view(np.uint32).astype(np.int64)
     remap = None
     hist_raw = hist_host
     if cfg.stage1 is not None:
@@ -164,8 +165,8 @@ def extract_features(raster: torch.Tensor, cfg: FeatureConfig = FeatureConfig(),
     if comm.world > 1:
         with timer("pca_allreduce"):
             comm.all_reduce(moments)
-    moments_host = torch.empty(M, dtype=torch.float64, pin_memory=True)
-    moments_host.copy_(moments, non_blocking=True)
+    moments_host = _pinned_f64(M)
+    _lib.call("rsx_store_to_host", ptr(moments), C.c_void_p(moments_host.data_ptr()), M * 8, st)   # not through the copy engine
     moments_ready = torch.cuda.Event()
     moments_ready.record()
 
@@ -192,7 +193,7 @@ def extract_features(raster: torch.Tensor, cfg: FeatureConfig = FeatureConfig(),
 
     # ---- K3b eigh on the host (the device is busy with K4), projection
     moments_ready.synchronize()
-    pca = hoststats.pca_from_moments(moments_host.numpy(), n_global, n_comp)
+    pca = hoststats.pca_from_moments(moments_host.numpy().copy(), n_global, n_comp)
     comps = np.ascontiguousarray(pca["components"], dtype=np.float32)
     mean32 = pca["mean"].astype(np.float32)
     # sklearn: X_transformed -= mean_ @ components_.T, both float32 for float32 data
@@ -502,13 +503,13 @@ class DeviceKMeans:
 
     def changed_count(self) -> int:
         """Pixels (all ranks) whose label changed in the last update pass; synchronises."""
-        return int(self.acc[2 * self.n_acc - 1].item())
+        return int(fetch(self.acc[2 * self.n_acc - 1:])[0])
 
     def near_ties(self) -> int:
         """Pixels (all ranks, all passes) decided by the float64 re-evaluation; collective, synchronises."""
         t = self.acc[self.n_acc - 2:self.n_acc - 1].clone()          # the final assign-only pass is not folded by an update
         self.comm.all_reduce(t)
-        return int(t.item()) + int(self.acc[2 * self.n_acc - 2].item())
+        return int(fetch(t)[0]) + int(fetch(self.acc[2 * self.n_acc - 2:2 * self.n_acc - 1])[0])
 
     def finish(self, labels_i32: bool = True):
         """The extra assignment pass of sklearn (_kmeans.py:742-754) + inertia."""
@@ -555,7 +556,7 @@ class DeviceKMeans:
         if empty:
             raise _lib.RsxError(f"KMeans: {empty} empty cluster(s) met; empty-cluster relocation "
                                 "(sklearn _k_means_common.pyx:167-211) is not implemented on the device")
-        return KMeansResult(labels=labels, centroids=cent, inertia=float(self.inertia.item()), n_iter=n_iter,
+        return KMeansResult(labels=labels, centroids=cent, inertia=float(fetch(self.inertia)[0]), n_iter=n_iter,
                             near_ties=self.near_ties(), shift_sq=shift)
 
     def fit(self, init_centroids_scaled: np.ndarray, n_iter: int, labels_i32: bool = True) -> KMeansResult:
@@ -567,7 +568,7 @@ class DeviceKMeans:
         if empty:
             raise _lib.RsxError(f"KMeans: {empty} empty cluster(s) met; empty-cluster relocation "
                                 "(sklearn _k_means_common.pyx:167-211) is not implemented on the device")
-        return KMeansResult(labels=labels, centroids=cent, inertia=float(self.inertia.item()), n_iter=n_iter,
+        return KMeansResult(labels=labels, centroids=cent, inertia=float(fetch(self.inertia)[0]), n_iter=n_iter,
                             near_ties=self.near_ties(), shift_sq=shift)
 
 
@@ -592,7 +593,7 @@ def kmeans_on_features(fr: FeatureResult, D: int, K: int, n_iter: int, seed: int
         comm.all_reduce(tmx, "max")
         mn, mx = tmn.cpu().numpy(), tmx.cpu().numpy()
     km.configure(mn[:D], mx[:D])
-    c0 = km.scale_rows(rows_dev.cpu().numpy())
+    c0 = km.scale_rows(fetch(rows_dev))
     res = km.fit(c0, n_iter, labels_i32)
     return res, km, c0
 
@@ -628,6 +629,15 @@ def segment_raster(raster_host: np.ndarray, cfg: FeatureConfig = FeatureConfig()
 
 
 _PINNED_LABELS = {}
+_PINNED_F64 = {}
+
+
+def _pinned_f64(n: int) -> torch.Tensor:
+    """Reusable page-locked float64 staging buffer (valid until the next call of the same size)."""
+    buf = _PINNED_F64.get(n)
+    if buf is None:
+        buf = _PINNED_F64[n] = torch.empty(n, dtype=torch.float64, pin_memory=True)
+    return buf
 
 
 def _pinned_labels(n: int) -> torch.Tensor:
@@ -670,6 +680,9 @@ def segment_stream(rasters, cfg: FeatureConfig = FeatureConfig(), n_clusters: in
     consumed = [torch.cuda.Event() for _ in range(2)]       # compute no longer reads dev[k]
     downloaded = [torch.cuda.Event() for _ in range(2)]
 
+    # The copy engines serve one transfer at a time, in order: nothing small may queue there while a scene is being computed.
+    # Every per-scene read-back (histograms, moments, min/max, KMeans state) is therefore a kernel store into page-locked
+    # memory (device.fetch / rsx_store_to_host); behind a 196 MB label download it would wait 3.5 ms.
     def upload(host, k, wait_consumed):
         with torch.cuda.stream(up):
             if wait_consumed:

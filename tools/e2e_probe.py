@@ -6,9 +6,9 @@ from rs_image_segmentation_b200 import pipeline as P
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 12
 H = W = 7000
-g = torch.Generator().manual_seed(1)
-pinned = torch.randint(0, 256, (H, W, 7), dtype=torch.uint8, generator=g).pin_memory()
-cfg = P.FeatureConfig()
+from rs_image_segmentation_b200.synth import synth_strip_torch
+pinned = synth_strip_torch(H, W, 7, 0, H, "uint8", seed=7000, device="cuda").cpu().pin_memory()
+cfg = P.FeatureConfig(glcm_window=7, glcm_step=1, glcm_levels=32)
 for rep in range(2):
     torch.cuda.synchronize()
     t = [time.perf_counter()]
@@ -16,5 +16,6 @@ for rep in range(2):
         t.append(time.perf_counter())
     torch.cuda.synchronize()
     t.append(time.perf_counter())
+    del labels, res
     d = np.diff(np.array(t)) * 1e3
     print("rep", rep, "total/scene %.2f ms" % ((t[-1] - t[0]) * 1e3 / n), "intervals", np.round(d, 2).tolist(), flush=True)
