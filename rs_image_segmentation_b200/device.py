@@ -62,6 +62,16 @@ def fetch(t: torch.Tensor) -> np.ndarray:
     return stage[:nbytes].view(t.dtype).reshape(t.shape).numpy().copy()
 
 
+def stage_to_host(t: torch.Tensor) -> torch.Tensor:
+    """Asynchronous fetch: starts the kernel store of a small device tensor into a NEW page-locked tensor and returns it; the
+    contents are valid after the next synchronisation of the current stream."""
+    t = t.contiguous()
+    host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    if t.numel():
+        _lib.call("rsx_store_to_host", ptr(t), C.c_void_p(host.data_ptr()), t.numel() * t.element_size(), stream_ptr())
+    return host
+
+
 class MinMaxTracker:
     """uint32 [n][2] device tracker (include/rsx.h 'min/max trackers')."""
 

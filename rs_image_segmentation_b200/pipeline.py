@@ -25,7 +25,7 @@ import numpy as np
 import torch
 
 from . import _lib, hoststats
-from .device import NO_TIMER, MinMaxTracker, StageTimer, fetch, hptr, ptr, require_cuda, stream_ptr
+from .device import NO_TIMER, MinMaxTracker, StageTimer, fetch, hptr, ptr, require_cuda, stage_to_host, stream_ptr
 from .dist import Comm, glcm_rows_needed, strip_bounds
 
 INDEX_NAMES = ("ndvi", "evi", "msavi", "ndwi", "mndwi", "ndbi", "bsi")       # RSX plane order (rsx.h)
@@ -511,6 +511,19 @@ class DeviceKMeans:
         self.comm.all_reduce(t)
         return int(fetch(t)[0]) + int(fetch(self.acc[2 * self.n_acc - 2:2 * self.n_acc - 1])[0])
 
+    def _result(self, labels, n_iter: int) -> KMeansResult:
+        """Collects centroids, inertia and counters with ONE synchronisation (the stores into page-locked memory are queued
+        first; reading the state waits for the stream)."""
+        t = self.acc[self.n_acc - 2:self.n_acc - 1].clone()          # near ties of the final assign-only pass
+        self.comm.all_reduce(t)
+        h_inertia, h_last, h_sofar = stage_to_host(self.inertia), stage_to_host(t), stage_to_host(self.acc[2 * self.n_acc - 2:2 * self.n_acc - 1])
+        cent, shift, empty = self.read()
+        if empty:
+            raise _lib.RsxError(f"KMeans: {empty} empty cluster(s) met; empty-cluster relocation "
+                                "(sklearn _k_means_common.pyx:167-211) is not implemented on the device")
+        return KMeansResult(labels=labels, centroids=cent, inertia=float(h_inertia[0]), n_iter=n_iter,
+                            near_ties=int(h_last[0]) + int(h_sofar[0]), shift_sq=shift)
+
     def finish(self, labels_i32: bool = True):
         """The extra assignment pass of sklearn (_kmeans.py:742-754) + inertia."""
         dev = self.planes.device
@@ -551,25 +564,13 @@ class DeviceKMeans:
             _, shift, _ = self.read()
             if shift <= tol:
                 break
-        labels = self.finish(True)
-        cent, shift, empty = self.read()
-        if empty:
-            raise _lib.RsxError(f"KMeans: {empty} empty cluster(s) met; empty-cluster relocation "
-                                "(sklearn _k_means_common.pyx:167-211) is not implemented on the device")
-        return KMeansResult(labels=labels, centroids=cent, inertia=float(fetch(self.inertia)[0]), n_iter=n_iter,
-                            near_ties=self.near_ties(), shift_sq=shift)
+        return self._result(self.finish(True), n_iter)
 
     def fit(self, init_centroids_scaled: np.ndarray, n_iter: int, labels_i32: bool = True) -> KMeansResult:
         self.setup(init_centroids_scaled)
         for _ in range(n_iter):
             self.step()
-        labels = self.finish(labels_i32)
-        cent, shift, empty = self.read()
-        if empty:
-            raise _lib.RsxError(f"KMeans: {empty} empty cluster(s) met; empty-cluster relocation "
-                                "(sklearn _k_means_common.pyx:167-211) is not implemented on the device")
-        return KMeansResult(labels=labels, centroids=cent, inertia=float(fetch(self.inertia)[0]), n_iter=n_iter,
-                            near_ties=self.near_ties(), shift_sq=shift)
+        return self._result(self.finish(labels_i32), n_iter)
 
 
 def kmeans_on_features(fr: FeatureResult, D: int, K: int, n_iter: int, seed: int, comm: Optional[Comm] = None,
@@ -584,7 +585,7 @@ def kmeans_on_features(fr: FeatureResult, D: int, K: int, n_iter: int, seed: int
     km = DeviceKMeans(fr.planes, fr.n_px, D, K, None, None, n_global, fr.W, comm, timer, delta)   # buffers first, ...
     if km.delta:
         km._label_planes()
-    rows_dev = gather_rows_device(fr.planes, D, fr.n_px, idx, first_row * fr.W, comm)   # ... all asynchronous
+    rows_host = stage_to_host(gather_rows_device(fr.planes, D, fr.n_px, idx, first_row * fr.W, comm))   # ... all asynchronous
     mn, mx = fr.minmax.read()                       # the one synchronisation between the feature kernels and KMeans
     if comm.world > 1:
         tmn = torch.from_numpy(mn[:D].copy()).to(fr.planes.device)
@@ -593,7 +594,7 @@ def kmeans_on_features(fr: FeatureResult, D: int, K: int, n_iter: int, seed: int
         comm.all_reduce(tmx, "max")
         mn, mx = tmn.cpu().numpy(), tmx.cpu().numpy()
     km.configure(mn[:D], mx[:D])
-    c0 = km.scale_rows(fetch(rows_dev))
+    c0 = km.scale_rows(rows_host.numpy())
     res = km.fit(c0, n_iter, labels_i32)
     return res, km, c0
 
