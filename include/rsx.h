@@ -37,6 +37,9 @@ extern "C" {
 #define RSX_MAX_BANDS 16
 #define RSX_MAX_FEATURES 32
 #define RSX_MAX_CLUSTERS 64
+#define RSX_MAX_PEERS 8             /* ranks of one node that reduce KMeans sums through peer memory */
+#define RSX_PEER_PASS_ELEMS 2560     /* int64 per pass buffer: >= MAX_CLUSTERS * (MAX_FEATURES + 1) + 2 */
+#define RSX_PEER_BLOCK_BYTES (2 * RSX_PEER_PASS_ELEMS * 8 + RSX_MAX_PEERS * 8)
 #define RSX_NUM_INDICES 7  /* ndvi, evi, msavi, ndwi, mndwi, ndbi, bsi (scripts/2_feature_extraction.py:63-73) */
 #define RSX_NUM_GLCM_PROPS 5 /* contrast, dissimilarity, homogeneity, energy, correlation (indices.py:292-296) */
 
@@ -236,6 +239,20 @@ int rsx_kmeans_assign(const float* d_stack, int64_t plane_stride, int64_t n_px, 
 /* d_adjust (may be NULL): int64 [K*D + K] added to the totals for this centroid computation only - the host-assisted
  * empty-cluster relocation of sklearn (_k_means_common.pyx:167-211); the running totals are not modified by it. */
 int rsx_kmeans_update(void* d_state, int64_t* d_acc, int delta, int D, const int64_t* d_adjust, rsx_stream_t stream);
+/* Multi-GPU (one node, one process per GPU) without a collective: every rank allocates one block of RSX_PEER_BLOCK_BYTES with
+ * rsx_peer_alloc, exchanges the 64-byte handle (e.g. torch.distributed.all_gather) and maps the others with rsx_peer_open.
+ * The assign pass of update number `seq` (1, 2, ... - the same on every rank, never reused) accumulates into the rank's own
+ * block at int64 offset (seq & 1) * RSX_PEER_PASS_ELEMS (pass it as d_acc of rsx_kmeans_assign); rsx_kmeans_update_peers then
+ * waits for all ranks at a flag barrier in peer memory, sums their blocks over NVLink into d_acc's pass block and continues
+ * as rsx_kmeans_update (d_acc = the local [pass | totals] array).  h_peer_blocks: HOST array of `world` device pointers
+ * (own block at [rank]).  A rank that never arrives makes the others time out after 4 s (reported by rsx_kmeans_read). */
+int rsx_peer_alloc(int64_t bytes, void** d_ptr, uint8_t* h_handle64);
+int rsx_peer_open(const uint8_t* h_handle64, void** d_peer);
+int rsx_peer_zero(void* d_ptr, int64_t bytes, rsx_stream_t stream);   /* before a new rsx_kmeans_setup: the two pass buffers */
+int rsx_peer_close(void* d_peer);
+int rsx_peer_free(void* d_ptr);
+int rsx_kmeans_update_peers(void* d_state, int64_t* d_acc, int delta, int D, const int64_t* d_adjust, void* const* h_peer_blocks,
+                            int rank, int world, int64_t seq, rsx_stream_t stream);
 /* SYNCHRONISES: the fixed-point scale 2^shift_d per feature (a raw sample enters the sums as rint(x * scale)). */
 int rsx_kmeans_fixed_point_scales(const void* d_state, double* h_pow2, rsx_stream_t stream);
 /* SYNCHRONISES the stream; centroids come back in scaled, un-centred coordinates, double [K][D];

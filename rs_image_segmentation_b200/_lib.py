@@ -59,6 +59,12 @@ SIGNATURES = {
     "rsx_kmeans_update": (i32, [vp, vp, i32, i32, vp, vp]),
     "rsx_kmeans_fixed_point_scales": (i32, [vp, vp, vp]),
     "rsx_kmeans_read": (i32, [vp, vp, vp, vp, vp]),
+    "rsx_kmeans_update_peers": (i32, [vp, vp, i32, i32, vp, vp, i32, i32, i64, vp]),
+    "rsx_peer_alloc": (i32, [i64, vp, vp]),
+    "rsx_peer_open": (i32, [vp, vp]),
+    "rsx_peer_zero": (i32, [vp, i64, vp]),
+    "rsx_peer_close": (i32, [vp]),
+    "rsx_peer_free": (i32, [vp]),
 }
 
 

@@ -91,6 +91,65 @@ int rsx_fetch_small(void* h_dst, const void* d_src, size_t bytes, cudaStream_t s
     return RSX_OK;
 }
 
+// ----------------------------------------------------------------------------- peer memory (one node, one process per GPU)
+// A small cudaMalloc'ed block that the other ranks map with CUDA IPC: the KMeans update kernel reduces the ranks' partial
+// sums through it over NVLink (rsx_kmeans_update_peers) instead of calling a collective.
+extern "C" int rsx_peer_alloc(int64_t bytes, void** d_ptr, uint8_t* h_handle64) {
+    RSX_REQUIRE(bytes > 0 && d_ptr && h_handle64, "rsx_peer_alloc: bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, (size_t)bytes);
+    if (e == cudaSuccess) e = cudaMemset(p, 0, (size_t)bytes);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        if (p) cudaFree(p);
+        rsx_set_error("rsx_peer_alloc(%lld): %s", (long long)bytes, cudaGetErrorString(e));
+        return RSX_ERR_CUDA;
+    }
+    memcpy(h_handle64, &h, 64);
+    *d_ptr = p;
+    return RSX_OK;
+}
+
+extern "C" int rsx_peer_open(const uint8_t* h_handle64, void** d_peer) {
+    RSX_REQUIRE(h_handle64 && d_peer, "rsx_peer_open: bad arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, h_handle64, 64);
+    cudaError_t e = cudaIpcOpenMemHandle(d_peer, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+        rsx_set_error("rsx_peer_open: %s", cudaGetErrorString(e));
+        return RSX_ERR_CUDA;
+    }
+    return RSX_OK;
+}
+
+extern "C" int rsx_peer_zero(void* d_ptr, int64_t bytes, rsx_stream_t stream) {
+    RSX_REQUIRE(d_ptr && bytes >= 0, "rsx_peer_zero: bad arguments");
+    cudaError_t e = cudaMemsetAsync(d_ptr, 0, (size_t)bytes, (cudaStream_t)stream);
+    if (e != cudaSuccess) {
+        rsx_set_error("rsx_peer_zero: %s", cudaGetErrorString(e));
+        return RSX_ERR_CUDA;
+    }
+    return RSX_OK;
+}
+
+extern "C" int rsx_peer_close(void* d_peer) {
+    if (d_peer && cudaIpcCloseMemHandle(d_peer) != cudaSuccess) {
+        cudaGetLastError();
+        return RSX_ERR_CUDA;
+    }
+    return RSX_OK;
+}
+
+extern "C" int rsx_peer_free(void* d_ptr) {
+    if (d_ptr && cudaFree(d_ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return RSX_ERR_CUDA;
+    }
+    return RSX_OK;
+}
+
 // ----------------------------------------------------------------------------- min/max trackers
 __global__ void minmax_init_kernel(uint32_t* mm, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;

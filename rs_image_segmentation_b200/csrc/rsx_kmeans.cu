@@ -188,11 +188,73 @@ extern "C" int rsx_kmeans_assign(const float* d_stack, int64_t plane_stride, int
 // pass); the centroids come from the totals; the pass block is zeroed for the next pass.
 // adjust (optional, [K*D + K]): empty-cluster relocation of sklearn (_k_means_common.pyx:167-211) - added to the totals for
 // THIS centroid computation only; the running totals stay "sums by label", which is what the next delta pass builds on.
-__global__ void __launch_bounds__(KM_CTRL_THREADS) km_update_kernel(KmState* gst, long long* acc, int delta, const long long* __restrict__ adjust) {
+// Peer reduction (multi-GPU, one node): every rank's assign pass accumulated into ITS block of peer-mapped memory; the update
+// kernels of all ranks meet at a flag barrier over NVLink, then each sums the ranks' blocks itself (integer sums: the same
+// result on every rank) - the all-reduce is part of the update kernel, no collective is launched.
+//   block layout (RSX_PEER_BLOCK_BYTES): two pass buffers [RSX_PEER_PASS_ELEMS] int64 (parity of the sequence number), then
+//   flags [RSX_MAX_PEERS] uint64: flags[p] = last sequence number rank p has published.
+// Safety of the buffers: rank r zeroes its buffer of parity (seq+1)&1 after the barrier of seq; a peer read it during its
+// update seq-1, which precedes that peer's flag seq in stream order.
+struct KmPeers {
+    const long long* pass[RSX_MAX_PEERS];         // every rank's pass buffer of this parity (own included)
+    unsigned long long* flag_out[RSX_MAX_PEERS];  // &flags[rank] inside every peer's block
+    const unsigned long long* flag_in;            // own flags
+    long long* zero_next;                         // own pass buffer of the other parity
+    unsigned long long seq;
+    int rank, world;
+};
+
+__device__ __forceinline__ unsigned long long km_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// returns false on time-out (a peer never arrived): the caller records it instead of hanging the GPU
+__device__ bool km_peer_reduce(const KmPeers& pr, long long* __restrict__ pass_out, int n) {
+    __shared__ int timed_out;
+    if (threadIdx.x == 0) timed_out = 0;
+    __syncthreads();
+    if (threadIdx.x < pr.world && threadIdx.x != pr.rank) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(pr.flag_out[threadIdx.x]), "l"(pr.seq) : "memory");
+        const unsigned long long t0 = km_globaltimer();
+        unsigned long long seen = 0;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(pr.flag_in + threadIdx.x) : "memory");
+            if (seen >= pr.seq) break;
+            if (km_globaltimer() - t0 > 4000000000ull) {  // 4 s
+                timed_out = 1;
+                break;
+            }
+            __nanosleep(200);
+        }
+    }
+    __syncthreads();
+    if (timed_out) return false;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        long long v = 0;
+        for (int p = 0; p < pr.world; ++p) v += *reinterpret_cast<const volatile long long*>(pr.pass[p] + i);
+        pass_out[i] = v;
+        pr.zero_next[i] = 0;
+    }
+    __syncthreads();
+    return true;
+}
+
+template <bool PEERS>
+__global__ void __launch_bounds__(KM_CTRL_THREADS) km_update_kernel(KmState* gst, long long* acc, int delta, const long long* __restrict__ adjust,
+                                                                    const KmPeers peers) {
     __shared__ __align__(16) KmState sst;
     KmState* st = &sst;
     km_state_copy(st, gst);
     const int D = st->D, K = st->K;
+    if (PEERS) {
+        if (!km_peer_reduce(peers, acc, K * D + K + 2)) {
+            if (threadIdx.x == 0) gst->n_empty = -1000000;  // reported by rsx_kmeans_read as a failed exchange
+            return;
+        }
+    }
     long long* tot = acc + K * D + K + 2;
     for (int i = threadIdx.x; i < K * D + K; i += blockDim.x) {
         const long long v = acc[i] + (delta ? tot[i] : 0ll);
@@ -246,9 +308,34 @@ __global__ void __launch_bounds__(KM_CTRL_THREADS) km_update_kernel(KmState* gst
 extern "C" int rsx_kmeans_update(void* d_state, int64_t* d_acc, int delta, int D, const int64_t* d_adjust, rsx_stream_t stream) {
     RSX_REQUIRE(d_state && d_acc && D >= 1 && D <= KM_MAXD, "rsx_kmeans_update: bad arguments");
     cudaStream_t s = (cudaStream_t)stream;
-    km_update_kernel<<<1, KM_CTRL_THREADS, 0, s>>>((KmState*)d_state, reinterpret_cast<long long*>(d_acc), delta,
-                                                   reinterpret_cast<const long long*>(d_adjust));
+    km_update_kernel<false><<<1, KM_CTRL_THREADS, 0, s>>>((KmState*)d_state, reinterpret_cast<long long*>(d_acc), delta,
+                                                          reinterpret_cast<const long long*>(d_adjust), KmPeers());
     if (int rc = rsx_check_launch("km_update")) return rc;
+    return km_publish(d_state, D, s);
+}
+
+extern "C" int rsx_kmeans_update_peers(void* d_state, int64_t* d_acc, int delta, int D, const int64_t* d_adjust, void* const* h_peer_blocks, int rank,
+                                       int world, int64_t seq, rsx_stream_t stream) {
+    RSX_REQUIRE(d_state && d_acc && D >= 1 && D <= KM_MAXD && h_peer_blocks, "rsx_kmeans_update_peers: bad arguments");
+    RSX_REQUIRE(world >= 2 && world <= RSX_MAX_PEERS && rank >= 0 && rank < world && seq >= 1, "rsx_kmeans_update_peers: needs 2..%d ranks, seq >= 1",
+                RSX_MAX_PEERS);
+    KmPeers pr;
+    memset(&pr, 0, sizeof(pr));
+    const int parity = (int)(seq & 1);
+    for (int p = 0; p < world; ++p) {
+        RSX_REQUIRE(h_peer_blocks[p], "rsx_kmeans_update_peers: missing block of rank %d", p);
+        char* base = reinterpret_cast<char*>(h_peer_blocks[p]);
+        pr.pass[p] = reinterpret_cast<const long long*>(base) + (size_t)parity * RSX_PEER_PASS_ELEMS;
+        pr.flag_out[p] = reinterpret_cast<unsigned long long*>(base + 2 * RSX_PEER_PASS_ELEMS * 8) + rank;
+    }
+    char* own = reinterpret_cast<char*>(h_peer_blocks[rank]);
+    pr.flag_in = reinterpret_cast<const unsigned long long*>(own + 2 * RSX_PEER_PASS_ELEMS * 8);
+    pr.zero_next = reinterpret_cast<long long*>(own) + (size_t)(parity ^ 1) * RSX_PEER_PASS_ELEMS;
+    pr.seq = (unsigned long long)seq, pr.rank = rank, pr.world = world;
+    cudaStream_t s = (cudaStream_t)stream;
+    km_update_kernel<true><<<1, KM_CTRL_THREADS, 0, s>>>((KmState*)d_state, reinterpret_cast<long long*>(d_acc), delta,
+                                                         reinterpret_cast<const long long*>(d_adjust), pr);
+    if (int rc = rsx_check_launch("km_update_peers")) return rc;
     return km_publish(d_state, D, s);
 }
 
@@ -268,6 +355,10 @@ extern "C" int rsx_kmeans_read(const void* d_state, double* h_centroids, double*
     if (h_centroids)
         for (int j = 0; j < h.K; ++j)
             for (int d = 0; d < h.D; ++d) h_centroids[j * h.D + d] = h.cent64[j * KM_MAXD + d] + h.mean64[d];
+    if (h.n_empty < -500000) {
+        rsx_set_error("rsx_kmeans_read: a peer rank never reached the update barrier (rsx_kmeans_update_peers timed out)");
+        return RSX_ERR_CUDA;
+    }
     if (h_shift_sq) *h_shift_sq = h.shift_sq;
     if (h_empty) *h_empty = h.n_empty;
     return RSX_OK;

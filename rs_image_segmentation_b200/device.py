@@ -83,9 +83,17 @@ class MinMaxTracker:
     def slot(self, i: int):
         return C.c_void_p(self.buf.data_ptr() + 8 * i)
 
-    def read(self):
-        """(min float32[n], max float32[n]); synchronises."""
-        h = fetch(self.buf).view(np.uint32)
+    def read(self, comm=None):
+        """(min float32[n], max float32[n]); synchronises.  With a multi-rank `comm` the trackers of all ranks are merged on
+        the device first (the encoding is order preserving as unsigned integers), collectively."""
+        buf = self.buf
+        if comm is not None and comm.world > 1:
+            enc = buf.to(torch.int64) & 0xFFFFFFFF
+            lo, hi = enc[:, 0].contiguous(), enc[:, 1].contiguous()
+            comm.all_reduce(lo, "min")
+            comm.all_reduce(hi, "max")
+            buf = torch.stack([lo, hi], dim=1).to(torch.int32)          # truncation keeps the 32 bits
+        h = fetch(buf).view(np.uint32)
         mn, mx = np.zeros(self.n, np.float32), np.zeros(self.n, np.float32)
         _lib.load().rsx_minmax_decode(hptr(np.ascontiguousarray(h)), self.n, hptr(mn), hptr(mx))
         return mn, mx

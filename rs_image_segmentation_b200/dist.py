@@ -10,10 +10,16 @@ contiguous row strips; every stage is per-pixel or per-window, so the only excha
 """
 from __future__ import annotations
 
+import ctypes as C
 import math
-from typing import Callable, List, Sequence, Tuple
+import os
+import warnings
+from typing import Callable, List, Optional, Sequence, Tuple
 
 import torch
+
+PEER_PASS_ELEMS = 2560                              # include/rsx.h RSX_PEER_PASS_ELEMS
+PEER_BLOCK_BYTES = 2 * PEER_PASS_ELEMS * 8 + 8 * 8  # RSX_PEER_BLOCK_BYTES
 
 Range = Tuple[int, int]
 
@@ -67,6 +73,24 @@ def exchange_plan(bounds: Sequence[Range], needs: Sequence[Range]) -> List[Tuple
     return plan
 
 
+class PeerBlocks:
+    """This rank's peer-mapped block and the other ranks' mappings of theirs (include/rsx.h, rsx_kmeans_update_peers).
+    The sequence number is shared by every KMeans instance of the process: all ranks advance it in lockstep."""
+
+    def __init__(self, own: int, ptrs, rank: int, world: int):
+        self.own, self.ptrs, self.rank, self.world = own, ptrs, rank, world
+        self.seq = 0
+
+    def next_pass(self) -> Tuple[int, C.c_void_p]:
+        """(sequence number of the coming update, device pointer of the pass buffer its assign pass accumulates into)."""
+        self.seq += 1
+        return self.seq, C.c_void_p(self.own + (self.seq & 1) * PEER_PASS_ELEMS * 8)
+
+    def zero(self, stream):
+        from . import _lib
+        _lib.call("rsx_peer_zero", C.c_void_p(self.own), 2 * PEER_PASS_ELEMS * 8, stream)
+
+
 class Comm:
     """torch.distributed wrapper; `Comm()` without an initialised process group is the 1-GPU case."""
 
@@ -77,6 +101,46 @@ class Comm:
         self.group = group
         self.rank = dist.get_rank(group) if self.active else 0
         self.world = dist.get_world_size(group) if self.active else 1
+
+    def peers(self) -> Optional["PeerBlocks"]:
+        """Peer-mapped blocks for the KMeans sums (rsx_kmeans_update_peers), or None: one rank, a CPU backend, more than 8
+        ranks, RSX_PEER_REDUCE=0, or CUDA IPC not available on some rank (then every rank stays on the all-reduce).
+        Collective on first use."""
+        if getattr(self, "_peers_tried", False):
+            return self._peers
+        self._peers_tried, self._peers = True, None
+        if not (self.active and 2 <= self.world <= 8) or os.environ.get("RSX_PEER_REDUCE", "1") == "0":
+            return None
+        if self.dist.get_backend(self.group) != "nccl" or not torch.cuda.is_available():
+            return None
+        from . import _lib
+        lib = _lib.load()
+        own, handle = C.c_void_p(), (C.c_uint8 * 64)()
+        ok = lib.rsx_peer_alloc(PEER_BLOCK_BYTES, C.byref(own), handle) == 0
+        mine = torch.tensor(list(handle) + [1 if ok else 0], dtype=torch.uint8, device="cuda")
+        every = [torch.empty_like(mine) for _ in range(self.world)]
+        self.dist.all_gather(every, mine, group=self.group)
+        every = [e.cpu().numpy() for e in every]
+        ptrs = (C.c_void_p * self.world)()
+        ok = all(int(e[64]) == 1 for e in every)
+        if ok:
+            for p, e in enumerate(every):
+                if p == self.rank:
+                    ptrs[p] = own.value
+                    continue
+                peer = C.c_void_p()
+                h = (C.c_uint8 * 64)(*[int(v) for v in e[:64]])
+                if lib.rsx_peer_open(h, C.byref(peer)) != 0:
+                    ok = False
+                    break
+                ptrs[p] = peer.value
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda")
+        self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) != 1:
+            warnings.warn("rsx: CUDA IPC peer mapping is not available; KMeans sums go through all-reduce")
+            return None
+        self._peers = PeerBlocks(own.value, ptrs, self.rank, self.world)
+        return self._peers
 
     def all_reduce(self, t: torch.Tensor, op: str = "sum") -> torch.Tensor:
         if self.active and self.world > 1:

@@ -390,6 +390,10 @@ class DeviceKMeans:
         self.full_passes = max(1, int(full_passes))
         self._labels = None
         self._passes = 0
+        # several GPUs: the update kernels reduce the ranks' sums themselves through peer-mapped memory (no collective per
+        # iteration); fit_converge, which inspects the reduced counts on the host before the update, keeps the all-reduce
+        self.peers = self.comm.peers() if self.comm.world > 1 else None
+        self._peer_seq = 0
 
     def configure(self, feat_min, feat_max):
         """MinMaxScaler.fit result (per-feature min / max of the raw stack).  May follow the constructor (feat_min=None) so
@@ -413,6 +417,8 @@ class DeviceKMeans:
         mu = np.full(self.D, 0.5) if mean_scaled is None else np.ascontiguousarray(mean_scaled, dtype=np.float64)
         self.acc.zero_()
         self._passes = 0
+        if self.peers is not None:
+            self.peers.zero(stream_ptr())
         _lib.call("rsx_kmeans_setup", ptr(self.state), self.D, self.K, hptr(self.fmin), hptr(self.fmax), hptr(mu), hptr(c0),
                   self.n_global, stream_ptr())
 
@@ -422,7 +428,7 @@ class DeviceKMeans:
             self._labels = [torch.full((max(npad, 4),), 255, dtype=torch.uint8, device=self.planes.device) for _ in range(2)]
         return self._labels
 
-    def assign_pass(self, track_labels: bool = False) -> int:
+    def assign_pass(self, track_labels: bool = False, peer_reduce: bool = False) -> int:
         """One fused assign + partial-sum pass and the all-reduce of its K*(D+1)+2 integers.  The first pass accumulates from
         scratch; later passes are delta passes (if enabled).  With track_labels (or delta) every pass writes uint8 labels
         and counts the pixels whose label changed.  Returns the mode used (1 = full, 2 = delta)."""
@@ -436,11 +442,15 @@ class DeviceKMeans:
                 planes[1].fill_(255)
             cur, prev = planes[self._passes % 2], planes[(self._passes + 1) % 2]
         self._cur_labels = cur
+        self._peer_seq = 0
+        d_acc = ptr(self.acc)
+        if peer_reduce and self.peers is not None:
+            self._peer_seq, d_acc = self.peers.next_pass()       # this pass accumulates into the peer-mapped block
         if self.n_px:
             with self.timer("kmeans_assign_delta" if mode == 2 else "kmeans_assign_full"):
-                _lib.call("rsx_kmeans_assign", ptr(self.planes), self.stride, self.n_px, self.row_len, ptr(self.state), ptr(self.acc),
+                _lib.call("rsx_kmeans_assign", ptr(self.planes), self.stride, self.n_px, self.row_len, ptr(self.state), d_acc,
                           ptr(cur), ptr(prev), None, None, mode, self.D, self.K, stream_ptr())
-        if self.comm.world > 1:
+        if self.comm.world > 1 and not self._peer_seq:
             with self.timer("kmeans_allreduce"):
                 self.comm.all_reduce(self.acc[:self.n_acc])
         return mode
@@ -448,12 +458,16 @@ class DeviceKMeans:
     def update(self, mode: int, adjust: Optional[torch.Tensor] = None):
         """Centroids <- totals / counts (the pass block is folded into the totals first)."""
         with self.timer("kmeans_update"):
-            _lib.call("rsx_kmeans_update", ptr(self.state), ptr(self.acc), 1 if mode == 2 else 0, self.D, ptr(adjust), stream_ptr())
+            if self._peer_seq:
+                _lib.call("rsx_kmeans_update_peers", ptr(self.state), ptr(self.acc), 1 if mode == 2 else 0, self.D, ptr(adjust),
+                          self.peers.ptrs, self.peers.rank, self.peers.world, self._peer_seq, stream_ptr())
+            else:
+                _lib.call("rsx_kmeans_update", ptr(self.state), ptr(self.acc), 1 if mode == 2 else 0, self.D, ptr(adjust), stream_ptr())
         self._passes += 1
 
     def step(self, track_labels: bool = False):
         """assign_pass + update, without host synchronisation (empty clusters are only reported, see fit_converge)."""
-        self.update(self.assign_pass(track_labels))
+        self.update(self.assign_pass(track_labels, peer_reduce=True))
 
     def relocation_adjust(self, empty: np.ndarray, first_px: int = 0) -> torch.Tensor:
         """sklearn's _relocate_empty_clusters_dense (_k_means_common.pyx:167-211) for the pass that has just been all-reduced:
@@ -586,13 +600,7 @@ def kmeans_on_features(fr: FeatureResult, D: int, K: int, n_iter: int, seed: int
     if km.delta:
         km._label_planes()
     rows_host = stage_to_host(gather_rows_device(fr.planes, D, fr.n_px, idx, first_row * fr.W, comm))   # ... all asynchronous
-    mn, mx = fr.minmax.read()                       # the one synchronisation between the feature kernels and KMeans
-    if comm.world > 1:
-        tmn = torch.from_numpy(mn[:D].copy()).to(fr.planes.device)
-        tmx = torch.from_numpy(mx[:D].copy()).to(fr.planes.device)
-        comm.all_reduce(tmn, "min")
-        comm.all_reduce(tmx, "max")
-        mn, mx = tmn.cpu().numpy(), tmx.cpu().numpy()
+    mn, mx = fr.minmax.read(comm)                   # the one synchronisation between the feature kernels and KMeans
     km.configure(mn[:D], mx[:D])
     c0 = km.scale_rows(rows_host.numpy())
     res = km.fit(c0, n_iter, labels_i32)
