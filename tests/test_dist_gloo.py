@@ -116,3 +116,21 @@ def test_fetch_rows_and_allreduce_gloo(world, H, W, w, s):
     for p in procs:
         assert p.exitcode == 0, "a gloo worker failed"
     assert len(ret) == world and all(all(v) for v in ret.values()), dict(ret)
+
+
+def test_peer_blocks_sequence_and_layout():
+    """dist.PeerBlocks: pass buffers alternate with the parity of the sequence number; the layout constants are those of
+    include/rsx.h; a CPU / single-process Comm never asks for peer memory."""
+    import re
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "rsx.h")).read()
+    elems = int(re.search(r"#define RSX_PEER_PASS_ELEMS (\d+)", hdr).group(1))
+    max_k = int(re.search(r"#define RSX_MAX_CLUSTERS (\d+)", hdr).group(1))
+    max_d = int(re.search(r"#define RSX_MAX_FEATURES (\d+)", hdr).group(1))
+    max_p = int(re.search(r"#define RSX_MAX_PEERS (\d+)", hdr).group(1))
+    assert elems == D.PEER_PASS_ELEMS and elems >= max_k * (max_d + 1) + 2
+    assert D.PEER_BLOCK_BYTES == 2 * elems * 8 + max_p * 8
+    pb = D.PeerBlocks(0x10000, None, 1, 2)
+    seqs = [pb.next_pass() for _ in range(4)]
+    assert [s for s, _ in seqs] == [1, 2, 3, 4]
+    assert [p.value - 0x10000 for _, p in seqs] == [elems * 8, 0, elems * 8, 0]
+    assert D.Comm().peers() is None

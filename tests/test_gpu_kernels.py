@@ -241,3 +241,21 @@ def test_hist_u16_large_and_mixed_range(rsx, B, n_px):
     for b in range(B):
         ref = torch.bincount(r[:, b].to(torch.int64), minlength=65536)
         assert torch.equal(h[b].to(torch.int64), ref), b
+
+
+# ------------------------------------------------------------------------------------------ read-backs without a copy engine
+@pytest.mark.parametrize("n,dtype", [(1, "int64"), (3, "float64"), (14, "int32"), (7 * 256, "int32"), (100_003, "uint8"), (13 * 65536, "int64")])
+def test_fetch_kernel_store_matches_copy(rsx, n, dtype):
+    """device.fetch / rsx_store_to_host (kernel store into page-locked memory) returns the bytes of a plain copy, for
+    aligned and unaligned starts and sizes that are not a multiple of 16."""
+    import torch
+    from rs_image_segmentation_b200.device import fetch, stage_to_host
+    g = torch.Generator(device="cuda").manual_seed(n)
+    base = torch.randint(0, 200, (n + 3,), generator=g, device="cuda").to(getattr(torch, dtype))
+    for off in (0, 1, 3):
+        t = base[off:off + n]
+        assert np.array_equal(fetch(t), t.cpu().numpy())
+    h = stage_to_host(base)
+    torch.cuda.current_stream().synchronize()
+    assert np.array_equal(h.numpy(), base.cpu().numpy())
+    assert fetch(base[:0]).size == 0
