@@ -151,6 +151,32 @@ def test_kmeans_labels_bit_exact(P, K, n_iter, H, W):
     assert abs(res.inertia - inertia) <= 1e-5 * inertia
 
 
+@pytest.mark.parametrize("D,K,n_iter,n_px", [(1, 2, 4, 5003), (8, 64, 3, 20011), (9, 17, 4, 12007), (16, 9, 3, 9001), (20, 64, 3, 30011),
+                                             (20, 1, 2, 4099), (13, 33, 3, 16411)])
+def test_kmeans_depth_and_cluster_extremes(P, D, K, n_iter, n_px):
+    """Every compiled range of stack depths (1..20) and the extremes of K (1, the 16/32/64 tag-width boundaries) on a random
+    planar stack with correlated, differently scaled features: labels, centroids and inertia against the oracle."""
+    import torch
+    rng = np.random.default_rng(1000 * D + K)
+    base = rng.normal(size=(n_px, 3))
+    mix = rng.normal(size=(3, D))
+    X = (base @ mix + 0.3 * rng.normal(size=(n_px, D))) * rng.uniform(0.01, 50.0, size=D) + rng.uniform(-5, 5, size=D)
+    X = X.astype(np.float32)
+    stride = (n_px + 31) // 32 * 32
+    planes = torch.zeros((D, stride), dtype=torch.float32, device="cuda")
+    planes[:, :n_px] = torch.from_numpy(np.ascontiguousarray(X.T)).cuda()
+    fmin, fmax = X.min(axis=0), X.max(axis=0)
+    km = P.DeviceKMeans(planes, n_px, D, K, fmin, fmax, n_px, 257)
+    idx = P.draw_init_indices(n_px, K, 5)
+    c0 = km.scale_rows(X[idx])
+    res = km.fit(c0, n_iter)
+    (lab, cent, inertia, n_run), _ = _kmeans_oracle(X, c0, n_iter, fmin, fmax)
+    got = res.labels.cpu().numpy()
+    assert np.array_equal(got, lab), f"{(got != lab).sum()} labels differ"
+    np.testing.assert_allclose(res.centroids, cent, rtol=0, atol=1e-9)
+    assert abs(res.inertia - inertia) <= 1e-5 * max(inertia, 1e-30)
+
+
 def test_kmeans_partition_invariance(P):
     """Integer partial sums: assigning two halves separately and adding the accumulators equals one pass."""
     import torch
