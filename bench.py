@@ -41,7 +41,7 @@ def peaks():
 
 
 class ClockSampler:
-    """SM clock + throttle reasons sampled DURING the timed region.  NVML in a thread, two cheap queries every 100 ms: every
+    """SM clock + throttle reasons sampled DURING the timed region.  NVML in a thread, two cheap queries every 40 ms (100 ms and 40 ms measured alike, 20 ms not): every
     NVML / nvidia-smi query takes driver locks that stall kernel launches (a polling `nvidia-smi -lms 100` child stretched
     a 20 ms step to 37 ms, NVML every 20 ms a 2-GPU step to 40 ms), so the sampling is kept sparse; nvidia-smi once as a
     fallback."""
@@ -244,7 +244,7 @@ def run_rsx(args):
         keep = None
         keep = step(StageTimer(enabled=False))
     keep = None
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, float(os.environ.get("RSX_BENCH_CLOCK_PERIOD", "0.04")))
     if rank == 0 and os.environ.get("RSX_BENCH_NOCLOCKS", "0") != "1":
         sampler.start()
     launches0 = _lib.launch_count()
