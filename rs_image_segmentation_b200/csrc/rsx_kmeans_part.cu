@@ -46,6 +46,41 @@ __device__ __noinline__ int km_exact_argmin(const float* __restrict__ stack, int
     return bi;
 }
 
+// K > 8: the same evaluation by the whole warp - lane j takes centroids j and j + 32 - so that a near tie costs ~100 warp
+// instructions instead of a K x D loop in one lane with the other 31 idle.  Same operations in the same order per centroid as
+// km_exact_argmin, and the same winner: the smallest value, the lowest index among equals.  c64s: shared copy of the centred
+// centroids [d][KP64] (KP64 = K rounded up to 32) followed by their squared norms [KP64].  Called by all 32 lanes.
+template <int D>
+__device__ __forceinline__ int km_exact_argmin_warp(const float* __restrict__ stack, int64_t plane_stride, int64_t p, int K, const double* __restrict__ c64s,
+                                                    double* dist_out) {
+    const int lane = threadIdx.x & 31;
+    const int KP64 = (K + 31) & ~31;
+    double X[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d)
+        X[d] = __dsub_rn(__dadd_rn(__dmul_rn((double)__ldg(stack + d * plane_stride + p), g_km.scale64[d]), g_km.min64[d]), g_km.mean64[d]);
+    double xx = 0.0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) xx = fma(X[d], X[d], xx);
+    double best = INFINITY;
+    int bi = 0x7fffffff;
+    for (int j = lane; j < K; j += 32) {
+        double dot = 0.0;
+#pragma unroll
+        for (int d = 0; d < D; ++d) dot = fma(X[d], c64s[d * KP64 + j], dot);
+        const double v = fma(-2.0, dot, c64s[D * KP64 + j]);
+        if (v < best) best = v, bi = j;  // j ascends within the lane: the first minimum stays
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double v2 = __shfl_xor_sync(0xffffffffu, best, o);
+        const int j2 = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (v2 < best || (v2 == best && j2 < bi)) best = v2, bi = j2;
+    }
+    *dist_out = fmax(xx + best, 0.0);
+    return bi;
+}
+
 // ----------------------------------------------------------------------------- fp32 distances + tagged argmin
 #define KM_ARGMIN_STEP(A, B_, S_, I_, J)          \
     S_ = fminf(S_, fmaxf(A, B_));                 \
@@ -425,11 +460,11 @@ __device__ __forceinline__ void km_move_samples(const float* __restrict__ st, in
     }
 }
 
-template <int D, int MODE, bool INERTIA, int KU>
+template <int D, int MODE, bool INERTIA, int KU, bool WARPX>
 __global__ void __launch_bounds__(KM_THREADS, 4) km_stream_kernel(const float* __restrict__ stack, int64_t plane_stride, int64_t n_px,
                                                                   long long* __restrict__ gacc, uint8_t* __restrict__ lab8,
                                                                   const uint8_t* __restrict__ prev8, int32_t* __restrict__ lab32,
-                                                                  double* __restrict__ inertia_out, int n_stages) {
+                                                                  double* __restrict__ inertia_out, int n_stages, int c64_offset) {
     constexpr bool SUMS = MODE != KM_ASSIGN;
     constexpr bool LOCKSTEP = false;  // true: one CTA barrier per block instead of the empty mbarriers (kept for experiments)
     extern __shared__ __align__(128) unsigned char km_smem[];
@@ -442,6 +477,8 @@ __global__ void __launch_bounds__(KM_THREADS, 4) km_stream_kernel(const float* _
     int* ticket = reinterpret_cast<int*>(empty + n_stages);                                                     // [n_stages] (+ pad): refills issued per stage
     float* wsm = reinterpret_cast<float*>(empty + n_stages) + 4;                                                    // KU == 0: [D][KP] weights, [KP] biases
     long long* wacc = wacc_all + warp * K * (D + 1);
+    // KU == 0: float64 centroids for the warp-wide near-tie evaluation, [D + 1][K rounded up to 32], after the fp32 tables
+    double* c64s = reinterpret_cast<double*>(km_smem + c64_offset);
     if (KU == 0) {
         const int KP = (K + 7) & ~7;
         for (int i = tid; i < D * KP; i += KM_THREADS) {  // [chunk][D][8]
@@ -451,6 +488,14 @@ __global__ void __launch_bounds__(KM_THREADS, 4) km_stream_kernel(const float* _
         for (int j = tid; j < KP; j += KM_THREADS) wsm[D * KP + j] = g_km.bias32[j];
         if (INERTIA)
             for (int i = tid; i < K * D; i += KM_THREADS) wsm[(D + 1) * KP + i] = g_km.cent32[(i / D) * KM_MAXD + i % D];
+        if (WARPX) {
+            const int KP64 = (K + 31) & ~31;
+            for (int i = tid; i < D * KP64; i += KM_THREADS) {
+                const int d = i / KP64, j = i - d * KP64;
+                c64s[i] = j < K ? g_km.cent64[j * KM_MAXD + d] : 0.0;
+            }
+            for (int j = tid; j < KP64; j += KM_THREADS) c64s[D * KP64 + j] = j < K ? g_km.cnorm64[j] : 0.0;
+        }
     }
     const int64_t n4 = n_px & ~(int64_t)3;
     const int64_t n_blocks = (n4 + KM_BLOCK_PX - 1) / KM_BLOCK_PX;
@@ -496,30 +541,107 @@ __global__ void __launch_bounds__(KM_THREADS, 4) km_stream_kernel(const float* _
         mbar_wait(&full[s], parity);
         const float* st = stages + (size_t)s * D * KM_BLOCK_PX;
         uint32_t packed = 0, diff = 0;
-        if (valid) {
-            float4 v[D];
+        if (KU == 8) {
+            if (valid) {
+                float4 v[D];
 #pragma unroll
-            for (int d = 0; d < D; ++d) v[d] = *reinterpret_cast<const float4*>(st + d * KM_BLOCK_PX + 4 * tid);
-            float b[4], sc[4];
-            km_distances<D, KU>(v, K, wsm, b, sc);
-            int l[4];
-            float x[D];
+                for (int d = 0; d < D; ++d) v[d] = *reinterpret_cast<const float4*>(st + d * KM_BLOCK_PX + 4 * tid);
+                float b[4], sc[4];
+                km_distances<D, KU>(v, K, wsm, b, sc);
+                int l[4];
+                float x[D];
 #pragma unroll
-            for (int d = 0; d < D; ++d) x[d] = v[d].x;
-            l[0] = km_decide<D, KU, INERTIA>(stack, plane_stride, p, x, b[0], sc[0], wsm, inertia, ties);
+                for (int d = 0; d < D; ++d) x[d] = v[d].x;
+                l[0] = km_decide<D, KU, INERTIA>(stack, plane_stride, p, x, b[0], sc[0], wsm, inertia, ties);
 #pragma unroll
-            for (int d = 0; d < D; ++d) x[d] = v[d].y;
-            l[1] = km_decide<D, KU, INERTIA>(stack, plane_stride, p + 1, x, b[1], sc[1], wsm, inertia, ties);
+                for (int d = 0; d < D; ++d) x[d] = v[d].y;
+                l[1] = km_decide<D, KU, INERTIA>(stack, plane_stride, p + 1, x, b[1], sc[1], wsm, inertia, ties);
 #pragma unroll
-            for (int d = 0; d < D; ++d) x[d] = v[d].z;
-            l[2] = km_decide<D, KU, INERTIA>(stack, plane_stride, p + 2, x, b[2], sc[2], wsm, inertia, ties);
+                for (int d = 0; d < D; ++d) x[d] = v[d].z;
+                l[2] = km_decide<D, KU, INERTIA>(stack, plane_stride, p + 2, x, b[2], sc[2], wsm, inertia, ties);
 #pragma unroll
-            for (int d = 0; d < D; ++d) x[d] = v[d].w;
-            l[3] = km_decide<D, KU, INERTIA>(stack, plane_stride, p + 3, x, b[3], sc[3], wsm, inertia, ties);
-            packed = (uint32_t)l[0] | ((uint32_t)l[1] << 8) | ((uint32_t)l[2] << 16) | ((uint32_t)l[3] << 24);
-            if (prev8) diff = packed ^ pv;
-            if (lab8) *reinterpret_cast<uint32_t*>(lab8 + p) = packed;
-            if (lab32) *reinterpret_cast<int4*>(lab32 + p) = make_int4(l[0], l[1], l[2], l[3]);
+                for (int d = 0; d < D; ++d) x[d] = v[d].w;
+                l[3] = km_decide<D, KU, INERTIA>(stack, plane_stride, p + 3, x, b[3], sc[3], wsm, inertia, ties);
+                packed = (uint32_t)l[0] | ((uint32_t)l[1] << 8) | ((uint32_t)l[2] << 16) | ((uint32_t)l[3] << 24);
+                if (prev8) diff = packed ^ pv;
+                if (lab8) *reinterpret_cast<uint32_t*>(lab8 + p) = packed;
+                if (lab32) *reinterpret_cast<int4*>(lab32 + p) = make_int4(l[0], l[1], l[2], l[3]);
+            }
+        } else {
+            // K > 16: tagged fp32 argmin per thread; the pixels inside the near-tie band are then evaluated in float64 by the
+            // whole warp, one after the other (warp-uniform loop over the ballot): 1.55 -> 1.43 ms per pass at K = 32.
+            // 8 < K <= 16 keeps the per-lane path (untagged fp32 re-check, then float64): half the lanes would idle (+6 %).
+            constexpr bool warpwide = WARPX;
+            int l[4] = {0, 0, 0, 0};
+            double dex[4] = {-1.0, -1.0, -1.0, -1.0};
+            unsigned unsure = 0;
+            if (valid) {
+                float4 v[D];
+#pragma unroll
+                for (int d = 0; d < D; ++d) v[d] = *reinterpret_cast<const float4*>(st + d * KM_BLOCK_PX + 4 * tid);
+                float b[4], sc[4];
+                km_distances<D, KU>(v, K, wsm, b, sc);
+                if (warpwide) {
+                    const unsigned tag_mask = (1u << g_km.tag_bits) - 1u;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        l[i] = (int)(__float_as_uint(b[i]) & tag_mask);
+                        if (!(sc[i] - b[i] > g_km.tau)) unsure |= 1u << i;  // also NaN
+                    }
+                } else {
+                    float x[D];
+#pragma unroll
+                    for (int d = 0; d < D; ++d) x[d] = v[d].x;
+                    l[0] = km_decide<D, KU, INERTIA>(stack, plane_stride, p, x, b[0], sc[0], wsm, inertia, ties);
+#pragma unroll
+                    for (int d = 0; d < D; ++d) x[d] = v[d].y;
+                    l[1] = km_decide<D, KU, INERTIA>(stack, plane_stride, p + 1, x, b[1], sc[1], wsm, inertia, ties);
+#pragma unroll
+                    for (int d = 0; d < D; ++d) x[d] = v[d].z;
+                    l[2] = km_decide<D, KU, INERTIA>(stack, plane_stride, p + 2, x, b[2], sc[2], wsm, inertia, ties);
+#pragma unroll
+                    for (int d = 0; d < D; ++d) x[d] = v[d].w;
+                    l[3] = km_decide<D, KU, INERTIA>(stack, plane_stride, p + 3, x, b[3], sc[3], wsm, inertia, ties);
+                }
+            }
+            unsigned any = warpwide ? __ballot_sync(0xffffffffu, unsure != 0) : 0u;
+            while (any) {
+                const int src = __ffs(any) - 1;
+                any &= any - 1;
+                const unsigned um = __shfl_sync(0xffffffffu, unsure, src);
+                const int64_t pw = blk * KM_BLOCK_PX + warp * 128 + 4 * src;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (um & (1u << i)) {  // warp-uniform
+                        double de;
+                        const int bi = km_exact_argmin_warp<D>(stack, plane_stride, pw + i, K, c64s, &de);
+                        if (lane == src) l[i] = bi, dex[i] = de, ++ties;
+                    }
+                }
+            }
+            if (valid) {
+                if (INERTIA && warpwide) {
+                    const int KP = (K + 7) & ~7;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (dex[i] < 0.0) {  // sum of squares of (x' - c) in fp32: all terms positive, relative error ~D * 2^-24
+                            const float* cent = wsm + (D + 1) * KP + l[i] * D;
+                            float dd = 0.f;
+#pragma unroll
+                            for (int d = 0; d < D; ++d) {
+                                const float df = fmaf(st[d * KM_BLOCK_PX + 4 * tid + i], g_km.scale32[d], g_km.off32[d]) - cent[d];
+                                dd = fmaf(df, df, dd);
+                            }
+                            dex[i] = (double)dd;
+                        }
+                        inertia += dex[i];
+                    }
+                }
+                packed = (uint32_t)l[0] | ((uint32_t)l[1] << 8) | ((uint32_t)l[2] << 16) | ((uint32_t)l[3] << 24);
+                if (prev8) diff = packed ^ pv;
+                if (lab8) *reinterpret_cast<uint32_t*>(lab8 + p) = packed;
+                if (lab32) *reinterpret_cast<int4*>(lab32 + p) = make_int4(l[0], l[1], l[2], l[3]);
+            }
         }
         unsigned cm = km_changed_mask(diff);
         changed += __popc(cm);  // sklearn's strict-convergence test (_kmeans.py:723)
@@ -603,12 +725,14 @@ static int km_launch_full(const KmLaunch& a, cudaStream_t s) {
     return rsx_check_launch("km_full");
 }
 
-template <int D, int MODE, bool INERTIA, int KU>
+template <int D, int MODE, bool INERTIA, int KU, bool WARPX = false>
 static int km_launch_stream(const KmLaunch& a, cudaStream_t s) {
-    auto kern = km_stream_kernel<D, MODE, INERTIA, KU>;
+    auto kern = km_stream_kernel<D, MODE, INERTIA, KU, WARPX>;
     const int acc_bytes = MODE == KM_ASSIGN ? 0 : KM_WARPS * a.K * (D + 1) * 8;
-    const int w_bytes = KU == 0 ? ((D + 1) * ((a.K + 7) & ~7) + (INERTIA ? a.K * D : 0)) * 4 : 0;
-    auto smem_for = [&](int stages) { return stages * D * KM_BLOCK_PX * 4 + acc_bytes + 2 * stages * 8 + 16 + w_bytes; };
+    const int w_bytes = KU == 0 ? (((D + 1) * ((a.K + 7) & ~7) + (INERTIA ? a.K * D : 0)) * 4 + 15) / 16 * 16 : 0;
+    const int c64_bytes = WARPX ? (D + 1) * ((a.K + 31) & ~31) * 8 : 0;
+    auto c64_off = [&](int stages) { return stages * D * KM_BLOCK_PX * 4 + acc_bytes + 2 * stages * 8 + 16 + w_bytes; };
+    auto smem_for = [&](int stages) { return c64_off(stages) + c64_bytes; };
     // stages: enough blocks in flight per SM to cover HBM latency at full bandwidth (~64 KB/SM), within shared memory
     static int cfg_K = -1, cfg_stages = 0, cfg_per_sm = 0;
     if (cfg_K != a.K) {
@@ -634,25 +758,30 @@ static int km_launch_stream(const KmLaunch& a, cudaStream_t s) {
     const int64_t n4 = a.n_px & ~(int64_t)3;
     const int64_t n_blocks = ceil_div(n4, (int64_t)KM_BLOCK_PX);
     const int grid = (int)max((int64_t)1, min(n_blocks, (int64_t)rsx_num_sms() * cfg_per_sm));
-    kern<<<grid, KM_THREADS, smem_for(cfg_stages), s>>>(a.stack, a.plane_stride, a.n_px, a.acc, a.lab8, a.prev8, a.lab32, a.inertia, cfg_stages);
+    kern<<<grid, KM_THREADS, smem_for(cfg_stages), s>>>(a.stack, a.plane_stride, a.n_px, a.acc, a.lab8, a.prev8, a.lab32, a.inertia, cfg_stages,
+                                                        c64_off(cfg_stages));
     return rsx_check_launch("km_stream");
 }
 
-template <int D, int KU>
+template <int D, int KU, bool WARPX>
 static int km_launch2(const KmLaunch& a, cudaStream_t s) {
     if (a.mode == KM_FULL) {
         if (KU == 8) return km_launch_full<D>(a, s);
-        return km_launch_stream<D, KM_FULL, false, KU>(a, s);
+        return km_launch_stream<D, KM_FULL, false, KU, WARPX>(a, s);
     }
-    if (a.mode == KM_DELTA) return km_launch_stream<D, KM_DELTA, false, KU>(a, s);
-    if (a.inertia) return km_launch_stream<D, KM_ASSIGN, true, KU>(a, s);
-    return km_launch_stream<D, KM_ASSIGN, false, KU>(a, s);
+    if (a.mode == KM_DELTA) return km_launch_stream<D, KM_DELTA, false, KU, WARPX>(a, s);
+    if (a.inertia) return km_launch_stream<D, KM_ASSIGN, true, KU, WARPX>(a, s);
+    return km_launch_stream<D, KM_ASSIGN, false, KU, WARPX>(a, s);
 }
 
+// K <= 8: unrolled constant-operand body.  8 < K <= 16: chunked body, near ties re-checked by the lane that owns the pixel.
+// K > 16: chunked body, near ties evaluated in float64 by the whole warp (1.55 -> 1.43 ms per pass at K = 32; at K = 16 half the
+// lanes would idle: +6 %).
 template <int D>
 static int km_launch(const KmLaunch& a, cudaStream_t s) {
-    if (a.K <= 8) return km_launch2<D, 8>(a, s);
-    return km_launch2<D, 0>(a, s);
+    if (a.K <= 8) return km_launch2<D, 8, false>(a, s);
+    if (a.K <= 16) return km_launch2<D, 0, false>(a, s);
+    return km_launch2<D, 0, true>(a, s);
 }
 
 #define KM_CAT2(a, b) a##b
