@@ -460,6 +460,41 @@ __device__ __forceinline__ void km_move_samples(const float* __restrict__ st, in
     }
 }
 
+// KM_FULL (K > 8): every pixel moves in, nothing moves out.  Lane d takes the four samples of an owning thread with one load,
+// converts them, and adds runs of equal labels together before touching the accumulator (neighbouring pixels mostly share
+// their label), so a thread's four pixels cost one or two read-modify-writes instead of four dependent ones.
+template <int D>
+__device__ __forceinline__ void km_move_in_all(const float* __restrict__ st, int warp_px, unsigned valid_mask, uint32_t new_packed,
+                                               long long* __restrict__ wacc, float my_pow2) {
+    const int lane = threadIdx.x & 31;
+    const float* mine = st + min(lane, D - 1) * KM_BLOCK_PX + warp_px;
+#pragma unroll 2
+    for (int src = 0; src < 32; ++src) {
+        if (!((valid_mask >> src) & 1u)) break;  // valid threads are a prefix of the warp
+        const uint32_t nv = __shfl_sync(0xffffffffu, new_packed, src);
+        if (lane <= D) {
+            const float4 xv = *reinterpret_cast<const float4*>(mine + 4 * src);
+            const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+            long long q[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) q[i] = lane < D ? __float2ll_rn(xs[i] * my_pow2) : 1ll;
+            unsigned cur = nv & 0xffu;
+            long long run = q[0];
+#pragma unroll
+            for (int i = 1; i < 4; ++i) {
+                const unsigned t = (nv >> (8 * i)) & 0xffu;
+                if (t == cur) {
+                    run += q[i];
+                } else {
+                    wacc[cur * (D + 1) + lane] += run;
+                    cur = t, run = q[i];
+                }
+            }
+            wacc[cur * (D + 1) + lane] += run;
+        }
+    }
+}
+
 template <int D, int MODE, bool INERTIA, int KU, bool WARPX>
 __global__ void __launch_bounds__(KM_THREADS, 4) km_stream_kernel(const float* __restrict__ stack, int64_t plane_stride, int64_t n_px,
                                                                   long long* __restrict__ gacc, uint8_t* __restrict__ lab8,
@@ -646,7 +681,10 @@ __global__ void __launch_bounds__(KM_THREADS, 4) km_stream_kernel(const float* _
         unsigned cm = km_changed_mask(diff);
         changed += __popc(cm);  // sklearn's strict-convergence test (_kmeans.py:723)
         if (MODE == KM_FULL) cm = valid ? 0xfu : 0u;
-        if (SUMS) km_move_samples<D>(st, warp * 128, cm, MODE == KM_FULL ? 0xffffffffu : pv, packed, wacc, my_pow2);
+        if (MODE == KM_FULL)
+            km_move_in_all<D>(st, warp * 128, __ballot_sync(0xffffffffu, valid), packed, wacc, my_pow2);
+        else if (SUMS)
+            km_move_samples<D>(st, warp * 128, cm, pv, packed, wacc, my_pow2);
         if (LOCKSTEP) {
             __syncthreads();  // everyone is done with stage s: refill it
             if (tid == 0) {

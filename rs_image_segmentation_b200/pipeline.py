@@ -433,8 +433,9 @@ class DeviceKMeans:
         scratch; later passes are delta passes (if enabled).  With track_labels (or delta) every pass writes uint8 labels
         and counts the pixels whose label changed.  Returns the mode used (1 = full, 2 = delta)."""
         use_labels = track_labels or self.delta
-        # K > 8: the delta kernel is also the full pass (previous labels = 255: every pixel "moves in" from nowhere)
-        mode = 2 if (self.delta and (self.K > 8 or self._passes >= self.full_passes)) else 1
+        # K <= 8: the first full_passes passes recompute the sums (per-thread accumulators); K > 8: only the very first one
+        # (the streaming kernel's "every pixel moves in" mode, which adds runs of equal labels before touching the sums)
+        mode = 2 if (self.delta and self._passes >= (self.full_passes if self.K <= 8 else 1)) else 1
         cur = prev = None
         if use_labels:
             planes = self._label_planes()
