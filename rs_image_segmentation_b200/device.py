@@ -102,8 +102,9 @@ class MinMaxTracker:
 class StageTimer:
     """CUDA-event sections on the current stream: `with timer("name"):`; totals after a synchronise."""
 
-    def __init__(self, enabled: bool = True):
+    def __init__(self, enabled: bool = True, only=None):
         self.enabled = enabled
+        self.only = set(only) if only is not None else None      # record these sections only (an event pair costs ~3 us)
         self.events = {}
 
     class _Section:
@@ -111,14 +112,15 @@ class StageTimer:
             self.t, self.name = timer, name
 
         def __enter__(self):
-            if self.t.enabled:
+            self.on = self.t.enabled and (self.t.only is None or self.name in self.t.only)
+            if self.on:
                 self.a = torch.cuda.Event(enable_timing=True)
                 self.b = torch.cuda.Event(enable_timing=True)
                 self.a.record()
             return self
 
         def __exit__(self, *exc):
-            if self.t.enabled:
+            if self.on:
                 self.b.record()
                 self.t.events.setdefault(self.name, []).append((self.a, self.b))
             return False
