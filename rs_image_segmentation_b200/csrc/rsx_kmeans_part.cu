@@ -77,6 +77,7 @@ __device__ __forceinline__ int km_exact_argmin_warp(const float* __restrict__ st
         const int j2 = __shfl_xor_sync(0xffffffffu, bi, o);
         if (v2 < best || (v2 == best && j2 < bi)) best = v2, bi = j2;
     }
+    if (bi >= K) bi = 0;  // every distance NaN (a NaN sample): the single-lane loop answers 0 as well
     *dist_out = fmax(xx + best, 0.0);
     return bi;
 }
