@@ -71,3 +71,42 @@ def test_analytic_known_answers():
             assert np.allclose(mt, m, atol=1e-6)
     c = og.props_map_numpy(np.full((7, 7), 5, np.uint8), 32, 7, 1)[:, 0, 0]
     assert np.allclose(c, [0, 0, 1, 1, 1])
+
+
+# ------------------------------------------------------------------------------------------ folded counters
+def _asm_unordered(win, dr, dc, fold=None):
+    """sum over unordered cells of weight * count^2 (weight 2 off the diagonal, 4 on it) = sum of squares of the symmetric
+    GLCM, with the cells optionally indexed by the levels modulo `fold`."""
+    h, w = win.shape
+    a = win[:h - dr, max(0, -dc):w - max(0, dc)].ravel().astype(np.int64)
+    b = win[dr:, max(0, dc):w + min(0, dc)].ravel().astype(np.int64)
+    diag = a == b                                            # the weight belongs to the TRUE pair, as in the kernel's code word
+    if fold:
+        a, b = a % fold, b % fold
+    lo, hi = np.minimum(a, b), np.maximum(a, b)
+    key = hi * 64 + lo
+    total = 0
+    for k in np.unique(key):
+        sel = key == k
+        u = int(sel.sum())
+        # a folded slot may mix diagonal and off-diagonal true cells only when the fold is not injective
+        wgt = 4 if diag[sel].all() else 2
+        total += wgt * u * u
+    return total
+
+
+def test_folded_counters_are_exact_when_the_level_span_is_below_the_fold():
+    """The planned 36-cell private counters index a cell by (a mod 8, b mod 8): exact whenever the grey levels of the window
+    span fewer than 8 values (the fold is injective there); a wider span can break it, which is why such windows get flagged."""
+    rng = np.random.default_rng(8)
+    offs = [(0, 1), (1, 1), (1, 0), (1, -1)]
+    for _ in range(300):
+        base = int(rng.integers(0, 25))
+        win = base + rng.integers(0, 8, size=(7, 7))         # span <= 7
+        for dr, dc in offs:
+            assert _asm_unordered(win, dr, dc) == _asm_unordered(win, dr, dc, fold=8)
+    # span 8: levels 3 and 11 fold onto each other, the counts of two different cells merge
+    win = np.full((7, 7), 3)
+    win[:, 4:] = 11
+    assert _asm_unordered(win, 0, 1) != _asm_unordered(win, 0, 1, fold=8)
+    assert int(win.max() - win.min()) >= 8                   # ... and the span test catches it
