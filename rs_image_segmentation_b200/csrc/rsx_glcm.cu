@@ -173,7 +173,11 @@ struct DenseShared {
 // WIDE (levels > 32): sum of a^2+b^2 needs its own 32-bit word, so the sum of a+b moves into the u64:
 //   narrow: W1 = s1 | sab << 13,  W2 = sa | sq << 14,  SH = homog * 2^40 | Neq << 52
 //   wide:   W1 = s1 | sab << 13,  W2 = sq,             SH = homog * 2^36 | Neq << 43 | sa << 50
-template <int WIN, int NT, int ANG, bool WIDE>
+// FOLD (levels <= 32, experimental): the private counters are indexed by the levels modulo 8 - 36 unordered cells instead of
+// L(L+1)/2, 36 B per window and angle instead of 528 - which is exact for every window whose levels span fewer than 8 values
+// (the fold is injective there).  Windows with a wider span are flagged by glcm_span_flag_kernel and get their energy from
+// glcm_energy_patch_kernel; the other four properties never use the counters.
+template <int WIN, int NT, int ANG, bool WIDE, bool FOLD>
 __device__ __forceinline__ void glcm_dense_body(const DenseShared sm, const uint8_t* __restrict__ q, int W, int L, int out_cols, int i_begin, int i_end,
                                                 int j0, int t, int NTW, float* __restrict__ props, int64_t plane_stride) {
     constexpr int RING = WIN + 1;
@@ -181,7 +185,7 @@ __device__ __forceinline__ void glcm_dense_body(const DenseShared sm, const uint
     constexpr int DC = ANG == 0 ? 1 : (ANG == 1 ? 1 : (ANG == 2 ? 0 : -1));
     constexpr int C0 = ANG == 3 ? 1 : 0, C1 = ANG <= 1 ? WIN - 1 : WIN;  // anchor columns of the angle inside a window
     constexpr int NPAIR = (ANG == 0 || ANG == 2) ? WIN * (WIN - 1) : (WIN - 1) * (WIN - 1);
-    const int ncell = L * (L + 1) / 2;
+    const int ncell = FOLD ? 36 : L * (L + 1) / 2;
     const bool has_win = t < NTW && j0 + t < out_cols;
     const bool col_ok = j0 + t < W;
     const bool pair_ok = t + DC >= 0 && t + DC < NT;  // partner column inside the band
@@ -213,7 +217,7 @@ __device__ __forceinline__ void glcm_dense_body(const DenseShared sm, const uint
         unsigned cell = 0xfffffff0u;  // never equal to a real cell
         if (pair_ok) {
             const int a = qt[sa * NT], b = qt[sb * NT + DC];
-            cell = ((unsigned)(tri_cell(a, b) * NTW) << 16) | (a == b ? 8u : 4u);
+            cell = ((unsigned)((FOLD ? tri_cell(a & 7, b & 7) : tri_cell(a, b)) * NTW) << 16) | (a == b ? 8u : 4u);
             unsigned w1, w2;
             unsigned long long sh;
             pair_terms(a, b, w1, w2, sh);
@@ -351,14 +355,14 @@ __device__ __forceinline__ void glcm_dense_body(const DenseShared sm, const uint
     }
 }
 
-template <int WIN, int NT, bool WIDE>
+template <int WIN, int NT, bool WIDE, bool FOLD>
 __global__ void __launch_bounds__(NT * 4) glcm_dense_kernel(const uint8_t* __restrict__ q, int W, int L, int out_rows, int out_cols, int rows_per_cta,
                                                             int NTW, float* __restrict__ props, int64_t plane_stride) {
     // NTW = windows per CTA, <= NT - (WIN - 1), capped by what the private counters leave of shared memory
     constexpr int RING = WIN + 1;
     extern __shared__ __align__(16) unsigned char dsm[];
     __shared__ unsigned long long homog_fx[64];
-    const int ncell = L * (L + 1) / 2;
+    const int ncell = FOLD ? 36 : L * (L + 1) / 2;
     DenseShared sm;
     sm.xch = reinterpret_cast<uint4*>(dsm);
     sm.outx = reinterpret_cast<float*>(sm.xch + 4 * NT);
@@ -383,10 +387,10 @@ __global__ void __launch_bounds__(NT * 4) glcm_dense_kernel(const uint8_t* __res
                         (tid == 0 ? (1ull << (WIDE ? 43 : 52)) : 0ull);
     __syncthreads();
     switch (ang) {  // warp-uniform
-        case 0: glcm_dense_body<WIN, NT, 0, WIDE>(sm, q, W, L, out_cols, i_begin, i_end, j0, t, NTW, props, plane_stride); break;
-        case 1: glcm_dense_body<WIN, NT, 1, WIDE>(sm, q, W, L, out_cols, i_begin, i_end, j0, t, NTW, props, plane_stride); break;
-        case 2: glcm_dense_body<WIN, NT, 2, WIDE>(sm, q, W, L, out_cols, i_begin, i_end, j0, t, NTW, props, plane_stride); break;
-        default: glcm_dense_body<WIN, NT, 3, WIDE>(sm, q, W, L, out_cols, i_begin, i_end, j0, t, NTW, props, plane_stride); break;
+        case 0: glcm_dense_body<WIN, NT, 0, WIDE, FOLD>(sm, q, W, L, out_cols, i_begin, i_end, j0, t, NTW, props, plane_stride); break;
+        case 1: glcm_dense_body<WIN, NT, 1, WIDE, FOLD>(sm, q, W, L, out_cols, i_begin, i_end, j0, t, NTW, props, plane_stride); break;
+        case 2: glcm_dense_body<WIN, NT, 2, WIDE, FOLD>(sm, q, W, L, out_cols, i_begin, i_end, j0, t, NTW, props, plane_stride); break;
+        default: glcm_dense_body<WIN, NT, 3, WIDE, FOLD>(sm, q, W, L, out_cols, i_begin, i_end, j0, t, NTW, props, plane_stride); break;
     }
 }
 
@@ -394,11 +398,11 @@ static size_t dense_smem_bytes(int win, int nt, int ntw, int ncell) {
     return (size_t)4 * ncell * ntw + (size_t)nt * (16 * (win + 1) + 16 + 64 + 80 + (win + 1)) + 16 * win + 64;
 }
 
-template <int WIN, int NT, bool WIDE>
+template <int WIN, int NT, bool WIDE, bool FOLD = false>
 static int launch_dense(const uint8_t* d_q, int W, int levels, int ntw, int out_rows, int out_cols, float* d_props, int64_t plane_stride, cudaStream_t s) {
-    const int ncell = levels * (levels + 1) / 2;
+    const int ncell = FOLD ? 36 : levels * (levels + 1) / 2;
     const size_t smem = dense_smem_bytes(WIN, NT, ntw, ncell);
-    auto kern = glcm_dense_kernel<WIN, NT, WIDE>;
+    auto kern = glcm_dense_kernel<WIN, NT, WIDE, FOLD>;
     static size_t configured = 0;
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max(smem, (size_t)49152));
@@ -460,6 +464,123 @@ static int dispatch_dense(const uint8_t* d_q, int W, int levels, int out_rows, i
     return -1;
 }
 
+// ----------------------------------------------------------------------------- folded counters: span flags + energy patch
+// flags[i * out_cols + j] = 1 when the levels of window (i, j) span 8 or more values (the fold modulo 8 may then merge two cells).
+// One CTA per tile of SPAN_TR x SPAN_TC windows: the clamped levels of the tile (+ win-1 halo) go to shared memory, a horizontal
+// min/max pass over win columns, then a vertical one over win rows.
+constexpr int SPAN_TR = 32, SPAN_TC = 128, SPAN_MAXW = 11;
+__global__ void __launch_bounds__(256) glcm_span_flag_kernel(const uint8_t* __restrict__ q, int W, int L, int win, int out_rows, int out_cols,
+                                                             uint8_t* __restrict__ flags) {
+    __shared__ uint8_t raw[SPAN_TR + SPAN_MAXW - 1][SPAN_TC + SPAN_MAXW - 1 + 1];
+    __shared__ uint8_t hmn[SPAN_TR + SPAN_MAXW - 1][SPAN_TC], hmx[SPAN_TR + SPAN_MAXW - 1][SPAN_TC];
+    const int i0 = blockIdx.y * SPAN_TR, j0 = blockIdx.x * SPAN_TC;
+    const int rows = min(SPAN_TR, out_rows - i0) + win - 1, cols = min(SPAN_TC, out_cols - j0) + win - 1;
+    for (int k = threadIdx.x; k < rows * cols; k += 256) {
+        const int r = k / cols, c = k - r * cols;
+        raw[r][c] = (uint8_t)min((int)q[(int64_t)(i0 + r) * W + j0 + c], L - 1);
+    }
+    __syncthreads();
+    const int ocols = cols - (win - 1), orows = rows - (win - 1);
+    for (int k = threadIdx.x; k < rows * ocols; k += 256) {
+        const int r = k / ocols, c = k - r * ocols;
+        int mn = 255, mx = 0;
+        for (int d = 0; d < win; ++d) mn = min(mn, (int)raw[r][c + d]), mx = max(mx, (int)raw[r][c + d]);
+        hmn[r][c] = (uint8_t)mn, hmx[r][c] = (uint8_t)mx;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < orows * ocols; k += 256) {
+        const int r = k / ocols, c = k - r * ocols;
+        int mn = 255, mx = 0;
+        for (int d = 0; d < win; ++d) mn = min(mn, (int)hmn[r + d][c]), mx = max(mx, (int)hmx[r + d][c]);
+        flags[(int64_t)(i0 + r) * out_cols + j0 + c] = (uint8_t)(mx - mn >= 8);
+    }
+}
+
+// Exact energy of the flagged windows, one warp per window, with the float operations of glcm_dense_body (so that a patched
+// value equals what the unfolded dense kernel writes): per angle E = sum over the pairs of w * U[cell of the pair] from a
+// warp-private histogram of all L(L+1)/2 unordered cells, energy = sqrtf(E) * (0.5 / n); mean of the four angles.
+__global__ void __launch_bounds__(256) glcm_energy_patch_kernel(const uint8_t* __restrict__ q, int W, int L, int win, int out_rows, int out_cols,
+                                                                const uint8_t* __restrict__ flags, float* __restrict__ energy) {
+    __shared__ unsigned hist_all[8][528];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned* hist = hist_all[warp];
+    for (int i = lane; i < 528; i += 32) hist[i] = 0;
+    __syncwarp();
+    const int64_t n_win = (int64_t)out_rows * out_cols;
+    const int64_t warps_total = (int64_t)gridDim.x * 8;
+    for (int64_t base = ((int64_t)blockIdx.x * 8 + warp) * 32; base < n_win; base += warps_total * 32) {
+        const int64_t mine = base + lane;
+        unsigned todo = __ballot_sync(0xffffffffu, mine < n_win && flags[mine] != 0);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int64_t o = base + src;
+            const int oi = (int)(o / out_cols), oj = (int)(o - (int64_t)oi * out_cols);
+            const uint8_t* wbase = q + (int64_t)oi * W + oj;
+            float part[4];
+#pragma unroll
+            for (int ang = 0; ang < 4; ++ang) {
+                const int dr = ang == 0 ? 0 : 1;
+                const int dc = ang == 0 ? 1 : (ang == 1 ? 1 : (ang == 2 ? 0 : -1));
+                const int nrows = win - dr, ncols = win - (dc != 0 ? 1 : 0), c0 = dc < 0 ? 1 : 0;
+                const int n = nrows * ncols, off = dr * W + dc;
+                for (int sidx = lane; sidx < n; sidx += 32) {
+                    const int r = sidx / ncols, c = sidx - r * ncols + c0;
+                    const uint8_t* pp = wbase + r * W + c;
+                    const int a = min((int)pp[0], L - 1), b = min((int)pp[off], L - 1);
+                    atomicAdd(&hist[tri_cell(a, b)], 1u);
+                }
+                __syncwarp();
+                int e = 0;
+                for (int sidx = lane; sidx < n; sidx += 32) {
+                    const int r = sidx / ncols, c = sidx - r * ncols + c0;
+                    const uint8_t* pp = wbase + r * W + c;
+                    const int a = min((int)pp[0], L - 1), b = min((int)pp[off], L - 1);
+                    e += (a != b ? 2 : 4) * (int)hist[tri_cell(a, b)];
+                }
+                __syncwarp();
+                for (int sidx = lane; sidx < n; sidx += 32) {
+                    const int r = sidx / ncols, c = sidx - r * ncols + c0;
+                    const uint8_t* pp = wbase + r * W + c;
+                    const int a = min((int)pp[0], L - 1), b = min((int)pp[off], L - 1);
+                    hist[tri_cell(a, b)] = 0;
+                }
+                __syncwarp();
+                e = __reduce_add_sync(0xffffffffu, e);
+                const float inv_n = 1.f / (float)n;
+                part[ang] = sqrtf((float)e) * (0.5f * inv_n);
+            }
+            if (lane == 0) energy[o] = ((part[0] + part[1]) + (part[2] + part[3])) * 0.25f;
+        }
+    }
+}
+
+static uint8_t* g_span_flags = nullptr;
+static size_t g_span_flags_cap = 0;
+
+// folded dense path (levels <= 32, RSX_GLCM_FOLD=1): flags, folded kernel, energy patch.  Returns -1 when not applicable.
+template <int WIN>
+static int dispatch_dense_folded(const uint8_t* d_q, int W, int levels, int out_rows, int out_cols, float* d_props, int64_t plane_stride, cudaStream_t s) {
+    const size_t n_win = (size_t)out_rows * out_cols;
+    if (n_win > g_span_flags_cap) {
+        if (g_span_flags) cudaFree(g_span_flags);
+        g_span_flags = nullptr, g_span_flags_cap = 0;
+        if (cudaMalloc(&g_span_flags, n_win) != cudaSuccess) {
+            cudaGetLastError();
+            return -1;
+        }
+        g_span_flags_cap = n_win;
+    }
+    glcm_span_flag_kernel<<<dim3(ceil_div(out_cols, SPAN_TC), ceil_div(out_rows, SPAN_TR)), 256, 0, s>>>(d_q, W, levels, WIN, out_rows, out_cols, g_span_flags);
+    if (int rc = rsx_check_launch("glcm_span_flags")) return rc;
+    constexpr int NT = 128;
+    const int ntw = NT - (WIN - 1);
+    if (int rc = launch_dense<WIN, NT, false, true>(d_q, W, levels, ntw, out_rows, out_cols, d_props, plane_stride, s)) return rc;
+    const int grid = (int)min((int64_t)ceil_div((int64_t)n_win, (int64_t)256), (int64_t)rsx_num_sms() * 8);
+    glcm_energy_patch_kernel<<<grid, 256, 0, s>>>(d_q, W, levels, WIN, out_rows, out_cols, g_span_flags, d_props + 3 * plane_stride);
+    return rsx_check_launch("glcm_energy_patch");
+}
+
 extern "C" int rsx_glcm_props(const uint8_t* d_q, int rows_avail, int W, int levels, int window, int step, int out_rows, int out_cols,
                               float* d_props, int64_t plane_stride, rsx_stream_t stream) {
     RSX_REQUIRE(d_q && d_props, "rsx_glcm_props: null argument");
@@ -474,6 +595,22 @@ extern "C" int rsx_glcm_props(const uint8_t* d_q, int rows_avail, int W, int lev
     // dense fast path: packed integer moments hold for levels <= 64 and window <= 11; uint8 counters hold w(w-1) <= 110
     if (step == 1 && levels <= 64) {
         int rc = -1;
+        static int fold_env = -1;
+        if (fold_env < 0) {
+            const char* e = getenv("RSX_GLCM_FOLD");
+            fold_env = e ? atoi(e) : 0;
+        }
+        if (fold_env && levels <= 32) {
+            switch (window) {
+                case 3: rc = dispatch_dense_folded<3>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, s); break;
+                case 5: rc = dispatch_dense_folded<5>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, s); break;
+                case 7: rc = dispatch_dense_folded<7>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, s); break;
+                case 9: rc = dispatch_dense_folded<9>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, s); break;
+                case 11: rc = dispatch_dense_folded<11>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, s); break;
+                default: break;
+            }
+            if (rc >= 0) return rc;
+        }
 #define DENSE(WW)                                                                                                    \
     case WW:                                                                                                         \
         rc = levels <= 32 ? dispatch_dense<WW, false>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, s)  \
