@@ -49,6 +49,9 @@ const char* rsx_last_error(void);
 int rsx_abi_version(void);
 /* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
 int64_t rsx_launch_count(void);
+/* Integer tuning knobs (kernel-variant switches for the profiling tools and A/B tests; never needed for correct results).
+ * A knob that was never set falls back to the environment variable RSX_<NAME IN UPPER CASE>, then to the built-in default. */
+int rsx_set_option(const char* name, int value);
 /* Copies `bytes` from device memory into PAGE-LOCKED host memory (cudaHostAlloc / torch pin_memory: under unified addressing
  * the device writes through the same pointer) with a kernel, on `stream`; the caller synchronises.  For the small per-scene
  * results (histograms, moments, min/max, KMeans state): unlike cudaMemcpyAsync it does not queue behind a large transfer on
@@ -142,6 +145,14 @@ int rsx_pca_project_u16(const uint16_t* d_raster, int64_t n_px, int n_bands, con
  * d_props:  5 planes [out_rows][out_cols], plane stride in elements. */
 int rsx_glcm_props(const uint8_t* d_q, int rows_avail, int W, int levels, int window, int step, int out_rows, int out_cols,
                    float* d_props, int64_t plane_stride, rsx_stream_t stream);
+/* rsx_glcm_props with the same kernels ALSO storing, for every window and angle, the exact integers the five properties are
+ * made from (validation of the production kernel's integer stage against graycomatrix counts, bit for bit):
+ * d_moments int64 [out_rows*out_cols][4][8] = n (pair instances), sum|a-b|, sum(a+b), sum(a^2+b^2), sum(a*b),
+ * E = sum over the cells of the symmetric count matrix P = C + C^T of P^2, pairs with a == b, sum of round(2^40/(1+(a-b)^2)).
+ * contrast = (sq-2sab)/n, dissimilarity = s1/n, homogeneity = hom/2^40/n, energy = sqrt(E)/2n,
+ * correlation = (4n*sab - sa^2)/(2n*sq - sa^2) (1 for a constant window). */
+int rsx_glcm_moments(const uint8_t* d_q, int rows_avail, int W, int levels, int window, int step, int out_rows, int out_cols,
+                     float* d_props, int64_t plane_stride, int64_t* d_moments, rsx_stream_t stream);
 /* Directed (un-symmetrised) uint32 co-occurrence counts, [n_win][4][levels][levels], for the
  * windows whose top-left corners are listed in d_anchors (int32 [n_win][2] = row, col):
  * skimage graycomatrix(symmetric=False, normed=False) of each window.  Validation entry point. */
@@ -196,6 +207,11 @@ void rsx_minmax_decode(const uint32_t* h_minmax, int n, float* h_min, float* h_m
 void rsx_minmax_encode(const float* h_min, const float* h_max, int n, uint32_t* h_minmax);
 /* NaN -> 0 in place (extract.py:548-556) */
 int rsx_nan_to_zero_f32(float* d_planes, int64_t n, rsx_stream_t stream);
+/* The same on ONE plane whose tracker slot was filled by its producer (the producers skip NaN): when a NaN is replaced, 0
+ * joins the tracked range, because the reference fits MinMaxScaler after the replacement (extract.py:548-570).  The device
+ * pipeline calls it on the MSAVI plane (the only index that can be NaN for finite input: sqrt of a float32 radicand that
+ * rounds below zero, indices.py:109-112) before KMeans. */
+int rsx_nan_to_zero_minmax_f32(float* d_plane, int64_t n, uint32_t* d_minmax_slot, rsx_stream_t stream);
 
 /* ---- K5: KMeans -------------------------------------------------------------------------------
  * Replaces MinMaxScaler.transform + the Lloyd iteration of sklearn KMeans as driven by

@@ -34,6 +34,12 @@ import numpy as np
 from .features import robust_normalize
 
 PROPS = ("contrast", "dissimilarity", "homogeneity", "energy", "correlation")
+# Property known answers published by scikit-image's own test suite (skimage/feature/tests/test_texture.py: test_contrast,
+# test_dissimilarity, test_homogeneity, test_energy, test_correlation) for the docstring image [[0,0,1,1],[0,0,1,1],[0,2,2,2],
+# [2,2,3,3]], levels 4, symmetric=True, normed=True, entry (distance 1, angle 0); correlation also at distance 2.  The contrast
+# and dissimilarity tests of scikit-image round the normalised matrix to 3 decimals first.
+SKIMAGE_PROP_KATS = dict(contrast_rounded=0.585, dissimilarity_rounded=0.418, homogeneity=0.80833333, energy=0.38188131,
+                         correlation=0.71953255, correlation_d2=0.41176470)
 DEFAULT_ANGLES = (0.0, np.pi / 4, np.pi / 2, 3 * np.pi / 4)
 
 
@@ -189,6 +195,44 @@ def counts_map_c(q, levels, window, step):
     if rc != 0:
         raise RuntimeError(f"oracle_glcm_counts failed: {rc}")
     return out
+
+
+# ------------------------------------------------------------------ integer pair moments (what the dense GPU kernel keeps)
+MOMENT_FIELDS = ("n", "s1", "sa", "sq", "sab", "e", "neq", "hom_fx")
+
+
+def pair_moments(q, levels, window, step=1):
+    """(oh, ow, 4, 8) int64: for every window and angle the exact integers from which the five properties follow without a
+    histogram (include/rsx.h rsx_glcm_moments; derived from the directed counts of counts_map_c, i.e. from the same
+    graycomatrix restatement that the docstring known answer pins):
+      n    pair instances            s1  sum |a-b|          sa  sum (a+b)        sq  sum (a^2+b^2)      sab  sum a*b
+      e    sum over the cells of the SYMMETRIC count matrix P = C + C^T of P^2 (so energy = sqrt(e) / 2n)
+      neq  pairs with a == b         hom_fx  sum of round(2^40 / (1 + (a-b)^2)) (the kernel's fixed-point homogeneity terms)"""
+    C = counts_map_c(q, levels, window, step).astype(np.int64)            # (oh, ow, 4, L, L)
+    a = np.arange(levels, dtype=np.int64).reshape(levels, 1)
+    b = np.arange(levels, dtype=np.int64).reshape(1, levels)
+    d = np.abs(a - b)
+    hom = np.floor(2.0 ** 40 / (1.0 + (d * d).astype(np.float64)) + 0.5).astype(np.int64)
+    S = C + C.transpose(0, 1, 2, 4, 3)
+    out = np.zeros(C.shape[:3] + (8,), dtype=np.int64)
+    out[..., 0] = C.sum(axis=(3, 4))
+    out[..., 1] = (C * d).sum(axis=(3, 4))
+    out[..., 2] = (C * (a + b)).sum(axis=(3, 4))
+    out[..., 3] = (C * (a * a + b * b)).sum(axis=(3, 4))
+    out[..., 4] = (C * (a * b)).sum(axis=(3, 4))
+    out[..., 5] = (S * S).sum(axis=(3, 4))
+    out[..., 6] = (C * (d == 0)).sum(axis=(3, 4))
+    out[..., 7] = (C * hom).sum(axis=(3, 4))
+    return out
+
+
+def props_from_moments(m):
+    """The five graycoprops of one angle from its pair moments, float64 (rsx_glcm.cu header comment)."""
+    n, s1, sa, sq, sab, e, neq, hom_fx = (int(v) for v in m)
+    var_num = 2 * n * sq - sa * sa
+    cov_num = 4 * n * sab - sa * sa
+    return dict(contrast=(sq - 2 * sab) / n, dissimilarity=s1 / n, homogeneity=hom_fx / 2.0 ** 40 / n, energy=np.sqrt(float(e)) / (2.0 * n),
+                correlation=1.0 if var_num <= 0 else cov_num / var_num)
 
 
 # ------------------------------------------------------------------ closed-form known answers (implementation independent)

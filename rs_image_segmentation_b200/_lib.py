@@ -17,6 +17,7 @@ SIGNATURES = {
     "rsx_last_error": (C.c_char_p, []),
     "rsx_abi_version": (i32, []),
     "rsx_launch_count": (i64, []),
+    "rsx_set_option": (i32, [C.c_char_p, i32]),
     "rsx_store_to_host": (i32, [vp, vp, i64, vp]),
     "rsx_raster_stats": (i32, [vp, i32, i32, i32, f64, f64, vp, vp, vp, vp, vp, vp]),
     "rsx_hist_u8": (i32, [vp, i64, i32, vp, vp]),
@@ -36,6 +37,7 @@ SIGNATURES = {
     "rsx_pca_project_u8": (i32, [vp, i64, i32, vp, vp, vp, i32, vp, i64, vp, vp]),
     "rsx_pca_project_u16": (i32, [vp, i64, i32, vp, vp, vp, vp, vp, vp, i32, vp, i64, vp, vp]),
     "rsx_glcm_props": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, vp, i64, vp]),
+    "rsx_glcm_moments": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, vp, i64, vp, vp]),
     "rsx_glcm_counts": (i32, [vp, i32, i32, i32, i32, vp, i32, vp, vp]),
     "rsx_resize_bilinear_f32": (i32, [vp, i32, i32, i32, i32, i64, vp, i32, i32, i32, i32, i64, i32, vp, vp]),
     "rsx_minmax_init": (i32, [vp, i32, vp]),
@@ -43,6 +45,7 @@ SIGNATURES = {
     "rsx_minmax_decode": (None, [vp, i32, vp, vp]),
     "rsx_minmax_encode": (None, [vp, vp, i32, vp]),
     "rsx_nan_to_zero_f32": (i32, [vp, i64, vp]),
+    "rsx_nan_to_zero_minmax_f32": (i32, [vp, i64, vp, vp]),
     "rsx_band_lut_u8": (i32, [vp, i64, i32, i32, vp, vp, vp]),
     "rsx_band_lut_f32": (i32, [vp, i64, i32, i32, vp, vp, vp]),
     "rsx_morph_gradient_u8": (i32, [vp, i32, i32, i32, i32, vp, i32, i32, i32, vp]),
@@ -102,6 +105,11 @@ def check(rc: int, what: str = ""):
 def call(name: str, *args):
     """Call an int-returning entry point and raise on a non-zero status."""
     check(getattr(load(), name)(*args), name)
+
+
+def set_option(name: str, value: int):
+    """Tuning knob of the library (include/rsx.h rsx_set_option)."""
+    check(load().rsx_set_option(name.encode(), int(value)), "rsx_set_option")
 
 
 def launch_count() -> int:

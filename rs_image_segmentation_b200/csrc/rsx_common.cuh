@@ -11,6 +11,8 @@
 void rsx_set_error(const char* fmt, ...);
 int rsx_check_launch(const char* what);
 int rsx_num_sms();
+// integer tuning knob: rsx_set_option value, else env RSX_<NAME>, else dflt (rsx_core.cu)
+int rsx_option(const char* name, int dflt);
 // device -> host of a small block through a kernel store into a page-locked staging buffer; synchronises the stream
 int rsx_fetch_small(void* h_dst, const void* d_src, size_t bytes, cudaStream_t s);
 
@@ -31,6 +33,8 @@ __device__ __forceinline__ float f_mul(float a, float b) { return __fmul_rn(a, b
 __device__ __forceinline__ float f_div(float a, float b) { return __fdiv_rn(a, b); }
 __device__ __forceinline__ float f_sqrt(float a) { return __fsqrt_rn(a); }
 __device__ __forceinline__ float f_clip(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+// np.clip keeps NaN (fminf/fmaxf would drop it): for the planar drop-ins, whose inputs are arbitrary caller arrays
+__device__ __forceinline__ float f_clip_nan(float x, float lo, float hi) { return x != x ? x : fminf(fmaxf(x, lo), hi); }
 
 // robust_normalize (modules/features/indices.py:42-46): (clip(x, lo, hi) - lo) / (hi - lo + 1e-10)
 // den = fl32(fl32(hi - lo) + 1e-10f) is precomputed on the host in float32.

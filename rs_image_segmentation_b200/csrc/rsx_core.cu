@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -37,6 +38,46 @@ int rsx_num_sms() {
             n = RSX_SM_COUNT_FALLBACK;
     }
     return n;
+}
+
+// ----------------------------------------------------------------------------- tuning options
+// Small registry of integer knobs (kernel variant switches used by the profiling tools and the A/B tests).  A knob set through
+// rsx_set_option wins; otherwise the environment variable RSX_<NAME IN UPPER CASE> is consulted on every query; otherwise the
+// default of the call site.
+struct RsxOption {
+    char name[32];
+    int value;
+};
+static RsxOption g_options[32];
+static int g_n_options = 0;
+static std::mutex g_option_mu;
+
+int rsx_option(const char* name, int dflt) {
+    {
+        std::lock_guard<std::mutex> lock(g_option_mu);
+        for (int i = 0; i < g_n_options; ++i)
+            if (!strcmp(g_options[i].name, name)) return g_options[i].value;
+    }
+    char env[48] = "RSX_";
+    size_t k = 4;
+    for (const char* c = name; *c && k + 1 < sizeof(env); ++c) env[k++] = (char)((*c >= 'a' && *c <= 'z') ? *c - 32 : *c);
+    env[k] = 0;
+    const char* e = getenv(env);
+    return e ? atoi(e) : dflt;
+}
+
+extern "C" int rsx_set_option(const char* name, int value) {
+    RSX_REQUIRE(name && strlen(name) < sizeof(g_options[0].name), "rsx_set_option: bad name");
+    std::lock_guard<std::mutex> lock(g_option_mu);
+    for (int i = 0; i < g_n_options; ++i)
+        if (!strcmp(g_options[i].name, name)) {
+            g_options[i].value = value;
+            return RSX_OK;
+        }
+    RSX_REQUIRE(g_n_options < (int)(sizeof(g_options) / sizeof(g_options[0])), "rsx_set_option: table full");
+    strcpy(g_options[g_n_options].name, name);
+    g_options[g_n_options++].value = value;
+    return RSX_OK;
 }
 
 extern "C" const char* rsx_last_error(void) { return g_err; }
@@ -222,6 +263,33 @@ __global__ void __launch_bounds__(256) nan_to_zero_kernel(float* p, int64_t n) {
         if (v != v) p[i] = 0.f;
     }
 }
+// NaN -> 0 on one plane of a stack whose min/max tracker was filled by the producer (which skips NaN): when a NaN was replaced,
+// 0 joins the tracked range - MinMaxScaler is fitted after the replacement in the reference (extract.py:548-570).
+__global__ void __launch_bounds__(256) nan_to_zero_minmax_kernel(float* __restrict__ p, int64_t n, uint32_t* __restrict__ slot) {
+    bool any = false;
+    const int64_t n4 = n >> 2;
+    const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = i0; i < n4; i += stride) {
+        float4 v = ldg_stream4(p + 4 * i);
+        if (v.x != v.x || v.y != v.y || v.z != v.z || v.w != v.w) {
+            v.x = v.x != v.x ? 0.f : v.x, v.y = v.y != v.y ? 0.f : v.y, v.z = v.z != v.z ? 0.f : v.z, v.w = v.w != v.w ? 0.f : v.w;
+            *reinterpret_cast<float4*>(p + 4 * i) = v;
+            any = true;
+        }
+    }
+    for (int64_t i = (n4 << 2) + i0; i < n; i += stride)
+        if (p[i] != p[i]) p[i] = 0.f, any = true;
+    if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0 && slot) {
+        atomicMin(slot, f2ord(0.f));
+        atomicMax(slot + 1, f2ord(0.f));
+    }
+}
+extern "C" int rsx_nan_to_zero_minmax_f32(float* d_plane, int64_t n, uint32_t* d_minmax_slot, rsx_stream_t stream) {
+    RSX_REQUIRE(d_plane && n > 0 && ((uintptr_t)d_plane & 15) == 0, "rsx_nan_to_zero_minmax_f32: bad arguments (the plane must be 16-byte aligned)");
+    nan_to_zero_minmax_kernel<<<(int)min((int64_t)rsx_num_sms() * 8, ceil_div(n, (int64_t)1024)), 256, 0, (cudaStream_t)stream>>>(d_plane, n, d_minmax_slot);
+    return rsx_check_launch("nan_to_zero_minmax");
+}
+
 extern "C" int rsx_nan_to_zero_f32(float* d, int64_t n, rsx_stream_t stream) {
     RSX_REQUIRE(d && n > 0, "rsx_nan_to_zero_f32: bad arguments");
     nan_to_zero_kernel<<<(int)min((int64_t)rsx_num_sms() * 8, ceil_div(n, (int64_t)256)), 256, 0, (cudaStream_t)stream>>>(d, n);
@@ -232,14 +300,14 @@ extern "C" int rsx_nan_to_zero_f32(float* d, int64_t n, rsx_stream_t stream) {
 // One functor per reference function; the driver handles vectorised body + scalar tail.
 struct OpNormalize {
     NormParam p;
-    __device__ float operator()(float x, float, float, float) const { return norm_apply(x, p); }
+    __device__ float operator()(float x, float, float, float) const { return f_div(f_sub(f_clip_nan(x, p.lo, p.hi), p.lo), p.den); }
 };
 // indices.py:62-69 and its three siblings: num = a-b, den = a+b
 struct OpRatio {
     __device__ float operator()(float a, float b, float, float) const {
         float den = f_add(a, b);
         float r = den > 0.001f ? f_div(f_sub(a, b), den) : 0.f;
-        return f_clip(r, -1.f, 1.f);
+        return f_clip_nan(r, -1.f, 1.f);
     }
 };
 // indices.py:86-93: den = nir + C1*red - C2*blue + L ; G*(nir-red)/den
@@ -248,7 +316,7 @@ struct OpEvi {
     __device__ float operator()(float nir, float red, float blue, float) const {
         float den = f_add(f_sub(f_add(nir, f_mul(C1, red)), f_mul(C2, blue)), L);
         float r = den > 0.001f ? f_div(f_mul(G, f_sub(nir, red)), den) : 0.f;
-        return f_clip(r, -1.f, 1.f);
+        return f_clip_nan(r, -1.f, 1.f);
     }
 };
 // indices.py:109: (2n+1 - sqrt((2n+1)^2 - 8(n-r)))/2 ; NaN propagates through the clip like np.clip
@@ -266,7 +334,7 @@ struct OpBsi {
         float a = f_add(swir, red), b = f_add(nir, blue);
         float den = f_add(a, b);
         float r = den > 0.001f ? f_div(f_sub(a, b), den) : 0.f;
-        return f_clip(r, -1.f, 1.f);
+        return f_clip_nan(r, -1.f, 1.f);
     }
 };
 

@@ -60,7 +60,8 @@ __device__ __forceinline__ void angle_props(const AngleSums& t, int n, double (&
 // Any window/step/levels.  The histogram of unordered cells lives in the warp's slice of shared memory and is
 // cleaned by revisiting only the touched cells, so the cost per window is O(pairs), not O(levels^2).
 __global__ void __launch_bounds__(128) glcm_props_warp_kernel(const uint8_t* __restrict__ q, int W, int L, int win, int step, int out_rows,
-                                                              int out_cols, float* __restrict__ props, int64_t plane_stride) {
+                                                              int out_cols, float* __restrict__ props, int64_t plane_stride,
+                                                              long long* __restrict__ moments) {
     extern __shared__ unsigned glcm_sm[];
     const int ncell = L * (L + 1) / 2;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -81,12 +82,15 @@ __global__ void __launch_bounds__(128) glcm_props_warp_kernel(const uint8_t* __r
             const int n = nrows * ncols;
             const int off = dr * W + dc;
             AngleSums t = {0, 0, 0, 0, 0, 0.0};
+            long long hfx = 0;  // moments dump only: the fixed-point homogeneity terms of the dense kernel
+            int neq = 0;
             // pass A: count + integer moments
             for (int s = lane; s < n; s += 32) {
                 const int r = s / ncols, c = s - r * ncols + c0;
                 const uint8_t* p = base + r * W + c;
                 const int a = p[0], b = p[off];
                 const int d = abs(a - b);
+                if (moments) hfx += (long long)(1099511627776.0 / (1.0 + (double)d * (double)d) + 0.5), neq += d == 0;
                 t.s1 += d;
                 t.sa += a + b;
                 t.sq += a * a + b * b;
@@ -118,6 +122,15 @@ __global__ void __launch_bounds__(128) glcm_props_warp_kernel(const uint8_t* __r
             t.e = __reduce_add_sync(0xffffffffu, t.e);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) t.sh += __shfl_xor_sync(0xffffffffu, t.sh, o);
+            if (moments) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) hfx += __shfl_xor_sync(0xffffffffu, hfx, o);
+                neq = __reduce_add_sync(0xffffffffu, neq);
+                if (lane == 0) {
+                    long long* m = moments + (((int64_t)oi * out_cols + oj) * 4 + ang) * 8;
+                    m[0] = n, m[1] = t.s1, m[2] = t.sa, m[3] = t.sq, m[4] = t.sab, m[5] = t.e, m[6] = neq, m[7] = hfx;
+                }
+            }
             if (lane == 0) angle_props(t, n, acc);
         }
         if (lane == 0) {
@@ -179,7 +192,8 @@ struct DenseShared {
 // glcm_energy_patch_kernel; the other four properties never use the counters.
 template <int WIN, int NT, int ANG, bool WIDE, bool FOLD>
 __device__ __forceinline__ void glcm_dense_body(const DenseShared sm, const uint8_t* __restrict__ q, int W, int L, int out_cols, int i_begin, int i_end,
-                                                int j0, int t, int NTW, float* __restrict__ props, int64_t plane_stride) {
+                                                int j0, int t, int NTW, float* __restrict__ props, int64_t plane_stride,
+                                                long long* __restrict__ moments) {
     constexpr int RING = WIN + 1;
     constexpr int DR = ANG == 0 ? 0 : 1;
     constexpr int DC = ANG == 0 ? 1 : (ANG == 1 ? 1 : (ANG == 2 ? 0 : -1));
@@ -324,6 +338,11 @@ __device__ __forceinline__ void glcm_dense_body(const DenseShared sm, const uint
             o[3 * NT] = sqrtf((float)(e + 2 * NPAIR + 2 * neq)) * (0.5f * inv_n);
             const int var_num = 2 * NPAIR * sq - sa * sa, cov_num = 4 * NPAIR * sab - sa * sa;
             o[4 * NT] = var_num <= 0 ? 1.f : (float)cov_num / (float)var_num;
+            if (moments) {  // validation dump of the exact integers the five values above were made from (rsx_glcm_moments)
+                long long* m = moments + (((int64_t)i * out_cols + j0 + t) * 4 + ANG) * 8;
+                m[0] = NPAIR, m[1] = s1, m[2] = sa, m[3] = sq, m[4] = sab, m[5] = e + 2 * NPAIR + 2 * neq, m[6] = neq;
+                m[7] = (long long)(WIDE ? (shom << 4) : shom);  // 2^40-scaled sum (the wide variant keeps 2^36)
+            }
         }
         int s_anchor = -1;
         if (more) {
@@ -357,7 +376,7 @@ __device__ __forceinline__ void glcm_dense_body(const DenseShared sm, const uint
 
 template <int WIN, int NT, bool WIDE, bool FOLD>
 __global__ void __launch_bounds__(NT * 4) glcm_dense_kernel(const uint8_t* __restrict__ q, int W, int L, int out_rows, int out_cols, int rows_per_cta,
-                                                            int NTW, float* __restrict__ props, int64_t plane_stride) {
+                                                            int NTW, float* __restrict__ props, int64_t plane_stride, long long* __restrict__ moments) {
     // NTW = windows per CTA, <= NT - (WIN - 1), capped by what the private counters leave of shared memory
     constexpr int RING = WIN + 1;
     extern __shared__ __align__(16) unsigned char dsm[];
@@ -387,10 +406,10 @@ __global__ void __launch_bounds__(NT * 4) glcm_dense_kernel(const uint8_t* __res
                         (tid == 0 ? (1ull << (WIDE ? 43 : 52)) : 0ull);
     __syncthreads();
     switch (ang) {  // warp-uniform
-        case 0: glcm_dense_body<WIN, NT, 0, WIDE, FOLD>(sm, q, W, L, out_cols, i_begin, i_end, j0, t, NTW, props, plane_stride); break;
-        case 1: glcm_dense_body<WIN, NT, 1, WIDE, FOLD>(sm, q, W, L, out_cols, i_begin, i_end, j0, t, NTW, props, plane_stride); break;
-        case 2: glcm_dense_body<WIN, NT, 2, WIDE, FOLD>(sm, q, W, L, out_cols, i_begin, i_end, j0, t, NTW, props, plane_stride); break;
-        default: glcm_dense_body<WIN, NT, 3, WIDE, FOLD>(sm, q, W, L, out_cols, i_begin, i_end, j0, t, NTW, props, plane_stride); break;
+        case 0: glcm_dense_body<WIN, NT, 0, WIDE, FOLD>(sm, q, W, L, out_cols, i_begin, i_end, j0, t, NTW, props, plane_stride, moments); break;
+        case 1: glcm_dense_body<WIN, NT, 1, WIDE, FOLD>(sm, q, W, L, out_cols, i_begin, i_end, j0, t, NTW, props, plane_stride, moments); break;
+        case 2: glcm_dense_body<WIN, NT, 2, WIDE, FOLD>(sm, q, W, L, out_cols, i_begin, i_end, j0, t, NTW, props, plane_stride, moments); break;
+        default: glcm_dense_body<WIN, NT, 3, WIDE, FOLD>(sm, q, W, L, out_cols, i_begin, i_end, j0, t, NTW, props, plane_stride, moments); break;
     }
 }
 
@@ -399,7 +418,8 @@ static size_t dense_smem_bytes(int win, int nt, int ntw, int ncell) {
 }
 
 template <int WIN, int NT, bool WIDE, bool FOLD = false>
-static int launch_dense(const uint8_t* d_q, int W, int levels, int ntw, int out_rows, int out_cols, float* d_props, int64_t plane_stride, cudaStream_t s) {
+static int launch_dense(const uint8_t* d_q, int W, int levels, int ntw, int out_rows, int out_cols, float* d_props, int64_t plane_stride, long long* d_moments,
+                        cudaStream_t s) {
     const int ncell = FOLD ? 36 : levels * (levels + 1) / 2;
     const size_t smem = dense_smem_bytes(WIN, NT, ntw, ncell);
     auto kern = glcm_dense_kernel<WIN, NT, WIDE, FOLD>;
@@ -429,13 +449,14 @@ static int launch_dense(const uint8_t* d_q, int W, int levels, int ntw, int out_
     }
     const int rows_per_cta = ceil_div(out_rows, best_gy);
     const int gy = ceil_div(out_rows, rows_per_cta);
-    kern<<<dim3(gx, gy), NT * 4, smem, s>>>(d_q, W, levels, out_rows, out_cols, rows_per_cta, ntw, d_props, plane_stride);
+    kern<<<dim3(gx, gy), NT * 4, smem, s>>>(d_q, W, levels, out_rows, out_cols, rows_per_cta, ntw, d_props, plane_stride, d_moments);
     return rsx_check_launch("glcm_dense");
 }
 
 // pick the widest CTA whose private counters fit in shared memory (and whose counter offsets fit the 16-bit code field)
 template <int WIN, bool WIDE>
-static int dispatch_dense(const uint8_t* d_q, int W, int levels, int out_rows, int out_cols, float* d_props, int64_t plane_stride, cudaStream_t s) {
+static int dispatch_dense(const uint8_t* d_q, int W, int levels, int out_rows, int out_cols, float* d_props, int64_t plane_stride, long long* d_moments,
+                          cudaStream_t s) {
     const int ncell = levels * (levels + 1) / 2;
     const size_t limit = (size_t)226 * 1024;
     auto windows = [&](int nt) {  // windows per CTA for this width (0 = does not fit)
@@ -444,23 +465,19 @@ static int dispatch_dense(const uint8_t* d_q, int W, int levels, int out_rows, i
         return ntw;
     };
     // a narrower CTA wastes fewer columns per window but has fewer warps; prefer the widest that keeps >= 3/4 of its windows
-    static int forced = -1;
-    if (forced < 0) {
-        const char* e = getenv("RSX_GLCM_NT");
-        forced = e ? atoi(e) : 0;
-    }
+    const int forced = rsx_option("glcm_nt", 0);
     const int nts[4] = {256, 128, 96, 64};
     for (int k = 0; k < 4; ++k) {
         const int nt = nts[k], ntw = windows(nt);
         if (forced ? (nt == forced && ntw >= 8) : (ntw * 4 >= (nt - (WIN - 1)) * 3)) {
-            if (nt == 256) return launch_dense<WIN, 256, WIDE>(d_q, W, levels, ntw, out_rows, out_cols, d_props, plane_stride, s);
-            if (nt == 128) return launch_dense<WIN, 128, WIDE>(d_q, W, levels, ntw, out_rows, out_cols, d_props, plane_stride, s);
-            if (nt == 96) return launch_dense<WIN, 96, WIDE>(d_q, W, levels, ntw, out_rows, out_cols, d_props, plane_stride, s);
-            return launch_dense<WIN, 64, WIDE>(d_q, W, levels, ntw, out_rows, out_cols, d_props, plane_stride, s);
+            if (nt == 256) return launch_dense<WIN, 256, WIDE>(d_q, W, levels, ntw, out_rows, out_cols, d_props, plane_stride, d_moments, s);
+            if (nt == 128) return launch_dense<WIN, 128, WIDE>(d_q, W, levels, ntw, out_rows, out_cols, d_props, plane_stride, d_moments, s);
+            if (nt == 96) return launch_dense<WIN, 96, WIDE>(d_q, W, levels, ntw, out_rows, out_cols, d_props, plane_stride, d_moments, s);
+            return launch_dense<WIN, 64, WIDE>(d_q, W, levels, ntw, out_rows, out_cols, d_props, plane_stride, d_moments, s);
         }
     }
     const int ntw = windows(32);
-    if (ntw >= 8 && (!forced || forced == 32)) return launch_dense<WIN, 32, WIDE>(d_q, W, levels, ntw, out_rows, out_cols, d_props, plane_stride, s);
+    if (ntw >= 8 && (!forced || forced == 32)) return launch_dense<WIN, 32, WIDE>(d_q, W, levels, ntw, out_rows, out_cols, d_props, plane_stride, d_moments, s);
     return -1;
 }
 
@@ -500,7 +517,8 @@ __global__ void __launch_bounds__(256) glcm_span_flag_kernel(const uint8_t* __re
 // value equals what the unfolded dense kernel writes): per angle E = sum over the pairs of w * U[cell of the pair] from a
 // warp-private histogram of all L(L+1)/2 unordered cells, energy = sqrtf(E) * (0.5 / n); mean of the four angles.
 __global__ void __launch_bounds__(256) glcm_energy_patch_kernel(const uint8_t* __restrict__ q, int W, int L, int win, int out_rows, int out_cols,
-                                                                const uint8_t* __restrict__ flags, float* __restrict__ energy) {
+                                                                const uint8_t* __restrict__ flags, float* __restrict__ energy,
+                                                                long long* __restrict__ moments) {
     __shared__ unsigned hist_all[8][528];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned* hist = hist_all[warp];
@@ -547,10 +565,11 @@ __global__ void __launch_bounds__(256) glcm_energy_patch_kernel(const uint8_t* _
                 }
                 __syncwarp();
                 e = __reduce_add_sync(0xffffffffu, e);
+                if (moments && lane == 0) moments[(o * 4 + ang) * 8 + 5] = e;
                 const float inv_n = 1.f / (float)n;
-                part[ang] = sqrtf((float)e) * (0.5f * inv_n);
+                part[ang] = __fmul_rn(sqrtf((float)e), 0.5f * inv_n);  // rounded product, as the dense kernel stores it (no FMA with the sum)
             }
-            if (lane == 0) energy[o] = ((part[0] + part[1]) + (part[2] + part[3])) * 0.25f;
+            if (lane == 0) energy[o] = __fmul_rn(__fadd_rn(__fadd_rn(part[0], part[1]), __fadd_rn(part[2], part[3])), 0.25f);
         }
     }
 }
@@ -560,7 +579,8 @@ static size_t g_span_flags_cap = 0;
 
 // folded dense path (levels <= 32, RSX_GLCM_FOLD=1): flags, folded kernel, energy patch.  Returns -1 when not applicable.
 template <int WIN>
-static int dispatch_dense_folded(const uint8_t* d_q, int W, int levels, int out_rows, int out_cols, float* d_props, int64_t plane_stride, cudaStream_t s) {
+static int dispatch_dense_folded(const uint8_t* d_q, int W, int levels, int out_rows, int out_cols, float* d_props, int64_t plane_stride, long long* d_moments,
+                                 cudaStream_t s) {
     const size_t n_win = (size_t)out_rows * out_cols;
     if (n_win > g_span_flags_cap) {
         if (g_span_flags) cudaFree(g_span_flags);
@@ -573,16 +593,22 @@ static int dispatch_dense_folded(const uint8_t* d_q, int W, int levels, int out_
     }
     glcm_span_flag_kernel<<<dim3(ceil_div(out_cols, SPAN_TC), ceil_div(out_rows, SPAN_TR)), 256, 0, s>>>(d_q, W, levels, WIN, out_rows, out_cols, g_span_flags);
     if (int rc = rsx_check_launch("glcm_span_flags")) return rc;
-    constexpr int NT = 128;
-    const int ntw = NT - (WIN - 1);
-    if (int rc = launch_dense<WIN, NT, false, true>(d_q, W, levels, ntw, out_rows, out_cols, d_props, plane_stride, s)) return rc;
+    const int fold_nt = rsx_option("glcm_fold_nt", 128);
+    int rc_d;
+    if (fold_nt == 256)
+        rc_d = launch_dense<WIN, 256, false, true>(d_q, W, levels, 256 - (WIN - 1), out_rows, out_cols, d_props, plane_stride, d_moments, s);
+    else if (fold_nt == 64)
+        rc_d = launch_dense<WIN, 64, false, true>(d_q, W, levels, 64 - (WIN - 1), out_rows, out_cols, d_props, plane_stride, d_moments, s);
+    else
+        rc_d = launch_dense<WIN, 128, false, true>(d_q, W, levels, 128 - (WIN - 1), out_rows, out_cols, d_props, plane_stride, d_moments, s);
+    if (rc_d) return rc_d;
     const int grid = (int)min((int64_t)ceil_div((int64_t)n_win, (int64_t)256), (int64_t)rsx_num_sms() * 8);
-    glcm_energy_patch_kernel<<<grid, 256, 0, s>>>(d_q, W, levels, WIN, out_rows, out_cols, g_span_flags, d_props + 3 * plane_stride);
+    glcm_energy_patch_kernel<<<grid, 256, 0, s>>>(d_q, W, levels, WIN, out_rows, out_cols, g_span_flags, d_props + 3 * plane_stride, d_moments);
     return rsx_check_launch("glcm_energy_patch");
 }
 
-extern "C" int rsx_glcm_props(const uint8_t* d_q, int rows_avail, int W, int levels, int window, int step, int out_rows, int out_cols,
-                              float* d_props, int64_t plane_stride, rsx_stream_t stream) {
+static int glcm_run(const uint8_t* d_q, int rows_avail, int W, int levels, int window, int step, int out_rows, int out_cols, float* d_props,
+                    int64_t plane_stride, long long* d_moments, rsx_stream_t stream) {
     RSX_REQUIRE(d_q && d_props, "rsx_glcm_props: null argument");
     RSX_REQUIRE(levels >= 2 && levels <= 128, "rsx_glcm_props: levels must be in [2,128]");
     RSX_REQUIRE(window >= 2 && window <= 127 && step >= 1, "rsx_glcm_props: window must be in [2,127], step >= 1");
@@ -595,26 +621,22 @@ extern "C" int rsx_glcm_props(const uint8_t* d_q, int rows_avail, int W, int lev
     // dense fast path: packed integer moments hold for levels <= 64 and window <= 11; uint8 counters hold w(w-1) <= 110
     if (step == 1 && levels <= 64) {
         int rc = -1;
-        static int fold_env = -1;
-        if (fold_env < 0) {
-            const char* e = getenv("RSX_GLCM_FOLD");
-            fold_env = e ? atoi(e) : 0;
-        }
+        const int fold_env = rsx_option("glcm_fold", 0);
         if (fold_env && levels <= 32) {
             switch (window) {
-                case 3: rc = dispatch_dense_folded<3>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, s); break;
-                case 5: rc = dispatch_dense_folded<5>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, s); break;
-                case 7: rc = dispatch_dense_folded<7>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, s); break;
-                case 9: rc = dispatch_dense_folded<9>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, s); break;
-                case 11: rc = dispatch_dense_folded<11>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, s); break;
+                case 3: rc = dispatch_dense_folded<3>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, d_moments, s); break;
+                case 5: rc = dispatch_dense_folded<5>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, d_moments, s); break;
+                case 7: rc = dispatch_dense_folded<7>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, d_moments, s); break;
+                case 9: rc = dispatch_dense_folded<9>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, d_moments, s); break;
+                case 11: rc = dispatch_dense_folded<11>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, d_moments, s); break;
                 default: break;
             }
             if (rc >= 0) return rc;
         }
 #define DENSE(WW)                                                                                                    \
     case WW:                                                                                                         \
-        rc = levels <= 32 ? dispatch_dense<WW, false>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, s)  \
-                          : dispatch_dense<WW, true>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, s);  \
+        rc = levels <= 32 ? dispatch_dense<WW, false>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, d_moments, s)  \
+                          : dispatch_dense<WW, true>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, d_moments, s);  \
         break;
         switch (window) {
             DENSE(3) DENSE(5) DENSE(7) DENSE(9) DENSE(11)
@@ -635,8 +657,19 @@ extern "C" int rsx_glcm_props(const uint8_t* d_q, int rows_avail, int W, int lev
     }
     const int64_t n_win = (int64_t)out_rows * out_cols;
     const int grid = (int)min(ceil_div(n_win, (int64_t)4), (int64_t)rsx_num_sms() * 8);
-    glcm_props_warp_kernel<<<grid, 128, smem, s>>>(d_q, W, levels, window, step, out_rows, out_cols, d_props, plane_stride);
+    glcm_props_warp_kernel<<<grid, 128, smem, s>>>(d_q, W, levels, window, step, out_rows, out_cols, d_props, plane_stride, d_moments);
     return rsx_check_launch("glcm_props_warp");
+}
+
+extern "C" int rsx_glcm_props(const uint8_t* d_q, int rows_avail, int W, int levels, int window, int step, int out_rows, int out_cols,
+                              float* d_props, int64_t plane_stride, rsx_stream_t stream) {
+    return glcm_run(d_q, rows_avail, W, levels, window, step, out_rows, out_cols, d_props, plane_stride, nullptr, stream);
+}
+
+extern "C" int rsx_glcm_moments(const uint8_t* d_q, int rows_avail, int W, int levels, int window, int step, int out_rows, int out_cols,
+                                float* d_props, int64_t plane_stride, int64_t* d_moments, rsx_stream_t stream) {
+    RSX_REQUIRE(d_moments, "rsx_glcm_moments: null argument");
+    return glcm_run(d_q, rows_avail, W, levels, window, step, out_rows, out_cols, d_props, plane_stride, reinterpret_cast<long long*>(d_moments), stream);
 }
 
 // ----------------------------------------------------------------------------- count dump (validation entry point)

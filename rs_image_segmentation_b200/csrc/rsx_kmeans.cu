@@ -92,9 +92,9 @@ __global__ void __launch_bounds__(KM_CTRL_THREADS) km_setup_kernel(KmState* gst)
 }
 
 static const km_assign_fn g_part_assign[KM_NUM_PARTS] = {rsx_km_part0_assign, rsx_km_part1_assign, rsx_km_part2_assign, rsx_km_part3_assign,
-                                                          rsx_km_part4_assign};
+                                                          rsx_km_part4_assign, rsx_km_part5_assign};
 static const km_publish_fn g_part_publish[KM_NUM_PARTS] = {rsx_km_part0_publish, rsx_km_part1_publish, rsx_km_part2_publish, rsx_km_part3_publish,
-                                                            rsx_km_part4_publish};
+                                                            rsx_km_part4_publish, rsx_km_part5_publish};
 
 // mirror the state into the __constant__ block of the translation unit that owns the kernels for this D
 static int km_publish(void* d_state, int D, cudaStream_t s) {
@@ -167,18 +167,8 @@ extern "C" int rsx_kmeans_assign(const float* d_stack, int64_t plane_stride, int
     a.stack = d_stack, a.plane_stride = plane_stride, a.n_px = n_px, a.row_len = row_len;
     a.acc = reinterpret_cast<long long*>(d_acc), a.lab8 = d_labels_u8, a.prev8 = d_labels_prev_u8, a.lab32 = d_labels_i32;
     a.inertia = d_inertia, a.mode = update, a.D = D, a.K = K;
-    static int pf_env = -2;
-    if (pf_env == -2) {
-        const char* e = getenv("RSX_KM_PF");
-        pf_env = e ? atoi(e) : -1;
-    }
-    a.pf_rows = pf_env >= 0 ? pf_env : 2;
-    static int st_env = -2;
-    if (st_env == -2) {
-        const char* e = getenv("RSX_KM_STAGES");
-        st_env = e ? atoi(e) : 0;
-    }
-    a.n_stages = st_env;
+    a.pf_rows = max(0, rsx_option("km_pf", 2));
+    a.n_stages = min(4, max(0, rsx_option("km_stages", 0)));  // the stream kernel's ticket area holds 4 stages
     return g_part_assign[km_part_of(D)](a, (cudaStream_t)stream);
 }
 

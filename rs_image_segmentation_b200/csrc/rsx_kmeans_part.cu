@@ -18,7 +18,7 @@
 #include "rsx_kmeans_state.cuh"
 
 #ifndef RSX_KM_PART
-#error "compile with -DRSX_KM_PART=<0..4>"
+#error "compile with -DRSX_KM_PART=<0..5>"
 #endif
 
 __constant__ KmState g_km;  // refreshed (device-to-device) after every setup/update, per translation unit
@@ -497,7 +497,7 @@ __device__ __forceinline__ void km_move_in_all(const float* __restrict__ st, int
 }
 
 template <int D, int MODE, bool INERTIA, int KU, bool WARPX>
-__global__ void __launch_bounds__(KM_THREADS, 4) km_stream_kernel(const float* __restrict__ stack, int64_t plane_stride, int64_t n_px,
+__global__ void __launch_bounds__(KM_THREADS, km_ctas_per_sm(D)) km_stream_kernel(const float* __restrict__ stack, int64_t plane_stride, int64_t n_px,
                                                                   long long* __restrict__ gacc, uint8_t* __restrict__ lab8,
                                                                   const uint8_t* __restrict__ prev8, int32_t* __restrict__ lab32,
                                                                   double* __restrict__ inertia_out, int n_stages, int c64_offset) {
@@ -746,8 +746,11 @@ template <int D>
 static int km_launch_full(const KmLaunch& a, cudaStream_t s) {
     const int smem = KmSmem<D>::CACHE_BYTES;
     auto kern = km_full_kernel<D>;
-    static int per_sm = 0;
-    if (per_sm <= 0) {
+    static int per_sm = 0, cfg_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (per_sm <= 0 || cfg_dev != dev) {
+        cfg_dev = dev;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max(smem, 48 * 1024));
         if (e != cudaSuccess) {
             rsx_set_error("km_full: cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e));
@@ -773,8 +776,10 @@ static int km_launch_stream(const KmLaunch& a, cudaStream_t s) {
     auto c64_off = [&](int stages) { return stages * D * KM_BLOCK_PX * 4 + acc_bytes + 2 * stages * 8 + 16 + w_bytes; };
     auto smem_for = [&](int stages) { return c64_off(stages) + c64_bytes; };
     // stages: enough blocks in flight per SM to cover HBM latency at full bandwidth (~64 KB/SM), within shared memory
-    static int cfg_K = -1, cfg_stages = 0, cfg_per_sm = 0;
-    if (cfg_K != a.K) {
+    static int cfg_K = -1, cfg_stages = 0, cfg_per_sm = 0, cfg_dev = -1, cfg_req = -1;  // per kernel instantiation
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cfg_K != a.K || cfg_dev != dev || cfg_req != a.n_stages) {
         int best_stages = 2, best_per_sm = 0;
         for (int stages = a.n_stages > 0 ? a.n_stages : 2; stages <= (a.n_stages > 0 ? a.n_stages : 3); ++stages) {
             const int smem = smem_for(stages);
@@ -791,7 +796,7 @@ static int km_launch_stream(const KmLaunch& a, cudaStream_t s) {
             return RSX_ERR_CUDA;
         }
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max(smem_for(best_stages), 48 * 1024));
-        cfg_K = a.K, cfg_stages = best_stages, cfg_per_sm = best_per_sm;
+        cfg_K = a.K, cfg_stages = best_stages, cfg_per_sm = best_per_sm, cfg_dev = dev, cfg_req = a.n_stages;
         if (getenv("RSX_DEBUG")) fprintf(stderr, "[rsx] km_stream D=%d K=%d mode=%d: %d stages, %d CTAs/SM, %d B smem\n", D, a.K, MODE, best_stages, best_per_sm, smem_for(best_stages));
     }
     const int64_t n4 = a.n_px & ~(int64_t)3;
@@ -805,7 +810,7 @@ static int km_launch_stream(const KmLaunch& a, cudaStream_t s) {
 template <int D, int KU, bool WARPX>
 static int km_launch2(const KmLaunch& a, cudaStream_t s) {
     if (a.mode == KM_FULL) {
-        if (KU == 8) return km_launch_full<D>(a, s);
+        if constexpr (KU == 8 && D <= 20) return km_launch_full<D>(a, s);
         return km_launch_stream<D, KM_FULL, false, KU, WARPX>(a, s);
     }
     if (a.mode == KM_DELTA) return km_launch_stream<D, KM_DELTA, false, KU, WARPX>(a, s);

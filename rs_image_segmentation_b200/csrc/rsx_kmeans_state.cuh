@@ -34,10 +34,14 @@ struct __align__(16) KmState {
 constexpr int KM_ASSIGN = 0, KM_FULL = 1, KM_DELTA = 2;  // the `update` argument of rsx_kmeans_assign
 
 // one translation unit per range of D (compile time); each owns a __constant__ mirror of the state
-#define KM_NUM_PARTS 5
-__host__ __device__ constexpr int km_part_of(int D) { return D <= 8 ? 0 : D <= 12 ? 1 : D <= 15 ? 2 : D <= 18 ? 3 : 4; }
-__host__ __device__ constexpr int km_part_lo(int part) { return part == 0 ? 1 : part == 1 ? 9 : part == 2 ? 13 : part == 3 ? 16 : 19; }
-__host__ __device__ constexpr int km_part_hi(int part) { return part == 0 ? 8 : part == 1 ? 12 : part == 2 ? 15 : part == 3 ? 18 : 20; }
+#define KM_NUM_PARTS 6
+#define KM_MAX_COMPILED_D 24  // the reference's own call site stacks 3 + 19 = 22 planes (scripts/3_classification.py:381-391)
+__host__ __device__ constexpr int km_part_of(int D) { return D <= 8 ? 0 : D <= 12 ? 1 : D <= 15 ? 2 : D <= 18 ? 3 : D <= 20 ? 4 : 5; }
+__host__ __device__ constexpr int km_part_lo(int part) { return part == 0 ? 1 : part == 1 ? 9 : part == 2 ? 13 : part == 3 ? 16 : part == 4 ? 19 : 21; }
+__host__ __device__ constexpr int km_part_hi(int part) { return part == 0 ? 8 : part == 1 ? 12 : part == 2 ? 15 : part == 3 ? 18 : part == 4 ? 20 : KM_MAX_COMPILED_D; }
+// D > 20: a thread's four pixels x D features no longer fit 128 registers - two CTAs per SM instead of four, and the first
+// (full) pass of K <= 8 goes through the streaming kernel (per-thread accumulators would not fit in shared memory)
+__host__ __device__ constexpr int km_ctas_per_sm(int D) { return D > 20 ? 2 : 4; }
 
 struct KmLaunch {
     const float* stack;
@@ -57,4 +61,4 @@ typedef int (*km_publish_fn)(const void* d_state, cudaStream_t);
 #define KM_DECLARE_PART(N)                                      \
     int rsx_km_part##N##_assign(const KmLaunch&, cudaStream_t); \
     int rsx_km_part##N##_publish(const void* d_state, cudaStream_t);
-KM_DECLARE_PART(0) KM_DECLARE_PART(1) KM_DECLARE_PART(2) KM_DECLARE_PART(3) KM_DECLARE_PART(4)
+KM_DECLARE_PART(0) KM_DECLARE_PART(1) KM_DECLARE_PART(2) KM_DECLARE_PART(3) KM_DECLARE_PART(4) KM_DECLARE_PART(5)

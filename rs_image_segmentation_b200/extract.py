@@ -105,8 +105,8 @@ def unsupervised_kmeans_classification(features_dict, n_clusters=5, feature_keys
     H, W = shape
     n = H * W
     D = len(planes_host)
-    if D > 20:
-        raise _lib.RsxError(f"{D} feature planes; the KMeans kernels are compiled for up to 20")
+    if D > 24:
+        raise _lib.RsxError(f"{D} feature planes; the KMeans kernels are compiled for up to 24")
     if n_clusters > 64:
         raise _lib.RsxError("n_clusters > 64 is not supported")
     stride = (n + 31) // 32 * 32

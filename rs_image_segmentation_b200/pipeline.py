@@ -61,6 +61,7 @@ class FeatureResult:
     minmax: MinMaxTracker
     quant: Optional[torch.Tensor] = None
     timings: dict = field(default_factory=dict)
+    nan_replaced: bool = False           # kmeans_on_features has replaced NaN by 0 in the MSAVI plane (extract.py:548-556)
 
     def plane(self, name: str) -> torch.Tensor:
         return self.planes[self.names.index(name), :self.n_px].view(self.H, self.W)
@@ -596,6 +597,14 @@ def kmeans_on_features(fr: FeatureResult, D: int, K: int, n_iter: int, seed: int
     comm = comm or Comm()
     H_total = H_total if H_total is not None else fr.H
     n_global = H_total * fr.W
+    # NaN -> 0 before MinMaxScaler / KMeans (extract.py:548-556).  Of the planes this pipeline makes only MSAVI can be NaN for a
+    # finite raster (float32 radicand rounding below zero, indices.py:109-112); the plane is modified in place and 0 joins its
+    # tracked range when a NaN was replaced.
+    if fr.n_px and "msavi" in fr.names[:D] and not getattr(fr, "nan_replaced", False):
+        i = fr.names.index("msavi")
+        with timer("nan_to_zero"):
+            _lib.call("rsx_nan_to_zero_minmax_f32", C.c_void_p(fr.planes[i].data_ptr()), fr.n_px, fr.minmax.slot(i), stream_ptr())
+        fr.nan_replaced = True
     idx = draw_init_indices(n_global, K, seed)
     km = DeviceKMeans(fr.planes, fr.n_px, D, K, None, None, n_global, fr.W, comm, timer, delta)   # buffers first, ...
     if km.delta:

@@ -259,3 +259,67 @@ def test_fetch_kernel_store_matches_copy(rsx, n, dtype):
     torch.cuda.current_stream().synchronize()
     assert np.array_equal(h.numpy(), base.cpu().numpy())
     assert fetch(base[:0]).size == 0
+
+
+# ============================================================================================ round-2 additions
+def _moments(rsx, q, L, win, step):
+    """(oh, ow, 4, 8) int64 pair moments written by the PRODUCTION kernels next to the property planes (rsx_glcm_moments)."""
+    import torch
+    from rs_image_segmentation_b200.device import ptr, stream_ptr
+    H, W = q.shape
+    oh, ow = (H - win) // step + 1, (W - win) // step + 1
+    stride = (oh * ow + 31) // 32 * 32
+    props = torch.zeros((5, stride), dtype=torch.float32, device="cuda")
+    mom = torch.full((oh * ow, 4, 8), -1, dtype=torch.int64, device="cuda")
+    rsx.call("rsx_glcm_moments", ptr(_dev(q)), H, W, L, win, step, oh, ow, ptr(props), stride, ptr(mom), stream_ptr())
+    return mom.cpu().numpy().reshape(oh, ow, 4, 8), props[:, : oh * ow].reshape(5, oh, ow).cpu().numpy()
+
+
+@pytest.mark.parametrize("fold", [0, 1])
+@pytest.mark.parametrize("L", [16, 32, 64])
+@pytest.mark.parametrize("win", [5, 7, 11])
+def test_glcm_production_kernel_integer_stage_is_exact(rsx, L, win, fold):
+    """the integer stage of the DENSE production kernel (glcm_dense_kernel - packed pair moments, sliding
+    private counters, folded or not) against the same integers derived from the oracle's graycomatrix counts, bit for bit,
+    for every (levels, window) of BASELINE.json config C; the float32 properties written by the same launch stay within 1e-5."""
+    from oracle import glcm as og
+    from rs_image_segmentation_b200 import _lib
+    q = _texture_image(97, 141, L, 7 * L + win)
+    q[:30, :40] = 5
+    q[60:, 100:] = np.random.default_rng(L + win).integers(0, L, size=(37, 41))        # wide level spans (flagged windows when folded)
+    _lib.set_option("glcm_fold", fold)
+    try:
+        got, props = _moments(rsx, q, L, win, 1)
+    finally:
+        _lib.set_option("glcm_fold", 0)
+    ref = og.pair_moments(q, L, win, 1)
+    for f, name in enumerate(og.MOMENT_FIELDS):
+        assert np.array_equal(got[..., f], ref[..., f]), name
+    np.testing.assert_allclose(props, og.props_map_c(q, L, win, 1), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("L,win,step", [(32, 21, 21), (32, 7, 7), (128, 9, 4), (32, 5, 3)])
+def test_glcm_general_kernel_integer_stage_is_exact(rsx, L, win, step):
+    from oracle import glcm as og
+    q = _texture_image(97, 141, L, L + win + step)
+    got, props = _moments(rsx, q, L, win, step)
+    ref = og.pair_moments(q, L, win, step)
+    for f, name in enumerate(og.MOMENT_FIELDS):
+        assert np.array_equal(got[..., f], ref[..., f]), name
+
+
+def test_glcm_skimage_property_known_answers_on_the_gpu(rsx):
+    """scikit-image's published property values for its docstring image (test_texture.py), reproduced from the integers the GPU
+    kernel writes for the 4x4 window, angle 0."""
+    from oracle import glcm as og
+    SKIMAGE_PROP_KATS = og.SKIMAGE_PROP_KATS
+    got, props = _moments(rsx, DOC_IMAGE, 4, 4, 4)
+    pr = og.props_from_moments(got[0, 0, 0])
+    assert abs(pr["contrast"] - 14 / 24) < 1e-12 and abs(pr["dissimilarity"] - 10 / 24) < 1e-12
+    np.testing.assert_almost_equal(pr["homogeneity"], SKIMAGE_PROP_KATS["homogeneity"], decimal=7)
+    np.testing.assert_almost_equal(pr["energy"], SKIMAGE_PROP_KATS["energy"], decimal=7)
+    np.testing.assert_almost_equal(pr["correlation"], SKIMAGE_PROP_KATS["correlation"], decimal=7)
+    # and the float32 plane values = mean over the four angles of the same quantities
+    for k, name in enumerate(og.PROPS):
+        want = np.mean([og.props_from_moments(got[0, 0, a])[name] for a in range(4)])
+        assert abs(props[k, 0, 0] - want) <= 1e-6 * max(1.0, abs(want)), name

@@ -400,3 +400,107 @@ def test_full_size_scene_properties(P):
     gap = np.partition(d2, 1, axis=1)
     clear = (gap[:, 1] - gap[:, 0]) > 1e-9                       # leave exact near-ties to the kernel's own float64 rule
     assert np.array_equal(best[clear], out[True][3][clear])
+
+
+# ============================================================================================ round-2 additions
+def _nan_raster(H=150, W=203, seed=0):
+    """uint16 x 13 raster whose red band normalises to exactly 0 for most pixels and whose NIR band normalises to a fine grid of
+    values around 0.5: there the float32 radicand (2n+1)^2 - 8(n-r) of MSAVI (indices.py:109-112) rounds below zero for ~0.5 %
+    of the values and np.sqrt returns NaN (the case the reference handles with its NaN -> 0 before KMeans, extract.py:548-556)."""
+    from rs_image_segmentation_b200.synth import synth_raster_numpy
+    rng = np.random.default_rng(seed)
+    bip = synth_raster_numpy(H, W, 13, np.uint16, seed, cell=16)
+    u = rng.random((H, W))
+    bip[:, :, 3] = np.where(u < 0.9, 100, rng.integers(100, 3000, (H, W)))                       # red: P2 == 100 -> 0 after the clip
+    v = rng.random((H, W))
+    bip[:, :, 7] = np.where(v < 0.04, 0, np.where(v > 0.96, 60000, rng.integers(29000, 31000, (H, W))))   # nir: n in 0.483 .. 0.517
+    return bip
+
+
+def test_msavi_nan_is_replaced_before_kmeans(P):
+    """a NaN sample must not reach the fixed-point sums.  The feature plane keeps the reference's NaN; the
+    KMeans entry replaces it by 0 (and 0 joins the MinMax range), and labels / centroids equal the oracle run on nan_to_num."""
+    import torch
+    from oracle import features as of
+    bip = _nan_raster()
+    cfg = P.FeatureConfig(band_map=(1, 2, 3, 7, 11), n_components=6, glcm=False)
+    fr = P.extract_features(torch.from_numpy(bip.view(np.int16)).cuda(), cfg)
+    with np.errstate(all="ignore"):
+        ref = _oracle_features(bip, cfg)
+    n_nan = int(np.isnan(ref["msavi"]).sum())
+    assert n_nan > 10, "the test raster must produce NaN in the oracle's MSAVI"
+    for k in of.INDEX_ORDER:
+        assert np.array_equal(fr.plane(k).cpu().numpy(), ref[k], equal_nan=True), k
+    D, K, T = 13, 6, 5
+    res, km, c0 = P.kmeans_on_features(fr, D, K, T, seed=9)
+    ms = fr.plane("msavi").cpu().numpy()
+    assert not np.isnan(ms).any() and int((ms == 0).sum()) >= n_nan
+    assert np.array_equal(ms, np.nan_to_num(ref["msavi"], nan=0.0))
+    stack = fr.planes[:D, :fr.n_px].t().contiguous().cpu().numpy()
+    assert km.fmin[2] == stack[:, 2].min() and km.fmax[2] == stack[:, 2].max() and km.fmin[2] <= 0.0 <= km.fmax[2]
+    (lab, cent, inertia, n_run), Xs = _kmeans_oracle(stack, c0, T, km.fmin, km.fmax)
+    assert np.array_equal(res.labels.cpu().numpy(), lab)
+    np.testing.assert_allclose(res.centroids, cent, rtol=0, atol=1e-9)
+    assert np.isfinite(res.centroids).all() and abs(res.inertia - inertia) <= 1e-5 * inertia
+
+
+def test_whole_path_2048_against_oracle(P):
+    """The whole path at 2048 x 2048 (4.2 Mpx: multi-CTA GLCM bands, several histogram flushes, 8k KMeans blocks) against the
+    oracle: indices + quantised band bit exact, GLCM properties 1e-5, PCA 1e-5 (float64 PCA of the same data), labels of the
+    fixed-iteration protocol bit exact vs sklearn on the float64 promotion of the GPU's stack, inertia 1e-5."""
+    import torch
+    from rs_image_segmentation_b200.synth import synth_raster_numpy
+    H = W = 2048
+    bip = synth_raster_numpy(H, W, 7, np.uint8, 2048)
+    cfg = P.FeatureConfig(glcm_window=7, glcm_step=1, glcm_levels=32)
+    fr = P.extract_features(torch.from_numpy(bip).cuda(), cfg)
+    _check_features(fr, _oracle_features(bip, cfg), cfg)
+    D, K, T = 13, 8, 6
+    res, km, c0 = P.kmeans_on_features(fr, D, K, T, seed=2048)
+    stack = fr.planes[:D, :fr.n_px].t().contiguous().cpu().numpy()
+    (lab, cent, inertia, n_run), _ = _kmeans_oracle(stack, c0, T, km.fmin, km.fmax)
+    got = res.labels.cpu().numpy()
+    assert np.array_equal(got, lab), f"{(got != lab).sum()} labels differ"
+    np.testing.assert_allclose(res.centroids, cent, rtol=0, atol=1e-9)
+    assert abs(res.inertia - inertia) <= 1e-5 * inertia
+
+
+@pytest.mark.parametrize("K", [8, 32])
+def test_kmeans_fixed_point_budget_of_the_40k_mosaic(P, K):
+    """The int64 fixed-point shift depends on the GLOBAL pixel count (rsx_kmeans.cu: 62 - ceil(log2 n) bits per sample).  With
+    n_global forced to 1.6e9 (config E: 31 bits) the labels on a small stack must still equal sklearn's float64 run."""
+    import torch
+    from rs_image_segmentation_b200.synth import synth_raster_numpy
+    bip = synth_raster_numpy(160, 300, 7, np.uint8, 77 + K, cell=16)
+    fr = P.extract_features(torch.from_numpy(bip).cuda(), P.FeatureConfig(glcm_window=7, glcm_step=1))
+    D, T = 13, 6
+    mn, mx = fr.minmax.read()
+    km = P.DeviceKMeans(fr.planes, fr.n_px, D, K, mn[:D], mx[:D], 40000 * 40000, fr.W)
+    c0 = km.scale_rows(km.gather_rows(P.draw_init_indices(fr.n_px, K, 6), 0))
+    res = km.fit(c0, T)
+    stack = fr.planes[:D, :fr.n_px].t().contiguous().cpu().numpy()
+    (lab, cent, inertia, n_run), _ = _kmeans_oracle(stack, c0, T, km.fmin, km.fmax)
+    got = res.labels.cpu().numpy()
+    assert np.array_equal(got, lab), f"{(got != lab).sum()} labels differ"
+    np.testing.assert_allclose(res.centroids, cent, rtol=0, atol=5e-9)           # sample quantum 2^-31 of the feature range
+    assert abs(res.inertia - inertia) <= 1e-5 * inertia
+
+
+@pytest.mark.parametrize("D,K", [(22, 7), (24, 16), (21, 40)])
+def test_kmeans_depth_21_to_24(P, D, K):
+    """The reference's own KMeans call site stacks ndvi, ndwi, ndbi + the 19 hierarchical channels = 22 planes
+    (scripts/3_classification.py:381-391)."""
+    import torch
+    n_px = 9001
+    rng = np.random.default_rng(100 * D + K)
+    X = (rng.normal(size=(n_px, 4)) @ rng.normal(size=(4, D)) + 0.3 * rng.normal(size=(n_px, D))).astype(np.float32)
+    stride = (n_px + 31) // 32 * 32
+    planes = torch.zeros((D, stride), dtype=torch.float32, device="cuda")
+    planes[:, :n_px] = torch.from_numpy(np.ascontiguousarray(X.T)).cuda()
+    fmin, fmax = X.min(axis=0), X.max(axis=0)
+    km = P.DeviceKMeans(planes, n_px, D, K, fmin, fmax, n_px, 257)
+    c0 = km.scale_rows(X[P.draw_init_indices(n_px, K, 5)])
+    res = km.fit(c0, 4)
+    (lab, cent, inertia, n_run), _ = _kmeans_oracle(X, c0, 4, fmin, fmax)
+    assert np.array_equal(res.labels.cpu().numpy(), lab)
+    np.testing.assert_allclose(res.centroids, cent, rtol=0, atol=1e-9)

@@ -110,3 +110,48 @@ def test_folded_counters_are_exact_when_the_level_span_is_below_the_fold():
     win[:, 4:] = 11
     assert _asm_unordered(win, 0, 1) != _asm_unordered(win, 0, 1, fold=8)
     assert int(win.max() - win.min()) >= 8                   # ... and the span test catches it
+
+
+# Property known answers published by scikit-image's own test suite (skimage/feature/tests/test_texture.py: test_contrast,
+# test_dissimilarity, test_homogeneity, test_energy, test_correlation) for the docstring image, symmetric=True, normed=True,
+# first (distance, angle) entry = (1, 0).  scikit-image cannot be installed here; these constants are its third-party pin.
+SKIMAGE_PROP_KATS = og.SKIMAGE_PROP_KATS
+
+
+def test_skimage_property_known_answers():
+    P = og.graycomatrix(DOC_IMAGE, (1, 2), (0.0,), levels=4, symmetric=True, normed=True)
+    # exact values (the matrix of d=1, angle 0 has 24 pair instances)
+    assert abs(og.graycoprops(P, "contrast")[0, 0] - 14 / 24) < 1e-12            # 0.58333...
+    assert abs(og.graycoprops(P, "dissimilarity")[0, 0] - 10 / 24) < 1e-12       # 0.41666...
+    np.testing.assert_almost_equal(og.graycoprops(P, "homogeneity")[0, 0], SKIMAGE_PROP_KATS["homogeneity"], decimal=7)
+    np.testing.assert_almost_equal(og.graycoprops(P, "energy")[0, 0], SKIMAGE_PROP_KATS["energy"], decimal=7)
+    corr = og.graycoprops(P, "correlation")
+    np.testing.assert_almost_equal(corr[0, 0], SKIMAGE_PROP_KATS["correlation"], decimal=7)
+    np.testing.assert_almost_equal(corr[1, 0], SKIMAGE_PROP_KATS["correlation_d2"], decimal=7)
+    # scikit-image's tests round the normalised matrix to 3 decimals first for contrast and dissimilarity
+    Pr = np.round(P, 3)
+    np.testing.assert_almost_equal(og.graycoprops(Pr, "contrast")[0, 0], SKIMAGE_PROP_KATS["contrast_rounded"], decimal=3)
+    np.testing.assert_almost_equal(og.graycoprops(Pr, "dissimilarity")[0, 0], SKIMAGE_PROP_KATS["dissimilarity_rounded"], decimal=3)
+
+
+def test_pair_moment_route_reproduces_the_known_answers():
+    """The integer pair moments the dense GPU kernel keeps per angle (s1, sa, sq, sab, e, neq; rsx_glcm.cu) give the same
+    property values as the histogram route - checked here on the scikit-image known answers through the numpy statement of those
+    moments (oracle.glcm.pair_moments), which is also what the GPU integer outputs are compared with, exactly."""
+    m = og.pair_moments(DOC_IMAGE, 4, 4)[0, 0, 0]                 # window (0, 0), angle 0
+    pr = og.props_from_moments(m)
+    assert abs(pr["contrast"] - 14 / 24) < 1e-12 and abs(pr["dissimilarity"] - 10 / 24) < 1e-12
+    np.testing.assert_almost_equal(pr["homogeneity"], SKIMAGE_PROP_KATS["homogeneity"], decimal=7)
+    np.testing.assert_almost_equal(pr["energy"], SKIMAGE_PROP_KATS["energy"], decimal=7)
+    np.testing.assert_almost_equal(pr["correlation"], SKIMAGE_PROP_KATS["correlation"], decimal=7)
+    # and against the histogram route on random windows, all four angles
+    rng = np.random.default_rng(3)
+    q = rng.integers(0, 16, size=(9, 12)).astype(np.uint8)
+    mm = og.pair_moments(q, 16, 7)
+    for i in range(mm.shape[0]):
+        for j in range(mm.shape[1]):
+            P = og.graycomatrix(q[i:i + 7, j:j + 7], (1,), og.DEFAULT_ANGLES, 16, symmetric=True, normed=True)
+            for a in range(4):
+                pr = og.props_from_moments(mm[i, j, a])
+                for name in og.PROPS:
+                    assert abs(pr[name] - og.graycoprops(P, name)[0, a]) < 1e-12, (i, j, a, name)
