@@ -53,7 +53,13 @@ __device__ void km_derive(KmState* st) {
         st->tau_tight = (float)(2.0 * 1.5 * e_max * 5.9604644775390625e-08);
         const int tag_bits = K <= 8 ? 3 : K <= 16 ? 4 : K <= 32 ? 5 : 6;
         st->tag_bits = tag_bits;
-        st->tau = (float)(2.0 * 1.5 * e_max * 5.9604644775390625e-08 + 2.0 * e_max_mag * (double)(1 << tag_bits) * 1.1920928955078125e-07);
+        const double tag_term = 2.0 * e_max_mag * (double)(1 << tag_bits) * 1.1920928955078125e-07;
+        st->tau = (float)(2.0 * 1.5 * e_max * 5.9604644775390625e-08 + tag_term);
+        // Tensor-core path (rsx_kmeans_part.cu km_tc_kernel): x = xh + xl + xr, w = wh + wl + wr with 11-bit pieces (|xr| < 2^-20 |x|);
+        // the three products kept (xh wh + xh wl + xl wh) miss < 3 * 2^-20 |x||w| per feature, the bias is carried in three pieces
+        // (< 2^-30).  Accumulation in the tensor core: measured 2^-22.8 of sum|terms| for 16 terms (tools/tc_probe.cu on the B200),
+        // budgeted here as 2 * 2^-20 for the 48 terms.  Total 5 * 2^-20 of the magnitude per distance; two distances, 1.5x safety.
+        st->tau_tc = (float)(2.0 * 1.5 * 5.0 * 9.5367431640625e-07 * e_max_mag + tag_term);
         // never-chosen padding centroids: the kernels evaluate centroids in groups of 8
         for (int j = K; j < KM_MAXK && j < ((K + 7) & ~7); ++j) {
             st->bias32[j] = 1e30f;  // finite: the index tag must not turn it into a NaN
@@ -169,6 +175,10 @@ extern "C" int rsx_kmeans_assign(const float* d_stack, int64_t plane_stride, int
     a.inertia = d_inertia, a.mode = update, a.D = D, a.K = K;
     a.pf_rows = max(0, rsx_option("km_pf", 2));
     a.n_stages = min(4, max(0, rsx_option("km_stages", 0)));  // the stream kernel's ticket area holds 4 stages
+    // 0: fp32 FFMA2 path.  1: tensor-core distances (km_tc_kernel): bit-identical labels / sums, measured at parity with the fp32 path
+    // at K = 32 and slower at K = 16 on the B200 (the per-pixel argmin over K distances, not the FMAs, is what both are bound by;
+    // DESIGN.md 4.2), so it stays an option.
+    a.use_tc = rsx_option("km_tc", 0);
     return g_part_assign[km_part_of(D)](a, (cudaStream_t)stream);
 }
 

@@ -741,6 +741,480 @@ __global__ void __launch_bounds__(KM_THREADS, km_ctas_per_sm(D)) km_stream_kerne
     km_commit_counters(gacc, K, D, ties, changed, inertia, inertia_out, INERTIA);
 }
 
+// ============================================================================= kernel C: K > 8 distances on the tensor cores
+// At K = 32, D = 13 a pass is 416 FMA per pixel: above the fp32 ridge of the B200, so kernel B runs at a quarter of the HBM rate
+// there.  Here the K distances of a pixel come from tcgen05 (5th-generation tensor cores, accumulators in TMEM):
+//     dist[128 px x N] = A[128 px x 16] * W[N x 16]^T,   columns 0..D-1 = the raw features, D..D+2 = 1.0 against the bias pieces
+// in TF32 with a three-term split so that what the tensor core drops is bounded: x = xh + xl (xh = the 11 leading bits), w = wh +
+// wl likewise, dist ~ xh.wh + xh.wl + xl.wh (six M128 N K8 instructions per 128-pixel tile, fp32 accumulation in TMEM).  The result
+// carries an error of at most ~5 * 2^-20 of the distance magnitude (KmState::tau_tc, rsx_kmeans.cu); pixels whose two nearest
+// centroids are closer than that band are decided in float64 by the whole warp (km_exact_argmin_warp), exactly as in kernel B, so
+// the tensor cores never decide a label either.
+//   * staging: the same ring of bulk-copied plane segments as kernel B (blocks of 384 pixels = three 128-pixel tiles);
+//   * A operand: thread t of the CTA owns pixel t of the tile = TMEM lane t; it reads its D features from the staged block (LDS.32,
+//     conflict free), splits them and writes xh / xl to 2 x 16 TMEM columns with tcgen05.st (no shared-memory copy of A);
+//   * B operand (weights): K-major, no swizzle, in shared memory, built once per CTA from the state: element (n, k) at
+//     (k/4) * (N/8) * 128 + (n/8) * 128 + (n%8) * 16 + (k%4) * 4 bytes (8 x 16 B core matrices; LBO = k-chunk stride,
+//     SBO = 128: layout verified on the B200 by tools/tc_probe.cu);
+//   * one elected thread issues the six MMAs and tcgen05.commit onto an mbarrier; every thread then reads its pixel's N distances
+//     with tcgen05.ld and runs the tagged argmin / delta update of kernel B.  Four CTAs per SM cover each other's MMA round trip
+//     (~300 cycles).  Sums: one int64 accumulator per CTA in shared memory (64-bit shared atomics), which is what lets four CTAs
+//     fit next to the staging ring.
+constexpr int KM_TC_SUBS = 3;
+constexpr int KM_TC_BPX = 128 * KM_TC_SUBS;  // pixels per staged block
+constexpr int KM_TC_KDIM = 16;               // D features + 3 bias slots <= 16
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&a)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr), "r"(a[0]),
+                 "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(a[8]), "r"(a[9]), "r"(a[10]), "r"(a[11]), "r"(a[12]),
+                 "r"(a[13]), "r"(a[14]), "r"(a[15])
+                 : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&d)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]), "=r"(d[8]), "=r"(d[9]), "=r"(d[10]),
+                   "=r"(d[11]), "=r"(d[12]), "=r"(d[13]), "=r"(d[14]), "=r"(d[15])
+                 : "r"(taddr)
+                 : "memory");
+}
+// shared-memory matrix descriptor: K-major, no swizzle (start address, leading / stride byte offsets in 16-byte units, version 1)
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) |
+           ((uint64_t)1 << 46);
+}
+// D[tmem] (+)= A[tmem, 128 lanes x 8 columns tf32] * B[smem descriptor, N x 8]^T
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+// 64-bit add on shared memory as two native 32-bit atomics (the carry is passed on by whoever produces it; additions commute, so
+// the word pair is exact once all adds have landed).  atomicAdd on a 64-bit shared address compiles to a compare-and-swap loop.
+__device__ __forceinline__ void km_smem_add64(long long* p, long long q) {
+    unsigned* w = reinterpret_cast<unsigned*>(p);
+    const unsigned lo = (unsigned)(unsigned long long)q, hi = (unsigned)((unsigned long long)q >> 32);
+    const unsigned old = atomicAdd(w, lo);
+    const unsigned carry = (old + lo) < old ? 1u : 0u;
+    if (hi + carry) atomicAdd(w + 1, hi + carry);
+}
+
+struct KmTcSmem {  // byte offsets inside the dynamic shared memory of km_tc_kernel (host and device agree through this one function)
+    int bop, c64, w32, wacc, cent, bars, total;
+    __host__ __device__ KmTcSmem(int D, int K, int n_stages, int npad, bool sums, bool inertia) {
+        const int KP64 = (K + 31) & ~31;
+        int o = n_stages * D * KM_TC_BPX * 4;
+        bop = o, o += 2 * npad * KM_TC_KDIM * 4;               // weights for the tensor core: hi, lo
+        c64 = o, o += (D + 1) * KP64 * 8;                      // float64 centroids + norms (near ties, second stage)
+        w32 = o, o += (D + 1) * KP64 * 4;                      // fp32 weights [d][j] + bias [j] (near ties, first stage)
+        wacc = o, o += sums ? K * (D + 1) * 8 : 0;             // the CTA's int64 sums
+        cent = o, o += inertia ? ((K * D * 4 + 15) & ~15) : 0;  // fp32 centroids (inertia)
+        bars = o, o += (2 * n_stages + 4) * 8 + (n_stages + 2) * 4 + 16;
+        total = (o + 15) & ~15;
+    }
+};
+
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&d)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]), "=r"(d[8]), "=r"(d[9]), "=r"(d[10]), "=r"(d[11]),
+          "=r"(d[12]), "=r"(d[13]), "=r"(d[14]), "=r"(d[15]), "=r"(d[16]), "=r"(d[17]), "=r"(d[18]), "=r"(d[19]), "=r"(d[20]), "=r"(d[21]), "=r"(d[22]),
+          "=r"(d[23]), "=r"(d[24]), "=r"(d[25]), "=r"(d[26]), "=r"(d[27]), "=r"(d[28]), "=r"(d[29]), "=r"(d[30]), "=r"(d[31])
+        : "r"(taddr)
+        : "memory");
+}
+
+// Near tie, first stage: the K distances of ONE pixel in plain fp32 (FMA chain from the bias, no index tags) by the whole warp -
+// lane j takes centroids j and j + 32 - from the staged block (xs: feature d at xs[d * stride]).  Returns true when the two
+// nearest are farther apart than the rounding-only bound tau_tight; *bi_out = the nearest.
+template <int D>
+__device__ __forceinline__ bool km_recheck_fp32_warp(const float* __restrict__ xs, int stride, int K, const float* __restrict__ w32s, int* bi_out) {
+    const int lane = threadIdx.x & 31;
+    const int KP64 = (K + 31) & ~31;
+    float b = INFINITY, sc = INFINITY;
+    int bi = 0;
+    for (int j = lane; j < K; j += 32) {
+        float a = w32s[D * KP64 + j];
+#pragma unroll
+        for (int d = 0; d < D; ++d) a = fmaf(xs[d * stride], w32s[d * KP64 + j], a);
+        KM_ARGMIN_STEP(a, b, sc, bi, j)
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float b2 = __shfl_xor_sync(0xffffffffu, b, o), s2 = __shfl_xor_sync(0xffffffffu, sc, o);
+        const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+        sc = fminf(fminf(sc, s2), fmaxf(b, b2));  // second smallest of the union
+        if (b2 < b) b = b2, bi = i2;
+    }
+    *bi_out = bi;
+    return sc - b > g_km.tau_tight;  // false also for NaN
+}
+
+// Near tie, second stage: km_exact_argmin_warp with the pixel's features read from the staged block instead of global memory.
+template <int D>
+__device__ __forceinline__ int km_exact_argmin_warp_staged(const float* __restrict__ xs, int stride, int K, const double* __restrict__ c64s, double* dist_out) {
+    const int lane = threadIdx.x & 31;
+    const int KP64 = (K + 31) & ~31;
+    double X[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) X[d] = __dsub_rn(__dadd_rn(__dmul_rn((double)xs[d * stride], g_km.scale64[d]), g_km.min64[d]), g_km.mean64[d]);
+    double xx = 0.0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) xx = fma(X[d], X[d], xx);
+    double best = INFINITY;
+    int bi = 0x7fffffff;
+    for (int j = lane; j < K; j += 32) {
+        double dot = 0.0;
+#pragma unroll
+        for (int d = 0; d < D; ++d) dot = fma(X[d], c64s[d * KP64 + j], dot);
+        const double v = fma(-2.0, dot, c64s[D * KP64 + j]);
+        if (v < best) best = v, bi = j;  // j ascends within the lane: the first minimum stays
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double v2 = __shfl_xor_sync(0xffffffffu, best, o);
+        const int j2 = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (v2 < best || (v2 == best && j2 < bi)) best = v2, bi = j2;
+    }
+    if (bi >= K) bi = 0;  // every distance NaN (a NaN sample): the single-lane loop answers 0 as well
+    *dist_out = fmax(xx + best, 0.0);
+    return bi;
+}
+
+template <int D, int MODE, bool INERTIA, int NPAD>
+__global__ void __launch_bounds__(KM_THREADS, 4) km_tc_kernel(const float* __restrict__ stack, int64_t plane_stride, int64_t n_px,
+                                                              long long* __restrict__ gacc, uint8_t* __restrict__ lab8, const uint8_t* __restrict__ prev8,
+                                                              int32_t* __restrict__ lab32, double* __restrict__ inertia_out, int n_stages, int tmem_cols) {
+    static_assert(D + 3 <= KM_TC_KDIM, "features + bias slots must fit the 16-wide K dimension");
+    static_assert(NPAD == 16 || NPAD == 32 || NPAD == 64, "MMA N");
+    constexpr bool SUMS = MODE != KM_ASSIGN;
+    constexpr int BPX = KM_TC_BPX;
+    extern __shared__ __align__(128) unsigned char km_smem[];
+    const int K = g_km.K;
+    const int KP64 = (K + 31) & ~31;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const KmTcSmem L(D, K, n_stages, NPAD, SUMS, INERTIA);
+    float* stages = reinterpret_cast<float*>(km_smem);
+    float* bop = reinterpret_cast<float*>(km_smem + L.bop);
+    double* c64s = reinterpret_cast<double*>(km_smem + L.c64);
+    float* w32s = reinterpret_cast<float*>(km_smem + L.w32);
+    long long* wacc = reinterpret_cast<long long*>(km_smem + L.wacc);
+    float* cent_s = reinterpret_cast<float*>(km_smem + L.cent);
+    uint64_t* full = reinterpret_cast<uint64_t*>(km_smem + L.bars);
+    uint64_t* empty = full + n_stages;
+    uint64_t* mma_bar = empty + n_stages;  // [2]: the MMAs of TMEM buffer b have completed
+    uint64_t* a_ready = mma_bar + 2;       // [2]: the four warps have written their lanes of A buffer b
+    int* ticket = reinterpret_cast<int*>(a_ready + 2);  // [n_stages] refills issued per stage, then [2] MMA batches issued per buffer
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ticket + n_stages + 2);
+
+    // ---- weights: W[n][k] = w32[n][k] (k < D), bias in three 11-bit pieces at k = D, D+1, D+2; never-chosen rows carry bias 1e30
+    constexpr int CSTR = (NPAD >> 3) * 128;  // bytes between k-chunks
+    for (int i = tid; i < NPAD * KM_TC_KDIM; i += KM_THREADS) {
+        const int n = i / KM_TC_KDIM, k = i - n * KM_TC_KDIM;
+        float hi = 0.f, lo = 0.f;
+        if (k < D) {
+            const float w = n < K ? g_km.w32[n * KM_MAXD + k] : 0.f;
+            hi = tf32_trunc(w), lo = tf32_trunc(w - hi);
+        } else if (k < D + 3) {
+            const float b = n < K ? g_km.bias32[n] : 1e30f;
+            const float b0 = tf32_trunc(b), b1 = tf32_trunc(b - b0), b2 = tf32_trunc(b - b0 - b1);
+            hi = k == D ? b0 : (k == D + 1 ? b1 : b2);
+        }
+        const int off = ((k >> 2) * CSTR + (n >> 3) * 128 + (n & 7) * 16 + (k & 3) * 4) >> 2;
+        bop[off] = hi;
+        bop[NPAD * KM_TC_KDIM + off] = lo;
+    }
+    for (int i = tid; i < D * KP64; i += KM_THREADS) {
+        const int d = i / KP64, j = i - d * KP64;
+        c64s[i] = j < K ? g_km.cent64[j * KM_MAXD + d] : 0.0;
+        w32s[i] = j < K ? g_km.w32[j * KM_MAXD + d] : 0.f;
+    }
+    for (int j = tid; j < KP64; j += KM_THREADS) c64s[D * KP64 + j] = j < K ? g_km.cnorm64[j] : 0.0, w32s[D * KP64 + j] = j < K ? g_km.bias32[j] : 1e30f;
+    if (INERTIA)
+        for (int i = tid; i < K * D; i += KM_THREADS) cent_s[i] = g_km.cent32[(i / D) * KM_MAXD + i % D];
+    if (SUMS)
+        for (int i = tid; i < K * (D + 1); i += KM_THREADS) wacc[i] = 0;
+    if (tid == 0) {
+        for (int s = 0; s < n_stages; ++s) mbar_init(&full[s], 1), mbar_init(&empty[s], KM_WARPS), ticket[s] = 0;
+        for (int b = 0; b < 2; ++b) mbar_init(&mma_bar[b], 1), mbar_init(&a_ready[b], KM_WARPS), ticket[n_stages + b] = 0;
+        mbar_fence_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the weights were written by generic stores, the tensor core reads them
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = *tmem_slot;
+    const uint32_t t_lane = tbase + ((uint32_t)(warp * 32) << 16);  // a warp reaches the 32 TMEM lanes of its quarter
+    // TMEM columns, two buffers b = 0, 1: A hi at b*32, A lo at b*32 + 16, distances at 64 + b*NPAD
+    constexpr uint32_t COL_D = 4 * KM_TC_KDIM;
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NPAD >> 3) << 17) | ((128u >> 4) << 24);  // f32 acc, tf32 x tf32, K-major, N, M = 128
+    const uint32_t bop_addr = smem_u32(bop);
+    const unsigned tag_mask = (1u << g_km.tag_bits) - 1u, KEEP = ~tag_mask;
+    const float tau = g_km.tau_tc;
+
+    const int64_t n4 = n_px & ~(int64_t)3;
+    const int64_t n_blocks = (n4 + BPX - 1) / BPX;
+    auto issue = [&](int64_t blk, int s) {
+        const int64_t p0 = blk * BPX;
+        const unsigned bytes = (unsigned)min((int64_t)BPX, n4 - p0) * 4u;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&full[s], bytes * D);
+        float* dst = stages + (size_t)s * D * BPX;
+#pragma unroll 1
+        for (int d = 0; d < D; ++d) bulk_g2s(dst + d * BPX, stack + d * plane_stride + p0, bytes, &full[s]);
+    };
+    if (tid == 0)
+        for (int s = 0; s < n_stages; ++s) {
+            const int64_t blk = blockIdx.x + (int64_t)s * gridDim.x;
+            if (blk < n_blocks) issue(blk, s);
+        }
+    const float my_pow2 = SUMS ? g_km.pow2[min(lane, D - 1)] : 0.f;
+    double inertia = 0.0;
+    unsigned ties = 0, changed = 0;
+
+    // ---- epilogue of one tile whose distances sit in TMEM buffer `buf`: wst = the warp's 32 pixels of feature 0 in the staged
+    //      block (feature d at + d * BPX), p = this thread's pixel, old = its previous label
+    auto epilogue = [&](const float* __restrict__ wst, int64_t p, unsigned old, bool valid, uint32_t buf) {
+        // tagged (best, second) of the N distances: four independent chains (instruction-level parallelism: a single chain is a
+        // dependent FMNMX sequence as long as N), merged at the end
+        float cb[4] = {INFINITY, INFINITY, INFINITY, INFINITY}, cs[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
+#pragma unroll
+        for (int c0 = 0; c0 < NPAD; c0 += 32) {
+            if constexpr (NPAD >= 32) {
+                uint32_t dv[32];
+                tc_ld32(t_lane + COL_D + buf * NPAD + c0, dv);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 32; ++j) KM_ARGMIN_TAGGED(__uint_as_float(dv[j]), cb[j & 3], cs[j & 3], c0 + j)
+            } else {
+                uint32_t dv[16];
+                tc_ld16(t_lane + COL_D + buf * NPAD + c0, dv);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 16; ++j) KM_ARGMIN_TAGGED(__uint_as_float(dv[j]), cb[j & 3], cs[j & 3], c0 + j)
+            }
+        }
+        // union of two (best, second) pairs: best = min of the bests, second = min(seconds, the larger best)
+        const float b01 = fminf(cb[0], cb[1]), s01 = fminf(fminf(cs[0], cs[1]), fmaxf(cb[0], cb[1]));
+        const float b23 = fminf(cb[2], cb[3]), s23 = fminf(fminf(cs[2], cs[3]), fmaxf(cb[2], cb[3]));
+        const float b = fminf(b01, b23), sc = fminf(fminf(s01, s23), fmaxf(b01, b23));
+        int l = (int)(__float_as_uint(b) & tag_mask);
+        double dex = -1.0;
+        unsigned any = __ballot_sync(0xffffffffu, valid && !(sc - b > tau));  // near ties (also NaN)
+        while (any) {  // the whole warp on one pixel: plain fp32 first, float64 if that is still too close
+            const int src = __ffs(any) - 1;
+            any &= any - 1;
+            int bi;
+            double de = -1.0;
+            if (!km_recheck_fp32_warp<D>(wst + src, BPX, K, w32s, &bi)) {
+                bi = km_exact_argmin_warp_staged<D>(wst + src, BPX, K, c64s, &de);
+                if (lane == src) ++ties;
+            }
+            if (lane == src) l = bi, dex = de;
+        }
+        if (valid) {
+            if (INERTIA) {
+                if (dex < 0.0) {  // sum of squares of (x' - c) in fp32: all terms positive, relative error ~D * 2^-24
+                    const float* cent = cent_s + l * D;
+                    float dd = 0.f;
+#pragma unroll
+                    for (int d = 0; d < D; ++d) {
+                        const float df = fmaf(wst[d * BPX + lane], g_km.scale32[d], g_km.off32[d]) - cent[d];
+                        dd = fmaf(df, df, dd);
+                    }
+                    dex = (double)dd;
+                }
+                inertia += dex;
+            }
+            if (lab8) lab8[p] = (uint8_t)l;
+            if (lab32) lab32[p] = l;
+        }
+        const bool moved = valid && prev8 && (unsigned)l != old;
+        changed += moved ? 1u : 0u;  // sklearn's strict-convergence test (_kmeans.py:723)
+        if (MODE == KM_DELTA) {
+            // the warp moves its relabelled pixels together: lane d takes feature d (lane D the count) from the staged block
+            unsigned mb = __ballot_sync(0xffffffffu, moved);
+            while (mb) {
+                const int src = __ffs(mb) - 1;
+                mb &= mb - 1;
+                const int to = __shfl_sync(0xffffffffu, l, src), from = (int)__shfl_sync(0xffffffffu, old, src);
+                if (lane <= D) {
+                    long long q = 1;
+                    if (lane < D) q = __float2ll_rn(wst[lane * BPX + src] * my_pow2);
+                    km_smem_add64(&wacc[to * (D + 1) + lane], q);
+                    if (from < KM_MAXK) km_smem_add64(&wacc[from * (D + 1) + lane], -q);
+                }
+            }
+        } else if (MODE == KM_FULL) {
+            // every pixel moves in: lane d walks the warp's 32 pixels and adds runs of equal labels together
+            const unsigned vb = __ballot_sync(0xffffffffu, valid);
+            const float* mine = wst + min(lane, D - 1) * BPX;
+            int cur = -1;
+            long long run = 0;
+#pragma unroll 4
+            for (int src = 0; src < 32; ++src) {
+                if (!((vb >> src) & 1u)) break;  // valid pixels are a prefix of the warp
+                const int tl = __shfl_sync(0xffffffffu, l, src);
+                if (lane <= D) {
+                    const long long q = lane < D ? __float2ll_rn(mine[src] * my_pow2) : 1ll;
+                    if (tl == cur) {
+                        run += q;
+                    } else {
+                        if (cur >= 0) km_smem_add64(&wacc[cur * (D + 1) + lane], run);
+                        cur = tl, run = q;
+                    }
+                }
+            }
+            if (lane <= D && cur >= 0) km_smem_add64(&wacc[cur * (D + 1) + lane], run);
+        }
+    };
+    // this warp has left a block's stage; the warp whose arrival completes the phase (the last one out) refills it
+    auto release = [&](int stage, unsigned parity, int use, int64_t blk) {
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive(&empty[stage]);
+            if (mbar_test(&empty[stage], parity) && atomicCAS(&ticket[stage], use, use + 1) == use) {
+                const int64_t nb = blk + (int64_t)n_stages * gridDim.x;
+                if (nb < n_blocks) issue(nb, stage);
+            }
+        }
+    };
+
+    // ---- software pipeline over this CTA's tiles (two TMEM buffers): a warp writes its lanes of A for tile i+1, announces them,
+    //      and goes on with the epilogue of tile i.  The warp whose announcement completes the four (a ticket makes it unique)
+    //      issues the six MMAs of tile i+1, which then run under everybody's epilogue of tile i.  No CTA-wide barrier: a warp
+    //      only ever waits for the MMAs of the tile it is about to read.
+    const float* wst_prev = nullptr;
+    int64_t p_prev = 0, blk_prev = 0;
+    unsigned old_prev = 255u, par_prev = 0;
+    int rel_prev = -1, use_prev = 0;  // stage to release after the previous tile's epilogue (-1: not the block's last tile)
+    bool valid_prev = false, have_prev = false;
+    uint32_t tile_idx = 0;
+    int s = 0, use = 0;
+    unsigned parity = 0;
+    for (int64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+        const int64_t p_blk = blk * BPX;
+        const int rem = (int)min((int64_t)BPX, n4 - p_blk);  // pixels of this block
+        const int n_sub = (rem + 127) >> 7;
+        const float* st = stages + (size_t)s * D * BPX;
+        mbar_wait(&full[s], parity);
+#pragma unroll 1
+        for (int sub = 0; sub < n_sub; ++sub) {
+            const uint32_t buf = tile_idx & 1u;
+            const int off = sub * 128 + tid;
+            const bool valid = off < rem;
+            const unsigned old = (prev8 && valid) ? (unsigned)__ldg(prev8 + p_blk + off) : 255u;  // in flight under the MMAs
+            {
+                // A operand: this thread's pixel in two pieces.  kind::tf32 reads the 11 leading bits of an fp32 operand and drops
+                // the rest (tools/tc_probe.cu: 128/128 truncation on the B200), so xh is x itself and xl = x - trunc11(x).
+                uint32_t ah[16], al[16];
+#pragma unroll
+                for (int d = 0; d < 16; ++d) {
+                    if (d < D) {
+                        const float x = st[d * BPX + off];
+                        ah[d] = __float_as_uint(x);
+                        al[d] = __float_as_uint(x - tf32_trunc(x));
+                    } else {
+                        ah[d] = d < D + 3 ? 0x3f800000u : 0u;  // 1.0 against the bias pieces
+                        al[d] = 0u;
+                    }
+                }
+                tc_st16(t_lane + buf * 2 * KM_TC_KDIM, ah);
+                tc_st16(t_lane + buf * 2 * KM_TC_KDIM + KM_TC_KDIM, al);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                // Announce this warp's lanes.  It has also finished reading the distances this buffer held two tiles ago (program
+                // order), so once all four warps are in, the buffer may be overwritten.
+                const int n_use = (int)(tile_idx >> 1);
+                mbar_arrive(&a_ready[buf]);
+                if (mbar_test(&a_ready[buf], n_use & 1) && atomicCAS(&ticket[n_stages + buf], n_use, n_use + 1) == n_use) {
+                    tc_fence_after();
+                    const uint32_t a_hi = tbase + buf * 2 * KM_TC_KDIM, d_col = tbase + COL_D + buf * NPAD;
+#pragma unroll
+                    for (int term = 0; term < 3; ++term) {  // xh.wh, xh.wl, xl.wh
+                        const uint32_t a_col = a_hi + (term == 2 ? KM_TC_KDIM : 0);
+                        const uint32_t b_base = bop_addr + (term == 1 ? NPAD * KM_TC_KDIM * 4 : 0);
+#pragma unroll
+                        for (int ks = 0; ks < 2; ++ks)
+                            tc_mma_tf32(d_col, a_col + 8 * ks, tc_smem_desc(b_base + ks * 2 * CSTR, CSTR, 128), IDESC, (term | ks) ? 1u : 0u);
+                    }
+                    tc_commit(&mma_bar[buf]);
+                }
+            }
+            __syncwarp();
+            if (have_prev) {
+                const uint32_t pt = tile_idx - 1;
+                mbar_wait(&mma_bar[pt & 1u], (pt >> 1) & 1u);
+                tc_fence_after();
+                epilogue(wst_prev, p_prev, old_prev, valid_prev, pt & 1u);
+                if (rel_prev >= 0) release(rel_prev, par_prev, use_prev, blk_prev);
+            }
+            wst_prev = st + sub * 128 + warp * 32, p_prev = p_blk + off, old_prev = old, valid_prev = valid, have_prev = true;
+            rel_prev = sub == n_sub - 1 ? s : -1, par_prev = parity, use_prev = use, blk_prev = blk;
+            ++tile_idx;
+        }
+        if (++s == n_stages) s = 0, parity ^= 1u, ++use;
+    }
+    if (have_prev) {  // drain
+        const uint32_t pt = tile_idx - 1;
+        mbar_wait(&mma_bar[pt & 1u], (pt >> 1) & 1u);
+        tc_fence_after();
+        epilogue(wst_prev, p_prev, old_prev, valid_prev, pt & 1u);
+        if (rel_prev >= 0) release(rel_prev, par_prev, use_prev, blk_prev);
+    }
+    // ragged tail (n_px % 4 pixels): one thread, scalar fp32 path
+    if (blockIdx.x == 0 && tid == 0) {
+        for (int64_t q = n4; q < n_px; ++q) {
+            float x[D];
+            const int l = km_scalar_pixel<D>(stack, plane_stride, q, K, x, INERTIA, inertia, ties);
+            const int old = (MODE == KM_FULL || !prev8) ? 255 : (int)prev8[q];
+            if (prev8 && prev8[q] != l) ++changed;
+            if (SUMS && (MODE == KM_FULL || old != l)) {
+                for (int d = 0; d <= D; ++d) {
+                    const long long qv = d < D ? __float2ll_rn(x[d] * g_km.pow2[d]) : 1ll;
+                    km_smem_add64(&wacc[l * (D + 1) + d], qv);
+                    if (old < KM_MAXK) km_smem_add64(&wacc[old * (D + 1) + d], -qv);
+                }
+            }
+            if (lab8) lab8[q] = (uint8_t)l;
+            if (lab32) lab32[q] = l;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(tmem_cols) : "memory");
+    if (SUMS) {
+        for (int i = tid; i < K * (D + 1); i += KM_THREADS) {
+            const long long t = wacc[i];
+            if (t) {
+                const int j = i / (D + 1), d = i % (D + 1);
+                long long* dst = d < D ? &gacc[j * D + d] : &gacc[K * D + j];
+                atomicAdd(reinterpret_cast<unsigned long long*>(dst), (unsigned long long)t);
+            }
+        }
+    }
+    km_commit_counters(gacc, K, D, ties, changed, inertia, inertia_out, INERTIA);
+}
+
 // ----------------------------------------------------------------------------- launchers
 template <int D>
 static int km_launch_full(const KmLaunch& a, cudaStream_t s) {
@@ -807,8 +1281,64 @@ static int km_launch_stream(const KmLaunch& a, cudaStream_t s) {
     return rsx_check_launch("km_stream");
 }
 
+template <int D, int MODE, bool INERTIA, int NPAD>
+static int km_launch_tc_n(const KmLaunch& a, cudaStream_t s) {
+    auto kern = km_tc_kernel<D, MODE, INERTIA, NPAD>;
+    constexpr int need_cols = 4 * KM_TC_KDIM + 2 * NPAD;  // two A buffers (hi, lo) + two distance buffers
+    constexpr int tmem_cols = need_cols <= 128 ? 128 : 256;
+    static int cfg_K = -1, cfg_stages = 0, cfg_per_sm = 0, cfg_dev = -1, cfg_req = -1;  // per kernel instantiation
+    int dev = 0;
+    cudaGetDevice(&dev);
+    auto smem_for = [&](int stages) { return KmTcSmem(D, a.K, stages, NPAD, MODE != KM_ASSIGN, INERTIA).total; };
+    const int forced = rsx_option("km_tc_ctas", 0);
+    if (cfg_K != a.K || cfg_dev != dev || cfg_req != a.n_stages * 16 + forced) {
+        int best_stages = 2, best_per_sm = 0;
+        for (int stages = a.n_stages > 0 ? a.n_stages : 2; stages <= (a.n_stages > 0 ? a.n_stages : 3); ++stages) {
+            const int smem = smem_for(stages);
+            if (smem > 227 * 1024) break;
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max(smem, 48 * 1024)) != cudaSuccess) break;
+            // The occupancy calculator answers 1 CTA/SM for a kernel that allocates tensor memory (it cannot know how many columns
+            // the kernel will ask for); the real limits are the 128-register launch bound (4 CTAs), shared memory and the TMEM
+            // columns every resident CTA holds for its whole life.
+            int per_sm = min(min(4, (227 * 1024) / (smem + 1024)), 512 / tmem_cols);
+            if (forced > 0) per_sm = min(per_sm, forced);
+            if (per_sm > best_per_sm || (per_sm == best_per_sm && per_sm > 0)) best_per_sm = per_sm, best_stages = stages;
+        }
+        if (best_per_sm <= 0) {
+            cudaGetLastError();
+            rsx_set_error("km_tc: no launch configuration fits (D=%d, K=%d)", D, a.K);
+            return RSX_ERR_CUDA;
+        }
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max(smem_for(best_stages), 48 * 1024));
+        cfg_K = a.K, cfg_stages = best_stages, cfg_per_sm = best_per_sm, cfg_dev = dev, cfg_req = a.n_stages * 16 + forced;
+        if (getenv("RSX_DEBUG"))
+            fprintf(stderr, "[rsx] km_tc D=%d K=%d mode=%d: N=%d, %d TMEM columns, %d stages, %d CTAs/SM, %d B smem\n", D, a.K, MODE, NPAD, tmem_cols, best_stages,
+                    best_per_sm, smem_for(best_stages));
+    }
+    const int64_t n4 = a.n_px & ~(int64_t)3;
+    const int64_t n_blocks = ceil_div(n4, (int64_t)KM_TC_BPX);
+    const int grid = (int)max((int64_t)1, min(n_blocks, (int64_t)rsx_num_sms() * cfg_per_sm));
+    kern<<<grid, KM_THREADS, smem_for(cfg_stages), s>>>(a.stack, a.plane_stride, a.n_px, a.acc, a.lab8, a.prev8, a.lab32, a.inertia, cfg_stages, tmem_cols);
+    return rsx_check_launch("km_tc");
+}
+
+template <int D, int MODE, bool INERTIA>
+static int km_launch_tc(const KmLaunch& a, cudaStream_t s) {
+    if (a.K <= 16) return km_launch_tc_n<D, MODE, INERTIA, 16>(a, s);
+    if (a.K <= 32) return km_launch_tc_n<D, MODE, INERTIA, 32>(a, s);
+    return km_launch_tc_n<D, MODE, INERTIA, 64>(a, s);
+}
+
 template <int D, int KU, bool WARPX>
 static int km_launch2(const KmLaunch& a, cudaStream_t s) {
+    if constexpr (KU == 0 && D + 3 <= KM_TC_KDIM && D >= 6) {  // shallower stacks: too few FMAs to matter
+        if (a.use_tc) {  // K > 8: distances on the tensor cores
+            if (a.mode == KM_FULL) return km_launch_tc<D, KM_FULL, false>(a, s);
+            if (a.mode == KM_DELTA) return km_launch_tc<D, KM_DELTA, false>(a, s);
+            if (a.inertia) return km_launch_tc<D, KM_ASSIGN, true>(a, s);
+            return km_launch_tc<D, KM_ASSIGN, false>(a, s);
+        }
+    }
     if (a.mode == KM_FULL) {
         if constexpr (KU == 8 && D <= 20) return km_launch_full<D>(a, s);
         return km_launch_stream<D, KM_FULL, false, KU, WARPX>(a, s);

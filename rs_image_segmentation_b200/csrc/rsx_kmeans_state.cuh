@@ -27,7 +27,7 @@ struct __align__(16) KmState {
     int n_empty;
     int n_updates;
     int tag_bits;  // width of the index tag in the fp32 distances: 3 (K <= 8), 4, 5, 6
-    int pad1;
+    float tau_tc;  // near-tie band of the tensor-core (3 x TF32) distances, tag included
 };
 
 
@@ -55,6 +55,7 @@ struct KmLaunch {
     int mode, D, K;
     int pf_rows;   // full-pass kernel: L2 prefetch distance in rows (0 = off)
     int n_stages;  // streaming kernel: blocks in flight per CTA (0 = choose)
+    int use_tc;    // K > 8, D <= 13: distances on the tensor cores (tcgen05, 3 x TF32 split); 0 = the fp32 FFMA2 path
 };
 typedef int (*km_assign_fn)(const KmLaunch&, cudaStream_t);
 typedef int (*km_publish_fn)(const void* d_state, cudaStream_t);

@@ -188,7 +188,7 @@ static void all_tests() {
     // 1. layout: small integers
     for (auto& v : A) v = (float)(rand() % 15 - 7);
     for (auto& v : B) v = (float)(rand() % 15 - 7);
-    for (int variant = 0; variant < 2; ++variant) {
+    for (int variant = 0; variant < 1; ++variant) {  // variant 1 (LBO/SBO swapped) reads outside the operand: illegal address on the B200
         long long cyc = 0;
         run<N>(variant, A, B, D, &cyc, 1);
         int bad = 0;
@@ -206,7 +206,7 @@ static void all_tests() {
     for (int m = 0; m < 128; ++m) A2[m * 16 + (m % 16)] = 1.0f + (float)(rand() % 8191 + 1) / 8388608.0f * 1023.0f + (float)(rand() % 1024) / 1024.0f;
     for (int n = 0; n < N; ++n)
         for (int k = 0; k < 16; ++k) B2[n * 16 + k] = 1.0f;
-    for (int variant = 0; variant < 2; ++variant) {
+    for (int variant = 0; variant < 1; ++variant) {  // variant 1 (LBO/SBO swapped) reads outside the operand: illegal address on the B200
         run<N>(variant, A2, B2, D, nullptr, 1);
         int t = 0, r = 0, x = 0;
         for (int m = 0; m < 128; ++m) {
@@ -220,7 +220,7 @@ static void all_tests() {
     // 3. accumulation error with 11-bit operands (exact products), 16 terms of mixed sign and magnitude
     for (auto& v : A) v = trunc13(((float)rand() / RAND_MAX - 0.5f) * 4.f);
     for (auto& v : B) v = trunc13(((float)rand() / RAND_MAX - 0.5f) * 4.f);
-    for (int variant = 0; variant < 2; ++variant) {
+    for (int variant = 0; variant < 1; ++variant) {  // variant 1 (LBO/SBO swapped) reads outside the operand: illegal address on the B200
         long long cyc = 0;
         run<N>(variant, A, B, D, &cyc, 200);
         double worst = 0, mag = 0;
