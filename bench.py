@@ -333,7 +333,8 @@ def run_rsx(args):
         d2h = int(P.segment_stream_d2h_bytes(H * W)) if hasattr(P, "segment_stream_d2h_bytes") else int(H * W * 4)
         e2e = {"value": n_global / (ms_e2e * 1e-3) / 1e6, "unit": "Mpixel/s", "h2d_bytes_per_step": int(pinned.numel()) * world,
                "d2h_bytes_per_step": d2h * world, "ms_per_step": ms_e2e, "steps": e2e_steps,
-               "api": "pipeline.segment_stream (double-buffered H2D / D2H on the copy engines); one scene alone through "
+               "api": "pipeline.segment_stream (double-buffered H2D / D2H on the copy engines; labels leave the device as uint8 and are "
+                      "widened to the reference's int32 by host threads, inside the timed region); one scene alone through "
                       "pipeline.segment_raster: see single_scene_ms"}
         if len(yields) >= 4:
             # host-clock interval between consecutive label arrays in the middle of the run: what a long stream of scenes

@@ -148,8 +148,9 @@ int rsx_glcm_props(const uint8_t* d_q, int rows_avail, int W, int levels, int wi
 /* rsx_glcm_props with the same kernels ALSO storing, for every window and angle, the exact integers the five properties are
  * made from (validation of the production kernel's integer stage against graycomatrix counts, bit for bit):
  * d_moments int64 [out_rows*out_cols][4][8] = n (pair instances), sum|a-b|, sum(a+b), sum(a^2+b^2), sum(a*b),
- * E = sum over the cells of the symmetric count matrix P = C + C^T of P^2, pairs with a == b, sum of round(2^40/(1+(a-b)^2)).
- * contrast = (sq-2sab)/n, dissimilarity = s1/n, homogeneity = hom/2^40/n, energy = sqrt(E)/2n,
+ * E = sum over the cells of the symmetric count matrix P = C + C^T of P^2, pairs with a == b, sum of round(2^h/(1+(a-b)^2))
+ * with h = 40 for levels <= 32 and h = 36 above (the fixed-point homogeneity terms of the kernels).
+ * contrast = (sq-2sab)/n, dissimilarity = s1/n, homogeneity = hom/2^h/n, energy = sqrt(E)/2n,
  * correlation = (4n*sab - sa^2)/(2n*sq - sa^2) (1 for a constant window). */
 int rsx_glcm_moments(const uint8_t* d_q, int rows_avail, int W, int levels, int window, int step, int out_rows, int out_cols,
                      float* d_props, int64_t plane_stride, int64_t* d_moments, rsx_stream_t stream);
@@ -198,6 +199,10 @@ int rsx_u8_over_255_f32(const uint8_t* d_in, int64_t n, float* d_out, rsx_stream
  * extract.py:795-807). */
 int rsx_planes_to_hwc_f64(const float* d_planes, int64_t plane_stride, int64_t n_px, int n_channels, double* d_out, rsx_stream_t stream);
 int rsx_labels_plus1_u8(const int32_t* d_labels, int64_t n, uint8_t* d_out, rsx_stream_t stream);
+/* HOST helper (no device work): widens a downloaded uint8 label plane into the caller's int32 array (the dtype the reference
+ * returns, extract.py:577) on n_threads host threads.  The device keeps labels as uint8; downloading those moves a quarter of
+ * the bytes of an int32 download over PCIe. */
+int rsx_widen_u8_to_i32(const uint8_t* h_src, int32_t* h_dst, int64_t n, int n_threads);
 
 /* ---- min/max trackers (MinMaxScaler.fit, sklearn/preprocessing/_data.py:527-541) --------------- */
 int rsx_minmax_init(uint32_t* d_minmax, int n, rsx_stream_t stream);

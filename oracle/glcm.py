@@ -201,18 +201,23 @@ def counts_map_c(q, levels, window, step):
 MOMENT_FIELDS = ("n", "s1", "sa", "sq", "sab", "e", "neq", "hom_fx")
 
 
+def hom_bits(levels):
+    """Fixed-point scale of the homogeneity terms in the GPU kernels: 2^40 up to 32 levels, 2^36 above (rsx.h rsx_glcm_moments)."""
+    return 40 if levels <= 32 else 36
+
+
 def pair_moments(q, levels, window, step=1):
     """(oh, ow, 4, 8) int64: for every window and angle the exact integers from which the five properties follow without a
     histogram (include/rsx.h rsx_glcm_moments; derived from the directed counts of counts_map_c, i.e. from the same
     graycomatrix restatement that the docstring known answer pins):
       n    pair instances            s1  sum |a-b|          sa  sum (a+b)        sq  sum (a^2+b^2)      sab  sum a*b
       e    sum over the cells of the SYMMETRIC count matrix P = C + C^T of P^2 (so energy = sqrt(e) / 2n)
-      neq  pairs with a == b         hom_fx  sum of round(2^40 / (1 + (a-b)^2)) (the kernel's fixed-point homogeneity terms)"""
+      neq  pairs with a == b         hom_fx  sum of round(2^h / (1 + (a-b)^2)), h = hom_bits(levels) (the kernels' fixed-point terms)"""
     C = counts_map_c(q, levels, window, step).astype(np.int64)            # (oh, ow, 4, L, L)
     a = np.arange(levels, dtype=np.int64).reshape(levels, 1)
     b = np.arange(levels, dtype=np.int64).reshape(1, levels)
     d = np.abs(a - b)
-    hom = np.floor(2.0 ** 40 / (1.0 + (d * d).astype(np.float64)) + 0.5).astype(np.int64)
+    hom = np.floor(2.0 ** hom_bits(levels) / (1.0 + (d * d).astype(np.float64)) + 0.5).astype(np.int64)
     S = C + C.transpose(0, 1, 2, 4, 3)
     out = np.zeros(C.shape[:3] + (8,), dtype=np.int64)
     out[..., 0] = C.sum(axis=(3, 4))
@@ -226,12 +231,12 @@ def pair_moments(q, levels, window, step=1):
     return out
 
 
-def props_from_moments(m):
+def props_from_moments(m, levels=32):
     """The five graycoprops of one angle from its pair moments, float64 (rsx_glcm.cu header comment)."""
     n, s1, sa, sq, sab, e, neq, hom_fx = (int(v) for v in m)
     var_num = 2 * n * sq - sa * sa
     cov_num = 4 * n * sab - sa * sa
-    return dict(contrast=(sq - 2 * sab) / n, dissimilarity=s1 / n, homogeneity=hom_fx / 2.0 ** 40 / n, energy=np.sqrt(float(e)) / (2.0 * n),
+    return dict(contrast=(sq - 2 * sab) / n, dissimilarity=s1 / n, homogeneity=hom_fx / 2.0 ** hom_bits(levels) / n, energy=np.sqrt(float(e)) / (2.0 * n),
                 correlation=1.0 if var_num <= 0 else cov_num / var_num)
 
 

@@ -55,6 +55,7 @@ SIGNATURES = {
     "rsx_u8_over_255_f32": (i32, [vp, i64, vp, vp]),
     "rsx_planes_to_hwc_f64": (i32, [vp, i64, i64, i32, vp, vp]),
     "rsx_labels_plus1_u8": (i32, [vp, i64, vp, vp]),
+    "rsx_widen_u8_to_i32": (i32, [vp, vp, i64, i32]),
     "rsx_box_mean_f32": (i32, [vp, i32, i32, i32, i32, i64, vp, i32, i32, i64, i32, i32, vp, vp]),
     "rsx_kmeans_state_bytes": (i64, []),
     "rsx_kmeans_setup": (i32, [vp, i32, i32, vp, vp, vp, vp, i64, vp]),

@@ -58,8 +58,11 @@ __device__ __forceinline__ void warp_minmax_commit(float mn, float mx, unsigned*
         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     }
     if ((threadIdx.x & 31) == 0) {
-        atomicMin(slot, f2ord(mn));
-        atomicMax(slot + 1, f2ord(mx));
+        // the tracker only ever moves outwards: a plain (possibly stale) read tells most warps that they have nothing to add, which
+        // keeps tens of thousands of same-address atomics of the many-CTA kernels out of the L2 atomic unit
+        const unsigned omn = f2ord(mn), omx = f2ord(mx);
+        if (omn < *reinterpret_cast<volatile unsigned*>(slot)) atomicMin(slot, omn);
+        if (omx > *reinterpret_cast<volatile unsigned*>(slot + 1)) atomicMax(slot + 1, omx);
     }
 }
 

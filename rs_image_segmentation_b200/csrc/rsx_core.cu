@@ -40,6 +40,32 @@ int rsx_num_sms() {
     return n;
 }
 
+// ----------------------------------------------------------------------------- host side of the label download
+// The reference returns int32 labels (extract.py:577); the device keeps them as uint8 (K <= 64).  Downloading the uint8 plane and
+// widening it on the host's cores moves a quarter of the bytes over PCIe (49 instead of 196 MB for a 7000 x 7000 scene), which is
+// what bounds the end-to-end rate once several GPUs of one box stream at the same time.
+#include <thread>
+#include <vector>
+extern "C" int rsx_widen_u8_to_i32(const uint8_t* h_src, int32_t* h_dst, int64_t n, int n_threads) {
+    RSX_REQUIRE(h_src && h_dst && n >= 0, "rsx_widen_u8_to_i32: bad arguments");
+    n_threads = (int)max((int64_t)1, min((int64_t)min(n_threads, 64), n / (1 << 16)));
+    auto work = [=](int64_t a, int64_t b) {
+        for (int64_t i = a; i < b; ++i) h_dst[i] = (int32_t)h_src[i];  // vectorised by the host compiler
+    };
+    if (n_threads <= 1) {
+        work(0, n);
+        return RSX_OK;
+    }
+    std::vector<std::thread> pool;
+    const int64_t chunk = ((n + n_threads - 1) / n_threads + 63) & ~(int64_t)63;
+    for (int t = 0; t < n_threads; ++t) {
+        const int64_t a = min(n, t * chunk), b = min(n, a + chunk);
+        if (b > a) pool.emplace_back(work, a, b);
+    }
+    for (auto& th : pool) th.join();
+    return RSX_OK;
+}
+
 // ----------------------------------------------------------------------------- tuning options
 // Small registry of integer knobs (kernel variant switches used by the profiling tools and the A/B tests).  A knob set through
 // rsx_set_option wins; otherwise the environment variable RSX_<NAME IN UPPER CASE> is consulted on every query; otherwise the

@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(128) glcm_props_warp_kernel(const uint8_t* __r
                 const uint8_t* p = base + r * W + c;
                 const int a = p[0], b = p[off];
                 const int d = abs(a - b);
-                if (moments) hfx += (long long)(1099511627776.0 / (1.0 + (double)d * (double)d) + 0.5), neq += d == 0;
+                if (moments) hfx += (long long)((L <= 32 ? 1099511627776.0 : 68719476736.0) / (1.0 + (double)d * (double)d) + 0.5), neq += d == 0;
                 t.s1 += d;
                 t.sa += a + b;
                 t.sq += a * a + b * b;
@@ -186,11 +186,15 @@ struct DenseShared {
 // WIDE (levels > 32): sum of a^2+b^2 needs its own 32-bit word, so the sum of a+b moves into the u64:
 //   narrow: W1 = s1 | sab << 13,  W2 = sa | sq << 14,  SH = homog * 2^40 | Neq << 52
 //   wide:   W1 = s1 | sab << 13,  W2 = sq,             SH = homog * 2^36 | Neq << 43 | sa << 50
-// FOLD (levels <= 32, experimental): the private counters are indexed by the levels modulo 8 - 36 unordered cells instead of
-// L(L+1)/2, 36 B per window and angle instead of 528 - which is exact for every window whose levels span fewer than 8 values
-// (the fold is injective there).  Windows with a wider span are flagged by glcm_span_flag_kernel and get their energy from
-// glcm_energy_patch_kernel; the other four properties never use the counters.
-template <int WIN, int NT, int ANG, bool WIDE, bool FOLD>
+// FOLD = 8 or 16 (levels <= 32): the private counters are indexed by the levels modulo FOLD - F(F+1)/2 cells for the pairs with
+// a != b plus F cells for the pairs with a == b (44 B per window and angle at FOLD 8 instead of 528) - which is exact for every
+// window whose levels span fewer than FOLD values (the fold is injective there).  Windows with a wider span are flagged by
+// glcm_span_flag_kernel and get their energy from glcm_energy_patch_kernel; the other four properties never use the counters.
+// The a == b pairs have their own cells because the incremental energy e is a function of the counters only as long as all
+// pairs of a cell carry the same weight (2 for a != b, 4 for a == b): with mixed cells a window that WAS flagged would leave a
+// wrong e behind for the unflagged windows below it.
+__host__ __device__ constexpr int fold_cells(int F) { return F * (F + 1) / 2 + F; }
+template <int WIN, int NT, int ANG, bool WIDE, int FOLD>
 __device__ __forceinline__ void glcm_dense_body(const DenseShared sm, const uint8_t* __restrict__ q, int W, int L, int out_cols, int i_begin, int i_end,
                                                 int j0, int t, int NTW, float* __restrict__ props, int64_t plane_stride,
                                                 long long* __restrict__ moments) {
@@ -199,7 +203,7 @@ __device__ __forceinline__ void glcm_dense_body(const DenseShared sm, const uint
     constexpr int DC = ANG == 0 ? 1 : (ANG == 1 ? 1 : (ANG == 2 ? 0 : -1));
     constexpr int C0 = ANG == 3 ? 1 : 0, C1 = ANG <= 1 ? WIN - 1 : WIN;  // anchor columns of the angle inside a window
     constexpr int NPAIR = (ANG == 0 || ANG == 2) ? WIN * (WIN - 1) : (WIN - 1) * (WIN - 1);
-    const int ncell = FOLD ? 36 : L * (L + 1) / 2;
+    const int ncell = FOLD ? fold_cells(FOLD) : L * (L + 1) / 2;
     const bool has_win = t < NTW && j0 + t < out_cols;
     const bool col_ok = j0 + t < W;
     const bool pair_ok = t + DC >= 0 && t + DC < NT;  // partner column inside the band
@@ -231,7 +235,8 @@ __device__ __forceinline__ void glcm_dense_body(const DenseShared sm, const uint
         unsigned cell = 0xfffffff0u;  // never equal to a real cell
         if (pair_ok) {
             const int a = qt[sa * NT], b = qt[sb * NT + DC];
-            cell = ((unsigned)((FOLD ? tri_cell(a & 7, b & 7) : tri_cell(a, b)) * NTW) << 16) | (a == b ? 8u : 4u);
+            const int cid = !FOLD ? tri_cell(a, b) : (a == b ? FOLD * (FOLD + 1) / 2 + (a & (FOLD - 1)) : tri_cell(a & (FOLD - 1), b & (FOLD - 1)));
+            cell = ((unsigned)(cid * NTW) << 16) | (a == b ? 8u : 4u);
             unsigned w1, w2;
             unsigned long long sh;
             pair_terms(a, b, w1, w2, sh);
@@ -341,7 +346,7 @@ __device__ __forceinline__ void glcm_dense_body(const DenseShared sm, const uint
             if (moments) {  // validation dump of the exact integers the five values above were made from (rsx_glcm_moments)
                 long long* m = moments + (((int64_t)i * out_cols + j0 + t) * 4 + ANG) * 8;
                 m[0] = NPAIR, m[1] = s1, m[2] = sa, m[3] = sq, m[4] = sab, m[5] = e + 2 * NPAIR + 2 * neq, m[6] = neq;
-                m[7] = (long long)(WIDE ? (shom << 4) : shom);  // 2^40-scaled sum (the wide variant keeps 2^36)
+                m[7] = (long long)shom;  // 2^40-scaled terms (levels <= 32), 2^36-scaled for the wide variant
             }
         }
         int s_anchor = -1;
@@ -374,14 +379,17 @@ __device__ __forceinline__ void glcm_dense_body(const DenseShared sm, const uint
     }
 }
 
-template <int WIN, int NT, bool WIDE, bool FOLD>
+template <int WIN, int NT, bool WIDE, int FOLD>
 __global__ void __launch_bounds__(NT * 4) glcm_dense_kernel(const uint8_t* __restrict__ q, int W, int L, int out_rows, int out_cols, int rows_per_cta,
-                                                            int NTW, float* __restrict__ props, int64_t plane_stride, long long* __restrict__ moments) {
+                                                            int NTW, float* __restrict__ props, int64_t plane_stride, long long* __restrict__ moments,
+                                                            const int* __restrict__ fold_mode) {
+    // several variants are launched back to back; the one the span statistics selected (glcm_fold_select_kernel) does the work
+    if (fold_mode && *fold_mode != FOLD) return;
     // NTW = windows per CTA, <= NT - (WIN - 1), capped by what the private counters leave of shared memory
     constexpr int RING = WIN + 1;
     extern __shared__ __align__(16) unsigned char dsm[];
     __shared__ unsigned long long homog_fx[64];
-    const int ncell = FOLD ? 36 : L * (L + 1) / 2;
+    const int ncell = FOLD ? fold_cells(FOLD) : L * (L + 1) / 2;
     DenseShared sm;
     sm.xch = reinterpret_cast<uint4*>(dsm);
     sm.outx = reinterpret_cast<float*>(sm.xch + 4 * NT);
@@ -417,10 +425,10 @@ static size_t dense_smem_bytes(int win, int nt, int ntw, int ncell) {
     return (size_t)4 * ncell * ntw + (size_t)nt * (16 * (win + 1) + 16 + 64 + 80 + (win + 1)) + 16 * win + 64;
 }
 
-template <int WIN, int NT, bool WIDE, bool FOLD = false>
+template <int WIN, int NT, bool WIDE, int FOLD = 0>
 static int launch_dense(const uint8_t* d_q, int W, int levels, int ntw, int out_rows, int out_cols, float* d_props, int64_t plane_stride, long long* d_moments,
-                        cudaStream_t s) {
-    const int ncell = FOLD ? 36 : levels * (levels + 1) / 2;
+                        cudaStream_t s, const int* d_fold_mode = nullptr) {
+    const int ncell = FOLD ? fold_cells(FOLD) : levels * (levels + 1) / 2;
     const size_t smem = dense_smem_bytes(WIN, NT, ntw, ncell);
     auto kern = glcm_dense_kernel<WIN, NT, WIDE, FOLD>;
     static size_t configured = 0;
@@ -449,14 +457,14 @@ static int launch_dense(const uint8_t* d_q, int W, int levels, int ntw, int out_
     }
     const int rows_per_cta = ceil_div(out_rows, best_gy);
     const int gy = ceil_div(out_rows, rows_per_cta);
-    kern<<<dim3(gx, gy), NT * 4, smem, s>>>(d_q, W, levels, out_rows, out_cols, rows_per_cta, ntw, d_props, plane_stride, d_moments);
+    kern<<<dim3(gx, gy), NT * 4, smem, s>>>(d_q, W, levels, out_rows, out_cols, rows_per_cta, ntw, d_props, plane_stride, d_moments, d_fold_mode);
     return rsx_check_launch("glcm_dense");
 }
 
 // pick the widest CTA whose private counters fit in shared memory (and whose counter offsets fit the 16-bit code field)
 template <int WIN, bool WIDE>
 static int dispatch_dense(const uint8_t* d_q, int W, int levels, int out_rows, int out_cols, float* d_props, int64_t plane_stride, long long* d_moments,
-                          cudaStream_t s) {
+                          cudaStream_t s, const int* d_fold_mode = nullptr) {
     const int ncell = levels * (levels + 1) / 2;
     const size_t limit = (size_t)226 * 1024;
     auto windows = [&](int nt) {  // windows per CTA for this width (0 = does not fit)
@@ -470,24 +478,24 @@ static int dispatch_dense(const uint8_t* d_q, int W, int levels, int out_rows, i
     for (int k = 0; k < 4; ++k) {
         const int nt = nts[k], ntw = windows(nt);
         if (forced ? (nt == forced && ntw >= 8) : (ntw * 4 >= (nt - (WIN - 1)) * 3)) {
-            if (nt == 256) return launch_dense<WIN, 256, WIDE>(d_q, W, levels, ntw, out_rows, out_cols, d_props, plane_stride, d_moments, s);
-            if (nt == 128) return launch_dense<WIN, 128, WIDE>(d_q, W, levels, ntw, out_rows, out_cols, d_props, plane_stride, d_moments, s);
-            if (nt == 96) return launch_dense<WIN, 96, WIDE>(d_q, W, levels, ntw, out_rows, out_cols, d_props, plane_stride, d_moments, s);
-            return launch_dense<WIN, 64, WIDE>(d_q, W, levels, ntw, out_rows, out_cols, d_props, plane_stride, d_moments, s);
+            if (nt == 256) return launch_dense<WIN, 256, WIDE>(d_q, W, levels, ntw, out_rows, out_cols, d_props, plane_stride, d_moments, s, d_fold_mode);
+            if (nt == 128) return launch_dense<WIN, 128, WIDE>(d_q, W, levels, ntw, out_rows, out_cols, d_props, plane_stride, d_moments, s, d_fold_mode);
+            if (nt == 96) return launch_dense<WIN, 96, WIDE>(d_q, W, levels, ntw, out_rows, out_cols, d_props, plane_stride, d_moments, s, d_fold_mode);
+            return launch_dense<WIN, 64, WIDE>(d_q, W, levels, ntw, out_rows, out_cols, d_props, plane_stride, d_moments, s, d_fold_mode);
         }
     }
     const int ntw = windows(32);
-    if (ntw >= 8 && (!forced || forced == 32)) return launch_dense<WIN, 32, WIDE>(d_q, W, levels, ntw, out_rows, out_cols, d_props, plane_stride, d_moments, s);
+    if (ntw >= 8 && (!forced || forced == 32)) return launch_dense<WIN, 32, WIDE>(d_q, W, levels, ntw, out_rows, out_cols, d_props, plane_stride, d_moments, s, d_fold_mode);
     return -1;
 }
 
 // ----------------------------------------------------------------------------- folded counters: span flags + energy patch
-// flags[i * out_cols + j] = 1 when the levels of window (i, j) span 8 or more values (the fold modulo 8 may then merge two cells).
-// One CTA per tile of SPAN_TR x SPAN_TC windows: the clamped levels of the tile (+ win-1 halo) go to shared memory, a horizontal
-// min/max pass over win columns, then a vertical one over win rows.
+// flags[i * out_cols + j]: bit 0 = the levels of window (i, j) span 8 or more values, bit 1 = 16 or more (the fold modulo 8 / 16
+// may then merge two cells).  stats[0], stats[1] count them.  One CTA per tile of SPAN_TR x SPAN_TC windows: the clamped levels of
+// the tile (+ win-1 halo) go to shared memory, a horizontal min/max pass over win columns, then a vertical one over win rows.
 constexpr int SPAN_TR = 32, SPAN_TC = 128, SPAN_MAXW = 11;
 __global__ void __launch_bounds__(256) glcm_span_flag_kernel(const uint8_t* __restrict__ q, int W, int L, int win, int out_rows, int out_cols,
-                                                             uint8_t* __restrict__ flags) {
+                                                             uint8_t* __restrict__ flags, unsigned long long* __restrict__ stats) {
     __shared__ uint8_t raw[SPAN_TR + SPAN_MAXW - 1][SPAN_TC + SPAN_MAXW - 1 + 1];
     __shared__ uint8_t hmn[SPAN_TR + SPAN_MAXW - 1][SPAN_TC], hmx[SPAN_TR + SPAN_MAXW - 1][SPAN_TC];
     const int i0 = blockIdx.y * SPAN_TR, j0 = blockIdx.x * SPAN_TC;
@@ -505,21 +513,42 @@ __global__ void __launch_bounds__(256) glcm_span_flag_kernel(const uint8_t* __re
         hmn[r][c] = (uint8_t)mn, hmx[r][c] = (uint8_t)mx;
     }
     __syncthreads();
+    unsigned n8 = 0, n16 = 0;
     for (int k = threadIdx.x; k < orows * ocols; k += 256) {
         const int r = k / ocols, c = k - r * ocols;
         int mn = 255, mx = 0;
         for (int d = 0; d < win; ++d) mn = min(mn, (int)hmn[r + d][c]), mx = max(mx, (int)hmx[r + d][c]);
-        flags[(int64_t)(i0 + r) * out_cols + j0 + c] = (uint8_t)(mx - mn >= 8);
+        const int span = mx - mn;
+        flags[(int64_t)(i0 + r) * out_cols + j0 + c] = (uint8_t)((span >= 8 ? 1 : 0) | (span >= 16 ? 2 : 0));
+        n8 += span >= 8, n16 += span >= 16;
     }
+    n8 = __reduce_add_sync(0xffffffffu, n8), n16 = __reduce_add_sync(0xffffffffu, n16);
+    if ((threadIdx.x & 31) == 0) {
+        if (n8) atomicAdd(&stats[0], (unsigned long long)n8);
+        if (n16) atomicAdd(&stats[1], (unsigned long long)n16);
+    }
+}
+
+// mode = 8 / 16: the fold whose flagged share is at most 1/256 of the windows (their energy is recomputed one warp per window, ~50x
+// the cost of a dense window); 0: the unfolded kernel.  Levels that fit the fold need no flags at all.
+__global__ void glcm_fold_select_kernel(const unsigned long long* __restrict__ stats, long long n_win, int levels, int force, int* __restrict__ mode) {
+    int m = 0;
+    if (levels <= 8 || (long long)stats[0] * 256 <= n_win) m = 8;
+    else if (levels <= 16 || (long long)stats[1] * 256 <= n_win) m = 16;
+    if (force == 8 || force == 16 || force == 0) m = force;
+    *mode = m;
 }
 
 // Exact energy of the flagged windows, one warp per window, with the float operations of glcm_dense_body (so that a patched
 // value equals what the unfolded dense kernel writes): per angle E = sum over the pairs of w * U[cell of the pair] from a
 // warp-private histogram of all L(L+1)/2 unordered cells, energy = sqrtf(E) * (0.5 / n); mean of the four angles.
 __global__ void __launch_bounds__(256) glcm_energy_patch_kernel(const uint8_t* __restrict__ q, int W, int L, int win, int out_rows, int out_cols,
-                                                                const uint8_t* __restrict__ flags, float* __restrict__ energy,
-                                                                long long* __restrict__ moments) {
+                                                                const uint8_t* __restrict__ flags, const int* __restrict__ fold_mode,
+                                                                float* __restrict__ energy, long long* __restrict__ moments) {
     __shared__ unsigned hist_all[8][528];
+    const int mode = *fold_mode;
+    if (mode == 0) return;
+    const unsigned bit = mode == 8 ? 1u : 2u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned* hist = hist_all[warp];
     for (int i = lane; i < 528; i += 32) hist[i] = 0;
@@ -528,7 +557,7 @@ __global__ void __launch_bounds__(256) glcm_energy_patch_kernel(const uint8_t* _
     const int64_t warps_total = (int64_t)gridDim.x * 8;
     for (int64_t base = ((int64_t)blockIdx.x * 8 + warp) * 32; base < n_win; base += warps_total * 32) {
         const int64_t mine = base + lane;
-        unsigned todo = __ballot_sync(0xffffffffu, mine < n_win && flags[mine] != 0);
+        unsigned todo = __ballot_sync(0xffffffffu, mine < n_win && (flags[mine] & bit) != 0);
         while (todo) {
             const int src = __ffs(todo) - 1;
             todo &= todo - 1;
@@ -574,36 +603,55 @@ __global__ void __launch_bounds__(256) glcm_energy_patch_kernel(const uint8_t* _
     }
 }
 
-static uint8_t* g_span_flags = nullptr;
-static size_t g_span_flags_cap = 0;
+// scratch of the folded path, per device: [0,16) two counters, [16,20) the selected mode, [64, 64 + n_win) the flags
+static uint8_t* g_span_buf = nullptr;
+static size_t g_span_cap = 0;
+static int g_span_dev = -1;
 
-// folded dense path (levels <= 32, RSX_GLCM_FOLD=1): flags, folded kernel, energy patch.  Returns -1 when not applicable.
+// Folded dense path (levels <= 32): span flags + statistics, fold selection on the device, the three dense variants back to
+// back (two of them return at once), energy patch for the flagged windows.  Returns -1 when not applicable.
 template <int WIN>
 static int dispatch_dense_folded(const uint8_t* d_q, int W, int levels, int out_rows, int out_cols, float* d_props, int64_t plane_stride, long long* d_moments,
                                  cudaStream_t s) {
     const size_t n_win = (size_t)out_rows * out_cols;
-    if (n_win > g_span_flags_cap) {
-        if (g_span_flags) cudaFree(g_span_flags);
-        g_span_flags = nullptr, g_span_flags_cap = 0;
-        if (cudaMalloc(&g_span_flags, n_win) != cudaSuccess) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (n_win + 64 > g_span_cap || dev != g_span_dev) {
+        if (g_span_buf && dev == g_span_dev) cudaFree(g_span_buf);
+        g_span_buf = nullptr, g_span_cap = 0, g_span_dev = dev;
+        if (cudaMalloc(&g_span_buf, n_win + 64) != cudaSuccess) {
             cudaGetLastError();
             return -1;
         }
-        g_span_flags_cap = n_win;
+        g_span_cap = n_win + 64;
     }
-    glcm_span_flag_kernel<<<dim3(ceil_div(out_cols, SPAN_TC), ceil_div(out_rows, SPAN_TR)), 256, 0, s>>>(d_q, W, levels, WIN, out_rows, out_cols, g_span_flags);
+    unsigned long long* stats = reinterpret_cast<unsigned long long*>(g_span_buf);
+    int* mode = reinterpret_cast<int*>(g_span_buf + 16);
+    uint8_t* flags = g_span_buf + 64;
+    if (cudaMemsetAsync(g_span_buf, 0, 64, s) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    glcm_span_flag_kernel<<<dim3(ceil_div(out_cols, SPAN_TC), ceil_div(out_rows, SPAN_TR)), 256, 0, s>>>(d_q, W, levels, WIN, out_rows, out_cols, flags, stats);
     if (int rc = rsx_check_launch("glcm_span_flags")) return rc;
-    const int fold_nt = rsx_option("glcm_fold_nt", 128);
+    glcm_fold_select_kernel<<<1, 1, 0, s>>>(stats, (long long)n_win, levels, rsx_option("glcm_fold_force", -1), mode);
+    if (int rc = rsx_check_launch("glcm_fold_select")) return rc;
+    const int nt = rsx_option("glcm_fold_nt", 64);
     int rc_d;
-    if (fold_nt == 256)
-        rc_d = launch_dense<WIN, 256, false, true>(d_q, W, levels, 256 - (WIN - 1), out_rows, out_cols, d_props, plane_stride, d_moments, s);
-    else if (fold_nt == 64)
-        rc_d = launch_dense<WIN, 64, false, true>(d_q, W, levels, 64 - (WIN - 1), out_rows, out_cols, d_props, plane_stride, d_moments, s);
-    else
-        rc_d = launch_dense<WIN, 128, false, true>(d_q, W, levels, 128 - (WIN - 1), out_rows, out_cols, d_props, plane_stride, d_moments, s);
+    if (nt == 32) {
+        rc_d = launch_dense<WIN, 32, false, 8>(d_q, W, levels, 32 - (WIN - 1), out_rows, out_cols, d_props, plane_stride, d_moments, s, mode);
+        if (!rc_d) rc_d = launch_dense<WIN, 32, false, 16>(d_q, W, levels, 32 - (WIN - 1), out_rows, out_cols, d_props, plane_stride, d_moments, s, mode);
+    } else {
+        rc_d = launch_dense<WIN, 64, false, 8>(d_q, W, levels, 64 - (WIN - 1), out_rows, out_cols, d_props, plane_stride, d_moments, s, mode);
+        if (!rc_d) rc_d = launch_dense<WIN, 64, false, 16>(d_q, W, levels, 64 - (WIN - 1), out_rows, out_cols, d_props, plane_stride, d_moments, s, mode);
+    }
     if (rc_d) return rc_d;
+    if (int rc = dispatch_dense<WIN, false>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, d_moments, s, mode)) {  // mode 0
+        if (rc < 0) rsx_set_error("rsx_glcm_props: no dense configuration for window %d at %d levels", WIN, levels);
+        return rc < 0 ? RSX_ERR_UNSUPPORTED : rc;
+    }
     const int grid = (int)min((int64_t)ceil_div((int64_t)n_win, (int64_t)256), (int64_t)rsx_num_sms() * 8);
-    glcm_energy_patch_kernel<<<grid, 256, 0, s>>>(d_q, W, levels, WIN, out_rows, out_cols, g_span_flags, d_props + 3 * plane_stride, d_moments);
+    glcm_energy_patch_kernel<<<grid, 256, 0, s>>>(d_q, W, levels, WIN, out_rows, out_cols, flags, mode, d_props + 3 * plane_stride, d_moments);
     return rsx_check_launch("glcm_energy_patch");
 }
 
@@ -621,7 +669,7 @@ static int glcm_run(const uint8_t* d_q, int rows_avail, int W, int levels, int w
     // dense fast path: packed integer moments hold for levels <= 64 and window <= 11; uint8 counters hold w(w-1) <= 110
     if (step == 1 && levels <= 64) {
         int rc = -1;
-        const int fold_env = rsx_option("glcm_fold", 0);
+        const int fold_env = rsx_option("glcm_fold", 1);  // 1: folded counters where the scene allows (chosen on the device), 0: never
         if (fold_env && levels <= 32) {
             switch (window) {
                 case 3: rc = dispatch_dense_folded<3>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, d_moments, s); break;
@@ -755,12 +803,93 @@ __global__ void __launch_bounds__(256) resize_bilinear_kernel(const float* __res
     if (minmax) warp_minmax_commit(mn, mx, minmax + 2 * plane);
 }
 
+// Fast path for scale factors up to ~1 (the dense GLCM map, (H-w+1) x (W-w+1) -> H x W): a CTA makes a 32 x 256 tile of one
+// destination plane from the source rows / columns it touches, staged in shared memory with coalesced row loads (the general
+// kernel above fetches four scattered taps per output: 0.72 ms for five 49 Mpx planes against 0.30 ms of HBM time).  Same
+// arithmetic, tap for tap: the weights and clamped tap indices of a row are computed once per CTA (double), of a column once per
+// thread.
+constexpr int RSZ_TR = 32, RSZ_TC = 256, RSZ_SR = RSZ_TR + 4, RSZ_SC = RSZ_TC + 8;
+__global__ void __launch_bounds__(256) resize_bilinear_tile_kernel(const float* __restrict__ src, int src_h, int src_w, int src_row0, int src_rows_avail,
+                                                                   int64_t src_stride, float* __restrict__ dst, int dst_w, int dst_row0, int dst_rows,
+                                                                   int64_t dst_stride, double scale_x, double scale_y, uint32_t* __restrict__ minmax) {
+    __shared__ float tile[RSZ_SR][RSZ_SC];
+    __shared__ float fy_s[RSZ_TR];
+    __shared__ int y0_s[RSZ_TR], y1_s[RSZ_TR];
+    const int plane = blockIdx.z;
+    const float* sp = src + plane * src_stride;
+    float* dp = dst + plane * dst_stride;
+    const int dx0 = blockIdx.x * RSZ_TC, ly0 = blockIdx.y * RSZ_TR;
+    const int n_rows = min(RSZ_TR, dst_rows - ly0), n_cols = min(RSZ_TC, dst_w - dx0);
+    auto tap = [](int d, double scale, int n, int& i0, int& i1) -> float {
+        const double c = (d + 0.5) * scale - 0.5;
+        const double f = floor(c);
+        const int s = (int)f;
+        i0 = min(max(s, 0), n - 1), i1 = min(max(s + 1, 0), n - 1);
+        return (float)(c - f);
+    };
+    // source footprint of the tile (taps are monotone in the destination index)
+    int a, b, sy_lo, sy_hi, sx_lo, sx_hi;
+    tap(dst_row0 + ly0, scale_y, src_h, sy_lo, a);
+    tap(dst_row0 + ly0 + n_rows - 1, scale_y, src_h, b, sy_hi);
+    tap(dx0, scale_x, src_w, sx_lo, a);
+    tap(dx0 + n_cols - 1, scale_x, src_w, b, sx_hi);
+    const int f_rows = sy_hi - sy_lo + 1, f_cols = sx_hi - sx_lo + 1;  // the launcher guarantees they fit the tile
+    if (threadIdx.x < n_rows) {
+        int y0, y1;
+        fy_s[threadIdx.x] = tap(dst_row0 + ly0 + threadIdx.x, scale_y, src_h, y0, y1);
+        y0_s[threadIdx.x] = y0 - sy_lo, y1_s[threadIdx.x] = y1 - sy_lo;
+    }
+    for (int r = threadIdx.x >> 5; r < f_rows; r += 8) {  // a warp takes whole rows: all of a row's loads are in flight together
+        const int gy = sy_lo + r - src_row0;
+        const bool ok = gy >= 0 && gy < src_rows_avail;
+        const float* row = sp + (int64_t)gy * src_w + sx_lo;
+        constexpr int NCH = (RSZ_SC + 31) / 32;
+        float v[NCH];
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) {
+            const int c = (threadIdx.x & 31) + 32 * k;
+            v[k] = (ok && c < f_cols) ? __ldg(row + c) : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) {
+            const int c = (threadIdx.x & 31) + 32 * k;
+            if (c < f_cols) tile[r][c] = v[k];
+        }
+    }
+    __syncthreads();
+    float mn = INFINITY, mx = -INFINITY;
+    if ((int)threadIdx.x < n_cols) {
+        int x0, x1;
+        const float fx = tap(dx0 + threadIdx.x, scale_x, src_w, x0, x1);
+        x0 -= sx_lo, x1 -= sx_lo;
+        float* out = dp + (int64_t)ly0 * dst_w + dx0 + threadIdx.x;
+#pragma unroll 4
+        for (int r = 0; r < n_rows; ++r) {
+            const int y0 = y0_s[r], y1 = y1_s[r];
+            const float p0 = tile[y0][x0], q0 = tile[y0][x1], p1 = tile[y1][x0], q1 = tile[y1][x1];
+            const float r0 = fmaf(f_sub(q0, p0), fx, p0);
+            const float r1 = fmaf(f_sub(q1, p1), fx, p1);
+            const float v = fmaf(f_sub(r1, r0), fy_s[r], r0);
+            out[(int64_t)r * dst_w] = v;
+            mn = fminf(mn, v), mx = fmaxf(mx, v);
+        }
+    }
+    if (minmax) warp_minmax_commit(mn, mx, minmax + 2 * plane);
+}
+
 extern "C" int rsx_resize_bilinear_f32(const float* d_src, int src_h_total, int src_w, int src_row0, int src_rows_avail, int64_t src_plane_stride,
                                        float* d_dst, int dst_h_total, int dst_w, int dst_row0, int dst_rows, int64_t dst_plane_stride, int n_planes,
                                        uint32_t* d_minmax, rsx_stream_t stream) {
     RSX_REQUIRE(d_src && d_dst && src_h_total >= 1 && src_w >= 1 && dst_h_total >= 1 && dst_w >= 1 && dst_rows >= 1 && n_planes >= 1,
                 "rsx_resize_bilinear_f32: bad arguments");
     const double scale_x = 1.0 / ((double)dst_w / (double)src_w), scale_y = 1.0 / ((double)dst_h_total / (double)src_h_total);
+    // source footprint of a 32 x 256 destination tile: (n - 1) * scale + 3 samples at most
+    if (rsx_option("resize_tiled", 1) && (RSZ_TR - 1) * scale_y + 3.0 <= RSZ_SR && (RSZ_TC - 1) * scale_x + 3.0 <= RSZ_SC) {
+        dim3 tgrid(ceil_div(dst_w, RSZ_TC), ceil_div(dst_rows, RSZ_TR), n_planes);
+        resize_bilinear_tile_kernel<<<tgrid, 256, 0, (cudaStream_t)stream>>>(d_src, src_h_total, src_w, src_row0, src_rows_avail, src_plane_stride, d_dst, dst_w,
+                                                                           dst_row0, dst_rows, dst_plane_stride, scale_x, scale_y, d_minmax);
+        return rsx_check_launch("resize_bilinear_tile");
+    }
     const int gx = ceil_div(dst_w, 256);
     const int rows_per_cta = 32;  // many small CTAs: tens of waves, so the last partial wave costs a few percent at most
     dim3 grid(gx, ceil_div(dst_rows, rows_per_cta), n_planes);

@@ -418,8 +418,9 @@ extern "C" int rsx_pca_build_lut_u16(const float* d_norm, const float* d_center,
 template <typename T, int B>
 __global__ void __launch_bounds__(256) pca_moments_kernel(const T* __restrict__ raster, int64_t n_px, const __grid_constant__ PcaParams<B> P,
                                                           double* __restrict__ scratch) {
-    using RT = RasterTiles<T, B, 3>;
     using MM = Moments<B>;
+    constexpr int MSUB = MM::NSPLIT > 1 ? 1 : 4;  // B > 8: one pixel group per thread and tile (small tiles, three CTAs per SM)
+    using RT = RasterTiles<T, B, 3, MSUB>;
     constexpr int PXT = RT::PXT;
     constexpr int NS = MM::NSPLIT;
     constexpr int TPP = 256 / NS;  // threads per part
@@ -435,29 +436,62 @@ __global__ void __launch_bounds__(256) pca_moments_kernel(const T* __restrict__ 
 #pragma unroll
     for (int i = 0; i < MM::NACC; ++i) acc[i] = 0.0;
 
-    for_each_tile<T, B, 3>(raster, n_px, smem, [&](const uint32_t* words, int64_t, int npx) {
-        for (int g = lt; g * PXT < npx; g += TPP) {
-            uint32_t w[B];
+    // B > 8 (NS = 4 thread groups share the 91 pair sums of 13 bands): the scaled values of a chunk of 256 * PXT pixels are
+    // computed ONCE by all threads into shared memory, planar [band][pixel]; each group then walks the chunk and accumulates its
+    // quarter of the pairs.  (Scaling a uint16 sample costs two float64 multiplications and five conversions: with every group
+    // scaling every pixel for itself the kernel spent 4/5 of its instructions there - 11.2 ms on the 120 Mpx x 13 tile.)
+    constexpr int CH = 256 * PXT;
+    float* xs = reinterpret_cast<float*>(smem + RT::SMEM_BYTES + 8 * MM::M * 8 + lut_bytes<T>(B));  // [B][CH], NS > 1 only
+    for_each_tile<T, B, 3, MSUB>(raster, n_px, smem, [&](const uint32_t* words, int64_t, int npx) {
+        if constexpr (NS == 1) {
+            for (int g = lt; g * PXT < npx; g += TPP) {
+                uint32_t w[B];
 #pragma unroll
-            for (int i = 0; i < B; ++i) w[i] = words[g * B + i];
-            int raw[PXT][B];
-            unpack_pixels<T, B>(w, raw);
+                for (int i = 0; i < B; ++i) w[i] = words[g * B + i];
+                int raw[PXT][B];
+                unpack_pixels<T, B>(w, raw);
 #pragma unroll
-            for (int p = 0; p < PXT; ++p) {
-                if (g * PXT + p < npx) {
-                    float x[B];
-                    scaled_pixel<T, B>(raw[p], P, lut_s, x);
-                    if (NS == 1) {
+                for (int p = 0; p < PXT; ++p) {
+                    if (g * PXT + p < npx) {
+                        float x[B];
+                        scaled_pixel<T, B>(raw[p], P, lut_s, x);
                         moments_accumulate<B, 0>(x, sum, acc);
-                    } else {
-                        switch (part) {
-                            case 0: moments_accumulate<B, 0>(x, sum, acc); break;
-                            case 1: moments_accumulate<B, 1 % NS>(x, sum, acc); break;
-                            case 2: moments_accumulate<B, 2 % NS>(x, sum, acc); break;
-                            default: moments_accumulate<B, 3 % NS>(x, sum, acc); break;
+                    }
+                }
+            }
+        } else {
+            for (int c0 = 0; c0 < npx; c0 += CH) {
+                const int n_ch = min(CH, npx - c0);
+                {
+                    const int g = c0 / PXT + threadIdx.x;  // this thread's pixel group of the chunk
+                    if (g * PXT < npx) {
+                        uint32_t w[B];
+#pragma unroll
+                        for (int i = 0; i < B; ++i) w[i] = words[g * B + i];
+                        int raw[PXT][B];
+                        unpack_pixels<T, B>(w, raw);
+#pragma unroll
+                        for (int p = 0; p < PXT; ++p) {
+                            float x[B];
+                            scaled_pixel<T, B>(raw[p], P, lut_s, x);
+#pragma unroll
+                            for (int b = 0; b < B; ++b) xs[b * CH + threadIdx.x * PXT + p] = x[b];
                         }
                     }
                 }
+                __syncthreads();
+                for (int px = lt; px < n_ch; px += TPP) {
+                    float x[B];
+#pragma unroll
+                    for (int b = 0; b < B; ++b) x[b] = xs[b * CH + px];
+                    switch (part) {
+                        case 0: moments_accumulate<B, 0>(x, sum, acc); break;
+                        case 1: moments_accumulate<B, 1 % NS>(x, sum, acc); break;
+                        case 2: moments_accumulate<B, 2 % NS>(x, sum, acc); break;
+                        default: moments_accumulate<B, 3 % NS>(x, sum, acc); break;
+                    }
+                }
+                __syncthreads();
             }
         }
     });
@@ -494,7 +528,7 @@ __global__ void pca_moments_finish_kernel(const double* __restrict__ scratch, in
     moments[m] += s;
 }
 
-static int pca_grid() { return rsx_num_sms(); }
+static int pca_grid() { return rsx_num_sms() * 4; }  // upper bound of the moments kernel's grid (the scratch is sized by it)
 extern "C" int64_t rsx_pca_scratch_elems(int n_bands) { return (int64_t)pca_grid() * (n_bands + n_bands * (n_bands + 1) / 2); }
 
 template <int B>
@@ -517,13 +551,16 @@ static int pca_moments_impl(const T* d_raster, int64_t n_px, int n_bands, const 
     RSX_REQUIRE(((uintptr_t)d_raster & 15) == 0, "rsx_pca_moments: raster must be 16-byte aligned");
 #define LAUNCH(BB)                                                                                                     \
     {                                                                                                                  \
-        using RT = RasterTiles<T, BB, 3>;                                                                              \
         using MM = Moments<BB>;                                                                                        \
+        using RT = RasterTiles<T, BB, 3, (MM::NSPLIT > 1 ? 1 : 4)>;                                                    \
         PcaParams<BB> P;                                                                                               \
         fill_pca_params<BB>(P, h_norm, h_center, h_scale, d_lut);                                                      \
-        int smem = RT::SMEM_BYTES + 8 * MM::M * 8 + lut_bytes<T>(BB);                                                  \
+        int smem = RT::SMEM_BYTES + 8 * MM::M * 8 + lut_bytes<T>(BB) + (MM::NSPLIT > 1 ? BB * 256 * RT::PXT * 4 : 0);  \
         if (int rc = set_smem(pca_moments_kernel<T, BB>, smem)) return rc;                                             \
-        int grid = (int)min((int64_t)pca_grid(), ceil_div(n_px, (int64_t)RT::TILE_PX));                                \
+        int per_sm = 1;                                                                                                \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pca_moments_kernel<T, BB>, 256, smem);                  \
+        per_sm = max(1, min(per_sm, MM::NSPLIT > 1 ? 4 : 1));                                                          \
+        int grid = (int)min((int64_t)rsx_num_sms() * per_sm, ceil_div(n_px, (int64_t)RT::TILE_PX));                    \
         pca_moments_kernel<T, BB><<<grid, 256, smem, (cudaStream_t)stream>>>(d_raster, n_px, P, d_scratch);            \
         if (int rc = rsx_check_launch("pca_moments")) return rc;                                                       \
         pca_moments_finish_kernel<<<ceil_div(MM::M, 128), 128, 0, (cudaStream_t)stream>>>(d_scratch, grid, MM::M, d_moments); \

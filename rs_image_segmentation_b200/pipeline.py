@@ -625,7 +625,8 @@ def segment_raster(raster_host: np.ndarray, cfg: FeatureConfig = FeatureConfig()
     """End-to-end call with HOST buffers: (h, W, B) uint8/uint16 numpy strip in, (h, W) int32 numpy labels out.
 
     Copies the strip to the device (pinned staging), runs extract_features + the fixed-iteration KMeans protocol,
-    copies the labels back.  Returns (labels, KMeansResult, FeatureResult)."""
+    copies the labels back.  Returns (labels, KMeansResult, FeatureResult); `labels` lives in a reusable host buffer that is
+    valid until the next call with a raster of the same size."""
     require_cuda()
     comm = comm or Comm()
     if pinned is None:
@@ -637,18 +638,45 @@ def segment_raster(raster_host: np.ndarray, cfg: FeatureConfig = FeatureConfig()
     fr = extract_features(dev_raster, cfg, comm, H_total, bounds, timer)
     D = stack_depth if stack_depth is not None else (13 if cfg.glcm else 7 + min(6, len(fr.names) - 7))
     first_row = bounds[comm.rank][0] if bounds is not None else 0
-    res, km, c0 = kmeans_on_features(fr, D, n_clusters, n_iter, seed, comm, H_total, first_row, True, timer)
-    # labels come back through page-locked memory (a pageable destination costs several times the copy itself)
-    if out_pinned is None or out_pinned.numel() != fr.n_px:
+    res, km, c0 = kmeans_on_features(fr, D, n_clusters, n_iter, seed, comm, H_total, first_row, False, timer)
+    # uint8 labels come back through page-locked memory (a pageable destination costs several times the copy itself) and are
+    # widened to the reference's int32 on the host (rsx_widen_u8_to_i32)
+    if out_pinned is None or out_pinned.numel() != fr.n_px or out_pinned.dtype != torch.uint8:
         out_pinned = _pinned_labels(fr.n_px)
     out_pinned.copy_(res.labels, non_blocking=True)
     torch.cuda.current_stream().synchronize()
-    labels = out_pinned.numpy().reshape(fr.H, fr.W)
-    return labels, res, fr
+    labels = _host_labels(fr.n_px)
+    threads = max(1, min(8, (os.cpu_count() or 8) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", comm.world)))))
+    _lib.call("rsx_widen_u8_to_i32", C.c_void_p(out_pinned.data_ptr()), hptr(labels), fr.n_px, threads)
+    return labels.reshape(fr.H, fr.W), res, fr
 
 
 _PINNED_LABELS = {}
 _PINNED_F64 = {}
+_STREAM_LABELS = {}
+_HOST_LABELS = {}
+
+
+def _stream_label_buffers(n: int):
+    """Three page-locked uint8 download buffers + three int32 host arrays for segment_stream (scene i is widened by a worker while
+    scene i-1 is with the caller and scene i-2 may still be referenced), kept between calls (first-touch page faults of a fresh
+    196 MB array cost more than the widening itself)."""
+    bufs = _STREAM_LABELS.get(n)
+    if bufs is None:
+        _STREAM_LABELS.clear()
+        out8 = [torch.empty(n, dtype=torch.uint8, pin_memory=True) for _ in range(3)]
+        out = [np.zeros(n, dtype=np.int32) for _ in range(3)]
+        bufs = _STREAM_LABELS[n] = (out8, out)
+    return bufs
+
+
+def _host_labels(n: int) -> np.ndarray:
+    """Reusable int32 host array for segment_raster's result (valid until the next call of the same size)."""
+    buf = _HOST_LABELS.get(n)
+    if buf is None:
+        _HOST_LABELS.clear()
+        buf = _HOST_LABELS[n] = np.zeros(n, dtype=np.int32)
+    return buf
 
 
 def _pinned_f64(n: int) -> torch.Tensor:
@@ -660,11 +688,11 @@ def _pinned_f64(n: int) -> torch.Tensor:
 
 
 def _pinned_labels(n: int) -> torch.Tensor:
-    """Reusable page-locked int32 staging buffer for the label image (valid until the next call of the same size)."""
+    """Reusable page-locked uint8 staging buffer for the label image (valid until the next call of the same size)."""
     buf = _PINNED_LABELS.get(n)
     if buf is None:
         _PINNED_LABELS.clear()
-        buf = _PINNED_LABELS[n] = torch.empty(n, dtype=torch.int32, pin_memory=True)
+        buf = _PINNED_LABELS[n] = torch.empty(n, dtype=torch.uint8, pin_memory=True)
     return buf
 
 
@@ -672,11 +700,12 @@ def segment_stream(rasters, cfg: FeatureConfig = FeatureConfig(), n_clusters: in
                    stack_depth: Optional[int] = None, comm: Optional[Comm] = None, H_total: Optional[int] = None,
                    bounds: Optional[Sequence[Tuple[int, int]]] = None):
     """Pipelined end-to-end path for a sequence of scenes (or of this rank's strips of them), all of one shape: an iterable of
-    page-locked host rasters in, a generator of (labels (h, W) int32 numpy, KMeansResult) out, in order.
+    page-locked host rasters in, a generator of (labels (h, W) int32 numpy, KMeansResult) out, in order (KMeansResult.labels is
+    the uint8 device plane here).
 
     The host-to-device copy of scene i+1 and the device-to-host copy of the labels of scene i-1 run on their own streams
     (the two copy engines) under the kernels of scene i, so a step costs max(compute, copies) instead of their sum.
-    A yielded label array lives in one of two page-locked buffers: it is valid until two more scenes have been yielded."""
+    A yielded label array lives in one of three reusable host buffers: it is valid until two more scenes have been yielded."""
     require_cuda()
     comm = comm or Comm()
     compute = torch.cuda.current_stream()
@@ -694,10 +723,27 @@ def segment_stream(rasters, cfg: FeatureConfig = FeatureConfig(), n_clusters: in
         return
     first = as_pinned(first)
     dev = [torch.empty(first.shape, dtype=first.dtype, device="cuda") for _ in range(2)]       # double-buffered device rasters
-    out = [torch.empty(first.shape[0] * first.shape[1], dtype=torch.int32, pin_memory=True) for _ in range(2)]
+    n_lab = first.shape[0] * first.shape[1]
+    # labels leave the device as uint8 (a quarter of the int32 bytes over PCIe) and are widened into the int32 array the
+    # reference's callers expect (extract.py:577) by a few host threads while the next scene's kernels run
+    out8, out = _stream_label_buffers(n_lab)
+    widen_threads = max(1, min(8, (os.cpu_count() or 8) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", comm.world)))))
+
+    import threading
+
+    def start_widen(k):
+        """Worker: waits for the uint8 download of slot k and widens it into out[k], off the launching thread's critical path
+        (both the event wait and the C call release the GIL)."""
+        def run():
+            downloaded[k].synchronize()
+            _lib.call("rsx_widen_u8_to_i32", C.c_void_p(out8[k].data_ptr()), hptr(out[k]), n_lab, widen_threads)
+        th = threading.Thread(target=run, daemon=True)
+        th.start()
+        return th
+
     uploaded = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]       # compute no longer reads dev[k]
-    downloaded = [torch.cuda.Event() for _ in range(2)]
+    downloaded = [torch.cuda.Event() for _ in range(3)]
 
     # The copy engines serve one transfer at a time, in order: nothing small may queue there while a scene is being computed.
     # Every per-scene read-back (histograms, moments, min/max, KMeans state) is therefore a kernel store into page-locked
@@ -723,22 +769,29 @@ def segment_stream(rasters, cfg: FeatureConfig = FeatureConfig(), n_clusters: in
         fr = extract_features(dev[k], cfg, comm, H_total, bounds)
         D = stack_depth if stack_depth is not None else (13 if cfg.glcm else 7 + min(6, len(fr.names) - 7))
         first_row = bounds[comm.rank][0] if bounds is not None else 0
-        res, km, c0 = kmeans_on_features(fr, D, n_clusters, n_iter, seed, comm, H_total, first_row, True)
+        res, km, c0 = kmeans_on_features(fr, D, n_clusters, n_iter, seed, comm, H_total, first_row, False)
         consumed[k].record(compute)
         done = torch.cuda.Event()
         done.record(compute)
-        if pending is not None:                             # hand out scene i-1 (its download overlapped this scene's kernels)
-            pk, pres, ph, pw = pending
-            downloaded[pk].synchronize()
-            yield out[pk].numpy().reshape(ph, pw), pres
+        slot = i % 3
         with torch.cuda.stream(down):
             down.wait_event(done)
-            out[k].copy_(res.labels, non_blocking=True)
-            downloaded[k].record(down)
+            out8[slot].copy_(res.labels, non_blocking=True)
+            downloaded[slot].record(down)
         res.labels.record_stream(down)
-        pending = (k, res, fr.H, fr.W)
+        worker = start_widen(slot)
+        if pending is not None:                             # hand out scene i-1 (its download and widening overlapped this scene)
+            pk, pres, ph, pw, pth = pending
+            pth.join()
+            yield out[pk].reshape(ph, pw), pres
+        pending = (slot, res, fr.H, fr.W, worker)
         cur = nxt
         i += 1
-    pk, pres, ph, pw = pending
-    downloaded[pk].synchronize()
-    yield out[pk].numpy().reshape(ph, pw), pres
+    pk, pres, ph, pw, pth = pending
+    pth.join()
+    yield out[pk].reshape(ph, pw), pres
+
+
+def segment_stream_d2h_bytes(n_px: int) -> int:
+    """Bytes per scene that segment_stream copies from the device to the host (uint8 labels)."""
+    return int(n_px)

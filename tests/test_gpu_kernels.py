@@ -275,7 +275,7 @@ def _moments(rsx, q, L, win, step):
     return mom.cpu().numpy().reshape(oh, ow, 4, 8), props[:, : oh * ow].reshape(5, oh, ow).cpu().numpy()
 
 
-@pytest.mark.parametrize("fold", [0, 1])
+@pytest.mark.parametrize("fold", [0, 1, 8, 16])
 @pytest.mark.parametrize("L", [16, 32, 64])
 @pytest.mark.parametrize("win", [5, 7, 11])
 def test_glcm_production_kernel_integer_stage_is_exact(rsx, L, win, fold):
@@ -287,11 +287,15 @@ def test_glcm_production_kernel_integer_stage_is_exact(rsx, L, win, fold):
     q = _texture_image(97, 141, L, 7 * L + win)
     q[:30, :40] = 5
     q[60:, 100:] = np.random.default_rng(L + win).integers(0, L, size=(37, 41))        # wide level spans (flagged windows when folded)
-    _lib.set_option("glcm_fold", fold)
+    # fold: 0 = unfolded counters, 1 = chosen on the device from the span statistics, 8 / 16 = forced (every window whose levels
+    # span more than the fold goes through the energy patch kernel)
+    _lib.set_option("glcm_fold", 1 if fold else 0)
+    _lib.set_option("glcm_fold_force", fold if fold > 1 else -1)
     try:
         got, props = _moments(rsx, q, L, win, 1)
     finally:
-        _lib.set_option("glcm_fold", 0)
+        _lib.set_option("glcm_fold", 1)
+        _lib.set_option("glcm_fold_force", -1)
     ref = og.pair_moments(q, L, win, 1)
     for f, name in enumerate(og.MOMENT_FIELDS):
         assert np.array_equal(got[..., f], ref[..., f]), name

@@ -16,8 +16,8 @@ from rs_image_segmentation_b200.device import StageTimer
 from rs_image_segmentation_b200.synth import synth_strip_torch
 
 size = int(sys.argv[1]) if len(sys.argv) > 1 else 7000
-variants = sys.argv[2:] or ["base:glcm_fold=0", "fold128:glcm_fold=1,glcm_fold_nt=128", "fold256:glcm_fold=1,glcm_fold_nt=256",
-                            "fold64:glcm_fold=1,glcm_fold_nt=64"]
+variants = sys.argv[2:] or ["base:glcm_fold=0", "auto64:glcm_fold=1,glcm_fold_nt=64,glcm_fold_force=-1", "auto32:glcm_fold=1,glcm_fold_nt=32,glcm_fold_force=-1",
+                            "force8:glcm_fold=1,glcm_fold_nt=64,glcm_fold_force=8", "force16:glcm_fold=1,glcm_fold_nt=64,glcm_fold_force=16"]
 
 
 def run(raster, cfg, reps=3):
