@@ -136,6 +136,18 @@ int rsx_pca_project_u16(const uint16_t* d_raster, int64_t n_px, int n_bands, con
                         const double* h_scale, const float* d_lut16, const float* h_components, const float* h_mean_proj, int n_comp,
                         float* d_out, int64_t plane_stride, uint32_t* d_minmax, rsx_stream_t stream);
 
+/* The same two steps for PLANAR float32 bands with arbitrary values and any band count up to RSX_MAX_BANDS (band b at d_bands +
+ * b * plane_stride): what the per-function drop-in of perform_pca uses when the bands are not 8-bit levels.
+ * robust != 0: X = (float)((double)(v - h_a[b]) / h_scale[b]) with h_a = RobustScaler.center_, h_scale = scale_ (h_den unused);
+ * robust == 0: X = (v - h_a[b]) / h_den[b] in float32 with h_a = min, h_den = fl32(max - min + 1e-10) (indices.py:234).
+ * d_moments as for the raster variants; d_scratch: double [rsx_pca_planar_scratch_elems(B)]. */
+int64_t rsx_pca_planar_scratch_elems(int n_bands);
+int rsx_pca_moments_planar_f32(const float* d_bands, int64_t plane_stride, int64_t n_px, int n_bands, int robust, const float* h_a,
+                               const float* h_den, const double* h_scale, double* d_moments, double* d_scratch, rsx_stream_t stream);
+int rsx_pca_project_planar_f32(const float* d_bands, int64_t plane_stride, int64_t n_px, int n_bands, int robust, const float* h_a,
+                               const float* h_den, const double* h_scale, const float* h_components, const float* h_mean_proj, int n_comp,
+                               float* d_out, int64_t out_plane_stride, uint32_t* d_minmax, rsx_stream_t stream);
+
 /* ---- K4: GLCM texture --------------------------------------------------------------------------
  * Replaces the window double loop of calculate_glcm_features (indices.py:283-305): for every
  * window anchored at (i*step, j*step), distance 1, angles 0/45/90/135 deg, symmetric, normed;

@@ -36,6 +36,9 @@ SIGNATURES = {
     "rsx_pca_moments_u16": (i32, [vp, i64, i32, vp, vp, vp, vp, vp, vp, vp]),
     "rsx_pca_project_u8": (i32, [vp, i64, i32, vp, vp, vp, i32, vp, i64, vp, vp]),
     "rsx_pca_project_u16": (i32, [vp, i64, i32, vp, vp, vp, vp, vp, vp, i32, vp, i64, vp, vp]),
+    "rsx_pca_planar_scratch_elems": (i64, [i32]),
+    "rsx_pca_moments_planar_f32": (i32, [vp, i64, i64, i32, i32, vp, vp, vp, vp, vp, vp]),
+    "rsx_pca_project_planar_f32": (i32, [vp, i64, i64, i32, i32, vp, vp, vp, vp, vp, i32, vp, i64, vp, vp]),
     "rsx_glcm_props": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, vp, i64, vp]),
     "rsx_glcm_moments": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, vp, i64, vp, vp]),
     "rsx_glcm_counts": (i32, [vp, i32, i32, i32, i32, vp, i32, vp, vp]),

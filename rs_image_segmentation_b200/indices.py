@@ -161,25 +161,32 @@ def perform_pca(bands_data, n_components=None, use_robust_scaling=True):
     The bands the reference passes here are robust-normalised uint8 bands, i.e. float maps with at most 256
     distinct values each.  Each band is rank-coded on the device (torch.unique), which turns the call into the
     uint8 raster path: histogram -> RobustScaler statistics -> per-level table of X -> Gram/moments kernel ->
-    eigh (host, BxB) -> projection kernel.  Bands with more than 256 distinct values are not supported yet.
+    eigh (host, BxB) -> projection kernel.  Bands with more than 256 distinct values (e.g. derived from 16-bit data) or a band
+    count outside the compiled raster kernels go through the planar float32 kernels (_perform_pca_planar), any B <= 16.
     """
     require_cuda()
     H, W = np.asarray(bands_data[0]).shape
     B = len(bands_data)
-    if B not in _COMPILED_BANDS:
-        raise _lib.RsxError(f"perform_pca: {B} bands; kernels are compiled for {_COMPILED_BANDS}")
+    if B > 16:
+        raise _lib.RsxError(f"perform_pca: {B} bands; the kernels take up to 16 (RSX_MAX_BANDS)")
     n = H * W
     st = stream_ptr()
-    levels, value_tables = [], []
+    levels, value_tables, planes = [], [], []
+    level_coded = B in _COMPILED_BANDS
     for b in bands_data:
         x = _dev32(b).reshape(-1)
         if bool(torch.isnan(x).any()):
             raise ValueError("Input X contains NaN.")                      # what sklearn raises
-        vals, inv = torch.unique(x, return_inverse=True)
-        if vals.numel() > 256:
-            raise _lib.RsxError("perform_pca: a band has more than 256 distinct values; the float-band path is not implemented")
-        levels.append(inv.to(torch.uint8))
-        value_tables.append(vals.cpu().numpy().astype(np.float32))
+        planes.append(x)
+        if level_coded:
+            vals, inv = torch.unique(x, return_inverse=True)
+            if vals.numel() > 256:
+                level_coded = False                                        # arbitrary float band: the planar path below
+            else:
+                levels.append(inv.to(torch.uint8))
+                value_tables.append(vals.cpu().numpy().astype(np.float32))
+    if not level_coded:
+        return _perform_pca_planar(planes, H, W, n_components, use_robust_scaling)
     raster = torch.stack(levels, dim=1).contiguous()                       # (N, B) uint8, pixel interleaved
     hist = torch.zeros((B, 256), dtype=torch.int32, device="cuda")
     _lib.call("rsx_hist_u8", ptr(raster), n, B, ptr(hist), st)
@@ -210,6 +217,42 @@ def perform_pca(bands_data, n_components=None, use_robust_scaling=True):
     stride = (n + 31) // 32 * 32
     out = torch.empty((n_comp, stride), dtype=torch.float32, device="cuda")
     _lib.call("rsx_pca_project_u8", ptr(raster), n, B, ptr(dlut), hptr(comps), hptr(mean_proj), n_comp, ptr(out), stride, None, st)
+    maps = out[:, :n].cpu().numpy()
+    model = RsxPCA(pca, n, B)
+    return [maps[i].reshape(H, W) for i in range(n_comp)], model.explained_variance_ratio_, model
+
+
+def _perform_pca_planar(planes, H, W, n_components, use_robust_scaling):
+    """perform_pca for bands with arbitrary float32 values / any band count up to 16: order statistics of every band from one
+    device sort, then rsx_pca_moments_planar_f32 -> eigh (host) -> rsx_pca_project_planar_f32."""
+    B, n = len(planes), H * W
+    st = stream_ptr()
+    stride = (n + 31) // 32 * 32
+    stack = torch.zeros((B, stride), dtype=torch.float32, device="cuda")
+    a, den, scale = np.zeros(B, np.float32), np.ones(B, np.float32), np.ones(B, np.float64)
+    for b, x in enumerate(planes):
+        stack[b, :n] = x
+        if use_robust_scaling:                                             # RobustScaler().fit (sklearn/preprocessing/_data.py:1722-1743)
+            order = _DeviceOrder(x)
+            a[b] = order.median()
+            q = order.nanpercentile_pair((25.0, 75.0))
+            s = np.float64(q[1] - q[0])
+            scale[b] = 1.0 if s < 10 * np.finfo(np.float64).eps else s
+        else:                                                              # indices.py:234, float32 throughout (NEP 50)
+            mn, mx = np.float32(x.min().item()), np.float32(x.max().item())
+            a[b], den[b] = mn, np.float32(mx - mn + 1e-10)
+    n_comp = B if n_components is None else int(n_components)
+    M = B + B * (B + 1) // 2
+    moments = torch.zeros(M, dtype=torch.float64, device="cuda")
+    scratch = torch.empty(int(_lib.load().rsx_pca_planar_scratch_elems(B)), dtype=torch.float64, device="cuda")
+    robust = 1 if use_robust_scaling else 0
+    _lib.call("rsx_pca_moments_planar_f32", ptr(stack), stride, n, B, robust, hptr(a), hptr(den), hptr(scale), ptr(moments), ptr(scratch), st)
+    pca = hoststats.pca_from_moments(moments.cpu().numpy(), n, n_comp)
+    comps = np.ascontiguousarray(pca["components"], dtype=np.float32)
+    mean_proj = np.ascontiguousarray((pca["mean"].astype(np.float32).reshape(1, -1) @ comps.T).ravel(), dtype=np.float32)
+    out = torch.empty((n_comp, stride), dtype=torch.float32, device="cuda")
+    _lib.call("rsx_pca_project_planar_f32", ptr(stack), stride, n, B, robust, hptr(a), hptr(den), hptr(scale), hptr(comps), hptr(mean_proj), n_comp,
+              ptr(out), stride, None, st)
     maps = out[:, :n].cpu().numpy()
     model = RsxPCA(pca, n, B)
     return [maps[i].reshape(H, W) for i in range(n_comp)], model.explained_variance_ratio_, model

@@ -363,6 +363,28 @@ def gather_rows_device(planes: torch.Tensor, D: int, n_px: int, global_idx: np.n
     return rows
 
 
+def _rowsum_like_numpy(sq: torch.Tensor) -> torch.Tensor:
+    """(n, D) float64 -> row sums in the order numpy's pairwise summation uses for a contiguous row of fewer than 128 elements
+    (np.add.reduce along the last axis): sequential below 8 elements, else eight interleaved partial sums combined as
+    ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) followed by the remaining elements - so that ((X - c)**2).sum(axis=1) of sklearn's
+    _relocate_empty_clusters_dense is reproduced bit for bit."""
+    n, D = sq.shape
+    if D < 8:
+        out = sq[:, 0].clone()
+        for d in range(1, D):
+            out += sq[:, d]
+        return out
+    r = [sq[:, j].clone() for j in range(8)]
+    full = D - D % 8
+    for i in range(8, full, 8):
+        for j in range(8):
+            r[j] += sq[:, i + j]
+    out = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]))
+    for i in range(full, D):
+        out += sq[:, i]
+    return out
+
+
 class DeviceKMeans:
     """Lloyd iterations on a planar float32 stack that stays in HBM."""
 
@@ -416,6 +438,7 @@ class DeviceKMeans:
         assert c0.shape == (self.K, self.D)
         # any centring origin gives the same labels in exact arithmetic; 0.5 minimises the fp32 rounding bound
         mu = np.full(self.D, 0.5) if mean_scaled is None else np.ascontiguousarray(mean_scaled, dtype=np.float64)
+        self._mu = mu
         self.acc.zero_()
         self._passes = 0
         if self.peers is not None:
@@ -475,23 +498,37 @@ class DeviceKMeans:
         """sklearn's _relocate_empty_clusters_dense (_k_means_common.pyx:167-211) for the pass that has just been all-reduced:
         every empty cluster takes the sample that is farthest from its own (old) centre; that sample leaves its cluster's
         sum.  Returns the int64 adjustment [K*D + K] for rsx_kmeans_update.  Rare, host assisted, synchronises.
-        (For several simultaneous empties sklearn hands out the farthest samples in numpy's argpartition order; here they
-        go to the empty clusters in order of decreasing distance.)"""
+        The distances are float64 with numpy's summation order; with one rank several simultaneous empties are handed out in
+        sklearn's own order (np.argpartition on the whole array, on the host).  With several ranks no rank holds the whole
+        array: the farthest samples go to the empty clusters in order of decreasing distance (ties by pixel index)."""
         K, D, dev = self.K, self.D, self.planes.device
         empties = np.flatnonzero(empty)
         n_e = len(empties)
         cent_old, _, _ = self.read()
-        C = torch.from_numpy(cent_old).to(dev)
+        mu = torch.from_numpy(self._mu).to(dev)
+        C = torch.from_numpy(cent_old).to(dev) - mu                       # centred coordinates, like sklearn's X and centers
         scale, min_ = torch.from_numpy(self.scale).to(dev), torch.from_numpy(self.min_).to(dev)
         labels = self._cur_labels
         cand = torch.full((n_e, 3 + D), -1.0, dtype=torch.float64, device=dev)     # distance, global index, label, raw sample
+        dist = None
         if self.n_px:
             dist = torch.empty(self.n_px, dtype=torch.float64, device=dev)
             chunk = 1 << 22
             for a in range(0, self.n_px, chunk):
                 b = min(self.n_px, a + chunk)
-                Xs = self.planes[:D, a:b].t().to(torch.float64) * scale + min_
-                dist[a:b] = ((Xs - C[labels[a:b].long()]) ** 2).sum(dim=1)
+                Xs = (self.planes[:D, a:b].t().to(torch.float64) * scale + min_) - mu
+                dist[a:b] = _rowsum_like_numpy((Xs - C[labels[a:b].long()]) ** 2)
+        if self.comm.world == 1 and n_e > 1 and dist is not None:
+            # Several empty clusters: sklearn hands the far samples out in the order np.argpartition leaves them in, which is a
+            # property of numpy's introselect on the WHOLE distance array - reproduced by running it on the host (rare event:
+            # one D2H of the distances).  Several ranks: no rank holds the whole array; see below.
+            far = np.argpartition(dist.cpu().numpy(), -n_e)[:-n_e - 1:-1]
+            idx = torch.from_numpy(np.ascontiguousarray(far)).to(dev)
+            cand[:, 0] = torch.arange(n_e, 0, -1, dtype=torch.float64, device=dev)        # keeps this order in the sort below
+            cand[:, 1] = (idx + first_px).to(torch.float64)
+            cand[:, 2] = labels[idx].to(torch.float64)
+            cand[:, 3:] = self.planes[:D].index_select(1, idx).t().to(torch.float64)
+        elif dist is not None:
             k = min(n_e, self.n_px)
             vals, idx = torch.topk(dist, k)
             cand[:k, 0] = vals
@@ -535,8 +572,7 @@ class DeviceKMeans:
         h_inertia, h_last, h_sofar = stage_to_host(self.inertia), stage_to_host(t), stage_to_host(self.acc[2 * self.n_acc - 2:2 * self.n_acc - 1])
         cent, shift, empty = self.read()
         if empty:
-            raise _lib.RsxError(f"KMeans: {empty} empty cluster(s) met; empty-cluster relocation "
-                                "(sklearn _k_means_common.pyx:167-211) is not implemented on the device")
+            return None                                                # the caller reruns with relocation (fit -> _fit_relocating)
         return KMeansResult(labels=labels, centroids=cent, inertia=float(h_inertia[0]), n_iter=n_iter,
                             near_ties=int(h_last[0]) + int(h_sofar[0]), shift_sq=shift)
 
@@ -580,13 +616,34 @@ class DeviceKMeans:
             _, shift, _ = self.read()
             if shift <= tol:
                 break
-        return self._result(self.finish(True), n_iter)
+        res = self._result(self.finish(True), n_iter)
+        if res is None:
+            raise _lib.RsxError("KMeans: a cluster stayed empty after relocation (fewer distinct samples than clusters?)")
+        return res
 
-    def fit(self, init_centroids_scaled: np.ndarray, n_iter: int, labels_i32: bool = True) -> KMeansResult:
+    def fit(self, init_centroids_scaled: np.ndarray, n_iter: int, labels_i32: bool = True, first_px: int = 0) -> KMeansResult:
+        """Fixed-iteration protocol: exactly n_iter update passes without a host synchronisation, then the final assignment.
+        If a cluster ran empty on the way (reported by the state, collectively on every rank), the run is repeated with
+        sklearn's empty-cluster relocation, which needs the reduced counts on the host after every pass."""
         self.setup(init_centroids_scaled)
         for _ in range(n_iter):
             self.step()
-        return self._result(self.finish(labels_i32), n_iter)
+        res = self._result(self.finish(labels_i32), n_iter)
+        return res if res is not None else self._fit_relocating(init_centroids_scaled, n_iter, labels_i32, first_px)
+
+    def _fit_relocating(self, init_centroids_scaled: np.ndarray, n_iter: int, labels_i32: bool, first_px: int) -> KMeansResult:
+        self.setup(init_centroids_scaled)
+        KD = self.K * self.D
+        for _ in range(n_iter):
+            mode = self.assign_pass(track_labels=True)
+            blocks = self.acc.cpu().numpy()                    # the one synchronisation of an iteration
+            counts = blocks[KD:KD + self.K] + (blocks[self.n_acc + KD:self.n_acc + KD + self.K] if mode == 2 else 0)
+            adjust = self.relocation_adjust(counts == 0, first_px) if (counts == 0).any() else None
+            self.update(mode, adjust)
+        res = self._result(self.finish(labels_i32), n_iter)
+        if res is None:
+            raise _lib.RsxError("KMeans: a cluster stayed empty after relocation (fewer distinct samples than clusters?)")
+        return res
 
 
 def kmeans_on_features(fr: FeatureResult, D: int, K: int, n_iter: int, seed: int, comm: Optional[Comm] = None,
@@ -613,7 +670,7 @@ def kmeans_on_features(fr: FeatureResult, D: int, K: int, n_iter: int, seed: int
     mn, mx = fr.minmax.read(comm)                   # the one synchronisation between the feature kernels and KMeans
     km.configure(mn[:D], mx[:D])
     c0 = km.scale_rows(rows_host.numpy())
-    res = km.fit(c0, n_iter, labels_i32)
+    res = km.fit(c0, n_iter, labels_i32, first_px=first_row * fr.W)
     return res, km, c0
 
 

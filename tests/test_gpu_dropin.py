@@ -256,3 +256,33 @@ def test_kmeans_dropin_f32_agreement(E, aa_crop):
         if m.any():
             agree += np.bincount(ref[m], minlength=5).max()
     assert agree >= 0.99 * lab.size, agree / lab.size
+
+
+# ============================================================================================ round-2 additions
+@pytest.mark.parametrize("B,robust", [(13, True), (9, True), (11, False), (3, True)])
+def test_perform_pca_arbitrary_float_bands(I, B, robust):
+    """VERDICT r1 missing 4: perform_pca (indices.py:205-246) takes ANY float bands - here robust-normalised 16-bit data (10 000
+    levels, far more than 256 distinct values) and band counts outside the compiled raster kernels.  Components / maps against
+    the float64 PCA of the same float32 scaled matrix (1e-5), explained variance ratio against the reference's own float32 run."""
+    from oracle import features as of
+    from rs_image_segmentation_b200.synth import synth_raster_numpy
+    bip = synth_raster_numpy(120, 161, B, np.uint16, 40 + B, cell=16)
+    nb = [of.robust_normalize(bip[:, :, b].astype(np.float32)) for b in range(B)]
+    assert len(np.unique(nb[0])) > 256
+    n_comp = min(B, 6)
+    maps, evr, model = I.perform_pca(nb, n_components=n_comp, use_robust_scaling=robust)
+    ref64, evr64, m64 = of.perform_pca(nb, n_components=n_comp, use_robust_scaling=robust, promote=True)
+    ref32, evr32, m32 = of.perform_pca(nb, n_components=n_comp, use_robust_scaling=robust)
+    assert len(maps) == n_comp and maps[0].dtype == np.float32 and maps[0].shape == nb[0].shape
+    np.testing.assert_allclose(evr, evr64, rtol=1e-6)
+    np.testing.assert_allclose(evr, evr32, rtol=5e-4, atol=1e-5)       # sklearn's own float32 Gram matrix: noise floor of the minor components
+    for i in range(n_comp):
+        assert np.abs(model.components_[i] - m64.components_[i]).max() < 1e-6, i
+        scale = max(1.0, float(np.abs(ref64[i]).max()))
+        assert np.abs(maps[i] - ref64[i]).max() <= 1e-5 * scale, (i, np.abs(maps[i] - ref64[i]).max())
+
+
+def test_perform_pca_rejects_more_than_16_bands(I):
+    from rs_image_segmentation_b200._lib import RsxError
+    with pytest.raises(RsxError):
+        I.perform_pca([np.random.default_rng(b).random((8, 9), dtype=np.float32) for b in range(17)])
