@@ -157,6 +157,11 @@ int rsx_pca_project_planar_f32(const float* d_bands, int64_t plane_stride, int64
  * d_props:  5 planes [out_rows][out_cols], plane stride in elements. */
 int rsx_glcm_props(const uint8_t* d_q, int rows_avail, int W, int levels, int window, int step, int out_rows, int out_cols,
                    float* d_props, int64_t plane_stride, rsx_stream_t stream);
+/* The same for an arbitrary list of pair offsets: h_offsets int32 [n_offsets][2] = (round(sin(angle)*d), round(cos(angle)*d)) for
+ * every (distance, angle) the caller of calculate_glcm_features asked for (indices.py:248-249,288-289); the properties are
+ * averaged over all of them (.mean() of the graycoprops array).  1 <= n_offsets <= 16; general kernel (one warp per window). */
+int rsx_glcm_props_offsets(const uint8_t* d_q, int rows_avail, int W, int levels, int window, int step, int out_rows, int out_cols,
+                           const int32_t* h_offsets, int n_offsets, float* d_props, int64_t plane_stride, rsx_stream_t stream);
 /* rsx_glcm_props with the same kernels ALSO storing, for every window and angle, the exact integers the five properties are
  * made from (validation of the production kernel's integer stage against graycomatrix counts, bit for bit):
  * d_moments int64 [out_rows*out_cols][4][8] = n (pair instances), sum|a-b|, sum(a+b), sum(a^2+b^2), sum(a*b),
@@ -278,7 +283,8 @@ int rsx_kmeans_update(void* d_state, int64_t* d_acc, int delta, int D, const int
  * block at int64 offset (seq & 1) * RSX_PEER_PASS_ELEMS (pass it as d_acc of rsx_kmeans_assign); rsx_kmeans_update_peers then
  * waits for all ranks at a flag barrier in peer memory, sums their blocks over NVLink into d_acc's pass block and continues
  * as rsx_kmeans_update (d_acc = the local [pass | totals] array).  h_peer_blocks: HOST array of `world` device pointers
- * (own block at [rank]).  A rank that never arrives makes the others time out after 4 s (reported by rsx_kmeans_read). */
+ * (own block at [rank]).  A rank that never arrives makes the others time out after 4 s (option peer_timeout_ms; reported by
+ * rsx_kmeans_read - the caller must then fail on every rank, pipeline.DeviceKMeans._result all-reduces the failure). */
 int rsx_peer_alloc(int64_t bytes, void** d_ptr, uint8_t* h_handle64);
 int rsx_peer_open(const uint8_t* h_handle64, void** d_peer);
 int rsx_peer_zero(void* d_ptr, int64_t bytes, rsx_stream_t stream);   /* before a new rsx_kmeans_setup: the two pass buffers */

@@ -118,14 +118,14 @@ def window_counts(q, i, j, window, levels, angles=DEFAULT_ANGLES):
     return graycomatrix(q[i:i + window, j:j + window], (1,), angles, levels)[:, :, 0, :]
 
 
-def props_map_numpy(q, levels, window, step, angles=DEFAULT_ANGLES):
+def props_map_numpy(q, levels, window, step, angles=DEFAULT_ANGLES, distances=(1,)):
     """indices.py:270-305 - the Python double loop, one graycomatrix per window."""
     H, W = q.shape
     oh, ow = (H - window) // step + 1, (W - window) // step + 1
     out = np.zeros((5, oh, ow), dtype=np.float32)
     for i in range(0, H - window + 1, step):
         for j in range(0, W - window + 1, step):
-            P = graycomatrix(q[i:i + window, j:j + window], (1,), angles, levels, symmetric=True, normed=True)
+            P = graycomatrix(q[i:i + window, j:j + window], distances, angles, levels, symmetric=True, normed=True)
             for k, name in enumerate(PROPS):
                 out[k, i // step, j // step] = graycoprops(P, name).mean()
     return out

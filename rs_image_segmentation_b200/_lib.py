@@ -40,6 +40,7 @@ SIGNATURES = {
     "rsx_pca_moments_planar_f32": (i32, [vp, i64, i64, i32, i32, vp, vp, vp, vp, vp, vp]),
     "rsx_pca_project_planar_f32": (i32, [vp, i64, i64, i32, i32, vp, vp, vp, vp, vp, i32, vp, i64, vp, vp]),
     "rsx_glcm_props": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, vp, i64, vp]),
+    "rsx_glcm_props_offsets": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp, i64, vp]),
     "rsx_glcm_moments": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, vp, i64, vp, vp]),
     "rsx_glcm_counts": (i32, [vp, i32, i32, i32, i32, vp, i32, vp, vp]),
     "rsx_resize_bilinear_f32": (i32, [vp, i32, i32, i32, i32, i64, vp, i32, i32, i32, i32, i64, i32, vp, vp]),

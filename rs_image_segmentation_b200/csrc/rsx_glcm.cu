@@ -59,9 +59,21 @@ __device__ __forceinline__ void angle_props(const AngleSums& t, int n, double (&
 // ----------------------------------------------------------------------------- general kernel: one warp per window
 // Any window/step/levels.  The histogram of unordered cells lives in the warp's slice of shared memory and is
 // cleaned by revisiting only the touched cells, so the cost per window is O(pairs), not O(levels^2).
+struct GlcmOffsets {  // (row, column) offsets of the co-occurrence pairs: round(sin(angle) * d), round(cos(angle) * d) per (distance, angle)
+    int n;
+    int dr[16], dc[16];
+};
+static GlcmOffsets default_offsets() {
+    GlcmOffsets o;
+    o.n = 4;
+    const int dr[4] = {0, 1, 1, 1}, dc[4] = {1, 1, 0, -1};
+    for (int i = 0; i < 16; ++i) o.dr[i] = i < 4 ? dr[i] : 0, o.dc[i] = i < 4 ? dc[i] : 0;
+    return o;
+}
+
 __global__ void __launch_bounds__(128) glcm_props_warp_kernel(const uint8_t* __restrict__ q, int W, int L, int win, int step, int out_rows,
                                                               int out_cols, float* __restrict__ props, int64_t plane_stride,
-                                                              long long* __restrict__ moments) {
+                                                              long long* __restrict__ moments, const __grid_constant__ GlcmOffsets offs) {
     extern __shared__ unsigned glcm_sm[];
     const int ncell = L * (L + 1) / 2;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -75,18 +87,23 @@ __global__ void __launch_bounds__(128) glcm_props_warp_kernel(const uint8_t* __r
         const uint8_t* base = q + (int64_t)oi * step * W + (int64_t)oj * step;
         double acc[5] = {0, 0, 0, 0, 0};
 #pragma unroll 1
-        for (int ang = 0; ang < 4; ++ang) {
-            const int dr = ang == 0 ? 0 : 1;
-            const int dc = ang == 0 ? 1 : (ang == 1 ? 1 : (ang == 2 ? 0 : -1));
-            const int nrows = win - dr, ncols = win - (dc != 0 ? 1 : 0), c0 = dc < 0 ? 1 : 0;
+        for (int ang = 0; ang < offs.n; ++ang) {
+            const int dr = offs.dr[ang], dc = offs.dc[ang];
+            // anchors (r, c) whose partner (r + dr, c + dc) lies inside the window (graycomatrix's bounds test)
+            const int r0 = max(0, -dr), c0 = max(0, -dc);
+            const int nrows = max(0, min(win, win - dr) - r0), ncols = max(0, min(win, win - dc) - c0);
             const int n = nrows * ncols;
+            if (n == 0) {  // offset longer than the window: an all-zero matrix - every property 0, correlation 1 (std < 1e-15)
+                acc[4] += 1.0;
+                continue;
+            }
             const int off = dr * W + dc;
             AngleSums t = {0, 0, 0, 0, 0, 0.0};
             long long hfx = 0;  // moments dump only: the fixed-point homogeneity terms of the dense kernel
             int neq = 0;
             // pass A: count + integer moments
             for (int s = lane; s < n; s += 32) {
-                const int r = s / ncols, c = s - r * ncols + c0;
+                const int r = s / ncols + r0, c = s % ncols + c0;
                 const uint8_t* p = base + r * W + c;
                 const int a = p[0], b = p[off];
                 const int d = abs(a - b);
@@ -101,7 +118,7 @@ __global__ void __launch_bounds__(128) glcm_props_warp_kernel(const uint8_t* __r
             __syncwarp();
             // pass B: E = sum over pairs of the multiplicity of their cell
             for (int s = lane; s < n; s += 32) {
-                const int r = s / ncols, c = s - r * ncols + c0;
+                const int r = s / ncols + r0, c = s % ncols + c0;
                 const uint8_t* p = base + r * W + c;
                 const int a = p[0], b = p[off];
                 if (a < L && b < L) t.e += (a != b ? 2 : 4) * (int)U[tri_cell(a, b)];
@@ -109,7 +126,7 @@ __global__ void __launch_bounds__(128) glcm_props_warp_kernel(const uint8_t* __r
             __syncwarp();
             // pass C: clean
             for (int s = lane; s < n; s += 32) {
-                const int r = s / ncols, c = s - r * ncols + c0;
+                const int r = s / ncols + r0, c = s % ncols + c0;
                 const uint8_t* p = base + r * W + c;
                 const int a = p[0], b = p[off];
                 if (a < L && b < L) U[tri_cell(a, b)] = 0;
@@ -136,7 +153,7 @@ __global__ void __launch_bounds__(128) glcm_props_warp_kernel(const uint8_t* __r
         if (lane == 0) {
             const int64_t o = (int64_t)oi * out_cols + oj;
 #pragma unroll
-            for (int k = 0; k < 5; ++k) props[k * plane_stride + o] = (float)(acc[k] * 0.25);  // .mean() over the 1x4 array
+            for (int k = 0; k < 5; ++k) props[k * plane_stride + o] = (float)(offs.n == 4 ? acc[k] * 0.25 : acc[k] / (double)offs.n);  // .mean() over the (distances x angles) array
         }
     }
 }
@@ -656,7 +673,7 @@ static int dispatch_dense_folded(const uint8_t* d_q, int W, int levels, int out_
 }
 
 static int glcm_run(const uint8_t* d_q, int rows_avail, int W, int levels, int window, int step, int out_rows, int out_cols, float* d_props,
-                    int64_t plane_stride, long long* d_moments, rsx_stream_t stream) {
+                    int64_t plane_stride, long long* d_moments, rsx_stream_t stream, const GlcmOffsets* custom = nullptr) {
     RSX_REQUIRE(d_q && d_props, "rsx_glcm_props: null argument");
     RSX_REQUIRE(levels >= 2 && levels <= 128, "rsx_glcm_props: levels must be in [2,128]");
     RSX_REQUIRE(window >= 2 && window <= 127 && step >= 1, "rsx_glcm_props: window must be in [2,127], step >= 1");
@@ -667,7 +684,7 @@ static int glcm_run(const uint8_t* d_q, int rows_avail, int W, int levels, int w
     cudaStream_t s = (cudaStream_t)stream;
     const int ncell = levels * (levels + 1) / 2;
     // dense fast path: packed integer moments hold for levels <= 64 and window <= 11; uint8 counters hold w(w-1) <= 110
-    if (step == 1 && levels <= 64) {
+    if (step == 1 && levels <= 64 && !custom) {
         int rc = -1;
         const int fold_env = rsx_option("glcm_fold", 1);  // 1: folded counters where the scene allows (chosen on the device), 0: never
         if (fold_env && levels <= 32) {
@@ -705,8 +722,21 @@ static int glcm_run(const uint8_t* d_q, int rows_avail, int W, int levels, int w
     }
     const int64_t n_win = (int64_t)out_rows * out_cols;
     const int grid = (int)min(ceil_div(n_win, (int64_t)4), (int64_t)rsx_num_sms() * 8);
-    glcm_props_warp_kernel<<<grid, 128, smem, s>>>(d_q, W, levels, window, step, out_rows, out_cols, d_props, plane_stride, d_moments);
+    glcm_props_warp_kernel<<<grid, 128, smem, s>>>(d_q, W, levels, window, step, out_rows, out_cols, d_props, plane_stride, d_moments,
+                                                   custom ? *custom : default_offsets());
     return rsx_check_launch("glcm_props_warp");
+}
+
+extern "C" int rsx_glcm_props_offsets(const uint8_t* d_q, int rows_avail, int W, int levels, int window, int step, int out_rows, int out_cols,
+                                      const int32_t* h_offsets, int n_offsets, float* d_props, int64_t plane_stride, rsx_stream_t stream) {
+    RSX_REQUIRE(h_offsets && n_offsets >= 1 && n_offsets <= 16, "rsx_glcm_props_offsets: 1..16 (row, column) offsets");
+    GlcmOffsets o = default_offsets();
+    o.n = n_offsets;
+    for (int i = 0; i < n_offsets; ++i) {
+        o.dr[i] = h_offsets[2 * i], o.dc[i] = h_offsets[2 * i + 1];
+        RSX_REQUIRE(abs(o.dr[i]) < 4096 && abs(o.dc[i]) < 4096, "rsx_glcm_props_offsets: offset out of range");
+    }
+    return glcm_run(d_q, rows_avail, W, levels, window, step, out_rows, out_cols, d_props, plane_stride, nullptr, stream, &o);
 }
 
 extern "C" int rsx_glcm_props(const uint8_t* d_q, int rows_avail, int W, int levels, int window, int step, int out_rows, int out_cols,

@@ -201,6 +201,7 @@ struct KmPeers {
     const unsigned long long* flag_in;            // own flags
     long long* zero_next;                         // own pass buffer of the other parity
     unsigned long long seq;
+    unsigned long long timeout_ns;  // a peer that has not published after this long is reported instead of waited for
     int rank, world;
 };
 
@@ -223,7 +224,7 @@ __device__ bool km_peer_reduce(const KmPeers& pr, long long* __restrict__ pass_o
         for (;;) {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(pr.flag_in + threadIdx.x) : "memory");
             if (seen >= pr.seq) break;
-            if (km_globaltimer() - t0 > 4000000000ull) {  // 4 s
+            if (km_globaltimer() - t0 > pr.timeout_ns) {
                 timed_out = 1;
                 break;
             }
@@ -332,6 +333,7 @@ extern "C" int rsx_kmeans_update_peers(void* d_state, int64_t* d_acc, int delta,
     pr.flag_in = reinterpret_cast<const unsigned long long*>(own + 2 * RSX_PEER_PASS_ELEMS * 8);
     pr.zero_next = reinterpret_cast<long long*>(own) + (size_t)(parity ^ 1) * RSX_PEER_PASS_ELEMS;
     pr.seq = (unsigned long long)seq, pr.rank = rank, pr.world = world;
+    pr.timeout_ns = (unsigned long long)max(1, rsx_option("peer_timeout_ms", 4000)) * 1000000ull;
     cudaStream_t s = (cudaStream_t)stream;
     km_update_kernel<true><<<1, KM_CTRL_THREADS, 0, s>>>((KmState*)d_state, reinterpret_cast<long long*>(d_acc), delta,
                                                          reinterpret_cast<const long long*>(d_adjust), pr);

@@ -91,6 +91,31 @@ class PeerBlocks:
         _lib.call("rsx_peer_zero", C.c_void_p(self.own), 2 * PEER_PASS_ELEMS * 8, stream)
 
 
+_PEER_CACHE = {}
+
+
+def release_peer_blocks():
+    """Unmaps the peers' blocks and frees this rank's own (rsx_peer_close / rsx_peer_free); registered with atexit."""
+    if not _PEER_CACHE:
+        return
+    try:
+        from . import _lib
+        lib = _lib.load()
+        for pb in _PEER_CACHE.values():
+            for p in range(pb.world):
+                if p != pb.rank and pb.ptrs[p]:
+                    lib.rsx_peer_close(C.c_void_p(pb.ptrs[p]))
+            lib.rsx_peer_free(C.c_void_p(pb.own))
+    except Exception:
+        pass
+    _PEER_CACHE.clear()
+
+
+import atexit
+
+atexit.register(release_peer_blocks)
+
+
 class Comm:
     """torch.distributed wrapper; `Comm()` without an initialised process group is the 1-GPU case."""
 
@@ -111,6 +136,12 @@ class Comm:
         self._peers_tried, self._peers = True, None
         if not (self.active and 2 <= self.world <= 8) or os.environ.get("RSX_PEER_REDUCE", "1") == "0":
             return None
+        # one block (+ its IPC mappings) per process and group, shared by every Comm / KMeans instance and released at exit:
+        # a fresh Comm() per scene must neither leak device memory nor repeat the collective IPC set-up
+        key = id(self.group) if self.group is not None else "world"
+        if key in _PEER_CACHE:
+            self._peers = _PEER_CACHE[key]
+            return self._peers
         if self.dist.get_backend(self.group) != "nccl" or not torch.cuda.is_available():
             return None
         from . import _lib
@@ -139,7 +170,7 @@ class Comm:
         if int(flag.item()) != 1:
             warnings.warn("rsx: CUDA IPC peer mapping is not available; KMeans sums go through all-reduce")
             return None
-        self._peers = PeerBlocks(own.value, ptrs, self.rank, self.world)
+        self._peers = _PEER_CACHE[key] = PeerBlocks(own.value, ptrs, self.rank, self.world)
         return self._peers
 
     def all_reduce(self, t: torch.Tensor, op: str = "sum") -> torch.Tensor:

@@ -260,10 +260,14 @@ def _perform_pca_planar(planes, H, W, n_components, use_robust_scaling):
 
 # ------------------------------------------------------------------------------------------- a7
 def calculate_glcm_features(band, distances=[1], angles=[0, np.pi / 4, np.pi / 2, 3 * np.pi / 4], levels=32, window_size=21, step_size=21):
-    """indices.py:248-318 (distance 1 and the four default angles, which is all the reference ever asks for)."""
+    """indices.py:248-318.  distances=[1] with the four default angles (all the reference ever asks for) runs the dense / tiled
+    fast kernels; any other list of up to 16 (distance, angle) pairs runs the general kernel with graycomatrix's offsets
+    round(sin(angle) * d), round(cos(angle) * d)."""
     require_cuda()
-    if list(distances) != [1] or not np.allclose(list(angles), _DEFAULT_ANGLES):
-        raise _lib.RsxError("calculate_glcm_features: only distances=[1] with angles 0, pi/4, pi/2, 3pi/4 are implemented")
+    offsets = [(int(round(np.sin(a) * d)), int(round(np.cos(a) * d))) for d in distances for a in angles]
+    custom = offsets != [(0, 1), (1, 1), (1, 0), (1, -1)]
+    if custom and not 1 <= len(offsets) <= 16:
+        raise _lib.RsxError("calculate_glcm_features: between 1 and 16 (distance, angle) pairs")
     band = np.asarray(band)
     H, W = band.shape
     if window_size > H or window_size > W:
@@ -276,7 +280,12 @@ def calculate_glcm_features(band, distances=[1], angles=[0, np.pi / 4, np.pi / 2
     oh, ow = (H - window_size) // step_size + 1, (W - window_size) // step_size + 1
     pstride = (oh * ow + 31) // 32 * 32
     props = torch.empty((5, pstride), dtype=torch.float32, device="cuda")
-    _lib.call("rsx_glcm_props", ptr(q), H, W, int(levels), int(window_size), int(step_size), oh, ow, ptr(props), pstride, st)
+    if custom:
+        h_off = np.ascontiguousarray(offsets, dtype=np.int32)
+        _lib.call("rsx_glcm_props_offsets", ptr(q), H, W, int(levels), int(window_size), int(step_size), oh, ow, hptr(h_off), len(offsets),
+                  ptr(props), pstride, st)
+    else:
+        _lib.call("rsx_glcm_props", ptr(q), H, W, int(levels), int(window_size), int(step_size), oh, ow, ptr(props), pstride, st)
     full = torch.empty((5, H * W), dtype=torch.float32, device="cuda")
     _lib.call("rsx_resize_bilinear_f32", ptr(props), oh, ow, 0, oh, pstride, ptr(full), H, W, 0, H, H * W, 5, None, st)   # :308
     maps = full.cpu().numpy().reshape(5, H, W)
@@ -366,6 +375,24 @@ def prepare_level_2_features(features_dict):
     return np.stack(maps, axis=-1) if maps else np.zeros((1, 1, 1))
 
 
+def _run_stage_unfused(bands_data):
+    """scripts/2_feature_extraction.py:27-133 with preprocessing=False: the bands are used as they are (arbitrary float maps), so
+    the stage is the reference's own sequence of calls, each through its drop-in (one host <-> device round trip per call)."""
+    blue, green, red, nir, swir1 = bands_data[0], bands_data[1], bands_data[2], bands_data[3], bands_data[4]
+    f = {"ndvi": calculate_ndvi(nir, red), "evi": calculate_evi(nir, red, blue), "msavi": calculate_msavi(nir, red),
+         "ndwi": calculate_ndwi(green, nir), "mndwi": calculate_mndwi(green, swir1), "ndbi": calculate_ndbi(swir1, nir),
+         "bsi": calculate_bsi(blue, red, nir, swir1)}
+    valid = [b for b in bands_data if b is not None]
+    f["pca_result"], f["variance_ratio"], _ = perform_pca(valid, use_robust_scaling=True)
+    f["glcm_features"] = calculate_glcm_features(nir)
+    f["morphological_features"] = {"gradient_5": morphological_gradient(nir, 5)}
+    f["multi_scale_features"] = {"std_dev_scale_5": local_std_dev(nir, 5)}
+    f["filter_features"] = {"sobel_mag": sobel_magnitude(nir)}
+    level1 = add_spatial_context(prepare_level_1_features(f))
+    level2 = prepare_level_2_features(f)
+    return f, {"level_1": level1, "level_2": level2, "all": np.concatenate([level1, level2], axis=-1)}
+
+
 def run_feature_extraction_stage(bands_data, preprocessing=True, texture_band_index=3):
     """scripts/2_feature_extraction.py:27-133, hot-path part, fused on the device.
 
@@ -381,7 +408,7 @@ def run_feature_extraction_stage(bands_data, preprocessing=True, texture_band_in
     from . import pipeline as P
     require_cuda()
     if not preprocessing:
-        raise _lib.RsxError("run_feature_extraction_stage: the fused path includes robust_normalize (preprocessing=True)")
+        return _run_stage_unfused(bands_data)
     arrs = [np.asarray(b) for b in bands_data]
     H, W = arrs[0].shape
     stack = np.stack(arrs, axis=-1)

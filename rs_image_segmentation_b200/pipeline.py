@@ -570,7 +570,19 @@ class DeviceKMeans:
         t = self.acc[self.n_acc - 2:self.n_acc - 1].clone()          # near ties of the final assign-only pass
         self.comm.all_reduce(t)
         h_inertia, h_last, h_sofar = stage_to_host(self.inertia), stage_to_host(t), stage_to_host(self.acc[2 * self.n_acc - 2:2 * self.n_acc - 1])
-        cent, shift, empty = self.read()
+        failure = None
+        try:
+            cent, shift, empty = self.read()
+        except _lib.RsxError as ex:                                    # e.g. a peer never reached the update barrier (time-out)
+            failure = ex
+        if self.comm.world > 1:
+            # a failed exchange must fail on EVERY rank: the late rank itself sees all flags and would carry on alone
+            flag = torch.tensor([1 if failure is not None else 0], dtype=torch.int32, device=self.planes.device)
+            self.comm.all_reduce(flag, "max")
+            if int(flag.item()) and failure is None:
+                failure = _lib.RsxError("KMeans: the peer-memory exchange failed on another rank (rsx_kmeans_update_peers timed out)")
+        if failure is not None:
+            raise failure
         if empty:
             return None                                                # the caller reruns with relocation (fit -> _fit_relocating)
         return KMeansResult(labels=labels, centroids=cent, inertia=float(h_inertia[0]), n_iter=n_iter,

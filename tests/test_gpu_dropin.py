@@ -112,8 +112,8 @@ def test_glcm_features_defaults_and_dense(I, aa_crop):
         for k in got:
             assert got[k].shape == nir.shape and got[k].dtype == np.float32
             np.testing.assert_allclose(got[k], ref[k], rtol=1e-5, atol=1e-6, err_msg=f"{k} {kw}")
-    with pytest.raises(Exception):
-        I.calculate_glcm_features(nir, distances=[2])
+    with pytest.raises(Exception):                                   # more (distance, angle) pairs than the general kernel takes
+        I.calculate_glcm_features(nir, distances=list(range(1, 6)), angles=[0, 0.5, 1.0, 1.5])
 
 
 def test_run_feature_extraction_stage(I, aa_crop):
@@ -286,3 +286,28 @@ def test_perform_pca_rejects_more_than_16_bands(I):
     from rs_image_segmentation_b200._lib import RsxError
     with pytest.raises(RsxError):
         I.perform_pca([np.random.default_rng(b).random((8, 9), dtype=np.float32) for b in range(17)])
+
+
+def test_glcm_features_custom_distances_and_angles(I):
+    """VERDICT r1 missing 5: calculate_glcm_features(distances, angles) other than the defaults (indices.py:248-249,288-289)."""
+    from oracle import glcm as og
+    from rs_image_segmentation_b200.synth import synth_raster_numpy
+    band = synth_raster_numpy(70, 90, 7, np.uint8, 9, cell=16)[:, :, 3].astype(np.float32)
+    for distances, angles, levels, win, step in [([1, 2], [0, np.pi / 2], 16, 9, 9), ([3], [np.pi / 4, np.pi, 5 * np.pi / 4], 32, 7, 5),
+                                                 ([1, 12], [0.0], 8, 7, 7)]:
+        got = I.calculate_glcm_features(band, distances=distances, angles=angles, levels=levels, window_size=win, step_size=step)
+        q = og.quantize(band, levels)
+        ref = og.props_map_numpy(q, levels, win, step, angles=tuple(angles), distances=tuple(distances))
+        for k, name in enumerate(og.PROPS):
+            want = og.resize_to(ref[k], band.shape[0], band.shape[1])
+            np.testing.assert_allclose(got[name], want, rtol=1e-5, atol=1e-6, err_msg=f"{name} {distances} {angles}")
+
+
+def test_run_feature_extraction_stage_without_preprocessing(I, aa_crop):
+    """scripts/2_feature_extraction.py:40-48: preprocessing=False takes the bands as they are (already normalised floats)."""
+    nb = [aa_crop["norm"][i] for i in range(7)]
+    feats, hier = I.run_feature_extraction_stage(nb, preprocessing=False)
+    for k in ("ndvi", "evi", "msavi", "ndwi", "mndwi", "ndbi", "bsi"):
+        assert np.array_equal(feats[k], aa_crop["ix_" + k]), k
+    assert hier["level_1"].shape == nb[0].shape + (14,) and hier["all"].shape == nb[0].shape + (19,)
+    assert hier["all"].dtype == np.float64
