@@ -292,6 +292,23 @@ int rsx_peer_close(void* d_peer);
 int rsx_peer_free(void* d_ptr);
 int rsx_kmeans_update_peers(void* d_state, int64_t* d_acc, int delta, int D, const int64_t* d_adjust, void* const* h_peer_blocks,
                             int rank, int world, int64_t seq, rsx_stream_t stream);
+/* ---- k-means++ seeding (sklearn/cluster/_kmeans.py:180-255) on the planar float32 stack, float64 arithmetic, 8 B/sample of
+ * state (the running closest squared distance); the host draws the random numbers and drives the rounds.
+ * h_scale / h_min: MinMaxScaler scale_, min_; h_mean: per-feature mean of the scaled stack (the centring of KMeans.fit).
+ * rsx_kpp_feature_moments: d_out double [2*D] = (sum, sum of squares) of every scaled feature.
+ * rsx_kpp_distances: h_cand double [T][D] = candidate centres in centred scaled coordinates.  mode 0: d_closest <- distance to
+ *   candidate 0, d_pot[0] = its sum; mode 1: d_pot[t] = sum_i min(d_closest_i, distance_i,t), T <= 8 candidates, d_closest
+ *   untouched; mode 2: d_closest <- min(d_closest, distance to candidate 0).  d_pot double [8].
+ * rsx_kpp_block_sums: d_sums double [ceil(n / rsx_kpp_block())] = sums of d_closest over blocks of rsx_kpp_block() samples.
+ * d_scratch: double [rsx_kpp_scratch_elems()]. */
+int64_t rsx_kpp_scratch_elems(void);
+int64_t rsx_kpp_block(void);
+int rsx_kpp_feature_moments(const float* d_stack, int64_t plane_stride, int64_t n, int D, const double* h_scale, const double* h_min,
+                            double* d_out, double* d_scratch, rsx_stream_t stream);
+int rsx_kpp_distances(const float* d_stack, int64_t plane_stride, int64_t n, int D, const double* h_scale, const double* h_min,
+                      const double* h_mean, const double* h_cand, int T, int mode, double* d_closest, double* d_pot, double* d_scratch,
+                      rsx_stream_t stream);
+int rsx_kpp_block_sums(const double* d_closest, int64_t n, double* d_sums, rsx_stream_t stream);
 /* SYNCHRONISES: the fixed-point scale 2^shift_d per feature (a raw sample enters the sums as rint(x * scale)). */
 int rsx_kmeans_fixed_point_scales(const void* d_state, double* h_pow2, rsx_stream_t stream);
 /* SYNCHRONISES the stream; centroids come back in scaled, un-centred coordinates, double [K][D];

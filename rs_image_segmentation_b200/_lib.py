@@ -66,6 +66,11 @@ SIGNATURES = {
     "rsx_kmeans_assign": (i32, [vp, i64, i64, i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
     "rsx_kmeans_update": (i32, [vp, vp, i32, i32, vp, vp]),
     "rsx_kmeans_fixed_point_scales": (i32, [vp, vp, vp]),
+    "rsx_kpp_scratch_elems": (i64, []),
+    "rsx_kpp_block": (i64, []),
+    "rsx_kpp_feature_moments": (i32, [vp, i64, i64, i32, vp, vp, vp, vp, vp]),
+    "rsx_kpp_distances": (i32, [vp, i64, i64, i32, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp]),
+    "rsx_kpp_block_sums": (i32, [vp, i64, vp, vp]),
     "rsx_kmeans_read": (i32, [vp, vp, vp, vp, vp]),
     "rsx_kmeans_update_peers": (i32, [vp, vp, i32, i32, vp, vp, i32, i32, i64, vp]),
     "rsx_peer_alloc": (i32, [i64, vp, vp]),

@@ -18,7 +18,7 @@ OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "librsx.so")
 # (source, object name, extra flags): the KMeans assign kernels are one source compiled once per range of D
 SOURCES = [("rsx_core.cu", "rsx_core", []), ("rsx_raster_kernels.cu", "rsx_raster_kernels", []), ("rsx_glcm.cu", "rsx_glcm", []), ("rsx_stencil.cu", "rsx_stencil", []), ("rsx_pca_planar.cu", "rsx_pca_planar", []),
-           ("rsx_kmeans.cu", "rsx_kmeans", [])] + [("rsx_kmeans_part.cu", f"rsx_kmeans_part{i}", [f"-DRSX_KM_PART={i}"]) for i in range(6)]
+           ("rsx_kmeans.cu", "rsx_kmeans", []), ("rsx_kmeans_seed.cu", "rsx_kmeans_seed", [])] + [("rsx_kmeans_part.cu", f"rsx_kmeans_part{i}", [f"-DRSX_KM_PART={i}"]) for i in range(6)]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off", "--expt-relaxed-constexpr"]
 

@@ -311,3 +311,22 @@ def test_run_feature_extraction_stage_without_preprocessing(I, aa_crop):
         assert np.array_equal(feats[k], aa_crop["ix_" + k]), k
     assert hier["level_1"].shape == nb[0].shape + (14,) and hier["all"].shape == nb[0].shape + (19,)
     assert hier["all"].dtype == np.float64
+
+
+def test_kmeans_dropin_with_the_reference_call_sites_22_planes(E, aa_crop):
+    """scripts/3_classification.py:381-391 clusters on ['ndvi', 'ndwi', 'ndbi', 'hierarchical_all'] = 3 + 19 planes.
+    Labels bit exact against sklearn (the oracle's restatement of extract.py:508-581) on the float64 promotion of float32
+    features.  (The drop-in works on float32 planes: float64 features that float32 cannot represent are rounded first -
+    INTEGRATION.md.)"""
+    from oracle import kmeans as ok
+    d, keys = _ix_dict(aa_crop, np.float64)
+    rng = np.random.default_rng(22)
+    extra = [np.asarray(aa_crop["pca_maps"][i], np.float64) for i in range(7)]
+    extra += [(d["ndvi"] * rng.uniform(0.2, 2.0) + d["evi"] * rng.uniform(-1, 1)).astype(np.float32).astype(np.float64) for _ in range(5)]
+    stack19 = np.stack([d[k] for k in keys] + extra, axis=-1)
+    assert stack19.shape[-1] == 19
+    fd = {"ndvi": d["ndvi"], "ndwi": d["ndwi"], "ndbi": d["ndbi"], "hierarchical_all": stack19, "height": d["height"], "width": d["width"]}
+    use = ["ndvi", "ndwi", "ndbi", "hierarchical_all"]
+    lab = E.unsupervised_kmeans_classification(fd, n_clusters=7, feature_keys_to_use=use)
+    ref = ok.kmeans_classification(fd, n_clusters=7, keys=use)
+    assert lab.shape == ref.shape and np.array_equal(lab, ref), f"{(lab != ref).sum()} labels differ"

@@ -83,3 +83,33 @@ def test_full_scene_table(aa_full_stats):
     # the numbers quoted in SURVEY.md 8(c), regenerated from the reference
     assert aa_full_stats["pct"].tolist() == [[59, 90], [18, 77], [8, 59], [28, 80], [10, 97], [63, 177], [4, 59]]
     assert int(aa_full_stats["q32_max"]) == 31
+
+
+def test_stage1_restatement_matches_the_reference_output(aa_full_stats):
+    """oracle.features.stage1_preprocess (gain/bias -> identity warp -> min-max stretch -> uint8,
+    modules/features/preprocessing.py:54-125) against the stage-1 output the UNMODIFIED reference functions produced for the
+    bundled scene: the SHA-256 of that (7, 600, 600) uint8 array is in the golden file (tests/golden/make_golden.py).  Needs the
+    reference's data/raw/AA.tif, i.e. runs in the build container only."""
+    import hashlib
+    import importlib.util
+    import os
+
+    import pytest
+
+    from oracle import features as of
+    tif = "/root/reference/data/raw/AA.tif"
+    if not os.path.exists(tif):
+        pytest.skip("the reference's bundled scene is not on this machine")
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(os.path.dirname(__file__), "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    raw = mg.read_tiff_planar_u8(tif)
+    stage1 = np.stack(of.stage1_preprocess([raw[i] for i in range(raw.shape[0])]))
+    assert stage1.dtype == np.uint8 and stage1.shape == (7, 600, 600)
+    assert hashlib.sha256(stage1.tobytes()).digest() == aa_full_stats["stage1_sha"].tobytes()
+    # and the level-table route the GPU path fuses into its loads (FeatureConfig.stage1) gives the same bytes
+    from rs_image_segmentation_b200 import hoststats
+    hist = np.stack([np.bincount(raw[b].ravel(), minlength=256) for b in range(7)]).astype(np.int64)
+    remap, _ = hoststats.stage1_level_tables(hist, of.TM_GAIN, of.TM_BIAS)
+    fused = np.stack([remap[b][raw[b]] for b in range(7)]).astype(np.uint8)
+    assert np.array_equal(fused, stage1)
