@@ -231,7 +231,10 @@ __device__ __forceinline__ void glcm_dense_body(const DenseShared sm, const uint
     int e = 0;
     unsigned* my_codes = sm.codes + ANG * RING * NT + t;
     unsigned* my_base = sm.base + ANG * (WIN + NT) + WIN + t;
-    unsigned char* my_cnt = sm.cnt + (size_t)ANG * ncell * NTW + t;
+    // Folded variants: the counters of a thread sit in ITS bank - cell c of thread t at word (c / 4) * NT + t, byte c % 4 (NT is a
+    // multiple of 32) - so a warp's 32 counter accesses never conflict.  (With the unfolded [cell][window] byte layout the bank is
+    // a function of the cell: ~3 wavefronts per access on imagery, 29 % of the kernel's shared-memory wavefronts.)
+    unsigned char* my_cnt = FOLD ? sm.cnt + ((size_t)ANG * ((ncell + 3) / 4) * NT + t) * 4 : sm.cnt + (size_t)ANG * ncell * NTW + t;
     const unsigned char* qt = sm.qring + t;
 
     auto slot_add = [](int s, int k) { s += k; return s >= RING ? s - RING : s; };
@@ -253,7 +256,7 @@ __device__ __forceinline__ void glcm_dense_body(const DenseShared sm, const uint
         if (pair_ok) {
             const int a = qt[sa * NT], b = qt[sb * NT + DC];
             const int cid = !FOLD ? tri_cell(a, b) : (a == b ? FOLD * (FOLD + 1) / 2 + (a & (FOLD - 1)) : tri_cell(a & (FOLD - 1), b & (FOLD - 1)));
-            cell = ((unsigned)(cid * NTW) << 16) | (a == b ? 8u : 4u);
+            cell = ((unsigned)(FOLD ? (cid >> 2) * (NT * 4) + (cid & 3) : cid * NTW) << 16) | (a == b ? 8u : 4u);
             unsigned w1, w2;
             unsigned long long sh;
             pair_terms(a, b, w1, w2, sh);
@@ -397,7 +400,7 @@ __device__ __forceinline__ void glcm_dense_body(const DenseShared sm, const uint
 }
 
 template <int WIN, int NT, bool WIDE, int FOLD>
-__global__ void __launch_bounds__(NT * 4) glcm_dense_kernel(const uint8_t* __restrict__ q, int W, int L, int out_rows, int out_cols, int rows_per_cta,
+__global__ void __launch_bounds__(NT * 4, (FOLD && WIN <= 7) ? 1280 / (NT * 4) : 1) glcm_dense_kernel(const uint8_t* __restrict__ q, int W, int L, int out_rows, int out_cols, int rows_per_cta,
                                                             int NTW, float* __restrict__ props, int64_t plane_stride, long long* __restrict__ moments,
                                                             const int* __restrict__ fold_mode) {
     // several variants are launched back to back; the one the span statistics selected (glcm_fold_select_kernel) does the work
@@ -424,7 +427,7 @@ __global__ void __launch_bounds__(NT * 4) glcm_dense_kernel(const uint8_t* __res
     const int i_end = min(out_rows, i_begin + rows_per_cta);
     if (i_begin >= i_end) return;
 
-    for (int i = tid; i < 4 * ncell * NTW; i += 4 * NT) sm.cnt[i] = 0;
+    for (int i = tid; i < (FOLD ? 4 * ((ncell + 3) / 4) * NT * 4 : 4 * ncell * NTW); i += 4 * NT) sm.cnt[i] = 0;
     for (int i = tid; i < 4 * (WIN + NT); i += 4 * NT) sm.base[i] = 0xfffffff0u;
     if (tid < 64)  // 2^40 (wide: 2^36) / (1+k^2); the k == 0 entry also counts the pair in the Neq field
         homog_fx[tid] = (unsigned long long)((WIDE ? 68719476736.0 : 1099511627776.0) / (1.0 + (double)tid * (double)tid) + 0.5) +
@@ -438,18 +441,19 @@ __global__ void __launch_bounds__(NT * 4) glcm_dense_kernel(const uint8_t* __res
     }
 }
 
-static size_t dense_smem_bytes(int win, int nt, int ntw, int ncell) {
-    return (size_t)4 * ncell * ntw + (size_t)nt * (16 * (win + 1) + 16 + 64 + 80 + (win + 1)) + 16 * win + 64;
+static size_t dense_smem_bytes(int win, int nt, int ntw, int ncell, bool fold = false) {
+    return (fold ? (size_t)4 * ((ncell + 3) / 4) * nt * 4 : (size_t)4 * ncell * ntw) + (size_t)nt * (16 * (win + 1) + 16 + 64 + 80 + (win + 1)) + 16 * win + 64;
 }
 
 template <int WIN, int NT, bool WIDE, int FOLD = 0>
 static int launch_dense(const uint8_t* d_q, int W, int levels, int ntw, int out_rows, int out_cols, float* d_props, int64_t plane_stride, long long* d_moments,
                         cudaStream_t s, const int* d_fold_mode = nullptr) {
     const int ncell = FOLD ? fold_cells(FOLD) : levels * (levels + 1) / 2;
-    const size_t smem = dense_smem_bytes(WIN, NT, ntw, ncell);
+    const size_t smem = dense_smem_bytes(WIN, NT, ntw, ncell, FOLD != 0);
     auto kern = glcm_dense_kernel<WIN, NT, WIDE, FOLD>;
     static size_t configured = 0;
     if (smem > configured) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);  // the counters want shared memory, not L1
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max(smem, (size_t)49152));
         if (e != cudaSuccess) {
             rsx_set_error("rsx_glcm_props: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
@@ -687,7 +691,7 @@ static int glcm_run(const uint8_t* d_q, int rows_avail, int W, int levels, int w
     if (step == 1 && levels <= 64 && !custom) {
         int rc = -1;
         const int fold_env = rsx_option("glcm_fold", 1);  // 1: folded counters where the scene allows (chosen on the device), 0: never
-        if (fold_env && levels <= 32) {
+        if (fold_env && levels <= 32 && levels > 16) {  // up to 16 levels the unfolded counters are as small as the folded ones
             switch (window) {
                 case 3: rc = dispatch_dense_folded<3>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, d_moments, s); break;
                 case 5: rc = dispatch_dense_folded<5>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, d_moments, s); break;
