@@ -566,13 +566,14 @@ __global__ void glcm_fold_select_kernel(const unsigned long long* __restrict__ s
 __global__ void __launch_bounds__(256) glcm_energy_patch_kernel(const uint8_t* __restrict__ q, int W, int L, int win, int out_rows, int out_cols,
                                                                 const uint8_t* __restrict__ flags, const int* __restrict__ fold_mode,
                                                                 float* __restrict__ energy, long long* __restrict__ moments) {
-    __shared__ unsigned hist_all[8][528];
+    extern __shared__ unsigned patch_hist[];  // [8 warps][L (L + 1) / 2]
     const int mode = *fold_mode;
     if (mode == 0) return;
     const unsigned bit = mode == 8 ? 1u : 2u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned* hist = hist_all[warp];
-    for (int i = lane; i < 528; i += 32) hist[i] = 0;
+    const int ncell = L * (L + 1) / 2;
+    unsigned* hist = patch_hist + warp * ncell;
+    for (int i = lane; i < ncell; i += 32) hist[i] = 0;
     __syncwarp();
     const int64_t n_win = (int64_t)out_rows * out_cols;
     const int64_t warps_total = (int64_t)gridDim.x * 8;
@@ -625,13 +626,14 @@ __global__ void __launch_bounds__(256) glcm_energy_patch_kernel(const uint8_t* _
 }
 
 // scratch of the folded path, per device: [0,16) two counters, [16,20) the selected mode, [64, 64 + n_win) the flags
+static int g_patch_smem_configured = 0;
 static uint8_t* g_span_buf = nullptr;
 static size_t g_span_cap = 0;
 static int g_span_dev = -1;
 
-// Folded dense path (levels <= 32): span flags + statistics, fold selection on the device, the three dense variants back to
-// back (two of them return at once), energy patch for the flagged windows.  Returns -1 when not applicable.
-template <int WIN>
+// Folded dense path: span flags + statistics, fold selection on the device, the three dense variants back to back (two of them
+// return at once), energy patch for the flagged windows.  Returns -1 when not applicable.
+template <int WIN, bool WIDE>
 static int dispatch_dense_folded(const uint8_t* d_q, int W, int levels, int out_rows, int out_cols, float* d_props, int64_t plane_stride, long long* d_moments,
                                  cudaStream_t s) {
     const size_t n_win = (size_t)out_rows * out_cols;
@@ -660,19 +662,29 @@ static int dispatch_dense_folded(const uint8_t* d_q, int W, int levels, int out_
     const int nt = rsx_option("glcm_fold_nt", 64);
     int rc_d;
     if (nt == 32) {
-        rc_d = launch_dense<WIN, 32, false, 8>(d_q, W, levels, 32 - (WIN - 1), out_rows, out_cols, d_props, plane_stride, d_moments, s, mode);
-        if (!rc_d) rc_d = launch_dense<WIN, 32, false, 16>(d_q, W, levels, 32 - (WIN - 1), out_rows, out_cols, d_props, plane_stride, d_moments, s, mode);
+        rc_d = launch_dense<WIN, 32, WIDE, 8>(d_q, W, levels, 32 - (WIN - 1), out_rows, out_cols, d_props, plane_stride, d_moments, s, mode);
+        if (!rc_d) rc_d = launch_dense<WIN, 32, WIDE, 16>(d_q, W, levels, 32 - (WIN - 1), out_rows, out_cols, d_props, plane_stride, d_moments, s, mode);
     } else {
-        rc_d = launch_dense<WIN, 64, false, 8>(d_q, W, levels, 64 - (WIN - 1), out_rows, out_cols, d_props, plane_stride, d_moments, s, mode);
-        if (!rc_d) rc_d = launch_dense<WIN, 64, false, 16>(d_q, W, levels, 64 - (WIN - 1), out_rows, out_cols, d_props, plane_stride, d_moments, s, mode);
+        rc_d = launch_dense<WIN, 64, WIDE, 8>(d_q, W, levels, 64 - (WIN - 1), out_rows, out_cols, d_props, plane_stride, d_moments, s, mode);
+        if (!rc_d) rc_d = launch_dense<WIN, 64, WIDE, 16>(d_q, W, levels, 64 - (WIN - 1), out_rows, out_cols, d_props, plane_stride, d_moments, s, mode);
     }
     if (rc_d) return rc_d;
-    if (int rc = dispatch_dense<WIN, false>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, d_moments, s, mode)) {  // mode 0
+    if (int rc = dispatch_dense<WIN, WIDE>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, d_moments, s, mode)) {  // mode 0
         if (rc < 0) rsx_set_error("rsx_glcm_props: no dense configuration for window %d at %d levels", WIN, levels);
         return rc < 0 ? RSX_ERR_UNSUPPORTED : rc;
     }
     const int grid = (int)min((int64_t)ceil_div((int64_t)n_win, (int64_t)256), (int64_t)rsx_num_sms() * 8);
-    glcm_energy_patch_kernel<<<grid, 256, 0, s>>>(d_q, W, levels, WIN, out_rows, out_cols, flags, mode, d_props + 3 * plane_stride, d_moments);
+    const int patch_smem = 8 * (levels * (levels + 1) / 2) * 4;
+    int& patch_configured = g_patch_smem_configured;  // one kernel, one attribute: shared by every instantiation of this dispatcher
+    if (patch_smem > patch_configured) {
+        if (cudaFuncSetAttribute(glcm_energy_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max(patch_smem, 48 * 1024)) != cudaSuccess) {
+            cudaGetLastError();
+            rsx_set_error("rsx_glcm_props: energy patch kernel needs %d B of shared memory", patch_smem);
+            return RSX_ERR_CUDA;
+        }
+        patch_configured = patch_smem;
+    }
+    glcm_energy_patch_kernel<<<grid, 256, patch_smem, s>>>(d_q, W, levels, WIN, out_rows, out_cols, flags, mode, d_props + 3 * plane_stride, d_moments);
     return rsx_check_launch("glcm_energy_patch");
 }
 
@@ -691,13 +703,13 @@ static int glcm_run(const uint8_t* d_q, int rows_avail, int W, int levels, int w
     if (step == 1 && levels <= 64 && !custom) {
         int rc = -1;
         const int fold_env = rsx_option("glcm_fold", 1);  // 1: folded counters where the scene allows (chosen on the device), 0: never
-        if (fold_env && levels <= 32 && levels > 16) {  // up to 16 levels the unfolded counters are as small as the folded ones
+        if (fold_env && levels > 16) {  // up to 16 levels the unfolded counters are as small as the folded ones
             switch (window) {
-                case 3: rc = dispatch_dense_folded<3>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, d_moments, s); break;
-                case 5: rc = dispatch_dense_folded<5>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, d_moments, s); break;
-                case 7: rc = dispatch_dense_folded<7>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, d_moments, s); break;
-                case 9: rc = dispatch_dense_folded<9>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, d_moments, s); break;
-                case 11: rc = dispatch_dense_folded<11>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, d_moments, s); break;
+                case 3: rc = levels <= 32 ? dispatch_dense_folded<3, false>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, d_moments, s) : dispatch_dense_folded<3, true>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, d_moments, s); break;
+                case 5: rc = levels <= 32 ? dispatch_dense_folded<5, false>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, d_moments, s) : dispatch_dense_folded<5, true>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, d_moments, s); break;
+                case 7: rc = levels <= 32 ? dispatch_dense_folded<7, false>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, d_moments, s) : dispatch_dense_folded<7, true>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, d_moments, s); break;
+                case 9: rc = levels <= 32 ? dispatch_dense_folded<9, false>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, d_moments, s) : dispatch_dense_folded<9, true>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, d_moments, s); break;
+                case 11: rc = levels <= 32 ? dispatch_dense_folded<11, false>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, d_moments, s) : dispatch_dense_folded<11, true>(d_q, W, levels, out_rows, out_cols, d_props, plane_stride, d_moments, s); break;
                 default: break;
             }
             if (rc >= 0) return rc;
