@@ -511,12 +511,27 @@ static int dispatch_dense(const uint8_t* d_q, int W, int levels, int out_rows, i
 }
 
 // ----------------------------------------------------------------------------- folded counters: span flags + energy patch
-// flags[i * out_cols + j]: bit 0 = the levels of window (i, j) span 8 or more values, bit 1 = 16 or more (the fold modulo 8 / 16
-// may then merge two cells).  stats[0], stats[1] count them.  One CTA per tile of SPAN_TR x SPAN_TC windows: the clamped levels of
-// the tile (+ win-1 halo) go to shared memory, a horizontal min/max pass over win columns, then a vertical one over win rows.
+// Windows whose levels span 8 or more values go to list 0, 16 or more to list 1 (the fold modulo 8 / 16 may merge two cells
+// there): lists of window indices with capacity `cap` each; stats[0], stats[1] = entries appended so far.  A list that is full
+// stops growing - its fold is not going to be selected - so a scene where every window is flagged costs no atomics.
+// One CTA per tile of SPAN_TR x SPAN_TC windows: the clamped levels of the tile (+ win-1 halo) go to shared memory, a
+// horizontal min/max pass over win columns, then a vertical one over win rows.
 constexpr int SPAN_TR = 32, SPAN_TC = 128, SPAN_MAXW = 11;
+__device__ __forceinline__ void span_append(bool flagged, unsigned idx, unsigned long long* __restrict__ counter, unsigned* __restrict__ list, unsigned cap) {
+    const unsigned m = __ballot_sync(0xffffffffu, flagged);
+    if (!m) return;
+    const int lane = threadIdx.x & 31;
+    unsigned long long pos = 0;
+    if (lane == 0 && *reinterpret_cast<volatile unsigned long long*>(counter) <= cap) pos = atomicAdd(counter, (unsigned long long)__popc(m)) + 1;
+    pos = __shfl_sync(0xffffffffu, pos, 0);  // 0: the list was already over its capacity
+    if (pos && flagged) {
+        const unsigned long long at = pos - 1 + __popc(m & ((1u << lane) - 1u));
+        if (at < cap) list[at] = idx;
+    }
+}
 __global__ void __launch_bounds__(256) glcm_span_flag_kernel(const uint8_t* __restrict__ q, int W, int L, int win, int out_rows, int out_cols,
-                                                             uint8_t* __restrict__ flags, unsigned long long* __restrict__ stats) {
+                                                             unsigned* __restrict__ list8, unsigned* __restrict__ list16, unsigned cap,
+                                                             unsigned long long* __restrict__ stats) {
     __shared__ uint8_t raw[SPAN_TR + SPAN_MAXW - 1][SPAN_TC + SPAN_MAXW - 1 + 1];
     __shared__ uint8_t hmn[SPAN_TR + SPAN_MAXW - 1][SPAN_TC], hmx[SPAN_TR + SPAN_MAXW - 1][SPAN_TC];
     const int i0 = blockIdx.y * SPAN_TR, j0 = blockIdx.x * SPAN_TC;
@@ -534,29 +549,29 @@ __global__ void __launch_bounds__(256) glcm_span_flag_kernel(const uint8_t* __re
         hmn[r][c] = (uint8_t)mn, hmx[r][c] = (uint8_t)mx;
     }
     __syncthreads();
-    unsigned n8 = 0, n16 = 0;
-    for (int k = threadIdx.x; k < orows * ocols; k += 256) {
-        const int r = k / ocols, c = k - r * ocols;
-        int mn = 255, mx = 0;
-        for (int d = 0; d < win; ++d) mn = min(mn, (int)hmn[r + d][c]), mx = max(mx, (int)hmx[r + d][c]);
-        const int span = mx - mn;
-        flags[(int64_t)(i0 + r) * out_cols + j0 + c] = (uint8_t)((span >= 8 ? 1 : 0) | (span >= 16 ? 2 : 0));
-        n8 += span >= 8, n16 += span >= 16;
-    }
-    n8 = __reduce_add_sync(0xffffffffu, n8), n16 = __reduce_add_sync(0xffffffffu, n16);
-    if ((threadIdx.x & 31) == 0) {
-        if (n8) atomicAdd(&stats[0], (unsigned long long)n8);
-        if (n16) atomicAdd(&stats[1], (unsigned long long)n16);
+    for (int k0 = 0; k0 < orows * ocols; k0 += 256) {  // block-uniform trip count: span_append is a warp collective
+        const int k = k0 + threadIdx.x;
+        int span = 0;
+        unsigned idx = 0;
+        if (k < orows * ocols) {
+            const int r = k / ocols, c = k - r * ocols;
+            int mn = 255, mx = 0;
+            for (int d = 0; d < win; ++d) mn = min(mn, (int)hmn[r + d][c]), mx = max(mx, (int)hmx[r + d][c]);
+            span = mx - mn;
+            idx = (unsigned)((int64_t)(i0 + r) * out_cols + j0 + c);
+        }
+        span_append(span >= 8, idx, &stats[0], list8, cap);
+        span_append(span >= 16, idx, &stats[1], list16, cap);
     }
 }
 
 // mode = 8 / 16: the fold whose flagged share is at most 1/256 of the windows (their energy is recomputed one warp per window, ~50x
 // the cost of a dense window); 0: the unfolded kernel.  Levels that fit the fold need no flags at all.
-__global__ void glcm_fold_select_kernel(const unsigned long long* __restrict__ stats, long long n_win, int levels, int force, int* __restrict__ mode) {
+__global__ void glcm_fold_select_kernel(const unsigned long long* __restrict__ stats, unsigned cap, int levels, int force, int* __restrict__ mode) {
     int m = 0;
-    if (levels <= 8 || (long long)stats[0] * 256 <= n_win) m = 8;
-    else if (levels <= 16 || (long long)stats[1] * 256 <= n_win) m = 16;
-    if (force == 8 || force == 16 || force == 0) m = force;
+    if (levels <= 8 || stats[0] <= cap) m = 8;
+    else if (levels <= 16 || stats[1] <= cap) m = 16;
+    if ((force == 8 && stats[0] <= cap) || (force == 16 && stats[1] <= cap) || force == 0) m = force;  // a forced fold needs its whole list
     *mode = m;
 }
 
@@ -564,26 +579,23 @@ __global__ void glcm_fold_select_kernel(const unsigned long long* __restrict__ s
 // value equals what the unfolded dense kernel writes): per angle E = sum over the pairs of w * U[cell of the pair] from a
 // warp-private histogram of all L(L+1)/2 unordered cells, energy = sqrtf(E) * (0.5 / n); mean of the four angles.
 __global__ void __launch_bounds__(256) glcm_energy_patch_kernel(const uint8_t* __restrict__ q, int W, int L, int win, int out_rows, int out_cols,
-                                                                const uint8_t* __restrict__ flags, const int* __restrict__ fold_mode,
+                                                                const unsigned* __restrict__ list8, const unsigned* __restrict__ list16,
+                                                                const unsigned long long* __restrict__ stats, const int* __restrict__ fold_mode,
                                                                 float* __restrict__ energy, long long* __restrict__ moments) {
     extern __shared__ unsigned patch_hist[];  // [8 warps][L (L + 1) / 2]
     const int mode = *fold_mode;
     if (mode == 0) return;
-    const unsigned bit = mode == 8 ? 1u : 2u;
+    const unsigned* list = mode == 8 ? list8 : list16;
+    const int64_t n_list = (int64_t)stats[mode == 8 ? 0 : 1];  // <= the capacity, or this fold would not have been selected
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ncell = L * (L + 1) / 2;
     unsigned* hist = patch_hist + warp * ncell;
     for (int i = lane; i < ncell; i += 32) hist[i] = 0;
     __syncwarp();
-    const int64_t n_win = (int64_t)out_rows * out_cols;
     const int64_t warps_total = (int64_t)gridDim.x * 8;
-    for (int64_t base = ((int64_t)blockIdx.x * 8 + warp) * 32; base < n_win; base += warps_total * 32) {
-        const int64_t mine = base + lane;
-        unsigned todo = __ballot_sync(0xffffffffu, mine < n_win && (flags[mine] & bit) != 0);
-        while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const int64_t o = base + src;
+    for (int64_t k = (int64_t)blockIdx.x * 8 + warp; k < n_list; k += warps_total) {
+        {
+            const int64_t o = (int64_t)list[k];
             const int oi = (int)(o / out_cols), oj = (int)(o - (int64_t)oi * out_cols);
             const uint8_t* wbase = q + (int64_t)oi * W + oj;
             float part[4];
@@ -625,39 +637,45 @@ __global__ void __launch_bounds__(256) glcm_energy_patch_kernel(const uint8_t* _
     }
 }
 
-// scratch of the folded path, per device: [0,16) two counters, [16,20) the selected mode, [64, 64 + n_win) the flags
+// scratch of the folded path, per device: [0,16) two counters, [16,20) the selected mode, [64, ...) two lists of `cap` window indices
 static int g_patch_smem_configured = 0;
 static uint8_t* g_span_buf = nullptr;
 static size_t g_span_cap = 0;
 static int g_span_dev = -1;
 
-// Folded dense path: span flags + statistics, fold selection on the device, the three dense variants back to back (two of them
-// return at once), energy patch for the flagged windows.  Returns -1 when not applicable.
+// Folded dense path: span lists + statistics, fold selection on the device, the three dense variants back to back (two of them
+// return at once), energy patch for the listed windows.  Returns -1 when not applicable.
 template <int WIN, bool WIDE>
 static int dispatch_dense_folded(const uint8_t* d_q, int W, int levels, int out_rows, int out_cols, float* d_props, int64_t plane_stride, long long* d_moments,
                                  cudaStream_t s) {
     const size_t n_win = (size_t)out_rows * out_cols;
+    if (n_win >= ((size_t)1 << 32)) return -1;  // window indices are 32-bit
+    // a fold is used while at most 1/256 of the windows need the patch (one warp per window, ~50x the cost of a dense window)
+    const unsigned cap = (unsigned)(n_win / (size_t)max(1, rsx_option("glcm_fold_cap_div", 256)) + 1);
+    const size_t need = 64 + (size_t)2 * cap * sizeof(unsigned);
     int dev = 0;
     cudaGetDevice(&dev);
-    if (n_win + 64 > g_span_cap || dev != g_span_dev) {
+    if (need > g_span_cap || dev != g_span_dev) {
         if (g_span_buf && dev == g_span_dev) cudaFree(g_span_buf);
         g_span_buf = nullptr, g_span_cap = 0, g_span_dev = dev;
-        if (cudaMalloc(&g_span_buf, n_win + 64) != cudaSuccess) {
+        if (cudaMalloc(&g_span_buf, need) != cudaSuccess) {
             cudaGetLastError();
             return -1;
         }
-        g_span_cap = n_win + 64;
+        g_span_cap = need;
     }
     unsigned long long* stats = reinterpret_cast<unsigned long long*>(g_span_buf);
     int* mode = reinterpret_cast<int*>(g_span_buf + 16);
-    uint8_t* flags = g_span_buf + 64;
+    unsigned* list8 = reinterpret_cast<unsigned*>(g_span_buf + 64);
+    unsigned* list16 = list8 + cap;
     if (cudaMemsetAsync(g_span_buf, 0, 64, s) != cudaSuccess) {
         cudaGetLastError();
         return -1;
     }
-    glcm_span_flag_kernel<<<dim3(ceil_div(out_cols, SPAN_TC), ceil_div(out_rows, SPAN_TR)), 256, 0, s>>>(d_q, W, levels, WIN, out_rows, out_cols, flags, stats);
+    glcm_span_flag_kernel<<<dim3(ceil_div(out_cols, SPAN_TC), ceil_div(out_rows, SPAN_TR)), 256, 0, s>>>(d_q, W, levels, WIN, out_rows, out_cols, list8, list16,
+                                                                                                       cap, stats);
     if (int rc = rsx_check_launch("glcm_span_flags")) return rc;
-    glcm_fold_select_kernel<<<1, 1, 0, s>>>(stats, (long long)n_win, levels, rsx_option("glcm_fold_force", -1), mode);
+    glcm_fold_select_kernel<<<1, 1, 0, s>>>(stats, cap, levels, rsx_option("glcm_fold_force", -1), mode);
     if (int rc = rsx_check_launch("glcm_fold_select")) return rc;
     const int nt = rsx_option("glcm_fold_nt", 64);
     int rc_d;
@@ -673,7 +691,7 @@ static int dispatch_dense_folded(const uint8_t* d_q, int W, int levels, int out_
         if (rc < 0) rsx_set_error("rsx_glcm_props: no dense configuration for window %d at %d levels", WIN, levels);
         return rc < 0 ? RSX_ERR_UNSUPPORTED : rc;
     }
-    const int grid = (int)min((int64_t)ceil_div((int64_t)n_win, (int64_t)256), (int64_t)rsx_num_sms() * 8);
+    const int grid = (int)min((int64_t)ceil_div((int64_t)cap, (int64_t)8), (int64_t)rsx_num_sms() * 8);
     const int patch_smem = 8 * (levels * (levels + 1) / 2) * 4;
     int& patch_configured = g_patch_smem_configured;  // one kernel, one attribute: shared by every instantiation of this dispatcher
     if (patch_smem > patch_configured) {
@@ -684,7 +702,8 @@ static int dispatch_dense_folded(const uint8_t* d_q, int W, int levels, int out_
         }
         patch_configured = patch_smem;
     }
-    glcm_energy_patch_kernel<<<grid, 256, patch_smem, s>>>(d_q, W, levels, WIN, out_rows, out_cols, flags, mode, d_props + 3 * plane_stride, d_moments);
+    glcm_energy_patch_kernel<<<grid, 256, patch_smem, s>>>(d_q, W, levels, WIN, out_rows, out_cols, list8, list16, stats, mode, d_props + 3 * plane_stride,
+                                                               d_moments);
     return rsx_check_launch("glcm_energy_patch");
 }
 

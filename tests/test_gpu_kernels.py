@@ -291,11 +291,13 @@ def test_glcm_production_kernel_integer_stage_is_exact(rsx, L, win, fold):
     # span more than the fold goes through the energy patch kernel)
     _lib.set_option("glcm_fold", 1 if fold else 0)
     _lib.set_option("glcm_fold_force", fold if fold > 1 else -1)
+    _lib.set_option("glcm_fold_cap_div", 1 if fold > 1 else 256)        # forced: every flagged window fits the patch list
     try:
         got, props = _moments(rsx, q, L, win, 1)
     finally:
         _lib.set_option("glcm_fold", 1)
         _lib.set_option("glcm_fold_force", -1)
+        _lib.set_option("glcm_fold_cap_div", 256)
     ref = og.pair_moments(q, L, win, 1)
     for f, name in enumerate(og.MOMENT_FIELDS):
         assert np.array_equal(got[..., f], ref[..., f]), name
