@@ -317,25 +317,34 @@ def run_rsx(args):
         # the public host-buffer API, pipelined over the steps: every step's H2D (pinned raster) and D2H (labels) are
         # inside the timed region; the copy engines work under the kernels of the neighbouring steps
         yields = []
+        # uint8 labels (K <= 256) are what the reference's writer stores (labels + 1 as uint8) and a quarter of the
+        # bytes; at 8 GPUs the int32 image makes the run host-memory bound (8 x 539 MB per 19 ms), so it is reported
+        # beside the headline as "int32_labels"
+        label_mode = os.environ.get("RSX_BENCH_LABELS", "uint8")
 
-        def e2e_run(steps):
+        def e2e_run(steps, mode):
             last = None
             yields.clear()
-            for labels, res in P.segment_stream((pinned for _ in range(steps)), cfg, K, T, 7000, D, comm, H_total, bounds):
+            for labels, res in P.segment_stream((pinned for _ in range(steps)), cfg, K, T, 7000, D, comm, H_total, bounds, labels=mode):
                 last = int(labels[0, 0]) + res.n_iter          # touch the result on the host
                 yields.append(time.perf_counter())
             return last
 
-        e2e_run(2)
         e2e_steps = max(2, args.steps)
-        ms_e2e, _ = timed(lambda: e2e_run(e2e_steps), 1)
+        alt_mode = "int32" if label_mode != "int32" else "uint8"
+        e2e_run(2, alt_mode)
+        ms_alt, _ = timed(lambda: e2e_run(e2e_steps, alt_mode), 1)
+        ms_alt /= e2e_steps
+        e2e_run(2, label_mode)
+        ms_e2e, _ = timed(lambda: e2e_run(e2e_steps, label_mode), 1)
         ms_e2e /= e2e_steps
-        d2h = int(P.segment_stream_d2h_bytes(H * W)) if hasattr(P, "segment_stream_d2h_bytes") else int(H * W * 4)
+        d2h = int(P.segment_stream_d2h_bytes(H * W, label_mode))
         e2e = {"value": n_global / (ms_e2e * 1e-3) / 1e6, "unit": "Mpixel/s", "h2d_bytes_per_step": int(pinned.numel()) * world,
-               "d2h_bytes_per_step": d2h * world, "ms_per_step": ms_e2e, "steps": e2e_steps,
-               "api": "pipeline.segment_stream (double-buffered H2D / D2H on the copy engines; labels leave the device as uint8 and are "
-                      "widened to the reference's int32 by host threads, inside the timed region); one scene alone through "
-                      "pipeline.segment_raster: see single_scene_ms"}
+               "d2h_bytes_per_step": d2h * world, "ms_per_step": ms_e2e, "steps": e2e_steps, "labels": label_mode,
+               alt_mode + "_labels": {"value": n_global / (ms_alt * 1e-3) / 1e6, "ms_per_step": ms_alt,
+                                      "d2h_bytes_per_step": int(P.segment_stream_d2h_bytes(H * W, alt_mode)) * world},
+               "api": f"pipeline.segment_stream(labels='{label_mode}') (double-buffered H2D / D2H on the copy engines); one scene alone "
+                      "through pipeline.segment_raster (int32 labels): see single_scene_ms"}
         if len(yields) >= 4:
             # host-clock interval between consecutive label arrays in the middle of the run: what a long stream of scenes
             # costs per scene; ms_per_step above also carries the first upload and the last download of this short run

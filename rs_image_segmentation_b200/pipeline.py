@@ -707,45 +707,31 @@ def segment_raster(raster_host: np.ndarray, cfg: FeatureConfig = FeatureConfig()
     fr = extract_features(dev_raster, cfg, comm, H_total, bounds, timer)
     D = stack_depth if stack_depth is not None else (13 if cfg.glcm else 7 + min(6, len(fr.names) - 7))
     first_row = bounds[comm.rank][0] if bounds is not None else 0
-    res, km, c0 = kmeans_on_features(fr, D, n_clusters, n_iter, seed, comm, H_total, first_row, False, timer)
-    # uint8 labels come back through page-locked memory (a pageable destination costs several times the copy itself) and are
-    # widened to the reference's int32 on the host (rsx_widen_u8_to_i32)
-    if out_pinned is None or out_pinned.numel() != fr.n_px or out_pinned.dtype != torch.uint8:
+    res, km, c0 = kmeans_on_features(fr, D, n_clusters, n_iter, seed, comm, H_total, first_row, True, timer)
+    # labels come back through page-locked memory (a pageable destination costs several times the copy itself)
+    if out_pinned is None or out_pinned.numel() != fr.n_px or out_pinned.dtype != torch.int32:
         out_pinned = _pinned_labels(fr.n_px)
     out_pinned.copy_(res.labels, non_blocking=True)
     torch.cuda.current_stream().synchronize()
-    labels = _host_labels(fr.n_px)
-    threads = max(1, min(8, (os.cpu_count() or 8) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", comm.world)))))
-    _lib.call("rsx_widen_u8_to_i32", C.c_void_p(out_pinned.data_ptr()), hptr(labels), fr.n_px, threads)
-    return labels.reshape(fr.H, fr.W), res, fr
+    return out_pinned.numpy().reshape(fr.H, fr.W), res, fr
 
 
 _PINNED_LABELS = {}
 _PINNED_F64 = {}
 _STREAM_LABELS = {}
-_HOST_LABELS = {}
 
 
-def _stream_label_buffers(n: int):
+def _stream_label_buffers(n: int, pinned_i32: bool = False):
     """Three page-locked uint8 download buffers + three int32 host arrays for segment_stream (scene i is widened by a worker while
     scene i-1 is with the caller and scene i-2 may still be referenced), kept between calls (first-touch page faults of a fresh
     196 MB array cost more than the widening itself)."""
-    bufs = _STREAM_LABELS.get(n)
+    bufs = _STREAM_LABELS.get((n, pinned_i32))
     if bufs is None:
         _STREAM_LABELS.clear()
         out8 = [torch.empty(n, dtype=torch.uint8, pin_memory=True) for _ in range(3)]
-        out = [np.zeros(n, dtype=np.int32) for _ in range(3)]
-        bufs = _STREAM_LABELS[n] = (out8, out)
+        out = [torch.zeros(n, dtype=torch.int32, pin_memory=True) if pinned_i32 else np.zeros(n, dtype=np.int32) for _ in range(3)]
+        bufs = _STREAM_LABELS[(n, pinned_i32)] = (out8, out)
     return bufs
-
-
-def _host_labels(n: int) -> np.ndarray:
-    """Reusable int32 host array for segment_raster's result (valid until the next call of the same size)."""
-    buf = _HOST_LABELS.get(n)
-    if buf is None:
-        _HOST_LABELS.clear()
-        buf = _HOST_LABELS[n] = np.zeros(n, dtype=np.int32)
-    return buf
 
 
 def _pinned_f64(n: int) -> torch.Tensor:
@@ -757,24 +743,32 @@ def _pinned_f64(n: int) -> torch.Tensor:
 
 
 def _pinned_labels(n: int) -> torch.Tensor:
-    """Reusable page-locked uint8 staging buffer for the label image (valid until the next call of the same size)."""
+    """Reusable page-locked int32 staging buffer for the label image (valid until the next call of the same size)."""
     buf = _PINNED_LABELS.get(n)
     if buf is None:
         _PINNED_LABELS.clear()
-        buf = _PINNED_LABELS[n] = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+        buf = _PINNED_LABELS[n] = torch.empty(n, dtype=torch.int32, pin_memory=True)
     return buf
 
 
 def segment_stream(rasters, cfg: FeatureConfig = FeatureConfig(), n_clusters: int = 8, n_iter: int = 20, seed: int = 42,
                    stack_depth: Optional[int] = None, comm: Optional[Comm] = None, H_total: Optional[int] = None,
-                   bounds: Optional[Sequence[Tuple[int, int]]] = None):
+                   bounds: Optional[Sequence[Tuple[int, int]]] = None, labels: str = "int32"):
     """Pipelined end-to-end path for a sequence of scenes (or of this rank's strips of them), all of one shape: an iterable of
     page-locked host rasters in, a generator of (labels (h, W) int32 numpy, KMeansResult) out, in order (KMeansResult.labels is
     the uint8 device plane here).
 
     The host-to-device copy of scene i+1 and the device-to-host copy of the labels of scene i-1 run on their own streams
     (the two copy engines) under the kernels of scene i, so a step costs max(compute, copies) instead of their sum.
-    A yielded label array lives in one of three reusable host buffers: it is valid until two more scenes have been yielded."""
+    A yielded label array lives in one of three reusable host buffers: it is valid until two more scenes have been yielded.
+
+    labels: "int32" (default) - the dtype the reference returns (extract.py:577), written by the device and copied as such;
+    "uint8" - the device's own uint8 plane (K <= 64), a quarter of the bytes, for callers that go on to the uint8 GeoTIFF
+    (scripts/3_classification.py:394) anyway; "int32_host_widen" - uint8 over PCIe, widened to int32 by host threads in a worker
+    (rsx_widen_u8_to_i32): wins where PCIe is the limit, loses where host memory bandwidth is (8 ranks on one socket: the widening
+    adds 2 GB of host traffic per step to a box that is already bound by it - 34 -> 50 ms per step measured)."""
+    if labels not in ("int32", "uint8", "int32_host_widen"):
+        raise ValueError("labels must be 'int32', 'uint8' or 'int32_host_widen'")
     require_cuda()
     comm = comm or Comm()
     compute = torch.cuda.current_stream()
@@ -795,7 +789,7 @@ def segment_stream(rasters, cfg: FeatureConfig = FeatureConfig(), n_clusters: in
     n_lab = first.shape[0] * first.shape[1]
     # labels leave the device as uint8 (a quarter of the int32 bytes over PCIe) and are widened into the int32 array the
     # reference's callers expect (extract.py:577) by a few host threads while the next scene's kernels run
-    out8, out = _stream_label_buffers(n_lab)
+    out8, out = _stream_label_buffers(n_lab, pinned_i32=labels == "int32")
     widen_threads = max(1, min(8, (os.cpu_count() or 8) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", comm.world)))))
 
     import threading
@@ -806,9 +800,18 @@ def segment_stream(rasters, cfg: FeatureConfig = FeatureConfig(), n_clusters: in
         def run():
             downloaded[k].synchronize()
             _lib.call("rsx_widen_u8_to_i32", C.c_void_p(out8[k].data_ptr()), hptr(out[k]), n_lab, widen_threads)
+        if labels != "int32_host_widen":
+            return None
         th = threading.Thread(target=run, daemon=True)
         th.start()
         return th
+
+    def host_labels(k, worker):
+        if worker is not None:
+            worker.join()
+        else:
+            downloaded[k].synchronize()
+        return out8[k].numpy() if labels == "uint8" else (out[k].numpy() if labels == "int32" else out[k])
 
     uploaded = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]       # compute no longer reads dev[k]
@@ -838,29 +841,27 @@ def segment_stream(rasters, cfg: FeatureConfig = FeatureConfig(), n_clusters: in
         fr = extract_features(dev[k], cfg, comm, H_total, bounds)
         D = stack_depth if stack_depth is not None else (13 if cfg.glcm else 7 + min(6, len(fr.names) - 7))
         first_row = bounds[comm.rank][0] if bounds is not None else 0
-        res, km, c0 = kmeans_on_features(fr, D, n_clusters, n_iter, seed, comm, H_total, first_row, False)
+        res, km, c0 = kmeans_on_features(fr, D, n_clusters, n_iter, seed, comm, H_total, first_row, labels == "int32")
         consumed[k].record(compute)
         done = torch.cuda.Event()
         done.record(compute)
         slot = i % 3
         with torch.cuda.stream(down):
             down.wait_event(done)
-            out8[slot].copy_(res.labels, non_blocking=True)
+            (out[slot] if labels == "int32" else out8[slot]).copy_(res.labels, non_blocking=True)
             downloaded[slot].record(down)
         res.labels.record_stream(down)
         worker = start_widen(slot)
-        if pending is not None:                             # hand out scene i-1 (its download and widening overlapped this scene)
+        if pending is not None:                             # hand out scene i-1 (its download overlapped this scene's kernels)
             pk, pres, ph, pw, pth = pending
-            pth.join()
-            yield out[pk].reshape(ph, pw), pres
+            yield host_labels(pk, pth).reshape(ph, pw), pres
         pending = (slot, res, fr.H, fr.W, worker)
         cur = nxt
         i += 1
     pk, pres, ph, pw, pth = pending
-    pth.join()
-    yield out[pk].reshape(ph, pw), pres
+    yield host_labels(pk, pth).reshape(ph, pw), pres
 
 
-def segment_stream_d2h_bytes(n_px: int) -> int:
-    """Bytes per scene that segment_stream copies from the device to the host (uint8 labels)."""
-    return int(n_px)
+def segment_stream_d2h_bytes(n_px: int, labels: str = "int32") -> int:
+    """Bytes per scene that segment_stream copies from the device to the host."""
+    return int(n_px) * (4 if labels == "int32" else 1)

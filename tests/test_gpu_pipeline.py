@@ -371,14 +371,17 @@ def test_segment_stream_matches_single_scene_calls(P):
     cfg = P.FeatureConfig(glcm_window=7, glcm_step=1)
     scenes = [synth_raster_numpy(90, 150, 7, np.uint8, 100 + i, cell=16) for i in range(5)]
     ref = [P.segment_raster(s, cfg, 6, 5, 9)[0].copy() for s in scenes]
-    got = []
-    for labels, res in P.segment_stream(scenes, cfg, 6, 5, 9):
-        got.append(labels.copy())                          # a yielded buffer is reused two scenes later
-        assert res.n_iter == 5
-    assert len(got) == len(ref)
-    for a, b in zip(got, ref):
-        assert a.dtype == np.int32 and np.array_equal(a, b)
+    for mode, dtype in (("int32", np.int32), ("uint8", np.uint8), ("int32_host_widen", np.int32)):
+        got = []
+        for labels, res in P.segment_stream(scenes, cfg, 6, 5, 9, labels=mode):
+            got.append(labels.copy())                      # a yielded buffer is reused two scenes later
+            assert res.n_iter == 5
+        assert len(got) == len(ref)
+        for a, b in zip(got, ref):
+            assert a.dtype == dtype and np.array_equal(a, b), mode
     assert list(P.segment_stream([], cfg)) == []
+    with pytest.raises(ValueError):
+        list(P.segment_stream(scenes[:1], cfg, labels="int64"))
 
 
 def test_full_size_scene_properties(P):
