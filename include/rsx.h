@@ -52,6 +52,7 @@ int64_t rsx_launch_count(void);
 /* Integer tuning knobs (kernel-variant switches for the profiling tools and A/B tests; never needed for correct results).
  * A knob that was never set falls back to the environment variable RSX_<NAME IN UPPER CASE>, then to the built-in default. */
 int rsx_set_option(const char* name, int value);
+int rsx_get_option(const char* name, int dflt); /* the value a call site with this default would see */
 /* Copies `bytes` from device memory into PAGE-LOCKED host memory (cudaHostAlloc / torch pin_memory: under unified addressing
  * the device writes through the same pointer) with a kernel, on `stream`; the caller synchronises.  For the small per-scene
  * results (histograms, moments, min/max, KMeans state): unlike cudaMemcpyAsync it does not queue behind a large transfer on
@@ -274,6 +275,17 @@ int rsx_kmeans_setup(void* d_state, int D, int K, const double* h_feat_min, cons
 int rsx_kmeans_assign(const float* d_stack, int64_t plane_stride, int64_t n_px, int row_len, const void* d_state,
                       int64_t* d_acc, uint8_t* d_labels_u8, const uint8_t* d_labels_prev_u8, int32_t* d_labels_i32,
                       double* d_inertia, int update, int D, int K, rsx_stream_t stream);
+/* A delta update pass (update = 2 above) with Hamerly's bound test in front of it (K <= 8): pixels whose label provably cannot
+ * have changed since their distances were last evaluated - their slack (distance to the second nearest centre minus distance to
+ * their own) exceeds what the centres have moved since, tracked by rsx_kmeans_update inside the state - are skipped unread; the
+ * rest is evaluated exactly like rsx_kmeans_assign does.  Labels, sums, counters: identical to the unbounded pass
+ * (sklearn/cluster/_k_means_lloyd.pyx:168-218 semantics; the bound is the one of sklearn's algorithm="elkan", _k_means_elkan.pyx).
+ * d_labels_u8: labels of the previous pass, updated IN PLACE.  d_aos: float [n_px][rsx_kmeans_aos_stride(D)] scratch, d_slack:
+ * float [n_px rounded up to 4] scratch; both are written by the call with first = 1 (which reads every pixel from the planes) and
+ * maintained by the calls with first = 0.  A pass of rsx_kmeans_assign in between invalidates them (start again with first = 1). */
+int64_t rsx_kmeans_aos_stride(int D);
+int rsx_kmeans_assign_bounded(const float* d_stack, int64_t plane_stride, int64_t n_px, const void* d_state, int64_t* d_acc,
+                              uint8_t* d_labels_u8, float* d_aos, float* d_slack, int first, int D, int K, rsx_stream_t stream);
 /* d_adjust (may be NULL): int64 [K*D + K] added to the totals for this centroid computation only - the host-assisted
  * empty-cluster relocation of sklearn (_k_means_common.pyx:167-211); the running totals are not modified by it. */
 int rsx_kmeans_update(void* d_state, int64_t* d_acc, int delta, int D, const int64_t* d_adjust, rsx_stream_t stream);

@@ -18,6 +18,7 @@ SIGNATURES = {
     "rsx_abi_version": (i32, []),
     "rsx_launch_count": (i64, []),
     "rsx_set_option": (i32, [C.c_char_p, i32]),
+    "rsx_get_option": (i32, [C.c_char_p, i32]),
     "rsx_store_to_host": (i32, [vp, vp, i64, vp]),
     "rsx_raster_stats": (i32, [vp, i32, i32, i32, f64, f64, vp, vp, vp, vp, vp, vp]),
     "rsx_hist_u8": (i32, [vp, i64, i32, vp, vp]),
@@ -64,6 +65,8 @@ SIGNATURES = {
     "rsx_kmeans_state_bytes": (i64, []),
     "rsx_kmeans_setup": (i32, [vp, i32, i32, vp, vp, vp, vp, i64, vp]),
     "rsx_kmeans_assign": (i32, [vp, i64, i64, i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
+    "rsx_kmeans_aos_stride": (i64, [i32]),
+    "rsx_kmeans_assign_bounded": (i32, [vp, i64, i64, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
     "rsx_kmeans_update": (i32, [vp, vp, i32, i32, vp, vp]),
     "rsx_kmeans_fixed_point_scales": (i32, [vp, vp, vp]),
     "rsx_kpp_scratch_elems": (i64, []),
@@ -120,6 +123,11 @@ def call(name: str, *args):
 def set_option(name: str, value: int):
     """Tuning knob of the library (include/rsx.h rsx_set_option)."""
     check(load().rsx_set_option(name.encode(), int(value)), "rsx_set_option")
+
+
+def get_option(name: str, default: int) -> int:
+    """The knob's value: set_option, else the environment variable RSX_<NAME>, else `default`."""
+    return int(load().rsx_get_option(name.encode(), int(default)))
 
 
 def launch_count() -> int:

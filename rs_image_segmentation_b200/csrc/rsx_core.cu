@@ -106,6 +106,8 @@ extern "C" int rsx_set_option(const char* name, int value) {
     return RSX_OK;
 }
 
+extern "C" int rsx_get_option(const char* name, int dflt) { return name ? rsx_option(name, dflt) : dflt; }
+
 extern "C" const char* rsx_last_error(void) { return g_err; }
 extern "C" int rsx_abi_version(void) { return 1; }
 extern "C" int64_t rsx_launch_count(void) { return g_launches.load(); }

@@ -60,6 +60,18 @@ __device__ void km_derive(KmState* st) {
         // (< 2^-30).  Accumulation in the tensor core: measured 2^-22.8 of sum|terms| for 16 terms (tools/tc_probe.cu on the B200),
         // budgeted here as 2 * 2^-20 for the 48 terms.  Total 5 * 2^-20 of the magnitude per distance; two distances, 1.5x safety.
         st->tau_tc = (float)(2.0 * 1.5 * 5.0 * 9.5367431640625e-07 * e_max_mag + tag_term);
+        // Bounded passes: squared distances q_j = |x'|^2 + dist_j.  dist_j is off by at most e_max * 2^-24 (above).  x'_d is evaluated
+        // as fma(x, scale32, off32): scale32, off32 and the fma round once each, all on magnitudes below m_d = absmax scale + |off|,
+        // so |x'_d - exact| <= 3 u m_d =: eps_d and |x'_d| <= m_d; the D squares and their running sum add (D + 1) u sum m_d^2.
+        double xs_err = 0.0, m2 = 0.0;
+        for (int d = 0; d < D; ++d) {
+            const double m = st->absmax[d] * st->scale64[d] + fabs(st->min64[d] - st->mean64[d]);
+            const double eps = 3.0 * 5.9604644775390625e-08 * m;
+            xs_err += 2.0 * m * eps + eps * eps;
+            m2 += m * m;
+        }
+        xs_err += (D + 1) * 5.9604644775390625e-08 * m2;
+        st->bound_err = __double2float_ru(1.5 * (e_max * 5.9604644775390625e-08 + xs_err));
         // never-chosen padding centroids: the kernels evaluate centroids in groups of 8
         for (int j = K; j < KM_MAXK && j < ((K + 7) & ~7); ++j) {
             st->bias32[j] = 1e30f;  // finite: the index tag must not turn it into a NaN
@@ -93,6 +105,7 @@ __global__ void __launch_bounds__(KM_CTRL_THREADS) km_setup_kernel(KmState* gst)
         st->n_empty = 0;
         st->n_updates = 0;
     }
+    for (int j = threadIdx.x; j < KM_MAXK; j += blockDim.x) st->drift64[j] = 0.0, st->drift_up[j] = 0.f, st->drift_dn[j] = 0.f;
     __syncthreads();
     km_state_copy(gst, st);
 }
@@ -179,6 +192,28 @@ extern "C" int rsx_kmeans_assign(const float* d_stack, int64_t plane_stride, int
     // at K = 32 and slower at K = 16 on the B200 (the per-pixel argmin over K distances, not the FMAs, is what both are bound by;
     // DESIGN.md 4.2), so it stays an option.
     a.use_tc = rsx_option("km_tc", 0);
+    a.bounded = 0, a.aos = nullptr, a.slack = nullptr;
+    return g_part_assign[km_part_of(D)](a, (cudaStream_t)stream);
+}
+
+extern "C" int64_t rsx_kmeans_aos_stride(int D) { return D >= 1 && D <= KM_MAXD ? (int64_t)km_aos_stride(D) : 0; }
+
+// A delta pass with Hamerly's test in front (K <= 8; km_bounded_kernel in rsx_kmeans_part.cu).  Labels are updated IN PLACE.
+extern "C" int rsx_kmeans_assign_bounded(const float* d_stack, int64_t plane_stride, int64_t n_px, const void* d_state, int64_t* d_acc,
+                                         uint8_t* d_labels_u8, float* d_aos, float* d_slack, int first, int D, int K, rsx_stream_t stream) {
+    RSX_REQUIRE(d_stack && d_state && d_acc && d_labels_u8 && d_aos && d_slack && n_px > 0, "rsx_kmeans_assign_bounded: null argument");
+    RSX_REQUIRE(D >= 1 && D <= KM_MAXD && K >= 1 && K <= KM_MAXK, "rsx_kmeans_assign_bounded: D/K out of range");
+    RSX_REQUIRE((((uintptr_t)d_labels_u8) & 3) == 0 && (((uintptr_t)d_aos | (uintptr_t)d_slack) & 15) == 0, "rsx_kmeans_assign_bounded: buffers must be aligned");
+    if (D > km_part_hi(KM_NUM_PARTS - 1)) {
+        rsx_set_error("rsx_kmeans_assign_bounded: D=%d not compiled (1..%d)", D, km_part_hi(KM_NUM_PARTS - 1));
+        return RSX_ERR_UNSUPPORTED;
+    }
+    KmLaunch a;
+    memset(&a, 0, sizeof(a));
+    a.stack = d_stack, a.plane_stride = plane_stride, a.n_px = n_px, a.row_len = 4096;
+    a.acc = reinterpret_cast<long long*>(d_acc), a.lab8 = d_labels_u8;
+    a.mode = KM_DELTA, a.D = D, a.K = K;
+    a.bounded = first ? 1 : 2, a.aos = d_aos, a.slack = d_slack;
     return g_part_assign[km_part_of(D)](a, (cudaStream_t)stream);
 }
 
@@ -298,6 +333,18 @@ __global__ void __launch_bounds__(KM_CTRL_THREADS) km_update_kernel(KmState* gst
         st->shift_sq = s;
         st->n_empty += e;
         st->n_updates += 1;
+    }
+    // Hamerly drift of every label: its own centre's move plus the largest move among the others (rounded outwards: the moves
+    // carry ~1e-15 of relative error, the float copies are pushed one further ulp apart)
+    for (int j = threadIdx.x; j < K; j += blockDim.x) {
+        double other = 0.0;
+        for (int i = 0; i < K; ++i)
+            if (i != j) other = fmax(other, shift_part[i]);
+        const double inc = (sqrt(shift_part[j]) + sqrt(other)) * (1.0 + 1e-9);
+        const double c = st->drift64[j] + inc;
+        st->drift64[j] = c;
+        st->drift_up[j] = nextafterf(__double2float_ru(c), INFINITY);
+        st->drift_dn[j] = fmaxf(nextafterf(__double2float_rd(c), -INFINITY), 0.f);
     }
     __syncthreads();
     km_derive(st);

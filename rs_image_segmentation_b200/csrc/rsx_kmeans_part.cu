@@ -435,7 +435,14 @@ __global__ void __launch_bounds__(KM_THREADS, 2) km_full_kernel(const float* __r
 //              not fit in shared memory)
 constexpr int KM_WARPS = KM_THREADS / 32;
 constexpr int KM_BLOCK_PX = KM_THREADS * 4;
+// staged planes are 4 floats apart from a whole number of bank rows: the delta update reads one pixel of every plane with lane =
+// feature (a 14-way bank conflict at a stride of 512 floats, 12 extra wavefronts per moved pixel; 2-way at 516)
+constexpr int KM_STAGE_STRIDE = KM_BLOCK_PX + 4;
 
+// Delta update of the sums: the pixels of this warp's 128 whose label changed move their sample from the old cluster's sums to the
+// new one's: lane = feature (lane D = the count), one warp-uniform iteration per moved pixel (loops over the set bits, nothing
+// predicated off).  (A shared-memory list of the moved pixels walked by two half-warps was measured: its 2 KB cost the fourth
+// CTA per SM, 0.46 -> 0.585 ms per late pass.)
 template <int D>
 __device__ __forceinline__ void km_move_samples(const float* __restrict__ st, int warp_px, unsigned cm, uint32_t old_packed, uint32_t new_packed,
                                                 long long* __restrict__ wacc, float my_pow2) {
@@ -444,19 +451,18 @@ __device__ __forceinline__ void km_move_samples(const float* __restrict__ st, in
     while (b) {
         const int src = __ffs(b) - 1;
         b &= b - 1;
-        const unsigned m = __shfl_sync(0xffffffffu, cm, src);
+        unsigned m = __shfl_sync(0xffffffffu, cm, src);
         const uint32_t ov = __shfl_sync(0xffffffffu, old_packed, src), nv = __shfl_sync(0xffffffffu, new_packed, src);
         if (lane <= D) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                if (m & (1u << i)) {
-                    const int from = (int)((ov >> (8 * i)) & 0xffu), to = (int)((nv >> (8 * i)) & 0xffu);
-                    long long q = 1;
-                    if (lane < D) q = __float2ll_rn(st[lane * KM_BLOCK_PX + warp_px + 4 * src + i] * my_pow2);
-                    wacc[to * (D + 1) + lane] += q;
-                    if (from < KM_MAXK) wacc[from * (D + 1) + lane] -= q;
-                }
-            }
+            do {  // warp uniform: m is the same in every lane
+                const int i = __ffs(m) - 1;
+                m &= m - 1;
+                const int from = (int)((ov >> (8 * i)) & 0xffu), to = (int)((nv >> (8 * i)) & 0xffu);
+                long long q = 1;
+                if (lane < D) q = __float2ll_rn(st[lane * KM_STAGE_STRIDE + warp_px + 4 * src + i] * my_pow2);
+                wacc[to * (D + 1) + lane] += q;
+                if (from < KM_MAXK) wacc[from * (D + 1) + lane] -= q;
+            } while (m);
         }
     }
 }
@@ -468,7 +474,7 @@ template <int D>
 __device__ __forceinline__ void km_move_in_all(const float* __restrict__ st, int warp_px, unsigned valid_mask, uint32_t new_packed,
                                                long long* __restrict__ wacc, float my_pow2) {
     const int lane = threadIdx.x & 31;
-    const float* mine = st + min(lane, D - 1) * KM_BLOCK_PX + warp_px;
+    const float* mine = st + min(lane, D - 1) * KM_STAGE_STRIDE + warp_px;
 #pragma unroll 2
     for (int src = 0; src < 32; ++src) {
         if (!((valid_mask >> src) & 1u)) break;  // valid threads are a prefix of the warp
@@ -507,7 +513,7 @@ __global__ void __launch_bounds__(KM_THREADS, km_ctas_per_sm(D)) km_stream_kerne
     const int K = g_km.K;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     float* stages = reinterpret_cast<float*>(km_smem);                                                          // [n_stages][D][512]
-    long long* wacc_all = reinterpret_cast<long long*>(km_smem + (size_t)n_stages * D * KM_BLOCK_PX * 4);       // [4 warps][K][D+1]
+    long long* wacc_all = reinterpret_cast<long long*>(km_smem + (size_t)n_stages * D * KM_STAGE_STRIDE * 4);       // [4 warps][K][D+1]
     uint64_t* full = reinterpret_cast<uint64_t*>(wacc_all + (SUMS ? KM_WARPS * K * (D + 1) : 0));               // [n_stages]
     uint64_t* empty = full + n_stages;                                                                          // [n_stages]
     int* ticket = reinterpret_cast<int*>(empty + n_stages);                                                     // [n_stages] (+ pad): refills issued per stage
@@ -548,9 +554,9 @@ __global__ void __launch_bounds__(KM_THREADS, km_ctas_per_sm(D)) km_stream_kerne
         const unsigned bytes = (unsigned)min((int64_t)KM_BLOCK_PX, n4 - p0) * 4u;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads of this stage precede the async refill
         mbar_expect_tx(&full[s], bytes * D);
-        float* dst = stages + (size_t)s * D * KM_BLOCK_PX;
+        float* dst = stages + (size_t)s * D * KM_STAGE_STRIDE;
 #pragma unroll 1
-        for (int d = 0; d < D; ++d) bulk_g2s(dst + d * KM_BLOCK_PX, stack + d * plane_stride + p0, bytes, &full[s]);
+        for (int d = 0; d < D; ++d) bulk_g2s(dst + d * KM_STAGE_STRIDE, stack + d * plane_stride + p0, bytes, &full[s]);
     };
     if (tid == 0)
         for (int s = 0; s < n_stages; ++s) {
@@ -575,13 +581,13 @@ __global__ void __launch_bounds__(KM_THREADS, km_ctas_per_sm(D)) km_stream_kerne
             if (prev8 && pn < n4) pv_next = __ldg(reinterpret_cast<const uint32_t*>(prev8 + pn));
         }
         mbar_wait(&full[s], parity);
-        const float* st = stages + (size_t)s * D * KM_BLOCK_PX;
+        const float* st = stages + (size_t)s * D * KM_STAGE_STRIDE;
         uint32_t packed = 0, diff = 0;
         if (KU == 8) {
             if (valid) {
                 float4 v[D];
 #pragma unroll
-                for (int d = 0; d < D; ++d) v[d] = *reinterpret_cast<const float4*>(st + d * KM_BLOCK_PX + 4 * tid);
+                for (int d = 0; d < D; ++d) v[d] = *reinterpret_cast<const float4*>(st + d * KM_STAGE_STRIDE + 4 * tid);
                 float b[4], sc[4];
                 km_distances<D, KU>(v, K, wsm, b, sc);
                 int l[4];
@@ -614,7 +620,7 @@ __global__ void __launch_bounds__(KM_THREADS, km_ctas_per_sm(D)) km_stream_kerne
             if (valid) {
                 float4 v[D];
 #pragma unroll
-                for (int d = 0; d < D; ++d) v[d] = *reinterpret_cast<const float4*>(st + d * KM_BLOCK_PX + 4 * tid);
+                for (int d = 0; d < D; ++d) v[d] = *reinterpret_cast<const float4*>(st + d * KM_STAGE_STRIDE + 4 * tid);
                 float b[4], sc[4];
                 km_distances<D, KU>(v, K, wsm, b, sc);
                 if (warpwide) {
@@ -665,7 +671,7 @@ __global__ void __launch_bounds__(KM_THREADS, km_ctas_per_sm(D)) km_stream_kerne
                             float dd = 0.f;
 #pragma unroll
                             for (int d = 0; d < D; ++d) {
-                                const float df = fmaf(st[d * KM_BLOCK_PX + 4 * tid + i], g_km.scale32[d], g_km.off32[d]) - cent[d];
+                                const float df = fmaf(st[d * KM_STAGE_STRIDE + 4 * tid + i], g_km.scale32[d], g_km.off32[d]) - cent[d];
                                 dd = fmaf(df, df, dd);
                             }
                             dex[i] = (double)dd;
@@ -1216,6 +1222,197 @@ __global__ void __launch_bounds__(KM_THREADS, 4) km_tc_kernel(const float* __res
 }
 
 // ----------------------------------------------------------------------------- launchers
+// ============================================================================= kernel D: bounded passes, K <= 8
+// Hamerly's test in front of the assignment (J. Hamerly, "Making k-means even faster", SDM 2010; sklearn's own algorithm="elkan" is
+// the same idea): a pixel keeps, next to its label, slack' = (distance to the second nearest centre - distance to its own centre)
+// + drift[label] at the time both were computed.  Centres move; by the triangle inequality the pixel's label cannot change while
+// slack' > drift[label] now (KmState::drift64).  Such a pixel is skipped without reading its features: 5 bytes (slack', label) instead
+// of 4 D.  The others are gathered from a pixel-interleaved copy of the stack (one to three whole sectors per pixel instead of D
+// sectors from the planes), evaluated exactly as in kernel B (fp32 distances, float64 inside the near-tie band) and their bound is
+// renewed.  Labels, sums and counters are what a delta pass of kernel B produces - every skipped pixel is one whose label provably
+// stays - so the centroids stay bit-identical.
+//   Rounding: the fp32 squared distances q_j = |x'|^2 + dist_j are within bound_err of the exact ones (rsx_kmeans.cu); the slack is
+//   sqrt_rd(q_second - err) - sqrt_ru(q_best + err), sums and drift copies are rounded outwards; a pixel decided in float64 gets
+//   slack' = -inf (looked at again in the next pass).
+//   FIRST = true: the first bounded pass reads the planes (every pixel) and writes the interleaved copy and the slacks.
+constexpr int KB_THREADS = 256;
+constexpr int KB_TILE = KB_THREADS * 4;
+
+template <int D, bool FIRST>
+__global__ void __launch_bounds__(KB_THREADS, D > 16 ? 2 : 4) km_bounded_kernel(const float* __restrict__ stack, int64_t plane_stride, int64_t n_px,
+                                                                             long long* __restrict__ gacc, uint8_t* __restrict__ lab8,
+                                                                             float* __restrict__ aos, float* __restrict__ slack) {
+    constexpr int DP = km_aos_stride(D);
+    __shared__ long long sacc[KM_SLOTS * (D + 1)];
+    __shared__ unsigned list[KB_TILE];
+    __shared__ int n_list;
+    __shared__ float drift_up[KM_SLOTS], drift_dn[KM_SLOTS];  // lanes index them by label: shared memory broadcasts, the constant bank replays
+    const int K = g_km.K;
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int i = tid; i < KM_SLOTS * (D + 1); i += KB_THREADS) sacc[i] = 0;
+    if (tid < KM_SLOTS) drift_up[tid] = g_km.drift_up[tid], drift_dn[tid] = g_km.drift_dn[tid];
+    if (tid == 0) n_list = 0;
+    __syncthreads();
+    const int64_t n_tiles = (n_px + KB_TILE - 1) / KB_TILE;
+    const float err = g_km.bound_err, tau = g_km.tau_tight;
+    unsigned ties = 0, changed = 0;
+
+    // slack' and labels of this thread's four pixels in the next tile: in flight while the current tile is evaluated
+    float4 sp_next = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t lb_next = 0;
+    auto prefetch = [&](int64_t tile) {
+        const int64_t p = tile * KB_TILE + 4 * tid;
+        if (!FIRST && tile < n_tiles && p < n_px) {
+            sp_next = __ldcs(reinterpret_cast<const float4*>(slack + p));
+            lb_next = __ldcs(reinterpret_cast<const uint32_t*>(lab8 + p));
+        }
+    };
+    prefetch(blockIdx.x);
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t p0 = tile * KB_TILE;
+        int count;
+        if (!FIRST) {
+            // ---- phase 1: Hamerly's test, the pixels that fail it are listed (local index | label << 16)
+            const float4 sp = sp_next;
+            const uint32_t lb = lb_next;
+            const int64_t p = p0 + 4 * tid;
+            unsigned mask = 0;
+            if (p < n_px) {
+                const float spv[4] = {sp.x, sp.y, sp.z, sp.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const unsigned l = (lb >> (8 * i)) & 0xffu;
+                                        if (p + i < n_px && !(spv[i] > drift_up[l & (KM_SLOTS - 1)])) mask |= 1u << i;
+                }
+            }
+            prefetch(tile + gridDim.x);
+            const int mine = __popc(mask);
+            int incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            int base = 0;
+            if (lane == 31 && incl) base = atomicAdd(&n_list, incl);
+            base = __shfl_sync(0xffffffffu, base, 31);
+            int at = base + incl - mine;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (mask & (1u << i)) list[at++] = (unsigned)(4 * tid + i) | (((lb >> (8 * i)) & 0xffu) << 16);
+            __syncthreads();
+            count = n_list;
+        } else {
+            count = (int)min((int64_t)KB_TILE, n_px - p0);
+        }
+        // ---- phase 2: the listed pixels
+        for (int e = tid; e < count; e += KB_THREADS) {
+            int local, old;
+            if (FIRST) {
+                local = e;
+                old = lab8[p0 + e];
+            } else {
+                const unsigned it = list[e];
+                local = (int)(it & 0xffffu), old = (int)(it >> 16);
+            }
+            const int64_t p = p0 + local;
+            float x[DP];
+            if (FIRST) {
+#pragma unroll
+                for (int d = 0; d < D; ++d) x[d] = __ldcs(stack + d * plane_stride + p);
+#pragma unroll
+                for (int d = D; d < DP; ++d) x[d] = 0.f;
+                float4* row = reinterpret_cast<float4*>(aos + p * DP);
+#pragma unroll
+                for (int d = 0; d < DP; d += 4) row[d / 4] = make_float4(x[d], x[d + 1], x[d + 2], x[d + 3]);
+            } else {
+                const float4* row = reinterpret_cast<const float4*>(aos + p * DP);
+#pragma unroll
+                for (int d = 0; d < DP; d += 4) {
+                    const float4 v = __ldg(row + d / 4);
+                    x[d] = v.x, x[d + 1] = v.y, x[d + 2] = v.z, x[d + 3] = v.w;
+                }
+            }
+            float xs = 0.f;
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                const float xc = fmaf(x[d], g_km.scale32[d], g_km.off32[d]);
+                xs = fmaf(xc, xc, xs);
+            }
+            float b = INFINITY, sc = INFINITY;
+            int bi = 0;
+#pragma unroll
+            for (int j = 0; j < KM_SLOTS; ++j) {
+                float a = g_km.bias32[j];
+#pragma unroll
+                for (int d = 0; d < D; ++d) a = fmaf(x[d], g_km.w32[j * KM_MAXD + d], a);
+                KM_ARGMIN_STEP(a, b, sc, bi, j)
+            }
+            float sp_new;
+            if (!(sc - b > tau)) {  // near tie (or NaN): float64 decides, no bound
+                double de;
+                bi = km_exact_argmin<D>(stack, plane_stride, p, &de);
+                ++ties;
+                sp_new = -INFINITY;
+            } else {
+                const float lo2 = __fsqrt_rd(fmaxf(__fsub_rd(__fadd_rd(xs, sc), err), 0.f));
+                const float hi1 = __fsqrt_ru(fmaxf(__fadd_ru(__fadd_ru(xs, b), err), 0.f));
+                sp_new = __fadd_rd(__fsub_rd(lo2, hi1), drift_dn[bi]);
+            }
+            slack[p] = sp_new;
+            if (bi != old) {
+                ++changed;
+                lab8[p] = (uint8_t)bi;
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    const long long q = __float2ll_rn(x[d] * g_km.pow2[d]);
+                    km_smem_add64(&sacc[bi * (D + 1) + d], q);
+                    if (old < KM_MAXK) km_smem_add64(&sacc[old * (D + 1) + d], -q);
+                }
+                km_smem_add64(&sacc[bi * (D + 1) + D], 1);
+                if (old < KM_MAXK) km_smem_add64(&sacc[old * (D + 1) + D], -1);
+            }
+        }
+        if (!FIRST) {
+            __syncthreads();
+            if (tid == 0) n_list = 0;
+            // the next phase 1 adds to n_list only after its own loads; the barrier inside it orders the reset before the reads
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < K * (D + 1); i += KB_THREADS) {
+        const long long t = sacc[i];
+        if (t) {
+            const int j = i / (D + 1), d = i % (D + 1);
+            long long* dst = d < D ? &gacc[j * D + d] : &gacc[K * D + j];
+            atomicAdd(reinterpret_cast<unsigned long long*>(dst), (unsigned long long)t);
+        }
+    }
+    km_commit_counters(gacc, K, D, ties, changed, 0.0, nullptr, false);
+}
+
+template <int D>
+static int km_launch_bounded(const KmLaunch& a, cudaStream_t s) {
+    static int per_sm[2] = {0, 0}, cfg_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cfg_dev != dev) {
+        cfg_dev = dev;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], km_bounded_kernel<D, false>, KB_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], km_bounded_kernel<D, true>, KB_THREADS, 0);
+    }
+    const bool first = a.bounded == 1;
+    const int64_t n_tiles = ceil_div(a.n_px, (int64_t)KB_TILE);
+    const int grid = (int)max((int64_t)1, min(n_tiles, (int64_t)rsx_num_sms() * max(1, per_sm[first ? 1 : 0])));
+    if (first)
+        km_bounded_kernel<D, true><<<grid, KB_THREADS, 0, s>>>(a.stack, a.plane_stride, a.n_px, a.acc, a.lab8, a.aos, a.slack);
+    else
+        km_bounded_kernel<D, false><<<grid, KB_THREADS, 0, s>>>(a.stack, a.plane_stride, a.n_px, a.acc, a.lab8, a.aos, a.slack);
+    return rsx_check_launch("km_bounded");
+}
+
 template <int D>
 static int km_launch_full(const KmLaunch& a, cudaStream_t s) {
     const int smem = KmSmem<D>::CACHE_BYTES;
@@ -1247,7 +1444,7 @@ static int km_launch_stream(const KmLaunch& a, cudaStream_t s) {
     const int acc_bytes = MODE == KM_ASSIGN ? 0 : KM_WARPS * a.K * (D + 1) * 8;
     const int w_bytes = KU == 0 ? (((D + 1) * ((a.K + 7) & ~7) + (INERTIA ? a.K * D : 0)) * 4 + 15) / 16 * 16 : 0;
     const int c64_bytes = WARPX ? (D + 1) * ((a.K + 31) & ~31) * 8 : 0;
-    auto c64_off = [&](int stages) { return stages * D * KM_BLOCK_PX * 4 + acc_bytes + 2 * stages * 8 + 16 + w_bytes; };
+    auto c64_off = [&](int stages) { return stages * D * KM_STAGE_STRIDE * 4 + acc_bytes + 2 * stages * 8 + 16 + w_bytes; };
     auto smem_for = [&](int stages) { return c64_off(stages) + c64_bytes; };
     // stages: enough blocks in flight per SM to cover HBM latency at full bandwidth (~64 KB/SM), within shared memory
     static int cfg_K = -1, cfg_stages = 0, cfg_per_sm = 0, cfg_dev = -1, cfg_req = -1;  // per kernel instantiation
@@ -1353,6 +1550,13 @@ static int km_launch2(const KmLaunch& a, cudaStream_t s) {
 // lanes would idle: +6 %).
 template <int D>
 static int km_launch(const KmLaunch& a, cudaStream_t s) {
+    if (a.bounded) {
+        if (a.K > KM_SLOTS) {
+            rsx_set_error("rsx_kmeans_assign_bounded: K=%d (bounded passes are compiled for K <= %d)", a.K, KM_SLOTS);
+            return RSX_ERR_UNSUPPORTED;
+        }
+        return km_launch_bounded<D>(a, s);
+    }
     if (a.K <= 8) return km_launch2<D, 8, false>(a, s);
     if (a.K <= 16) return km_launch2<D, 0, false>(a, s);
     return km_launch2<D, 0, true>(a, s);

@@ -28,6 +28,13 @@ struct __align__(16) KmState {
     int n_updates;
     int tag_bits;  // width of the index tag in the fp32 distances: 3 (K <= 8), 4, 5, 6
     float tau_tc;  // near-tie band of the tensor-core (3 x TF32) distances, tag included
+    // Bounded passes (km_bounded_kernel): Hamerly's test.  A pixel whose stored slack (distance to the second nearest minus distance
+    // to its own centre, a rigorous lower bound) exceeds what its centre and the fastest other centre have moved since cannot
+    // change its label and is skipped unread.  drift64[j] = sum over the updates of |dc_j| + max_{i != j} |dc_i|.
+    double drift64[KM_MAXK];
+    float drift_up[KM_MAXK], drift_dn[KM_MAXK];  // drift64 rounded outwards (one float ulp beyond)
+    float bound_err;                             // error bound of the fp32 squared distances |x'|^2 + dist_j (tau_tight + that of |x'|^2)
+    float pad_[3];
 };
 
 
@@ -56,7 +63,12 @@ struct KmLaunch {
     int pf_rows;   // full-pass kernel: L2 prefetch distance in rows (0 = off)
     int n_stages;  // streaming kernel: blocks in flight per CTA (0 = choose)
     int use_tc;    // K > 8, D <= 13: distances on the tensor cores (tcgen05, 3 x TF32 split); 0 = the fp32 FFMA2 path
+    // bounded passes (K <= 8): 0 = off; 1 = first one (reads the planes, writes the pixel-interleaved copy + slacks); 2 = later ones
+    int bounded;
+    float* aos;    // [n_px][km_aos_stride(D)] pixel-interleaved copy of the stack (scattered reads cost 1-3 sectors instead of D)
+    float* slack;  // [n_px rounded up to 4] slack + drift of the label at the time it was computed
 };
+__host__ __device__ constexpr int km_aos_stride(int D) { return (D + 7) & ~7; }  // whole 32-byte sectors per pixel
 typedef int (*km_assign_fn)(const KmLaunch&, cudaStream_t);
 typedef int (*km_publish_fn)(const void* d_state, cudaStream_t);
 #define KM_DECLARE_PART(N)                                      \

@@ -389,7 +389,8 @@ class DeviceKMeans:
     """Lloyd iterations on a planar float32 stack that stays in HBM."""
 
     def __init__(self, planes: torch.Tensor, n_px: int, D: int, K: int, feat_min, feat_max, n_global: int, row_len: int,
-                 comm: Optional[Comm] = None, timer: StageTimer = NO_TIMER, delta: bool = True, full_passes: int = 3):
+                 comm: Optional[Comm] = None, timer: StageTimer = NO_TIMER, delta: bool = True, full_passes: Optional[int] = None,
+                 bounded: Optional[bool] = None):
         require_cuda()
         self.comm = comm or Comm()
         self.timer = timer
@@ -410,7 +411,17 @@ class DeviceKMeans:
         self.delta = bool(delta)
         # K <= 8: the first passes relabel > 7 % of the pixels, where recomputing the sums with the per-thread accumulators
         # (0.72 ms at 49 Mpx) beats moving that many samples; any split gives the same integers
+        # K <= 8: the delta passes carry Hamerly's bound test (rsx_kmeans_assign_bounded): pixels that provably keep their label
+        # are skipped unread; the others are gathered from a pixel-interleaved copy of the stack (scratch: 4 * (aos_stride + 1)
+        # bytes per pixel).  Same labels, sums and counters as the unbounded passes.
+        if bounded is None:
+            bounded = bool(_lib.get_option("km_bounded", 0))
+        self.bounded = bool(bounded) and self.delta and K <= 8
+        if full_passes is None:
+            full_passes = _lib.get_option("km_full_passes", 3)
         self.full_passes = max(1, int(full_passes))
+        self._aos = self._slack = self._bound_plane = None
+        self._bounds_valid = False
         self._labels = None
         self._passes = 0
         # several GPUs: the update kernels reduce the ranks' sums themselves through peer-mapped memory (no collective per
@@ -441,6 +452,7 @@ class DeviceKMeans:
         self._mu = mu
         self.acc.zero_()
         self._passes = 0
+        self._bounds_valid = False
         if self.peers is not None:
             self.peers.zero(stream_ptr())
         _lib.call("rsx_kmeans_setup", ptr(self.state), self.D, self.K, hptr(self.fmin), hptr(self.fmax), hptr(mu), hptr(c0),
@@ -471,7 +483,22 @@ class DeviceKMeans:
         d_acc = ptr(self.acc)
         if peer_reduce and self.peers is not None:
             self._peer_seq, d_acc = self.peers.next_pass()       # this pass accumulates into the peer-mapped block
-        if self.n_px:
+        if mode == 2 and self.bounded:
+            # labels in place: the plane that holds the previous pass (the first bounded pass), the same one from then on
+            first = not self._bounds_valid
+            lab = prev if first else self._bound_plane
+            self._bound_plane = self._cur_labels = cur = lab
+            if self.n_px:
+                if self._aos is None:
+                    stride = int(_lib.load().rsx_kmeans_aos_stride(self.D))
+                    self._aos = torch.empty(self.n_px * stride, dtype=torch.float32, device=self.planes.device)
+                    self._slack = torch.empty((self.n_px + 3) // 4 * 4, dtype=torch.float32, device=self.planes.device)
+                with self.timer("kmeans_assign_bounded_first" if first else "kmeans_assign_delta"):
+                    _lib.call("rsx_kmeans_assign_bounded", ptr(self.planes), self.stride, self.n_px, ptr(self.state), d_acc, ptr(lab),
+                              ptr(self._aos), ptr(self._slack), 1 if first else 0, self.D, self.K, stream_ptr())
+            self._bounds_valid = True
+        elif self.n_px:
+            self._bounds_valid = False
             with self.timer("kmeans_assign_delta" if mode == 2 else "kmeans_assign_full"):
                 _lib.call("rsx_kmeans_assign", ptr(self.planes), self.stride, self.n_px, self.row_len, ptr(self.state), d_acc,
                           ptr(cur), ptr(prev), None, None, mode, self.D, self.K, stream_ptr())

@@ -223,6 +223,48 @@ def test_kmeans_delta_passes_equal_full_passes(P, K, D, n_iter):
     assert out[False][4] == out[True][4]
 
 
+@pytest.mark.parametrize("K,D,n_iter,full_passes", [(8, 13, 14, 3), (5, 6, 10, 1), (7, 22, 9, 2), (3, 17, 9, 3)])
+def test_kmeans_bounded_passes_equal_unbounded(P, K, D, n_iter, full_passes):
+    """Delta passes behind Hamerly's bound test (rsx_kmeans_assign_bounded: pixels that provably keep their label are skipped,
+    the others gathered from the pixel-interleaved copy) leave the same labels after EVERY pass, the same integer totals and
+    centroids as the unbounded passes - and they do skip pixels."""
+    import torch
+    n_px = 30011 + K                                                       # ragged: not a multiple of 4 for some K
+    rng = np.random.default_rng(100 * D + K)
+    X = (rng.normal(size=(n_px, 3)) @ rng.normal(size=(3, D)) + 0.3 * rng.normal(size=(n_px, D))) * rng.uniform(0.01, 50.0, size=D) + rng.uniform(-5, 5, size=D)
+    X = X.astype(np.float32)
+    stride = (n_px + 31) // 32 * 32
+    planes = torch.zeros((D, stride), dtype=torch.float32, device="cuda")
+    planes[:, :n_px] = torch.from_numpy(np.ascontiguousarray(X.T)).cuda()
+
+    class fr:                                                              # what DeviceKMeans needs of a FeatureResult
+        pass
+    fr.planes, fr.n_px, fr.W = planes, n_px, 257
+    mn, mx = X.min(axis=0), X.max(axis=0)
+    runs = {}
+    for bounded in (False, True):
+        km = P.DeviceKMeans(fr.planes, fr.n_px, D, K, mn[:D], mx[:D], fr.n_px, fr.W, bounded=bounded, full_passes=full_passes)
+        c0 = km.scale_rows(X[P.draw_init_indices(fr.n_px, K, 5)])
+        km.setup(c0)
+        per_pass = []
+        for _ in range(n_iter):
+            mode = km.assign_pass()
+            per_pass.append((km._cur_labels[:fr.n_px].clone(), km.acc[:K * D + K].clone(), int(km.acc[km.n_acc - 1])))
+            km.update(mode)
+        res = km._result(km.finish(True), n_iter)
+        slack = km._slack[:fr.n_px].clone() if bounded else None
+        runs[bounded] = (per_pass, res, km.acc[km.n_acc:km.n_acc + K * D + K].clone(), slack)
+    for i, (a, b) in enumerate(zip(runs[False][0], runs[True][0])):
+        assert torch.equal(a[0], b[0]), f"labels differ after pass {i}"
+        assert torch.equal(a[1], b[1]), f"pass sums differ in pass {i}"
+        assert a[2] == b[2], f"changed-label counter differs in pass {i}"
+    assert torch.equal(runs[False][2], runs[True][2])
+    assert np.array_equal(runs[False][1].centroids, runs[True][1].centroids)
+    assert torch.equal(runs[False][1].labels, runs[True][1].labels)
+    # the bound did something: after the last pass most pixels hold a slack above their label's drift (would be skipped next)
+    assert float((runs[True][3] > 0).float().mean()) > 0.5
+
+
 def test_kmeans_changed_counter(P):
     """The changed-label counter of an update pass equals the number of labels that differ from the previous pass."""
     import torch
