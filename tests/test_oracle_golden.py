@@ -79,6 +79,29 @@ def test_lloyd_restatements_agree(aa_crop):
     assert abs(i1 - i2) <= 1e-9 * i1
 
 
+def test_cv2_blur_is_a_correctly_rounded_double_sum(aa_crop):
+    """The N2 local-std kernel (rsx_stencil.cu local_std_kernel) sums the 25 taps in double in its own order and rounds
+    (float)(sum * 1/25) once.  cv2.blur, which the reference calls (indices.py:531-548), keeps running double sums; the two
+    orders never reach the float32 result, so the kernel can be - and is tested to be - bit exact against cv2."""
+    import cv2
+    from oracle import features as of
+    b = of.robust_normalize(aa_crop["stage1_u8"][3].astype(np.float32))
+    rng = np.random.default_rng(3)
+    for img in (b, (rng.random((301, 517), dtype=np.float32) * 3 - 1)):
+        H, W = img.shape
+        for ks in (3, 5, 7):
+            R = ks // 2
+            for a in (img, img * img):
+                p = np.pad(a.astype(np.float64), R, mode="reflect")
+                rows = np.zeros((H + 2 * R, W))
+                for dx in range(ks):
+                    rows += p[:, dx:dx + W]
+                s = np.zeros((H, W))
+                for dy in range(ks):
+                    s += rows[dy:dy + H]
+                assert np.array_equal((s * (1.0 / (ks * ks))).astype(np.float32), cv2.blur(a, (ks, ks)))
+
+
 def test_full_scene_table(aa_full_stats):
     # the numbers quoted in SURVEY.md 8(c), regenerated from the reference
     assert aa_full_stats["pct"].tolist() == [[59, 90], [18, 77], [8, 59], [28, 80], [10, 97], [63, 177], [4, 59]]

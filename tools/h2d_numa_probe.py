@@ -23,10 +23,25 @@ if rank == 0:
     os.system("nvidia-smi topo -m 2>&1 | head -24; lscpu | grep -i -E 'numa|socket|model name' ")
 
 
-def measure(tag):
+def host_alloc(n, write_combined):
+    """n bytes of page-locked host memory as a uint8 tensor; write_combined: cudaHostAllocWriteCombined (not snooped, slow to read
+    from the CPU, meant for buffers the CPU only writes and the GPU only reads)."""
+    if not write_combined:
+        return torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    import ctypes
+    import numpy as np
+    rt = ctypes.CDLL("libcudart.so")
+    p = ctypes.c_void_p()
+    rc = rt.cudaHostAlloc(ctypes.byref(p), ctypes.c_size_t(n), ctypes.c_uint(0x04))
+    assert rc == 0, rc
+    return torch.from_numpy(np.ctypeslib.as_array((ctypes.c_uint8 * n).from_address(p.value)))
+
+
+def measure(tag, write_combined=False):
     n = 343_000_000
-    host = torch.empty(n, dtype=torch.uint8, pin_memory=True)
-    host.fill_(1)
+    host = host_alloc(n, write_combined)
+    host[::4096] = 1                      # touch every page
+    print(f"rank {rank}: {tag}: is_pinned {host.is_pinned()}", flush=True) if rank == 0 else None
     out = torch.empty(196_000_000, dtype=torch.uint8, pin_memory=True)
     dev = torch.empty(n, dtype=torch.uint8, device="cuda")
     up, down = torch.cuda.Stream(), torch.cuda.Stream()
@@ -49,6 +64,7 @@ def measure(tag):
 
 
 measure("default placement")
+measure("write-combined source", write_combined=True)
 if cpus:
     os.sched_setaffinity(0, cpus)
     measure("bound to GPU-local CPUs")
