@@ -266,6 +266,13 @@ int64_t rsx_kmeans_state_bytes(void);
  * Not re-entrant: the state is mirrored in one __constant__ block per process. */
 int rsx_kmeans_setup(void* d_state, int D, int K, const double* h_feat_min, const double* h_feat_max,
                      const double* h_mean_scaled, const double* h_init_centroids, int64_t n_px_global, rsx_stream_t stream);
+/* The same set-up without a host round trip: the per-feature range is taken from D min/max trackers on the device (d_minmax:
+ * uint32 [D][2] as maintained by the feature kernels, see "min/max trackers"), the initial centroids from K raw feature rows on the
+ * device (d_init_rows_raw: double [K][D]; scaled by the kernel exactly like MinMaxScaler.transform, X * scale_ + min_).
+ * h_mean_scaled may be NULL (0.5 for every feature).  The state is bit-identical to rsx_kmeans_setup's for the same numbers.
+ * rsx_kmeans_read_all returns the range that was used next to what rsx_kmeans_read returns. */
+int rsx_kmeans_setup_device(void* d_state, int D, int K, const uint32_t* d_minmax, const double* d_init_rows_raw,
+                            const double* h_mean_scaled, int64_t n_px_global, rsx_stream_t stream);
 /* The caller zeroes d_acc once.  update: 0 = assign only, 1 = full update pass, 2 = delta update pass (needs d_labels_u8 and
  * d_labels_prev_u8, distinct buffers; entries >= RSX_MAX_CLUSTERS in the previous labels mean "no previous label").
  * d_labels_prev_u8 (may be NULL): labels of the previous pass; the number of pixels whose label differs is
@@ -326,6 +333,8 @@ int rsx_kmeans_fixed_point_scales(const void* d_state, double* h_pow2, rsx_strea
 /* SYNCHRONISES the stream; centroids come back in scaled, un-centred coordinates, double [K][D];
  * h_shift_sq = squared centre shift of the last update; h_empty = empty clusters met so far. */
 int rsx_kmeans_read(const void* d_state, double* h_centroids, double* h_shift_sq, int32_t* h_empty, rsx_stream_t stream);
+int rsx_kmeans_read_all(const void* d_state, double* h_centroids, double* h_shift_sq, int32_t* h_empty, double* h_feat_min,
+                        double* h_feat_max, rsx_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -65,6 +65,7 @@ SIGNATURES = {
     "rsx_kmeans_state_bytes": (i64, []),
     "rsx_kmeans_setup": (i32, [vp, i32, i32, vp, vp, vp, vp, i64, vp]),
     "rsx_kmeans_assign": (i32, [vp, i64, i64, i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
+    "rsx_kmeans_setup_device": (i32, [vp, i32, i32, vp, vp, vp, i64, vp]),
     "rsx_kmeans_aos_stride": (i64, [i32]),
     "rsx_kmeans_assign_bounded": (i32, [vp, i64, i64, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
     "rsx_kmeans_update": (i32, [vp, vp, i32, i32, vp, vp]),
@@ -75,6 +76,7 @@ SIGNATURES = {
     "rsx_kpp_distances": (i32, [vp, i64, i64, i32, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp]),
     "rsx_kpp_block_sums": (i32, [vp, i64, vp, vp]),
     "rsx_kmeans_read": (i32, [vp, vp, vp, vp, vp]),
+    "rsx_kmeans_read_all": (i32, [vp, vp, vp, vp, vp, vp, vp]),
     "rsx_kmeans_update_peers": (i32, [vp, vp, i32, i32, vp, vp, i32, i32, i64, vp]),
     "rsx_peer_alloc": (i32, [i64, vp, vp]),
     "rsx_peer_open": (i32, [vp, vp]),

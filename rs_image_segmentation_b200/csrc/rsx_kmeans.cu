@@ -110,6 +110,55 @@ __global__ void __launch_bounds__(KM_CTRL_THREADS) km_setup_kernel(KmState* gst)
     km_state_copy(gst, st);
 }
 
+// rsx_kmeans_setup without the host in between: the per-feature range comes straight from the min/max trackers the feature kernels
+// maintained, the initial centroids from raw feature rows gathered on the device.  Same IEEE operations in the same order as
+// rsx_kmeans_setup / MinMaxScaler (every product and sum rounded on its own), so the state is bit-identical.
+struct KmMean {
+    double v[KM_MAXD];
+};
+__global__ void __launch_bounds__(KM_CTRL_THREADS) km_setup_device_kernel(KmState* gst, int D, int K, const uint32_t* __restrict__ minmax,
+                                                                          const double* __restrict__ rows, const KmMean mean, long long n_global) {
+    __shared__ __align__(16) KmState sst;
+    KmState* st = &sst;
+    {
+        int4* z = reinterpret_cast<int4*>(st);
+        for (int i = threadIdx.x; i < (int)(sizeof(KmState) / 16); i += blockDim.x) z[i] = make_int4(0, 0, 0, 0);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) st->D = D, st->K = K, st->n_global = n_global;
+    int nbits = 0;
+    while ((1ll << nbits) < n_global) ++nbits;
+    const int budget = 62 - nbits;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        const double fmin = (double)ord2f(minmax[2 * d]), fmax_ = (double)ord2f(minmax[2 * d + 1]);
+        double range = __dsub_rn(fmax_, fmin);
+        if (!(range >= 10.0 * 2.220446049250313e-16)) range = 1.0;  // also for an empty tracker (+inf / -inf -> NaN)
+        const double scale = __ddiv_rn(1.0, range);
+        st->fmin64[d] = fmin, st->fmax64[d] = fmax_;
+        st->scale64[d] = scale;
+        st->min64[d] = __dsub_rn(0.0, __dmul_rn(fmin, scale));
+        st->mean64[d] = mean.v[d];
+        const double am = fmax(fabs(fmin), fabs(fmax_));
+        st->absmax[d] = am;
+        int e = 0;
+        if (am > 0) frexp(am, &e);
+        int shift = budget - e;
+        shift = shift > 100 ? 100 : (shift < -100 ? -100 : shift);
+        st->pow2[d] = (float)ldexp(1.0, shift);
+        st->inv_pow2[d] = ldexp(1.0, -shift);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < K * D; i += blockDim.x) {
+        const int j = i / D, d = i - j * D;
+        // MinMaxScaler.transform: X * scale_ + min_, then the centring
+        st->cent64[j * KM_MAXD + d] = __dsub_rn(__dadd_rn(__dmul_rn(rows[i], st->scale64[d]), st->min64[d]), st->mean64[d]);
+    }
+    __syncthreads();
+    km_derive(st);
+    __syncthreads();
+    km_state_copy(gst, st);
+}
+
 static const km_assign_fn g_part_assign[KM_NUM_PARTS] = {rsx_km_part0_assign, rsx_km_part1_assign, rsx_km_part2_assign, rsx_km_part3_assign,
                                                           rsx_km_part4_assign, rsx_km_part5_assign};
 static const km_publish_fn g_part_publish[KM_NUM_PARTS] = {rsx_km_part0_publish, rsx_km_part1_publish, rsx_km_part2_publish, rsx_km_part3_publish,
@@ -141,6 +190,7 @@ extern "C" int rsx_kmeans_setup(void* d_state, int D, int K, const double* h_fea
         h.mean64[d] = h_mean_scaled[d];
         double am = fmax(fabs(h_feat_min[d]), fabs(h_feat_max[d]));
         h.absmax[d] = am;
+        h.fmin64[d] = h_feat_min[d], h.fmax64[d] = h_feat_max[d];
         int e = 0;
         if (am > 0) frexp(am, &e);  // am < 2^e
         int shift = budget - e;
@@ -159,6 +209,18 @@ extern "C" int rsx_kmeans_setup(void* d_state, int D, int K, const double* h_fea
     }
     km_setup_kernel<<<1, KM_CTRL_THREADS, 0, s>>>((KmState*)d_state);
     if (int rc = rsx_check_launch("km_setup")) return rc;
+    return km_publish(d_state, D, s);
+}
+
+extern "C" int rsx_kmeans_setup_device(void* d_state, int D, int K, const uint32_t* d_minmax, const double* d_init_rows_raw,
+                                       const double* h_mean_scaled, int64_t n_px_global, rsx_stream_t stream) {
+    RSX_REQUIRE(d_state && d_minmax && d_init_rows_raw, "rsx_kmeans_setup_device: null argument");
+    RSX_REQUIRE(D >= 1 && D <= KM_MAXD && K >= 1 && K <= KM_MAXK && n_px_global > 0, "rsx_kmeans_setup_device: need 1<=D<=%d, 1<=K<=%d", KM_MAXD, KM_MAXK);
+    KmMean mean;
+    for (int d = 0; d < KM_MAXD; ++d) mean.v[d] = (h_mean_scaled && d < D) ? h_mean_scaled[d] : 0.5;
+    cudaStream_t s = (cudaStream_t)stream;
+    km_setup_device_kernel<<<1, KM_CTRL_THREADS, 0, s>>>((KmState*)d_state, D, K, d_minmax, d_init_rows_raw, mean, (long long)n_px_global);
+    if (int rc = rsx_check_launch("km_setup_device")) return rc;
     return km_publish(d_state, D, s);
 }
 
@@ -193,6 +255,7 @@ extern "C" int rsx_kmeans_assign(const float* d_stack, int64_t plane_stride, int
     // DESIGN.md 4.2), so it stays an option.
     a.use_tc = rsx_option("km_tc", 0);
     a.bounded = 0, a.aos = nullptr, a.slack = nullptr;
+    a.full_stream = rsx_option("km_full_stream", 0);
     return g_part_assign[km_part_of(D)](a, (cudaStream_t)stream);
 }
 
@@ -398,9 +461,19 @@ extern "C" int rsx_kmeans_fixed_point_scales(const void* d_state, double* h_pow2
 }
 
 extern "C" int rsx_kmeans_read(const void* d_state, double* h_centroids, double* h_shift_sq, int32_t* h_empty, rsx_stream_t stream) {
+    return rsx_kmeans_read_all(d_state, h_centroids, h_shift_sq, h_empty, nullptr, nullptr, stream);
+}
+
+// + the per-feature raw range the state's scaling was derived from (what MinMaxScaler.fit saw), in the same fetch
+extern "C" int rsx_kmeans_read_all(const void* d_state, double* h_centroids, double* h_shift_sq, int32_t* h_empty, double* h_feat_min,
+                                   double* h_feat_max, rsx_stream_t stream) {
     RSX_REQUIRE(d_state, "rsx_kmeans_read: bad arguments");
     static thread_local KmState h;
     if (int rc = rsx_fetch_small(&h, d_state, sizeof(h), (cudaStream_t)stream)) return rc;
+    for (int d = 0; d < h.D; ++d) {
+        if (h_feat_min) h_feat_min[d] = h.fmin64[d];
+        if (h_feat_max) h_feat_max[d] = h.fmax64[d];
+    }
     if (h_centroids)
         for (int j = 0; j < h.K; ++j)
             for (int d = 0; d < h.D; ++d) h_centroids[j * h.D + d] = h.cent64[j * KM_MAXD + d] + h.mean64[d];

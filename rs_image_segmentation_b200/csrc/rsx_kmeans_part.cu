@@ -1537,7 +1537,9 @@ static int km_launch2(const KmLaunch& a, cudaStream_t s) {
         }
     }
     if (a.mode == KM_FULL) {
-        if constexpr (KU == 8 && D <= 20) return km_launch_full<D>(a, s);
+        if constexpr (KU == 8 && D <= 20) {
+            if (!a.full_stream) return km_launch_full<D>(a, s);
+        }
         return km_launch_stream<D, KM_FULL, false, KU, WARPX>(a, s);
     }
     if (a.mode == KM_DELTA) return km_launch_stream<D, KM_DELTA, false, KU, WARPX>(a, s);

@@ -33,6 +33,7 @@ struct __align__(16) KmState {
     // change its label and is skipped unread.  drift64[j] = sum over the updates of |dc_j| + max_{i != j} |dc_i|.
     double drift64[KM_MAXK];
     float drift_up[KM_MAXK], drift_dn[KM_MAXK];  // drift64 rounded outwards (one float ulp beyond)
+    double fmin64[KM_MAXD], fmax64[KM_MAXD];     // the raw per-feature range the scaling was derived from (rsx_kmeans_read_scaling)
     float bound_err;                             // error bound of the fp32 squared distances |x'|^2 + dist_j (tau_tight + that of |x'|^2)
     float pad_[3];
 };
@@ -65,6 +66,7 @@ struct KmLaunch {
     int use_tc;    // K > 8, D <= 13: distances on the tensor cores (tcgen05, 3 x TF32 split); 0 = the fp32 FFMA2 path
     // bounded passes (K <= 8): 0 = off; 1 = first one (reads the planes, writes the pixel-interleaved copy + slacks); 2 = later ones
     int bounded;
+    int full_stream;  // K <= 8 full pass through the streaming kernel (every pixel moves in) instead of the per-thread accumulators
     float* aos;    // [n_px][km_aos_stride(D)] pixel-interleaved copy of the stack (scattered reads cost 1-3 sectors instead of D)
     float* slack;  // [n_px rounded up to 4] slack + drift of the label at the time it was computed
 };

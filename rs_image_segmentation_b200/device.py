@@ -72,6 +72,54 @@ def stage_to_host(t: torch.Tensor) -> torch.Tensor:
     return host
 
 
+class _UploadRing:
+    """Small host arrays reach the device through a ring of page-locked chunks and cudaMemcpyAsync: torch's `.to(device)` of a
+    pageable tensor WAITS for the stream (staging copy + synchronise), which drains every kernel queued before it - in the middle
+    of a scene that is a hidden full synchronisation."""
+    CHUNK, N = 1 << 17, 24
+
+    def __init__(self):
+        self.chunks = [torch.empty(self.CHUNK, dtype=torch.uint8, pin_memory=True) for _ in range(self.N)]
+        self.events = [None] * self.N
+        self.i = 0
+
+    def upload(self, a: np.ndarray, device) -> torch.Tensor:
+        a = np.ascontiguousarray(a)
+        nbytes = a.nbytes
+        src = torch.from_numpy(a.reshape(-1).view(np.uint8)) if nbytes else None
+        out = torch.empty(a.shape, dtype=torch.from_numpy(np.empty(0, a.dtype)).dtype, device=device)
+        if not nbytes:
+            return out
+        if nbytes > self.CHUNK:                                   # large: a one-off pinned copy
+            pinned = src.pin_memory()
+            out.view(torch.uint8).reshape(-1).copy_(pinned, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return out
+        k = self.i
+        self.i = (k + 1) % self.N
+        if self.events[k] is not None:
+            self.events[k].synchronize()                            # the copy that last used this chunk (long done)
+        self.chunks[k][:nbytes].copy_(src)
+        out.view(torch.uint8).reshape(-1).copy_(self.chunks[k][:nbytes], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.events[k] = ev
+        return out
+
+
+_UPLOAD = {}
+
+
+def upload_small(a: np.ndarray, device=None) -> torch.Tensor:
+    """Host array -> device tensor of the same shape and dtype without synchronising the stream (see _UploadRing)."""
+    device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    ring = _UPLOAD.get(key)
+    if ring is None:
+        ring = _UPLOAD[key] = _UploadRing()
+    return ring.upload(a, device)
+
+
 class MinMaxTracker:
     """uint32 [n][2] device tracker (include/rsx.h 'min/max trackers')."""
 
@@ -83,17 +131,21 @@ class MinMaxTracker:
     def slot(self, i: int):
         return C.c_void_p(self.buf.data_ptr() + 8 * i)
 
-    def read(self, comm=None):
-        """(min float32[n], max float32[n]); synchronises.  With a multi-rank `comm` the trackers of all ranks are merged on
-        the device first (the encoding is order preserving as unsigned integers), collectively."""
+    def merged(self, comm=None) -> torch.Tensor:
+        """The tracker buffer (uint32 [n][2] stored as int32) on the device; with a multi-rank `comm` the trackers of all ranks
+        merged first (the encoding is order preserving as unsigned integers), collectively.  No synchronisation."""
         buf = self.buf
         if comm is not None and comm.world > 1:
             enc = buf.to(torch.int64) & 0xFFFFFFFF
             lo, hi = enc[:, 0].contiguous(), enc[:, 1].contiguous()
             comm.all_reduce(lo, "min")
             comm.all_reduce(hi, "max")
-            buf = torch.stack([lo, hi], dim=1).to(torch.int32)          # truncation keeps the 32 bits
-        h = fetch(buf).view(np.uint32)
+            buf = torch.stack([lo, hi], dim=1).to(torch.int32).contiguous()          # truncation keeps the 32 bits
+        return buf
+
+    def read(self, comm=None):
+        """(min float32[n], max float32[n]); synchronises (collective with a multi-rank `comm`, see merged())."""
+        h = fetch(self.merged(comm)).view(np.uint32)
         mn, mx = np.zeros(self.n, np.float32), np.zeros(self.n, np.float32)
         _lib.load().rsx_minmax_decode(hptr(np.ascontiguousarray(h)), self.n, hptr(mn), hptr(mx))
         return mn, mx

@@ -25,7 +25,7 @@ import numpy as np
 import torch
 
 from . import _lib, hoststats
-from .device import NO_TIMER, MinMaxTracker, StageTimer, fetch, hptr, ptr, require_cuda, stage_to_host, stream_ptr
+from .device import NO_TIMER, MinMaxTracker, StageTimer, fetch, hptr, ptr, require_cuda, stage_to_host, stream_ptr, upload_small
 from .dist import Comm, glcm_rows_needed, strip_bounds
 
 INDEX_NAMES = ("ndvi", "evi", "msavi", "ndwi", "mndwi", "ndbi", "bsi")       # RSX plane order (rsx.h)
@@ -148,14 +148,14 @@ def extract_features(raster: torch.Tensor, cfg: FeatureConfig = FeatureConfig(),
         # X per 16-bit level, tabulated on the device with the exact per-sample arithmetic (3.4 MB for 13 bands, L2
         # resident).  Off by default: 13 scattered 4-byte gathers per pixel cost more than the reciprocal arithmetic.
         lut = torch.empty((B, 65536), dtype=torch.float32, device=dev)
-        d_norm, d_center, d_scale = torch.from_numpy(norm).to(dev), torch.from_numpy(center).to(dev), torch.from_numpy(scale).to(dev)
+        d_norm, d_center, d_scale = upload_small(norm, dev), upload_small(center, dev), upload_small(scale, dev)
         _lib.call("rsx_pca_build_lut_u16", ptr(d_norm), ptr(d_center), ptr(d_scale), B, ptr(lut), st)
         lut_inputs = (d_norm, d_center, d_scale)            # stay referenced until the stream has consumed them
     if not is16:
         x_lut = np.ascontiguousarray(stats.x_lut, dtype=np.float32)
         if remap is not None:                                   # table of the RAW level: x_lut[b][remap[b][v]]
             x_lut = np.ascontiguousarray(np.take_along_axis(x_lut, remap.astype(np.int64), axis=1))
-        lut = torch.from_numpy(x_lut).to(dev)
+        lut = upload_small(x_lut, dev)
     if n_px:
         with timer("pca_moments"):
             if is16:
@@ -355,7 +355,7 @@ class KMeansResult:
 def gather_rows_device(planes: torch.Tensor, D: int, n_px: int, global_idx: np.ndarray, first_px: int, comm: Comm) -> torch.Tensor:
     """Raw float32 feature rows of the given GLOBAL pixel indices as a (len, D) float64 device tensor (all-reduced so
     every rank has all of them); asynchronous."""
-    loc = torch.as_tensor(global_idx - first_px, device=planes.device)
+    loc = upload_small(np.asarray(global_idx - first_px, dtype=np.int64), planes.device)
     mine = (loc >= 0) & (loc < n_px)
     sel = torch.where(mine, loc, torch.zeros_like(loc))
     rows = (planes[:D].index_select(1, sel).t().to(torch.float64) * mine.to(torch.float64).unsqueeze(1)).contiguous()
@@ -457,6 +457,39 @@ class DeviceKMeans:
             self.peers.zero(stream_ptr())
         _lib.call("rsx_kmeans_setup", ptr(self.state), self.D, self.K, hptr(self.fmin), hptr(self.fmax), hptr(mu), hptr(c0),
                   self.n_global, stream_ptr())
+
+    def setup_device(self, minmax_buf: torch.Tensor, rows_raw: torch.Tensor, mean_scaled: Optional[np.ndarray] = None):
+        """setup() without the host in between (rsx_kmeans_setup_device): per-feature range from the device min/max trackers
+        (uint32 [>= D][2], already merged over the ranks), initial centroids from raw feature rows on the device ((K, D)
+        float64).  No synchronisation; configure_from_device() fills fmin / fmax / scale afterwards."""
+        assert rows_raw.dtype == torch.float64 and rows_raw.is_contiguous() and tuple(rows_raw.shape) == (self.K, self.D)
+        mu = np.full(self.D, 0.5) if mean_scaled is None else np.ascontiguousarray(mean_scaled, dtype=np.float64)
+        self._mu = mu
+        self.acc.zero_()
+        self._passes = 0
+        self._bounds_valid = False
+        if self.peers is not None:
+            self.peers.zero(stream_ptr())
+        _lib.call("rsx_kmeans_setup_device", ptr(self.state), self.D, self.K, ptr(minmax_buf), ptr(rows_raw), hptr(mu), self.n_global,
+                  stream_ptr())
+
+    def configure_from_device(self):
+        """fmin / fmax / scale / min_ as the device set-up derived them (from the last read() of the state)."""
+        self.configure(*self._dev_range)
+
+    def fit_device_init(self, minmax_buf: torch.Tensor, rows_raw: torch.Tensor, n_iter: int, labels_i32: bool = True, first_px: int = 0):
+        """fit() with the set-up done on the device: nothing between the feature kernels and the last KMeans pass waits for the
+        host.  Returns (result, scaled initial centroids)."""
+        self.setup_device(minmax_buf, rows_raw)
+        rows_host = stage_to_host(rows_raw)
+        for _ in range(n_iter):
+            self.step()
+        res = self._result(self.finish(labels_i32), n_iter)                  # the one synchronisation
+        self.configure_from_device()
+        c0 = self.scale_rows(rows_host.numpy())
+        if res is None:
+            res = self._fit_relocating(c0, n_iter, labels_i32, first_px)
+        return res, c0
 
     def _label_planes(self):
         if self._labels is None:
@@ -632,7 +665,9 @@ class DeviceKMeans:
         cent = np.zeros((self.K, self.D), np.float64)
         shift = np.zeros(1, np.float64)
         empty = np.zeros(1, np.int32)
-        _lib.call("rsx_kmeans_read", ptr(self.state), hptr(cent), hptr(shift), hptr(empty), stream_ptr())
+        fmin, fmax = np.zeros(self.D, np.float64), np.zeros(self.D, np.float64)
+        _lib.call("rsx_kmeans_read_all", ptr(self.state), hptr(cent), hptr(shift), hptr(empty), hptr(fmin), hptr(fmax), stream_ptr())
+        self._dev_range = (fmin, fmax)
         return cent, float(shift[0]), int(empty[0])
 
     def fit_converge(self, init_centroids_scaled: np.ndarray, max_iter: int = 300, tol: float = 0.0,
@@ -705,7 +740,13 @@ def kmeans_on_features(fr: FeatureResult, D: int, K: int, n_iter: int, seed: int
     km = DeviceKMeans(fr.planes, fr.n_px, D, K, None, None, n_global, fr.W, comm, timer, delta)   # buffers first, ...
     if km.delta:
         km._label_planes()
-    rows_host = stage_to_host(gather_rows_device(fr.planes, D, fr.n_px, idx, first_row * fr.W, comm))   # ... all asynchronous
+    rows = gather_rows_device(fr.planes, D, fr.n_px, idx, first_row * fr.W, comm)                      # ... all asynchronous
+    if _lib.get_option("km_device_setup", 1):
+        # MinMaxScaler.fit and the scaling of the initial centroids happen in the set-up kernel, from the trackers the feature
+        # kernels maintained: the device never waits for the host between the last feature kernel and the last KMeans pass
+        res, c0 = km.fit_device_init(fr.minmax.merged(comm), rows, n_iter, labels_i32, first_px=first_row * fr.W)
+        return res, km, c0
+    rows_host = stage_to_host(rows)
     mn, mx = fr.minmax.read(comm)                   # the one synchronisation between the feature kernels and KMeans
     km.configure(mn[:D], mx[:D])
     c0 = km.scale_rows(rows_host.numpy())

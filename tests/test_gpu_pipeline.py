@@ -265,6 +265,38 @@ def test_kmeans_bounded_passes_equal_unbounded(P, K, D, n_iter, full_passes):
     assert float((runs[True][3] > 0).float().mean()) > 0.5
 
 
+@pytest.mark.parametrize("D,K", [(13, 8), (7, 5), (22, 32)])
+def test_kmeans_device_setup_equals_host_setup(P, D, K):
+    """rsx_kmeans_setup_device (range from the device min/max trackers, initial centroids scaled by the kernel) leaves the same
+    state, byte for byte, as rsx_kmeans_setup fed with the numbers the host derives - constant features and features far from
+    zero included."""
+    import torch
+    from rs_image_segmentation_b200.device import MinMaxTracker, ptr, stream_ptr
+    from rs_image_segmentation_b200 import _lib
+    n_px = 20011
+    rng = np.random.default_rng(D * 100 + K)
+    X = (rng.normal(size=(n_px, D)) * rng.uniform(1e-3, 300.0, size=D) + rng.uniform(-1000, 1000, size=D)).astype(np.float32)
+    X[:, 1] = 0.25                                                         # constant feature: range 0 -> scale 1
+    X[:, 2] = np.where(rng.random(n_px) < 0.5, -3.0, -3.0 + 1e-7).astype(np.float32)
+    stride = (n_px + 31) // 32 * 32
+    planes = torch.zeros((D, stride), dtype=torch.float32, device="cuda")
+    planes[:, :n_px] = torch.from_numpy(np.ascontiguousarray(X.T)).cuda()
+    mm = MinMaxTracker(D)
+    _lib.call("rsx_minmax_planes_f32", ptr(planes), n_px, stride, D, ptr(mm.buf), stream_ptr())
+    mn, mx = mm.read()
+    assert np.array_equal(mn, X.min(axis=0)) and np.array_equal(mx, X.max(axis=0))
+    idx = P.draw_init_indices(n_px, K, 3)
+    a = P.DeviceKMeans(planes, n_px, D, K, mn, mx, 40000 * 40000, 257)
+    a.setup(a.scale_rows(X[idx]))
+    b = P.DeviceKMeans(planes, n_px, D, K, None, None, 40000 * 40000, 257)
+    b.setup_device(mm.merged(), torch.from_numpy(X[idx].astype(np.float64)).cuda().contiguous())
+    torch.cuda.synchronize()
+    assert torch.equal(a.state, b.state)
+    b.read()
+    b.configure_from_device()
+    assert np.array_equal(a.fmin, b.fmin) and np.array_equal(a.scale, b.scale) and np.array_equal(a.min_, b.min_)
+
+
 def test_kmeans_changed_counter(P):
     """The changed-label counter of an update pass equals the number of labels that differ from the previous pass."""
     import torch
