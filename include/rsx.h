@@ -76,6 +76,16 @@ int rsx_hist_u16(const uint16_t* d_raster, int64_t n_px, int n_bands, uint32_t* 
 int rsx_raster_stats(const int64_t* h_hist, int n_bands, int n_levels, int texture_band, double lower, double upper,
                      float* h_norm, float* h_qnorm, float* h_center, double* h_scale, float* h_norm_lut, float* h_x_lut);
 
+/* The same statistics computed ON THE DEVICE for uint8 rasters (L = 256), so that the histograms need not visit the host between
+ * two kernels: d_hist = the [B][256] counters of rsx_hist_u8 (uint32; int64 after a multi-rank all-reduce: hist_is_int64 = 1);
+ * d_stats = a device block of rsx_raster_stats_device_bytes() bytes holding norm [16][3], qnorm [4], center [16], scale (double)
+ * [16] and, at byte offset rsx_raster_stats_device_lut_offset(), x_lut float [16][256] (rows 0..B-1 = the table rsx_pca_*_u8 take).
+ * Bit-identical to rsx_raster_stats (same operations, individually rounded).  rsx_indices_fused_u8_dev reads the block. */
+int64_t rsx_raster_stats_device_bytes(void);
+int64_t rsx_raster_stats_device_lut_offset(void);
+int rsx_raster_stats_u8_device(const void* d_hist, int hist_is_int64, int n_bands, int texture_band, double lower, double upper,
+                               void* d_stats, rsx_stream_t stream);
+
 /* ---- K2: fused normalise + spectral indices (+ GLCM quantisation) ---------------------------
  * Replaces robust_normalize x B (indices.py:25-48 via scripts/2...:43-47) and the seven index
  * functions (indices.py:50-203) in one pass over the raster.
@@ -92,6 +102,10 @@ int rsx_raster_stats(const int64_t* h_hist, int n_bands, int n_levels, int textu
 int rsx_indices_fused_u8(const uint8_t* d_raster, int64_t n_px, int n_bands, const int* band_map, const float* h_norm,
                          const float* evi, float* d_indices, int64_t plane_stride, uint32_t* d_minmax, uint8_t* d_quant,
                          const float* h_qnorm, int levels, const uint8_t* h_remap, rsx_stream_t stream);
+/* rsx_indices_fused_u8 with the normalisation parameters (h_norm, h_qnorm) read from the device block of rsx_raster_stats_u8_device */
+int rsx_indices_fused_u8_dev(const uint8_t* d_raster, int64_t n_px, int n_bands, const int* band_map, const void* d_stats,
+                             const float* evi, float* d_indices, int64_t plane_stride, uint32_t* d_minmax, uint8_t* d_quant, int levels,
+                             rsx_stream_t stream);
 int rsx_indices_fused_u16(const uint16_t* d_raster, int64_t n_px, int n_bands, const int* band_map, const float* h_norm,
                           const float* evi, float* d_indices, int64_t plane_stride, uint32_t* d_minmax, uint8_t* d_quant,
                           const float* h_qnorm, int levels, rsx_stream_t stream);

@@ -24,6 +24,10 @@ SIGNATURES = {
     "rsx_hist_u8": (i32, [vp, i64, i32, vp, vp]),
     "rsx_hist_u16": (i32, [vp, i64, i32, vp, vp]),
     "rsx_indices_fused_u8": (i32, [vp, i64, i32, vp, vp, vp, vp, i64, vp, vp, vp, i32, vp, vp]),
+    "rsx_indices_fused_u8_dev": (i32, [vp, i64, i32, vp, vp, vp, vp, i64, vp, vp, i32, vp]),
+    "rsx_raster_stats_device_bytes": (i64, []),
+    "rsx_raster_stats_device_lut_offset": (i64, []),
+    "rsx_raster_stats_u8_device": (i32, [vp, i32, i32, i32, C.c_double, C.c_double, vp, vp]),
     "rsx_indices_fused_u16": (i32, [vp, i64, i32, vp, vp, vp, vp, i64, vp, vp, vp, i32, vp]),
     "rsx_normalize_f32": (i32, [vp, i64, f32, f32, f32, vp, vp]),
     "rsx_index_ratio_f32": (i32, [vp, vp, i64, vp, vp]),

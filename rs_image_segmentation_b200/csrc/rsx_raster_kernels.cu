@@ -138,6 +138,131 @@ extern "C" int rsx_hist_u16(const uint16_t* d_raster, int64_t n_px, int n_bands,
     return rsx_check_launch("rsx_hist_u16");
 }
 
+// ============================================================================ K1b: order statistics on the device (uint8 rasters)
+// rsx_raster_stats (rsx_core.cu: numpy's percentile arithmetic restated for the host) once more for the device, operation by
+// operation with explicitly rounded intrinsics, so that the K1 histograms never have to visit the host between two kernels: one
+// warp per band, the per-level loops spread over the lanes, the few scalar percentile evaluations done redundantly by every lane.
+// The results stay in a device block that K2 / K3 read; tests/test_gpu_kernels.py holds them bit for bit against rsx_raster_stats.
+struct RsxDevStats {
+    float norm[RSX_MAX_BANDS][3];  // lo, hi, den of robust_normalize
+    float qnorm[4];                // second robust_normalize of the texture band (+ pad)
+    float center[RSX_MAX_BANDS];
+    double scale[RSX_MAX_BANDS];
+    float x_lut[RSX_MAX_BANDS][256];  // RobustScaler value of every grey level
+};
+
+struct DevOrder {
+    const long long* cum;  // inclusive cumulative counts (shared memory)
+    const float* values;   // value of every level (shared memory)
+    long long n;
+    __device__ float at(long long k) const {
+        k = k < 0 ? 0 : (k >= n ? n - 1 : k);
+        int lo = 0, hi = 256;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (cum[mid] > k) hi = mid; else lo = mid + 1;
+        }
+        return values[lo < 256 ? lo : 255];
+    }
+    __device__ float percentile32(double q) const {
+        const float q32 = __fdiv_rn((float)q, 100.0f);
+        const float nm1 = __ll2float_rn(n - 1);
+        const float vi = __fmul_rn(nm1, q32);
+        float prev = floorf(vi), nxt = __fadd_rn(prev, 1.0f);
+        if (vi >= nm1) prev = nxt = -1.0f;
+        if (vi < 0.0f) prev = nxt = 0.0f;
+        const long long pi = (long long)prev, ni = (long long)nxt;
+        const float a = at(pi >= 0 ? pi : n - 1), b = at(ni >= 0 ? ni : n - 1);
+        if (a == b) return a;
+        const float t = __double2float_rn(__dsub_rn((double)vi, (double)pi));
+        const float diff = __fsub_rn(b, a);
+        float out = __fadd_rn(a, __fmul_rn(diff, t));
+        if (t >= 0.5f) out = __fsub_rn(b, __fmul_rn(diff, __fsub_rn(1.0f, t)));
+        return out;
+    }
+    __device__ double percentile64(double q) const {
+        const double qq = __ddiv_rn(q, 100.0);
+        const double vi = __dmul_rn((double)(n - 1), qq);
+        double prev = floor(vi), nxt = __dadd_rn(prev, 1.0);
+        if (vi >= (double)(n - 1)) prev = nxt = -1.0;
+        if (vi < 0.0) prev = nxt = 0.0;
+        const long long pi = (long long)prev, ni = (long long)nxt;
+        const float a = at(pi >= 0 ? pi : n - 1), b = at(ni >= 0 ? ni : n - 1);
+        if (a == b) return (double)a;
+        const double t = __dsub_rn(vi, (double)pi);
+        const float diff = __fsub_rn(b, a);
+        double out = __dadd_rn((double)a, __dmul_rn((double)diff, t));
+        if (t >= 0.5) out = __dsub_rn((double)b, __dmul_rn((double)diff, __dsub_rn(1.0, t)));
+        return out;
+    }
+    __device__ float median32() const {
+        if (n & 1) return at(n / 2);
+        return __fdiv_rn(__fadd_rn(at(n / 2 - 1), at(n / 2)), 2.0f);
+    }
+};
+
+// hist: [B][256] counters, uint32 (one rank) or int64 (after the all-reduce); one warp per band
+__global__ void __launch_bounds__(32 * RSX_MAX_BANDS) raster_stats_u8_kernel(const void* __restrict__ hist, int is64, int texture_band, double lower,
+                                                                             double upper, RsxDevStats* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char stats_smem[];  // [B][256] int64 cumulative counts, [B][256] float values, [256] levels
+    const int n_bands = blockDim.x >> 5;
+    long long(*cum)[256] = reinterpret_cast<long long(*)[256]>(stats_smem);
+    float(*f)[256] = reinterpret_cast<float(*)[256]>(stats_smem + (size_t)n_bands * 256 * 8);
+    float* levels = reinterpret_cast<float*>(stats_smem + (size_t)n_bands * 256 * 12);
+    const int b = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int v = threadIdx.x; v < 256; v += blockDim.x) levels[v] = (float)v;
+    if (threadIdx.x == 0 && (texture_band < 0 || texture_band >= n_bands)) out->qnorm[0] = 0.f, out->qnorm[1] = 1.f, out->qnorm[2] = 1.f;
+    // inclusive cumulative counts: 8 consecutive levels per lane, then a warp scan of the lane totals
+    long long c[8], run = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int v = lane * 8 + k;
+        const long long h = is64 ? reinterpret_cast<const long long*>(hist)[b * 256 + v] : (long long)reinterpret_cast<const unsigned*>(hist)[b * 256 + v];
+        run += h, c[k] = run;
+    }
+    long long incl = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+    }
+    const long long before = incl - run;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) cum[b][lane * 8 + k] = before + c[k];
+    const long long n = __shfl_sync(0xffffffffu, incl, 31);
+    __syncthreads();
+    if (n <= 0) return;  // empty histogram: the caller's tables stay as they were (rsx_raster_stats reports it on the host)
+    const DevOrder raw{cum[b], levels, n};
+    const float lo = raw.percentile32(lower), hi = raw.percentile32(upper);
+    const float den = __fadd_rn(__fsub_rn(hi, lo), 1e-10f);
+    for (int v = lane; v < 256; v += 32) f[b][v] = __fdiv_rn(__fsub_rn(fminf(fmaxf(levels[v], lo), hi), lo), den);
+    __syncwarp();
+    const DevOrder nb{cum[b], f[b], n};
+    if (b == texture_band) {
+        const float lo2 = nb.percentile32(lower), hi2 = nb.percentile32(upper);
+        if (lane == 0) out->qnorm[0] = lo2, out->qnorm[1] = hi2, out->qnorm[2] = __fadd_rn(__fsub_rn(hi2, lo2), 1e-10f);
+    }
+    const float center = nb.median32();
+    double sc = __dsub_rn(nb.percentile64(75.0), nb.percentile64(25.0));
+    if (sc < 10.0 * 2.220446049250313e-16) sc = 1.0;
+    if (lane == 0) out->norm[b][0] = lo, out->norm[b][1] = hi, out->norm[b][2] = den, out->center[b] = center, out->scale[b] = sc;
+    for (int v = lane; v < 256; v += 32) out->x_lut[b][v] = __double2float_rn(__ddiv_rn((double)__fsub_rn(f[b][v], center), sc));
+}
+
+extern "C" int64_t rsx_raster_stats_device_bytes(void) { return (int64_t)sizeof(RsxDevStats); }
+extern "C" int64_t rsx_raster_stats_device_lut_offset(void) { return (int64_t)offsetof(RsxDevStats, x_lut); }
+
+extern "C" int rsx_raster_stats_u8_device(const void* d_hist, int hist_is_int64, int n_bands, int texture_band, double lower, double upper, void* d_stats,
+                                          rsx_stream_t stream) {
+    RSX_REQUIRE(d_hist && d_stats && n_bands >= 1 && n_bands <= RSX_MAX_BANDS, "rsx_raster_stats_u8_device: bad arguments");
+    RSX_REQUIRE(((uintptr_t)d_stats & 15) == 0 && ((uintptr_t)d_hist & 7) == 0, "rsx_raster_stats_u8_device: buffers must be aligned");
+    const int smem = n_bands * 256 * 12 + 1024;
+    if (int rc = set_smem(raster_stats_u8_kernel, smem)) return rc;
+    raster_stats_u8_kernel<<<1, 32 * n_bands, smem, (cudaStream_t)stream>>>(d_hist, hist_is_int64, texture_band, lower, upper,
+                                                                           reinterpret_cast<RsxDevStats*>(d_stats));
+    return rsx_check_launch("rsx_raster_stats_u8_device");
+}
+
 // ============================================================================ K2: fused normalise + indices
 struct IndexParams {
     NormParam norm[5];  // blue, green, red, nir, swir1 (already gathered through band_map)
@@ -193,7 +318,8 @@ __device__ __forceinline__ void seven_indices(float blue, float green, float red
 
 template <typename T, int B>
 __global__ void __launch_bounds__(256) indices_fused_kernel(const T* __restrict__ raster, int64_t n_px, IndexParams P, float* __restrict__ out,
-                                                            int64_t plane_stride, uint32_t* __restrict__ minmax, uint8_t* __restrict__ quant) {
+                                                            int64_t plane_stride, uint32_t* __restrict__ minmax, uint8_t* __restrict__ quant,
+                                                            const RsxDevStats* __restrict__ ds) {
     using RT = RasterTiles<T, B, 3>;
     constexpr int PXT = RT::PXT;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -205,9 +331,15 @@ __global__ void __launch_bounds__(256) indices_fused_kernel(const T* __restrict_
     __shared__ float nlut[sizeof(T) == 1 ? 5 * 256 : 1];
     __shared__ uint8_t qlut[sizeof(T) == 1 ? 256 : 1];
     if constexpr (sizeof(T) == 1) {
-        for (int i = threadIdx.x; i < 5 * 256; i += 256) nlut[i] = norm_apply((float)P.remap[i >> 8][i & 255], P.norm[i >> 8]);
+        // ds: the normalisation parameters come from the device block raster_stats_u8_kernel filled (no host round trip)
+        for (int i = threadIdx.x; i < 5 * 256; i += 256) {
+            const int k = i >> 8;
+            const NormParam np = ds ? NormParam{ds->norm[P.band[k]][0], ds->norm[P.band[k]][1], ds->norm[P.band[k]][2]} : P.norm[k];
+            nlut[i] = norm_apply((float)P.remap[k][i & 255], np);
+        }
         __syncthreads();
-        for (int i = threadIdx.x; i < 256; i += 256) qlut[i] = (uint8_t)(int)f_mul(norm_apply(nlut[3 * 256 + i], P.qnorm), P.q_scale);
+        const NormParam qn = ds ? NormParam{ds->qnorm[0], ds->qnorm[1], ds->qnorm[2]} : P.qnorm;
+        for (int i = threadIdx.x; i < 256; i += 256) qlut[i] = (uint8_t)(int)f_mul(norm_apply(nlut[3 * 256 + i], qn), P.q_scale);
         __syncthreads();
     }
 
@@ -276,29 +408,31 @@ __global__ void __launch_bounds__(256) indices_fused_kernel(const T* __restrict_
 template <typename T>
 static int indices_fused_impl(const T* d_raster, int64_t n_px, int n_bands, const int* band_map, const float* h_norm, const float* evi,
                               float* d_indices, int64_t plane_stride, uint32_t* d_minmax, uint8_t* d_quant, const float* h_qnorm, int levels,
-                              const uint8_t* h_remap, rsx_stream_t stream) {
-    RSX_REQUIRE(d_raster && band_map && h_norm && evi && d_indices && n_px > 0, "rsx_indices_fused: bad arguments");
+                              const uint8_t* h_remap, rsx_stream_t stream, const RsxDevStats* d_stats = nullptr) {
+    RSX_REQUIRE(d_raster && band_map && (h_norm || d_stats) && evi && d_indices && n_px > 0, "rsx_indices_fused: bad arguments");
+    RSX_REQUIRE(!d_stats || sizeof(T) == 1, "rsx_indices_fused: device statistics are defined for uint8 rasters");
     RSX_REQUIRE(!h_remap || sizeof(T) == 1, "rsx_indices_fused: a level remap is only defined for uint8 rasters");
     RSX_REQUIRE(((uintptr_t)d_raster & 15) == 0 && ((uintptr_t)d_indices & 15) == 0 && (plane_stride & 3) == 0 && plane_stride >= n_px,
                 "rsx_indices_fused: raster/planes must be 16-byte aligned, plane_stride a multiple of 4 and >= n_px");
-    RSX_REQUIRE(!d_quant || (h_qnorm && levels >= 2 && levels <= 256 && ((uintptr_t)d_quant & 3) == 0), "rsx_indices_fused: bad quantisation arguments");
+    RSX_REQUIRE(!d_quant || ((h_qnorm || d_stats) && levels >= 2 && levels <= 256 && ((uintptr_t)d_quant & 3) == 0), "rsx_indices_fused: bad quantisation arguments");
     IndexParams P;
     for (int k = 0; k < 5; ++k) {
         int b = band_map[k];
         RSX_REQUIRE(b >= 0 && b < n_bands, "rsx_indices_fused: band_map[%d]=%d out of range", k, b);
         P.band[k] = b;
-        P.norm[k] = NormParam{h_norm[3 * b], h_norm[3 * b + 1], h_norm[3 * b + 2]};
+        P.norm[k] = h_norm ? NormParam{h_norm[3 * b], h_norm[3 * b + 1], h_norm[3 * b + 2]} : NormParam{0.f, 1.f, 1.f};
         for (int v = 0; v < 256; ++v) P.remap[k][v] = h_remap ? h_remap[b * 256 + v] : (uint8_t)v;
     }
     P.evi_L = evi[0], P.evi_C1 = evi[1], P.evi_C2 = evi[2], P.evi_G = evi[3];
-    P.qnorm = d_quant ? NormParam{h_qnorm[0], h_qnorm[1], h_qnorm[2]} : NormParam{0.f, 1.f, 1.f};
+    P.qnorm = (d_quant && h_qnorm) ? NormParam{h_qnorm[0], h_qnorm[1], h_qnorm[2]} : NormParam{0.f, 1.f, 1.f};
     P.q_scale = (float)(levels - 1);
 #define LAUNCH(BB)                                                                                                                  \
     {                                                                                                                               \
         using RT = RasterTiles<T, BB, 3>;                                                                                           \
         if (int rc = set_smem(indices_fused_kernel<T, BB>, RT::SMEM_BYTES)) return rc;                                              \
         int grid = persistent_grid(ceil_div(n_px, (int64_t)RT::TILE_PX), RT::SMEM_BYTES > 110000 ? 1 : 2);                          \
-        indices_fused_kernel<T, BB><<<grid, 256, RT::SMEM_BYTES, (cudaStream_t)stream>>>(d_raster, n_px, P, d_indices, plane_stride, d_minmax, d_quant); \
+        indices_fused_kernel<T, BB><<<grid, 256, RT::SMEM_BYTES, (cudaStream_t)stream>>>(d_raster, n_px, P, d_indices, plane_stride, d_minmax, d_quant, \
+                                                                                         d_stats);                                            \
     }
     RSX_DISPATCH_BANDS(n_bands, LAUNCH)
 #undef LAUNCH
@@ -310,6 +444,13 @@ extern "C" int rsx_indices_fused_u8(const uint8_t* d_raster, int64_t n_px, int n
                                     const uint8_t* h_remap, rsx_stream_t stream) {
     return indices_fused_impl<uint8_t>(d_raster, n_px, n_bands, band_map, h_norm, evi, d_indices, plane_stride, d_minmax, d_quant, h_qnorm, levels, h_remap,
                                        stream);
+}
+// normalisation parameters from the device block of rsx_raster_stats_u8_device instead of host arrays
+extern "C" int rsx_indices_fused_u8_dev(const uint8_t* d_raster, int64_t n_px, int n_bands, const int* band_map, const void* d_stats, const float* evi,
+                                        float* d_indices, int64_t plane_stride, uint32_t* d_minmax, uint8_t* d_quant, int levels, rsx_stream_t stream) {
+    RSX_REQUIRE(d_stats, "rsx_indices_fused_u8_dev: null statistics block");
+    return indices_fused_impl<uint8_t>(d_raster, n_px, n_bands, band_map, nullptr, evi, d_indices, plane_stride, d_minmax, d_quant, nullptr, levels, nullptr,
+                                       stream, reinterpret_cast<const RsxDevStats*>(d_stats));
 }
 extern "C" int rsx_indices_fused_u16(const uint16_t* d_raster, int64_t n_px, int n_bands, const int* band_map, const float* h_norm, const float* evi,
                                      float* d_indices, int64_t plane_stride, uint32_t* d_minmax, uint8_t* d_quant, const float* h_qnorm, int levels,

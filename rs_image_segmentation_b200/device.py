@@ -113,6 +113,8 @@ _UPLOAD = {}
 def upload_small(a: np.ndarray, device=None) -> torch.Tensor:
     """Host array -> device tensor of the same shape and dtype without synchronising the stream (see _UploadRing)."""
     device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    if device.type != "cuda":                                       # host-side callers (the gloo tests)
+        return torch.from_numpy(np.ascontiguousarray(a)).to(device)
     key = device.index if device.index is not None else torch.cuda.current_device()
     ring = _UPLOAD.get(key)
     if ring is None:

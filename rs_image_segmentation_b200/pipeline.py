@@ -105,57 +105,78 @@ def extract_features(raster: torch.Tensor, cfg: FeatureConfig = FeatureConfig(),
     mm = MinMaxTracker(len(names), device=dev)
     quant = torch.empty(_pad4(max(n_px, 1)), dtype=torch.uint8, device=dev) if cfg.glcm else None
 
+    # uint8 rasters: the order statistics are computed by a kernel from the device histograms and stay on the device for K2 / K3;
+    # the host copy of the histograms (for FeatureResult.stats) is read when the host next has to wait anyway (the PCA moments).
+    # (uint16 rasters and the fused stage-1 chain keep the host path: 65536-level tables / level remaps are built there.)
+    dev_stats = None
+    hist_dev, hist_is64 = hist, 0
     if comm.world > 1:
         with timer("hist_allreduce"):
             hist64 = hist.to(torch.int64) & 0xFFFFFFFF      # the kernel's counters are uint32
             comm.all_reduce(hist64)
-        hist_host = fetch(hist64)
-    else:
-        hist_host = fetch(hist).view(np.uint32).astype(np.int64)
+        hist_dev, hist_is64 = hist64, 1
     remap = None
-    hist_raw = hist_host
-    if cfg.stage1 is not None:
-        if is16:
-            raise _lib.RsxError("the fused stage-1 chain is defined for 8-bit rasters")
-        remap, hist_host = hoststats.stage1_level_tables(hist_host, cfg.stage1[0], cfg.stage1[1])
-        remap = np.ascontiguousarray(remap)
-    stats = hoststats.RasterStats(hist_host, glcm_band=cfg.band_map[3], lower=cfg.percentiles[0], upper=cfg.percentiles[1])
-    stats.hist_raw = hist_raw
-
-    # ---- K2 fused normalise + indices (+ quantised NIR)
+    stats = None
     band_map = np.asarray(cfg.band_map, dtype=np.int32)
-    norm = np.ascontiguousarray(stats.norm, dtype=np.float32)
     evi = np.asarray(cfg.evi, dtype=np.float32)
-    qnorm = np.ascontiguousarray(stats.qnorm, dtype=np.float32)
-    if n_px:
-        with timer("indices"):
+    if not is16 and cfg.stage1 is None and _lib.get_option("device_stats", 1):
+        dev_stats = torch.empty(int(_lib.load().rsx_raster_stats_device_bytes()), dtype=torch.uint8, device=dev)
+        gb = int(cfg.band_map[3])
+        _lib.call("rsx_raster_stats_u8_device", ptr(hist_dev), hist_is64, B, gb if 0 <= gb < B else -1, float(cfg.percentiles[0]),
+                  float(cfg.percentiles[1]), ptr(dev_stats), st)
+        hist_pinned = stage_to_host(hist_dev)
+        if n_px:
+            with timer("indices"):
+                _lib.call("rsx_indices_fused_u8_dev", ptr(raster), n_px, B, hptr(band_map), ptr(dev_stats), hptr(evi), ptr(planes), stride,
+                          mm.slot(0), ptr(quant), cfg.glcm_levels, st)
+    else:
+        hist_host = fetch(hist_dev) if hist_is64 else fetch(hist).view(np.uint32).astype(np.int64)
+        hist_raw = hist_host
+        if cfg.stage1 is not None:
             if is16:
-                _lib.call("rsx_indices_fused_u16", ptr(raster), n_px, B, hptr(band_map), hptr(norm), hptr(evi), ptr(planes), stride,
-                          mm.slot(0), ptr(quant), hptr(qnorm), cfg.glcm_levels, st)
-            else:
-                _lib.call("rsx_indices_fused_u8", ptr(raster), n_px, B, hptr(band_map), hptr(norm), hptr(evi), ptr(planes), stride,
-                          mm.slot(0), ptr(quant), hptr(qnorm), cfg.glcm_levels, hptr(remap), st)
+                raise _lib.RsxError("the fused stage-1 chain is defined for 8-bit rasters")
+            remap, hist_host = hoststats.stage1_level_tables(hist_host, cfg.stage1[0], cfg.stage1[1])
+            remap = np.ascontiguousarray(remap)
+        stats = hoststats.RasterStats(hist_host, glcm_band=cfg.band_map[3], lower=cfg.percentiles[0], upper=cfg.percentiles[1])
+        stats.hist_raw = hist_raw
+
+        # ---- K2 fused normalise + indices (+ quantised NIR)
+        norm = np.ascontiguousarray(stats.norm, dtype=np.float32)
+        qnorm = np.ascontiguousarray(stats.qnorm, dtype=np.float32)
+        if n_px:
+            with timer("indices"):
+                if is16:
+                    _lib.call("rsx_indices_fused_u16", ptr(raster), n_px, B, hptr(band_map), hptr(norm), hptr(evi), ptr(planes), stride,
+                              mm.slot(0), ptr(quant), hptr(qnorm), cfg.glcm_levels, st)
+                else:
+                    _lib.call("rsx_indices_fused_u8", ptr(raster), n_px, B, hptr(band_map), hptr(norm), hptr(evi), ptr(planes), stride,
+                              mm.slot(0), ptr(quant), hptr(qnorm), cfg.glcm_levels, hptr(remap), st)
 
     # ---- K3a PCA moments (+ all-reduce).  The RobustScaler statistics (host, phase 2) are computed while K2 runs; the
     #      moments come back through pinned memory so that the host can do the eigen-decomposition under the GLCM kernel.
     M = B + B * (B + 1) // 2
     moments = torch.zeros(M, dtype=torch.float64, device=dev)
     scratch = torch.empty(int(_lib.load().rsx_pca_scratch_elems(B)), dtype=torch.float64, device=dev)
-    center = np.ascontiguousarray(stats.center, dtype=np.float32)
-    scale = np.ascontiguousarray(stats.scale, dtype=np.float64)
     lut = lut_inputs = None
-    if is16 and cfg.u16_level_table:
-        # X per 16-bit level, tabulated on the device with the exact per-sample arithmetic (3.4 MB for 13 bands, L2
-        # resident).  Off by default: 13 scattered 4-byte gathers per pixel cost more than the reciprocal arithmetic.
-        lut = torch.empty((B, 65536), dtype=torch.float32, device=dev)
-        d_norm, d_center, d_scale = upload_small(norm, dev), upload_small(center, dev), upload_small(scale, dev)
-        _lib.call("rsx_pca_build_lut_u16", ptr(d_norm), ptr(d_center), ptr(d_scale), B, ptr(lut), st)
-        lut_inputs = (d_norm, d_center, d_scale)            # stay referenced until the stream has consumed them
-    if not is16:
-        x_lut = np.ascontiguousarray(stats.x_lut, dtype=np.float32)
-        if remap is not None:                                   # table of the RAW level: x_lut[b][remap[b][v]]
-            x_lut = np.ascontiguousarray(np.take_along_axis(x_lut, remap.astype(np.int64), axis=1))
-        lut = upload_small(x_lut, dev)
+    norm = center = scale = None
+    if dev_stats is not None:
+        lut = dev_stats[int(_lib.load().rsx_raster_stats_device_lut_offset()):].view(torch.float32)      # [16][256], rows 0..B-1 used
+    else:
+        center = np.ascontiguousarray(stats.center, dtype=np.float32)
+        scale = np.ascontiguousarray(stats.scale, dtype=np.float64)
+        norm = np.ascontiguousarray(stats.norm, dtype=np.float32)
+        if is16 and cfg.u16_level_table:
+            # X per 16-bit level, tabulated on the device with the exact per-sample arithmetic (3.4 MB for 13 bands, L2
+            # resident).  Off by default: 13 scattered 4-byte gathers per pixel cost more than the reciprocal arithmetic.
+            lut = torch.empty((B, 65536), dtype=torch.float32, device=dev)
+            d_norm, d_center, d_scale = upload_small(norm, dev), upload_small(center, dev), upload_small(scale, dev)
+            _lib.call("rsx_pca_build_lut_u16", ptr(d_norm), ptr(d_center), ptr(d_scale), B, ptr(lut), st)
+            lut_inputs = (d_norm, d_center, d_scale)            # stay referenced until the stream has consumed them
+        if not is16:
+            x_lut = np.ascontiguousarray(stats.x_lut, dtype=np.float32)
+            if remap is not None:                                   # table of the RAW level: x_lut[b][remap[b][v]]
+                x_lut = np.ascontiguousarray(np.take_along_axis(x_lut, remap.astype(np.int64), axis=1))
+            lut = upload_small(x_lut, dev)
     if n_px:
         with timer("pca_moments"):
             if is16:
@@ -194,6 +215,11 @@ def extract_features(raster: torch.Tensor, cfg: FeatureConfig = FeatureConfig(),
 
     # ---- K3b eigh on the host (the device is busy with K4), projection
     moments_ready.synchronize()
+    if stats is None:                                   # the histograms arrived with (before) the moments
+        hp = hist_pinned.numpy()
+        hist_host = hp.astype(np.int64) if hist_is64 else hp.view(np.uint32).astype(np.int64)
+        stats = hoststats.RasterStats(hist_host, glcm_band=cfg.band_map[3], lower=cfg.percentiles[0], upper=cfg.percentiles[1])
+        stats.hist_raw = hist_host
     pca = hoststats.pca_from_moments(moments_host.numpy().copy(), n_global, n_comp)
     comps = np.ascontiguousarray(pca["components"], dtype=np.float32)
     mean32 = pca["mean"].astype(np.float32)

@@ -53,6 +53,64 @@ def test_hist_u16(rsx, n_px):
     assert np.array_equal(h.cpu().numpy(), _hist_np(r, 65536))
 
 
+def _random_histograms(rng, B, kind):
+    h = np.zeros((B, 256), np.int64)
+    for b in range(B):
+        k = kind if kind != "mixed" else ["uniform", "two", "constant", "skewed", "sparse", "huge"][b % 6]
+        if k == "uniform":
+            h[b] = rng.integers(0, 5000, 256)
+        elif k == "two":
+            h[b, rng.integers(0, 128)] = rng.integers(1, 1000)
+            h[b, rng.integers(128, 256)] = rng.integers(1, 1000)
+        elif k == "constant":
+            h[b, rng.integers(0, 256)] = rng.integers(1, 100000)
+        elif k == "skewed":
+            h[b] = (rng.pareto(1.2, 256) * 50).astype(np.int64)
+            h[b, 0] += 1
+        elif k == "sparse":
+            idx = rng.choice(256, 9, replace=False)
+            h[b, idx] = rng.integers(1, 40, 9)
+        else:                                                  # counts of the 40k x 40k mosaic: beyond 2^31 in total
+            h[b] = rng.integers(0, 2 ** 24, 256)
+            h[b, 100] += 2 ** 30
+    return h
+
+
+@pytest.mark.parametrize("B,kind,seed", [(7, "mixed", 1), (13, "mixed", 2), (16, "mixed", 3), (1, "sparse", 4), (7, "uniform", 5), (5, "two", 6),
+                                        (7, "sparse", 7), (3, "constant", 8), (7, "skewed", 9)])
+@pytest.mark.parametrize("is64", [0, 1])
+def test_raster_stats_on_the_device_equal_the_host_restatement(rsx, B, kind, seed, is64):
+    """rsx_raster_stats_u8_device (order statistics by a kernel, so that the histograms never visit the host between two kernels)
+    against rsx_raster_stats, the host restatement of numpy's percentile arithmetic that tests/test_hoststats.py holds against
+    numpy itself: every output bit for bit - percentiles that fall on and between samples, constant bands, 2^31+ counts."""
+    import torch
+    from rs_image_segmentation_b200.device import ptr, stream_ptr
+    from rs_image_segmentation_b200 import hoststats
+    rng = np.random.default_rng(seed)
+    for rep in range(6):
+        h = _random_histograms(rng, B, kind)
+        if not is64:
+            h = np.minimum(h, 2 ** 31 // 300)                  # the uint32 counters of one rank
+        tb = int(rng.integers(0, B))
+        lower, upper = [(2, 98), (0, 100), (5.5, 94.25), (50, 50)][rep % 4]
+        ref = hoststats.RasterStats(h, glcm_band=tb, lower=lower, upper=upper)
+        d_h = torch.from_numpy(h if is64 else h.astype(np.uint32).view(np.int32)).cuda()
+        n_bytes, off = int(rsx.load().rsx_raster_stats_device_bytes()), int(rsx.load().rsx_raster_stats_device_lut_offset())
+        blk = torch.zeros(n_bytes, dtype=torch.uint8, device="cuda")
+        rsx.call("rsx_raster_stats_u8_device", ptr(d_h), is64, B, tb, float(lower), float(upper), ptr(blk), stream_ptr())
+        raw = blk.cpu().numpy()
+        norm = raw[:16 * 12].view(np.float32).reshape(16, 3)[:B]
+        qnorm = raw[192:204].view(np.float32)
+        center = raw[208:208 + 64].view(np.float32)[:B]
+        scale = raw[272:272 + 128].view(np.float64)[:B]
+        x_lut = raw[off:off + 16 * 1024].view(np.float32).reshape(16, 256)[:B]
+        assert np.array_equal(norm.view(np.uint32), np.asarray(ref.norm, np.float32).view(np.uint32)), (rep, norm, ref.norm)
+        assert np.array_equal(qnorm.view(np.uint32), np.asarray(ref.qnorm, np.float32).view(np.uint32)), (rep, qnorm, ref.qnorm)
+        assert np.array_equal(center.view(np.uint32), np.asarray(ref.center, np.float32).view(np.uint32)), rep
+        assert np.array_equal(scale.view(np.uint64), np.asarray(ref.scale, np.float64).view(np.uint64)), rep
+        assert np.array_equal(x_lut.view(np.uint32), np.ascontiguousarray(ref.x_lut, np.float32).view(np.uint32)), rep
+
+
 # ------------------------------------------------------------------------------------------ planar element-wise drop-ins
 def test_planar_ops_bit_exact(rsx):
     import torch
