@@ -307,6 +307,17 @@ int rsx_kmeans_assign(const float* d_stack, int64_t plane_stride, int64_t n_px, 
 int64_t rsx_kmeans_aos_stride(int D);
 int rsx_kmeans_assign_bounded(const float* d_stack, int64_t plane_stride, int64_t n_px, const void* d_state, int64_t* d_acc,
                               uint8_t* d_labels_u8, float* d_aos, float* d_slack, int first, int D, int K, rsx_stream_t stream);
+/* 16-bit screening passes (K <= 8).  rsx_kmeans_quantize_u16 writes a uint16 copy of the stack (d_q16: [D] planes q_stride samples
+ * apart, q_stride a multiple of 8 and >= n_px rounded up to 8) on the grid rint((x - min_d) * 65535 / range_d) of the state's
+ * feature ranges.  rsx_kmeans_assign_q16 is a delta pass (update = 2 of rsx_kmeans_assign: same labels, sums, counters) that reads
+ * the copy - half the bytes of a pass - and goes back to the float32 planes for the pixels whose two nearest centroids are closer
+ * than the quantisation can resolve (a rigorous bound kept in the state) and for the samples that change cluster.  The copy stays
+ * valid as long as the state's feature ranges do (one rsx_kmeans_setup*). */
+int rsx_kmeans_quantize_u16(const float* d_stack, int64_t plane_stride, int64_t n_px, const void* d_state, uint16_t* d_q16,
+                            int64_t q_stride, int D, rsx_stream_t stream);
+int rsx_kmeans_assign_q16(const float* d_stack, int64_t plane_stride, int64_t n_px, const void* d_state, int64_t* d_acc,
+                          uint8_t* d_labels_u8, const uint8_t* d_labels_prev_u8, const uint16_t* d_q16, int64_t q_stride, int D, int K,
+                          rsx_stream_t stream);
 /* d_adjust (may be NULL): int64 [K*D + K] added to the totals for this centroid computation only - the host-assisted
  * empty-cluster relocation of sklearn (_k_means_common.pyx:167-211); the running totals are not modified by it. */
 int rsx_kmeans_update(void* d_state, int64_t* d_acc, int delta, int D, const int64_t* d_adjust, rsx_stream_t stream);

@@ -70,6 +70,8 @@ SIGNATURES = {
     "rsx_kmeans_setup": (i32, [vp, i32, i32, vp, vp, vp, vp, i64, vp]),
     "rsx_kmeans_assign": (i32, [vp, i64, i64, i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
     "rsx_kmeans_setup_device": (i32, [vp, i32, i32, vp, vp, vp, i64, vp]),
+    "rsx_kmeans_quantize_u16": (i32, [vp, i64, i64, vp, vp, i64, i32, vp]),
+    "rsx_kmeans_assign_q16": (i32, [vp, i64, i64, vp, vp, vp, vp, vp, i64, i32, i32, vp]),
     "rsx_kmeans_aos_stride": (i64, [i32]),
     "rsx_kmeans_assign_bounded": (i32, [vp, i64, i64, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
     "rsx_kmeans_update": (i32, [vp, vp, i32, i32, vp, vp]),

@@ -81,6 +81,30 @@ __device__ void km_derive(KmState* st) {
     for (int d = threadIdx.x; d < D; d += blockDim.x) {
         st->scale32[d] = (float)st->scale64[d];
         st->off32[d] = (float)(st->min64[d] - st->mean64[d]);
+        // 16-bit grid over [fmin, fmax] (a constant feature: step 0, every sample reads back as fmin)
+        const double range = st->fmax64[d] - st->fmin64[d];
+        const bool flat = !(range >= 10.0 * 2.220446049250313e-16);
+        const float step = flat ? 0.f : (float)(range / 65535.0);
+        st->qstep32[d] = step;
+        st->qinv32[d] = flat ? 0.f : (float)(65535.0 / range);
+        st->qmin32[d] = (float)st->fmin64[d];
+        st->qoff32[d] = (float)(st->fmin64[d] - 8388608.0 * (double)step);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // |x~ - x|: 0.51 steps from the rounding to the grid (the fp32 evaluation of (x - fmin) * qinv32 included), 0.5 steps from the
+        // rounding of qoff32 (its magnitude is 2^23 steps), 2^-24 relative from qstep32 and from the fma: 1.02 steps + 2^-22 (range + |x|)
+        double worst = 0.0;
+        for (int j = 0; j < K; ++j) {
+            double e = 0.0;
+            for (int d = 0; d < D; ++d) {
+                const double range = st->fmax64[d] - st->fmin64[d];
+                const double qerr = 1.02 * (double)st->qstep32[d] + 2.384185791015625e-07 * ((range > 0 ? range : 0.0) + st->absmax[d]);
+                e += fabs((double)st->w32[j * KM_MAXD + d]) * qerr;
+            }
+            worst = fmax(worst, e);
+        }
+        st->tau_q = __double2float_ru((double)st->tau + 2.0 * 1.01 * worst);
     }
 }
 
@@ -254,7 +278,7 @@ extern "C" int rsx_kmeans_assign(const float* d_stack, int64_t plane_stride, int
     // at K = 32 and slower at K = 16 on the B200 (the per-pixel argmin over K distances, not the FMAs, is what both are bound by;
     // DESIGN.md 4.2), so it stays an option.
     a.use_tc = rsx_option("km_tc", 0);
-    a.bounded = 0, a.aos = nullptr, a.slack = nullptr;
+    a.bounded = 0, a.aos = nullptr, a.slack = nullptr, a.q16 = nullptr, a.q_stride = 0;
     a.full_stream = rsx_option("km_full_stream", 0);
     return g_part_assign[km_part_of(D)](a, (cudaStream_t)stream);
 }
@@ -277,6 +301,45 @@ extern "C" int rsx_kmeans_assign_bounded(const float* d_stack, int64_t plane_str
     a.acc = reinterpret_cast<long long*>(d_acc), a.lab8 = d_labels_u8;
     a.mode = KM_DELTA, a.D = D, a.K = K;
     a.bounded = first ? 1 : 2, a.aos = d_aos, a.slack = d_slack;
+    return g_part_assign[km_part_of(D)](a, (cudaStream_t)stream);
+}
+
+// 16-bit screening passes (K <= 8): rsx_kmeans_quantize_u16 writes the uint16 copy of the stack on the grid the state derives from
+// the feature ranges; rsx_kmeans_assign_q16 is a delta pass (update = 2 of rsx_kmeans_assign) that reads the copy instead of the
+// float32 planes and falls back to them for the pixels it cannot decide and for the samples that move.
+extern "C" int rsx_kmeans_quantize_u16(const float* d_stack, int64_t plane_stride, int64_t n_px, const void* d_state, uint16_t* d_q16, int64_t q_stride,
+                                       int D, rsx_stream_t stream) {
+    RSX_REQUIRE(d_stack && d_state && d_q16 && n_px > 0 && D >= 1 && D <= KM_MAXD, "rsx_kmeans_quantize_u16: bad arguments");
+    RSX_REQUIRE(((uintptr_t)d_stack & 15) == 0 && (plane_stride & 3) == 0 && ((uintptr_t)d_q16 & 15) == 0 && (q_stride & 7) == 0 && q_stride >= ((n_px + 7) & ~(int64_t)7),
+                "rsx_kmeans_quantize_u16: planes must be 16-byte aligned, q_stride a multiple of 8 and >= n_px rounded up to 8");
+    if (D > km_part_hi(KM_NUM_PARTS - 1)) {
+        rsx_set_error("rsx_kmeans_quantize_u16: D=%d not compiled (1..%d)", D, km_part_hi(KM_NUM_PARTS - 1));
+        return RSX_ERR_UNSUPPORTED;
+    }
+    KmLaunch a;
+    memset(&a, 0, sizeof(a));
+    a.stack = d_stack, a.plane_stride = plane_stride, a.n_px = n_px, a.D = D, a.q16 = d_q16, a.q_stride = q_stride, a.bounded = -1;
+    return g_part_assign[km_part_of(D)](a, (cudaStream_t)stream);
+}
+
+extern "C" int rsx_kmeans_assign_q16(const float* d_stack, int64_t plane_stride, int64_t n_px, const void* d_state, int64_t* d_acc, uint8_t* d_labels_u8,
+                                     const uint8_t* d_labels_prev_u8, const uint16_t* d_q16, int64_t q_stride, int D, int K, rsx_stream_t stream) {
+    RSX_REQUIRE(d_stack && d_state && d_acc && d_labels_u8 && d_labels_prev_u8 && d_q16 && n_px > 0, "rsx_kmeans_assign_q16: null argument");
+    RSX_REQUIRE(d_labels_u8 != d_labels_prev_u8, "rsx_kmeans_assign_q16: a delta pass needs distinct previous and current label buffers");
+    RSX_REQUIRE(D >= 1 && D <= KM_MAXD && K >= 1 && K <= 8, "rsx_kmeans_assign_q16: needs 1 <= K <= 8");
+    RSX_REQUIRE(((uintptr_t)d_stack & 15) == 0 && (plane_stride & 3) == 0 && ((uintptr_t)d_q16 & 15) == 0 && (q_stride & 7) == 0,
+                "rsx_kmeans_assign_q16: planes must be 16-byte aligned");
+    RSX_REQUIRE((((uintptr_t)d_labels_u8 | (uintptr_t)d_labels_prev_u8) & 3) == 0, "rsx_kmeans_assign_q16: label buffers must be aligned");
+    if (D > km_part_hi(KM_NUM_PARTS - 1)) {
+        rsx_set_error("rsx_kmeans_assign_q16: D=%d not compiled (1..%d)", D, km_part_hi(KM_NUM_PARTS - 1));
+        return RSX_ERR_UNSUPPORTED;
+    }
+    KmLaunch a;
+    memset(&a, 0, sizeof(a));
+    a.stack = d_stack, a.plane_stride = plane_stride, a.n_px = n_px, a.row_len = 4096;
+    a.acc = reinterpret_cast<long long*>(d_acc), a.lab8 = d_labels_u8, a.prev8 = d_labels_prev_u8;
+    a.mode = KM_DELTA, a.D = D, a.K = K, a.q16 = d_q16, a.q_stride = q_stride;
+    a.n_stages = min(4, max(0, rsx_option("km_stages", 0)));
     return g_part_assign[km_part_of(D)](a, (cudaStream_t)stream);
 }
 

@@ -502,18 +502,68 @@ __device__ __forceinline__ void km_move_in_all(const float* __restrict__ st, int
     }
 }
 
-template <int D, int MODE, bool INERTIA, int KU, bool WARPX>
+// ---- 16-bit screening passes (QIN): the stage holds the uint16 copy of the stack (half the bytes of a pass); a sample reads back
+// as x~ = fma(2^23 + u, step, off) - the float whose low mantissa bits are u, built with one PRMT - and its distances are within
+// KmState::tau_q of the exact ones.  A pixel whose two nearest centroids are closer than that is evaluated from the float32 planes
+// (km_uncertain_pixel: fp32 distances, float64 inside their own near-tie band); the pixels that move fetch their float32 sample
+// for the integer sums.  Labels, sums, counters: those of the float32 pass.
+constexpr int KM_QSTRIDE = KM_BLOCK_PX + 8;  // uint16 elements between staged planes (16-byte aligned rows, 4 banks apart)
+__device__ __forceinline__ float km_q_lo(uint32_t w, float step, float off) { return fmaf(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)), step, off); }
+__device__ __forceinline__ float km_q_hi(uint32_t w, float step, float off) { return fmaf(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632)), step, off); }
+
+template <int D>
+__device__ __noinline__ int km_uncertain_pixel(const float* __restrict__ stack, int64_t plane_stride, int64_t p, unsigned* ties_out) {
+    float x[D];
+    double inertia = 0.0;
+    unsigned ties = 0;
+    const int l = km_scalar_pixel<D>(stack, plane_stride, p, g_km.K, x, false, inertia, ties);
+    *ties_out += ties;
+    return l;
+}
+
+// km_move_samples with the samples fetched from the float32 planes (the stage holds the 16-bit copy)
+template <int D>
+__device__ __forceinline__ void km_move_samples_global(const float* __restrict__ stack, int64_t plane_stride, int64_t warp_p0, unsigned cm,
+                                                       uint32_t old_packed, uint32_t new_packed, long long* __restrict__ wacc, float my_pow2) {
+    unsigned b = __ballot_sync(0xffffffffu, cm != 0);
+    const int lane = threadIdx.x & 31;
+    const float* mine = stack + (int64_t)min(lane, D - 1) * plane_stride + warp_p0;
+    while (b) {
+        const int src = __ffs(b) - 1;
+        b &= b - 1;
+        unsigned m = __shfl_sync(0xffffffffu, cm, src);
+        const uint32_t ov = __shfl_sync(0xffffffffu, old_packed, src), nv = __shfl_sync(0xffffffffu, new_packed, src);
+        if (lane <= D) {
+            const float4 xv = __ldg(reinterpret_cast<const float4*>(mine + 4 * src));  // the owning thread's four pixels of this feature
+            const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (m & (1u << i)) {
+                    const int from = (int)((ov >> (8 * i)) & 0xffu), to = (int)((nv >> (8 * i)) & 0xffu);
+                    const long long q = lane < D ? __float2ll_rn(xs[i] * my_pow2) : 1ll;
+                    wacc[to * (D + 1) + lane] += q;
+                    if (from < KM_MAXK) wacc[from * (D + 1) + lane] -= q;
+                }
+            }
+        }
+    }
+}
+
+template <int D, int MODE, bool INERTIA, int KU, bool WARPX, bool QIN = false>
 __global__ void __launch_bounds__(KM_THREADS, km_ctas_per_sm(D)) km_stream_kernel(const float* __restrict__ stack, int64_t plane_stride, int64_t n_px,
                                                                   long long* __restrict__ gacc, uint8_t* __restrict__ lab8,
                                                                   const uint8_t* __restrict__ prev8, int32_t* __restrict__ lab32,
-                                                                  double* __restrict__ inertia_out, int n_stages, int c64_offset) {
+                                                                  double* __restrict__ inertia_out, int n_stages, int c64_offset,
+                                                                  const uint16_t* __restrict__ q16, int64_t q_stride) {
     constexpr bool SUMS = MODE != KM_ASSIGN;
+    constexpr int STAGE_BYTES = QIN ? D * KM_QSTRIDE * 2 : D * KM_STAGE_STRIDE * 4;
+    static_assert(!QIN || (KU == 8 && MODE == KM_DELTA && !INERTIA), "the 16-bit screening pass is a K <= 8 delta pass");
     constexpr bool LOCKSTEP = false;  // true: one CTA barrier per block instead of the empty mbarriers (kept for experiments)
     extern __shared__ __align__(128) unsigned char km_smem[];
     const int K = g_km.K;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     float* stages = reinterpret_cast<float*>(km_smem);                                                          // [n_stages][D][512]
-    long long* wacc_all = reinterpret_cast<long long*>(km_smem + (size_t)n_stages * D * KM_STAGE_STRIDE * 4);       // [4 warps][K][D+1]
+    long long* wacc_all = reinterpret_cast<long long*>(km_smem + (size_t)n_stages * STAGE_BYTES);                  // [4 warps][K][D+1]
     uint64_t* full = reinterpret_cast<uint64_t*>(wacc_all + (SUMS ? KM_WARPS * K * (D + 1) : 0));               // [n_stages]
     uint64_t* empty = full + n_stages;                                                                          // [n_stages]
     int* ticket = reinterpret_cast<int*>(empty + n_stages);                                                     // [n_stages] (+ pad): refills issued per stage
@@ -551,9 +601,17 @@ __global__ void __launch_bounds__(KM_THREADS, km_ctas_per_sm(D)) km_stream_kerne
     __syncthreads();
     auto issue = [&](int64_t blk, int s) {  // one thread: stage block blk
         const int64_t p0 = blk * KM_BLOCK_PX;
-        const unsigned bytes = (unsigned)min((int64_t)KM_BLOCK_PX, n4 - p0) * 4u;
+        const unsigned npx = (unsigned)min((int64_t)KM_BLOCK_PX, n4 - p0);
+        // bulk copies move multiples of 16 bytes: the 16-bit planes are padded to a multiple of 8 samples
+        const unsigned bytes = QIN ? ((npx + 7u) & ~7u) * 2u : npx * 4u;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads of this stage precede the async refill
         mbar_expect_tx(&full[s], bytes * D);
+        if (QIN) {
+            uint16_t* dst = reinterpret_cast<uint16_t*>(km_smem + (size_t)s * STAGE_BYTES);
+#pragma unroll 1
+            for (int d = 0; d < D; ++d) bulk_g2s(dst + d * KM_QSTRIDE, q16 + d * q_stride + p0, bytes, &full[s]);
+            return;
+        }
         float* dst = stages + (size_t)s * D * KM_STAGE_STRIDE;
 #pragma unroll 1
         for (int d = 0; d < D; ++d) bulk_g2s(dst + d * KM_STAGE_STRIDE, stack + d * plane_stride + p0, bytes, &full[s]);
@@ -584,7 +642,27 @@ __global__ void __launch_bounds__(KM_THREADS, km_ctas_per_sm(D)) km_stream_kerne
         const float* st = stages + (size_t)s * D * KM_STAGE_STRIDE;
         uint32_t packed = 0, diff = 0;
         if (KU == 8) {
-            if (valid) {
+            if (valid && QIN) {
+                const uint16_t* sq = reinterpret_cast<const uint16_t*>(km_smem + (size_t)s * STAGE_BYTES) + 4 * tid;
+                float4 v[D];
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    const uint2 r = *reinterpret_cast<const uint2*>(sq + d * KM_QSTRIDE);
+                    const float qs = g_km.qstep32[d], qo = g_km.qoff32[d];
+                    v[d] = make_float4(km_q_lo(r.x, qs, qo), km_q_hi(r.x, qs, qo), km_q_lo(r.y, qs, qo), km_q_hi(r.y, qs, qo));
+                }
+                float b[4], sc[4];
+                km_distances<D, KU>(v, K, wsm, b, sc);
+                int l[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    l[i] = (int)(__float_as_uint(b[i]) & 7u);
+                    if (!(sc[i] - b[i] > g_km.tau_q)) l[i] = km_uncertain_pixel<D>(stack, plane_stride, p + i, &ties);
+                }
+                packed = (uint32_t)l[0] | ((uint32_t)l[1] << 8) | ((uint32_t)l[2] << 16) | ((uint32_t)l[3] << 24);
+                diff = packed ^ pv;
+                *reinterpret_cast<uint32_t*>(lab8 + p) = packed;
+            } else if (valid) {
                 float4 v[D];
 #pragma unroll
                 for (int d = 0; d < D; ++d) v[d] = *reinterpret_cast<const float4*>(st + d * KM_STAGE_STRIDE + 4 * tid);
@@ -690,6 +768,8 @@ __global__ void __launch_bounds__(KM_THREADS, km_ctas_per_sm(D)) km_stream_kerne
         if (MODE == KM_FULL) cm = valid ? 0xfu : 0u;
         if (MODE == KM_FULL)
             km_move_in_all<D>(st, warp * 128, __ballot_sync(0xffffffffu, valid), packed, wacc, my_pow2);
+        else if (SUMS && QIN)
+            km_move_samples_global<D>(stack, plane_stride, blk * KM_BLOCK_PX + warp * 128, cm, pv, packed, wacc, my_pow2);
         else if (SUMS)
             km_move_samples<D>(st, warp * 128, cm, pv, packed, wacc, my_pow2);
         if (LOCKSTEP) {
@@ -1413,6 +1493,28 @@ static int km_launch_bounded(const KmLaunch& a, cudaStream_t s) {
     return rsx_check_launch("km_bounded");
 }
 
+// the 16-bit copy of the stack for the screening passes: u = rint((x - fmin) * 65535 / range), planes q_stride apart
+static __global__ void __launch_bounds__(256) km_quantize_kernel(const float* __restrict__ stack, int64_t plane_stride, int64_t n_px, uint16_t* __restrict__ q16,
+                                                          int64_t q_stride) {
+    const int d = blockIdx.y;
+    const float fmin = g_km.qmin32[d], inv = g_km.qinv32[d];
+    const float* src = stack + d * plane_stride;
+    uint16_t* dst = q16 + d * q_stride;
+    const int64_t n4 = (n_px + 3) >> 2;  // the planes are padded to a multiple of 4 samples
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
+        const float4 x = __ldcs(reinterpret_cast<const float4*>(src) + i);
+        auto qz = [&](float v) { return (uint32_t)__float2uint_rn(fminf(fmaxf(__fmul_rn(__fsub_rn(v, fmin), inv), 0.f), 65535.f)); };
+        const uint2 o = make_uint2(qz(x.x) | (qz(x.y) << 16), qz(x.z) | (qz(x.w) << 16));
+        *reinterpret_cast<uint2*>(dst + 4 * i) = o;
+    }
+}
+static int km_launch_quantize(const KmLaunch& a, uint16_t* q16, cudaStream_t s) {
+    const int64_t n4 = (a.n_px + 3) >> 2;
+    dim3 grid((unsigned)max((int64_t)1, min(ceil_div(n4, (int64_t)256), (int64_t)rsx_num_sms() * 8)), (unsigned)a.D);
+    km_quantize_kernel<<<grid, 256, 0, s>>>(a.stack, a.plane_stride, a.n_px, q16, a.q_stride);
+    return rsx_check_launch("km_quantize");
+}
+
 template <int D>
 static int km_launch_full(const KmLaunch& a, cudaStream_t s) {
     const int smem = KmSmem<D>::CACHE_BYTES;
@@ -1438,13 +1540,14 @@ static int km_launch_full(const KmLaunch& a, cudaStream_t s) {
     return rsx_check_launch("km_full");
 }
 
-template <int D, int MODE, bool INERTIA, int KU, bool WARPX = false>
+template <int D, int MODE, bool INERTIA, int KU, bool WARPX = false, bool QIN = false>
 static int km_launch_stream(const KmLaunch& a, cudaStream_t s) {
-    auto kern = km_stream_kernel<D, MODE, INERTIA, KU, WARPX>;
+    auto kern = km_stream_kernel<D, MODE, INERTIA, KU, WARPX, QIN>;
+    constexpr int STAGE_BYTES = QIN ? D * KM_QSTRIDE * 2 : D * KM_STAGE_STRIDE * 4;
     const int acc_bytes = MODE == KM_ASSIGN ? 0 : KM_WARPS * a.K * (D + 1) * 8;
     const int w_bytes = KU == 0 ? (((D + 1) * ((a.K + 7) & ~7) + (INERTIA ? a.K * D : 0)) * 4 + 15) / 16 * 16 : 0;
     const int c64_bytes = WARPX ? (D + 1) * ((a.K + 31) & ~31) * 8 : 0;
-    auto c64_off = [&](int stages) { return stages * D * KM_STAGE_STRIDE * 4 + acc_bytes + 2 * stages * 8 + 16 + w_bytes; };
+    auto c64_off = [&](int stages) { return stages * STAGE_BYTES + acc_bytes + 2 * stages * 8 + 16 + w_bytes; };
     auto smem_for = [&](int stages) { return c64_off(stages) + c64_bytes; };
     // stages: enough blocks in flight per SM to cover HBM latency at full bandwidth (~64 KB/SM), within shared memory
     static int cfg_K = -1, cfg_stages = 0, cfg_per_sm = 0, cfg_dev = -1, cfg_req = -1;  // per kernel instantiation
@@ -1452,7 +1555,7 @@ static int km_launch_stream(const KmLaunch& a, cudaStream_t s) {
     cudaGetDevice(&dev);
     if (cfg_K != a.K || cfg_dev != dev || cfg_req != a.n_stages) {
         int best_stages = 2, best_per_sm = 0;
-        for (int stages = a.n_stages > 0 ? a.n_stages : 2; stages <= (a.n_stages > 0 ? a.n_stages : 3); ++stages) {
+        for (int stages = a.n_stages > 0 ? a.n_stages : 2; stages <= (a.n_stages > 0 ? a.n_stages : (QIN ? 4 : 3)); ++stages) {
             const int smem = smem_for(stages);
             if (smem > 227 * 1024) break;
             if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max(smem, 48 * 1024)) != cudaSuccess) break;
@@ -1474,7 +1577,7 @@ static int km_launch_stream(const KmLaunch& a, cudaStream_t s) {
     const int64_t n_blocks = ceil_div(n4, (int64_t)KM_BLOCK_PX);
     const int grid = (int)max((int64_t)1, min(n_blocks, (int64_t)rsx_num_sms() * cfg_per_sm));
     kern<<<grid, KM_THREADS, smem_for(cfg_stages), s>>>(a.stack, a.plane_stride, a.n_px, a.acc, a.lab8, a.prev8, a.lab32, a.inertia, cfg_stages,
-                                                        c64_off(cfg_stages));
+                                                        c64_off(cfg_stages), a.q16, a.q_stride);
     return rsx_check_launch("km_stream");
 }
 
@@ -1542,6 +1645,9 @@ static int km_launch2(const KmLaunch& a, cudaStream_t s) {
         }
         return km_launch_stream<D, KM_FULL, false, KU, WARPX>(a, s);
     }
+    if constexpr (KU == 8) {
+        if (a.mode == KM_DELTA && a.q16) return km_launch_stream<D, KM_DELTA, false, KU, false, true>(a, s);
+    }
     if (a.mode == KM_DELTA) return km_launch_stream<D, KM_DELTA, false, KU, WARPX>(a, s);
     if (a.inertia) return km_launch_stream<D, KM_ASSIGN, true, KU, WARPX>(a, s);
     return km_launch_stream<D, KM_ASSIGN, false, KU, WARPX>(a, s);
@@ -1579,7 +1685,10 @@ static int km_dispatch(const KmLaunch& a, cudaStream_t s) {
     }
 }
 
-int KM_PART_FN(_assign)(const KmLaunch& a, cudaStream_t s) { return km_dispatch<km_part_lo(RSX_KM_PART)>(a, s); }
+int KM_PART_FN(_assign)(const KmLaunch& a, cudaStream_t s) {
+    if (a.bounded == -1) return km_launch_quantize(a, const_cast<uint16_t*>(a.q16), s);  // build the 16-bit copy (reads this unit's constant mirror)
+    return km_dispatch<km_part_lo(RSX_KM_PART)>(a, s);
+}
 
 int KM_PART_FN(_publish)(const void* d_state, cudaStream_t s) {
     cudaError_t e = cudaMemcpyToSymbolAsync(g_km, d_state, sizeof(KmState), 0, cudaMemcpyDeviceToDevice, s);

@@ -34,8 +34,13 @@ struct __align__(16) KmState {
     double drift64[KM_MAXK];
     float drift_up[KM_MAXK], drift_dn[KM_MAXK];  // drift64 rounded outwards (one float ulp beyond)
     double fmin64[KM_MAXD], fmax64[KM_MAXD];     // the raw per-feature range the scaling was derived from (rsx_kmeans_read_scaling)
+    // 16-bit screening passes (km_stream_kernel<..., QIN>): features quantised to u = rint((x - fmin) * qinv32), read back as
+    // x~ = fma(2^23 + u, qstep32, qoff32) with qoff32 = fl32(fmin - 2^23 qstep32); |x~ - x| <= qerr (derived in km_derive), hence
+    // distances within sum_d |w_jd| qerr_d of the fp32 ones: tau_q = tau + twice the largest such sum
+    float qstep32[KM_MAXD], qoff32[KM_MAXD], qinv32[KM_MAXD], qmin32[KM_MAXD];
+    float tau_q;
     float bound_err;                             // error bound of the fp32 squared distances |x'|^2 + dist_j (tau_tight + that of |x'|^2)
-    float pad_[3];
+    float pad_[2];
 };
 
 
@@ -66,6 +71,8 @@ struct KmLaunch {
     int use_tc;    // K > 8, D <= 13: distances on the tensor cores (tcgen05, 3 x TF32 split); 0 = the fp32 FFMA2 path
     // bounded passes (K <= 8): 0 = off; 1 = first one (reads the planes, writes the pixel-interleaved copy + slacks); 2 = later ones
     int bounded;
+    const uint16_t* q16;  // [D][q_stride] 16-bit copy of the stack (screening passes), or nullptr
+    int64_t q_stride;
     int full_stream;  // K <= 8 full pass through the streaming kernel (every pixel moves in) instead of the per-thread accumulators
     float* aos;    // [n_px][km_aos_stride(D)] pixel-interleaved copy of the stack (scattered reads cost 1-3 sectors instead of D)
     float* slack;  // [n_px rounded up to 4] slack + drift of the label at the time it was computed

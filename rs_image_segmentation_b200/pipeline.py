@@ -448,6 +448,11 @@ class DeviceKMeans:
         self.full_passes = max(1, int(full_passes))
         self._aos = self._slack = self._bound_plane = None
         self._bounds_valid = False
+        # K <= 8: late delta passes read a 16-bit copy of the stack (half the bytes; rsx_kmeans_assign_q16) once few enough labels
+        # move that fetching the float32 samples of the moving pixels costs less than the bytes saved
+        self.q16_from = int(_lib.get_option("km_q16_from", 6)) if (_lib.get_option("km_q16", 0) and self.delta and K <= 8) else -1
+        self._q16 = None
+        self._q16_valid = False
         self._labels = None
         self._passes = 0
         # several GPUs: the update kernels reduce the ranks' sums themselves through peer-mapped memory (no collective per
@@ -479,6 +484,7 @@ class DeviceKMeans:
         self.acc.zero_()
         self._passes = 0
         self._bounds_valid = False
+        self._q16_valid = False
         if self.peers is not None:
             self.peers.zero(stream_ptr())
         _lib.call("rsx_kmeans_setup", ptr(self.state), self.D, self.K, hptr(self.fmin), hptr(self.fmax), hptr(mu), hptr(c0),
@@ -494,6 +500,7 @@ class DeviceKMeans:
         self.acc.zero_()
         self._passes = 0
         self._bounds_valid = False
+        self._q16_valid = False
         if self.peers is not None:
             self.peers.zero(stream_ptr())
         _lib.call("rsx_kmeans_setup_device", ptr(self.state), self.D, self.K, ptr(minmax_buf), ptr(rows_raw), hptr(mu), self.n_global,
@@ -556,6 +563,19 @@ class DeviceKMeans:
                     _lib.call("rsx_kmeans_assign_bounded", ptr(self.planes), self.stride, self.n_px, ptr(self.state), d_acc, ptr(lab),
                               ptr(self._aos), ptr(self._slack), 1 if first else 0, self.D, self.K, stream_ptr())
             self._bounds_valid = True
+        elif mode == 2 and 0 <= self.q16_from <= self._passes and self.n_px:
+            self._bounds_valid = False
+            if not self._q16_valid:
+                qs = (self.n_px + 7) // 8 * 8
+                if self._q16 is None:
+                    self._q16 = torch.empty((self.D, qs), dtype=torch.int16, device=self.planes.device)
+                with self.timer("kmeans_quantize"):
+                    _lib.call("rsx_kmeans_quantize_u16", ptr(self.planes), self.stride, self.n_px, ptr(self.state), ptr(self._q16), qs, self.D,
+                              stream_ptr())
+                self._q16_valid = True
+            with self.timer("kmeans_assign_delta"):
+                _lib.call("rsx_kmeans_assign_q16", ptr(self.planes), self.stride, self.n_px, ptr(self.state), d_acc, ptr(cur), ptr(prev),
+                          ptr(self._q16), self._q16.shape[1], self.D, self.K, stream_ptr())
         elif self.n_px:
             self._bounds_valid = False
             with self.timer("kmeans_assign_delta" if mode == 2 else "kmeans_assign_full"):

@@ -265,6 +265,49 @@ def test_kmeans_bounded_passes_equal_unbounded(P, K, D, n_iter, full_passes):
     assert float((runs[True][3] > 0).float().mean()) > 0.5
 
 
+@pytest.mark.parametrize("K,D,n_iter,q_from", [(8, 13, 12, 3), (5, 6, 9, 1), (6, 22, 8, 2)])
+def test_kmeans_16bit_screening_passes_equal_float32_passes(P, K, D, n_iter, q_from):
+    """Delta passes that read the uint16 copy of the stack (rsx_kmeans_assign_q16; the float32 planes only for the pixels the
+    quantisation cannot decide and for the samples that move) leave the same labels after every pass, the same integer totals
+    and centroids as the float32 passes - a constant feature and a feature far from zero included."""
+    import torch
+    from rs_image_segmentation_b200 import _lib
+    n_px = 40013 + K
+    rng = np.random.default_rng(10 * D + K)
+    X = (rng.normal(size=(n_px, 3)) @ rng.normal(size=(3, D)) + 0.3 * rng.normal(size=(n_px, D))) * rng.uniform(0.01, 50.0, size=D) + rng.uniform(-5, 5, size=D)
+    X[:, 1] = 7.5
+    X[:, 2] += 4000.0
+    X = X.astype(np.float32)
+    stride = (n_px + 31) // 32 * 32
+    planes = torch.zeros((D, stride), dtype=torch.float32, device="cuda")
+    planes[:, :n_px] = torch.from_numpy(np.ascontiguousarray(X.T)).cuda()
+    mn, mx = X.min(axis=0), X.max(axis=0)
+    runs = {}
+    try:
+        for q16 in (0, 1):
+            _lib.set_option("km_q16", q16)
+            _lib.set_option("km_q16_from", q_from)
+            km = P.DeviceKMeans(planes, n_px, D, K, mn, mx, n_px, 257, full_passes=1)
+            km.setup(km.scale_rows(X[P.draw_init_indices(n_px, K, 5)]))
+            per_pass = []
+            for _ in range(n_iter):
+                mode = km.assign_pass()
+                per_pass.append((km._cur_labels[:n_px].clone(), km.acc[:K * D + K].clone(), int(km.acc[km.n_acc - 1])))
+                km.update(mode)
+            res = km._result(km.finish(True), n_iter)
+            runs[q16] = (per_pass, res, km.acc[km.n_acc:km.n_acc + K * D + K].clone(), km._q16 is not None)
+    finally:
+        _lib.set_option("km_q16", 0)
+    assert runs[1][3] and not runs[0][3]
+    for i, (a, b) in enumerate(zip(runs[0][0], runs[1][0])):
+        assert torch.equal(a[0], b[0]), f"labels differ after pass {i}"
+        assert torch.equal(a[1], b[1]), f"pass sums differ in pass {i}"
+        assert a[2] == b[2], f"changed-label counter differs in pass {i}"
+    assert torch.equal(runs[0][2], runs[1][2])
+    assert np.array_equal(runs[0][1].centroids, runs[1][1].centroids)
+    assert torch.equal(runs[0][1].labels, runs[1][1].labels)
+
+
 @pytest.mark.parametrize("D,K", [(13, 8), (7, 5), (22, 32)])
 def test_kmeans_device_setup_equals_host_setup(P, D, K):
     """rsx_kmeans_setup_device (range from the device min/max trackers, initial centroids scaled by the kernel) leaves the same

@@ -26,7 +26,9 @@ P.kmeans_on_features(fr, D, K, 1, 7000)          # NaN pass etc.
 mn, mx = fr.minmax.read()
 
 
-def run(bounded, full_passes):
+def run(bounded, full_passes, q16_from=-1):
+    _lib.set_option("km_q16", 1 if q16_from >= 0 else 0)
+    _lib.set_option("km_q16_from", max(q16_from, 0))
     km = P.DeviceKMeans(fr.planes, fr.n_px, D, K, mn[:D], mx[:D], fr.n_px, fr.W, bounded=bounded, full_passes=full_passes)
     c0 = km.scale_rows(km.gather_rows(P.draw_init_indices(fr.n_px, K, 7000), 0))
     for rep in range(2):
@@ -47,10 +49,12 @@ def run(bounded, full_passes):
 
 
 base = None
-FP = [int(v) for v in os.environ.get("PROBE_FULL_PASSES", "3").split(",")]
+FP = [int(v) for v in os.environ.get("PROBE_FULL_PASSES", "3").split(",") if v]
 UFP = [int(v) for v in os.environ.get("PROBE_UNBOUNDED_FULL_PASSES", "").split(",") if v]
-for name, bounded, fp in [("unbounded", False, 3)] + [(f"unbounded_fp{v}", False, v) for v in UFP] + [(f"bounded_fp{v}", True, v) for v in FP]:
-    ms, changed, res = run(bounded, fp)
+Q16 = [int(v) for v in os.environ.get("PROBE_Q16_FROM", "").split(",") if v]
+for name, bounded, fp, qf in [("unbounded", False, 3, -1)] + [(f"unbounded_fp{v}", False, v, -1) for v in UFP] + [(f"bounded_fp{v}", True, v, -1) for v in FP] + \
+        [(f"q16_from{v}", False, 3, v) for v in Q16]:
+    ms, changed, res = run(bounded, fp, qf)
     out = {"variant": name, "sum_ms": round(sum(ms), 3), "ms": [round(m, 3) for m in ms], "inertia": res.inertia, "near_ties": res.near_ties}
     if base is None:
         base = res
