@@ -318,7 +318,7 @@ extern "C" int rsx_kmeans_quantize_u16(const float* d_stack, int64_t plane_strid
     }
     KmLaunch a;
     memset(&a, 0, sizeof(a));
-    a.stack = d_stack, a.plane_stride = plane_stride, a.n_px = n_px, a.D = D, a.q16 = d_q16, a.q_stride = q_stride, a.bounded = -1;
+    a.stack = d_stack, a.plane_stride = plane_stride, a.n_px = n_px, a.D = D, a.q16 = d_q16, a.q_stride = q_stride, a.mode = KM_QUANTIZE;
     return g_part_assign[km_part_of(D)](a, (cudaStream_t)stream);
 }
 

@@ -1686,7 +1686,7 @@ static int km_dispatch(const KmLaunch& a, cudaStream_t s) {
 }
 
 int KM_PART_FN(_assign)(const KmLaunch& a, cudaStream_t s) {
-    if (a.bounded == -1) return km_launch_quantize(a, const_cast<uint16_t*>(a.q16), s);  // build the 16-bit copy (reads this unit's constant mirror)
+    if (a.mode == KM_QUANTIZE) return km_launch_quantize(a, const_cast<uint16_t*>(a.q16), s);  // reads this unit's constant mirror of the state
     return km_dispatch<km_part_lo(RSX_KM_PART)>(a, s);
 }
 

@@ -45,6 +45,7 @@ struct __align__(16) KmState {
 
 
 constexpr int KM_ASSIGN = 0, KM_FULL = 1, KM_DELTA = 2;  // the `update` argument of rsx_kmeans_assign
+constexpr int KM_QUANTIZE = 3;                           // KmLaunch::mode only: write the 16-bit copy of the stack (no pass)
 
 // one translation unit per range of D (compile time); each owns a __constant__ mirror of the state
 #define KM_NUM_PARTS 6
