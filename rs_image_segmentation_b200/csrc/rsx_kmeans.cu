@@ -23,12 +23,30 @@
 extern "C" int64_t rsx_kmeans_state_bytes(void) { return (int64_t)sizeof(KmState); }
 
 // ----------------------------------------------------------------------------- derived tables (device, 1 CTA)
+// The 16-bit grid of the screening passes depends on the feature ranges only: set-up kernels, once (the CTA synchronises after it).
+__device__ void km_derive_grid(KmState* st) {
+    for (int d = threadIdx.x; d < st->D; d += blockDim.x) {
+        // grid over [fmin, fmax] (a constant feature: step 0, every sample reads back as fmin)
+        const double range = st->fmax64[d] - st->fmin64[d];
+        const bool flat = !(range >= 10.0 * 2.220446049250313e-16);
+        const float step = flat ? 0.f : (float)(range / 65535.0);
+        st->qstep32[d] = step;
+        st->qinv32[d] = flat ? 0.f : (float)(65535.0 / range);
+        st->qmin32[d] = (float)st->fmin64[d];
+        st->qoff32[d] = (float)(st->fmin64[d] - 8388608.0 * (double)step);
+        // |x~ - x|: 0.51 steps from the rounding to the grid (the fp32 evaluation of (x - fmin) * qinv32 included), 0.5 steps from the
+        // rounding of qoff32 (its magnitude is 2^23 steps), 2^-24 relative from qstep32 and from the fma: 1.02 steps + 2^-22 (range + |x|)
+        st->qerr32[d] = __double2float_ru(1.02 * (double)step + 2.384185791015625e-07 * ((flat ? 0.0 : range) + st->absmax[d]));
+    }
+    __syncthreads();
+}
+
 __device__ void km_derive(KmState* st) {
     // called by one CTA; thread j < K handles centroid j
     const int D = st->D, K = st->K;
-    __shared__ double e_arr[KM_MAXK];
+    __shared__ double e_arr[KM_MAXK], q_arr[KM_MAXK];
     for (int j = threadIdx.x; j < K; j += blockDim.x) {
-        double cn = 0.0, bias = 0.0, mag = 0.0;
+        double cn = 0.0, bias = 0.0, mag = 0.0, qe = 0.0;
         for (int d = 0; d < D; ++d) {
             double c = st->cent64[j * KM_MAXD + d];
             double w = -2.0 * c * st->scale64[d];
@@ -37,17 +55,19 @@ __device__ void km_derive(KmState* st) {
             st->w32[j * KM_MAXD + d] = (float)w;
             st->cent32[j * KM_MAXD + d] = (float)c;
             mag += st->absmax[d] * fabs(w) + fabs(2.0 * c * (st->min64[d] - st->mean64[d]));
+            qe += fabs(w) * (double)st->qerr32[d];
         }
         st->cnorm64[j] = cn;
         st->bias32[j] = (float)(cn + bias);
         // rounding bound of the fp32 path (DESIGN.md "KMeans near-tie bound"): every term of the D+1 term sum and
         // every partial sum is below mag + cn in magnitude; w32, bias32 and each FMA round once (u = 2^-24)
         e_arr[j] = (D + 3) * (mag + cn);
+        q_arr[j] = qe;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        double e_max = 0.0;
-        for (int j = 0; j < K; ++j) e_max = fmax(e_max, e_arr[j]);
+        double e_max = 0.0, q_max = 0.0;
+        for (int j = 0; j < K; ++j) e_max = fmax(e_max, e_arr[j]), q_max = fmax(q_max, q_arr[j]);
         const double e_max_mag = e_max / (D + 3);  // largest |distance| the fp32 path can produce
         // two distances, 1.5x safety; plus the index tag written over the low mantissa bits of each distance
         st->tau_tight = (float)(2.0 * 1.5 * e_max * 5.9604644775390625e-08);
@@ -55,6 +75,8 @@ __device__ void km_derive(KmState* st) {
         st->tag_bits = tag_bits;
         const double tag_term = 2.0 * e_max_mag * (double)(1 << tag_bits) * 1.1920928955078125e-07;
         st->tau = (float)(2.0 * 1.5 * e_max * 5.9604644775390625e-08 + tag_term);
+        // screening passes: what the 16-bit grid can move the difference of two distances, on top of the fp32 band
+        st->tau_q = __double2float_ru((double)st->tau + 2.0 * 1.01 * q_max);
         // Tensor-core path (rsx_kmeans_part.cu km_tc_kernel): x = xh + xl + xr, w = wh + wl + wr with 11-bit pieces (|xr| < 2^-20 |x|);
         // the three products kept (xh wh + xh wl + xl wh) miss < 3 * 2^-20 |x||w| per feature, the bias is carried in three pieces
         // (< 2^-30).  Accumulation in the tensor core: measured 2^-22.8 of sum|terms| for 16 terms (tools/tc_probe.cu on the B200),
@@ -81,48 +103,38 @@ __device__ void km_derive(KmState* st) {
     for (int d = threadIdx.x; d < D; d += blockDim.x) {
         st->scale32[d] = (float)st->scale64[d];
         st->off32[d] = (float)(st->min64[d] - st->mean64[d]);
-        // 16-bit grid over [fmin, fmax] (a constant feature: step 0, every sample reads back as fmin)
-        const double range = st->fmax64[d] - st->fmin64[d];
-        const bool flat = !(range >= 10.0 * 2.220446049250313e-16);
-        const float step = flat ? 0.f : (float)(range / 65535.0);
-        st->qstep32[d] = step;
-        st->qinv32[d] = flat ? 0.f : (float)(65535.0 / range);
-        st->qmin32[d] = (float)st->fmin64[d];
-        st->qoff32[d] = (float)(st->fmin64[d] - 8388608.0 * (double)step);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        // |x~ - x|: 0.51 steps from the rounding to the grid (the fp32 evaluation of (x - fmin) * qinv32 included), 0.5 steps from the
-        // rounding of qoff32 (its magnitude is 2^23 steps), 2^-24 relative from qstep32 and from the fma: 1.02 steps + 2^-22 (range + |x|)
-        double worst = 0.0;
-        for (int j = 0; j < K; ++j) {
-            double e = 0.0;
-            for (int d = 0; d < D; ++d) {
-                const double range = st->fmax64[d] - st->fmin64[d];
-                const double qerr = 1.02 * (double)st->qstep32[d] + 2.384185791015625e-07 * ((range > 0 ? range : 0.0) + st->absmax[d]);
-                e += fabs((double)st->w32[j * KM_MAXD + d]) * qerr;
-            }
-            worst = fmax(worst, e);
-        }
-        st->tau_q = __double2float_ru((double)st->tau + 2.0 * 1.01 * worst);
     }
 }
 
 // The set-up / update kernels are one CTA of dependent scalar work; run against a shared-memory mirror of the state their
 // per-centroid loops cost shared-memory latency instead of a chain of global-memory round trips.
 constexpr int KM_CTRL_THREADS = 256;
-__device__ __forceinline__ void km_state_copy(void* dst, const void* src) {
+// Only the rows of the per-centroid tables that the K centroids (rounded up to the group of 8 the kernels evaluate) occupy are
+// copied: at K = 8 that is 11 of the 40 KB, and the copies in and out are most of what an update costs.
+__device__ __forceinline__ void km_state_copy(void* dst, const void* src, int K) {
     static_assert(sizeof(KmState) % 16 == 0, "KmState is copied in 16-byte pieces");
+    static_assert(offsetof(KmState, cent64) % 16 == 0 && offsetof(KmState, w32) % 16 == 0 && offsetof(KmState, cent32) % 16 == 0 &&
+                      offsetof(KmState, cnorm64) % 16 == 0 && offsetof(KmState, bias32) % 16 == 0 && offsetof(KmState, tau) % 16 == 0,
+                  "the per-centroid tables start on 16-byte boundaries");
+    const int KP = min(KM_MAXK, (K + 7) & ~7);
+    // [begin, end) of the unused tails, in 16-byte units
+    const int a0 = (int)(offsetof(KmState, cent64) + (size_t)KP * KM_MAXD * 8) / 16, a1 = (int)offsetof(KmState, cnorm64) / 16;
+    const int b0 = (int)(offsetof(KmState, w32) + (size_t)KP * KM_MAXD * 4) / 16, b1 = (int)offsetof(KmState, bias32) / 16;
+    const int c0 = (int)(offsetof(KmState, cent32) + (size_t)KP * KM_MAXD * 4) / 16, c1 = (int)offsetof(KmState, tau) / 16;
     const int4* s4 = reinterpret_cast<const int4*>(src);
     int4* d4 = reinterpret_cast<int4*>(dst);
-    for (int i = threadIdx.x; i < (int)(sizeof(KmState) / 16); i += blockDim.x) d4[i] = s4[i];
+    for (int i = threadIdx.x; i < (int)(sizeof(KmState) / 16); i += blockDim.x) {
+        if ((i >= a0 && i < a1) || (i >= b0 && i < b1) || (i >= c0 && i < c1)) continue;
+        d4[i] = s4[i];
+    }
     __syncthreads();
 }
 
 __global__ void __launch_bounds__(KM_CTRL_THREADS) km_setup_kernel(KmState* gst) {
     __shared__ __align__(16) KmState sst;
     KmState* st = &sst;
-    km_state_copy(st, gst);
+    km_state_copy(st, gst, KM_MAXK);
+    km_derive_grid(st);
     km_derive(st);
     if (threadIdx.x == 0) {
         st->shift_sq = 0.0;
@@ -131,7 +143,7 @@ __global__ void __launch_bounds__(KM_CTRL_THREADS) km_setup_kernel(KmState* gst)
     }
     for (int j = threadIdx.x; j < KM_MAXK; j += blockDim.x) st->drift64[j] = 0.0, st->drift_up[j] = 0.f, st->drift_dn[j] = 0.f;
     __syncthreads();
-    km_state_copy(gst, st);
+    km_state_copy(gst, st, KM_MAXK);
 }
 
 // rsx_kmeans_setup without the host in between: the per-feature range comes straight from the min/max trackers the feature kernels
@@ -178,9 +190,10 @@ __global__ void __launch_bounds__(KM_CTRL_THREADS) km_setup_device_kernel(KmStat
         st->cent64[j * KM_MAXD + d] = __dsub_rn(__dadd_rn(__dmul_rn(rows[i], st->scale64[d]), st->min64[d]), st->mean64[d]);
     }
     __syncthreads();
+    km_derive_grid(st);
     km_derive(st);
     __syncthreads();
-    km_state_copy(gst, st);
+    km_state_copy(gst, st, KM_MAXK);
 }
 
 static const km_assign_fn g_part_assign[KM_NUM_PARTS] = {rsx_km_part0_assign, rsx_km_part1_assign, rsx_km_part2_assign, rsx_km_part3_assign,
@@ -409,7 +422,7 @@ __global__ void __launch_bounds__(KM_CTRL_THREADS) km_update_kernel(KmState* gst
                                                                     const KmPeers peers) {
     __shared__ __align__(16) KmState sst;
     KmState* st = &sst;
-    km_state_copy(st, gst);
+    km_state_copy(st, gst, gst->K);
     const int D = st->D, K = st->K;
     if (PEERS) {
         if (!km_peer_reduce(peers, acc, K * D + K + 2)) {
@@ -430,26 +443,28 @@ __global__ void __launch_bounds__(KM_CTRL_THREADS) km_update_kernel(KmState* gst
     acc = tot;
     __shared__ double shift_part[KM_MAXK];
     __shared__ int empty_part[KM_MAXK];
-    for (int j = threadIdx.x; j < K; j += blockDim.x) {
+    // one warp per centroid, lane = feature: the D sums of a centroid arrive with one round trip to memory instead of D dependent
+    // ones, and the squared shift is added up by a fixed shuffle tree (the same bits on every rank and in every run)
+    for (int j = threadIdx.x >> 5; j < K; j += blockDim.x >> 5) {
+        const int d = threadIdx.x & 31;
         const long long cnt = acc[K * D + j] + (adjust ? adjust[K * D + j] : 0ll);
-        double sh = 0.0;
-        int empty = 0;
-        if (cnt > 0) {
+        double sq = 0.0;
+        if (cnt > 0 && d < D) {
             // _average_centers: centers *= 1/weight  (_k_means_common.pyx:274-296)
-            double alpha = 1.0 / (double)cnt;
-            for (int d = 0; d < D; ++d) {
-                const long long sum_q = acc[j * D + d] + (adjust ? adjust[j * D + d] : 0ll);
-                double mean_raw = ((double)sum_q * st->inv_pow2[d]) * alpha;
-                double c = (mean_raw * st->scale64[d] + st->min64[d]) - st->mean64[d];
-                double old = st->cent64[j * KM_MAXD + d];
-                sh += (c - old) * (c - old);
-                st->cent64[j * KM_MAXD + d] = c;
-            }
-        } else {
-            empty = 1;  // no relocation was supplied: the centre keeps its position and the event is reported
+            const double alpha = 1.0 / (double)cnt;
+            const long long sum_q = acc[j * D + d] + (adjust ? adjust[j * D + d] : 0ll);
+            const double mean_raw = ((double)sum_q * st->inv_pow2[d]) * alpha;
+            const double c = (mean_raw * st->scale64[d] + st->min64[d]) - st->mean64[d];
+            const double old = st->cent64[j * KM_MAXD + d];
+            sq = (c - old) * (c - old);
+            st->cent64[j * KM_MAXD + d] = c;
         }
-        shift_part[j] = sh;
-        empty_part[j] = empty;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        if (d == 0) {
+            shift_part[j] = sq;
+            empty_part[j] = cnt > 0 ? 0 : 1;  // no relocation was supplied: the centre keeps its position and the event is reported
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -476,7 +491,7 @@ __global__ void __launch_bounds__(KM_CTRL_THREADS) km_update_kernel(KmState* gst
     km_derive(st);
     __syncthreads();
     for (int i = threadIdx.x; i < K * D + K + 2; i += blockDim.x) (tot - (K * D + K + 2))[i] = 0;
-    km_state_copy(gst, st);
+    km_state_copy(gst, st, K);
 }
 
 extern "C" int rsx_kmeans_update(void* d_state, int64_t* d_acc, int delta, int D, const int64_t* d_adjust, rsx_stream_t stream) {

@@ -37,7 +37,7 @@ struct __align__(16) KmState {
     // 16-bit screening passes (km_stream_kernel<..., QIN>): features quantised to u = rint((x - fmin) * qinv32), read back as
     // x~ = fma(2^23 + u, qstep32, qoff32) with qoff32 = fl32(fmin - 2^23 qstep32); |x~ - x| <= qerr (derived in km_derive), hence
     // distances within sum_d |w_jd| qerr_d of the fp32 ones: tau_q = tau + twice the largest such sum
-    float qstep32[KM_MAXD], qoff32[KM_MAXD], qinv32[KM_MAXD], qmin32[KM_MAXD];
+    float qstep32[KM_MAXD], qoff32[KM_MAXD], qinv32[KM_MAXD], qmin32[KM_MAXD], qerr32[KM_MAXD];
     float tau_q;
     float bound_err;                             // error bound of the fp32 squared distances |x'|^2 + dist_j (tau_tight + that of |x'|^2)
     float pad_[2];
