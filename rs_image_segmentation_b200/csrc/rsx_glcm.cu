@@ -529,39 +529,67 @@ __device__ __forceinline__ void span_append(bool flagged, unsigned idx, unsigned
         if (at < cap) list[at] = idx;
     }
 }
+// Four windows per thread and step: the levels sit in shared memory as bytes, a word holds four neighbouring columns, and
+// __vminu4 / __vmaxu4 take the running minimum / maximum of four windows at once (the window's column d is the word pair
+// funnel-shifted by d bytes).  0.40 -> 0.1 ms for 49 M windows against one byte per thread and step.
+constexpr int SPAN_RS = (SPAN_TC + SPAN_MAXW - 1 + 3) / 4 + 1;  // words per tile row (+1: the funnel shift reads one word ahead)
 __global__ void __launch_bounds__(256) glcm_span_flag_kernel(const uint8_t* __restrict__ q, int W, int L, int win, int out_rows, int out_cols,
                                                              unsigned* __restrict__ list8, unsigned* __restrict__ list16, unsigned cap,
                                                              unsigned long long* __restrict__ stats) {
-    __shared__ uint8_t raw[SPAN_TR + SPAN_MAXW - 1][SPAN_TC + SPAN_MAXW - 1 + 1];
-    __shared__ uint8_t hmn[SPAN_TR + SPAN_MAXW - 1][SPAN_TC], hmx[SPAN_TR + SPAN_MAXW - 1][SPAN_TC];
+    __shared__ unsigned raw[SPAN_TR + SPAN_MAXW - 1][SPAN_RS];
+    __shared__ unsigned hmn[SPAN_TR + SPAN_MAXW - 1][SPAN_TC / 4], hmx[SPAN_TR + SPAN_MAXW - 1][SPAN_TC / 4];
     const int i0 = blockIdx.y * SPAN_TR, j0 = blockIdx.x * SPAN_TC;
-    const int rows = min(SPAN_TR, out_rows - i0) + win - 1, cols = min(SPAN_TC, out_cols - j0) + win - 1;
-    for (int k = threadIdx.x; k < rows * cols; k += 256) {
-        const int r = k / cols, c = k - r * cols;
-        raw[r][c] = (uint8_t)min((int)q[(int64_t)(i0 + r) * W + j0 + c], L - 1);
-    }
-    __syncthreads();
-    const int ocols = cols - (win - 1), orows = rows - (win - 1);
-    for (int k = threadIdx.x; k < rows * ocols; k += 256) {
-        const int r = k / ocols, c = k - r * ocols;
-        int mn = 255, mx = 0;
-        for (int d = 0; d < win; ++d) mn = min(mn, (int)raw[r][c + d]), mx = max(mx, (int)raw[r][c + d]);
-        hmn[r][c] = (uint8_t)mn, hmx[r][c] = (uint8_t)mx;
-    }
-    __syncthreads();
-    for (int k0 = 0; k0 < orows * ocols; k0 += 256) {  // block-uniform trip count: span_append is a warp collective
-        const int k = k0 + threadIdx.x;
-        int span = 0;
-        unsigned idx = 0;
-        if (k < orows * ocols) {
-            const int r = k / ocols, c = k - r * ocols;
-            int mn = 255, mx = 0;
-            for (int d = 0; d < win; ++d) mn = min(mn, (int)hmn[r + d][c]), mx = max(mx, (int)hmx[r + d][c]);
-            span = mx - mn;
-            idx = (unsigned)((int64_t)(i0 + r) * out_cols + j0 + c);
+    const int orows = min(SPAN_TR, out_rows - i0), ocols = min(SPAN_TC, out_cols - j0);
+    const int rows = orows + win - 1, cols = ocols + win - 1;
+    // the tile: whole words where the image rows are word aligned (W a multiple of 4) and the word lies inside the row
+    const bool words_ok = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(q) & 3) == 0;
+    const unsigned lmax = (unsigned)(L - 1) * 0x01010101u;
+    for (int k = threadIdx.x; k < rows * SPAN_RS; k += 256) {
+        const int r = k / SPAN_RS, cw = k - r * SPAN_RS;
+        const uint8_t* src = q + (int64_t)(i0 + r) * W + j0 + 4 * cw;
+        unsigned w = 0;
+        if (4 * cw + 3 < cols && words_ok) {
+            w = *reinterpret_cast<const unsigned*>(src);
+        } else {
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                if (4 * cw + b < cols) w |= (unsigned)src[b] << (8 * b);
         }
-        span_append(span >= 8, idx, &stats[0], list8, cap);
-        span_append(span >= 16, idx, &stats[1], list16, cap);
+        raw[r][cw] = __vminu4(w, lmax);
+    }
+    __syncthreads();
+    // horizontal pass: min / max over win columns, for the columns 4g .. 4g+3 of every tile row
+    for (int k = threadIdx.x; k < rows * (SPAN_TC / 4); k += 256) {
+        const int r = k / (SPAN_TC / 4), g = k - r * (SPAN_TC / 4);
+        unsigned mn = 0xffffffffu, mx = 0u;
+        for (int d = 0; d < win; ++d) {
+            const unsigned v = __funnelshift_r(raw[r][g + (d >> 2)], raw[r][g + (d >> 2) + 1], 8 * (d & 3));
+            mn = __vminu4(mn, v), mx = __vmaxu4(mx, v);
+        }
+        hmn[r][g] = mn, hmx[r][g] = mx;
+    }
+    __syncthreads();
+    // vertical pass + flags; block-uniform trip count: span_append is a warp collective
+    for (int k0 = 0; k0 < SPAN_TR * (SPAN_TC / 4); k0 += 256) {
+        const int k = k0 + threadIdx.x;
+        const int r = k / (SPAN_TC / 4), g = k - r * (SPAN_TC / 4);
+        unsigned span = 0;
+        if (r < orows) {
+            unsigned mn = 0xffffffffu, mx = 0u;
+            for (int d = 0; d < win; ++d) mn = __vminu4(mn, hmn[r + d][g]), mx = __vmaxu4(mx, hmx[r + d][g]);
+            span = __vsub4(mx, mn);
+        }
+        const unsigned base = (unsigned)((int64_t)(i0 + r) * out_cols + j0 + 4 * g);
+        // columns past the tile's last window never count
+        const int nb = r < orows ? min(4, ocols - 4 * g) : 0;
+        if (nb < 4) span &= nb <= 0 ? 0u : (0xffffffffu >> (8 * (4 - nb)));
+        if (!__any_sync(0xffffffffu, __vcmpgeu4(span, 0x08080808u) != 0u)) continue;  // nothing to list in this warp (the common case)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const unsigned sp = (span >> (8 * b)) & 0xffu;
+            span_append(sp >= 8u, base + b, &stats[0], list8, cap);
+            span_append(sp >= 16u, base + b, &stats[1], list16, cap);
+        }
     }
 }
 
