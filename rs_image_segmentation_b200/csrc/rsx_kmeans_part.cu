@@ -200,11 +200,11 @@ __device__ __forceinline__ int km_decide(const float* __restrict__ stack, int64_
         if (dist_exact < 0.0) {
             // sum of squares of (x' - c): all terms positive, relative error ~D * 2^-24
             float dd = 0.f;
-            // K > 8: the centroid comes from shared memory (lanes hold different labels; a constant-bank read would replay)
-            const float* cent = KU == 0 ? wsm + (D + 1) * ((g_km.K + 7) & ~7) + bi * D : nullptr;
+            // the centroid comes from shared memory (lanes hold different labels: a constant-bank read would replay once per label)
+            const float* cent = KU == 0 ? wsm + (D + 1) * ((g_km.K + 7) & ~7) + bi * D : wsm + bi * D;
 #pragma unroll
             for (int d = 0; d < D; ++d) {
-                float df = fmaf(x[d], g_km.scale32[d], g_km.off32[d]) - (KU == 0 ? cent[d] : g_km.cent32[bi * KM_MAXD + d]);
+                float df = fmaf(x[d], g_km.scale32[d], g_km.off32[d]) - cent[d];
                 dd = fmaf(df, df, dd);
             }
             dist_exact = (double)dd;
@@ -589,6 +589,8 @@ __global__ void __launch_bounds__(KM_THREADS, km_ctas_per_sm(D)) km_stream_kerne
             for (int j = tid; j < KP64; j += KM_THREADS) c64s[D * KP64 + j] = j < K ? g_km.cnorm64[j] : 0.0;
         }
     }
+    if (KU == 8 && INERTIA)  // K <= 8, final pass: the centroids for the inertia term, [K][D]
+        for (int i = tid; i < K * D; i += KM_THREADS) wsm[i] = g_km.cent32[(i / D) * KM_MAXD + i % D];
     const int64_t n4 = n_px & ~(int64_t)3;
     const int64_t n_blocks = (n4 + KM_BLOCK_PX - 1) / KM_BLOCK_PX;
 
@@ -1545,7 +1547,7 @@ static int km_launch_stream(const KmLaunch& a, cudaStream_t s) {
     auto kern = km_stream_kernel<D, MODE, INERTIA, KU, WARPX, QIN>;
     constexpr int STAGE_BYTES = QIN ? D * KM_QSTRIDE * 2 : D * KM_STAGE_STRIDE * 4;
     const int acc_bytes = MODE == KM_ASSIGN ? 0 : KM_WARPS * a.K * (D + 1) * 8;
-    const int w_bytes = KU == 0 ? (((D + 1) * ((a.K + 7) & ~7) + (INERTIA ? a.K * D : 0)) * 4 + 15) / 16 * 16 : 0;
+    const int w_bytes = KU == 0 ? (((D + 1) * ((a.K + 7) & ~7) + (INERTIA ? a.K * D : 0)) * 4 + 15) / 16 * 16 : (INERTIA ? (a.K * D * 4 + 15) / 16 * 16 : 0);
     const int c64_bytes = WARPX ? (D + 1) * ((a.K + 31) & ~31) * 8 : 0;
     auto c64_off = [&](int stages) { return stages * STAGE_BYTES + acc_bytes + 2 * stages * 8 + 16 + w_bytes; };
     auto smem_for = [&](int stages) { return c64_off(stages) + c64_bytes; };
