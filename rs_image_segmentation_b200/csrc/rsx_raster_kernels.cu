@@ -3,9 +3,11 @@
 #include "rsx_raster.cuh"
 
 // ============================================================================ K1: histograms
-// The raster is treated as a sample stream: sample s belongs to band s % B (tiles start on pixel
-// boundaries).  A lane reads one 32-bit word = 4 consecutive samples, so lanes that can collide on
-// one (band, value) bin are B apart - at most ceil(32/B) lanes, not 32 as with a pixel-per-lane map.
+// A thread takes the B consecutive 32-bit words of four pixels, so the band of every byte is a compile-time constant and a
+// sample costs a byte extract and a shared atomic with an immediate offset (3-4 instructions; 14.5 with a run-time band
+// per byte: the kernel was bound by instruction issue, 68 % of the slots busy).  All lanes of a warp then count the same
+// band at once and neighbouring pixels mostly hold similar values, so lane l counts into copy l % NCOPY of the histograms:
+// at most 32 / NCOPY lanes can meet on one address.
 template <int B, int NCOPY>
 __global__ void __launch_bounds__(256) hist_u8_kernel(const uint8_t* __restrict__ raster, int64_t n_px, uint32_t* __restrict__ hist) {
     using RT = RasterTiles<uint8_t, B, 2>;
@@ -13,19 +15,21 @@ __global__ void __launch_bounds__(256) hist_u8_kernel(const uint8_t* __restrict_
     uint32_t* sh = reinterpret_cast<uint32_t*>(smem + RT::SMEM_BYTES);  // [NCOPY][B][256]
     for (int i = threadIdx.x; i < NCOPY * B * 256; i += 256) sh[i] = 0;
     __syncthreads();
-    uint32_t* mine = sh + ((threadIdx.x >> 5) % NCOPY) * (B * 256);
+    uint32_t* mine = sh + (threadIdx.x % NCOPY) * (B * 256);
     for_each_tile<uint8_t, B, 2>(raster, n_px, smem, [&](const uint32_t* words, int64_t, int npx) {
-        const int nwords = (npx * B + 3) >> 2;
-        const int nbytes = npx * B;
-        for (int wi = threadIdx.x; wi < nwords; wi += 256) {
-            uint32_t w = words[wi];
-            int band = (wi * 4) % B;
+        const int nquads = npx >> 2;
+        for (int g = threadIdx.x; g < nquads; g += 256) {
+            const uint32_t* wq = words + g * B;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (wi * 4 + k < nbytes) atomicAdd(&mine[band * 256 + ((w >> (8 * k)) & 0xffu)], 1u);
-                band = band + 1 == B ? 0 : band + 1;
+            for (int k = 0; k < B; ++k) {
+                const uint32_t w = wq[k];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) atomicAdd(&mine[((4 * k + j) % B) * 256 + ((w >> (8 * j)) & 0xffu)], 1u);
             }
         }
+        // the last tile's npx % 4 pixels, byte by byte
+        const uint8_t* bytes = reinterpret_cast<const uint8_t*>(words);
+        for (int s = nquads * 4 * B + threadIdx.x; s < npx * B; s += 256) atomicAdd(&mine[(s % B) * 256 + bytes[s]], 1u);
     });
     __syncthreads();
     for (int i = threadIdx.x; i < B * 256; i += 256) {
@@ -108,7 +112,7 @@ extern "C" int rsx_hist_u8(const uint8_t* d_raster, int64_t n_px, int n_bands, u
 #define LAUNCH(BB)                                                                                         \
     {                                                                                                      \
         using RT = RasterTiles<uint8_t, BB, 2>;                                                            \
-        constexpr int NCOPY = 4;                                                                           \
+        constexpr int NCOPY = BB <= 8 ? 8 : 4;                                                             \
         int smem = RT::SMEM_BYTES + NCOPY * BB * 256 * 4;                                                  \
         if (int rc = set_smem(hist_u8_kernel<BB, NCOPY>, smem)) return rc;                                 \
         int grid = persistent_grid(ceil_div(n_px, (int64_t)RT::TILE_PX), 2);                               \
@@ -700,7 +704,7 @@ static int pca_moments_impl(const T* d_raster, int64_t n_px, int n_bands, const 
         if (int rc = set_smem(pca_moments_kernel<T, BB>, smem)) return rc;                                             \
         int per_sm = 1;                                                                                                \
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pca_moments_kernel<T, BB>, 256, smem);                  \
-        per_sm = max(1, min(per_sm, MM::NSPLIT > 1 ? 4 : 1));                                                          \
+        per_sm = max(1, min(per_sm, MM::NSPLIT > 1 ? 4 : 2));                                                          \
         int grid = (int)min((int64_t)rsx_num_sms() * per_sm, ceil_div(n_px, (int64_t)RT::TILE_PX));                    \
         pca_moments_kernel<T, BB><<<grid, 256, smem, (cudaStream_t)stream>>>(d_raster, n_px, P, d_scratch);            \
         if (int rc = rsx_check_launch("pca_moments")) return rc;                                                       \
