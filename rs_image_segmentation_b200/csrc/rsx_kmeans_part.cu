@@ -102,6 +102,7 @@ __device__ __forceinline__ float km_tag(float a, unsigned keep_mask, int j) { re
 
 constexpr int KM_THREADS = 128;
 constexpr int KM_SLOTS = 8;
+constexpr int KM_CHUNK = 4;  // centroids per inner-loop chunk of the K > 8 path (= one LDS.128 of weights per feature)
 
 // best / second-best tagged distances of the thread's 4 pixels (v[d] = feature d of pixels p..p+3).
 // KU = 8: eight centroid slots, fully unrolled, weights as constant-bank (uniform register) operands of FFMA2 (K <= 8;
@@ -126,33 +127,37 @@ __device__ __forceinline__ void km_distances(const float4* v, int K, const float
             KM_ARGMIN_TAGGED(a23.x, b[2], s[2], j) KM_ARGMIN_TAGGED(a23.y, b[3], s[3], j)
         }
     } else {
-        // K > 8: chunks of 8 centroids, weights from shared memory (wsm = [chunk][D][8] then bias [KP], KP = K rounded up to
-        // 8; padding slots carry bias 1e30); broadcast LDS.128 at immediate offsets from one base, small code whatever K is
+        // K > 8: chunks of KM_CHUNK centroids, weights from shared memory (wsm = [chunk][D][KM_CHUNK] then bias [KP], KP = K rounded
+        // up to 8; padding slots carry bias 1e30); one broadcast LDS.128 per feature and chunk, loaded one feature ahead of the
+        // FFMA2s that consume it (with chunks of 8 the 128-register budget left no room for that and the FFMA2s waited on the
+        // shared-memory scoreboard: 24 % of the stall samples of a K = 32 pass)
         const int KP = (K + 7) & ~7;
         const float* bias = wsm + D * KP;
 #pragma unroll 1
-        for (int jc = 0; jc < KP; jc += 8) {
-            float2 a[8][2];
-            const float* wc = wsm + jc * D;  // this chunk's [D][8] block
+        for (int jc = 0; jc < KP; jc += KM_CHUNK) {
+            float2 a[KM_CHUNK][2];
+            const float4* wc = reinterpret_cast<const float4*>(wsm + jc * D);  // this chunk's [D][4] block
             {
-                const float4 bA = *reinterpret_cast<const float4*>(bias + jc), bB = *reinterpret_cast<const float4*>(bias + jc + 4);
-                const float bb[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
+                const float4 bA = *reinterpret_cast<const float4*>(bias + jc);
+                const float bb[4] = {bA.x, bA.y, bA.z, bA.w};
 #pragma unroll
-                for (int jj = 0; jj < 8; ++jj) a[jj][0] = a[jj][1] = make_float2(bb[jj], bb[jj]);
+                for (int jj = 0; jj < KM_CHUNK; ++jj) a[jj][0] = a[jj][1] = make_float2(bb[jj], bb[jj]);
             }
+            float4 wn = wc[0];
 #pragma unroll
             for (int d = 0; d < D; ++d) {
-                const float4 wA = *reinterpret_cast<const float4*>(wc + d * 8), wB = *reinterpret_cast<const float4*>(wc + d * 8 + 4);
-                const float ww[8] = {wA.x, wA.y, wA.z, wA.w, wB.x, wB.y, wB.z, wB.w};
+                const float4 wA = wn;
+                if (d + 1 < D) wn = wc[d + 1];
+                const float ww[4] = {wA.x, wA.y, wA.z, wA.w};
                 const float2 x01 = make_float2(v[d].x, v[d].y), x23 = make_float2(v[d].z, v[d].w);
 #pragma unroll
-                for (int jj = 0; jj < 8; ++jj) {
+                for (int jj = 0; jj < KM_CHUNK; ++jj) {
                     a[jj][0] = __ffma2_rn(x01, make_float2(ww[jj], ww[jj]), a[jj][0]);
                     a[jj][1] = __ffma2_rn(x23, make_float2(ww[jj], ww[jj]), a[jj][1]);
                 }
             }
 #pragma unroll
-            for (int jj = 0; jj < 8; ++jj) {
+            for (int jj = 0; jj < KM_CHUNK; ++jj) {
                 KM_ARGMIN_TAGGED(a[jj][0].x, b[0], s[0], jc + jj) KM_ARGMIN_TAGGED(a[jj][0].y, b[1], s[1], jc + jj)
                 KM_ARGMIN_TAGGED(a[jj][1].x, b[2], s[2], jc + jj) KM_ARGMIN_TAGGED(a[jj][1].y, b[3], s[3], jc + jj)
             }
@@ -176,7 +181,7 @@ __device__ __noinline__ bool km_recheck_fp32(const float* __restrict__ stack, in
     for (int j = 0; j < K; ++j) {
         float a = wsm[D * KP + j];
 #pragma unroll
-        for (int d = 0; d < D; ++d) a = fmaf(x[d], wsm[(j >> 3) * (D * 8) + d * 8 + (j & 7)], a);
+        for (int d = 0; d < D; ++d) a = fmaf(x[d], wsm[(j / KM_CHUNK) * (D * KM_CHUNK) + d * KM_CHUNK + (j % KM_CHUNK)], a);
         KM_ARGMIN_STEP(a, b, s, bi, j)
     }
     *bi_out = bi;
@@ -573,8 +578,8 @@ __global__ void __launch_bounds__(KM_THREADS, km_ctas_per_sm(D)) km_stream_kerne
     double* c64s = reinterpret_cast<double*>(km_smem + c64_offset);
     if (KU == 0) {
         const int KP = (K + 7) & ~7;
-        for (int i = tid; i < D * KP; i += KM_THREADS) {  // [chunk][D][8]
-            const int c = i / (D * 8), r = i - c * (D * 8), d = r >> 3, j = c * 8 + (r & 7);
+        for (int i = tid; i < D * KP; i += KM_THREADS) {  // [chunk][D][KM_CHUNK]
+            const int c = i / (D * KM_CHUNK), r = i - c * (D * KM_CHUNK), d = r / KM_CHUNK, j = c * KM_CHUNK + (r % KM_CHUNK);
             wsm[i] = g_km.w32[j * KM_MAXD + d];
         }
         for (int j = tid; j < KP; j += KM_THREADS) wsm[D * KP + j] = g_km.bias32[j];
